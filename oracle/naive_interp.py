@@ -1,0 +1,503 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Never imported by the product (`dawn_b200/`).
+
+CPU restatement of what the reference's *naive* backends execute for a given IIR, written as a
+NumPy interpreter over the same IIR JSON the B200 emitter consumes.
+
+Cartesian (`cxxnaive`) semantics followed, file:line in /root/reference:
+  * run(): per MultiStage, per partitioned k-interval (reversed for Backward loop order), per k,
+    per Stage: `for i in [iMin+ext.iMinus, iMax+ext.iPlus]: for j in [...]`: all statements of every
+    DoMethod whose interval overlaps                 dawn/src/dawn/CodeGen/CXXNaive/CXXNaiveCodeGen.cpp:380-495
+  * loop bounds iMin=iminus, iMax=isize-iplus-1 ...   CXXNaiveCodeGen.cpp:381-387
+  * interval bounds: Start -> kMin+level+offset, End -> kMax+offset   CXXNaiveCodeGen.cpp:56-67
+  * interval partition                               dawn/src/dawn/IIR/Interval.cpp:224-330
+  * stage extents (backward propagation of read extents over all stages of a stencil)
+                                                     dawn/src/dawn/IIR/StencilInstantiation.cpp:304-373
+  * expressions are evaluated exactly as the fully parenthesised tree, one IEEE operation per
+    node (no contraction)                            dawn/src/dawn/CodeGen/ASTCodeGenCXX.cpp:109-153
+  * field(i+a, j+b, k+c) view indexing, masked dimensions ignored
+                                                     dawn/src/dawn/CodeGen/CXXNaive/ASTStencilBody.cpp:121-178
+  * temporaries are full 3-D storages                CXXNaiveCodeGen.cpp:318-345
+  * global iteration spaces (i_range/j_range): `checkOffset(lo, hi, globalOffset + idx)`
+                                                     CXXNaiveCodeGen.cpp:455-486, CodeGen.cpp:447-470
+
+Unstructured (`naive-ico`) semantics:
+  * per k, per stage `for loc in getCells/Edges/Vertices(mesh)`; reductions iterate the neighbour
+    list of `chain` in mesh-library order, accumulating from `init`, weights indexed by position
+                                                     dawn/src/dawn/CodeGen/CXXNaive-ico/CXXNaiveCodeGen.cpp:366-617
+                                                     dawn/src/interface/toylib_interface.hpp:280-323
+
+Because a Dawn stage never reads at a horizontal offset something it writes itself (that is what
+stage splitting guarantees, `dawn/src/dawn/Optimizer/PassStageSplitter.cpp`), executing a stage
+statement-by-statement over the whole (i,j) plane is equivalent to the reference's point-by-point
+loop; NumPy float64 elementwise kernels perform one correctly rounded IEEE operation per node.
+
+Parity status: PINNED — checked against the reference's own pre-generated cxxnaive code compiled
+from /root/reference (oracle/_ref) on `conditional_stencil.iir`, `update_dz_c.iir`
+(tests/test_oracle_vs_ref.py) and against committed golden vectors produced by that build
+(tests/golden/).
+"""
+from __future__ import annotations
+
+import json
+import math
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+END = 1 << 20
+_HALF = 1 << 19
+
+
+# ------------------------------------------------------------------------------------------------
+# IIR helpers
+# ------------------------------------------------------------------------------------------------
+def load_iir(path_or_dict):
+    if isinstance(path_or_dict, dict):
+        return path_or_dict
+    with open(path_or_dict) as f:
+        return json.load(f)
+
+
+def _kind(node: dict) -> Tuple[str, dict]:
+    (k, v), = node.items()
+    return k, v
+
+
+def interval_bounds(iv: dict) -> Tuple[int, int]:
+    lo_level = END if iv.get("special_lower_level") == "End" else iv.get("lower_level", 0)
+    hi_level = END if iv.get("special_upper_level") == "End" else iv.get("upper_level", 0)
+    if "special_lower_level" in iv and iv["special_lower_level"] == "Start":
+        lo_level = 0
+    if "special_upper_level" in iv and iv["special_upper_level"] == "Start":
+        hi_level = 0
+    return lo_level + iv.get("lower_offset", 0), hi_level + iv.get("upper_offset", 0)
+
+
+def partition(bounds: List[Tuple[int, int]]) -> List[Tuple[int, int]]:
+    """Disjoint cover of the union of closed integer intervals, split at every bound."""
+    cuts = set()
+    for lo, hi in bounds:
+        cuts.add(lo)
+        cuts.add(hi + 1)
+    cuts = sorted(cuts)
+    out = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        if any(lo <= a and b - 1 <= hi for lo, hi in bounds):
+            out.append((a, b - 1))
+    return out
+
+
+def resolve(bound: int, k_min: int, k_max: int) -> int:
+    if bound >= END - _HALF:
+        return k_max + (bound - END)
+    return k_min + bound
+
+
+class Ext:
+    __slots__ = ("im", "ip", "jm", "jp")
+
+    def __init__(self, im=0, ip=0, jm=0, jp=0):
+        self.im, self.ip, self.jm, self.jp = im, ip, jm, jp
+
+    def merge(self, o):
+        self.im, self.ip = min(self.im, o.im), max(self.ip, o.ip)
+        self.jm, self.jp = min(self.jm, o.jm), max(self.jp, o.jp)
+
+    def add(self, o):
+        return Ext(self.im + o.im, self.ip + o.ip, self.jm + o.jm, self.jp + o.jp)
+
+    def tup(self):
+        return (self.im, self.ip, self.jm, self.jp)
+
+
+def _walk_exprs(node, fn):
+    """Call fn(kind, payload, is_write) on every field_access_expr below an expression node."""
+    k, v = _kind(node)
+    if k == "field_access_expr":
+        fn(v)
+    elif k == "binary_operator":
+        _walk_exprs(v["left"], fn)
+        _walk_exprs(v["right"], fn)
+    elif k == "assignment_expr":
+        _walk_exprs(v["left"], fn)
+        _walk_exprs(v["right"], fn)
+    elif k == "unary_operator":
+        _walk_exprs(v["operand"], fn)
+    elif k == "ternary_operator":
+        _walk_exprs(v["cond"], fn)
+        _walk_exprs(v["left"], fn)
+        _walk_exprs(v["right"], fn)
+    elif k == "fun_call_expr":
+        for a in v.get("arguments", []):
+            _walk_exprs(a, fn)
+    elif k == "reduction_over_neighbor_expr":
+        _walk_exprs(v["rhs"], fn)
+        _walk_exprs(v["init"], fn)
+        for w in v.get("weights", []):
+            _walk_exprs(w, fn)
+
+
+def _stmt_accesses(stmt, reads: Dict[int, Ext], writes: set):
+    k, v = _kind(stmt)
+
+    def rd(fa):
+        off = fa.get("cartesian_offset", {})
+        e = Ext(off.get("i_offset", 0), off.get("i_offset", 0), off.get("j_offset", 0),
+                off.get("j_offset", 0))
+        aid = fa["data"]["accessID"]
+        if aid in reads:
+            reads[aid].merge(e)
+        else:
+            reads[aid] = e
+
+    if k == "expr_stmt":
+        ek, ev = _kind(v["expr"])
+        if ek == "assignment_expr":
+            lk, lv = _kind(ev["left"])
+            if lk == "field_access_expr":
+                writes.add(lv["data"]["accessID"])
+                if ev.get("op", "=") != "=":
+                    rd(lv)
+            _walk_exprs(ev["right"], rd)
+        else:
+            _walk_exprs(v["expr"], rd)
+    elif k == "var_decl_stmt":
+        for e in v.get("init_list", []):
+            _walk_exprs(e, rd)
+    elif k == "if_stmt":
+        _stmt_accesses(v["cond_part"], reads, writes)
+        _stmt_accesses(v["then_part"], reads, writes)
+        if "else_part" in v and v["else_part"]:
+            _stmt_accesses(v["else_part"], reads, writes)
+    elif k == "block_stmt":
+        for s in v.get("statements", []):
+            _stmt_accesses(s, reads, writes)
+
+
+def stage_extents(stencil: dict) -> List[Ext]:
+    """StencilInstantiation.cpp:304-373 restated; returns one Ext per stage in stencil order."""
+    stages = [s for ms in stencil["multiStages"] for s in ms["stages"]]
+    info = []
+    for s in stages:
+        reads: Dict[int, Ext] = {}
+        writes: set = set()
+        for dm in s["doMethods"]:
+            _stmt_accesses(dm["ast"], reads, writes)
+        info.append((reads, writes))
+    exts = [Ext() for _ in stages]
+    for i in range(len(stages) - 1, -1, -1):
+        if "i_range" in stages[i] or "j_range" in stages[i]:
+            exts[i] = Ext()
+            continue
+        reads, writes_i = info[i]
+        # every field of the stage participates (written-only fields contribute zero extents)
+        fields = dict(reads)
+        for w in writes_i:
+            fields.setdefault(w, Ext())
+        for aid, rext in fields.items():
+            fext = rext.add(exts[i])
+            for j in range(i - 1, -1, -1):
+                if aid in info[j][1]:
+                    exts[j].merge(fext)
+    return exts
+
+
+# ------------------------------------------------------------------------------------------------
+# Cartesian interpreter
+# ------------------------------------------------------------------------------------------------
+_MATH = {
+    "sqrt": np.sqrt, "fabs": np.fabs, "abs": np.fabs, "exp": np.exp, "log": np.log,
+    "pow": np.power, "min": np.minimum, "max": np.maximum, "floor": np.floor, "ceil": np.ceil,
+    "trunc": np.trunc, "sin": np.sin, "cos": np.cos, "tan": np.tan, "asin": np.arcsin,
+    "acos": np.arccos, "atan": np.arctan, "fmod": np.fmod, "isnan": np.isnan, "isinf": np.isinf,
+}
+
+_BIN = {
+    "+": np.add, "-": np.subtract, "*": np.multiply, "/": np.divide,
+    "<": np.less, ">": np.greater, "<=": np.less_equal, ">=": np.greater_equal,
+    "==": np.equal, "!=": np.not_equal, "&&": np.logical_and, "||": np.logical_or,
+}
+
+
+class CartesianRun:
+    """Executes one IIR on storages given as dict name -> ndarray.
+
+    Storage convention: arrays are indexed [k, j, i] (i fastest).  Fields with masked dimensions
+    have extent 1 along them (e.g. a `storage_j` is shape (1, nj, 1)).
+    `dom` = (isize, jsize, ksize) *including* halos, `halos` = (iminus, iplus, jminus, jplus,
+    kminus, kplus) as in driver-includes/domain.hpp:42-58.
+    """
+
+    def __init__(self, iir, dom, halos=(3, 3, 3, 3, 0, 0), globals_: Optional[dict] = None,
+                 global_offsets=(0, 0)):
+        self.iir = load_iir(iir)
+        self.meta = self.iir["metadata"]
+        self.ir = self.iir["internalIR"]
+        self.dom = dom
+        self.halos = halos
+        self.names = {int(k): v for k, v in self.meta["accessIDToName"].items()}
+        self.globals = {}
+        for name, gv in self.ir.get("globalVariableToValue", {}).items():
+            self.globals[name] = gv.get("value", 0)
+        if globals_:
+            self.globals.update(globals_)
+        self.global_offsets = global_offsets
+        self.tmp_ids = set(self.meta.get("temporaryFieldIDs", []))
+
+    def run(self, fields: Dict[str, np.ndarray]):
+        ni, nj, nk = self.dom
+        im, ip, jm, jp, km, kp = self.halos
+        self.iMin, self.iMax = im, ni - ip - 1
+        self.jMin, self.jMax = jm, nj - jp - 1
+        self.kMin, self.kMax = km, nk - kp - 1
+        self.f = dict(fields)
+        for st in self.ir["stencils"]:
+            exts = stage_extents(st)
+            # temporaries: full 3-D storages (CXXNaiveCodeGen.cpp:318-345), +1 safety level
+            for aid in self.tmp_ids:
+                nm = self.names[aid]
+                if nm not in self.f:
+                    self.f[nm] = np.zeros((nk + 1, nj + 1, ni + 1))
+            sidx = 0
+            for ms in st["multiStages"]:
+                stages = ms["stages"]
+                s_exts = exts[sidx:sidx + len(stages)]
+                sidx += len(stages)
+                self._run_ms(ms, stages, s_exts)
+        return self.f
+
+    def _run_ms(self, ms, stages, s_exts):
+        backward = ms.get("loopOrder", "Forward") == "Backward"
+        bounds = [interval_bounds(dm["interval"]) for s in stages for dm in s["doMethods"]]
+        parts = partition(bounds)
+        if backward:
+            parts = parts[::-1]
+        for lo, hi in parts:
+            k0, k1 = resolve(lo, self.kMin, self.kMax), resolve(hi, self.kMin, self.kMax)
+            ks = range(k1, k0 - 1, -1) if backward else range(k0, k1 + 1)
+            for k in ks:
+                for stage, ext in zip(stages, s_exts):
+                    dms = [dm for dm in stage["doMethods"]
+                           if _overlap(interval_bounds(dm["interval"]), (lo, hi))]
+                    if not dms:
+                        continue
+                    self._run_stage(stage, dms, ext, k)
+
+    def _run_stage(self, stage, dms, ext: Ext, k):
+        self.k = k
+        self.i0, self.i1 = self.iMin + ext.im, self.iMax + ext.ip
+        self.j0, self.j1 = self.jMin + ext.jm, self.jMax + ext.jp
+        if self.i1 < self.i0 or self.j1 < self.j0:
+            return
+        self.locals: Dict[int, np.ndarray] = {}
+        mask = None
+        if "i_range" in stage or "j_range" in stage:
+            # CXXNaiveCodeGen.cpp:455-486 + generated ctor (`stageNGlobalIIndices({dom.iminus()+lo,
+            # dom.iminus()+hi})`, reference/global_indexing.cpp:72-73): lo <= idx < hi with the
+            # interval's End level mapped to the global size.
+            shape = (self.j1 - self.j0 + 1, self.i1 - self.i0 + 1)
+            mask = np.ones(shape, dtype=bool)
+            ii = np.arange(self.i0, self.i1 + 1)[None, :] + self.global_offsets[0]
+            jj = np.arange(self.j0, self.j1 + 1)[:, None] + self.global_offsets[1]
+            if "i_range" in stage:
+                lo, hi = self._global_range(stage["i_range"], self.dom[0], self.halos[0], self.halos[1])
+                mask &= (ii >= lo) & (ii < hi)
+            if "j_range" in stage:
+                lo, hi = self._global_range(stage["j_range"], self.dom[1], self.halos[2], self.halos[3])
+                mask &= (jj >= lo) & (jj < hi)
+        for dm in dms:
+            self._block(dm["ast"], mask)
+
+    @staticmethod
+    def _global_range(iv, size, minus, plus):
+        def one(special, level, off):
+            if special == "End":
+                return size - plus + off
+            base = 0 if special == "Start" else level
+            return minus + base + off
+        lo = one(iv.get("special_lower_level"), iv.get("lower_level", 0), iv.get("lower_offset", 0))
+        hi = one(iv.get("special_upper_level"), iv.get("upper_level", 0), iv.get("upper_offset", 0))
+        return lo, hi
+
+    # -- statements -------------------------------------------------------------------------------
+    def _block(self, node, mask):
+        k, v = _kind(node)
+        if k != "block_stmt":
+            return self._stmt(node, mask)
+        for s in v.get("statements", []):
+            self._stmt(s, mask)
+
+    def _stmt(self, node, mask):
+        k, v = _kind(node)
+        if k == "block_stmt":
+            self._block(node, mask)
+        elif k == "expr_stmt":
+            ek, ev = _kind(v["expr"])
+            if ek == "assignment_expr":
+                self._assign(ev, mask)
+            else:
+                self._eval(v["expr"])
+        elif k == "var_decl_stmt":
+            aid = v["var_decl_stmt_data"]["accessID"]
+            init = v.get("init_list", [])
+            val = self._eval(init[0]) if init else 0.0
+            tid = v.get("type", {}).get("builtin_type", {}).get("type_id", "Float")
+            val = self._cast(val, tid)
+            shape = (self.j1 - self.j0 + 1, self.i1 - self.i0 + 1)
+            self.locals[aid] = np.broadcast_to(np.asarray(val), shape).copy()
+        elif k == "if_stmt":
+            ck, cv = _kind(v["cond_part"])
+            cond = self._eval(cv["expr"]) if ck == "expr_stmt" else self._eval(v["cond_part"])
+            cond = np.asarray(cond).astype(bool)
+            m_then = cond if mask is None else (mask & cond)
+            self._block(v["then_part"], m_then)
+            if "else_part" in v and v["else_part"]:
+                m_else = ~cond if mask is None else (mask & ~cond)
+                self._block(v["else_part"], m_else)
+        else:
+            raise NotImplementedError(k)
+
+    @staticmethod
+    def _cast(val, tid):
+        if tid == "Integer":
+            return np.trunc(val)
+        if tid == "Boolean":
+            return np.asarray(val).astype(bool)
+        return val
+
+    def _assign(self, ev, mask):
+        op = ev.get("op", "=")
+        rhs = self._eval(ev["right"])
+        lk, lv = _kind(ev["left"])
+        if lk == "var_access_expr":
+            aid = lv["data"]["accessID"]
+            if lv.get("is_external", False):
+                raise NotImplementedError("assignment to global")
+            cur = self.locals[aid]
+            new = rhs if op == "=" else _BIN[op[0]](cur, rhs)
+            self.locals[aid] = np.where(mask, new, cur) if mask is not None else \
+                np.broadcast_to(np.asarray(new, dtype=float), cur.shape).copy()
+            return
+        assert lk == "field_access_expr"
+        view = self._field_view(lv, write=True)
+        new = rhs if op == "=" else _BIN[op[0]](view, rhs)
+        if mask is not None:
+            m = np.broadcast_to(mask, (self.j1 - self.j0 + 1, self.i1 - self.i0 + 1))
+            if view.shape != m.shape:  # masked-dimension storage
+                m = m[:view.shape[0], :view.shape[1]]
+            view[...] = np.where(m, new, view)
+        else:
+            view[...] = new
+
+    # -- expressions ------------------------------------------------------------------------------
+    def _field_view(self, fa, write=False):
+        name = fa["name"]
+        arr = self.f[name]
+        off = fa.get("cartesian_offset", {})
+        di, dj = off.get("i_offset", 0), off.get("j_offset", 0)
+        dk = fa.get("vertical_shift", 0)
+        nk_a, nj_a, ni_a = arr.shape
+        kk = self.k + dk if nk_a > 1 else 0
+        js = slice(self.j0 + dj, self.j1 + dj + 1) if nj_a > 1 else slice(0, 1)
+        is_ = slice(self.i0 + di, self.i1 + di + 1) if ni_a > 1 else slice(0, 1)
+        return arr[kk, js, is_]
+
+    def _eval(self, node):
+        k, v = _kind(node)
+        if k == "field_access_expr":
+            return self._field_view(v)
+        if k == "literal_access_expr":
+            t = v.get("type", {}).get("type_id", "Float")
+            s = v["value"]
+            if t == "Boolean":
+                return s in ("true", "1")
+            if t == "Integer":
+                return int(s)
+            return float(s)
+        if k == "var_access_expr":
+            if v.get("is_external", False):
+                return self.globals[v["name"]]
+            return self.locals[v["data"]["accessID"]]
+        if k == "binary_operator":
+            a, b = self._eval(v["left"]), self._eval(v["right"])
+            op = v["op"]
+            if op == "/" and isinstance(a, int) and isinstance(b, int):
+                return int(a / b)  # C integer division truncates
+            with np.errstate(all="ignore"):
+                return _BIN[op](a, b)
+        if k == "unary_operator":
+            a = self._eval(v["operand"])
+            op = v["op"]
+            if op == "-":
+                return np.negative(a) if not isinstance(a, (int, float)) else -a
+            if op == "+":
+                return a
+            if op == "!":
+                return np.logical_not(a)
+            raise NotImplementedError(op)
+        if k == "ternary_operator":
+            c = self._eval(v["cond"])
+            a, b = self._eval(v["left"]), self._eval(v["right"])
+            if isinstance(c, (bool, np.bool_)):
+                return a if c else b
+            return np.where(c, a, b)
+        if k == "fun_call_expr":
+            callee = v["callee"].split("::")[-1]
+            args = [self._eval(a) for a in v.get("arguments", [])]
+            with np.errstate(all="ignore"):
+                return _MATH[callee](*args)
+        raise NotImplementedError(k)
+
+
+def _overlap(a, b):
+    return a[0] <= b[1] and b[0] <= a[1]
+
+
+def run_cartesian(iir, dom, fields, halos=(3, 3, 3, 3, 0, 0), globals_=None, global_offsets=(0, 0)):
+    return CartesianRun(iir, dom, halos, globals_, global_offsets).run(fields)
+
+
+def field_extents(iir) -> Dict[str, Tuple[int, int, int, int, int, int]]:
+    """Accumulated read extents per API field (`static constexpr cartesian_extent <f>_extent`,
+    dawn/src/dawn/CodeGen/CodeGen.cpp:509-522): field read extent + extent of the reading stage."""
+    iir = load_iir(iir)
+    names = {int(k): v for k, v in iir["metadata"]["accessIDToName"].items()}
+    out: Dict[str, List[int]] = {}
+    for st in iir["internalIR"]["stencils"]:
+        exts = stage_extents(st)
+        stages = [s for ms in st["multiStages"] for s in ms["stages"]]
+        for s, ext in zip(stages, exts):
+            reads: Dict[int, Ext] = {}
+            writes: set = set()
+            kext: Dict[int, List[int]] = {}
+            for dm in s["doMethods"]:
+                _stmt_accesses(dm["ast"], reads, writes)
+                _collect_k(dm["ast"], kext)
+            for aid in set(reads) | writes:
+                r = reads.get(aid, Ext()).add(ext) if aid in reads else Ext()
+                kk = kext.get(aid, [0, 0])
+                cur = out.setdefault(names[aid], [0, 0, 0, 0, 0, 0])
+                new = [r.im, r.ip, r.jm, r.jp, kk[0], kk[1]]
+                for n in (0, 2, 4):
+                    cur[n] = min(cur[n], new[n])
+                for n in (1, 3, 5):
+                    cur[n] = max(cur[n], new[n])
+    return {k: tuple(v) for k, v in out.items()}
+
+
+def _collect_k(node, kext):
+    def visit(n):
+        if isinstance(n, dict):
+            if "field_access_expr" in n:
+                fa = n["field_access_expr"]
+                aid = fa["data"]["accessID"]
+                dk = fa.get("vertical_shift", 0)
+                cur = kext.setdefault(aid, [0, 0])
+                cur[0], cur[1] = min(cur[0], dk), max(cur[1], dk)
+            for key, val in n.items():
+                if key not in ("data", "loc"):
+                    visit(val)
+        elif isinstance(n, list):
+            for x in n:
+                visit(x)
+    visit(node)

@@ -1,0 +1,180 @@
+"""Writes the optimized-IIR fixtures under stencils/ (the emitter's input for tests and bench).
+
+Dawn's optimizer cannot be built in this image, and the reference ships no optimized `.iir` for its
+headline stencils (only `dawn/test/unit-test/dawn/CodeGen/input/{conditional_stencil,update_dz_c}.iir`),
+so the IIRs are authored here with tools/iir_builder.py in the shape the reference's pass pipeline
+produces for a CUDA-class backend (stencil functions inlined, stages merged per multistage, K-caches
+set by PassSetCaches):
+
+  hori_diff_type2_stencil   gtclang/test/integration-test/CodeGen/hori_diff_type2_stencil.cpp:5-55
+  hori_diff_stencil_01      gtclang/test/integration-test/CodeGen/hori_diff_stencil_01.cpp:21-31
+  hori_diff_stencil         dawn/test/integration-test/dawn4py-tests/hori_diff_stencil.py
+                            (expression trees pinned by data/hori_diff_stencil_ref.cpp:105-119)
+  tridiagonal_solve         gtclang/test/integration-test/CodeGen/tridiagonal_solve.cpp:21-38
+                            (caches as in data/tridiagonal_solve_stencil_ref.cpp: c,d K-cached)
+  laplacian_stencil         dawn/examples/tutorial/laplacian_stencil.cpp:1-13
+  copy_stencil              gtclang/test/integration-test/CodeGen/copy_stencil.cpp
+  global_indexing           dawn/test/unit-test/dawn/CodeGen/Stencils.cpp (getGlobalIndexStencil)
+  nonoverlapping_stencil    dawn/test/unit-test/dawn/CodeGen/Stencils.cpp (getNonOverlappingInterval)
+
+Run:  python tools/make_stencils.py   (idempotent; output is committed)
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(__file__))
+from iir_builder import FULL, IIRBuilder, Interval, k_cache, where  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "stencils")
+
+
+def hori_diff_type2():
+    b = IIRBuilder("hori_diff_type2_stencil")
+    out, inn = b.field("out"), b.field("in")
+    crlato, crlatu = b.field("crlato", "j"), b.field("crlatu", "j")
+    hdmask = b.field("hdmask")
+    lap = b.tmp("lap")
+
+    def delta(data, di, dj, ci=0, cj=0):  # data(off) - data, evaluated at centre shift (ci,cj)
+        return data(ci + di, cj + dj) - data(ci, cj)
+
+    lap_expr = (inn(1, 0) + inn(-1, 0) - 2.0 * inn() + crlato() * delta(inn, 0, 1)
+                + crlatu() * delta(inn, 0, -1))
+    s1 = b.stage(b.do(FULL, b.assign(lap, lap_expr)))
+
+    stmts = []
+
+    def flux_x(ci):
+        decl, flx = b.local("flx", delta(lap, 1, 0, ci, 0), "Double", True)
+        stmts.append(decl)
+        return where((flx * delta(inn, 1, 0, ci, 0)) > 0.0, 0.0, flx)
+
+    def flux_y(cj):
+        decl, fly = b.local("fly", crlato(0, cj) * delta(lap, 0, 1, 0, cj), "Double", True)
+        stmts.append(decl)
+        return where((fly * delta(inn, 0, 1, 0, cj)) > 0.0, 0.0, fly)
+
+    fx = flux_x(0) - flux_x(-1)
+    d1, dfx = b.local("delta_flux_x", fx, "Double", True)
+    stmts.append(d1)
+    fy = flux_y(0) - flux_y(-1)
+    d2, dfy = b.local("delta_flux_y", fy, "Double", True)
+    stmts.append(d2)
+    stmts.append(b.assign(out, inn() - hdmask() * (dfx + dfy)))
+    s2 = b.stage(b.do(FULL, *stmts))
+    b.stencil(b.multistage("Parallel", s1, s2,
+                           caches={lap.access_id: k_cache("CP_Local", ctype="CT_IJ")}))
+    return b
+
+
+def hori_diff_01():
+    b = IIRBuilder("hori_diff_stencil_01")
+    u, out = b.field("u"), b.field("out")
+    lap = b.tmp("lap")
+    s1 = b.stage(b.do(FULL, b.assign(lap, u(1, 0) + u(-1, 0) + u(0, 1) + u(0, -1) - 4.0 * u())))
+    s2 = b.stage(b.do(FULL, b.assign(
+        out, lap(1, 0) + lap(-1, 0) + lap(0, 1) + lap(0, -1) - 4.0 * lap())))
+    b.stencil(b.multistage("Parallel", s1, s2,
+                           caches={lap.access_id: k_cache("CP_Local", ctype="CT_IJ")}))
+    return b
+
+
+def hori_diff_dawn4py():
+    b = IIRBuilder("hori_diff_stencil")
+    inn, out, coeff = b.field("in"), b.field("out"), b.field("coeff")
+    lap = b.tmp("lap")
+
+    def five(f):
+        return (-4.0 * f()) + (coeff() * (f(1, 0) + (f(-1, 0) + (f(0, 1) + f(0, -1)))))
+
+    s1 = b.stage(b.do(FULL, b.assign(lap, five(inn))))
+    s2 = b.stage(b.do(FULL, b.assign(out, five(lap))))
+    b.stencil(b.multistage("Parallel", s1, s2,
+                           caches={lap.access_id: k_cache("CP_Local", ctype="CT_IJ")}))
+    return b
+
+
+def tridiagonal_solve():
+    b = IIRBuilder("tridiagonal_solve")
+    d, a, bb, c = b.field("d"), b.field("a"), b.field("b"), b.field("c")
+    first = Interval("Start", "Start", 0, 0)
+    rest = Interval("Start", "End", 1, 0)
+    back = Interval("Start", "End", 0, -1)
+    mdecl, m = b.local("m", 1.0 / (bb() - a() * c(0, 0, -1)), "Double")
+    fwd = b.stage(
+        b.do(first, b.assign(c, c() / bb()), b.assign(d, d() / bb())),
+        b.do(rest, mdecl, b.assign(c, c() * m), b.assign(d, (d() - a() * d(0, 0, -1)) * m)),
+    )
+    bwd = b.stage(b.do(back, b.assign(d, c() * d(0, 0, 1), op="-=")))
+    b.stencil(
+        b.multistage("Forward", fwd, caches={
+            c.access_id: k_cache("CP_FillFlush", (-1, 0)),
+            d.access_id: k_cache("CP_FillFlush", (-1, 0))}),
+        b.multistage("Backward", bwd, caches={d.access_id: k_cache("CP_FillFlush", (0, 1))}),
+    )
+    return b
+
+
+def tutorial_laplacian():
+    b = IIRBuilder("laplacian_stencil")
+    dx = b.global_var("dx", "Double", 1.0)
+    out, inn = b.field("out_field", "ij"), b.field("in_field", "ij")
+    e = (-4 * inn() + inn(1, 0) + inn(-1, 0) + inn(0, -1) + inn(0, 1)) / (dx * dx)
+    b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, b.assign(out, e)))))
+    return b
+
+
+def copy_stencil():
+    b = IIRBuilder("copy_stencil")
+    inn, out = b.field("in"), b.field("out")
+    b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, b.assign(out, inn())))))
+    return b
+
+
+def global_indexing():
+    # reference/global_indexing.cpp:84-106: out=in everywhere; then out=10 where the global j
+    # index lies in [jminus+0, jminus+2)
+    b = IIRBuilder("global_indexing")
+    inn, out = b.field("in_field"), b.field("out_field")
+    s1 = b.stage(b.do(FULL, b.assign(out, inn())))
+    s2 = b.stage(b.do(FULL, b.assign(out, 10)), j_range=Interval("Start", "Start", 0, 2))
+    b.stencil(b.multistage("Parallel", s1, s2))
+    return b
+
+
+def nonoverlapping():
+    # reference/nonoverlapping_stencil.cpp:75-98: [0,10] laplacian / (dx*dx) with a LOCAL dx that the
+    # reference leaves uninitialised (not a numeric oracle there); [15,end] out = 10.
+    b = IIRBuilder("nonoverlapping_stencil")
+    inn, out = b.field("in"), b.field("out")
+    ddecl, dx = b.local("dx", 2.0, "Double")
+    e = (-4 * (inn() + (inn(1, 0) + (inn(-1, 0) + (inn(0, -1) + inn(0, 1)))))) / (dx * dx)
+    s1 = b.stage(b.do(Interval("Start", 10, 0, 0), ddecl, b.assign(out, e)),
+                 b.do(Interval(15, "End", 0, 0), b.assign(out, 10)))
+    b.stencil(b.multistage("Parallel", s1))
+    return b
+
+
+ALL = {
+    "hori_diff_type2_stencil": hori_diff_type2,
+    "hori_diff_stencil_01": hori_diff_01,
+    "hori_diff_stencil": hori_diff_dawn4py,
+    "tridiagonal_solve": tridiagonal_solve,
+    "laplacian_stencil": tutorial_laplacian,
+    "copy_stencil": copy_stencil,
+    "global_indexing": global_indexing,
+    "nonoverlapping_stencil": nonoverlapping,
+}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for name, fn in ALL.items():
+        path = os.path.join(OUT, name + ".iir")
+        with open(path, "w") as f:
+            f.write(fn().dumps())
+        print("wrote", path)
+
+
+if __name__ == "__main__":
+    main()
