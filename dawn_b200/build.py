@@ -1,0 +1,137 @@
+"""In-tree builds: emitter (g++), C-ABI runtime (nvcc, sm_100a) and generated stencil modules.
+
+Everything lands under dawn_b200/lib/ (git-ignored, shipped to the GPU box by gpurun).  nvcc
+cross-compiles for sm_100a without a GPU.  Generated translation units are compiled with
+-fmad=false so that every arithmetic node stays one IEEE operation (bit parity with cxxnaive).
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+LIB = os.path.join(PKG, "lib")
+GEN = os.path.join(LIB, "generated")
+CSRC = os.path.join(PKG, "csrc")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_COMMON = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+                      "-cudart", "shared"]
+
+EMITTER_SRCS = ["codegen.cpp", "iir.cpp", "emit_cartesian.cpp", "emit_ico.cpp", "capi.cpp"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return r.stdout
+
+
+def build_emitter(force=False):
+    os.makedirs(LIB, exist_ok=True)
+    edir = os.path.join(CSRC, "emitter")
+    srcs = [os.path.join(edir, s) for s in EMITTER_SRCS]
+    deps = srcs + [os.path.join(edir, h) for h in os.listdir(edir) if h.endswith(".hpp")] + \
+        [os.path.join(ROOT, "include", "dawn_b200_codegen.h")]
+    so = os.path.join(LIB, "libdawn_b200_codegen.so")
+    exe = os.path.join(LIB, "dawn-b200-codegen")
+    if force or _newer(so, deps):
+        _run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-o", so] + srcs)
+    if force or _newer(exe, deps + [os.path.join(edir, "main.cpp")]):
+        _run(["g++", "-std=c++17", "-O2", "-Wall", "-o", exe, os.path.join(edir, "main.cpp")] +
+             srcs[:-1])
+    return so
+
+
+def build_runtime(force=False):
+    os.makedirs(LIB, exist_ok=True)
+    src = os.path.join(CSRC, "runtime", "rt.cu")
+    so = os.path.join(LIB, "libdawn_b200rt.so")
+    if force or _newer(so, [src, os.path.join(ROOT, "include", "dawn_b200_rt.h")]):
+        _run([NVCC] + NVCC_COMMON + ["-o", so, src, "-ldl"])
+    return so
+
+
+def module_path(name, tag=""):
+    return os.path.join(LIB, "stencils", name + (("_" + tag) if tag else "") + ".so")
+
+
+def compile_module(name, code, tag="", force=False, extra_flags=(), keep_ptxas=False):
+    """Compiles one generated translation unit into dawn_b200/lib/stencils/<name>[_tag].so."""
+    build_runtime()
+    os.makedirs(GEN, exist_ok=True)
+    os.makedirs(os.path.join(LIB, "stencils"), exist_ok=True)
+    cu = os.path.join(GEN, name + (("_" + tag) if tag else "") + ".cu")
+    so = module_path(name, tag)
+    digest = hashlib.sha256(code.encode()).hexdigest()
+    stamp = so + ".sha"
+    hdrs = [os.path.join(PKG, "driver-includes", h)
+            for h in os.listdir(os.path.join(PKG, "driver-includes"))]
+    if (not force and os.path.exists(so) and os.path.exists(stamp)
+            and open(stamp).read() == digest and not _newer(so, hdrs)):
+        return so
+    with open(cu, "w") as f:
+        f.write(code)
+    cmd = [NVCC] + NVCC_COMMON + ["-fmad=false", "-Xptxas", "-v", "-I", PKG, "-o", so, cu,
+                                  "-L", LIB, "-ldawn_b200rt", "-Xlinker", "-rpath,$ORIGIN/.."] + \
+        list(extra_flags)
+    out = _run(cmd)
+    with open(so + ".ptxas.txt", "w") as f:
+        f.write(out)
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return so
+
+
+# planner variants exercised by tests/ and bench sweeps; prebuilt here so they travel to the GPU box
+VARIANTS = {
+    "hori_diff_type2_stencil": [
+        dict(rows_per_thread=1), dict(rows_per_thread=4),
+        dict(block_size_i=32, block_size_j=8, rows_per_thread=2), dict(inline_temporaries=0),
+    ],
+    "tridiagonal_solve": [dict(fuse_columns=0)],
+}
+
+
+def variant_tag(options):
+    return "_".join("%s%s" % (k[:2] + k.split("_")[-1][:1], v) for k, v in sorted(options.items()))
+
+
+def build_all(force=False):
+    """Everything bench/tests need: emitter, runtime, and a module per stencils/*.iir fixture."""
+    from . import codegen
+    build_emitter(force)
+    build_runtime(force)
+    built = []
+    sdir = os.path.join(ROOT, "stencils")
+    for fn in sorted(os.listdir(sdir)):
+        if not fn.endswith(".iir"):
+            continue
+        name = fn[:-4]
+        with open(os.path.join(sdir, fn)) as f:
+            iir = f.read()
+        backend = "b200-ico" if '"gridType": "Unstructured"' in iir else "b200"
+        try:
+            code = codegen.compile_iir(iir, backend=backend)
+        except codegen.CodeGenError as e:
+            if "not yet supported" in str(e):
+                continue
+            raise
+        built.append(compile_module(name, code, force=force))
+        for opts in VARIANTS.get(name, []):
+            vcode = codegen.compile_iir(iir, backend=backend, **opts)
+            built.append(compile_module(name, vcode, tag=variant_tag(opts), force=force))
+    return built
+
+
+def clean():
+    shutil.rmtree(LIB, ignore_errors=True)

@@ -1,0 +1,98 @@
+// C ABI of the emitter (include/dawn_b200_codegen.h).
+#include "../../../include/dawn_b200_codegen.h"
+#include "codegen.hpp"
+
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+namespace {
+thread_local std::string g_error;
+
+b200::codegen::Options convert(const dawn_b200_options* o) {
+  b200::codegen::Options r;
+  if(!o)
+    return r;
+  r.MaxHaloSize = o->max_halo_points;
+  r.UseParallelEP = o->use_parallel_ep != 0;
+  r.MaxBlocksPerSM = o->max_blocks_per_sm;
+  r.nsms = o->nsms;
+  r.DomainSizeI = o->domain_size_i, r.DomainSizeJ = o->domain_size_j, r.DomainSizeK = o->domain_size_k;
+  r.RunWithSync = o->run_with_sync != 0;
+  r.BlockSizeI = o->block_size_i, r.BlockSizeJ = o->block_size_j;
+  r.RowsPerThread = o->rows_per_thread, r.BlockSizeK = o->block_size_k;
+  r.InlineTemporaries = o->inline_temporaries, r.FuseColumns = o->fuse_columns;
+  r.UnrollK = o->unroll_k;
+  r.LevelsPerThread = o->levels_per_thread, r.BlockSizeIco = o->block_size_ico;
+  return r;
+}
+} // namespace
+
+namespace b200 {
+namespace codegen {
+int icoChainSize(const std::vector<iir::LocationType>& chain, bool includeCenter);
+}
+} // namespace b200
+
+extern "C" {
+
+void dawn_b200_default_options(dawn_b200_options* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->max_halo_points = 3;
+  o->run_with_sync = 1;
+  o->inline_temporaries = 1;
+  o->fuse_columns = 1;
+}
+
+int dawn_b200_parse_backend(const char* s) {
+  try {
+    return static_cast<int>(b200::codegen::parseBackendString(s ? s : ""));
+  } catch(std::exception& e) {
+    g_error = e.what();
+    return -1;
+  }
+}
+
+int dawn_b200_codegen_run(const char* const* names, const char* const* iir_json,
+                          const size_t* iir_len, int n, int backend, const dawn_b200_options* opts,
+                          char** out_code, size_t* out_len) {
+  try {
+    if(!names || !iir_json || !out_code || n <= 0)
+      throw std::invalid_argument("dawn_b200_codegen_run: bad arguments");
+    std::map<std::string, std::string> ctx;
+    for(int i = 0; i < n; ++i)
+      ctx[names[i]] = iir_len ? std::string(iir_json[i], iir_len[i]) : std::string(iir_json[i]);
+    auto tu = b200::codegen::run(ctx, static_cast<b200::codegen::Backend>(backend), convert(opts));
+    std::string code = tu.str();
+    char* buf = static_cast<char*>(std::malloc(code.size() + 1));
+    if(!buf)
+      throw std::bad_alloc();
+    std::memcpy(buf, code.c_str(), code.size() + 1);
+    *out_code = buf;
+    if(out_len)
+      *out_len = code.size();
+    return 0;
+  } catch(std::exception& e) {
+    g_error = e.what();
+    return 1;
+  }
+}
+
+void dawn_b200_free(void* p) { std::free(p); }
+const char* dawn_b200_codegen_last_error(void) { return g_error.c_str(); }
+
+int dawn_b200_ico_chain_size(const int* chain, int chain_len, int include_center) {
+  try {
+    std::vector<b200::iir::LocationType> ch;
+    for(int i = 0; i < chain_len; ++i) {
+      if(chain[i] < 0 || chain[i] > 2)
+        return -1;
+      ch.push_back(static_cast<b200::iir::LocationType>(chain[i]));
+    }
+    return b200::codegen::icoChainSize(ch, include_center != 0);
+  } catch(std::exception& e) {
+    g_error = e.what();
+    return -1;
+  }
+}
+}

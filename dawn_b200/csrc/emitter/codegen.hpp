@@ -1,0 +1,62 @@
+// Public C++ interface of the B200 emitter.  Mirrors the reference's backend entry points
+//   std::unique_ptr<TranslationUnit> cuda::run(context, Options)   (CodeGen/Cuda/CudaCodeGen.h:34-37)
+//   std::string codegen::run(map<name, serializedIIR>, Format, Backend, Options) (CodeGen/Driver.h:38-40)
+// with serialized IIR (JSON) as the input so it can live behind a C ABI (include/dawn_b200_codegen.h).
+#pragma once
+#include "iir.hpp"
+
+#include <map>
+#include <string>
+#include <vector>
+
+namespace b200 {
+namespace codegen {
+
+// Backend enum twin of dawn::codegen::Backend (CodeGen/Options.h:22) extended by the two new values.
+enum class Backend { GridTools, CXXNaive, CXXNaiveIco, CUDAIco, CUDA, CXXOpt, B200, B200Ico };
+
+// Accepts the strings of dawn::codegen::parseBackendString (CodeGen/Driver.cpp:47-64) plus
+// "b200"/"B200" and "b200-ico"/"B200Ico"; unknown -> std::invalid_argument("Backend not supported").
+Backend parseBackendString(const std::string& backendStr);
+
+// Options twin of dawn::codegen::Options (CodeGen/Options.inc:36-52) + Blackwell planning knobs that
+// replace PassSetBlockSize / PassSetCaches decisions (Optimizer/PassSetBlockSize.cpp:24-71).
+struct Options {
+  int MaxHaloSize = 3;
+  bool UseParallelEP = false;
+  int MaxBlocksPerSM = 0;
+  int nsms = 0;
+  int DomainSizeI = 0, DomainSizeJ = 0, DomainSizeK = 0;
+  bool RunWithSync = true;
+  // --- b200 planner knobs (0 = let the planner decide) ---
+  int BlockSizeI = 0;     // tile width in i (threads along i)
+  int BlockSizeJ = 0;     // thread rows per block
+  int RowsPerThread = 0;  // consecutive j rows computed by one thread (register micro-tile)
+  int BlockSizeK = 0;     // k levels per block for Parallel multistages
+  int InlineTemporaries = 1; // 1: recompute cheap temporaries in registers, 0: stage through memory
+  int FuseColumns = 1;    // 1: fuse consecutive horizontally-pointwise multistages into one kernel
+  int UnrollK = 0;        // k-loop unroll factor (0 = planner default)
+  int LevelsPerThread = 0; // unstructured: levels per thread
+  int BlockSizeIco = 0;    // unstructured: threads per block
+};
+
+// TranslationUnit twin (CodeGen/TranslationUnit.h:26-53)
+struct TranslationUnit {
+  std::string filename;
+  std::vector<std::string> ppDefines;
+  std::map<std::string, std::string> stencils; // stencil name -> generated code
+  std::string globals;
+  // Concatenation ppDefines + globals + stencils, like codegen::generate (CodeGen/Driver.cpp:105-159)
+  std::string str() const;
+};
+
+// context: name -> serialized StencilInstantiation (JSON).
+TranslationUnit run(const std::map<std::string, std::string>& context, Backend backend,
+                    const Options& options);
+
+// Per-backend entry points (twins of cuda::run / cudaico::run).
+TranslationUnit runCartesian(const std::map<std::string, iir::Instantiation>& ctx, const Options&);
+TranslationUnit runIco(const std::map<std::string, iir::Instantiation>& ctx, const Options&);
+
+} // namespace codegen
+} // namespace b200

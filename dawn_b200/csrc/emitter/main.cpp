@@ -1,0 +1,78 @@
+// dawn-b200-codegen: command-line twin of `dawn-codegen` (dawn/src/dawn/dawn-codegen.cpp:71-143)
+// for the two backends this project provides.  Reads optimized IIR (proto3 JSON, as written by
+// `dawn-opt`) from a file or stdin, writes the CUDA translation unit to -o or stdout.
+//   dawn-opt x.sir | dawn-b200-codegen --backend=b200 -o x_b200.cu
+#include "codegen.hpp"
+
+#include <fstream>
+#include <iostream>
+#include <iterator>
+#include <sstream>
+
+int main(int argc, char** argv) {
+  using namespace b200::codegen;
+  std::string backend = "b200", input, output;
+  Options opts;
+  auto intOpt = [&](const std::string& a, const char* name, int& dst) {
+    std::string p = std::string("--") + name + "=";
+    if(a.compare(0, p.size(), p) == 0) {
+      dst = std::stoi(a.substr(p.size()));
+      return true;
+    }
+    return false;
+  };
+  for(int n = 1; n < argc; ++n) {
+    std::string a = argv[n];
+    if(a == "-h" || a == "--help") {
+      std::cout << "Usage: dawn-b200-codegen [-b|--backend b200|b200-ico] [-o out.cu] [in.iir]\n"
+                   "  planner knobs: --block-size-i= --block-size-j= --rows-per-thread= "
+                   "--block-size-k= --inline-temporaries= --fuse-columns= --unroll-k= "
+                   "--levels-per-thread= --block-size-ico= --max-halo-points= --run-with-sync=\n";
+      return 0;
+    } else if((a == "-b" || a == "--backend") && n + 1 < argc)
+      backend = argv[++n];
+    else if(a.compare(0, 10, "--backend=") == 0)
+      backend = a.substr(10);
+    else if(a == "-o" && n + 1 < argc)
+      output = argv[++n];
+    else if(intOpt(a, "block-size-i", opts.BlockSizeI) || intOpt(a, "block-size-j", opts.BlockSizeJ) ||
+            intOpt(a, "rows-per-thread", opts.RowsPerThread) ||
+            intOpt(a, "block-size-k", opts.BlockSizeK) ||
+            intOpt(a, "inline-temporaries", opts.InlineTemporaries) ||
+            intOpt(a, "fuse-columns", opts.FuseColumns) || intOpt(a, "unroll-k", opts.UnrollK) ||
+            intOpt(a, "levels-per-thread", opts.LevelsPerThread) ||
+            intOpt(a, "block-size-ico", opts.BlockSizeIco) ||
+            intOpt(a, "max-halo-points", opts.MaxHaloSize)) {
+    } else if(a.compare(0, 16, "--run-with-sync=") == 0)
+      opts.RunWithSync = a.substr(16) != "0" && a.substr(16) != "false";
+    else if(!a.empty() && a[0] != '-')
+      input = a;
+    else {
+      std::cerr << "dawn-b200-codegen: unknown option " << a << "\n";
+      return 2;
+    }
+  }
+  try {
+    std::string text;
+    if(input.empty())
+      text.assign(std::istreambuf_iterator<char>(std::cin), std::istreambuf_iterator<char>());
+    else {
+      std::ifstream f(input);
+      if(!f)
+        throw std::runtime_error("cannot open " + input);
+      text.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+    }
+    auto tu = run({{"restoredIIR", text}}, parseBackendString(backend), opts);
+    std::string code = tu.str();
+    if(output.empty())
+      std::cout << code;
+    else {
+      std::ofstream o(output);
+      o << code;
+    }
+  } catch(std::exception& e) {
+    std::cerr << "dawn-b200-codegen: error: " << e.what() << "\n";
+    return 1;
+  }
+  return 0;
+}

@@ -1,0 +1,500 @@
+// libdawn_b200rt.so — implementation of include/dawn_b200_rt.h (sm_100a).
+#include "../../../include/dawn_b200_rt.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+thread_local std::string g_err;
+
+int cudaFail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return B200_ERR_CUDA;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if(e_ != cudaSuccess)                                                                          \
+      return cudaFail(e_, #call);                                                                  \
+  } while(0)
+
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+} // namespace
+
+extern "C" {
+
+const char* b200rt_last_error(void) { return g_err.c_str(); }
+int b200rt_set_error(int code, const char* msg) {
+  g_err = msg ? msg : "";
+  return code;
+}
+
+int b200rt_device_count(int* n) {
+  CK(cudaGetDeviceCount(n));
+  return 0;
+}
+int b200rt_set_device(int device) {
+  CK(cudaSetDevice(device));
+  return 0;
+}
+int b200rt_device_synchronize(void) {
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+int b200rt_malloc(void** p, size_t bytes) {
+  CK(cudaMalloc(p, bytes ? bytes : 1));
+  return 0;
+}
+int b200rt_free(void* p) {
+  if(p)
+    CK(cudaFree(p));
+  return 0;
+}
+int b200rt_malloc_host(void** p, size_t bytes) {
+  CK(cudaMallocHost(p, bytes ? bytes : 1));
+  return 0;
+}
+int b200rt_free_host(void* p) {
+  if(p)
+    CK(cudaFreeHost(p));
+  return 0;
+}
+int b200rt_memset(void* p, int v, size_t bytes, void* s) {
+  CK(cudaMemsetAsync(p, v, bytes, S(s)));
+  return 0;
+}
+int b200rt_memcpy_h2d(void* d, const void* h, size_t bytes, void* s) {
+  CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, S(s)));
+  return 0;
+}
+int b200rt_memcpy_d2h(void* h, const void* d, size_t bytes, void* s) {
+  CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, S(s)));
+  return 0;
+}
+int b200rt_memcpy_d2d(void* d, const void* s0, size_t bytes, void* s) {
+  CK(cudaMemcpyAsync(d, s0, bytes, cudaMemcpyDeviceToDevice, S(s)));
+  return 0;
+}
+int b200rt_memcpy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width,
+                    size_t height, void* s) {
+  CK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDefault, S(s)));
+  return 0;
+}
+int b200rt_stream_create(void** s) {
+  cudaStream_t st;
+  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  *s = st;
+  return 0;
+}
+int b200rt_stream_destroy(void* s) {
+  CK(cudaStreamDestroy(S(s)));
+  return 0;
+}
+int b200rt_stream_synchronize(void* s) {
+  CK(cudaStreamSynchronize(S(s)));
+  return 0;
+}
+int b200rt_event_create(void** e) {
+  cudaEvent_t ev;
+  CK(cudaEventCreate(&ev));
+  *e = ev;
+  return 0;
+}
+int b200rt_event_destroy(void* e) {
+  CK(cudaEventDestroy(static_cast<cudaEvent_t>(e)));
+  return 0;
+}
+int b200rt_event_record(void* e, void* s) {
+  CK(cudaEventRecord(static_cast<cudaEvent_t>(e), S(s)));
+  return 0;
+}
+int b200rt_event_synchronize(void* e) {
+  CK(cudaEventSynchronize(static_cast<cudaEvent_t>(e)));
+  return 0;
+}
+int b200rt_event_elapsed_ms(void* a, void* b, float* ms) {
+  CK(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(a), static_cast<cudaEvent_t>(b)));
+  return 0;
+}
+int b200rt_check_last_launch(void) {
+  CK(cudaGetLastError());
+  return 0;
+}
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Fused verification: one pass, block-level reduction, one atomic per block and metric.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct VerifyAcc {
+  double max_rel, min_rel, max_abs, min_abs;
+  unsigned long long n_failed;
+};
+
+__device__ inline double atomicMaxD(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if(__longlong_as_double(assumed) >= v)
+      break;
+    old = atomicCAS(a, assumed, __double_as_longlong(v));
+  } while(assumed != old);
+  return __longlong_as_double(old);
+}
+__device__ inline double atomicMinD(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if(__longlong_as_double(assumed) <= v)
+      break;
+    old = atomicCAS(a, assumed, __double_as_longlong(v));
+  } while(assumed != old);
+  return __longlong_as_double(old);
+}
+
+__global__ void __launch_bounds__(256)
+verify_kernel(const double* __restrict__ dsl, const double* __restrict__ ref, size_t n,
+              double rel_tol, double abs_tol, VerifyAcc* acc) {
+  double mxr = 0, mnr = 1e300, mxa = 0, mna = 1e300;
+  unsigned long long bad = 0;
+  for(size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n;
+      idx += (size_t)gridDim.x * blockDim.x) {
+    const double a = __ldg(&dsl[idx]), b = __ldg(&ref[idx]);
+    const double ae = fabs(a - b);
+    // relative error as cuda_verify.hpp:47-56 (RelErrTag): |a-b| / |b|
+    const double re = fabs(b) > 0 ? ae / fabs(b) : (ae > 0 ? 1e300 : 0.0);
+    const bool bothNan = isnan(a) && isnan(b);
+    const bool close = bothNan || (ae <= abs_tol + rel_tol * fabs(b));
+    if(!bothNan) {
+      mxr = fmax(mxr, re), mnr = fmin(mnr, re);
+      mxa = fmax(mxa, ae), mna = fmin(mna, ae);
+    }
+    bad += close ? 0ull : 1ull;
+  }
+  for(int o = 16; o > 0; o >>= 1) {
+    mxr = fmax(mxr, __shfl_xor_sync(0xffffffffu, mxr, o));
+    mnr = fmin(mnr, __shfl_xor_sync(0xffffffffu, mnr, o));
+    mxa = fmax(mxa, __shfl_xor_sync(0xffffffffu, mxa, o));
+    mna = fmin(mna, __shfl_xor_sync(0xffffffffu, mna, o));
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  __shared__ double s[4][8];
+  __shared__ unsigned long long sb[8];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if(l == 0)
+    s[0][w] = mxr, s[1][w] = mnr, s[2][w] = mxa, s[3][w] = mna, sb[w] = bad;
+  __syncthreads();
+  if(threadIdx.x == 0) {
+    for(int q = 1; q < 8; ++q) {
+      mxr = fmax(mxr, s[0][q]), mnr = fmin(mnr, s[1][q]);
+      mxa = fmax(mxa, s[2][q]), mna = fmin(mna, s[3][q]);
+      bad += sb[q];
+    }
+    atomicMaxD(&acc->max_rel, mxr);
+    atomicMinD(&acc->min_rel, mnr);
+    atomicMaxD(&acc->max_abs, mxa);
+    atomicMinD(&acc->min_abs, mna);
+    if(bad)
+      atomicAdd(&acc->n_failed, bad);
+  }
+}
+
+// [elem][sparse][k] (k fastest)  ->  [k][sparse][elem] (elem fastest); 32x32 smem transpose per
+// sparse slot so that both the read and the write are coalesced.
+__global__ void __launch_bounds__(256)
+reshape_kernel(const double* __restrict__ in, double* __restrict__ out, int k_size, int n_elem,
+               int sparse, bool back) {
+  __shared__ double tile[32][33];
+  const int s = blockIdx.z;
+  const int e0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 x 8
+  if(!back) {
+    for(int r = ty; r < 32; r += 8) {
+      int e = e0 + r, k = k0 + tx;
+      if(e < n_elem && k < k_size)
+        tile[r][tx] = in[((size_t)e * sparse + s) * k_size + k];
+    }
+    __syncthreads();
+    for(int r = ty; r < 32; r += 8) {
+      int k = k0 + r, e = e0 + tx;
+      if(e < n_elem && k < k_size)
+        out[((size_t)k * sparse + s) * n_elem + e] = tile[tx][r];
+    }
+  } else {
+    for(int r = ty; r < 32; r += 8) {
+      int k = k0 + r, e = e0 + tx;
+      if(e < n_elem && k < k_size)
+        tile[r][tx] = in[((size_t)k * sparse + s) * n_elem + e];
+    }
+    __syncthreads();
+    for(int r = ty; r < 32; r += 8) {
+      int e = e0 + r, k = k0 + tx;
+      if(e < n_elem && k < k_size)
+        out[((size_t)e * sparse + s) * k_size + k] = tile[tx][r];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+nbh_transpose_kernel(const int* __restrict__ rm, int* __restrict__ soa, int n_elem, int nbh) {
+  size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if(idx >= (size_t)n_elem * nbh)
+    return;
+  int e = (int)(idx % n_elem), n = (int)(idx / n_elem);
+  soa[idx] = __ldg(&rm[(size_t)e * nbh + n]);
+}
+
+// pack / unpack of j-rows for the slab halo exchange: buf[k][row][i]
+__global__ void __launch_bounds__(256)
+halo_pack_kernel(const double* __restrict__ field, double* __restrict__ buf, int ni, int nk, int sj,
+                 int sk, int j_first, int rows, bool unpack, double* __restrict__ field_w) {
+  const size_t total = (size_t)ni * rows * nk;
+  for(size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+      idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % ni);
+    const int r = (int)((idx / ni) % rows);
+    const int k = (int)(idx / ((size_t)ni * rows));
+    const size_t f = (size_t)i + (size_t)(j_first + r) * sj + (size_t)k * sk;
+    if(unpack)
+      field_w[f] = buf[idx];
+    else
+      buf[idx] = __ldg(&field[f]);
+  }
+}
+} // namespace
+
+extern "C" {
+
+int b200rt_verify_field(const double* dsl, const double* ref, size_t n, double rel_tol,
+                        double abs_tol, int iteration, b200_verification_metrics* out, void* stream) {
+  if(!out)
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_verify_field: out is null");
+  VerifyAcc init{0.0, 1e300, 0.0, 1e300, 0ull};
+  VerifyAcc* d = nullptr;
+  CK(cudaMalloc(&d, sizeof(VerifyAcc)));
+  CK(cudaMemcpyAsync(d, &init, sizeof(init), cudaMemcpyHostToDevice, S(stream)));
+  if(n) {
+    int blocks = (int)((n + 255) / 256);
+    if(blocks > 148 * 8)
+      blocks = 148 * 8;
+    verify_kernel<<<blocks, 256, 0, S(stream)>>>(dsl, ref, n, rel_tol, abs_tol, d);
+  }
+  VerifyAcc h;
+  cudaError_t e = cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, S(stream));
+  if(e == cudaSuccess)
+    e = cudaStreamSynchronize(S(stream));
+  cudaFree(d);
+  if(e != cudaSuccess)
+    return cudaFail(e, "b200rt_verify_field");
+  out->iteration = iteration;
+  out->max_rel_err = h.max_rel, out->max_abs_err = h.max_abs;
+  out->min_rel_err = n ? h.min_rel : 0, out->min_abs_err = n ? h.min_abs : 0;
+  out->n_failed = (long long)h.n_failed;
+  out->is_valid = h.n_failed == 0;
+  return 0;
+}
+
+static int reshape_impl(const double* in, double* out, int k_size, int n_elem, int sparse,
+                        bool back, void* stream) {
+  if(k_size <= 0 || n_elem <= 0 || sparse <= 0)
+    return 0;
+  dim3 grid((n_elem + 31) / 32, (k_size + 31) / 32, sparse);
+  reshape_kernel<<<grid, 256, 0, S(stream)>>>(in, out, k_size, n_elem, sparse, back);
+  CK(cudaGetLastError());
+  return 0;
+}
+int b200rt_reshape(const double* in, double* out, int k, int n, int sp, void* s) {
+  return reshape_impl(in, out, k, n, sp, false, s);
+}
+int b200rt_reshape_back(const double* in, double* out, int k, int n, int sp, void* s) {
+  return reshape_impl(in, out, k, n, sp, true, s);
+}
+
+int b200rt_upload_nbh_table(const int* row_major, int n_elem, int nbh, int* d_soa, void* stream) {
+  size_t cnt = (size_t)n_elem * nbh;
+  if(!cnt)
+    return 0;
+  int* tmp = nullptr;
+  CK(cudaMalloc(&tmp, cnt * sizeof(int)));
+  cudaError_t e = cudaMemcpyAsync(tmp, row_major, cnt * sizeof(int), cudaMemcpyHostToDevice, S(stream));
+  if(e == cudaSuccess) {
+    nbh_transpose_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, S(stream)>>>(tmp, d_soa, n_elem, nbh);
+    e = cudaGetLastError();
+  }
+  if(e == cudaSuccess)
+    e = cudaStreamSynchronize(S(stream));
+  cudaFree(tmp);
+  if(e != cudaSuccess)
+    return cudaFail(e, "b200rt_upload_nbh_table");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL (resolved at run time so that the library loads on boxes without libnccl)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Id128 {
+  char internal[128];
+};
+struct Nccl {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ Id128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+Nccl g_nccl;
+
+int loadNccl() {
+  if(g_nccl.lib)
+    return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for(const char* n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if(g_nccl.lib)
+      break;
+  }
+  if(!g_nccl.lib)
+    return b200rt_set_error(B200_ERR_NCCL, "libnccl.so.2 not found");
+#define SYM(field, name)                                                                           \
+  *reinterpret_cast<void**>(&g_nccl.field) = dlsym(g_nccl.lib, name);                              \
+  if(!g_nccl.field)                                                                                \
+    return b200rt_set_error(B200_ERR_NCCL, "missing NCCL symbol " name);
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  return 0;
+}
+int ncclFail(int r, const char* what) {
+  g_err = std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return B200_ERR_NCCL;
+}
+#define NK(call)                                                                                   \
+  do {                                                                                             \
+    int r_ = (call);                                                                               \
+    if(r_ != 0)                                                                                    \
+      return ncclFail(r_, #call);                                                                  \
+  } while(0)
+constexpr int kNcclFloat64 = 8; // ncclDouble
+} // namespace
+
+int b200rt_nccl_unique_id(void* id128) {
+  if(int e = loadNccl())
+    return e;
+  NK(g_nccl.GetUniqueId(id128));
+  return 0;
+}
+int b200rt_comm_init_rank(void** comm, int nranks, const void* id128, int rank) {
+  if(int e = loadNccl())
+    return e;
+  Id128 id;
+  std::memcpy(&id, id128, sizeof(id));
+  NK(g_nccl.CommInitRank(comm, nranks, id, rank));
+  return 0;
+}
+int b200rt_comm_destroy(void* comm) {
+  if(int e = loadNccl())
+    return e;
+  NK(g_nccl.CommDestroy(comm));
+  return 0;
+}
+} // extern "C"
+
+struct b200_halo_plan {
+  void* comm;
+  int rank, nranks, ni, nj, nk, sj, sk, halo, wminus, wplus;
+  double *send_lo = nullptr, *send_hi = nullptr, *recv_lo = nullptr, *recv_hi = nullptr;
+};
+
+extern "C" {
+int b200rt_halo_plan_create(b200_halo_plan** plan, void* comm, int rank, int nranks, int ni, int nj,
+                            int nk, int stride_j, int stride_k, int halo_j, int width_minus,
+                            int width_plus) {
+  if(!plan || width_minus > halo_j || width_plus > halo_j || width_minus < 0 || width_plus < 0)
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_halo_plan_create: bad widths");
+  auto* p = new b200_halo_plan{comm, rank,     nranks,   ni,     nj,         nk,
+                               stride_j, stride_k, halo_j, width_minus, width_plus};
+  // my low halo (width_minus rows) is filled from rank-1's top interior rows; my high halo
+  // (width_plus rows) from rank+1's bottom interior rows.
+  size_t lo = (size_t)ni * nk * (size_t)std::max(width_minus, width_plus) * sizeof(double);
+  if(lo == 0)
+    lo = sizeof(double);
+  CK(cudaMalloc(&p->send_lo, lo));
+  CK(cudaMalloc(&p->send_hi, lo));
+  CK(cudaMalloc(&p->recv_lo, lo));
+  CK(cudaMalloc(&p->recv_hi, lo));
+  *plan = p;
+  return 0;
+}
+
+int b200rt_halo_exchange(b200_halo_plan* p, double* field, void* stream) {
+  if(!p)
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_halo_exchange: null plan");
+  if(p->nranks > 1)
+    if(int e = loadNccl())
+      return e;
+  const bool has_lo = p->rank > 0, has_hi = p->rank + 1 < p->nranks;
+  auto launch = [&](const double* f, double* buf, int j_first, int rows, bool unpack, double* fw) {
+    size_t total = (size_t)p->ni * rows * p->nk;
+    if(!total)
+      return;
+    int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+    halo_pack_kernel<<<blocks, 256, 0, S(stream)>>>(f, buf, p->ni, p->nk, p->sj, p->sk, j_first,
+                                                    rows, unpack, fw);
+  };
+  // rows I send down (to rank-1): my first `wplus` interior rows fill its high halo;
+  // rows I send up (to rank+1): my last `wminus` interior rows fill its low halo.
+  const int j_int0 = p->halo, j_int1 = p->nj - p->halo; // interior rows [j_int0, j_int1)
+  if(has_lo && p->wplus)
+    launch(field, p->send_lo, j_int0, p->wplus, false, nullptr);
+  if(has_hi && p->wminus)
+    launch(field, p->send_hi, j_int1 - p->wminus, p->wminus, false, nullptr);
+  if(has_lo || has_hi) {
+    NK(g_nccl.GroupStart());
+    size_t n_lo_send = (size_t)p->ni * p->nk * p->wplus, n_hi_send = (size_t)p->ni * p->nk * p->wminus;
+    size_t n_lo_recv = (size_t)p->ni * p->nk * p->wminus, n_hi_recv = (size_t)p->ni * p->nk * p->wplus;
+    if(has_lo && n_lo_send)
+      NK(g_nccl.Send(p->send_lo, n_lo_send, kNcclFloat64, p->rank - 1, p->comm, S(stream)));
+    if(has_lo && n_lo_recv)
+      NK(g_nccl.Recv(p->recv_lo, n_lo_recv, kNcclFloat64, p->rank - 1, p->comm, S(stream)));
+    if(has_hi && n_hi_send)
+      NK(g_nccl.Send(p->send_hi, n_hi_send, kNcclFloat64, p->rank + 1, p->comm, S(stream)));
+    if(has_hi && n_hi_recv)
+      NK(g_nccl.Recv(p->recv_hi, n_hi_recv, kNcclFloat64, p->rank + 1, p->comm, S(stream)));
+    NK(g_nccl.GroupEnd());
+  }
+  if(has_lo && p->wminus)
+    launch(nullptr, p->recv_lo, j_int0 - p->wminus, p->wminus, true, field);
+  if(has_hi && p->wplus)
+    launch(nullptr, p->recv_hi, j_int1, p->wplus, true, field);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200rt_halo_plan_destroy(b200_halo_plan* p) {
+  if(!p)
+    return 0;
+  cudaFree(p->send_lo), cudaFree(p->send_hi), cudaFree(p->recv_lo), cudaFree(p->recv_hi);
+  delete p;
+  return 0;
+}
+}

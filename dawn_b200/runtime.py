@@ -1,0 +1,89 @@
+"""ctypes binding of the C-ABI runtime libdawn_b200rt.so (include/dawn_b200_rt.h)."""
+import ctypes
+import os
+
+from . import build as _build
+
+
+class RuntimeError_(RuntimeError):
+    pass
+
+
+class Field(ctypes.Structure):
+    """b200_field_t"""
+    _fields_ = [("data", ctypes.c_void_p), ("stride_j", ctypes.c_int), ("stride_k", ctypes.c_int)]
+
+
+class VerificationMetrics(ctypes.Structure):
+    """b200_verification_metrics (twin of driver-includes/verification_metrics.hpp:3-10)"""
+    _fields_ = [("iteration", ctypes.c_int), ("is_valid", ctypes.c_int),
+                ("max_rel_err", ctypes.c_double), ("min_rel_err", ctypes.c_double),
+                ("max_abs_err", ctypes.c_double), ("min_abs_err", ctypes.c_double),
+                ("n_failed", ctypes.c_longlong)]
+
+
+_lib = None
+
+# every symbol include/dawn_b200_rt.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "b200rt_last_error", "b200rt_set_error", "b200rt_device_count", "b200rt_set_device",
+    "b200rt_device_synchronize", "b200rt_malloc", "b200rt_free", "b200rt_malloc_host",
+    "b200rt_free_host", "b200rt_memset", "b200rt_memcpy_h2d", "b200rt_memcpy_d2h",
+    "b200rt_memcpy_d2d", "b200rt_memcpy2d", "b200rt_stream_create", "b200rt_stream_destroy",
+    "b200rt_stream_synchronize", "b200rt_event_create", "b200rt_event_destroy",
+    "b200rt_event_record", "b200rt_event_synchronize", "b200rt_event_elapsed_ms",
+    "b200rt_check_last_launch", "b200rt_verify_field", "b200rt_reshape", "b200rt_reshape_back",
+    "b200rt_upload_nbh_table", "b200rt_nccl_unique_id", "b200rt_comm_init_rank",
+    "b200rt_comm_destroy", "b200rt_halo_plan_create", "b200rt_halo_exchange",
+    "b200rt_halo_plan_destroy",
+]
+
+
+def lib():
+    """Loads (building in-tree if needed) the runtime.  There is no fallback: without the CUDA
+    runtime library the product cannot run and this raises."""
+    global _lib
+    if _lib is None:
+        so = os.path.join(_build.LIB, "libdawn_b200rt.so")
+        if not os.path.exists(so):
+            so = _build.build_runtime()
+        _lib = ctypes.CDLL(so, mode=ctypes.RTLD_GLOBAL)
+        _lib.b200rt_last_error.restype = ctypes.c_char_p
+        for name in ("b200rt_malloc", "b200rt_malloc_host"):
+            getattr(_lib, name).argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]
+        for name in ("b200rt_free", "b200rt_free_host"):
+            getattr(_lib, name).argtypes = [ctypes.c_void_p]
+        for name in ("b200rt_memcpy_h2d", "b200rt_memcpy_d2h", "b200rt_memcpy_d2d"):
+            getattr(_lib, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                            ctypes.c_void_p]
+        _lib.b200rt_verify_field.argtypes = [
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_double, ctypes.c_double,
+            ctypes.c_int, ctypes.POINTER(VerificationMetrics), ctypes.c_void_p]
+        for name in ("b200rt_reshape", "b200rt_reshape_back"):
+            getattr(_lib, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        _lib.b200rt_upload_nbh_table.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_void_p, ctypes.c_void_p]
+        _lib.b200rt_comm_init_rank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                                               ctypes.c_void_p, ctypes.c_int]
+        _lib.b200rt_comm_destroy.argtypes = [ctypes.c_void_p]
+        _lib.b200rt_nccl_unique_id.argtypes = [ctypes.c_void_p]
+        _lib.b200rt_halo_plan_create.argtypes = [
+            ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p] + [ctypes.c_int] * 10
+        _lib.b200rt_halo_exchange.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _lib.b200rt_halo_plan_destroy.argtypes = [ctypes.c_void_p]
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError_("dawn_b200 runtime error %d: %s" %
+                            (rc, lib().b200rt_last_error().decode(errors="replace")))
+
+
+def verify_field(dsl_ptr, ref_ptr, n, rel_tol=1e-12, abs_tol=0.0, iteration=0, stream=None):
+    """GPU-side single-pass verification (replaces cuda_verify.hpp:84-196)."""
+    m = VerificationMetrics()
+    check(lib().b200rt_verify_field(dsl_ptr, ref_ptr, n, rel_tol, abs_tol, iteration,
+                                    ctypes.byref(m), stream))
+    return m

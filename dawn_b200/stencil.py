@@ -1,0 +1,245 @@
+"""Host-side mirror of the reference's generated-stencil interface for Python drivers.
+
+The reference's user code is C++ (`domain`, storages, `dawn_generated::<ns>::<S> s(dom); s.run(...)`,
+gtclang/test/integration-test/CodeGen/hori_diff_type2_stencil_benchmark.cpp:44-73).  The same objects
+exist here, over the C ABI every generated module exports (include/dawn_b200_stencil.h):
+`Domain`, `Storage` (HBM-resident, reference layout rules of driver-includes/storage.hpp in this
+repo), and `Stencil(domain).run(...)`.  torch provides device memory and streams only.
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+
+from . import build as _build
+from . import codegen as _codegen
+from . import runtime as _rt
+
+HALO = 3  # GRIDTOOLS_DAWN_HALO_EXTENT
+
+
+class Domain:
+    """gridtools::dawn::domain (sizes include halos; driver-includes/domain.hpp)."""
+
+    def __init__(self, isize, jsize, ksize):
+        self.dims = (int(isize), int(jsize), int(ksize))
+        self.halos = [HALO, HALO, HALO, HALO, 0, 0]
+
+    def set_halos(self, iminus=0, iplus=0, jminus=0, jplus=0, kminus=0, kplus=0):
+        self.halos = [iminus, iplus, jminus, jplus, kminus, kplus]
+
+    isize = property(lambda s: s.dims[0])
+    jsize = property(lambda s: s.dims[1])
+    ksize = property(lambda s: s.dims[2])
+
+    def interior(self):
+        h = self.halos
+        return (self.dims[0] - h[0] - h[1], self.dims[1] - h[2] - h[3], self.dims[2] - h[4] - h[5])
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class Storage:
+    """Device-resident storage with the layout of driver-includes/storage.hpp: i fastest, rows padded
+    to 16 doubles, first interior point of each row 128-byte aligned.  `dims` in {"ijk","ij","i","j",
+    "k"}.  Backed by a torch CUDA tensor (float64)."""
+
+    def __init__(self, ni, nj, nk, dims="ijk", device="cuda", halo=HALO):
+        import torch
+        self.dims = dims
+        mi, mj, mk = "i" in dims, "j" in dims, "k" in dims
+        self.shape = (ni if mi else 1, nj if mj else 1, nk if mk else 1)
+        s = 1
+        self.lead = 0
+        self.stride_i = self.stride_j = self.stride_k = 0
+        if mi:
+            self.stride_i = 1
+            self.lead = (16 - halo % 16) % 16
+            s = _round_up(self.shape[0], 16)
+        if mj:
+            self.stride_j = s
+            s *= self.shape[1]
+        if mk:
+            self.stride_k = s
+            s *= self.shape[2]
+        self.elems = s + self.lead + 16
+        self.buf = torch.zeros(self.elems, dtype=torch.float64, device=device)
+
+    # -- views --------------------------------------------------------------------------------
+    def _strided(self, t):
+        import torch
+        ni, nj, nk = self.shape
+        return torch.as_strided(t, (nk, nj, ni), (max(self.stride_k, 0), max(self.stride_j, 0),
+                                                  max(self.stride_i, 0)), self.lead)
+
+    def view(self):
+        """torch view indexed [k, j, i] over the logical (unpadded) extent."""
+        return self._strided(self.buf)
+
+    def from_numpy(self, arr):
+        """arr indexed [k, j, i] (length 1 along masked dimensions)."""
+        import torch
+        arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(self.shape[2], self.shape[1],
+                                                                  self.shape[0])
+        self.view().copy_(torch.from_numpy(arr))
+        return self
+
+    def to_numpy(self):
+        return self.view().cpu().numpy().copy()
+
+    def fill(self, v):
+        self.buf.fill_(v)
+        return self
+
+    def descriptor(self):
+        return _rt.Field(self.buf.data_ptr() + 8 * self.lead, self.stride_j, self.stride_k)
+
+
+def dense_descriptor(ptr, ni, nj, dims="ijk"):
+    """Descriptor of a dense [k][j][i] device buffer (no padding)."""
+    mi, mj = "i" in dims, "j" in dims
+    sj = ni if mi else 1
+    sk = (ni if mi else 1) * (nj if mj else 1)
+    return _rt.Field(ptr, sj if mj else 0, sk if "k" in dims else 0)
+
+
+class StencilModule:
+    """A compiled generated translation unit (one .so per stencil instantiation)."""
+
+    def __init__(self, name, so_path):
+        if not os.path.exists(so_path):
+            raise FileNotFoundError(
+                "generated stencil module %s not built (run __graft_entry__.build()); there is no "
+                "CPU fallback" % so_path)
+        _rt.lib()  # the module links against the runtime
+        self.name = name
+        self.path = so_path
+        self.lib = ctypes.CDLL(so_path)
+        info = getattr(self.lib, "b200_module_info_" + name)
+        info.restype = ctypes.c_char_p
+        self.info = json.loads(info().decode())
+        self.fields = self.info["fields"]
+        self._setup = getattr(self.lib, "setup_" + name)
+        self._setup.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int,
+                                ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
+        self._run = getattr(self.lib, "run_" + name)
+        self._run.argtypes = [ctypes.c_void_p, ctypes.POINTER(_rt.Field), ctypes.c_int,
+                              ctypes.c_void_p]
+        self._free = getattr(self.lib, "free_" + name)
+        self._free.argtypes = [ctypes.c_void_p]
+        self._launches = getattr(self.lib, "launches_" + name)
+        self._launches.argtypes = [ctypes.c_void_p]
+        self._launches.restype = ctypes.c_long
+
+    def __call__(self, domain, stream=None):
+        return Stencil(self, domain, stream)
+
+
+class Stencil:
+    """Instance of a generated stencil bound to a domain: constructor from domain, fields bound at
+    run(), like `dawn_generated::cuda::<S>` (CudaCodeGen.cpp:144-174,412-452)."""
+
+    def __init__(self, module, domain, stream=None):
+        self.module = module
+        self.domain = domain
+        self.handle = ctypes.c_void_p()
+        halos = (ctypes.c_int * 6)(*domain.halos)
+        _rt.check(module._setup(ctypes.byref(self.handle), domain.isize, domain.jsize, domain.ksize,
+                                halos, stream))
+        self._host_storages = None
+
+    def set_global(self, name, value):
+        fn = getattr(self.module.lib, "set_%s_%s" % (self.module.name, name))
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_double]
+        fn(self.handle, float(value))
+
+    def get_global(self, name):
+        fn = getattr(self.module.lib, "get_%s_%s" % (self.module.name, name))
+        fn.argtypes = [ctypes.c_void_p]
+        fn.restype = ctypes.c_double
+        return fn(self.handle)
+
+    def run(self, *fields, stream=None):
+        """fields: Storage objects or runtime.Field descriptors in API order (device-resident)."""
+        n = len(self.module.fields)
+        if len(fields) != n:
+            raise TypeError("%s.run expects %d fields (%s)" % (
+                self.module.name, n, ", ".join(f["name"] for f in self.module.fields)))
+        arr = (_rt.Field * n)(*[f.descriptor() if isinstance(f, Storage) else f for f in fields])
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
+        _rt.check(self.module._run(self.handle, arr, n, ctypes.c_void_p(stream)))
+
+    def run_from_host(self, *arrays, stream=None):
+        """End-to-end call with HOST buffers: numpy arrays indexed [k, j, i] in API order (length 1
+        along masked dimensions).  Copies inputs host->device, runs, copies every field the stencil
+        writes back into the given arrays.  Returns (h2d_bytes, d2h_bytes)."""
+        import torch
+        dom = self.domain
+        if self._host_storages is None:
+            self._host_storages = []
+            self._pinned = []
+            for f, a in zip(self.module.fields, arrays):
+                nk = a.shape[0]
+                st = Storage(dom.isize, dom.jsize, nk, f["dims"])
+                self._host_storages.append(st)
+                self._pinned.append(torch.empty(a.shape, dtype=torch.float64).pin_memory())
+        h2d = d2h = 0
+        for st, a, pin in zip(self._host_storages, arrays, self._pinned):
+            pin.copy_(torch.from_numpy(a))
+            st.view().copy_(pin.reshape(st.shape[2], st.shape[1], st.shape[0]), non_blocking=True)
+            h2d += a.nbytes
+        self.run(*self._host_storages, stream=stream)
+        written = self.written_fields()
+        for f, st, a, pin in zip(self.module.fields, self._host_storages, arrays, self._pinned):
+            if f["name"] in written:
+                pin.reshape(st.shape[2], st.shape[1], st.shape[0]).copy_(st.view(), non_blocking=True)
+                d2h += a.nbytes
+        torch.cuda.current_stream().synchronize()
+        for f, a, pin in zip(self.module.fields, arrays, self._pinned):
+            if f["name"] in written:
+                np.copyto(a, pin.numpy())
+        return h2d, d2h
+
+    def written_fields(self):
+        return set(self.module.info.get("written", [f["name"] for f in self.module.fields]))
+
+    def launches(self):
+        return int(self.module._launches(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.module._free(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def load_stencil(name, iir_path=None, tag="", **options) -> StencilModule:
+    """Loads the module generated from stencils/<name>.iir; with codegen options (or a tag) a variant
+    is emitted and compiled in-tree first (needs nvcc)."""
+    if options or tag:
+        path = iir_path or os.path.join(_build.ROOT, "stencils", name + ".iir")
+        with open(path) as f:
+            iir = f.read()
+        backend = "b200-ico" if '"gridType": "Unstructured"' in iir else "b200"
+        code = _codegen.compile_iir(iir, backend=backend, **options)
+        tag = tag or _build.variant_tag(options)
+        so = _build.compile_module(name, code, tag=tag)
+    else:
+        so = _build.module_path(name)
+        if not os.path.exists(so):
+            path = iir_path or os.path.join(_build.ROOT, "stencils", name + ".iir")
+            with open(path) as f:
+                iir = f.read()
+            backend = "b200-ico" if '"gridType": "Unstructured"' in iir else "b200"
+            so = _build.compile_module(name, _codegen.compile_iir(iir, backend=backend))
+    return StencilModule(name, so)

@@ -1,0 +1,80 @@
+/* dawn_b200_codegen.h — C ABI of the B200 code-generation backend (libdawn_b200_codegen.so).
+ *
+ * This is the string-level seam of the reference's backend selection:
+ *   std::string dawn::codegen::run(const std::map<std::string, std::string>& serializedIIR,
+ *                                  IIRSerializer::Format, Backend, const Options&)
+ *                                                   dawn/src/dawn/CodeGen/Driver.h:38-40
+ *   Backend dawn::codegen::parseBackendString(const std::string&)   CodeGen/Driver.cpp:47-64
+ * i.e. serialized optimized IIR in, one translation unit of source text out.  A Dawn tree binds it
+ * with the ~40-line adapter shown in INTEGRATION.md (Backend::B200 / Backend::B200Ico cases of the
+ * switch in CodeGen/Driver.cpp:67-85).  Plain pointers and sizes only; no C++ types cross it.
+ */
+#ifndef DAWN_B200_CODEGEN_H
+#define DAWN_B200_CODEGEN_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Values of dawn::codegen::Backend (CodeGen/Options.h:22) followed by the two new backends. */
+enum dawn_b200_backend {
+  DAWN_BACKEND_GRIDTOOLS = 0,
+  DAWN_BACKEND_CXXNAIVE = 1,
+  DAWN_BACKEND_CXXNAIVEICO = 2,
+  DAWN_BACKEND_CUDAICO = 3,
+  DAWN_BACKEND_CUDA = 4,
+  DAWN_BACKEND_CXXOPT = 5,
+  DAWN_BACKEND_B200 = 6,
+  DAWN_BACKEND_B200ICO = 7
+};
+
+/* dawn::codegen::Options (CodeGen/Options.inc:36-52) + Blackwell planner knobs (0 = automatic).
+ * The planner knobs take over what --block-size-i/j/k (Optimizer/Options.inc:44-46) and the cache
+ * passes decide for the reference's CUDA backend. */
+typedef struct dawn_b200_options {
+  int max_halo_points;   /* --max-halo-points, default 3 */
+  int use_parallel_ep;   /* accepted, unused */
+  int max_blocks_per_sm; /* accepted, unused: occupancy comes from __launch_bounds__ */
+  int nsms;              /* accepted, unused */
+  int domain_size_i, domain_size_j, domain_size_k; /* accepted, unused (sizes are run-time) */
+  int run_with_sync;     /* --run-with-sync, default 1 */
+  int block_size_i;      /* threads along i per block */
+  int block_size_j;      /* thread rows per block */
+  int rows_per_thread;   /* j rows computed per thread (register micro-tile) */
+  int block_size_k;      /* k levels per block for Parallel multistages */
+  int inline_temporaries; /* default 1: recompute single-assignment temporaries in registers */
+  int fuse_columns;      /* default 1: fuse horizontally pointwise multistages (solver sweeps) */
+  int unroll_k;          /* k-loop unroll factor */
+  int levels_per_thread; /* unstructured: k levels per thread */
+  int block_size_ico;    /* unstructured: threads per block */
+} dawn_b200_options;
+
+/* Fills `opts` with the defaults above. */
+void dawn_b200_default_options(dawn_b200_options* opts);
+
+/* parseBackendString twin: returns the enum value, or -1 ("Backend not supported"). */
+int dawn_b200_parse_backend(const char* backend_str);
+
+/* Generates code for `n` serialized stencil instantiations (IIR as proto3 JSON text).
+ *   names[i], iir_json[i], iir_len[i]: instantiation name and its serialized bytes.
+ *   backend: DAWN_BACKEND_B200 or DAWN_BACKEND_B200ICO (others -> error: not provided here).
+ * On success returns 0 and stores a malloc'ed, NUL-terminated translation unit in *out_code
+ * (release with dawn_b200_free).  On failure returns non-zero; dawn_b200_codegen_last_error()
+ * describes the problem (the reference throws std::runtime_error / SemanticError instead). */
+int dawn_b200_codegen_run(const char* const* names, const char* const* iir_json,
+                          const size_t* iir_len, int n, int backend, const dawn_b200_options* opts,
+                          char** out_code, size_t* out_len);
+
+void dawn_b200_free(void* p);
+const char* dawn_b200_codegen_last_error(void);
+
+/* ICOChainSize twin (dawn/src/dawn/CodeGen/IcoChainSizes.cpp:199-264): number of neighbours
+ * reached by a chain of location types (0 cells, 1 edges, 2 vertices) on a regular triangular
+ * mesh.  Returns -1 for an invalid chain. */
+int dawn_b200_ico_chain_size(const int* chain, int chain_len, int include_center);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,124 @@
+/* dawn_b200_rt.h — thin C-ABI runtime under the generated B200 stencils (libdawn_b200rt.so).
+ *
+ * Replaces, for the generated-code path, what the reference's generated CUDA code gets from
+ * GridTools device storages and its driver-includes:
+ *   storage allocation / host<->device movement   dawn/src/driver-includes/storage_runtime.hpp:69-97
+ *                                                 dawn/src/driver-includes/cuda_utils.hpp:127-210
+ *   event timers                                  dawn/src/driver-includes/timer_cuda.hpp:39-84
+ *   field verification on the GPU                 dawn/src/driver-includes/cuda_verify.hpp:84-196
+ *   layout transposition element-major<->level-major  cuda_utils.hpp:81-125 (reshape/reshape_back)
+ *   neighbour-table construction                  cuda_utils.hpp:212-263 (generateNbhTable)
+ * and adds what the reference lacks entirely: j-slab halo exchange between the GPUs of a box.
+ *
+ * Conventions: every function returns 0 on success or a B200_ERR_* code (the reference aborts the
+ * process in gpuErrchk, cuda_utils.hpp:31-39); b200rt_last_error() gives the message of the last
+ * failure on the calling thread.  Streams and events are opaque `void*` (cudaStream_t/cudaEvent_t).
+ * Plain pointers and sizes only.
+ */
+#ifndef DAWN_B200_RT_H
+#define DAWN_B200_RT_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  B200_OK = 0,
+  B200_ERR_CUDA = 1,    /* a CUDA runtime call failed */
+  B200_ERR_ARG = 2,     /* bad argument */
+  B200_ERR_HALO = 3,    /* domain halo smaller than the stencil's access extent */
+  B200_ERR_LAYOUT = 4,  /* field strides incompatible */
+  B200_ERR_RUNTIME = 5, /* other run-time failure */
+  B200_ERR_NCCL = 6
+};
+
+/* Device-resident field handed to a generated stencil: `data` addresses element (0,0,0) of the
+ * storage (halo included); i-stride is 1 for fields with an i dimension.  For masked dimensions the
+ * stride is ignored.  Unstructured dense fields: element-stride 1, `stride_k` = level stride;
+ * sparse fields: [k][nbh][element], `stride_j` = neighbour stride (= level-local element count). */
+typedef struct b200_field_t {
+  void* data;
+  int stride_j;
+  int stride_k;
+} b200_field_t;
+
+const char* b200rt_last_error(void);
+int b200rt_set_error(int code, const char* msg); /* returns code */
+
+int b200rt_device_count(int* n);
+int b200rt_set_device(int device);
+int b200rt_device_synchronize(void);
+
+int b200rt_malloc(void** dptr, size_t bytes);
+int b200rt_free(void* dptr);
+int b200rt_malloc_host(void** hptr, size_t bytes); /* pinned */
+int b200rt_free_host(void* hptr);
+int b200rt_memset(void* dptr, int value, size_t bytes, void* stream);
+int b200rt_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
+int b200rt_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
+int b200rt_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+/* strided 2-D copies (rows of `width_bytes`, `height` rows), either direction by pointer kind */
+int b200rt_memcpy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes,
+                    size_t height, void* stream);
+
+int b200rt_stream_create(void** stream);
+int b200rt_stream_destroy(void* stream);
+int b200rt_stream_synchronize(void* stream);
+
+int b200rt_event_create(void** event);
+int b200rt_event_destroy(void* event);
+int b200rt_event_record(void* event, void* stream);
+int b200rt_event_synchronize(void* event);
+int b200rt_event_elapsed_ms(void* start, void* stop, float* ms);
+int b200rt_check_last_launch(void); /* cudaGetLastError -> B200_ERR_CUDA */
+
+/* VerificationMetrics twin (driver-includes/verification_metrics.hpp:3-10), computed in ONE pass
+ * over the two device arrays (the reference runs 2 kernels + 8 thrust reductions + 2 cudaMallocs per
+ * field, cuda_verify.hpp:84-196). */
+typedef struct b200_verification_metrics {
+  int iteration;
+  int is_valid;
+  double max_rel_err, min_rel_err, max_abs_err, min_abs_err;
+  long long n_failed;
+} b200_verification_metrics;
+
+/* isclose semantics of cuda_verify.hpp:58-80: |a-b| <= abs_tol + rel_tol*|b| (NaN==NaN is close).
+ * `dsl` is the tested field, `ref` the reference one; both device pointers of n doubles. */
+int b200rt_verify_field(const double* dsl, const double* ref, size_t n, double rel_tol,
+                        double abs_tol, int iteration, b200_verification_metrics* out, void* stream);
+
+/* Layout transposition element-major [elem][k] <-> level-major [k][elem] on the device
+ * (cuda_utils.hpp:81-125 does this on one host thread).  sparse: [elem][sparse][k] <-> [k][sparse][elem]. */
+int b200rt_reshape(const double* in, double* out, int k_size, int num_elements, int sparse_size,
+                   void* stream);
+int b200rt_reshape_back(const double* in, double* out, int k_size, int num_elements, int sparse_size,
+                        void* stream);
+
+/* Neighbour table: row-major host table [elem][nbh] -> device SoA table [nbh][elem] (int32, -1
+ * padded), bit-exact with generateNbhTable (cuda_utils.hpp:212-263). */
+int b200rt_upload_nbh_table(const int* row_major, int num_elements, int nbh_size, int* d_table_soa,
+                            void* stream);
+
+/* ---- j-slab halo exchange across the GPUs of one box (new: the reference has no communication
+ * layer at all).  One process per GPU.  `comm` is an ncclComm_t created by the host
+ * (e.g. from torch.distributed's unique id) or by b200rt_comm_init_rank. ---- */
+int b200rt_nccl_unique_id(void* id128 /* 128 bytes out */);
+int b200rt_comm_init_rank(void** comm, int nranks, const void* id128, int rank);
+int b200rt_comm_destroy(void* comm);
+
+/* Exchanges `width` j-rows of every k level of an ijk field with the slab neighbours rank-1 / rank+1
+ * (non-periodic).  The field is the local slab INCLUDING halos: rows [0,halo) and [nj-halo,nj) are
+ * halo rows.  Interior rows adjacent to each boundary are packed by one kernel, sent with
+ * ncclSend/ncclRecv inside one group, and unpacked into the halo rows.  Scratch is owned by the plan. */
+typedef struct b200_halo_plan b200_halo_plan;
+int b200rt_halo_plan_create(b200_halo_plan** plan, void* comm, int rank, int nranks, int ni, int nj,
+                            int nk, int stride_j, int stride_k, int halo_j, int width_minus,
+                            int width_plus);
+int b200rt_halo_exchange(b200_halo_plan* plan, double* field, void* stream);
+int b200rt_halo_plan_destroy(b200_halo_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
