@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: horizontal diffusion (hori_diff_type2_stencil, 4th-order lap +
+flux limiter) on 1024x1024x80 doubles per GPU, grid-point updates/s and fraction of HBM roofline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload hori_diff|tridiagonal]
+
+N>1 is launched with torchrun (one rank per GPU): the global domain is 1024 x (1024*N) x 80 sharded
+into j-slabs (weak scaling); every step exchanges the 2-row j halos of `in` with the slab neighbours
+over NCCL and then runs the generated kernel.  Rank 0 prints ONE JSON line.
+
+Timing: CUDA events on the launching stream, W untimed + exactly K timed steps between barriers,
+max over ranks.  The three 0.68 GB fields of a step (2.0 GB) exceed the 126 MB L2, so no L2 flush is
+needed between steps.  The oracle (oracle/) is used only for the `cpu_baseline` leg and for
+`--impl reference`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+HALO = 3
+BYTES_PER_POINT = {"hori_diff": 24, "tridiagonal": 48}  # SURVEY.md §8(d), DESIGN.md §4
+STENCIL = {"hori_diff": "hori_diff_type2_stencil", "tridiagonal": "tridiagonal_solve"}
+SHAPE = {"hori_diff": (1024, 1024, 80), "tridiagonal": (512, 512, 80)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU legs (oracle): cpu_baseline and --impl reference
+# --------------------------------------------------------------------------------------------------
+def cpu_inputs(workload, I, J, K):
+    from util import hori_diff_type2_inputs, tridiagonal_inputs
+    return hori_diff_type2_inputs(I, J, K) if workload == "hori_diff" else tridiagonal_inputs(I, J, K)
+
+
+def cpu_run(workload, f, K, threads):
+    from oracle import capi
+    if workload == "hori_diff":
+        capi.hori_diff_type2(f["out"], f["in"], f["crlato"].reshape(-1), f["crlatu"].reshape(-1),
+                             f["hdmask"], nk=K, threads=threads)
+    else:
+        capi.tridiagonal_solve(f["d"], f["a"], f["b"], f["c"], nk=K, threads=threads)
+
+
+def cpu_baseline(workload):
+    """The reference's naive algorithm (oracle/naive_stencils.c, loop shape of CXXNaiveCodeGen.cpp:
+    380-495), single thread exactly as generated, full per-GPU domain, 1 warm-up + 3 timed runs."""
+    I, J, K = SHAPE[workload]
+    f = cpu_inputs(workload, I, J, K)
+    ts = []
+    for rep in range(4):
+        g = {k: v.copy() for k, v in f.items()}
+        t = time.perf_counter()
+        cpu_run(workload, g, K, 1)
+        ts.append(time.perf_counter() - t)
+    ts = sorted(ts[1:])
+    med = ts[len(ts) // 2]
+    return {"value": I * J * K / med, "unit": "grid-point updates/s", "cores": 1, "kind": "port",
+            "sample": "full %dx%dx%d domain, naive i-outer/j-inner loops, 1 warm-up + 3 timed runs, "
+                      "median %.3f s; g++ -O3 -ffp-contract=off" % (I, J, K, med)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workload = args.workload
+    I, J, K = SHAPE[workload]
+    Ks = min(K, 16)  # bounded sample per step: the first 16 levels of the domain
+    threads = os.cpu_count() or 1
+    f = cpu_inputs(workload, I, J, Ks)
+    for _ in range(args.warmup):
+        cpu_run(workload, f, Ks, threads)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_run(workload, f, Ks, threads)
+    dt = time.perf_counter() - t
+    val = I * J * Ks * args.steps / dt
+    sample = ("each step = levels [0,%d) of the %dx%dx%d domain (%d of %d levels), k split over %d "
+              "pthreads" % (Ks, I, J, K, Ks, K, threads))
+    if workload == "tridiagonal":
+        sample = "each step = full %dx%dx%d solve, i columns split over %d pthreads" % (I, J, Ks, threads)
+    line = {
+        "impl": "reference", "metric": "grid-point updates/s", "value": val,
+        "unit": "grid-point updates/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s %dx%dx%d double (reference naive C++ algorithm on host cores)" % (
+            STENCIL[workload], I, J, K)},
+        "cpu_baseline": {"value": val, "unit": "grid-point updates/s", "cores": threads,
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "grid-point updates/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU leg
+# --------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import numpy as np
+    import torch
+
+    import dawn_b200
+    from dawn_b200 import runtime as rt
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    workload = args.workload
+    I, J, K = SHAPE[workload]
+    name = STENCIL[workload]
+    ni, nj = I + 2 * HALO, J + 2 * HALO
+    opts = {}
+    for kv in args.opt:
+        k, v = kv.split("=")
+        opts[k] = int(v)
+    mod = dawn_b200.load_stencil(name, **opts)
+    dom = dawn_b200.Domain(ni, nj, K)
+    dom.set_halos(HALO, HALO, HALO, HALO, 0, 0)
+    st = mod(dom)
+
+    # synthetic inputs: fillMath closed form of the reference drivers, generated on the device for
+    # this rank's slab of the global domain (global j offset = rank * J)
+    stor = {}
+    for fd in mod.fields:
+        stor[fd["name"]] = dawn_b200.Storage(ni, nj, K + 1, fd["dims"])
+    from util import FILL
+    keymap = {"in": "u", "out": None}
+
+    def dev_fill(s, consts, gj0, gnj):
+        a, b, c, d, e, f = consts
+        nk_, nj_, ni_ = s.shape[2], s.shape[1], s.shape[0]
+        ii = torch.arange(ni_, device="cuda", dtype=torch.float64) / (ni_ if "i" in s.dims else 1)
+        jj = (torch.arange(nj_, device="cuda", dtype=torch.float64) + gj0) / gnj
+        kk = torch.arange(nk_, device="cuda", dtype=torch.float64)
+        x = ii[None, None, :] if "i" in s.dims else torch.zeros(1, 1, 1, device="cuda", dtype=torch.float64)
+        y = jj[None, :, None] if "j" in s.dims else torch.zeros(1, 1, 1, device="cuda", dtype=torch.float64)
+        v = kk[:, None, None] * 10e-3 + a * (b + torch.cos(np.pi * (x + c * y)) +
+                                             torch.sin(d * np.pi * (x + e * y))) / f
+        s.view().copy_(v.expand(nk_, nj_, ni_))
+
+    gnj = J * world + 2 * HALO
+    for fd in mod.fields:
+        s = stor[fd["name"]]
+        key = keymap.get(fd["name"], fd["name"])
+        if key is None:
+            s.fill(-1.0)
+        else:
+            dev_fill(s, FILL[key], rank * J, gnj)
+            if workload == "tridiagonal" and fd["name"] == "b":
+                s.buf.add_(12.0)
+    torch.cuda.synchronize()
+    fields = [stor[fd["name"]] for fd in mod.fields]
+
+    # halo exchange plan for every input with a j extent (multi-GPU only)
+    plans = []
+    comm = None
+    if world > 1:
+        import ctypes
+        idbuf = (ctypes.c_char * 128)()
+        if rank == 0:
+            rt.check(rt.lib().b200rt_nccl_unique_id(idbuf))
+        obj = [bytes(idbuf)]
+        dist.broadcast_object_list(obj, src=0)
+        idbuf = (ctypes.c_char * 128).from_buffer_copy(obj[0])
+        comm = ctypes.c_void_p()
+        rt.check(rt.lib().b200rt_comm_init_rank(ctypes.byref(comm), world, idbuf, rank))
+        written = st.written_fields()
+        for fd in mod.fields:
+            jm, jp = -fd["extent"][2], fd["extent"][3]
+            if fd["dims"] == "ijk" and fd["name"] not in written and (jm or jp):
+                s = stor[fd["name"]]
+                plan = ctypes.c_void_p()
+                rt.check(rt.lib().b200rt_halo_plan_create(
+                    ctypes.byref(plan), comm, rank, world, ni, nj, K, s.stride_j, s.stride_k, HALO,
+                    jm, jp))
+                plans.append((plan, s))
+
+    stream = torch.cuda.current_stream().cuda_stream
+    launches_per_step = [0]
+
+    def step():
+        n = 0
+        for plan, s in plans:
+            rt.check(rt.lib().b200rt_halo_exchange(plan, s.buf.data_ptr() + 8 * s.lead, stream))
+            n += (2 if rank > 0 else 0) + (2 if rank + 1 < world else 0)
+        st.run(*fields)
+        launches_per_step[0] = n
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- kernel-only time (roofline): events around the generated kernel alone -----------------
+    l0 = st.launches()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(args.steps):
+        st.run(*fields)
+    ev[1].record()
+    torch.cuda.synchronize()
+    kernel_ms = ev[0].elapsed_time(ev[1]) / args.steps
+    kernels_per_run = (st.launches() - l0) // args.steps
+
+    # ---- timed region: K steps ------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = st.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    launches = (st.launches() - l0) + launches_per_step[0] * args.steps
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    # ---- end to end through the public API with HOST buffers --------------------------------------
+    e2e_steps = min(args.steps, 5)
+    host = [torch.empty(s.shape[2], s.shape[1], s.shape[0], dtype=torch.float64).pin_memory()
+            for s in fields]
+    for h, s in zip(host, fields):
+        h.copy_(s.view())
+    st2 = mod(dom)
+    h2d, d2h = st2.run_from_host(*host)  # warm-up (allocates the device-side storages)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        h2d, d2h = st2.run_from_host(*host)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+
+    pts = I * J * K
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = BYTES_PER_POINT[workload] * pts / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % workload)
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        line = {
+            "metric": "grid-point updates/s", "value": pts * world * args.steps / (ms_max * 1e-3),
+            "unit": "grid-point updates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (fillMath closed form of the reference drivers, generated on device)",
+            "config": {
+                "workload": "%s %dx%dx%d double per GPU (halo 3, storages %dx%dx%d)%s" % (
+                    name, I, J, K, ni, nj, K + 1,
+                    "" if world == 1 else ", global %dx%dx%d in %d j-slabs, NCCL halo exchange of "
+                    "`in` (2 rows each way) every step" % (I, J * world, K, world)),
+                "l2": "inputs larger than L2 (2.0 GB per step vs 126 MB), no flush",
+                "codegen_options": opts,
+            },
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "kernel": "%s (generated), %d launch(es)/step, %.4f ms/launch, %d algorithmic B/point"
+                          % (name, kernels_per_run, kernel_ms / max(1, kernels_per_run),
+                             BYTES_PER_POINT[workload]),
+                "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+            },
+            "e2e": {"value": pts * world * e2e_steps / e2e_s, "unit": "grid-point updates/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "dawn_b200.Stencil.run_from_host (pinned host buffers)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(workload)
+        print(json.dumps(line))
+    for plan, _ in plans:
+        rt.lib().b200rt_halo_plan_destroy(plan)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="hori_diff", choices=list(STENCIL))
+    ap.add_argument("--opt", action="append", default=[], help="codegen option key=value (sweeps)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -81,7 +81,10 @@ def compile_module(name, code, tag="", force=False, extra_flags=(), keep_ptxas=F
         return so
     with open(cu, "w") as f:
         f.write(code)
+    # hidden visibility + -Bsymbolic: several variants of one stencil (same kernel and class names)
+    # can live in one process without their symbols interposing each other
     cmd = [NVCC] + NVCC_COMMON + ["-fmad=false", "-Xptxas", "-v", "-I", PKG, "-o", so, cu,
+                                  "-Xcompiler", "-fvisibility=hidden", "-Xlinker", "-Bsymbolic",
                                   "-L", LIB, "-ldawn_b200rt", "-Xlinker", "-rpath,$ORIGIN/.."] + \
         list(extra_flags)
     out = _run(cmd)
@@ -97,6 +100,7 @@ VARIANTS = {
     "hori_diff_type2_stencil": [
         dict(rows_per_thread=1), dict(rows_per_thread=4),
         dict(block_size_i=32, block_size_j=8, rows_per_thread=2), dict(inline_temporaries=0),
+        dict(use_tma=0), dict(tma_stages=2, block_size_k=3), dict(inline_temporaries=0, use_tma=0),
     ],
     "tridiagonal_solve": [dict(fuse_columns=0)],
 }

@@ -24,6 +24,7 @@ b200::codegen::Options convert(const dawn_b200_options* o) {
   r.InlineTemporaries = o->inline_temporaries, r.FuseColumns = o->fuse_columns;
   r.UnrollK = o->unroll_k;
   r.LevelsPerThread = o->levels_per_thread, r.BlockSizeIco = o->block_size_ico;
+  r.UseTMA = o->use_tma, r.TmaStages = o->tma_stages;
   return r;
 }
 } // namespace
@@ -42,6 +43,7 @@ void dawn_b200_default_options(dawn_b200_options* o) {
   o->run_with_sync = 1;
   o->inline_temporaries = 1;
   o->fuse_columns = 1;
+  o->use_tma = 1;
 }
 
 int dawn_b200_parse_backend(const char* s) {

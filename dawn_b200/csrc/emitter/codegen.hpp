@@ -38,6 +38,8 @@ struct Options {
   int UnrollK = 0;        // k-loop unroll factor (0 = planner default)
   int LevelsPerThread = 0; // unstructured: levels per thread
   int BlockSizeIco = 0;    // unstructured: threads per block
+  int UseTMA = 1;          // 1: tile kernels stage their read-only inputs with TMA (when aligned)
+  int TmaStages = 0;       // depth of the TMA shared-memory ring over k (0 = planner default 4)
 };
 
 // TranslationUnit twin (CodeGen/TranslationUnit.h:26-53)

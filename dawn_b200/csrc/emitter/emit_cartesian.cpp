@@ -88,6 +88,23 @@ struct KernelPlan {
   std::set<int> fieldsUsed;   // storage-backed fields referenced by this kernel (pointer args)
   std::set<int> fieldsWritten;
   bool usesGlobals = false;
+  // --- TMA variant: read-only ijk inputs staged as (tile + extent) boxes in a smem ring over k ---
+  struct Staged {
+    int field;
+    int im, ip, jm, jp; // box extent relative to the tile
+    int W, H;           // box size in elements (W padded to an even count: 16-byte rows)
+    int offset;         // element offset inside one pipeline stage
+  };
+  bool tma = false;
+  std::vector<Staged> staged;
+  int stages = 0;
+  int stageElems = 0; // doubles per pipeline stage (every field 128-byte aligned)
+  const Staged* stagedOf(int f) const {
+    for(auto const& s : staged)
+      if(s.field == f)
+        return &s;
+    return nullptr;
+  }
 };
 
 class CartesianEmitter {
@@ -131,6 +148,7 @@ private:
   void planTemporaries(const Stencil& st);
   std::vector<KernelPlan> planKernels(const Stencil& st);
   void collectUse(KernelPlan& kp) const;
+  bool planTma(KernelPlan& kp) const;
 
   void emitGlobalsStruct();
   void emitKernel(const Stencil& st, const KernelPlan& kp);
@@ -317,6 +335,100 @@ void CartesianEmitter::collectUse(KernelPlan& kp) const {
     }
 }
 
+// Which inputs of a tile kernel are staged through shared memory by TMA, and with which box.
+bool CartesianEmitter::planTma(KernelPlan& kp) const {
+  if(kp.ms.size() != 1)
+    return false;
+  const MultiStage& ms = *kp.ms[0];
+  struct Box {
+    bool any = false, vertical = false;
+    int im = 0, ip = 0, jm = 0, jp = 0;
+  };
+  std::map<int, Box> boxes;
+  std::function<void(const ExprPtr&, int, int, const Extent&)> walk = [&](const ExprPtr& e, int si,
+                                                                         int sj, const Extent& ex) {
+    if(!e)
+      return;
+    if(e->kind == Expr::Field) {
+      auto inl = inlined_.find(e->accessID);
+      MaskClass m = maskOf(e->accessID);
+      int di = m.i ? e->di + si : 0, dj = m.j ? e->dj + sj : 0;
+      if(inl != inlined_.end()) {
+        walk(inl->second.expr, di, dj, ex);
+        return;
+      }
+      Box& b = boxes[e->accessID];
+      if(e->dk != 0)
+        b.vertical = true;
+      int lo_i = di + ex.iMinus, hi_i = di + ex.iPlus, lo_j = dj + ex.jMinus, hi_j = dj + ex.jPlus;
+      if(!b.any)
+        b.im = lo_i, b.ip = hi_i, b.jm = lo_j, b.jp = hi_j, b.any = true;
+      else
+        b.im = std::min(b.im, lo_i), b.ip = std::max(b.ip, hi_i), b.jm = std::min(b.jm, lo_j),
+        b.jp = std::max(b.jp, hi_j);
+      return;
+    }
+    for(auto const& k : e->kids)
+      walk(k, si, sj, ex);
+  };
+  std::function<void(const StmtPtr&, const Extent&)> ws = [&](const StmtPtr& st, const Extent& ex) {
+    if(st->kind == Stmt::ExprStmt && st->expr->kind == Expr::Assign) {
+      const Expr& l = *st->expr->kids[0];
+      if(l.kind == Expr::Field && inlined_.count(l.accessID))
+        return; // definition of an inlined temporary
+      walk(st->expr->kids[1], 0, 0, ex);
+      if(st->expr->op != "=")
+        walk(st->expr->kids[0], 0, 0, ex);
+    } else
+      walk(st->expr, 0, 0, ex);
+    for(auto const& c : st->body)
+      ws(c, ex);
+    for(auto const& c : st->orelse)
+      ws(c, ex);
+  };
+  for(auto const& stage : ms.stages) {
+    if(droppedStages_.count(stage.id))
+      continue;
+    if(stage.hasIRange || stage.hasJRange)
+      return false;
+    for(auto const& dm : stage.doMethods)
+      for(auto const& st : dm.stmts)
+        ws(st, stage.extent);
+  }
+  int offset = 0;
+  for(auto const& bp : boxes) {
+    int f = bp.first;
+    const Box& b = bp.second;
+    MaskClass m = maskOf(f);
+    if(!(m.i && m.j && m.k) || b.vertical || kp.fieldsWritten.count(f) || !kp.fieldsUsed.count(f))
+      continue;
+    KernelPlan::Staged sg;
+    sg.field = f;
+    // the box starts on an even i coordinate: every row segment TMA reads begins 16-byte aligned
+    sg.im = -(((std::max(0, -b.im) + 1) / 2) * 2), sg.ip = std::max(0, b.ip);
+    sg.jm = std::min(0, b.jm), sg.jp = std::max(0, b.jp);
+    sg.W = kp.TI + sg.ip - sg.im;
+    sg.W += sg.W & 1; // 16-byte multiple rows for the TMA box
+    sg.H = kp.tileJ() + sg.jp - sg.jm;
+    if(sg.W > 256 || sg.H > 256)
+      return false;
+    sg.offset = offset;
+    offset += ((sg.W * sg.H + 15) / 16) * 16; // keep every field 128-byte aligned
+    kp.staged.push_back(sg);
+  }
+  if(kp.staged.empty())
+    return false;
+  kp.tma = true;
+  kp.stageElems = offset;
+  kp.stages = opt_.TmaStages > 0 ? opt_.TmaStages : 4;
+  // keep at least two blocks per SM resident (227 KB of shared memory per SM)
+  while(kp.stages > 2 && (size_t)kp.stages * kp.stageElems * 8 + 128 > 100 * 1024)
+    --kp.stages;
+  if((size_t)kp.stages * kp.stageElems * 8 + 128 > 200 * 1024)
+    return false;
+  return true;
+}
+
 std::vector<KernelPlan> CartesianEmitter::planKernels(const Stencil& st) {
   auto msPointwise = [&](const MultiStage& ms) {
     for(auto const& stage : ms.stages) {
@@ -408,7 +520,7 @@ std::vector<KernelPlan> CartesianEmitter::planKernels(const Stencil& st) {
       kp.TI = opt_.BlockSizeI > 0 ? opt_.BlockSizeI : 64;
       kp.TJ = opt_.BlockSizeJ > 0 ? opt_.BlockSizeJ : 4;
       kp.RJ = opt_.RowsPerThread > 0 ? opt_.RowsPerThread : 2;
-      kp.KC = opt_.BlockSizeK > 0 ? opt_.BlockSizeK : 8;
+      kp.KC = opt_.BlockSizeK > 0 ? opt_.BlockSizeK : 20;
     }
     if(kp.NT() > 1024 || kp.NT() < 32)
       throw std::runtime_error("b200: block size must be within [32,1024] threads");
@@ -416,6 +528,13 @@ std::vector<KernelPlan> CartesianEmitter::planKernels(const Stencil& st) {
               std::to_string(kidx++) + "_kernel";
     collectUse(kp);
     out.push_back(kp);
+    if(opt_.UseTMA && !kp.pointwise) {
+      KernelPlan kt = kp;
+      if(planTma(kt)) {
+        kt.name = kp.name.substr(0, kp.name.size() - 7) + "_tma_kernel";
+        out.push_back(kt);
+      }
+    }
     m = e;
   }
   return out;
@@ -512,6 +631,24 @@ public:
         return fieldName(e.accessID) + "_kc" + std::to_string(trailing);
     }
     bool readOnly = !kp.fieldsWritten.count(e.accessID);
+    const KernelPlan::Staged* sg = kp.tma ? kp.stagedOf(e.accessID) : nullptr;
+    if(sg && dk == 0) {
+      std::string key = "S" + std::to_string(e.accessID) + ":" + std::to_string(di) + ":" +
+                        std::to_string(djAbs);
+      auto it = valueNo.find(key);
+      if(it != valueNo.end())
+        return it->second;
+      std::string var = fieldName(e.accessID) + "_" + offTag(di) + "_" + offTag(djAbs) + "_s";
+      int firstRow = std::max(0, std::min(rows - 1, curRow));
+      std::string guard = rowGuards ? "v" + std::to_string(firstRow) + " ? " : "";
+      std::string tail = rowGuards ? " : (::dawn::float_type)0" : "";
+      loads.push_back("const ::dawn::float_type " + var + " = " + guard + "s_" +
+                      fieldName(e.accessID) + "[(lyb + (" + std::to_string(djAbs - sg->jm) + ")) * " +
+                      std::to_string(sg->W) + " + lx + (" + std::to_string(di - sg->im) + ")]" + tail +
+                      ";");
+      valueNo[key] = var;
+      return var;
+    }
     if(readOnly) {
       std::string key = "F" + std::to_string(e.accessID) + ":" + std::to_string(di) + ":" +
                         std::to_string(djAbs) + ":" + std::to_string(dk);
@@ -710,7 +847,8 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
   os_ << "// kernel " << kp.name << ": " << (kp.pointwise ? "column" : "tile") << " kernel over "
       << kp.ms.size() << " multistage(s), block " << kp.TI << "x" << kp.TJ << " threads, "
       << kp.RJ << " row(s)/thread" << (kp.zchunk ? ", k split over blockIdx.z" : "") << "\n";
-  os_ << "__global__ void __launch_bounds__(" << kp.NT() << ")\n"
+  os_ << "__global__ void __launch_bounds__(" << kp.NT()
+      << (opt_.MaxBlocksPerSM > 0 ? ", " + std::to_string(opt_.MaxBlocksPerSM) : std::string()) << ")\n"
       << kp.name << "(";
   if(kp.usesGlobals)
     os_ << "const globals g, ";
@@ -727,6 +865,8 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
     os_ << ",\n    " << (ro ? "const " : "") << "::dawn::float_type* __restrict__ " << fname(f)
         << "_p";
   }
+  for(auto const& sg : kp.staged)
+    os_ << ",\n    const __grid_constant__ CUtensorMap tm_" << fname(sg.field);
   os_ << ") {\n";
   os_ << "  const int tid = threadIdx.x;\n";
   os_ << "  const int i0 = blockIdx.x * " << kp.TI << ";\n";
@@ -735,6 +875,39 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
   os_ << "  (void)kmin; (void)kmax; (void)kchunk;\n";
 
   BodyEmitter be(inst_, kp, inlined_, [this](int id) { return maskOf(id); });
+
+  // ---- TMA ring: one mbarrier per pipeline stage, thread 0 is the producer ----------------------
+  size_t tmaBytes = 0;
+  for(auto const& sg : kp.staged)
+    tmaBytes += (size_t)sg.W * sg.H * 8;
+  if(kp.tma) {
+    os_ << "  extern __shared__ __align__(128) unsigned char b200_smem[];\n";
+    os_ << "  unsigned long long* tma_full = reinterpret_cast<unsigned long long*>(b200_smem);\n";
+    os_ << "  ::dawn::float_type* tma_ring = reinterpret_cast<::dawn::float_type*>(b200_smem + 128);\n";
+    os_ << "  if(tid == 0) {\n";
+    os_ << "    for(int s = 0; s < " << kp.stages << "; ++s)\n"
+        << "      ::dawn_b200::tma::barrier_init(&tma_full[s], 1);\n";
+    os_ << "    ::dawn_b200::tma::fence_barrier_init();\n  }\n";
+    os_ << "  __syncthreads();\n";
+    os_ << "  unsigned tma_it = 0; // k iterations consumed so far: stage = it % " << kp.stages
+        << ", parity = (it / " << kp.stages << ") & 1\n";
+  }
+  auto emitTmaIssue = [&](const std::string& pad, const std::string& kExpr,
+                          const std::string& stageExpr) {
+    os_ << pad << "{\n";
+    os_ << pad << "  const unsigned ts = " << stageExpr << ";\n";
+    os_ << pad << "  ::dawn_b200::tma::expect_bytes(&tma_full[ts], " << tmaBytes << "u);\n";
+    for(auto const& sg : kp.staged) {
+      int EI = ((-sg.im + 1) / 2) * 2;
+      if(EI < 0)
+        EI = 0;
+      int EJ = sg.jm < 0 ? -sg.jm : 0;
+      os_ << pad << "  ::dawn_b200::tma::load_3d(tma_ring + ts * " << kp.stageElems << " + "
+          << sg.offset << ", &tm_" << fname(sg.field) << ", i0 + (" << sg.im + EI << "), j0 + ("
+          << sg.jm + EJ << "), " << kExpr << ", &tma_full[ts]);\n";
+    }
+    os_ << pad << "}\n";
+  };
 
   auto emitIndexBases = [&](const std::string& pad) {
     for(auto const& c : classes) {
@@ -811,12 +984,33 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         os_ << "      }\n";
       }
       first = false;
-      int unroll = opt_.UnrollK > 0 ? opt_.UnrollK : (sequential ? 4 : 2);
-      os_ << "#pragma unroll " << unroll << "\n";
-      if(backward)
-        os_ << "      for(int k = ke; k >= kb; --k) {\n";
-      else
-        os_ << "      for(int k = kb; k <= ke; ++k) {\n";
+      int unroll = opt_.UnrollK > 0 ? opt_.UnrollK : (sequential ? 4 : 1);
+      if(kp.tma) {
+        const std::string kOf = backward ? "ke - " : "kb + ";
+        os_ << "      const int nk_loc = ke - kb + 1;\n";
+        os_ << "      if(tid == 0) {\n";
+        os_ << "        for(int q = 0; q < " << kp.stages - 1 << " && q < nk_loc; ++q)\n";
+        emitTmaIssue("          ", kOf + "q", "(tma_it + q) % " + std::to_string(kp.stages));
+        os_ << "      }\n";
+        os_ << "      for(int it = 0; it < nk_loc; ++it) {\n";
+        os_ << "        const int k = " << kOf << "it;\n";
+        os_ << "        const unsigned tcur = (tma_it + it) % " << kp.stages << ";\n";
+        os_ << "        if(tid == 0 && it + " << kp.stages - 1 << " < nk_loc)\n";
+        emitTmaIssue("          ", kOf + "(it + " + std::to_string(kp.stages - 1) + ")",
+                     "(tma_it + it + " + std::to_string(kp.stages - 1) + ") % " +
+                         std::to_string(kp.stages));
+        os_ << "        ::dawn_b200::tma::wait(&tma_full[tcur], ((tma_it + it) / " << kp.stages
+            << ") & 1u);\n";
+        for(auto const& sg : kp.staged)
+          os_ << "        const ::dawn::float_type* s_" << fname(sg.field) << " = tma_ring + tcur * "
+              << kp.stageElems << " + " << sg.offset << ";\n";
+      } else {
+        os_ << "#pragma unroll " << unroll << "\n";
+        if(backward)
+          os_ << "      for(int k = ke; k >= kb; --k) {\n";
+        else
+          os_ << "      for(int k = kb; k <= ke; ++k) {\n";
+      }
 
       // stages
       std::vector<const Stage*> live;
@@ -943,9 +1137,13 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
           os_ << "        " << fname(r.first) << "_kc" << n << " = " << fname(r.first) << "_kc"
               << n - 1 << ";\n";
       // a stage of the next level may overwrite scratch another thread still reads
-      if(!kp.pointwise && live.size() > 1 && sequential)
+      if(kp.tma)
+        os_ << "        __syncthreads(); // every thread is done with this ring slot before its refill\n";
+      else if(!kp.pointwise && live.size() > 1 && sequential)
         os_ << "        __syncthreads();\n";
       os_ << "      }\n";
+      if(kp.tma)
+        os_ << "      tma_it += nk_loc > 0 ? (unsigned)nk_loc : 0u;\n";
       os_ << "    }\n";
     }
     os_ << "  }\n";
@@ -1114,13 +1312,22 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
         classRep["111"] = -1;
       }
     }
-    for(auto const& kp : kps) {
-      os_ << "      {\n";
-      os_ << "        const int kchunk = " << kp.KC << ";\n";
-      os_ << "        dim3 grid((nx + " << kp.TI - 1 << ") / " << kp.TI << ", (ny + "
+    auto emitLaunch = [&](const KernelPlan& kp, const std::string& pad) {
+      os_ << pad << "const int kchunk = " << kp.KC << ";\n";
+      os_ << pad << "dim3 grid((nx + " << kp.TI - 1 << ") / " << kp.TI << ", (ny + "
           << kp.tileJ() - 1 << ") / " << kp.tileJ() << ", "
           << (kp.zchunk ? "(nz + kchunk - 1) / kchunk" : "1") << ");\n";
-      os_ << "        " << kp.name << "<<<grid, " << kp.NT() << ", 0, stream>>>(";
+      size_t smem = kp.tma ? 128 + (size_t)kp.stages * kp.stageElems * 8 : 0;
+      if(kp.tma) {
+        os_ << pad << "static bool smem_set = false;\n";
+        os_ << pad << "if(!smem_set) {\n";
+        os_ << pad << "  cudaError_t ae = cudaFuncSetAttribute(reinterpret_cast<const void*>(&" << kp.name
+            << "), cudaFuncAttributeMaxDynamicSharedMemorySize, " << smem << ");\n";
+        os_ << pad << "  if(ae != cudaSuccess) return ::dawn_b200::set_error(B200_ERR_CUDA, "
+            << "cudaGetErrorString(ae));\n";
+        os_ << pad << "  smem_set = true;\n" << pad << "}\n";
+      }
+      os_ << pad << kp.name << "<<<grid, " << kp.NT() << ", " << smem << ", stream>>>(";
       if(kp.usesGlobals)
         os_ << "m_globals, ";
       os_ << "nx, ny, nz, kchunk";
@@ -1133,13 +1340,50 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
       }
       for(int f : kernelArgs(kp))
         os_ << ", " << fname(f) << "_p";
+      for(auto const& sg : kp.staged)
+        os_ << ", tm_" << fname(sg.field);
       os_ << ");\n";
-      os_ << "        ++m_launches;\n";
+      os_ << pad << "++m_launches;\n";
+    };
+    for(size_t n = 0; n < kps.size(); ++n) {
+      const KernelPlan& kp = kps[n];
+      const KernelPlan* twin = (n + 1 < kps.size() && kps[n + 1].tma) ? &kps[n + 1] : nullptr;
+      os_ << "      {\n";
+      if(twin) {
+        // TMA needs 16-byte aligned rows: interior origin 16 B aligned, even j/k strides
+        os_ << "        bool tma_ok = m_use_tma && sj_111 % 2 == 0 && sk_111 % 2 == 0";
+        for(auto const& sg : twin->staged)
+          os_ << " && (reinterpret_cast<uintptr_t>(" << fname(sg.field) << "_p) % 16 == 0)";
+        os_ << ";\n";
+        for(auto const& sg : twin->staged)
+          os_ << "        alignas(64) CUtensorMap tm_" << fname(sg.field) << ";\n";
+        os_ << "        if(tma_ok) {\n";
+        for(auto const& sg : twin->staged) {
+          int EI = ((-sg.im + 1) / 2) * 2;
+          if(EI < 0)
+            EI = 0;
+          int EJ = sg.jm < 0 ? -sg.jm : 0;
+          os_ << "          if(b200rt_tensor_map_3d(&tm_" << fname(sg.field) << ", " << fname(sg.field)
+              << "_p - " << EI << " - (ptrdiff_t)" << EJ << " * sj_111, " << EI
+              << " + nx + (int)m_dom.iplus(), " << EJ << " + ny + (int)m_dom.jplus(), nz, sj_111, "
+              << "sk_111, " << sg.W << ", " << sg.H << ")) tma_ok = false;\n";
+        }
+        os_ << "        }\n";
+        os_ << "        if(tma_ok) {\n";
+        emitLaunch(*twin, "          ");
+        os_ << "        } else {\n";
+        emitLaunch(kp, "          ");
+        os_ << "        }\n";
+        ++n;
+      } else {
+        emitLaunch(kp, "        ");
+      }
       os_ << "      }\n";
     }
     os_ << "      return ::dawn_b200::check_launch();\n";
     os_ << "    }\n";
     os_ << "    long m_launches = 0;\n";
+    os_ << "    bool m_use_tma = true;\n";
     // ---- storage path ----
     os_ << "\n    void run(";
     for(size_t a = 0; a < sargs.size(); ++a)
@@ -1268,8 +1512,9 @@ void CartesianEmitter::emitCAbi() {
   // 1186-1228), but handle-based instead of static class members.
   const std::string n = cIdent(inst_.name);
   const std::string cls = "dawn_generated::b200::" + n;
+  os_ << "#define B200_EXPORT __attribute__((visibility(\"default\")))\n";
   os_ << "extern \"C\" {\n";
-  os_ << "int setup_" << n << "(void** handle, int isize, int jsize, int ksize, const int* halos, void* stream) {\n"
+  os_ << "B200_EXPORT int setup_" << n << "(void** handle, int isize, int jsize, int ksize, const int* halos, void* stream) {\n"
       << "  try {\n"
       << "    gridtools::dawn::domain dom(isize, jsize, ksize);\n"
       << "    if(halos) dom.set_halos(halos[0], halos[1], halos[2], halos[3], halos[4], halos[5]);\n"
@@ -1278,22 +1523,22 @@ void CartesianEmitter::emitCAbi() {
       << "    *handle = s;\n"
       << "    return 0;\n"
       << "  } catch(std::exception& e) { return ::dawn_b200::set_error(B200_ERR_RUNTIME, e.what()); }\n}\n";
-  os_ << "int run_" << n << "(void* handle, const b200_field_t* fields, int nfields, void* stream) {\n"
+  os_ << "B200_EXPORT int run_" << n << "(void* handle, const b200_field_t* fields, int nfields, void* stream) {\n"
       << "  if(!handle || nfields != " << inst_.apiFieldIDs.size()
       << ") return ::dawn_b200::set_error(B200_ERR_ARG, \"run_" << n << ": expected "
       << inst_.apiFieldIDs.size() << " fields\");\n"
       << "  return static_cast<" << cls << "*>(handle)->run_raw(fields, stream);\n}\n";
-  os_ << "void free_" << n << "(void* handle) { delete static_cast<" << cls << "*>(handle); }\n";
-  os_ << "long launches_" << n << "(void* handle) { return static_cast<" << cls
+  os_ << "B200_EXPORT void free_" << n << "(void* handle) { delete static_cast<" << cls << "*>(handle); }\n";
+  os_ << "B200_EXPORT long launches_" << n << "(void* handle) { return static_cast<" << cls
       << "*>(handle)->launches(); }\n";
   for(auto const& g : inst_.globals) {
-    os_ << "void set_" << n << "_" << cIdent(g.first) << "(void* handle, double v) { static_cast<"
+    os_ << "B200_EXPORT void set_" << n << "_" << cIdent(g.first) << "(void* handle, double v) { static_cast<"
         << cls << "*>(handle)->set_" << cIdent(g.first) << "(v); }\n";
-    os_ << "double get_" << n << "_" << cIdent(g.first) << "(void* handle) { return static_cast<"
+    os_ << "B200_EXPORT double get_" << n << "_" << cIdent(g.first) << "(void* handle) { return static_cast<"
         << cls << "*>(handle)->get_" << cIdent(g.first) << "(); }\n";
   }
   // module description for generic hosts (Python ctypes, Fortran)
-  os_ << "const char* b200_module_info_" << n << "() {\n  return \"{\\\"name\\\": \\\"" << inst_.name
+  os_ << "B200_EXPORT const char* b200_module_info_" << n << "() {\n  return \"{\\\"name\\\": \\\"" << inst_.name
       << "\\\", \\\"grid\\\": \\\"Cartesian\\\", \\\"fields\\\": [";
   auto fext = inst_.stencils.size() == 1 ? analysis::fieldExtents(inst_, inst_.stencils[0])
                                          : std::map<int, Extent>{};

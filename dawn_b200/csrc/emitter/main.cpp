@@ -41,7 +41,9 @@ int main(int argc, char** argv) {
             intOpt(a, "inline-temporaries", opts.InlineTemporaries) ||
             intOpt(a, "fuse-columns", opts.FuseColumns) || intOpt(a, "unroll-k", opts.UnrollK) ||
             intOpt(a, "levels-per-thread", opts.LevelsPerThread) ||
-            intOpt(a, "block-size-ico", opts.BlockSizeIco) ||
+            intOpt(a, "block-size-ico", opts.BlockSizeIco) || intOpt(a, "use-tma", opts.UseTMA) ||
+            intOpt(a, "tma-stages", opts.TmaStages) ||
+            intOpt(a, "max-blocks-sm", opts.MaxBlocksPerSM) ||
             intOpt(a, "max-halo-points", opts.MaxHaloSize)) {
     } else if(a.compare(0, 16, "--run-with-sync=") == 0)
       opts.RunWithSync = a.substr(16) != "0" && a.substr(16) != "false";

@@ -1,6 +1,7 @@
 // libdawn_b200rt.so — implementation of include/dawn_b200_rt.h (sm_100a).
 #include "../../../include/dawn_b200_rt.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -124,6 +125,40 @@ int b200rt_event_elapsed_ms(void* a, void* b, float* ms) {
 }
 int b200rt_check_last_launch(void) {
   CK(cudaGetLastError());
+  return 0;
+}
+
+int b200rt_tensor_map_3d(void* map, const void* base, int size_i, int size_j, int size_k,
+                         int stride_j, int stride_k, int box_i, int box_j) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if(!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if(qres != cudaDriverEntryPointSuccess || !fn)
+      return b200rt_set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    encode = reinterpret_cast<encode_fn>(fn);
+  }
+  if((reinterpret_cast<uintptr_t>(base) & 15) || (stride_j & 1) || (stride_k & 1) || box_i > 256 ||
+     box_j > 256 || ((box_i * 8) & 15))
+    return b200rt_set_error(B200_ERR_LAYOUT, "b200rt_tensor_map_3d: TMA alignment rules violated");
+  cuuint64_t dims[3] = {(cuuint64_t)size_i, (cuuint64_t)size_j, (cuuint64_t)size_k};
+  cuuint64_t strides[2] = {(cuuint64_t)stride_j * 8, (cuuint64_t)stride_k * 8};
+  cuuint32_t box[3] = {(cuuint32_t)box_i, (cuuint32_t)box_j, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(static_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+                      const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if(r != CUDA_SUCCESS) {
+    char buf[96];
+    std::snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return b200rt_set_error(B200_ERR_CUDA, buf);
+  }
   return 0;
 }
 } // extern "C"

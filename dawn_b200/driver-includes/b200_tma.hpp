@@ -1,0 +1,40 @@
+// Device-side helpers for the TMA shared-memory ring of generated tile kernels (sm_90+ PTX through
+// libcu++'s cuda::ptx wrappers; SASS: UTMALDG / SYNCS).  One elected thread arms an mbarrier with the
+// byte count of a pipeline stage and issues one cp.async.bulk.tensor per staged field; every thread
+// of the block then waits on the barrier's phase parity before reading the stage.
+#pragma once
+#if defined(__CUDACC__)
+#include <cuda.h>
+#include <cuda/ptx>
+#include <cstdint>
+
+namespace dawn_b200 {
+namespace tma {
+
+__device__ __forceinline__ void barrier_init(unsigned long long* bar, unsigned count) {
+  cuda::ptx::mbarrier_init(reinterpret_cast<uint64_t*>(bar), count);
+}
+// make the initialised barriers visible to the async (TMA) proxy
+__device__ __forceinline__ void fence_barrier_init() {
+  cuda::ptx::fence_mbarrier_init(cuda::ptx::sem_release, cuda::ptx::scope_cluster);
+  cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
+}
+__device__ __forceinline__ void expect_bytes(unsigned long long* bar, unsigned bytes) {
+  cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta,
+                                       cuda::ptx::space_shared, reinterpret_cast<uint64_t*>(bar),
+                                       bytes);
+}
+__device__ __forceinline__ void load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                        int c2, unsigned long long* bar) {
+  const int32_t coords[3] = {c0, c1, c2};
+  cuda::ptx::cp_async_bulk_tensor(cuda::ptx::space_cluster, cuda::ptx::space_global, smem_dst, map,
+                                  coords, reinterpret_cast<uint64_t*>(bar));
+}
+__device__ __forceinline__ void wait(unsigned long long* bar, unsigned parity) {
+  while(!cuda::ptx::mbarrier_try_wait_parity(reinterpret_cast<uint64_t*>(bar), parity)) {
+  }
+}
+
+} // namespace tma
+} // namespace dawn_b200
+#endif

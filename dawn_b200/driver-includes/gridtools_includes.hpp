@@ -14,3 +14,5 @@
 #include "b200_runtime.hpp"
 #include "storage.hpp"
 #include "timer_b200.hpp"
+#include "b200_tma.hpp"
+#include <cstdint>

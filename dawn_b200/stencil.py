@@ -175,34 +175,42 @@ class Stencil:
         _rt.check(self.module._run(self.handle, arr, n, ctypes.c_void_p(stream)))
 
     def run_from_host(self, *arrays, stream=None):
-        """End-to-end call with HOST buffers: numpy arrays indexed [k, j, i] in API order (length 1
-        along masked dimensions).  Copies inputs host->device, runs, copies every field the stencil
-        writes back into the given arrays.  Returns (h2d_bytes, d2h_bytes)."""
+        """End-to-end call with HOST buffers in API order, indexed [k, j, i] (length 1 along masked
+        dimensions): numpy arrays, or torch CPU tensors (pinned ones are copied from directly).
+        Copies the inputs host->device, runs, and copies every field the stencil writes back into
+        the given buffers.  Returns (h2d_bytes, d2h_bytes)."""
         import torch
         dom = self.domain
         if self._host_storages is None:
-            self._host_storages = []
-            self._pinned = []
-            for f, a in zip(self.module.fields, arrays):
-                nk = a.shape[0]
-                st = Storage(dom.isize, dom.jsize, nk, f["dims"])
-                self._host_storages.append(st)
-                self._pinned.append(torch.empty(a.shape, dtype=torch.float64).pin_memory())
-        h2d = d2h = 0
-        for st, a, pin in zip(self._host_storages, arrays, self._pinned):
-            pin.copy_(torch.from_numpy(a))
-            st.view().copy_(pin.reshape(st.shape[2], st.shape[1], st.shape[0]), non_blocking=True)
-            h2d += a.nbytes
-        self.run(*self._host_storages, stream=stream)
+            self._host_storages = [Storage(dom.isize, dom.jsize, a.shape[0], f["dims"])
+                                   for f, a in zip(self.module.fields, arrays)]
+            self._pinned = [None] * len(arrays)
         written = self.written_fields()
-        for f, st, a, pin in zip(self.module.fields, self._host_storages, arrays, self._pinned):
+        h2d = d2h = 0
+        staged = []
+        for n, (st, a) in enumerate(zip(self._host_storages, arrays)):
+            if isinstance(a, torch.Tensor) and a.is_pinned():
+                pin = a
+            else:
+                if self._pinned[n] is None:
+                    self._pinned[n] = torch.empty(tuple(a.shape), dtype=torch.float64).pin_memory()
+                pin = self._pinned[n]
+                pin.copy_(a if isinstance(a, torch.Tensor) else torch.from_numpy(a))
+            staged.append(pin)
+            st.view().copy_(pin.reshape(st.shape[2], st.shape[1], st.shape[0]), non_blocking=True)
+            h2d += pin.numel() * 8
+        self.run(*self._host_storages, stream=stream)
+        for f, st, pin in zip(self.module.fields, self._host_storages, staged):
             if f["name"] in written:
                 pin.reshape(st.shape[2], st.shape[1], st.shape[0]).copy_(st.view(), non_blocking=True)
-                d2h += a.nbytes
+                d2h += pin.numel() * 8
         torch.cuda.current_stream().synchronize()
-        for f, a, pin in zip(self.module.fields, arrays, self._pinned):
-            if f["name"] in written:
-                np.copyto(a, pin.numpy())
+        for f, a, pin in zip(self.module.fields, arrays, staged):
+            if f["name"] in written and pin is not a:
+                if isinstance(a, torch.Tensor):
+                    a.copy_(pin)
+                else:
+                    np.copyto(a, pin.numpy())
         return h2d, d2h
 
     def written_fields(self):

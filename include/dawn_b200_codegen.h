@@ -48,6 +48,8 @@ typedef struct dawn_b200_options {
   int unroll_k;          /* k-loop unroll factor */
   int levels_per_thread; /* unstructured: k levels per thread */
   int block_size_ico;    /* unstructured: threads per block */
+  int use_tma;           /* default 1: tile kernels stage read-only inputs through smem with TMA */
+  int tma_stages;        /* depth of the TMA ring over k (0 = default 4) */
 } dawn_b200_options;
 
 /* Fills `opts` with the defaults above. */
