@@ -102,7 +102,8 @@ VARIANTS = {
         dict(block_size_i=32, block_size_j=8, rows_per_thread=2), dict(inline_temporaries=0),
         dict(use_tma=0), dict(tma_stages=2, block_size_k=3), dict(inline_temporaries=0, use_tma=0),
     ],
-    "tridiagonal_solve": [dict(fuse_columns=0)],
+    "tridiagonal_solve": [dict(fuse_columns=0), dict(column_ring=0), dict(column_ring=0, column_cache=1, prefetch_k=3),
+                          dict(ring_levels=2, tma_stages=2), dict(block_size_i=32, block_size_j=2)],
 }
 
 

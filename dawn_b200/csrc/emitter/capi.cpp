@@ -25,6 +25,8 @@ b200::codegen::Options convert(const dawn_b200_options* o) {
   r.UnrollK = o->unroll_k;
   r.LevelsPerThread = o->levels_per_thread, r.BlockSizeIco = o->block_size_ico;
   r.UseTMA = o->use_tma, r.TmaStages = o->tma_stages;
+  r.ColumnCache = o->column_cache, r.PrefetchK = o->prefetch_k;
+  r.ColumnRing = o->column_ring, r.RingLevels = o->ring_levels;
   return r;
 }
 } // namespace
@@ -44,6 +46,8 @@ void dawn_b200_default_options(dawn_b200_options* o) {
   o->inline_temporaries = 1;
   o->fuse_columns = 1;
   o->use_tma = 1;
+  o->column_cache = 0;
+  o->column_ring = 1;
 }
 
 int dawn_b200_parse_backend(const char* s) {

@@ -40,6 +40,10 @@ struct Options {
   int BlockSizeIco = 0;    // unstructured: threads per block
   int UseTMA = 1;          // 1: tile kernels stage their read-only inputs with TMA (when aligned)
   int TmaStages = 0;       // depth of the TMA shared-memory ring over k (0 = planner default 4)
+  int ColumnCache = 0;     // 1: fused column kernels keep sweep-to-sweep fields in shared memory
+  int ColumnRing = 1;      // 1: sequential column kernels stream their inputs through a TMA ring
+  int RingLevels = 0;      // k levels per ring slot (0 = default 4)
+  int PrefetchK = 0;       // register prefetch depth of sequential column loops (0 = default 8)
 };
 
 // TranslationUnit twin (CodeGen/TranslationUnit.h:26-53)

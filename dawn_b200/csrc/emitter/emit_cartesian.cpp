@@ -73,6 +73,8 @@ std::string cType(const std::string& typeId) {
 }
 
 // ------------------------------------------------------------------------------------------------
+bool firstCentreAccessIsWrite(const std::vector<const DoMethod*>& dms, int fid);
+
 struct InlineDef {
   ExprPtr expr; // defining expression of the temporary
 };
@@ -95,6 +97,18 @@ struct KernelPlan {
     int W, H;           // box size in elements (W padded to an even count: 16-byte rows)
     int offset;         // element offset inside one pipeline stage
   };
+  // --- column-cache variant of fused column kernels: fields produced by one sweep and consumed by
+  // a later one stay in shared memory ([field][k][thread]); centre reads of the sequential loops are
+  // software-pipelined `prefetch` levels ahead in registers
+  bool colcache = false;
+  std::vector<int> carried;
+  int prefetch = 0;
+  // --- column-ring variant: the centre reads of sequential sweeps arrive through a TMA ring of
+  // (TI x TJ x ringKB)-level boxes; later sweeps re-read what earlier ones wrote from L2
+  bool colring = false;
+  int ringKB = 4;
+  std::vector<int> ringFields; // every field that may be streamed (tensor-map kernel args)
+  int ringMaxFields = 0;       // largest number of fields streamed by one k range
   bool tma = false;
   std::vector<Staged> staged;
   int stages = 0;
@@ -149,6 +163,12 @@ private:
   std::vector<KernelPlan> planKernels(const Stencil& st);
   void collectUse(KernelPlan& kp) const;
   bool planTma(KernelPlan& kp) const;
+  bool planColumnCache(KernelPlan& kp) const;
+  bool planColumnRing(KernelPlan& kp) const;
+  std::map<int, int> ringDepths(const MultiStage& ms) const;
+  std::set<int> streamedFields(const KernelPlan& kp, const MultiStage& ms, const KRange& part,
+                               const std::map<int, int>& depths) const;
+  std::set<int> fullyWritten(const MultiStage& ms) const;
 
   void emitGlobalsStruct();
   void emitKernel(const Stencil& st, const KernelPlan& kp);
@@ -333,6 +353,137 @@ void CartesianEmitter::collectUse(KernelPlan& kp) const {
             kp.fieldsWritten.insert(e.accessID);
         });
     }
+}
+
+// Fields a multistage writes unconditionally on every level [Start, End].
+std::set<int> CartesianEmitter::fullyWritten(const MultiStage& ms) const {
+  std::map<int, std::vector<std::pair<int, int>>> ivs;
+  for(auto const& stage : ms.stages)
+    for(auto const& dm : stage.doMethods)
+      for(auto const& st : dm.stmts)
+        if(st->kind == Stmt::ExprStmt && st->expr->kind == Expr::Assign &&
+           st->expr->kids[0]->kind == Expr::Field && isStorageField(st->expr->kids[0]->accessID))
+          ivs[st->expr->kids[0]->accessID].push_back(
+              {dm.interval.lowerBound(), dm.interval.upperBound()});
+  std::set<int> out;
+  for(auto& kv : ivs) {
+    std::sort(kv.second.begin(), kv.second.end());
+    int reach = -1;
+    for(auto const& iv : kv.second) {
+      if(iv.first > reach + 1)
+        break;
+      reach = std::max(reach, iv.second);
+    }
+    if(!kv.second.empty() && kv.second.front().first <= 0 && reach >= Interval::End)
+      out.insert(kv.first);
+  }
+  return out;
+}
+
+// Trailing vertical read depth per field of a sequential multistage (register K-cache rings).
+std::map<int, int> CartesianEmitter::ringDepths(const MultiStage& ms) const {
+  std::map<int, int> depth;
+  const bool backward = ms.loopOrder == LoopOrder::Backward;
+  for(auto const& stage : ms.stages)
+    for(auto const& dm : stage.doMethods)
+      analysis::visitStmts(dm.stmts, [&](const Expr& e, bool w) {
+        if(e.kind != Expr::Field || w || inlined_.count(e.accessID))
+          return;
+        int trailing = backward ? e.dk : -e.dk;
+        if(trailing > 0 && maskOf(e.accessID).k)
+          depth[e.accessID] = std::max(depth[e.accessID], trailing);
+      });
+  return depth;
+}
+
+// Fields whose centre value of every level of `part` can be fetched ahead of the sweep: not written
+// by this multistage, or K-cached with a read as first centre access.  Empty for short ranges.
+std::set<int> CartesianEmitter::streamedFields(const KernelPlan& kp, const MultiStage& ms,
+                                               const KRange& part,
+                                               const std::map<int, int>& depths) const {
+  std::set<int> out;
+  if(ms.loopOrder == LoopOrder::Parallel)
+    return out;
+  bool sameLevel =
+      (part.lo >= Interval::End - (1 << 19)) == (part.hi >= Interval::End - (1 << 19));
+  if(sameLevel && (part.hi - part.lo + 1) < 2 * kp.ringKB)
+    return out;
+  std::vector<const DoMethod*> all;
+  std::set<int> writtenInMs;
+  for(auto const& stage : ms.stages) {
+    if(droppedStages_.count(stage.id))
+      continue;
+    StageInfo info = analysis::stageInfo(inst_, stage);
+    for(auto const& fp : info.fields)
+      if(fp.second.written)
+        writtenInMs.insert(fp.first);
+    for(auto const& dm : stage.doMethods)
+      if(dm.interval.overlaps(part.lo, part.hi))
+        all.push_back(&dm);
+  }
+  std::set<int> centreReads;
+  for(auto const* dm : all)
+    analysis::visitStmts(dm->stmts, [&](const Expr& e, bool w) {
+      if(e.kind == Expr::Field && !w && e.di == 0 && e.dj == 0 && e.dk == 0 &&
+         !inlined_.count(e.accessID))
+        centreReads.insert(e.accessID);
+    });
+  for(int f : centreReads) {
+    MaskClass m = maskOf(f);
+    if(!(m.i && m.j && m.k))
+      continue;
+    if(!writtenInMs.count(f) || (depths.count(f) && !firstCentreAccessIsWrite(all, f)))
+      out.insert(f);
+  }
+  return out;
+}
+
+bool CartesianEmitter::planColumnRing(KernelPlan& kp) const {
+  kp.ringKB = opt_.RingLevels > 0 ? opt_.RingLevels : 4;
+  std::set<int> fields;
+  int maxFields = 0;
+  for(auto const* ms : kp.ms) {
+    auto depths = ringDepths(*ms);
+    for(auto const& part : analysis::partition(*ms)) {
+      auto sf = streamedFields(kp, *ms, part, depths);
+      fields.insert(sf.begin(), sf.end());
+      maxFields = std::max(maxFields, (int)sf.size());
+    }
+  }
+  if(fields.empty())
+    return false;
+  kp.colring = true;
+  kp.ringFields.assign(fields.begin(), fields.end());
+  kp.ringMaxFields = maxFields;
+  kp.stages = opt_.TmaStages > 0 ? opt_.TmaStages : 4;
+  kp.TI = opt_.BlockSizeI > 0 ? opt_.BlockSizeI : 32;
+  kp.TJ = opt_.BlockSizeJ > 0 ? opt_.BlockSizeJ : 1;
+  if((kp.TI * 8) % 16 != 0 || kp.TI > 256 || kp.TJ > 256 || kp.ringKB > 256)
+    return false;
+  return true;
+}
+
+// Column-cache twin of a fused column kernel: which fields are handed from one sweep to a later one.
+bool CartesianEmitter::planColumnCache(KernelPlan& kp) const {
+  std::set<int> produced, carried;
+  for(auto const* ms : kp.ms) {
+    for(auto const& stage : ms->stages) {
+      StageInfo info = analysis::stageInfo(inst_, stage);
+      for(auto const& fp : info.fields)
+        if(fp.second.read && produced.count(fp.first) && maskOf(fp.first).i &&
+           maskOf(fp.first).j && maskOf(fp.first).k)
+          carried.insert(fp.first);
+    }
+    for(int f : fullyWritten(*ms))
+      produced.insert(f);
+  }
+  if(carried.empty())
+    return false;
+  kp.colcache = true;
+  kp.carried.assign(carried.begin(), carried.end());
+  kp.TI = 32, kp.TJ = 1, kp.RJ = 1; // one warp per block: 5 blocks/SM at 80 levels x 2 fields
+  kp.prefetch = opt_.PrefetchK > 0 ? opt_.PrefetchK : 8;
+  return true;
 }
 
 // Which inputs of a tile kernel are staged through shared memory by TMA, and with which box.
@@ -528,6 +679,19 @@ std::vector<KernelPlan> CartesianEmitter::planKernels(const Stencil& st) {
               std::to_string(kidx++) + "_kernel";
     collectUse(kp);
     out.push_back(kp);
+    if(opt_.ColumnRing && kp.pointwise && !kp.zchunk) {
+      KernelPlan kr = kp;
+      if(planColumnRing(kr)) {
+        kr.name = kp.name.substr(0, kp.name.size() - 7) + "_ring_kernel";
+        out.push_back(kr);
+      }
+    } else if(opt_.ColumnCache && kp.pointwise && kp.ms.size() > 1) {
+      KernelPlan kc = kp;
+      if(planColumnCache(kc)) {
+        kc.name = kp.name.substr(0, kp.name.size() - 7) + "_cc_kernel";
+        out.push_back(kc);
+      }
+    }
     if(opt_.UseTMA && !kp.pointwise) {
       KernelPlan kt = kp;
       if(planTma(kt)) {
@@ -568,6 +732,20 @@ public:
   bool backward = false;
   int rows = 1;
   bool rowGuards = false; // tile kernels: loads/stores predicated on the validity of their row
+  std::set<int> ccRead;     // carried fields already produced: read from the shared column cache
+  std::set<int> ccWrite;    // carried fields: every write also updates the column cache
+  std::set<int> prefetched; // fields whose centre value of this level sits in a prefetch register
+
+  std::string ccAddress(int id, int dk) const {
+    return "cc_" + fieldName(id) + "[(k + (" + std::to_string(dk) + ")) * " +
+           std::to_string(kp.NT()) + " + tid]";
+  }
+  // value of field `id` at vertical offset dk of the thread's own column, from wherever it lives
+  std::string columnRead(int id, int dk) const {
+    if(ccRead.count(id))
+      return ccAddress(id, dk);
+    return address(id, 0, 0, dk);
+  }
 
   // per micro-tile state
   std::vector<std::string> loads; // hoisted loads (read-only fields)
@@ -588,9 +766,9 @@ public:
   std::string fieldName(int id) const { return cIdent(inst.nameOf(id)); }
 
   // address expression of field `id` at (di, dj_abs (relative to micro-tile base row), dk)
-  std::string address(int id, int di, int djAbs, int dk) const {
+  std::string address(int id, int di, int djAbs, int dk, const std::string& base = "b") const {
     MaskClass m = maskOf(id);
-    std::string a = fieldName(id) + "_p[b" + m.tag();
+    std::string a = fieldName(id) + "_p[" + base + m.tag();
     if(m.i && di)
       a += " + (" + std::to_string(di) + ")";
     if(m.j && djAbs)
@@ -630,6 +808,10 @@ public:
       if(trailing >= 0 && trailing <= rg->second.depth)
         return fieldName(e.accessID) + "_kc" + std::to_string(trailing);
     }
+    if(di == 0 && djAbs == 0 && dk == 0 && prefetched.count(e.accessID))
+      return "pfv_" + fieldName(e.accessID);
+    if(di == 0 && djAbs == 0 && ccRead.count(e.accessID))
+      return ccAddress(e.accessID, dk);
     bool readOnly = !kp.fieldsWritten.count(e.accessID);
     const KernelPlan::Staged* sg = kp.tma ? kp.stagedOf(e.accessID) : nullptr;
     if(sg && dk == 0) {
@@ -750,6 +932,19 @@ public:
         std::string r0 = fieldName(lhs.accessID) + "_kc0";
         out.push_back(pad + r0 + " " + s->expr->op + " " + rhs + ";");
         out.push_back(pad + address(lhs.accessID, 0, curRow, 0) + " = " + r0 + ";");
+        if(ccWrite.count(lhs.accessID))
+          out.push_back(pad + ccAddress(lhs.accessID, 0) + " = " + r0 + ";");
+      } else if(ccWrite.count(lhs.accessID)) {
+        std::string tmp = "ccv_" + fieldName(lhs.accessID);
+        std::string cur = ccRead.count(lhs.accessID) ? ccAddress(lhs.accessID, 0)
+                                                     : address(lhs.accessID, 0, curRow, 0);
+        if(s->expr->op == "=")
+          out.push_back(pad + "{ const ::dawn::float_type " + tmp + " = " + rhs + ";");
+        else
+          out.push_back(pad + "{ const ::dawn::float_type " + tmp + " = " + cur + " " +
+                        s->expr->op.substr(0, 1) + " " + rhs + ";");
+        out.push_back(pad + "  " + address(lhs.accessID, 0, curRow, 0) + " = " + tmp + ";");
+        out.push_back(pad + "  " + ccAddress(lhs.accessID, 0) + " = " + tmp + "; }");
       } else {
         out.push_back(pad + address(lhs.accessID, 0, curRow, 0) + " " + s->expr->op + " " + rhs +
                       ";");
@@ -867,6 +1062,8 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
   }
   for(auto const& sg : kp.staged)
     os_ << ",\n    const __grid_constant__ CUtensorMap tm_" << fname(sg.field);
+  for(int f : kp.ringFields)
+    os_ << ",\n    const __grid_constant__ CUtensorMap tm_" << fname(f);
   os_ << ") {\n";
   os_ << "  const int tid = threadIdx.x;\n";
   os_ << "  const int i0 = blockIdx.x * " << kp.TI << ";\n";
@@ -880,7 +1077,8 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
   size_t tmaBytes = 0;
   for(auto const& sg : kp.staged)
     tmaBytes += (size_t)sg.W * sg.H * 8;
-  if(kp.tma) {
+  const int ringSlotElems = kp.ringMaxFields * kp.ringKB * kp.NT();
+  if(kp.tma || kp.colring) {
     os_ << "  extern __shared__ __align__(128) unsigned char b200_smem[];\n";
     os_ << "  unsigned long long* tma_full = reinterpret_cast<unsigned long long*>(b200_smem);\n";
     os_ << "  ::dawn::float_type* tma_ring = reinterpret_cast<::dawn::float_type*>(b200_smem + 128);\n";
@@ -909,16 +1107,17 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
     os_ << pad << "}\n";
   };
 
-  auto emitIndexBases = [&](const std::string& pad) {
+  auto emitIndexBases = [&](const std::string& pad, const std::string& prefix = "b",
+                            const std::string& kname = "k") {
     for(auto const& c : classes) {
       MaskClass m{c[0] == '1', c[1] == '1', c[2] == '1'};
-      os_ << pad << "const int b" << c << " = 0";
+      os_ << pad << "const int " << prefix << c << " = 0";
       if(m.i)
         os_ << " + i";
       if(m.j)
         os_ << " + jb * " << m.sj();
       if(m.k)
-        os_ << " + k * " << m.sk();
+        os_ << " + " << kname << " * " << m.sk();
       os_ << ";\n";
     }
   };
@@ -926,8 +1125,19 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
   if(kp.pointwise) {
     os_ << "  const int i = i0 + tid % " << kp.TI << ";\n";
     os_ << "  const int jb = j0 + tid / " << kp.TI << ";\n";
-    os_ << "  if(i >= nx || jb >= ny)\n    return;\n";
+    if(kp.colring)
+      os_ << "  const bool active = i < nx && jb < ny; // no early exit: the block synchronises\n";
+    else
+      os_ << "  if(i >= nx || jb >= ny)\n    return;\n";
   }
+  if(kp.colcache) {
+    os_ << "  extern __shared__ ::dawn::float_type cc_smem[]; // [field][k][thread]\n";
+    for(size_t c = 0; c < kp.carried.size(); ++c)
+      os_ << "  ::dawn::float_type* cc_" << fname(kp.carried[c]) << " = cc_smem + (size_t)" << c
+          << " * nz * " << kp.NT() << ";\n";
+  }
+  std::set<int> producedSoFar;
+  std::set<int> writtenSoFar; // fields stored by earlier multistages of this kernel
 
   for(auto const* ms : kp.ms) {
     bool backward = ms->loopOrder == LoopOrder::Backward;
@@ -937,6 +1147,14 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
     os_ << "  {\n";
     be.backward = backward;
     be.rings.clear();
+    be.ccRead.clear();
+    be.ccWrite.clear();
+    if(kp.colcache)
+      for(int f : kp.carried) {
+        be.ccWrite.insert(f);
+        if(producedSoFar.count(f))
+          be.ccRead.insert(f);
+      }
     // ---- register rings (K-caches) for column kernels --------------------------------------
     if(kp.pointwise && sequential) {
       std::map<int, int> depth;
@@ -959,6 +1177,17 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
     }
     auto parts = analysis::partition(*ms);
     bool first = true;
+    std::map<int, int> msDepths = ringDepths(*ms);
+    if(kp.colring) {
+      bool needFence = false;
+      for(auto const& part : parts)
+        for(int f : streamedFields(kp, *ms, part, msDepths))
+          needFence = needFence || writtenSoFar.count(f);
+      if(needFence)
+        os_ << "    // this sweep streams (async proxy) what an earlier sweep stored (generic proxy)\n"
+            << "    __threadfence_block();\n    ::dawn_b200::tma::fence_proxy_async();\n"
+            << "    __syncthreads();\n";
+    }
     for(auto const& part : parts) {
       os_ << "    { // k in [" << analysis::boundExpr(part.lo) << ", "
           << analysis::boundExpr(part.hi) << "]\n";
@@ -971,20 +1200,55 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
       }
       // ring pre-fill at the first level the multistage touches
       if(first && !be.rings.empty()) {
-        os_ << "      if(kb <= ke) {\n";
+        os_ << "      if(" << (kp.colring ? "active && " : "") << "kb <= ke) {\n";
         os_ << "        const int k = " << (backward ? "ke" : "kb") << ";\n";
         emitIndexBases("        ");
         for(auto const& r : be.rings)
           for(int n = 1; n <= r.second.depth; ++n) {
             int dk = backward ? n : -n;
             os_ << "        if(k + (" << dk << ") >= 0 && k + (" << dk << ") <= kmax) "
-                << fname(r.first) << "_kc" << n << " = " << be.address(r.first, 0, 0, dk)
-                << ";\n";
+                << fname(r.first) << "_kc" << n << " = " << be.columnRead(r.first, dk) << ";\n";
           }
         os_ << "      }\n";
       }
       first = false;
       int unroll = opt_.UnrollK > 0 ? opt_.UnrollK : (sequential ? 4 : 1);
+      // ---- register prefetch of the centre reads of this range (column-cache kernels) ------------
+      be.prefetched.clear();
+      bool usePrefetch = false;
+      bool useRing = false;
+      if(kp.colring) {
+        be.prefetched = streamedFields(kp, *ms, part, msDepths);
+        useRing = !be.prefetched.empty();
+      }
+      if(!kp.colring && kp.pointwise && sequential && kp.prefetch > 0) {
+        bool sameLevel = (part.lo >= Interval::End - (1 << 19)) == (part.hi >= Interval::End - (1 << 19));
+        bool shortRange = sameLevel && (part.hi - part.lo + 1) < 2 * kp.prefetch;
+        if(!shortRange) {
+          std::vector<const DoMethod*> all;
+          for(auto const& stage : ms->stages)
+            if(!droppedStages_.count(stage.id))
+              for(auto const& dm : stage.doMethods)
+                if(dm.interval.overlaps(part.lo, part.hi))
+                  all.push_back(&dm);
+          std::set<int> centreReads;
+          for(auto const* dm : all)
+            analysis::visitStmts(dm->stmts, [&](const Expr& e, bool w) {
+              if(e.kind == Expr::Field && !w && e.di == 0 && e.dj == 0 && e.dk == 0 &&
+                 !inlined_.count(e.accessID) && maskOf(e.accessID).k)
+                centreReads.insert(e.accessID);
+            });
+          for(int f : centreReads) {
+            if(be.ccRead.count(f))
+              continue;
+            bool ring = be.rings.count(f) > 0;
+            bool readOnly = !kp.fieldsWritten.count(f);
+            if(readOnly || (ring && !firstCentreAccessIsWrite(all, f)))
+              be.prefetched.insert(f);
+          }
+          usePrefetch = !be.prefetched.empty();
+        }
+      }
       if(kp.tma) {
         const std::string kOf = backward ? "ke - " : "kb + ";
         os_ << "      const int nk_loc = ke - kb + 1;\n";
@@ -1004,7 +1268,81 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         for(auto const& sg : kp.staged)
           os_ << "        const ::dawn::float_type* s_" << fname(sg.field) << " = tma_ring + tcur * "
               << kp.stageElems << " + " << sg.offset << ";\n";
+      } else if(useRing) {
+        const int KB = kp.ringKB, S = kp.stages, NT = kp.NT();
+        const size_t bytes = (size_t)be.prefetched.size() * KB * NT * 8;
+        auto issue = [&](const std::string& pad, const std::string& chunk) {
+          os_ << pad << "{\n";
+          os_ << pad << "  const unsigned ts = (tma_it + " << chunk << ") % " << S << ";\n";
+          os_ << pad << "  const int k0 = "
+              << (backward ? "ke - (" + chunk + ") * " + std::to_string(KB) + " - " +
+                                 std::to_string(KB - 1)
+                           : "kb + (" + chunk + ") * " + std::to_string(KB))
+              << ";\n";
+          os_ << pad << "  ::dawn_b200::tma::expect_bytes(&tma_full[ts], " << bytes << "u);\n";
+          int fi = 0;
+          for(int f : be.prefetched) {
+            os_ << pad << "  ::dawn_b200::tma::load_3d(tma_ring + ts * " << ringSlotElems << " + "
+                << fi * KB * NT << ", &tm_" << fname(f) << ", i0, j0, k0, &tma_full[ts]);\n";
+            ++fi;
+          }
+          os_ << pad << "}\n";
+        };
+        os_ << "      const int nk_loc = ke - kb + 1;\n";
+        os_ << "      const int nch = nk_loc > 0 ? (nk_loc + " << KB - 1 << ") / " << KB << " : 0;\n";
+        os_ << "      if(tid == 0) {\n";
+        os_ << "        for(int c = 0; c < " << S - 1 << " && c < nch; ++c)\n";
+        issue("          ", "c");
+        os_ << "      }\n";
+        os_ << "      for(int ch = 0; ch < nch; ++ch) {\n";
+        os_ << "        if(tid == 0 && ch + " << S - 1 << " < nch)\n";
+        issue("          ", "ch + " + std::to_string(S - 1));
+        os_ << "        const unsigned tcur = (tma_it + ch) % " << S << ";\n";
+        os_ << "        ::dawn_b200::tma::wait(&tma_full[tcur], ((tma_it + ch) / " << S << ") & 1u);\n";
+        os_ << "        const ::dawn::float_type* slot = tma_ring + tcur * " << ringSlotElems << ";\n";
+        os_ << "#pragma unroll\n";
+        os_ << "      for(int q = 0; q < " << KB << "; ++q) {\n";
+        os_ << "      const int k = " << (backward ? "ke - ch * " : "kb + ch * ") << KB
+            << (backward ? " - q" : " + q") << ";\n";
+        os_ << "      if(active && " << (backward ? "k >= kb" : "k <= ke") << ") {\n";
+      } else if(usePrefetch) {
+        const int P = kp.prefetch;
+        const std::string sgn = backward ? "-" : "+";
+        const std::string inRange = backward ? "k >= kb" : "k <= ke";
+        os_ << "      ::dawn::float_type";
+        {
+          bool firstPf = true;
+          for(int f : be.prefetched) {
+            os_ << (firstPf ? " " : ", ") << "pf_" << fname(f) << "[" << P << "]";
+            firstPf = false;
+          }
+        }
+        os_ << ";\n";
+        os_ << "#pragma unroll\n";
+        os_ << "      for(int q = 0; q < " << P << "; ++q) {\n";
+        // levels past the end of the range are clamped (loaded, never used): an unconditional load
+        // lets the compiler keep one live register per slot instead of a select on the loaded value
+        os_ << "        const int k = " << (backward ? "(ke - q > kb ? ke - q : kb)" : "(kb + q < ke ? kb + q : ke)")
+            << ";\n";
+        os_ << "        if(kb <= ke) {\n";
+        emitIndexBases("          ");
+        for(int f : be.prefetched)
+          os_ << "          pf_" << fname(f) << "[q] = "
+              << (kp.fieldsWritten.count(f) ? be.address(f, 0, 0, 0)
+                                            : "__ldg(&" + be.address(f, 0, 0, 0) + ")")
+              << ";\n";
+        os_ << "        }\n      }\n";
+        if(backward)
+          os_ << "      for(int k0 = ke; k0 >= kb; k0 -= " << P << ") {\n";
+        else
+          os_ << "      for(int k0 = kb; k0 <= ke; k0 += " << P << ") {\n";
+        os_ << "#pragma unroll\n";
+        os_ << "      for(int q = 0; q < " << P << "; ++q) {\n";
+        os_ << "      const int k = k0 " << sgn << " q;\n";
+        os_ << "      if(" << inRange << ") {\n";
       } else {
+        if(kp.colring)
+          os_ << "      if(active)\n";
         os_ << "#pragma unroll " << unroll << "\n";
         if(backward)
           os_ << "      for(int k = ke; k >= kb; --k) {\n";
@@ -1073,8 +1411,43 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
             for(auto const& dm : sg->doMethods)
               if(dm.interval.overlaps(part.lo, part.hi))
                 all.push_back(&dm);
+          if(be.prefetched.count(r.first))
+            continue; // filled from the prefetch register below
           if(!firstCentreAccessIsWrite(all, r.first))
-            os_ << pad << fname(r.first) << "_kc0 = " << be.address(r.first, 0, 0, 0) << ";\n";
+            os_ << pad << fname(r.first) << "_kc0 = " << be.columnRead(r.first, 0) << ";\n";
+        }
+        if(useRing && sn == 0) {
+          int fi = 0;
+          for(int f : be.prefetched) {
+            os_ << pad << "const ::dawn::float_type pfv_" << fname(f) << " = slot[("
+                << fi * kp.ringKB << " + " << (backward ? std::to_string(kp.ringKB - 1) + " - q" : "q")
+                << ") * " << kp.NT() << " + tid];\n";
+            ++fi;
+          }
+          for(auto const& r : be.rings)
+            if(be.prefetched.count(r.first))
+              os_ << pad << fname(r.first) << "_kc0 = pfv_" << fname(r.first) << ";\n";
+        }
+        if(usePrefetch && sn == 0) {
+          const int P = kp.prefetch;
+          for(int f : be.prefetched)
+            os_ << pad << "const ::dawn::float_type pfv_" << fname(f) << " = pf_" << fname(f)
+                << "[q];\n";
+          os_ << pad << "{\n";
+          os_ << pad << "  const int kn = "
+              << (backward ? "(k - " + std::to_string(P) + " > kb ? k - " + std::to_string(P) + " : kb)"
+                           : "(k + " + std::to_string(P) + " < ke ? k + " + std::to_string(P) + " : ke)")
+              << ";\n";
+          emitIndexBases(pad + "  ", "n", "kn");
+          for(int f : be.prefetched) {
+            std::string a = be.address(f, 0, 0, 0, "n");
+            os_ << pad << "  pf_" << fname(f) << "[q] = "
+                << (kp.fieldsWritten.count(f) ? a : "__ldg(&" + a + ")") << ";\n";
+          }
+          os_ << pad << "}\n";
+          for(auto const& r : be.rings)
+            if(be.prefetched.count(r.first))
+              os_ << pad << fname(r.first) << "_kc0 = pfv_" << fname(r.first) << ";\n";
         }
         be.reset();
         std::vector<std::vector<std::string>> rowLines(rows);
@@ -1142,11 +1515,27 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
       else if(!kp.pointwise && live.size() > 1 && sequential)
         os_ << "        __syncthreads();\n";
       os_ << "      }\n";
+      if(usePrefetch)
+        os_ << "      }\n      }\n";
+      if(useRing) {
+        os_ << "      }\n"; // q loop
+        os_ << "        __syncthreads(); // slot consumed by every thread before it is refilled\n";
+        os_ << "      }\n"; // chunk loop
+        os_ << "      tma_it += (unsigned)nch;\n";
+      }
       if(kp.tma)
         os_ << "      tma_it += nk_loc > 0 ? (unsigned)nk_loc : 0u;\n";
       os_ << "    }\n";
     }
     os_ << "  }\n";
+    for(int f : fullyWritten(*ms))
+      producedSoFar.insert(f);
+    for(auto const& stage : ms->stages) {
+      StageInfo info = analysis::stageInfo(inst_, stage);
+      for(auto const& fp : info.fields)
+        if(fp.second.written)
+          writtenSoFar.insert(fp.first);
+    }
   }
   os_ << "}\n\n";
 }
@@ -1312,22 +1701,28 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
         classRep["111"] = -1;
       }
     }
-    auto emitLaunch = [&](const KernelPlan& kp, const std::string& pad) {
+    auto emitLaunch = [&](const KernelPlan& kp, const std::string& pad,
+                          const std::string& smemExpr = "") {
       os_ << pad << "const int kchunk = " << kp.KC << ";\n";
       os_ << pad << "dim3 grid((nx + " << kp.TI - 1 << ") / " << kp.TI << ", (ny + "
           << kp.tileJ() - 1 << ") / " << kp.tileJ() << ", "
           << (kp.zchunk ? "(nz + kchunk - 1) / kchunk" : "1") << ");\n";
       size_t smem = kp.tma ? 128 + (size_t)kp.stages * kp.stageElems * 8 : 0;
-      if(kp.tma) {
+      if(kp.colring)
+        smem = 128 + (size_t)kp.stages * kp.ringMaxFields * kp.ringKB * kp.NT() * 8;
+      if(kp.tma || kp.colring) {
         os_ << pad << "static bool smem_set = false;\n";
         os_ << pad << "if(!smem_set) {\n";
         os_ << pad << "  cudaError_t ae = cudaFuncSetAttribute(reinterpret_cast<const void*>(&" << kp.name
             << "), cudaFuncAttributeMaxDynamicSharedMemorySize, " << smem << ");\n";
         os_ << pad << "  if(ae != cudaSuccess) return ::dawn_b200::set_error(B200_ERR_CUDA, "
             << "cudaGetErrorString(ae));\n";
+        os_ << pad << "  cudaFuncSetAttribute(reinterpret_cast<const void*>(&" << kp.name
+            << "), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);\n";
         os_ << pad << "  smem_set = true;\n" << pad << "}\n";
       }
-      os_ << pad << kp.name << "<<<grid, " << kp.NT() << ", " << smem << ", stream>>>(";
+      os_ << pad << kp.name << "<<<grid, " << kp.NT() << ", "
+          << (smemExpr.empty() ? std::to_string(smem) : smemExpr) << ", stream>>>(";
       if(kp.usesGlobals)
         os_ << "m_globals, ";
       os_ << "nx, ny, nz, kchunk";
@@ -1342,14 +1737,55 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
         os_ << ", " << fname(f) << "_p";
       for(auto const& sg : kp.staged)
         os_ << ", tm_" << fname(sg.field);
+      for(int f : kp.ringFields)
+        os_ << ", tm_" << fname(f);
       os_ << ");\n";
       os_ << pad << "++m_launches;\n";
     };
     for(size_t n = 0; n < kps.size(); ++n) {
       const KernelPlan& kp = kps[n];
       const KernelPlan* twin = (n + 1 < kps.size() && kps[n + 1].tma) ? &kps[n + 1] : nullptr;
+      const KernelPlan* cc = (n + 1 < kps.size() && kps[n + 1].colcache) ? &kps[n + 1] : nullptr;
+      const KernelPlan* ring = (n + 1 < kps.size() && kps[n + 1].colring) ? &kps[n + 1] : nullptr;
       os_ << "      {\n";
-      if(twin) {
+      if(ring) {
+        os_ << "        bool ring_ok = m_use_tma && sj_111 % 2 == 0 && sk_111 % 2 == 0";
+        for(int f : ring->ringFields)
+          os_ << " && (reinterpret_cast<uintptr_t>(" << fname(f) << "_p) % 16 == 0)";
+        os_ << ";\n";
+        for(int f : ring->ringFields)
+          os_ << "        alignas(64) CUtensorMap tm_" << fname(f) << ";\n";
+        os_ << "        if(ring_ok) {\n";
+        for(int f : ring->ringFields)
+          os_ << "          if(b200rt_tensor_map_3d(&tm_" << fname(f) << ", " << fname(f)
+              << "_p, nx, ny, nz, sj_111, sk_111, " << ring->TI << ", " << ring->TJ << ", "
+              << ring->ringKB << ")) ring_ok = false;\n";
+        os_ << "        }\n";
+        os_ << "        if(ring_ok) {\n";
+        emitLaunch(*ring, "          ");
+        os_ << "        } else {\n";
+        emitLaunch(kp, "          ");
+        os_ << "        }\n";
+        ++n;
+      } else if(cc) {
+        os_ << "        const size_t cc_bytes = (size_t)" << cc->carried.size() << " * nz * "
+            << cc->NT() << " * sizeof(::dawn::float_type);\n";
+        os_ << "        if(m_use_colcache && cc_bytes <= 200 * 1024) {\n";
+        os_ << "          static size_t cc_set = 0;\n";
+        os_ << "          if(cc_bytes > cc_set) {\n";
+        os_ << "            cudaFuncSetAttribute(reinterpret_cast<const void*>(&" << cc->name
+            << "), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);\n";
+        os_ << "            cudaError_t ae = cudaFuncSetAttribute(reinterpret_cast<const void*>(&"
+            << cc->name << "), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc_bytes);\n";
+        os_ << "            if(ae != cudaSuccess) return ::dawn_b200::set_error(B200_ERR_CUDA, "
+               "cudaGetErrorString(ae));\n";
+        os_ << "            cc_set = cc_bytes;\n          }\n";
+        emitLaunch(*cc, "          ", "cc_bytes");
+        os_ << "        } else {\n";
+        emitLaunch(kp, "          ", "");
+        os_ << "        }\n";
+        ++n;
+      } else if(twin) {
         // TMA needs 16-byte aligned rows: interior origin 16 B aligned, even j/k strides
         os_ << "        bool tma_ok = m_use_tma && sj_111 % 2 == 0 && sk_111 % 2 == 0";
         for(auto const& sg : twin->staged)
@@ -1366,7 +1802,7 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
           os_ << "          if(b200rt_tensor_map_3d(&tm_" << fname(sg.field) << ", " << fname(sg.field)
               << "_p - " << EI << " - (ptrdiff_t)" << EJ << " * sj_111, " << EI
               << " + nx + (int)m_dom.iplus(), " << EJ << " + ny + (int)m_dom.jplus(), nz, sj_111, "
-              << "sk_111, " << sg.W << ", " << sg.H << ")) tma_ok = false;\n";
+              << "sk_111, " << sg.W << ", " << sg.H << ", 1)) tma_ok = false;\n";
         }
         os_ << "        }\n";
         os_ << "        if(tma_ok) {\n";
@@ -1384,6 +1820,7 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
     os_ << "    }\n";
     os_ << "    long m_launches = 0;\n";
     os_ << "    bool m_use_tma = true;\n";
+    os_ << "    bool m_use_colcache = true;\n";
     // ---- storage path ----
     os_ << "\n    void run(";
     for(size_t a = 0; a < sargs.size(); ++a)

@@ -43,6 +43,8 @@ int main(int argc, char** argv) {
             intOpt(a, "levels-per-thread", opts.LevelsPerThread) ||
             intOpt(a, "block-size-ico", opts.BlockSizeIco) || intOpt(a, "use-tma", opts.UseTMA) ||
             intOpt(a, "tma-stages", opts.TmaStages) ||
+            intOpt(a, "column-cache", opts.ColumnCache) || intOpt(a, "prefetch-k", opts.PrefetchK) ||
+            intOpt(a, "column-ring", opts.ColumnRing) || intOpt(a, "ring-levels", opts.RingLevels) ||
             intOpt(a, "max-blocks-sm", opts.MaxBlocksPerSM) ||
             intOpt(a, "max-halo-points", opts.MaxHaloSize)) {
     } else if(a.compare(0, 16, "--run-with-sync=") == 0)

@@ -129,7 +129,7 @@ int b200rt_check_last_launch(void) {
 }
 
 int b200rt_tensor_map_3d(void* map, const void* base, int size_i, int size_j, int size_k,
-                         int stride_j, int stride_k, int box_i, int box_j) {
+                         int stride_j, int stride_k, int box_i, int box_j, int box_k) {
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                 const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -144,11 +144,11 @@ int b200rt_tensor_map_3d(void* map, const void* base, int size_i, int size_j, in
     encode = reinterpret_cast<encode_fn>(fn);
   }
   if((reinterpret_cast<uintptr_t>(base) & 15) || (stride_j & 1) || (stride_k & 1) || box_i > 256 ||
-     box_j > 256 || ((box_i * 8) & 15))
+     box_j > 256 || box_k > 256 || box_k < 1 || ((box_i * 8) & 15))
     return b200rt_set_error(B200_ERR_LAYOUT, "b200rt_tensor_map_3d: TMA alignment rules violated");
   cuuint64_t dims[3] = {(cuuint64_t)size_i, (cuuint64_t)size_j, (cuuint64_t)size_k};
   cuuint64_t strides[2] = {(cuuint64_t)stride_j * 8, (cuuint64_t)stride_k * 8};
-  cuuint32_t box[3] = {(cuuint32_t)box_i, (cuuint32_t)box_j, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_i, (cuuint32_t)box_j, (cuuint32_t)box_k};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = encode(static_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
                       const_cast<void*>(base), dims, strides, box, estr,

@@ -19,6 +19,8 @@ __device__ __forceinline__ void fence_barrier_init() {
   cuda::ptx::fence_mbarrier_init(cuda::ptx::sem_release, cuda::ptx::scope_cluster);
   cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
 }
+// orders this thread's earlier generic-proxy writes before later async-proxy (TMA) reads
+__device__ __forceinline__ void fence_proxy_async() { cuda::ptx::fence_proxy_async(); }
 __device__ __forceinline__ void expect_bytes(unsigned long long* bar, unsigned bytes) {
   cuda::ptx::mbarrier_arrive_expect_tx(cuda::ptx::sem_release, cuda::ptx::scope_cta,
                                        cuda::ptx::space_shared, reinterpret_cast<uint64_t*>(bar),

@@ -50,6 +50,10 @@ typedef struct dawn_b200_options {
   int block_size_ico;    /* unstructured: threads per block */
   int use_tma;           /* default 1: tile kernels stage read-only inputs through smem with TMA */
   int tma_stages;        /* depth of the TMA ring over k (0 = default 4) */
+  int column_cache;      /* default 0: fused solver sweeps hand fields over through shared memory */
+  int column_ring;       /* default 1: sequential column kernels stream inputs through a TMA ring */
+  int ring_levels;       /* k levels per ring slot (0 = default 4) */
+  int prefetch_k;        /* register prefetch depth of sequential column loops (0 = default 8) */
 } dawn_b200_options;
 
 /* Fills `opts` with the defaults above. */

@@ -74,10 +74,10 @@ int b200rt_event_elapsed_ms(void* start, void* stop, float* ms);
 int b200rt_check_last_launch(void); /* cudaGetLastError -> B200_ERR_CUDA */
 
 /* Encodes a CUtensorMap (128 bytes, 64-byte aligned, written to `map`) for TMA loads of
- * (box_i x box_j x 1) boxes of doubles out of a 3-D field: `base` must be 16-byte aligned and both
- * strides (in elements) even.  Out-of-range box elements are zero-filled and never read. */
+ * (box_i x box_j x box_k) boxes of doubles out of a 3-D field: `base` must be 16-byte aligned and
+ * both strides (in elements) even.  Out-of-range box elements are zero-filled and never read. */
 int b200rt_tensor_map_3d(void* map, const void* base, int size_i, int size_j, int size_k,
-                         int stride_j, int stride_k, int box_i, int box_j);
+                         int stride_j, int stride_k, int box_i, int box_j, int box_k);
 
 /* VerificationMetrics twin (driver-includes/verification_metrics.hpp:3-10), computed in ONE pass
  * over the two device arrays (the reference runs 2 kernels + 8 thrust reductions + 2 cudaMallocs per

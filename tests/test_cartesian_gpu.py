@@ -69,13 +69,37 @@ def test_tridiagonal_solve(I, J, K):
     assert bit_equal(got["c"], want["c"])
 
 
-def test_tridiagonal_unfused_matches():
-    I, J, K = 40, 33, 12
+@pytest.mark.parametrize("opts", [dict(fuse_columns=0), dict(column_ring=0),
+                                  dict(column_ring=0, column_cache=1, prefetch_k=3),
+                                  dict(ring_levels=2, tma_stages=2),
+                                  dict(block_size_i=32, block_size_j=2)])
+@pytest.mark.parametrize("K", [1, 2, 12, 37])
+def test_tridiagonal_planner_variants(opts, K):
+    I, J = 40, 33
     f = tridiagonal_inputs(I, J, K)
     dom = (I + 2 * HALO, J + 2 * HALO, K)
     want = run_oracle("tridiagonal_solve", dom, f)
-    got = _run_gpu("tridiagonal_solve", dom, f, ["d", "a", "b", "c"], fuse_columns=0)
+    got = _run_gpu("tridiagonal_solve", dom, f, ["d", "a", "b", "c"], **opts)
     assert bit_equal(got["d"], want["d"]) and bit_equal(got["c"], want["c"])
+
+
+def test_tridiagonal_known_answer():
+    # reference known-answer: a=b=k+1... ToylibIntegrationTestCompareOutput.cpp:343-376 uses
+    # a = b = 1 .. (cells); here the Cartesian analogue: a=k+1, b=k+1 (+diag), c=k+2, d chosen so
+    # that the solution of the tridiagonal system is x[k] = k+1.
+    I, J, K = 16, 8, 5
+    ni, nj = I + 2 * HALO, J + 2 * HALO
+    k = np.arange(K + 1, dtype=float)[:, None, None] * np.ones((K + 1, nj, ni))
+    a, b, c = k + 1.0, k + 1.0, k + 2.0
+    x = k + 1.0
+    d = b * x
+    d[1:] += a[1:] * x[:-1]
+    d[:K - 1] += c[:K - 1] * x[1:K]
+    f = {"d": d, "a": a, "b": b, "c": c}
+    dom = (ni, nj, K)
+    got = _run_gpu("tridiagonal_solve", dom, f, ["d", "a", "b", "c"])
+    sol = got["d"][:K, HALO:-HALO, HALO:-HALO]
+    assert np.allclose(sol, x[:K, HALO:-HALO, HALO:-HALO], rtol=0, atol=1e3 * np.finfo(float).eps * K)
 
 
 @pytest.mark.parametrize("name,order", [
