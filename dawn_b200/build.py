@@ -107,6 +107,15 @@ VARIANTS = {
 }
 
 
+# optimized IIR fixtures shipped by the reference itself: compiled where they lie when the reference
+# tree is present (build container); only the built modules travel to the GPU box
+REFERENCE_IIR = {
+    "update_dz_c": "dawn/test/unit-test/dawn/CodeGen/input/update_dz_c.iir",
+    "conditional_stencil": "dawn/test/unit-test/dawn/CodeGen/input/conditional_stencil.iir",
+}
+REFERENCE_ROOT = "/root/reference"
+
+
 def variant_tag(options):
     return "_".join("%s%s" % (k[:2] + k.split("_")[-1][:1], v) for k, v in sorted(options.items()))
 
@@ -135,6 +144,17 @@ def build_all(force=False):
         for opts in VARIANTS.get(name, []):
             vcode = codegen.compile_iir(iir, backend=backend, **opts)
             built.append(compile_module(name, vcode, tag=variant_tag(opts), force=force))
+    for name, rel in REFERENCE_IIR.items():
+        path = os.path.join(REFERENCE_ROOT, rel)
+        if not os.path.exists(path):
+            continue
+        with open(path) as f:
+            iir = f.read()
+        built.append(compile_module(name, codegen.compile_iir(iir, backend="b200"), tag="ref",
+                                    force=force))
+        built.append(compile_module(name, codegen.compile_iir(iir, backend="b200", use_tma=0,
+                                                              inline_temporaries=0),
+                                    tag="ref_plain", force=force))
     return built
 
 

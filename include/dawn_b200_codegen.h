@@ -52,7 +52,7 @@ typedef struct dawn_b200_options {
   int tma_stages;        /* depth of the TMA ring over k (0 = default 4) */
   int column_cache;      /* default 0: fused solver sweeps hand fields over through shared memory */
   int column_ring;       /* default 1: sequential column kernels stream inputs through a TMA ring */
-  int ring_levels;       /* k levels per ring slot (0 = default 4) */
+  int ring_levels;       /* k levels per ring slot (0 = default 8) */
   int prefetch_k;        /* register prefetch depth of sequential column loops (0 = default 8) */
 } dawn_b200_options;
 

@@ -50,6 +50,6 @@ int ref_verify(int ni, int nj, int nk, int nk_alloc, int halo, double precision,
   verifier verif(dom, precision);
   meta_data_t md(ni, nj, nk_alloc);
   storage_t sa = refw::wrap_in(md, a, "a"), sb = refw::wrap_in(md, b, "b");
-  return verif.verify(sa, sb) ? 1 : 0;
+  return verif.verify(sa, sb, /*max_erros=*/0) ? 1 : 0; // 0: keep the reference from printing
 }
 }

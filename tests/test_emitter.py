@@ -1,0 +1,138 @@
+"""CPU tests of the emitter: backend selection contract, planner decisions, derived information,
+error behaviour (the reference's CodeGen tests are golden-string tests without execution,
+dawn/test/unit-test/dawn/CodeGen/Stencils.cpp:112-123; structural assertions play that role here)."""
+import json
+import os
+import re
+
+import pytest
+
+from util import iir_path
+import dawn_b200
+from dawn_b200 import codegen
+
+REF = "/root/reference/dawn/test/"
+
+
+def _code(name, **opts):
+    return codegen.compile_iir(open(iir_path(name)).read(), **opts)
+
+
+def test_parse_backend_string_contract():
+    # dawn::codegen::parseBackendString, CodeGen/Driver.cpp:47-64 + the two new values
+    P = codegen.parse_backend_string
+    B = codegen.CodeGenBackend
+    assert P("cuda") == B.CUDA and P("CUDA") == B.CUDA
+    assert P("cuda-ico") == B.CUDAIco and P("CUDAIco") == B.CUDAIco
+    assert P("naive") == B.CXXNaive and P("c++-naive") == B.CXXNaive and P("cxxnaive") == B.CXXNaive
+    assert P("ico") == B.CXXNaiveIco and P("naive-ico") == B.CXXNaiveIco
+    assert P("gt") == B.GridTools and P("gridtools") == B.GridTools
+    assert P("b200") == B.B200 and P("B200") == B.B200
+    assert P("b200-ico") == B.B200Ico and P("B200Ico") == B.B200Ico
+    with pytest.raises(ValueError, match="Backend not supported"):
+        P("opencl")
+
+
+def test_only_b200_backends_are_provided():
+    with pytest.raises(codegen.CodeGenError, match="not provided"):
+        _code("copy_stencil", backend="cuda")
+
+
+def test_hori_diff_plan_inlines_lap_and_stages_inputs_with_tma():
+    code = _code("hori_diff_type2_stencil")
+    kernels = re.findall(r"^// kernel (\S+): (\w+) kernel", code, flags=re.M)
+    assert [k[1] for k in kernels] == ["tile", "tile"]
+    assert kernels[1][0].endswith("_tma_kernel")
+    assert "lap_ijcache" not in code and "__shared__ ::dawn::float_type lap" not in code
+    assert "const ::dawn::float_type lap_p0_p0" in code       # lap re-evaluated in registers
+    assert "CUtensorMap tm_in" in code and "CUtensorMap tm_hdmask" in code
+    assert "tma::load_3d" in code and "tma::wait" in code
+    # no temporary storage, one launch per run
+    assert "scratch_field" not in code
+    # the reference's class API is kept
+    for s in ("class hori_diff_type2_stencil", "void run(storage_ijk_t out, storage_ijk_t in, "
+              "storage_j_t crlato, storage_j_t crlatu, storage_ijk_t hdmask)", "get_total_time",
+              "reset_meters", "get_name", "in_extent = {-2, 2, -2, 2, 0, 0}"):
+        assert s in code, s
+
+
+def test_temporaries_fall_back_to_scratch_when_inlining_is_off():
+    code = _code("hori_diff_type2_stencil", inline_temporaries=0)
+    assert "scratch_field m_lap" in code and "__syncthreads();" in code
+    assert "stage" in code and "extent i[-1,1] j[-1,1]" in code  # redundant halo computation
+
+
+def test_tridiagonal_plan_fuses_sweeps_with_register_kcaches():
+    code = _code("tridiagonal_solve")
+    kernels = re.findall(r"^// kernel (\S+): (\w+) kernel over (\d+) multistage", code, flags=re.M)
+    assert all(k[1] == "column" and k[2] == "2" for k in kernels)
+    assert any(k[0].endswith("_ring_kernel") for k in kernels)
+    assert "c_kc0" in code and "c_kc1" in code and "d_kc1" in code
+    assert "fence_proxy_async" in code  # backward sweep streams what the forward sweep stored
+    unfused = _code("tridiagonal_solve", fuse_columns=0, column_ring=0)
+    assert len(re.findall(r"^// kernel ", unfused, flags=re.M)) == 2
+    info = json.loads(re.search(r'return "(\{.*\})";', code).group(1).replace('\\"', '"'))
+    assert info["written"] == ["d", "c"]
+    assert [f["extent"] for f in info["fields"]] == [[0, 0, 0, 0, -1, 1], [0] * 6, [0] * 6,
+                                                     [0, 0, 0, 0, -1, 0]]
+
+
+def test_planner_knobs_change_the_tile():
+    code = _code("hori_diff_type2_stencil", block_size_i=32, block_size_j=8, rows_per_thread=4)
+    assert "block 32x8 threads, 4 row(s)/thread" in code and "__launch_bounds__(256)" in code
+    with pytest.raises(codegen.CodeGenError, match="block size"):
+        _code("hori_diff_type2_stencil", block_size_i=64, block_size_j=32)
+    with pytest.raises(TypeError):
+        _code("hori_diff_type2_stencil", no_such_option=1)
+
+
+def test_globals_and_masked_fields():
+    code = _code("laplacian_stencil")
+    assert "struct globals" in code and "double dx;" in code and "dx(1)" in code
+    assert "double get_dx()" in code and "void set_dx(double dx)" in code
+    assert "storage_ij_t out_field, storage_ij_t in_field" in code
+    assert "g.dx" in code
+
+
+def test_malformed_iir_is_an_error_not_a_crash():
+    with pytest.raises(codegen.CodeGenError):
+        codegen.compile_iir("{not json")
+    with pytest.raises(codegen.CodeGenError, match="missing key"):
+        codegen.compile_iir("{}")
+    iir = json.load(open(iir_path("copy_stencil")))
+    stmt = iir["internalIR"]["stencils"][0]["multiStages"][0]["stages"][0]["doMethods"][0]["ast"][
+        "block_stmt"]["statements"][0]
+    stmt["expr_stmt"]["expr"]["assignment_expr"]["right"] = {"stencil_fun_call_expr": {"callee": "f"}}
+    with pytest.raises(codegen.CodeGenError, match="inlined"):
+        codegen.compile_iir(json.dumps(iir))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_reference_iir_fixtures_are_accepted():
+    fixtures = {
+        "unit-test/dawn/CodeGen/input/update_dz_c.iir": 7,
+        "unit-test/dawn/CodeGen/input/conditional_stencil.iir": 1,
+        "integration-test/serializer/reference_iir/copy_stencil.iir": 1,
+        "integration-test/serializer/reference_iir/lap_stencil.iir": 1,
+        "unit-test/dawn/Optimizer/input/tridiagonal_solve.iir": 1,
+    }
+    for rel, nk in fixtures.items():
+        code = codegen.compile_iir(open(REF + rel).read(), use_tma=0, column_ring=0)
+        assert len(re.findall(r"^// kernel ", code, flags=re.M)) == nk, rel
+    code = codegen.compile_iir(open(REF + "unit-test/dawn/CodeGen/input/update_dz_c.iir").read())
+    # extents exported like reference/update_dz_c.cpp:80-89
+    assert "dp_ref_extent = {0, 1, 0, 1, -2, 1}" in code and "gz_x_extent = {-1, 1, 0, 1, 0, 0}" in code
+    assert "gz_0_extent = {0, 0, 0, 0, 0, 1}" in code
+    assert "gridtools::dawn::storage_t m_gz_0" in code  # allocated (versioned) field owned by wrapper
+
+
+def test_cli_matches_library(tmp_path):
+    import subprocess
+    from dawn_b200 import build
+    build.build_emitter()
+    exe = os.path.join(build.LIB, "dawn-b200-codegen")
+    out = tmp_path / "x.cu"
+    subprocess.check_call([exe, "--backend=b200", "-o", str(out), iir_path("copy_stencil")])
+    assert out.read_text() == _code("copy_stencil")
+    r = subprocess.run([exe, "-b", "nope", iir_path("copy_stencil")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Backend not supported" in r.stderr
