@@ -1049,7 +1049,7 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
       << kp.name << "(";
   if(kp.usesGlobals)
     os_ << "const globals g, ";
-  os_ << "const int nx, const int ny, const int nz, const int kchunk";
+  os_ << "const int nx, const int ny, const int jofs, const int nz, const int kchunk";
   for(auto const& c : classes) {
     MaskClass m{c[0] == '1', c[1] == '1', c[2] == '1'};
     if(m.needSJ())
@@ -1069,7 +1069,7 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
   os_ << ") {\n";
   os_ << "  const int tid = threadIdx.x;\n";
   os_ << "  const int i0 = blockIdx.x * " << kp.TI << ";\n";
-  os_ << "  const int j0 = blockIdx.y * " << kp.tileJ() << ";\n";
+  os_ << "  const int j0 = blockIdx.y * " << kp.tileJ() << " + jofs; // rows [jofs, ny) of the domain\n";
   os_ << "  const int kmin = 0, kmax = nz - 1;\n";
   os_ << "  (void)kmin; (void)kmax; (void)kchunk;\n";
 
@@ -1629,12 +1629,18 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
     // ---- raw launch path ----
     os_ << "\n    // Launches the kernels on `stream`; fields are device-resident descriptors in run() "
            "argument order.\n";
-    os_ << "    int launch(const b200_field_t* f, void* stream_) {\n";
+    os_ << "    int launch(const b200_field_t* f, void* stream_) { return launch_rows(f, stream_, 0, "
+           "m_dom.jsize()); }\n";
+    os_ << "    // Same, restricted to the interior rows [j_begin, j_end) (0-based, halo excluded): lets "
+           "a driver compute the\n    // rows that do not depend on halos while a halo exchange is "
+           "in flight.\n";
+    os_ << "    int launch_rows(const b200_field_t* f, void* stream_, int j_begin, int j_end) {\n";
     os_ << "      cudaStream_t stream = static_cast<cudaStream_t>(stream_);\n";
     os_ << "      const int nx = m_dom.isize() - m_dom.iminus() - m_dom.iplus();\n";
     os_ << "      const int ny = m_dom.jsize() - m_dom.jminus() - m_dom.jplus();\n";
     os_ << "      const int nz = m_dom.ksize() - m_dom.kminus() - m_dom.kplus();\n";
-    os_ << "      if(nx <= 0 || ny <= 0 || nz <= 0) return 0;\n";
+    os_ << "      const int jlo = j_begin < 0 ? 0 : j_begin, jhi = j_end > ny ? ny : j_end;\n";
+    os_ << "      if(nx <= 0 || ny <= 0 || nz <= 0 || jhi <= jlo) return 0;\n";
     // halo check against accumulated extents
     for(size_t a = 0; a < sargs.size(); ++a) {
       int f = sargs[a];
@@ -1705,8 +1711,15 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
     }
     auto emitLaunch = [&](const KernelPlan& kp, const std::string& pad,
                           const std::string& smemExpr = "") {
-      os_ << pad << "const int kchunk = " << kp.KC << ";\n";
-      os_ << pad << "dim3 grid((nx + " << kp.TI - 1 << ") / " << kp.TI << ", (ny + "
+      os_ << pad << "int kchunk = " << kp.KC << ";\n";
+      if(kp.zchunk) {
+        // few ij tiles (small domains, boundary strips of a slab): split k finer so that the launch
+        // still fills the 148 SMs at least twice
+        os_ << pad << "while(kchunk > 2 && (long)((nx + " << kp.TI - 1 << ") / " << kp.TI
+            << ") * ((jhi - jlo + " << kp.tileJ() - 1 << ") / " << kp.tileJ()
+            << ") * ((nz + kchunk - 1) / kchunk) < 296) kchunk = (kchunk + 1) / 2;\n";
+      }
+      os_ << pad << "dim3 grid((nx + " << kp.TI - 1 << ") / " << kp.TI << ", (jhi - jlo + "
           << kp.tileJ() - 1 << ") / " << kp.tileJ() << ", "
           << (kp.zchunk ? "(nz + kchunk - 1) / kchunk" : "1") << ");\n";
       size_t smem = kp.tma ? 128 + (size_t)kp.stages * kp.stageElems * 8 : 0;
@@ -1727,7 +1740,7 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
           << (smemExpr.empty() ? std::to_string(smem) : smemExpr) << ", stream>>>(";
       if(kp.usesGlobals)
         os_ << "m_globals, ";
-      os_ << "nx, ny, nz, kchunk";
+      os_ << "nx, jhi, jlo, nz, kchunk";
       for(auto const& c : kernelClasses(kp)) {
         MaskClass m{c[0] == '1', c[1] == '1', c[2] == '1'};
         if(m.needSJ())
@@ -1908,7 +1921,9 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
   }
   os_ << "  }\n\n";
   // raw run used by the C ABI (device descriptors, API order)
-  os_ << "  int run_raw(const b200_field_t* f, void* stream) {\n";
+  os_ << "  int run_raw(const b200_field_t* f, void* stream) { return run_raw_rows(f, stream, 0, "
+         "1 << 30); }\n";
+  os_ << "  int run_raw_rows(const b200_field_t* f, void* stream, int j_begin, int j_end) {\n";
   for(size_t sidx = 0; sidx < inst_.stencils.size(); ++sidx) {
     auto sargs = stencilArgs(inst_.stencils[sidx], plans[sidx]);
     os_ << "    {\n      b200_field_t a[" << std::max<size_t>(1, sargs.size()) << "];\n";
@@ -1922,7 +1937,7 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
       }
     }
     os_ << "      if(int err = m_stencil_" << inst_.stencils[sidx].id
-        << ".launch(a, stream)) return err;\n    }\n";
+        << ".launch_rows(a, stream, j_begin, j_end)) return err;\n    }\n";
   }
   os_ << "    return 0;\n  }\n\n";
   os_ << "  long launches() const { return 0";
@@ -1967,6 +1982,12 @@ void CartesianEmitter::emitCAbi() {
       << ") return ::dawn_b200::set_error(B200_ERR_ARG, \"run_" << n << ": expected "
       << inst_.apiFieldIDs.size() << " fields\");\n"
       << "  return static_cast<" << cls << "*>(handle)->run_raw(fields, stream);\n}\n";
+  os_ << "B200_EXPORT int run_rows_" << n
+      << "(void* handle, const b200_field_t* fields, int nfields, void* stream, int j_begin, int j_end) {\n"
+      << "  if(!handle || nfields != " << inst_.apiFieldIDs.size()
+      << ") return ::dawn_b200::set_error(B200_ERR_ARG, \"run_rows_" << n << ": expected "
+      << inst_.apiFieldIDs.size() << " fields\");\n"
+      << "  return static_cast<" << cls << "*>(handle)->run_raw_rows(fields, stream, j_begin, j_end);\n}\n";
   os_ << "B200_EXPORT void free_" << n << "(void* handle) { delete static_cast<" << cls << "*>(handle); }\n";
   os_ << "B200_EXPORT long launches_" << n << "(void* handle) { return static_cast<" << cls
       << "*>(handle)->launches(); }\n";

@@ -128,6 +128,9 @@ class StencilModule:
         self._run = getattr(self.lib, "run_" + name)
         self._run.argtypes = [ctypes.c_void_p, ctypes.POINTER(_rt.Field), ctypes.c_int,
                               ctypes.c_void_p]
+        self._run_rows = getattr(self.lib, "run_rows_" + name)
+        self._run_rows.argtypes = [ctypes.c_void_p, ctypes.POINTER(_rt.Field), ctypes.c_int,
+                                   ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         self._free = getattr(self.lib, "free_" + name)
         self._free.argtypes = [ctypes.c_void_p]
         self._launches = getattr(self.lib, "launches_" + name)
@@ -162,8 +165,9 @@ class Stencil:
         fn.restype = ctypes.c_double
         return fn(self.handle)
 
-    def run(self, *fields, stream=None):
-        """fields: Storage objects or runtime.Field descriptors in API order (device-resident)."""
+    def run(self, *fields, stream=None, rows=None):
+        """fields: Storage objects or runtime.Field descriptors in API order (device-resident).
+        rows=(j_begin, j_end) restricts the computation to those interior rows."""
         n = len(self.module.fields)
         if len(fields) != n:
             raise TypeError("%s.run expects %d fields (%s)" % (
@@ -172,7 +176,11 @@ class Stencil:
         if stream is None:
             import torch
             stream = torch.cuda.current_stream().cuda_stream
-        _rt.check(self.module._run(self.handle, arr, n, ctypes.c_void_p(stream)))
+        if rows is None:
+            _rt.check(self.module._run(self.handle, arr, n, ctypes.c_void_p(stream)))
+        else:
+            _rt.check(self.module._run_rows(self.handle, arr, n, ctypes.c_void_p(stream),
+                                            int(rows[0]), int(rows[1])))
 
     def run_from_host(self, *arrays, stream=None):
         """End-to-end call with HOST buffers in API order, indexed [k, j, i] (length 1 along masked

@@ -31,6 +31,12 @@ int setup_NAME(void** handle, int isize, int jsize, int ksize, const int* halos,
  * dimensionality disagree on strides, B200_ERR_ARG on a wrong field count. */
 int run_NAME(void* handle, const b200_field_t* fields, int nfields, void* stream);
 
+/* Same, restricted to the interior rows [j_begin, j_end) (0-based, halos excluded).  Lets a driver
+ * run the rows that do not depend on halo rows while a halo exchange is in flight and the boundary
+ * strips afterwards (j-slab sharding across GPUs). */
+int run_rows_NAME(void* handle, const b200_field_t* fields, int nfields, void* stream, int j_begin,
+                  int j_end);
+
 void free_NAME(void* handle);
 
 /* Number of kernel launches issued by this instance so far. */
