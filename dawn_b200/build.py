@@ -102,6 +102,7 @@ VARIANTS = {
         dict(block_size_i=32, block_size_j=8, rows_per_thread=2), dict(inline_temporaries=0),
         dict(use_tma=0), dict(tma_stages=2, block_size_k=3), dict(inline_temporaries=0, use_tma=0),
     ],
+    "ICON_laplacian_stencil": [dict(fuse_columns=0, levels_per_thread=1), dict(levels_per_thread=8)],
     "tridiagonal_solve": [dict(fuse_columns=0), dict(column_ring=0), dict(column_ring=0, column_cache=1, prefetch_k=3),
                           dict(ring_levels=2, tma_stages=2), dict(block_size_i=32, block_size_j=2)],
 }
@@ -156,6 +157,27 @@ def build_all(force=False):
                                                               inline_temporaries=0),
                                     tag="ref_plain", force=force))
     return built
+
+
+def build_cpp_driver(force=False):
+    """tests/cpp/hori_diff_driver.cu: a reference-style C++ driver that #includes the generated TU."""
+    from . import codegen
+    src = os.path.join(ROOT, "tests", "cpp", "hori_diff_driver.cu")
+    exe = os.path.join(LIB, "hori_diff_driver")
+    gen = os.path.join(GEN, "hori_diff_type2_stencil.cu")
+    if not os.path.exists(gen):
+        with open(os.path.join(ROOT, "stencils", "hori_diff_type2_stencil.iir")) as f:
+            code = codegen.compile_iir(f.read())
+        compile_module("hori_diff_type2_stencil", code)
+    oracle_so = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not os.path.exists(oracle_so):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
+    if force or _newer(exe, [src, gen, oracle_so]):
+        _run([NVCC] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-cudart", "shared",
+                              "-I", PKG, '-DGENERATED_FILE="%s"' % gen, "-o", exe, src,
+                              "-L", LIB, "-ldawn_b200rt", "-Xlinker", "-rpath,$ORIGIN",
+                              oracle_so, "-Xlinker", "-rpath," + os.path.join(ROOT, "oracle")])
+    return exe
 
 
 def clean():

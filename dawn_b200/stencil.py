@@ -122,15 +122,21 @@ class StencilModule:
         info.restype = ctypes.c_char_p
         self.info = json.loads(info().decode())
         self.fields = self.info["fields"]
+        self.unstructured = self.info.get("grid") == "Unstructured"
         self._setup = getattr(self.lib, "setup_" + name)
-        self._setup.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int,
-                                ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
+        if self.unstructured:
+            self._setup.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int,
+                                    ctypes.c_void_p]
+        else:
+            self._setup.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
         self._run = getattr(self.lib, "run_" + name)
         self._run.argtypes = [ctypes.c_void_p, ctypes.POINTER(_rt.Field), ctypes.c_int,
                               ctypes.c_void_p]
-        self._run_rows = getattr(self.lib, "run_rows_" + name)
-        self._run_rows.argtypes = [ctypes.c_void_p, ctypes.POINTER(_rt.Field), ctypes.c_int,
-                                   ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        if not self.unstructured:
+            self._run_rows = getattr(self.lib, "run_rows_" + name)
+            self._run_rows.argtypes = [ctypes.c_void_p, ctypes.POINTER(_rt.Field), ctypes.c_int,
+                                       ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         self._free = getattr(self.lib, "free_" + name)
         self._free.argtypes = [ctypes.c_void_p]
         self._launches = getattr(self.lib, "launches_" + name)
@@ -139,6 +145,11 @@ class StencilModule:
 
     def __call__(self, domain, stream=None):
         return Stencil(self, domain, stream)
+
+    def on_mesh(self, adapter, k_size, stream=None):
+        """Unstructured modules: bind to a mesh adapter (e.g. trimesh.TriMesh) and a level count,
+        like the reference's setup_<N>(mesh, k_size, stream) (CudaIcoCodeGen.cpp:1198-1219)."""
+        return UnstructuredStencil(self, adapter, k_size, stream)
 
 
 class Stencil:
@@ -223,6 +234,56 @@ class Stencil:
 
     def written_fields(self):
         return set(self.module.info.get("written", [f["name"] for f in self.module.fields]))
+
+    def launches(self):
+        return int(self.module._launches(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.module._free(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class UnstructuredStencil:
+    """Instance of a generated b200-ico stencil on a mesh.  Fields are torch CUDA tensors (float64):
+    dense [k, element], sparse [k, nbh, element], in the module's API order."""
+
+    def __init__(self, module, adapter, k_size, stream=None):
+        from .mesh import Mesh
+        self.module = module
+        self.mesh = Mesh(adapter, module.info["tables"])
+        self.k_size = int(k_size)
+        self.handle = ctypes.c_void_p()
+        _rt.check(module._setup(ctypes.byref(self.handle), ctypes.addressof(self.mesh.struct),
+                                self.k_size, stream))
+
+    def descriptors(self, tensors):
+        out = []
+        for f, t in zip(self.module.fields, tensors):
+            if t.dim() == 3:   # sparse [k, nbh, n]
+                out.append(_rt.Field(t.data_ptr(), t.shape[2], t.shape[1] * t.shape[2]))
+            elif t.dim() == 2:
+                out.append(_rt.Field(t.data_ptr(), 0, t.shape[1]))
+            else:
+                out.append(_rt.Field(t.data_ptr(), 0, 1))
+        return out
+
+    def run(self, *tensors, stream=None):
+        n = len(self.module.fields)
+        if len(tensors) != n:
+            raise TypeError("%s.run expects %d fields (%s)" % (
+                self.module.name, n, ", ".join(f["name"] for f in self.module.fields)))
+        arr = (_rt.Field * n)(*self.descriptors(tensors))
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
+        _rt.check(self.module._run(self.handle, arr, n, ctypes.c_void_p(stream)))
 
     def launches(self):
         return int(self.module._launches(self.handle))

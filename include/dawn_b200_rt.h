@@ -106,6 +106,24 @@ int b200rt_reshape_back(const double* in, double* out, int k_size, int num_eleme
 int b200rt_upload_nbh_table(const int* row_major, int num_elements, int nbh_size, int* d_table_soa,
                             void* stream);
 
+/* ---- unstructured meshes: what the reference passes as dawn::GlobalGpuTriMesh
+ * (driver-includes/cuda_utils.hpp:43-57: element counts + a map (chain, include_center) -> device
+ * neighbour table) as a plain struct.  Location codes: 0 cells, 1 edges, 2 vertices.  Tables are
+ * SoA [nbh][element] int32 on the device, -1 = missing neighbour (b200rt_upload_nbh_table). ---- */
+typedef struct b200_nbh_table_t {
+  int chain[8];
+  int chain_len;
+  int include_center;
+  int nbh_size;
+  const int* table;
+} b200_nbh_table_t;
+
+typedef struct b200_mesh_t {
+  int num_cells, num_edges, num_vertices;
+  int num_tables;
+  const b200_nbh_table_t* tables;
+} b200_mesh_t;
+
 /* ---- j-slab halo exchange across the GPUs of one box (new: the reference has no communication
  * layer at all).  One process per GPU.  `comm` is an ncclComm_t created by the host
  * (e.g. from torch.distributed's unique id) or by b200rt_comm_init_rank. ---- */

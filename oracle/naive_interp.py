@@ -501,3 +501,180 @@ def _collect_k(node, kext):
             for x in n:
                 visit(x)
     visit(node)
+
+
+# ------------------------------------------------------------------------------------------------
+# Unstructured (naive-ico) interpreter
+# ------------------------------------------------------------------------------------------------
+_LOC = {"Cell": 0, "Edge": 1, "Vertex": 2}
+
+
+class UnstructuredRun:
+    """Executes an unstructured IIR with the semantics of the reference's naive-ico backend
+    (dawn/src/dawn/CodeGen/CXXNaive-ico/CXXNaiveCodeGen.cpp:366-617): per multistage, per k of the
+    interval, per stage `for loc in get<Cells|Edges|Vertices>(mesh)`; a reduction iterates the
+    neighbour list of its chain in mesh order starting from `init`, `lhs op= [weight *] rhs`
+    (toylib_interface.hpp:280-323).  Vectorised over the elements of a stage (a stage never reads
+    through a chain what it writes itself).
+
+    `mesh` must offer num(loc), valid(loc) and nbh_table(chain, include_center) (row-major, -1
+    padded): dawn_b200.trimesh.TriMesh is pinned bit-exactly against the reference's toylib.
+    Fields: dense [k, n]; sparse [k, n, nbh]; vertical-only [k]."""
+
+    def __init__(self, iir, mesh, k_size, globals_=None):
+        self.iir = load_iir(iir)
+        self.meta = self.iir["metadata"]
+        self.ir = self.iir["internalIR"]
+        self.mesh = mesh
+        self.k_size = k_size
+        self.globals = {n: g.get("value", 0) for n, g in self.ir.get("globalVariableToValue", {}).items()}
+        if globals_:
+            self.globals.update(globals_)
+        self.dims = {int(k): v for k, v in self.meta.get("fieldIDtoDimensions", {}).items()}
+
+    def _is_sparse(self, aid):
+        d = self.dims.get(aid, {}).get("unstructured_horizontal_dimension")
+        return bool(d) and len(d.get("iter_space", {}).get("chain", [])) > 1
+
+    def run(self, fields):
+        self.f = fields
+        kmin, kmax = 0, self.k_size - 1
+        for st in self.ir["stencils"]:
+            for ms in st["multiStages"]:
+                backward = ms.get("loopOrder", "Forward") == "Backward"
+                stages = ms["stages"]
+                bounds = [interval_bounds(dm["interval"]) for s in stages for dm in s["doMethods"]]
+                parts = partition(bounds)
+                if backward:
+                    parts = parts[::-1]
+                for lo, hi in parts:
+                    k0, k1 = resolve(lo, kmin, kmax), resolve(hi, kmin, kmax)
+                    ks = range(k1, k0 - 1, -1) if backward else range(k0, k1 + 1)
+                    for k in ks:
+                        for stage in stages:
+                            dms = [dm for dm in stage["doMethods"]
+                                   if _overlap(interval_bounds(dm["interval"]), (lo, hi))]
+                            if dms:
+                                self._stage(stage, dms, k)
+        return self.f
+
+    def _stage(self, stage, dms, k):
+        self.k = k
+        self.loc = _LOC[stage["locationType"]]
+        self.elems = np.nonzero(self.mesh.valid(self.loc))[0]
+        self.locals = {}
+        self.nb = None       # neighbour ids of the reduction being evaluated (per element)
+        self.nb_idx = None   # position in the neighbour list
+        for dm in dms:
+            for s in dm["ast"]["block_stmt"].get("statements", []):
+                self._stmt(s, None)
+
+    def _stmt(self, node, mask):
+        kd, v = _kind(node)
+        if kd == "block_stmt":
+            for s in v.get("statements", []):
+                self._stmt(s, mask)
+        elif kd == "expr_stmt":
+            ek, ev = _kind(v["expr"])
+            assert ek == "assignment_expr", ek
+            rhs = self._eval(ev["right"])
+            op = ev.get("op", "=")
+            lk, lv = _kind(ev["left"])
+            if lk == "var_access_expr":
+                aid = lv["data"]["accessID"]
+                cur = self.locals[aid]
+                new = rhs if op == "=" else _BIN[op[0]](cur, rhs)
+                self.locals[aid] = np.where(mask, new, cur) if mask is not None else \
+                    np.broadcast_to(np.asarray(new, dtype=float), cur.shape).copy()
+            else:
+                arr = self.f[lv["name"]]
+                kk = self.k + lv.get("vertical_shift", 0)
+                cur = arr[kk, self.elems] if arr.ndim > 1 else arr[kk]
+                new = rhs if op == "=" else _BIN[op[0]](cur, rhs)
+                if mask is not None:
+                    new = np.where(mask, new, cur)
+                if arr.ndim > 1:
+                    arr[kk, self.elems] = new
+                else:
+                    arr[kk] = new
+        elif kd == "var_decl_stmt":
+            aid = v["var_decl_stmt_data"]["accessID"]
+            init = v.get("init_list", [])
+            val = self._eval(init[0]) if init else 0.0
+            tid = v.get("type", {}).get("builtin_type", {}).get("type_id", "Float")
+            if tid == "Integer":
+                val = np.trunc(val)
+            self.locals[aid] = np.broadcast_to(np.asarray(val, dtype=float), self.elems.shape).copy()
+        elif kd == "if_stmt":
+            ck, cv = _kind(v["cond_part"])
+            cond = np.broadcast_to(np.asarray(self._eval(cv["expr"])).astype(bool), self.elems.shape)
+            self._stmt(v["then_part"], cond if mask is None else mask & cond)
+            if v.get("else_part"):
+                self._stmt(v["else_part"], ~cond if mask is None else mask & ~cond)
+        else:
+            raise NotImplementedError(kd)
+
+    def _eval(self, node):
+        kd, v = _kind(node)
+        if kd == "literal_access_expr":
+            t = v.get("type", {}).get("type_id", "Float")
+            return int(v["value"]) if t == "Integer" else (v["value"] in ("true", "1") if t == "Boolean"
+                                                           else float(v["value"]))
+        if kd == "var_access_expr":
+            if v.get("is_external", False):
+                return self.globals[v["name"]]
+            return self.locals[v["data"]["accessID"]]
+        if kd == "field_access_expr":
+            arr = self.f[v["name"]]
+            kk = self.k + v.get("vertical_shift", 0)
+            if arr.ndim == 1:
+                return arr[kk]
+            if self._is_sparse(v["data"]["accessID"]):
+                return arr[kk, self.elems, self.nb_idx]
+            if v.get("unstructured_offset", {}).get("has_offset", False):
+                return arr[kk, np.maximum(self.nb, 0)]
+            return arr[kk, self.elems]
+        if kd == "binary_operator":
+            a, b = self._eval(v["left"]), self._eval(v["right"])
+            with np.errstate(all="ignore"):
+                return _BIN[v["op"]](a, b)
+        if kd == "unary_operator":
+            a = self._eval(v["operand"])
+            return np.negative(a) if v["op"] == "-" else (np.logical_not(a) if v["op"] == "!" else a)
+        if kd == "ternary_operator":
+            return np.where(self._eval(v["cond"]), self._eval(v["left"]), self._eval(v["right"]))
+        if kd == "fun_call_expr":
+            with np.errstate(all="ignore"):
+                return _MATH[v["callee"].split("::")[-1]](*[self._eval(a) for a in v.get("arguments", [])])
+        if kd == "reduction_over_neighbor_expr":
+            if self.nb is not None:
+                raise NotImplementedError("nested reductions")
+            chain = v["iter_space"]["chain"]
+            table = self.mesh.nbh_table(chain, v["iter_space"].get("include_center", False))[self.elems]
+            acc = np.broadcast_to(np.asarray(self._eval(v["init"]), dtype=float), self.elems.shape).copy()
+            weights = v.get("weights", [])
+            op = v.get("op", "+")
+            for idx in range(table.shape[1]):
+                self.nb, self.nb_idx = table[:, idx], idx
+                valid = self.nb >= 0
+                if not valid.any():
+                    continue
+                rhs = self._eval(v["rhs"])
+                if weights:
+                    rhs = np.multiply(self._eval(weights[idx]), rhs)
+                if op in ("+", "-", "*", "/"):
+                    new = _BIN[op](acc, rhs)
+                elif op == "min":
+                    new = np.minimum(acc, rhs)
+                elif op == "max":
+                    new = np.maximum(acc, rhs)
+                else:
+                    raise NotImplementedError(op)
+                acc = np.where(valid, new, acc)
+            self.nb = self.nb_idx = None
+            return acc
+        raise NotImplementedError(kd)
+
+
+def run_unstructured(iir, mesh, k_size, fields, globals_=None):
+    return UnstructuredRun(iir, mesh, k_size, globals_).run(fields)

@@ -1,0 +1,23 @@
+"""The generated class API used from C++ exactly like the reference's drivers use theirs
+(gtclang/test/integration-test/CodeGen/hori_diff_type2_stencil_benchmark.cpp)."""
+import os
+import subprocess
+
+import pytest
+
+from dawn_b200 import build
+
+
+def test_cpp_driver_compiles_against_generated_code():
+    exe = build.build_cpp_driver()
+    assert os.path.exists(exe)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [(12, 12, 10), (70, 33, 7)])
+def test_cpp_driver_verifies_on_gpu(size):
+    exe = os.path.join(build.LIB, "hori_diff_driver")
+    if not os.path.exists(exe):
+        exe = build.build_cpp_driver()
+    r = subprocess.run([exe] + [str(x) for x in size], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "VERIFIED" in r.stdout, r.stdout + r.stderr

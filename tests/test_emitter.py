@@ -136,3 +136,40 @@ def test_cli_matches_library(tmp_path):
     assert out.read_text() == _code("copy_stencil")
     r = subprocess.run([exe, "-b", "nope", iir_path("copy_stencil")], capture_output=True, text=True)
     assert r.returncode == 1 and "Backend not supported" in r.stderr
+
+
+def test_ico_chain_sizes_known_answers():
+    # dawn/test/unit-test/dawn/CodeGen/Cuda-Ico/TestCuda-IcoCodeGen.cpp:31-87 (C=0, E=1, V=2)
+    C, E, V = 0, 1, 2
+    tests = [([C, E], 3), ([C, V], 3), ([E, C], 2), ([E, V], 2), ([V, C], 6), ([V, E], 6),
+             ([E, C, E], 4), ([E, C, V], 4), ([E, C, V, C], 16), ([C, V, C], 12), ([C, V, C, E], 24),
+             ([E, V, E], 10), ([E, V, E, C], 10), ([V, E, C], 6), ([V, E, C, V], 6),
+             ([V, E, C, V, E], 30), ([V, E, C, V, E, C], 24), ([C, E, C], 3), ([C, E, C, E], 9),
+             ([C, E, C, E, C], 9), ([C, E, C, E, C, E], 21)]
+    assert len(tests) == 21
+    for chain, want in tests:
+        assert codegen.ico_chain_size(chain) == want, chain
+    assert codegen.ico_chain_size([C, C]) == -1  # invalid chain
+
+
+def test_icon_laplacian_plan_fuses_edge_stages():
+    code = _code("ICON_laplacian_stencil", backend="b200-ico")
+    kernels = re.findall(r"^// kernel (\S+): (\d+) fused stage\(s\) on (\w+)", code, flags=re.M)
+    assert [(k[1], k[2]) for k in kernels] == [("1", "vertices"), ("1", "cells"), ("5", "edges")]
+    assert "__tmp_nab_60_p" not in code and "scratch_field" not in code  # temporaries stay in registers
+    assert "setup_ICON_laplacian_stencil(void** handle, const b200_mesh_t* mesh, int k_size" in code
+    unfused = _code("ICON_laplacian_stencil", backend="b200-ico", fuse_columns=0)
+    assert len(re.findall(r"^// kernel ", unfused, flags=re.M)) == 7
+    assert "scratch_field m___tmp_nab_60" in unfused
+    with pytest.raises(codegen.CodeGenError, match="unstructured"):
+        _code("ICON_laplacian_stencil", backend="b200")
+    with pytest.raises(codegen.CodeGenError, match="Cartesian"):
+        _code("copy_stencil", backend="b200-ico")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_reference_unstructured_fixtures_are_accepted():
+    for rel in ("integration-test/serializer/reference_iir/unstructured_sum_edge_to_cells.iir",
+                "integration-test/serializer/reference_iir/unstructured_mixed_copies.iir"):
+        code = codegen.compile_iir(open(REF + rel).read(), backend="b200-ico")
+        assert "__global__" in code

@@ -1,0 +1,124 @@
+"""GPU parity of generated b200-ico kernels against the (reference-pinned) unstructured oracle,
+bit-exact, through the C ABI."""
+import numpy as np
+import pytest
+
+from util import bit_equal, iir_path
+from oracle import naive_interp
+from dawn_b200.trimesh import CELL, EDGE, VERTEX, TriMesh
+
+pytestmark = pytest.mark.gpu
+
+LOC = {"cells": CELL, "edges": EDGE, "vertices": VERTEX}
+
+
+def _run(name, mesh, k, fields, **opts):
+    import torch
+    import dawn_b200
+    mod = dawn_b200.load_stencil(name, **opts)
+    st = mod.on_mesh(mesh, k)
+    tens = []
+    for fd in mod.fields:
+        a = fields[fd["name"]]
+        if fd["sparse"]:
+            a = np.ascontiguousarray(a.transpose(0, 2, 1))  # oracle [k,n,nbh] -> device [k,nbh,n]
+        tens.append(torch.from_numpy(np.ascontiguousarray(a)).cuda())
+    st.run(*tens)
+    torch.cuda.synchronize()
+    out = {}
+    for fd, t in zip(mod.fields, tens):
+        a = t.cpu().numpy()
+        out[fd["name"]] = a.transpose(0, 2, 1) if fd["sparse"] else a
+    return out, st
+
+
+def _rand(rng, m, k, spec):
+    return {n: rng.uniform(0.5, 1.5, (k, m.num(loc))) for n, loc in spec.items()}
+
+
+def _check(got, want, m, names):
+    for n, loc in names.items():
+        v = m.valid(loc)
+        assert bit_equal(got[n][:, v], want[n][:, v]), n
+
+
+@pytest.mark.parametrize("nx,ny,k", [(7, 5, 3), (33, 20, 9), (64, 64, 65)])
+@pytest.mark.parametrize("opts", [dict(), dict(fuse_columns=0, levels_per_thread=1),
+                                  dict(levels_per_thread=8)])
+def test_icon_laplacian(nx, ny, k, opts):
+    m = TriMesh(nx, ny)
+    rng = np.random.default_rng(31)
+    f = _rand(rng, m, k, {"vec": EDGE, "div_vec": CELL, "rot_vec": VERTEX, "nabla2_vec": EDGE,
+                          "primal_edge_length": EDGE, "dual_edge_length": EDGE,
+                          "tangent_orientation": EDGE})
+    f["geofac_rot"] = rng.uniform(-1, 1, (k, m.num_vertices, 6))
+    f["geofac_div"] = rng.uniform(-1, 1, (k, m.num_cells, 3))
+    want = {n: v.copy() for n, v in f.items()}
+    want["__tmp_nab_60"] = np.zeros((k, m.num_edges))
+    want["__tmp_nab_61"] = np.zeros((k, m.num_edges))
+    naive_interp.run_unstructured(iir_path("ICON_laplacian_stencil"), m, k, want)
+    got, st = _run("ICON_laplacian_stencil", m, k, f, **opts)
+    _check(got, want, m, {"rot_vec": VERTEX, "div_vec": CELL, "nabla2_vec": EDGE})
+    assert st.launches() == (3 if opts.get("fuse_columns", 1) else 7)
+
+
+@pytest.mark.parametrize("name,spec,outs", [
+    ("diffusion", {"in_field": CELL, "out_field": CELL}, {"out_field": CELL}),
+    ("gradient", {"cell_field": CELL, "edge_field": EDGE}, {"cell_field": CELL, "edge_field": EDGE}),
+    ("diamond", {"edge_field": EDGE, "vertex_field": VERTEX}, {"edge_field": EDGE}),
+    ("diamondWeights", {"out": EDGE, "inv_edge_length": EDGE, "inv_vert_length": EDGE, "in": VERTEX},
+     {"out": EDGE}),
+    ("intp", {"in": CELL, "out": CELL}, {"out": CELL}),
+])
+def test_reference_unstructured_stencils(name, spec, outs):
+    m = TriMesh(12, 9)
+    k = 5
+    f = _rand(np.random.default_rng(32), m, k, spec)
+    want = naive_interp.run_unstructured(iir_path(name), m, k, {n: v.copy() for n, v in f.items()})
+    got, _ = _run(name, m, k, f)
+    _check(got, want, m, outs)
+
+
+def test_neighbour_tables_on_device_are_bit_exact():
+    import dawn_b200
+    m = TriMesh(9, 6)
+    mod = dawn_b200.load_stencil("ICON_laplacian_stencil")
+    st = mod.on_mesh(m, 2)
+    for n, t in enumerate(mod.info["tables"]):
+        host = m.nbh_table(t["chain"], bool(t["include_center"]), nbh_size=t["size"])
+        assert np.array_equal(st.mesh.soa_table(n), host.T)
+
+
+def test_missing_table_is_an_error():
+    import ctypes
+    import dawn_b200
+    from dawn_b200 import runtime as rt
+    from dawn_b200.mesh import MeshStruct
+    mod = dawn_b200.load_stencil("diamond")
+    empty = MeshStruct(10, 10, 10, 0, None)
+    h = ctypes.c_void_p()
+    rc = mod._setup(ctypes.byref(h), ctypes.addressof(empty), 3, None)
+    assert rc != 0 and b"neighbour table" in rt.lib().b200rt_last_error()
+
+
+def test_runtime_reshape_and_verify_kernels():
+    import torch
+    from dawn_b200 import runtime as rt
+    k, n, sp = 7, 45, 3
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((n, sp, k))                 # element-major, k fastest
+    d_in = torch.from_numpy(a).cuda()
+    d_out = torch.empty(k * sp * n, dtype=torch.float64, device="cuda")
+    rt.check(rt.lib().b200rt_reshape(d_in.data_ptr(), d_out.data_ptr(), k, n, sp, None))
+    assert np.array_equal(d_out.cpu().numpy().reshape(k, sp, n), a.transpose(2, 1, 0))
+    back = torch.empty_like(d_in)
+    rt.check(rt.lib().b200rt_reshape_back(d_out.data_ptr(), back.data_ptr(), k, n, sp, None))
+    assert np.array_equal(back.cpu().numpy(), a)
+    x = torch.from_numpy(rng.standard_normal(1000)).cuda()
+    y = x.clone()
+    m = rt.verify_field(x.data_ptr(), y.data_ptr(), 1000)
+    assert m.is_valid == 1 and m.max_abs_err == 0.0 and m.n_failed == 0
+    y[17] += 1e-3
+    m = rt.verify_field(x.data_ptr(), y.data_ptr(), 1000, rel_tol=1e-12, abs_tol=0.0, iteration=4)
+    assert m.is_valid == 0 and m.n_failed == 1 and m.iteration == 4
+    assert abs(m.max_abs_err - 1e-3) < 1e-12

@@ -134,6 +134,18 @@ def lit(v) -> Expr:
     raise TypeError(v)
 
 
+def reduce_over(chain, rhs, init=0.0, op="+", weights=None, include_center=False) -> Expr:
+    """reduction_over_neighbor_expr over `chain` (e.g. ["Edge", "Cell"])."""
+    return Reduce(op, _lit_or_field(rhs), _lit_or_field(init), list(chain),
+                  None if weights is None else [_lit_or_field(w) for w in weights], include_center)
+
+
+def _lit_or_field(x):
+    if hasattr(x, "_e"):
+        return x._e()
+    return lit(x)
+
+
 def where(cond, a, b) -> Expr:
     return Ternary(lit(cond), lit(a), lit(b))
 
@@ -151,6 +163,11 @@ class FieldHandle:
 
     def at(self, k=0, nbh=False) -> FieldAccess:
         return FieldAccess(self.name, self.access_id, 0, 0, k, True, nbh)
+
+    @property
+    def nbh(self) -> FieldAccess:
+        """value at the neighbour inside a reduction"""
+        return self.at(0, True)
 
     # allow using the bare handle as a centre access
     def _e(self):
@@ -303,10 +320,7 @@ class IIRBuilder:
         chain = sparse_chain if sparse_chain else [location]
         return {
             "unstructured_horizontal_dimension": {
-                "iter_space": {"chain": list(chain), "include_center": False},
-                "dense_location_type": chain[0],
-                **({"sparse_part": list(chain)} if sparse_chain else {}),
-            },
+                "iter_space": {"chain": list(chain), "include_center": False}},
             "mask_k": 1 if "k" in dims else 0,
         }
 

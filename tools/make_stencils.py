@@ -23,7 +23,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(__file__))
-from iir_builder import FULL, IIRBuilder, Interval, k_cache, where  # noqa: E402
+from iir_builder import FULL, IIRBuilder, Interval, k_cache, reduce_over, where  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "stencils")
 
@@ -155,6 +155,100 @@ def nonoverlapping():
     return b
 
 
+def icon_laplacian():
+    # dawn/test/integration-test/dawn4py-tests/ICON_laplacian_stencil.py:36-216; statement trees as in
+    # the reference's generated naive-ico text data/ICON_laplacian_stencil_ref.cpp:62-139
+    b = IIRBuilder("ICON_laplacian_stencil", grid="Unstructured")
+    vec = b.field("vec", "k", "Edge")
+    div_vec = b.field("div_vec", "k", "Cell")
+    rot_vec = b.field("rot_vec", "k", "Vertex")
+    nabla2 = b.field("nabla2_vec", "k", "Edge")
+    pel = b.field("primal_edge_length", "k", "Edge")
+    del_ = b.field("dual_edge_length", "k", "Edge")
+    tang = b.field("tangent_orientation", "k", "Edge")
+    geofac_rot = b.field("geofac_rot", "k", sparse_chain=["Vertex", "Edge"])
+    geofac_div = b.field("geofac_div", "k", sparse_chain=["Cell", "Edge"])
+    t60 = b.tmp("__tmp_nab_60", "k", "Edge")
+    t61 = b.tmp("__tmp_nab_61", "k", "Edge")
+    s = [
+        b.stage(b.do(FULL, b.assign(rot_vec, reduce_over(["Vertex", "Edge"], vec.nbh * geofac_rot.at()))),
+                location="Vertex"),
+        b.stage(b.do(FULL, b.assign(div_vec, reduce_over(["Cell", "Edge"], vec.nbh * geofac_div.at()))),
+                location="Cell"),
+        b.stage(b.do(FULL, b.assign(t60, reduce_over(["Edge", "Vertex"], rot_vec.nbh,
+                                                     weights=[-1.0, 1.0]))), location="Edge"),
+        b.stage(b.do(FULL, b.assign(t60, (tang.at() * t60.at()) / pel.at())), location="Edge"),
+        b.stage(b.do(FULL, b.assign(t61, reduce_over(["Edge", "Cell"], div_vec.nbh,
+                                                     weights=[-1.0, 1.0]))), location="Edge"),
+        b.stage(b.do(FULL, b.assign(t61, t61.at() / del_.at())), location="Edge"),
+        b.stage(b.do(FULL, b.assign(nabla2, t61.at() - t60.at())), location="Edge"),
+    ]
+    b.stencil(b.multistage("Parallel", *s))
+    return b
+
+
+def unstructured_diffusion():
+    # dawn/test/integration-test/unstructured/reference/reference_diffusion.hpp:31-69
+    b = IIRBuilder("diffusion", grid="Unstructured")
+    inn = b.field("in_field", "k", "Cell")
+    out = b.field("out_field", "k", "Cell")
+    chain = ["Cell", "Edge", "Cell"]
+    cdecl, cnt = b.local("cnt", reduce_over(chain, 1, init=0), "Integer")
+    st = b.stage(b.do(FULL, cdecl,
+                      b.assign(out, reduce_over(chain, inn.nbh, init=(-cnt) * inn.at())),
+                      b.assign(out, inn.at() + 0.1 * out.at())), location="Cell")
+    b.stencil(b.multistage("Parallel", st))
+    return b
+
+
+def unstructured_gradient():
+    # reference/reference_gradient.hpp:28-60
+    b = IIRBuilder("gradient", grid="Unstructured")
+    cell = b.field("cell_field", "k", "Cell")
+    edge = b.field("edge_field", "k", "Edge")
+    s1 = b.stage(b.do(FULL, b.assign(edge, reduce_over(["Edge", "Cell"], cell.nbh, weights=[1.0, -1.0]))),
+                 location="Edge")
+    s2 = b.stage(b.do(FULL, b.assign(cell, reduce_over(["Cell", "Edge"], edge.nbh,
+                                                       weights=[0.5, 0.0, 0.0, 0.5]))), location="Cell")
+    b.stencil(b.multistage("Parallel", s1, s2))
+    return b
+
+
+def unstructured_diamond():
+    # reference/reference_diamond.hpp:28-50 (chain E -> C -> V, 4 vertices)
+    b = IIRBuilder("diamond", grid="Unstructured")
+    edge = b.field("edge_field", "k", "Edge")
+    vert = b.field("vertex_field", "k", "Vertex")
+    b.stencil(b.multistage("Parallel", b.stage(
+        b.do(FULL, b.assign(edge, reduce_over(["Edge", "Cell", "Vertex"], vert.nbh))), location="Edge")))
+    return b
+
+
+def unstructured_diamond_weights():
+    # reference/reference_diamondWeights.hpp:35-62 (weights are expressions of edge fields)
+    b = IIRBuilder("diamondWeights", grid="Unstructured")
+    out = b.field("out", "k", "Edge")
+    iel = b.field("inv_edge_length", "k", "Edge")
+    ivl = b.field("inv_vert_length", "k", "Edge")
+    inn = b.field("in", "k", "Vertex")
+    w = [iel.at() * iel.at(), iel.at() * iel.at(), ivl.at() * ivl.at(), ivl.at() * ivl.at()]
+    b.stencil(b.multistage("Parallel", b.stage(
+        b.do(FULL, b.assign(out, reduce_over(["Edge", "Cell", "Vertex"], inn.nbh, weights=w))),
+        location="Edge")))
+    return b
+
+
+def unstructured_intp():
+    # reference/reference_intp.hpp:28-50 (chain C-E-C-E-C, 9 cells)
+    b = IIRBuilder("intp", grid="Unstructured")
+    inn = b.field("in", "k", "Cell")
+    out = b.field("out", "k", "Cell")
+    b.stencil(b.multistage("Parallel", b.stage(
+        b.do(FULL, b.assign(out, reduce_over(["Cell", "Edge", "Cell", "Edge", "Cell"], inn.nbh))),
+        location="Cell")))
+    return b
+
+
 ALL = {
     "hori_diff_type2_stencil": hori_diff_type2,
     "hori_diff_stencil_01": hori_diff_01,
@@ -164,6 +258,12 @@ ALL = {
     "copy_stencil": copy_stencil,
     "global_indexing": global_indexing,
     "nonoverlapping_stencil": nonoverlapping,
+    "ICON_laplacian_stencil": icon_laplacian,
+    "diffusion": unstructured_diffusion,
+    "gradient": unstructured_gradient,
+    "diamond": unstructured_diamond,
+    "diamondWeights": unstructured_diamond_weights,
+    "intp": unstructured_intp,
 }
 
 
