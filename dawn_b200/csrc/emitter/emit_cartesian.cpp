@@ -177,6 +177,14 @@ private:
 
   std::vector<int> stencilArgs(const Stencil& st, const std::vector<KernelPlan>& kps) const;
   std::vector<int> kernelArgs(const KernelPlan& kp) const;
+  std::vector<const Stage*> rangedStages(const KernelPlan& kp) const {
+    std::vector<const Stage*> out;
+    for(auto const* ms : kp.ms)
+      for(auto const& st : ms->stages)
+        if(!droppedStages_.count(st.id) && (st.hasIRange || st.hasJRange))
+          out.push_back(&st);
+    return out;
+  }
   std::set<std::string> kernelClasses(const KernelPlan& kp) const;
 };
 
@@ -1050,6 +1058,16 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
   if(kp.usesGlobals)
     os_ << "const globals g, ";
   os_ << "const int nx, const int ny, const int jofs, const int nz, const int kchunk";
+  // global iteration spaces (reference: stageNGlobalI/JIndices + globalOffsets in __constant__
+  // memory, CudaCodeGen.cpp:454-458,567-579) travel as kernel scalars
+  if(!rangedStages(kp).empty())
+    os_ << ", const int gi0, const int gj0";
+  for(auto const* rs : rangedStages(kp)) {
+    if(rs->hasIRange)
+      os_ << ", const int s" << rs->id << "_ilo, const int s" << rs->id << "_ihi";
+    if(rs->hasJRange)
+      os_ << ", const int s" << rs->id << "_jlo, const int s" << rs->id << "_jhi";
+  }
   for(auto const& c : classes) {
     MaskClass m{c[0] == '1', c[1] == '1', c[2] == '1'};
     if(m.needSJ())
@@ -1563,14 +1581,6 @@ std::string CartesianEmitter::generate() {
   Instantiation& mut = const_cast<Instantiation&>(inst_);
   analysis::computeStageExtents(mut);
 
-  // global iteration spaces need constant-memory-free handling: passed as kernel scalars
-  for(auto const& st : inst_.stencils)
-    for(auto const& ms : st.multiStages)
-      for(auto const& stage : ms.stages)
-        if(stage.hasIRange || stage.hasJRange)
-          throw std::runtime_error("b200: global iteration spaces (i_range/j_range) are not yet "
-                                   "supported by the b200 backend");
-
   os_ << "namespace dawn_generated {\nnamespace b200 {\n\n";
   if(!inst_.globals.empty())
     emitGlobalsStruct();
@@ -1617,7 +1627,12 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
     os_ << "    stencil_" << st.id << "(const gridtools::dawn::domain& dom_, "
         << (hasGlobals ? "globals& globals_, " : "") << "int rank, int xcols, int ycols)\n"
         << "        : sbase(\"stencil_" << st.id << "\"), m_dom(dom_)"
-        << (hasGlobals ? ", m_globals(globals_)" : "") << " { (void)rank; (void)xcols; (void)ycols; }\n";
+        << (hasGlobals ? ", m_globals(globals_)" : "") << " {\n"
+        << "      // computeGlobalOffsets of the reference (CodeGen.cpp:461-470)\n"
+        << "      const unsigned r = (unsigned)rank % (unsigned)(xcols * ycols);\n"
+        << "      m_global_offsets[0] = (r % (unsigned)ycols) * (dom_.isize() - dom_.iplus());\n"
+        << "      m_global_offsets[1] = (r / (unsigned)xcols) * (dom_.jsize() - dom_.jplus());\n    }\n"
+        << "    unsigned m_global_offsets[2];\n";
     // extents (CodeGen.cpp:509-522)
     auto fext = analysis::fieldExtents(inst_, st);
     for(int f : sargs) {
@@ -1741,6 +1756,22 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
       if(kp.usesGlobals)
         os_ << "m_globals, ";
       os_ << "nx, jhi, jlo, nz, kchunk";
+      if(!rangedStages(kp).empty())
+        os_ << ", (int)(m_global_offsets[0] + m_dom.iminus()), (int)(m_global_offsets[1] + m_dom.jminus())";
+      auto bound = [&](const Interval& iv, bool upper, const char* dim) {
+        int level = upper ? iv.upperLevel : iv.lowerLevel;
+        int off = upper ? iv.upperOffset : iv.lowerOffset;
+        std::string d(dim);
+        if(level == Interval::End)
+          return "(int)(m_dom." + d + "size() - m_dom." + d + "plus()) + (" + std::to_string(off) + ")";
+        return "(int)m_dom." + d + "minus() + (" + std::to_string(level + off) + ")";
+      };
+      for(auto const* rs : rangedStages(kp)) {
+        if(rs->hasIRange)
+          os_ << ", " << bound(rs->iRange, false, "i") << ", " << bound(rs->iRange, true, "i");
+        if(rs->hasJRange)
+          os_ << ", " << bound(rs->jRange, false, "j") << ", " << bound(rs->jRange, true, "j");
+      }
       for(auto const& c : kernelClasses(kp)) {
         MaskClass m{c[0] == '1', c[1] == '1', c[2] == '1'};
         if(m.needSJ())

@@ -248,3 +248,18 @@ def test_row_restricted_runs_compose(name, make, outs):
     got = {fd["name"]: s.to_numpy() for fd, s in zip(mod.fields, stor)}
     for o in outs:
         assert bit_equal(got[o], want[o]), o
+
+
+def test_global_iteration_space_against_reference_golden():
+    """i_range/j_range stages (reference/global_indexing.cpp:84-106), output of the reference's own
+    generated naive code as golden."""
+    g = _golden("indexing")
+    ni, nj, nk = (int(x) for x in g["dims"])
+    rng = np.random.default_rng(int(g["seed"]))
+    inn = rng.uniform(-1, 1, (nk + 1, nj, ni))
+    f = {"in_field": inn, "out_field": np.full_like(inn, -1.0)}
+    got = _run_gpu("global_indexing", (ni, nj, nk), f, ["in_field", "out_field"])
+    assert bit_equal(got["out_field"], g["global_indexing"])
+    got = _run_gpu("nonoverlapping_stencil", (ni, nj, nk), {"in": inn, "out": np.full_like(inn, -1.0)},
+                   ["in", "out"])
+    assert bit_equal(got["out"][11:], g["nonoverlapping_from_k11"])
