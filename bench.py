@@ -404,11 +404,23 @@ def run_icon(args):
     import dawn_b200
     from dawn_b200.trimesh import TriMesh
 
-    torch.cuda.set_device(0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nx = ny = args.icon_n
     K = 65
     t0 = time.perf_counter()
-    mesh = TriMesh(nx, ny)
+    # weak scaling: every rank owns `ny` quad rows of a global nx x (ny*world) mesh plus one halo quad
+    # row towards each neighbour; `vec` (the only field read through chains) is exchanged every step
+    from dawn_b200 import runtime as rt, slabs
+    sl = slabs.mesh_slab(nx, ny * world, world, rank)
+    mesh = TriMesh(nx, sl.local_ny)
     mod = dawn_b200.load_stencil("ICON_laplacian_stencil")
     st = mod.on_mesh(mesh, K)
     t_mesh = time.perf_counter() - t0
@@ -423,32 +435,71 @@ def run_icon(args):
         t.uniform_(0.5, 1.5, generator=gen)
         tens.append(t)
     torch.cuda.synchronize()
-    for _ in range(max(args.warmup, 3)):
+    plan = comm = None
+    stream = torch.cuda.current_stream().cuda_stream
+    if world > 1:
+        import ctypes
+        idbuf = (ctypes.c_char * 128)()
+        if rank == 0:
+            rt.check(rt.lib().b200rt_nccl_unique_id(idbuf))
+        obj = [bytes(idbuf)]
+        dist.broadcast_object_list(obj, src=0)
+        idbuf = (ctypes.c_char * 128).from_buffer_copy(obj[0])
+        comm = ctypes.c_void_p()
+        rt.check(rt.lib().b200rt_comm_init_rank(ctypes.byref(comm), world, idbuf, rank))
+        per = sl.slots_per_row(1)
+        plan = ctypes.c_void_p()
+        rt.check(rt.lib().b200rt_halo_plan_create2(ctypes.byref(plan), comm, rank, world, per,
+                                                   sl.local_ny, K, per, E, sl.halo_lo, sl.halo_hi, 1, 1))
+    vec = tens[[fd["name"] for fd in mod.fields].index("vec")]
+
+    def step():
+        if plan is not None:
+            rt.check(rt.lib().b200rt_halo_exchange(plan, vec.data_ptr(), stream))
         st.run(*tens)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(0)
-    sampler.start()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     l0 = st.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        st.run(*tens)
+        step()
     e1.record()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1) / args.steps
-    launches = st.launches() - l0
-    units = E * K
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = st.launches() - l0 + (0 if plan is None else args.steps * 2 * (sl.halo_lo + sl.halo_hi))
+    # work and bytes of the OWNED rows of one rank (halo rows are redundant work)
+    own = TriMesh(nx, ny)
+    E, C, V = own.num_edges, own.num_cells, own.num_vertices
+    units = E * K * world
     bytes_run = K * (40 * E + 56 * V + 32 * C) + 4 * (6 * V + 3 * C + 2 * E + 2 * E)
     peak, peak_src = measured_peak()
     achieved = bytes_run / (ms * 1e-3) / 1e9
     line = {
         "metric": "edge-level updates/s", "value": units / (ms * 1e-3), "unit": "edge-level updates/s",
-        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (uniform random fields generated on device; regular triangle mesh)",
-        "config": {"workload": "ICON_laplacian_stencil (nabla2) on TriMesh %dx%d: %d edge slots, %d "
-                               "cells, %d vertices x %d levels" % (nx, ny, E, C, V, K),
+        "config": {"workload": "ICON_laplacian_stencil (nabla2) on TriMesh %dx%d per GPU: %d edge slots, "
+                               "%d cells, %d vertices x %d levels%s" % (
+                                   nx, ny, E, C, V, K, "" if world == 1 else
+                                   "; global mesh %dx%d in %d row slabs, 1 halo quad row, NCCL exchange "
+                                   "of `vec` every step" % (nx, ny * world, world)),
                    "l2": "inputs larger than L2 (%.1f GB per step), no flush" % (bytes_run / 1e9),
                    "mesh_build_s": t_mesh},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -457,7 +508,13 @@ def run_icon(args):
                                "%.0f algorithmic bytes/step" % bytes_run, "peak_source": peak_src},
         "gpu_launches": launches, "clocks": clocks,
     }
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
+    if plan is not None:
+        rt.lib().b200rt_halo_plan_destroy(plan)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

@@ -136,7 +136,7 @@ class IcoEmitter {
 public:
   IcoEmitter(const Instantiation& i, const Options& o) : inst_(i), opt_(o) {
     block_ = o.BlockSizeIco > 0 ? o.BlockSizeIco : 128;
-    lpt_ = o.LevelsPerThread > 0 ? o.LevelsPerThread : 4;
+    lpt_ = o.LevelsPerThread > 0 ? o.LevelsPerThread : 8;
   }
   std::string generate();
 

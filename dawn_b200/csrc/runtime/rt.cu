@@ -456,7 +456,7 @@ int b200rt_comm_destroy(void* comm) {
 
 struct b200_halo_plan {
   void* comm;
-  int rank, nranks, ni, nj, nk, sj, sk, halo, wminus, wplus;
+  int rank, nranks, ni, nj, nk, sj, sk, halo, halo_hi, wminus, wplus;
   double *send_lo = nullptr, *send_hi = nullptr, *recv_lo = nullptr, *recv_hi = nullptr;
 };
 
@@ -464,10 +464,19 @@ extern "C" {
 int b200rt_halo_plan_create(b200_halo_plan** plan, void* comm, int rank, int nranks, int ni, int nj,
                             int nk, int stride_j, int stride_k, int halo_j, int width_minus,
                             int width_plus) {
-  if(!plan || width_minus > halo_j || width_plus > halo_j || width_minus < 0 || width_plus < 0)
+  return b200rt_halo_plan_create2(plan, comm, rank, nranks, ni, nj, nk, stride_j, stride_k, halo_j,
+                                  halo_j, width_minus, width_plus);
+}
+
+int b200rt_halo_plan_create2(b200_halo_plan** plan, void* comm, int rank, int nranks, int ni, int nj,
+                             int nk, int stride_j, int stride_k, int halo_lo, int halo_hi,
+                             int width_minus, int width_plus) {
+  const bool has_lo = rank > 0, has_hi = rank + 1 < nranks;
+  if(!plan || width_minus < 0 || width_plus < 0 || (has_lo && width_minus > halo_lo) ||
+     (has_hi && width_plus > halo_hi))
     return b200rt_set_error(B200_ERR_ARG, "b200rt_halo_plan_create: bad widths");
   auto* p = new b200_halo_plan{comm, rank,     nranks,   ni,     nj,         nk,
-                               stride_j, stride_k, halo_j, width_minus, width_plus};
+                               stride_j, stride_k, halo_lo, halo_hi, width_minus, width_plus};
   // my low halo (width_minus rows) is filled from rank-1's top interior rows; my high halo
   // (width_plus rows) from rank+1's bottom interior rows.
   size_t lo = (size_t)ni * nk * (size_t)std::max(width_minus, width_plus) * sizeof(double);
@@ -498,7 +507,7 @@ int b200rt_halo_exchange(b200_halo_plan* p, double* field, void* stream) {
   };
   // rows I send down (to rank-1): my first `wplus` interior rows fill its high halo;
   // rows I send up (to rank+1): my last `wminus` interior rows fill its low halo.
-  const int j_int0 = p->halo, j_int1 = p->nj - p->halo; // interior rows [j_int0, j_int1)
+  const int j_int0 = p->halo, j_int1 = p->nj - p->halo_hi; // interior rows [j_int0, j_int1)
   if(has_lo && p->wplus)
     launch(field, p->send_lo, j_int0, p->wplus, false, nullptr);
   if(has_hi && p->wminus)

@@ -34,7 +34,8 @@ SYMBOLS = [
     "b200rt_event_record", "b200rt_event_synchronize", "b200rt_event_elapsed_ms",
     "b200rt_check_last_launch", "b200rt_tensor_map_3d", "b200rt_verify_field", "b200rt_reshape", "b200rt_reshape_back",
     "b200rt_upload_nbh_table", "b200rt_nccl_unique_id", "b200rt_comm_init_rank",
-    "b200rt_comm_destroy", "b200rt_halo_plan_create", "b200rt_halo_exchange",
+    "b200rt_comm_destroy", "b200rt_halo_plan_create", "b200rt_halo_plan_create2",
+    "b200rt_halo_exchange",
     "b200rt_halo_plan_destroy",
 ]
 
@@ -70,6 +71,8 @@ def lib():
         _lib.b200rt_nccl_unique_id.argtypes = [ctypes.c_void_p]
         _lib.b200rt_halo_plan_create.argtypes = [
             ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p] + [ctypes.c_int] * 10
+        _lib.b200rt_halo_plan_create2.argtypes = [
+            ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p] + [ctypes.c_int] * 11
         _lib.b200rt_halo_exchange.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _lib.b200rt_halo_plan_destroy.argtypes = [ctypes.c_void_p]
     return _lib

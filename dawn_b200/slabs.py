@@ -91,3 +91,52 @@ def exchange_torch(t, slab: Slab, width_minus: int, width_plus: int, dist):
     for buf, (a, b) in recvs:
         t[:, a:b, :] = buf
     return t
+
+
+# ------------------------------------------------------------------------------------------------
+# Unstructured: row slabs of a TriMesh
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class MeshSlab:
+    """Rank-local piece of a global TriMesh(nx, ny): the owned quad rows [j0, j0+nrows) plus one halo
+    quad row on every side that has a neighbour.  Element ids are row-major in j for all three
+    location types, so a quad row of edge slots / cells / vertices is a contiguous id range and the
+    Cartesian halo plan applies with rows = slot rows."""
+    rank: int
+    nranks: int
+    nx: int
+    j0: int        # first owned global quad row
+    nrows: int     # owned quad rows
+    halo_lo: int   # halo quad rows below (0 on the first rank)
+    halo_hi: int   # halo quad rows above (0 on the last rank)
+
+    @property
+    def local_ny(self):
+        return self.nrows + self.halo_lo + self.halo_hi
+
+    @property
+    def row_offset(self):
+        """global quad row of local quad row 0"""
+        return self.j0 - self.halo_lo
+
+    def slots_per_row(self, loc):
+        """elements per row of slots: 0 cells, 1 edges, 2 vertices"""
+        return (2 * self.nx, 3 * (self.nx + 1), self.nx + 1)[loc]
+
+    def owned_slice(self, loc):
+        """local id range of the elements this rank owns (edges/vertices of the row above the last
+        owned quad row belong to the next rank, except on the last rank)"""
+        n = self.slots_per_row(loc)
+        rows = self.nrows + (1 if (loc != 0 and self.halo_hi == 0) else 0)
+        return slice(self.halo_lo * n, (self.halo_lo + rows) * n)
+
+    def global_slice(self, loc):
+        n = self.slots_per_row(loc)
+        rows = self.nrows + (1 if (loc != 0 and self.halo_hi == 0) else 0)
+        return slice(self.j0 * n, (self.j0 + rows) * n)
+
+
+def mesh_slab(nx: int, ny: int, nranks: int, rank: int) -> MeshSlab:
+    sl = decompose(ny, nranks, rank, 1)
+    return MeshSlab(rank, nranks, nx, sl.j0, sl.nj_local, 1 if rank > 0 else 0,
+                    1 if rank + 1 < nranks else 0)

@@ -139,6 +139,12 @@ typedef struct b200_halo_plan b200_halo_plan;
 int b200rt_halo_plan_create(b200_halo_plan** plan, void* comm, int rank, int nranks, int ni, int nj,
                             int nk, int stride_j, int stride_k, int halo_j, int width_minus,
                             int width_plus);
+/* Same with different halo depths at the two ends: rows [0,halo_lo) and [nj-halo_hi,nj) are halo rows
+ * (a slab at the edge of the global domain has no halo on that side; row slabs of an unstructured
+ * triangle mesh exchange whole rows of edge/cell/vertex slots this way). */
+int b200rt_halo_plan_create2(b200_halo_plan** plan, void* comm, int rank, int nranks, int ni, int nj,
+                             int nk, int stride_j, int stride_k, int halo_lo, int halo_hi,
+                             int width_minus, int width_plus);
 int b200rt_halo_exchange(b200_halo_plan* plan, double* field, void* stream);
 int b200rt_halo_plan_destroy(b200_halo_plan* plan);
 

@@ -66,9 +66,64 @@ def main():
     dist.all_reduce(res, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("MULTIGPU_OK" if int(res) == 1 else "MULTIGPU_MISMATCH", "ranks", world)
+    ok_icon = icon_check(rank, world, comm, stream)
+    res2 = torch.tensor([1 if ok_icon else 0], device="cuda")
+    dist.all_reduce(res2, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTIGPU_ICON_OK" if int(res2) == 1 else "MULTIGPU_ICON_MISMATCH", "ranks", world)
     rt.lib().b200rt_comm_destroy(comm)
     dist.destroy_process_group()
-    sys.exit(0 if int(res) == 1 else 1)
+    sys.exit(0 if int(res) == 1 and int(res2) == 1 else 1)
+
+
+def icon_check(rank, world, comm, stream):
+    """ICON nabla2 on row slabs of a TriMesh: 1 halo quad row, `vec` exchanged over NCCL, owned edges
+    must equal the oracle's result on the undivided mesh bit for bit."""
+    from oracle import naive_interp
+    from util import iir_path
+    from dawn_b200.trimesh import CELL, EDGE, VERTEX, TriMesh
+    nx, ny, K = 9, 5 * world + 2, 4
+    gm = TriMesh(nx, ny)
+    rng = np.random.default_rng(77)
+    locs = {"vec": EDGE, "div_vec": CELL, "rot_vec": VERTEX, "nabla2_vec": EDGE,
+            "primal_edge_length": EDGE, "dual_edge_length": EDGE, "tangent_orientation": EDGE,
+            "geofac_rot": VERTEX, "geofac_div": CELL}
+    G = {n: rng.uniform(0.5, 1.5, (K, gm.num(l))) for n, l in locs.items() if not n.startswith("geofac")}
+    G["geofac_rot"] = rng.uniform(-1, 1, (K, gm.num_vertices, 6))
+    G["geofac_div"] = rng.uniform(-1, 1, (K, gm.num_cells, 3))
+    want = {n: v.copy() for n, v in G.items()}
+    want["__tmp_nab_60"] = np.zeros((K, gm.num_edges))
+    want["__tmp_nab_61"] = np.zeros((K, gm.num_edges))
+    naive_interp.run_unstructured(iir_path("ICON_laplacian_stencil"), gm, K, want)
+    sl = slabs.mesh_slab(nx, ny, world, rank)
+    lm = TriMesh(nx, sl.local_ny)
+    mod = dawn_b200.load_stencil("ICON_laplacian_stencil")
+    st = mod.on_mesh(lm, K)
+    tens = {}
+    for fd in mod.fields:
+        l = locs[fd["name"]]
+        per = sl.slots_per_row(l)
+        a = G[fd["name"]][:, sl.row_offset * per: sl.row_offset * per + lm.num(l)].copy()
+        if fd["name"] == "vec":  # halo rows must come from the neighbours
+            if sl.halo_lo:
+                a[:, :per] = np.nan
+            if sl.halo_hi:
+                a[:, (sl.local_ny - 1) * per: sl.local_ny * per] = np.nan
+        if fd["sparse"]:
+            a = np.ascontiguousarray(a.transpose(0, 2, 1))
+        tens[fd["name"]] = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    per = sl.slots_per_row(EDGE)
+    plan = ctypes.c_void_p()
+    rt.check(rt.lib().b200rt_halo_plan_create2(ctypes.byref(plan), comm, rank, world, per, sl.local_ny,
+                                               K, per, lm.num_edges, sl.halo_lo, sl.halo_hi, 1, 1))
+    rt.check(rt.lib().b200rt_halo_exchange(plan, tens["vec"].data_ptr(), stream))
+    st.run(*[tens[fd["name"]] for fd in mod.fields])
+    torch.cuda.synchronize()
+    rt.check(rt.lib().b200rt_halo_plan_destroy(plan))
+    got = tens["nabla2_vec"].cpu().numpy()
+    o, g = sl.owned_slice(EDGE), sl.global_slice(EDGE)
+    valid = gm.edge_valid[g]
+    return bool(np.array_equal(got[:, o][:, valid], want["nabla2_vec"][:, g][:, valid]))
 
 
 if __name__ == "__main__":

@@ -224,6 +224,7 @@ def test_multi_gpu_slab_parity():
                         "--master-port", "29617", os.path.join(root, "tests", "multigpu_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert "MULTIGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "MULTIGPU_ICON_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
 @pytest.mark.parametrize("name,make,outs", [
