@@ -574,7 +574,9 @@ bool CartesianEmitter::planTma(KernelPlan& kp) const {
     if(sg.W > 256 || sg.H > 256)
       return false;
     sg.offset = offset;
-    offset += ((sg.W * sg.H + 15) / 16) * 16; // keep every field 128-byte aligned
+    // keep every field 128-byte aligned; RJ-1 spare rows so that unpredicated reads of a thread's
+    // invalid rows stay inside the slot
+    offset += ((sg.W * (sg.H + kp.RJ - 1) + 15) / 16) * 16;
     kp.staged.push_back(sg);
   }
   if(kp.staged.empty())
@@ -758,6 +760,9 @@ public:
   }
 
   // per micro-tile state
+  bool hoistInvariant = false;            // loads of k-less read-only fields go before the k loops
+  std::vector<std::string> invariantLoads;
+  std::map<std::string, std::string> invariantNo;
   std::vector<std::string> loads; // hoisted loads (read-only fields)
   std::vector<std::string> temps; // inlined temporary evaluations
   std::map<std::string, std::string> valueNo;
@@ -831,19 +836,28 @@ public:
       if(it != valueNo.end())
         return it->second;
       std::string var = fieldName(e.accessID) + "_" + offTag(di) + "_" + offTag(djAbs) + "_s";
-      int firstRow = std::max(0, std::min(rows - 1, curRow));
-      std::string guard = rowGuards ? "v" + std::to_string(firstRow) + " ? " : "";
-      std::string tail = rowGuards ? " : (::dawn::float_type)0" : "";
-      loads.push_back("const ::dawn::float_type " + var + " = " + guard + "s_" +
-                      fieldName(e.accessID) + "[(lyb + (" + std::to_string(djAbs - sg->jm) + ")) * " +
-                      std::to_string(sg->W) + " + lx + (" + std::to_string(di - sg->im) + ")]" + tail +
-                      ";");
+      // no predicate: rows past the thread's valid rows still lie inside the (padded) ring slot
+      loads.push_back("const ::dawn::float_type " + var + " = s_" + fieldName(e.accessID) +
+                      "[(lyb + (" + std::to_string(djAbs - sg->jm) + ")) * " + std::to_string(sg->W) +
+                      " + lx + (" + std::to_string(di - sg->im) + ")];");
       valueNo[key] = var;
       return var;
     }
     if(readOnly) {
       std::string key = "F" + std::to_string(e.accessID) + ":" + std::to_string(di) + ":" +
                         std::to_string(djAbs) + ":" + std::to_string(dk);
+      if(hoistInvariant && !m.k) {
+        auto iv = invariantNo.find(key);
+        if(iv != invariantNo.end())
+          return iv->second;
+        std::string var = fieldName(e.accessID) + "_" + offTag(di) + "_" + offTag(djAbs) + "_inv";
+        int firstRow = std::max(0, std::min(rows - 1, curRow));
+        invariantLoads.push_back("const ::dawn::float_type " + var + " = v" + std::to_string(firstRow) +
+                                 " ? __ldg(&" + address(e.accessID, di, djAbs, 0) +
+                                 ") : (::dawn::float_type)0;");
+        invariantNo[key] = var;
+        return var;
+      }
       auto it = valueNo.find(key);
       if(it != valueNo.end())
         return it->second;
@@ -1159,6 +1173,33 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
   std::set<int> producedSoFar;
   std::set<int> writtenSoFar; // fields stored by earlier multistages of this kernel
 
+  // Tile kernels whose live stages all run on the plain tile (no redundant halo computation): the
+  // thread -> point map is the same for every stage and level, so it is set up once and loads that
+  // do not depend on k (j/i-vectors, ij-fields) are issued once before the k loops.
+  bool uniformRegion = !kp.pointwise;
+  if(uniformRegion)
+    for(auto const* ms : kp.ms)
+      for(auto const& stage : ms->stages)
+        if(!droppedStages_.count(stage.id) && !stage.extent.horizontalZero())
+          uniformRegion = false;
+  if(uniformRegion) {
+    os_ << "  const int lx = tid % " << kp.TI << ";\n";
+    os_ << "  const int lyb = (tid / " << kp.TI << ") * " << kp.RJ << ";\n";
+    os_ << "  const int i = i0 + lx;\n";
+    os_ << "  const int jb = j0 + lyb;\n";
+    for(int r = 0; r < kp.RJ; ++r)
+      os_ << "  const bool v" << r << " = i <= nx - 1 && jb + " << r << " <= ny - 1;\n";
+    for(auto const& c : classes)
+      if(c[2] == '0') {
+        MaskClass m{c[0] == '1', c[1] == '1', false};
+        os_ << "  const int b" << c << " = 0" << (m.i ? " + i" : "")
+            << (m.j ? " + jb * " + m.sj() : std::string()) << ";\n";
+      }
+    be.hoistInvariant = true;
+  }
+  const std::string kernelHead = os_.str();
+  os_.str("");
+
   for(auto const* ms : kp.ms) {
     bool backward = ms->loopOrder == LoopOrder::Backward;
     bool sequential = ms->loopOrder != LoopOrder::Parallel;
@@ -1394,7 +1435,12 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         int rows = kp.pointwise ? 1 : kp.RJ;
         be.rows = rows;
         be.rowGuards = !kp.pointwise;
-        if(!kp.pointwise) {
+        if(uniformRegion) {
+          os_ << pad << "{\n";
+          pad += "  ";
+          os_ << pad << "{\n";
+          pad += "  ";
+        } else if(!kp.pointwise) {
           int W = kp.TI + ex.iPlus - ex.iMinus;
           int H = kp.tileJ() + ex.jPlus - ex.jMinus;
           int HC = (H + rows - 1) / rows;
@@ -1556,6 +1602,14 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         if(fp.second.written)
           writtenSoFar.insert(fp.first);
     }
+  }
+  {
+    const std::string body = os_.str();
+    os_.str("");
+    os_ << kernelHead;
+    for(auto const& l : be.invariantLoads)
+      os_ << "  " << l << "\n";
+    os_ << body;
   }
   os_ << "}\n\n";
 }
