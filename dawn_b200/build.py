@@ -103,6 +103,10 @@ VARIANTS = {
         dict(use_tma=0), dict(tma_stages=2, block_size_k=3), dict(inline_temporaries=0, use_tma=0),
     ],
     "ICON_laplacian_stencil": [dict(fuse_columns=0, levels_per_thread=1), dict(levels_per_thread=8)],
+    "kcache_fill": [dict(column_ring=0)], "kcache_flush": [dict(column_ring=0)],
+    "kcache_fill_backward": [dict(column_ring=0)], "intervals02": [dict(column_ring=0)],
+    "intervals03": [dict(column_ring=0)], "kparallel_solver": [dict(column_ring=0)],
+    "asymmetric_stencil": [dict(use_tma=0)], "coriolis_stencil": [dict(use_tma=0)],
     "tridiagonal_solve": [dict(fuse_columns=0), dict(column_ring=0), dict(column_ring=0, column_cache=1, prefetch_k=3),
                           dict(ring_levels=2, tma_stages=2), dict(block_size_i=32, block_size_j=2)],
 }

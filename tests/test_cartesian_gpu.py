@@ -264,3 +264,47 @@ def test_global_iteration_space_against_reference_golden():
     got = _run_gpu("nonoverlapping_stencil", (ni, nj, nk), {"in": inn, "out": np.full_like(inn, -1.0)},
                    ["in", "out"])
     assert bit_equal(got["out"][11:], g["nonoverlapping_from_k11"])
+
+
+# ---- stencils of the reference's executed integration tests
+# (gtclang/test/integration-test/CodeGen/<name>.cpp, run there at 12x12x10 against c++-naive) ----
+REF_INTEGRATION = [
+    ("kcache_fill", ["in", "out"]), ("kcache_flush", ["in", "out"]),
+    ("kcache_fill_backward", ["in", "out"]), ("local_kcache", ["out_a", "out_b", "out_c", "out_d"]),
+    ("intervals02", ["in", "out"]), ("intervals03", ["in", "out"]),
+    ("asymmetric_stencil", ["in", "out"]),
+    ("coriolis_stencil", ["u_tens", "u_nnow", "v_tens", "v_nnow", "fc"]),
+    ("globals_stencil", ["in", "out"]), ("kparallel_solver", ["d", "a", "b", "c"]),
+]
+PLAIN = {"kcache_fill": dict(column_ring=0), "kcache_flush": dict(column_ring=0),
+         "kcache_fill_backward": dict(column_ring=0), "intervals02": dict(column_ring=0),
+         "intervals03": dict(column_ring=0), "kparallel_solver": dict(column_ring=0),
+         "asymmetric_stencil": dict(use_tma=0), "coriolis_stencil": dict(use_tma=0)}
+
+
+@pytest.mark.parametrize("name,order", REF_INTEGRATION)
+@pytest.mark.parametrize("size", [(12, 12, 10), (70, 37, 21)])
+@pytest.mark.parametrize("plain", [False, True])
+def test_reference_integration_stencils(name, order, size, plain):
+    if plain and name not in PLAIN:
+        pytest.skip("no separate plain variant")
+    I, J, K = size
+    ni, nj = I + 2 * HALO, J + 2 * HALO
+    rng = np.random.default_rng(41)
+    f = {n: rng.uniform(0.5, 1.5, (K + 1, nj, ni)) for n in order}
+    want = run_oracle(name, (ni, nj, K), f)
+    got = _run_gpu(name, (ni, nj, K), f, order, **(PLAIN[name] if plain else {}))
+    for n in order:
+        assert bit_equal(got[n], want[n]), n
+
+
+def test_globals_of_every_type_reach_the_kernel():
+    I, J, K = 20, 10, 4
+    ni, nj = I + 2 * HALO, J + 2 * HALO
+    rng = np.random.default_rng(43)
+    f = {"in": rng.uniform(0.5, 1.5, (K + 1, nj, ni)), "out": np.full((K + 1, nj, ni), -1.0)}
+    for g in ({"var_runtime": 5, "var_default": 0.25, "var_compiletime": 1},
+              {"var_runtime": 5, "var_default": 0.25, "var_compiletime": 0}):
+        want = run_oracle("globals_stencil", (ni, nj, K), f, globals_=g)
+        got = _run_gpu("globals_stencil", (ni, nj, K), f, ["in", "out"], globals_=g)
+        assert bit_equal(got["out"], want["out"])

@@ -249,6 +249,140 @@ def unstructured_intp():
     return b
 
 
+# ---- reference integration-test stencils (gtclang/test/integration-test/CodeGen/<name>.cpp) --------
+def kcache_fill():
+    b = IIRBuilder("kcache_fill")
+    i, o = b.field("in"), b.field("out")
+    st = b.stage(
+        b.do(Interval("Start", "Start", 2, 2),
+             b.assign(o, i() + i(0, 0, 1) + i(0, 0, 2) + i(0, 0, -1) + i(0, 0, -2))),
+        b.do(Interval("Start", "End", 3, -2),
+             b.assign(o, i() + i(0, 0, -1) + i(0, 0, 1) + i(0, 0, 2) + o(0, 0, -1))),
+        b.do(Interval("End", "End", -1, -1), b.assign(o, i() + i(0, 0, -1) + i(0, 0, 1) + o(0, 0, -1))),
+        b.do(Interval("End", "End", 0, 0), b.assign(o, i() + i(0, 0, -1) + o(0, 0, -1))))
+    b.stencil(b.multistage("Forward", st))
+    return b
+
+
+def kcache_flush():
+    b = IIRBuilder("kcache_flush")
+    i, o = b.field("in"), b.field("out")
+    st = b.stage(
+        b.do(Interval("Start", "Start", 1, 2), b.assign(o, i() + i(0, 0, 1) + i(0, 0, 2) + i(0, 0, -1))),
+        b.do(Interval("Start", "End", 3, -2),
+             b.assign(o, i() + i(0, 0, -1) + i(0, 0, 1) + i(0, 0, 2) + o(0, 0, -1) + o(0, 0, -2))),
+        b.do(Interval("End", "End", -1, -1),
+             b.assign(o, i() + i(0, 0, -1) + i(0, 0, 1) + o(0, 0, -1) + o(0, 0, -2) + o(0, 0, -3))),
+        b.do(Interval("End", "End", 0, 0), b.assign(o, i() + i(0, 0, -1) + o(0, 0, -1))))
+    b.stencil(b.multistage("Forward", st))
+    return b
+
+
+def kcache_fill_backward():
+    b = IIRBuilder("kcache_fill_backward")
+    i, o = b.field("in"), b.field("out")
+    st = b.stage(
+        b.do(Interval("End", "End", -2, -2),
+             b.assign(o, i() + i(0, 0, -1) + i(0, 0, -2) + i(0, 0, 1) + i(0, 0, 2))),
+        b.do(Interval("Start", "End", 2, -3),
+             b.assign(o, i() + i(0, 0, 1) + i(0, 0, -1) + i(0, 0, -2) + o(0, 0, 1))),
+        b.do(Interval("Start", "Start", 1, 1), b.assign(o, i() + i(0, 0, 1) + i(0, 0, -1) + o(0, 0, 1))),
+        b.do(Interval("Start", "Start", 0, 0), b.assign(o, i() + i(0, 0, 1) + o(0, 0, 1))))
+    b.stencil(b.multistage("Backward", st))
+    return b
+
+
+def local_kcache():
+    b = IIRBuilder("local_kcache")
+    oa, ob, oc, od = b.field("out_a"), b.field("out_b"), b.field("out_c"), b.field("out_d")
+    a, bb, c, d = b.tmp("a"), b.tmp("b"), b.tmp("c"), b.tmp("d")
+    fwd = b.stage(
+        b.do(Interval("Start", "Start", 0, 0), b.assign(c, 2.1), b.assign(d, 3.1), b.assign(oc, c()),
+             b.assign(od, d())),
+        b.do(Interval("Start", "Start", 1, 1), b.assign(d, 4.1), b.assign(od, d()), b.assign(oc, c())),
+        b.do(Interval("Start", "End", 2, 0), b.assign(c, c(0, 0, -1) * 1.1),
+             b.assign(d, d(0, 0, -1) * 1.1 + d(0, 0, -2) * 1.2), b.assign(oc, c()), b.assign(od, d())))
+    bwd = b.stage(
+        b.do(Interval("End", "End", 0, 0), b.assign(a, 2.1), b.assign(bb, 3.1), b.assign(oa, a()),
+             b.assign(ob, bb())),
+        b.do(Interval("End", "End", -1, -1), b.assign(bb, 4.1), b.assign(ob, bb()), b.assign(oa, a())),
+        b.do(Interval("Start", "End", 0, -2), b.assign(a, a(0, 0, 1) * 1.1),
+             b.assign(bb, bb(0, 0, 1) * 1.1 + bb(0, 0, 2) * 1.2), b.assign(oa, a()), b.assign(ob, bb())))
+    b.stencil(b.multistage("Forward", fwd), b.multistage("Backward", bwd))
+    return b
+
+
+def intervals02():
+    # k_flat = 4 (an interval level of the DSL; any fixed level below k_end)
+    b = IIRBuilder("intervals02")
+    i, o = b.field("in"), b.field("out")
+    st = b.stage(
+        b.do(Interval("Start", "Start", 1, 1), b.assign(o, 0)),
+        b.do(Interval("Start", 4, 2, 0), b.assign(o, o(0, 0, -1) + i() + 1)),
+        b.do(Interval(4, 4, 2, 2), b.assign(o, 0)),
+        b.do(Interval(4, "End", 3, -1), b.assign(o, o(0, 0, -1) + i() + 3)))
+    b.stencil(b.multistage("Forward", st))
+    return b
+
+
+def intervals03():
+    b = IIRBuilder("intervals03")
+    i, o = b.field("in"), b.field("out")
+    st = b.stage(
+        b.do(Interval("End", "End", -1, -1), b.assign(o, 0)),
+        b.do(Interval(6, "End", 0, -2), b.assign(o, o(0, 0, 1) + i() + 3)),
+        b.do(Interval(6, 6, -2, -2), b.assign(o, 1)),
+        b.do(Interval("Start", 6, 0, -3), b.assign(o, o(0, 0, 1) + i() + 3)))
+    b.stencil(b.multistage("Backward", st))
+    return b
+
+
+def asymmetric():
+    b = IIRBuilder("asymmetric_stencil")
+    i, o = b.field("in"), b.field("out")
+    tmp = b.tmp("tmp")
+    s1 = b.stage(b.do(Interval("Start", "Start", 0, 0), b.assign(tmp, i(1, 0) + i(0, -2))),
+                 b.do(Interval("Start", "End", 1, 0), b.assign(tmp, i(-3, 0) + i(0, 1))))
+    s2 = b.stage(b.do(Interval("Start", "Start", 0, 0), b.assign(o, 1)),
+                 b.do(Interval("Start", "End", 1, 0), b.assign(o, tmp(0, 0, -1))))
+    b.stencil(b.multistage("Forward", s1, s2))
+    return b
+
+
+def coriolis():
+    b = IIRBuilder("coriolis_stencil")
+    ut, un, vt, vn, fc = (b.field(n) for n in ("u_tens", "u_nnow", "v_tens", "v_nnow", "fc"))
+    d1, zn = b.local("z_fv_north", fc() * (vn() + vn(1, 0)), "Double")
+    d2, zs = b.local("z_fv_south", fc(0, -1) * (vn(0, -1) + vn(1, -1)), "Double")
+    d3, ze = b.local("z_fu_east", fc() * (un() + un(0, 1)), "Double")
+    d4, zw = b.local("z_fu_west", fc(-1, 0) * (un(-1, 0) + un(-1, 1)), "Double")
+    st = b.stage(b.do(FULL, d1, d2, b.assign(ut, 0.25 * (zn + zs), op="+="), d3, d4,
+                      b.assign(vt, 0.25 * (ze + zw), op="-=")))
+    b.stencil(b.multistage("Parallel", st))
+    return b
+
+
+def globals_stencil():
+    b = IIRBuilder("globals_stencil")
+    vr = b.global_var("var_runtime", "Integer", 1)
+    vd = b.global_var("var_default", "Double", 2.0)
+    vc = b.global_var("var_compiletime", "Boolean", 1)
+    i, o = b.field("in"), b.field("out")
+    st = b.stage(b.do(FULL, b.if_(vc, [b.assign(o, i() + vr + vd)])))
+    b.stencil(b.multistage("Parallel", st))
+    return b
+
+
+def kparallel_solver():
+    b = IIRBuilder("kparallel_solver")
+    d, a, bb, c = b.field("d"), b.field("a"), b.field("b"), b.field("c")
+    s1 = b.stage(b.do(Interval("Start", "Start", 0, 0), b.assign(c, a(0, 0, 1)), b.assign(d, bb() * 2.1)),
+                 b.do(Interval("Start", "End", 1, 0), b.assign(c, a(0, 0, -1)), b.assign(d, bb() * 2.0 - 1)))
+    s2 = b.stage(b.do(Interval("Start", "End", 0, -1), b.assign(d, d() + a(), op="-=")))
+    b.stencil(b.multistage("Parallel", s1), b.multistage("Parallel", s2))
+    return b
+
+
 ALL = {
     "hori_diff_type2_stencil": hori_diff_type2,
     "hori_diff_stencil_01": hori_diff_01,
@@ -258,6 +392,16 @@ ALL = {
     "copy_stencil": copy_stencil,
     "global_indexing": global_indexing,
     "nonoverlapping_stencil": nonoverlapping,
+    "kcache_fill": kcache_fill,
+    "kcache_flush": kcache_flush,
+    "kcache_fill_backward": kcache_fill_backward,
+    "local_kcache": local_kcache,
+    "intervals02": intervals02,
+    "intervals03": intervals03,
+    "asymmetric_stencil": asymmetric,
+    "coriolis_stencil": coriolis,
+    "globals_stencil": globals_stencil,
+    "kparallel_solver": kparallel_solver,
     "ICON_laplacian_stencil": icon_laplacian,
     "diffusion": unstructured_diffusion,
     "gradient": unstructured_gradient,
