@@ -334,11 +334,16 @@ def run_gpu(args):
     for h, s in zip(host, fields):
         h.copy_(s.view())
     st2 = mod(dom)
+    # inputs go up and the result comes down every step; `out` is write-only, so it is not an input
+    # (uploaded once by the warm-up call); levels are independent, so the domain is streamed through
+    # the device in chunks of 8 levels with H2D, kernels and D2H overlapping
+    e2e_kw = dict(upload_outputs=False, k_chunk=8)
     h2d, d2h = st2.run_from_host(*host)  # warm-up (allocates the device-side storages)
+    h2d, d2h = st2.run_from_host(*host, **e2e_kw)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        h2d, d2h = st2.run_from_host(*host)
+        h2d, d2h = st2.run_from_host(*host, **e2e_kw)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
@@ -380,7 +385,8 @@ def run_gpu(args):
             },
             "e2e": {"value": pts * world * e2e_steps / e2e_s, "unit": "grid-point updates/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "dawn_b200.Stencil.run_from_host (pinned host buffers)"},
+                    "api": "dawn_b200.Stencil.run_from_host(pinned host buffers, upload_outputs=False, "
+                           "k_chunk=8): inputs H2D + result D2H every step, pipelined over k chunks"},
             "gpu_launches": launches,
             "clocks": clocks,
         }

@@ -2096,8 +2096,18 @@ void CartesianEmitter::emitCAbi() {
       if(fe.count(f))
         e.merge(fe[f]);
     }
+    bool readAnywhere = false;
+    for(auto const& st : inst_.stencils)
+      for(auto const& ms : st.multiStages)
+        for(auto const& stage : ms.stages) {
+          StageInfo info = analysis::stageInfo(inst_, stage);
+          auto it = info.fields.find(f);
+          if(it != info.fields.end() && it->second.read)
+            readAnywhere = true;
+        }
     os_ << (a ? ", " : "") << "{\\\"name\\\": \\\"" << inst_.nameOf(f) << "\\\", \\\"dims\\\": \\\""
-        << (m.i ? "i" : "") << (m.j ? "j" : "") << (m.k ? "k" : "") << "\\\", \\\"extent\\\": ["
+        << (m.i ? "i" : "") << (m.j ? "j" : "") << (m.k ? "k" : "") << "\\\", \\\"write_only\\\": "
+        << ((writtenFields_.count(f) && !readAnywhere) ? "true" : "false") << ", \\\"extent\\\": ["
         << e.iMinus << ", " << e.iPlus << ", " << e.jMinus << ", " << e.jPlus << ", " << e.kMinus
         << ", " << e.kPlus << "]}";
   }
@@ -2110,7 +2120,27 @@ void CartesianEmitter::emitCAbi() {
         firstW = false;
       }
   }
-  os_ << "], \\\"globals\\\": [";
+  {
+    // levels are independent (every multistage Parallel, no vertical offsets): a host may stream the
+    // domain through the device in k chunks
+    bool kParallel = true;
+    for(auto const& st : inst_.stencils)
+      for(auto const& ms : st.multiStages) {
+        if(ms.loopOrder != LoopOrder::Parallel)
+          kParallel = false;
+        for(auto const& stage : ms.stages) {
+          for(auto const& dm : stage.doMethods) {
+            if(dm.interval.lowerBound() != 0 || dm.interval.upperBound() != Interval::End)
+              kParallel = false;
+            analysis::visitStmts(dm.stmts, [&](const Expr& e, bool) {
+              if(e.kind == Expr::Field && e.dk != 0)
+                kParallel = false;
+            });
+          }
+        }
+      }
+    os_ << "], \\\"k_parallel\\\": " << (kParallel ? "true" : "false") << ", \\\"globals\\\": [";
+  }
   for(size_t g = 0; g < inst_.globals.size(); ++g)
     os_ << (g ? ", " : "") << "\\\"" << inst_.globals[g].first << "\\\"";
   os_ << "]}\";\n}\n";

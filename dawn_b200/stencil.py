@@ -193,21 +193,26 @@ class Stencil:
             _rt.check(self.module._run_rows(self.handle, arr, n, ctypes.c_void_p(stream),
                                             int(rows[0]), int(rows[1])))
 
-    def run_from_host(self, *arrays, stream=None):
+    def run_from_host(self, *arrays, stream=None, upload_outputs=True, k_chunk=0):
         """End-to-end call with HOST buffers in API order, indexed [k, j, i] (length 1 along masked
         dimensions): numpy arrays, or torch CPU tensors (pinned ones are copied from directly).
         Copies the inputs host->device, runs, and copies every field the stencil writes back into
-        the given buffers.  Returns (h2d_bytes, d2h_bytes)."""
+        the given buffers.  Returns (h2d_bytes, d2h_bytes).
+
+        upload_outputs=False skips the upload of fields the stencil only writes (their halo on the
+        device is whatever an earlier call uploaded).  k_chunk > 0 streams a level-independent stencil
+        (module.info["k_parallel"]) through the device in chunks of k_chunk levels on three streams,
+        so that H2D copies, kernels and D2H copies of different chunks overlap (PCIe is full duplex)."""
         import torch
         dom = self.domain
         if self._host_storages is None:
             self._host_storages = [Storage(dom.isize, dom.jsize, a.shape[0], f["dims"])
                                    for f, a in zip(self.module.fields, arrays)]
             self._pinned = [None] * len(arrays)
+            self._uploaded_once = False
         written = self.written_fields()
-        h2d = d2h = 0
         staged = []
-        for n, (st, a) in enumerate(zip(self._host_storages, arrays)):
+        for n, a in enumerate(arrays):
             if isinstance(a, torch.Tensor) and a.is_pinned():
                 pin = a
             else:
@@ -216,20 +221,91 @@ class Stencil:
                 pin = self._pinned[n]
                 pin.copy_(a if isinstance(a, torch.Tensor) else torch.from_numpy(a))
             staged.append(pin)
-            st.view().copy_(pin.reshape(st.shape[2], st.shape[1], st.shape[0]), non_blocking=True)
-            h2d += pin.numel() * 8
-        self.run(*self._host_storages, stream=stream)
-        for f, st, pin in zip(self.module.fields, self._host_storages, staged):
-            if f["name"] in written:
-                pin.reshape(st.shape[2], st.shape[1], st.shape[0]).copy_(st.view(), non_blocking=True)
-                d2h += pin.numel() * 8
-        torch.cuda.current_stream().synchronize()
+
+        def needs_upload(f):
+            if f["name"] not in written:
+                return True
+            return upload_outputs or not self._uploaded_once or not f.get("write_only", False)
+
+        if k_chunk and self.module.info.get("k_parallel") and all(
+                f["dims"] in ("ijk", "ij", "i", "j") for f in self.module.fields):
+            h2d, d2h = self._run_chunked(staged, k_chunk, needs_upload, written)
+        else:
+            h2d = d2h = 0
+            for f, st, pin in zip(self.module.fields, self._host_storages, staged):
+                if needs_upload(f):
+                    st.view().copy_(pin.reshape(st.shape[2], st.shape[1], st.shape[0]),
+                                    non_blocking=True)
+                    h2d += pin.numel() * 8
+            self.run(*self._host_storages, stream=stream)
+            for f, st, pin in zip(self.module.fields, self._host_storages, staged):
+                if f["name"] in written:
+                    pin.reshape(st.shape[2], st.shape[1], st.shape[0]).copy_(st.view(),
+                                                                             non_blocking=True)
+                    d2h += pin.numel() * 8
+            torch.cuda.current_stream().synchronize()
+        self._uploaded_once = True
         for f, a, pin in zip(self.module.fields, arrays, staged):
             if f["name"] in written and pin is not a:
                 if isinstance(a, torch.Tensor):
                     a.copy_(pin)
                 else:
                     np.copyto(a, pin.numpy())
+        return h2d, d2h
+
+    def _run_chunked(self, staged, k_chunk, needs_upload, written):
+        """H2D / compute / D2H software pipeline over chunks of levels."""
+        import torch
+        dom = self.domain
+        nz = dom.ksize
+        if not hasattr(self, "_chunk_streams"):
+            self._chunk_streams = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream())
+            self._chunk_instances = {}
+        s_up, s_run, s_down = self._chunk_streams
+        main = torch.cuda.current_stream()
+        for s in self._chunk_streams:
+            s.wait_stream(main)
+        h2d = d2h = 0
+        fields = self.module.fields
+        # fields without a k dimension go up once
+        with torch.cuda.stream(s_up):
+            for f, st, pin in zip(fields, self._host_storages, staged):
+                if "k" not in f["dims"] and needs_upload(f):
+                    st.view().copy_(pin.reshape(st.shape[2], st.shape[1], st.shape[0]),
+                                    non_blocking=True)
+                    h2d += pin.numel() * 8
+        for k0 in range(0, nz, k_chunk):
+            kc = min(k_chunk, nz - k0)
+            ev_up, ev_run = torch.cuda.Event(), torch.cuda.Event()
+            with torch.cuda.stream(s_up):
+                for f, st, pin in zip(fields, self._host_storages, staged):
+                    if "k" in f["dims"] and needs_upload(f):
+                        st.view()[k0:k0 + kc].copy_(pin[k0:k0 + kc], non_blocking=True)
+                        h2d += pin[k0:k0 + kc].numel() * 8
+                ev_up.record(s_up)
+            inst = self._chunk_instances.get(kc)
+            if inst is None:
+                d = Domain(dom.isize, dom.jsize, kc)
+                d.halos = list(dom.halos)
+                inst = self._chunk_instances[kc] = Stencil(self.module, d)
+            descs = []
+            for f, st in zip(fields, self._host_storages):
+                fd = st.descriptor()
+                if "k" in f["dims"]:
+                    fd = _rt.Field(fd.data + 8 * k0 * st.stride_k, fd.stride_j, fd.stride_k)
+                descs.append(fd)
+            s_run.wait_event(ev_up)
+            inst.run(*descs, stream=s_run.cuda_stream)
+            ev_run.record(s_run)
+            s_down.wait_event(ev_run)
+            with torch.cuda.stream(s_down):
+                for f, st, pin in zip(fields, self._host_storages, staged):
+                    if f["name"] in written and "k" in f["dims"]:
+                        pin[k0:k0 + kc].copy_(st.view()[k0:k0 + kc], non_blocking=True)
+                        d2h += pin[k0:k0 + kc].numel() * 8
+        for s in self._chunk_streams:
+            main.wait_stream(s)
+        main.synchronize()
         return h2d, d2h
 
     def written_fields(self):

@@ -308,3 +308,23 @@ def test_globals_of_every_type_reach_the_kernel():
         want = run_oracle("globals_stencil", (ni, nj, K), f, globals_=g)
         got = _run_gpu("globals_stencil", (ni, nj, K), f, ["in", "out"], globals_=g)
         assert bit_equal(got["out"], want["out"])
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(k_chunk=3), dict(k_chunk=4, upload_outputs=False)])
+def test_run_from_host_end_to_end(kw):
+    """Host buffers in, host buffers out (H2D + kernels + D2H), plain and k-chunk pipelined."""
+    import dawn_b200
+    I, J, K = 50, 31, 10
+    f = hori_diff_type2_inputs(I, J, K)
+    dims = (I + 2 * HALO, J + 2 * HALO, K)
+    want = run_oracle("hori_diff_type2_stencil", dims, f)
+    mod = dawn_b200.load_stencil("hori_diff_type2_stencil")
+    assert mod.info["k_parallel"] is True
+    dom = dawn_b200.Domain(*dims)
+    st = mod(dom)
+    host = [f[fd["name"]].copy() for fd in mod.fields]
+    for rep in range(2):   # second call exercises the upload_outputs=False path
+        h2d, d2h = st.run_from_host(*host, **kw)
+        assert bit_equal(host[0], want["out"])
+        assert d2h > 0 and h2d > 0
+    assert dawn_b200.load_stencil("tridiagonal_solve").info["k_parallel"] is False
