@@ -92,3 +92,20 @@ def ico_chain_size(chain, include_center=False) -> int:
     """ICOChainSize (dawn/src/dawn/CodeGen/IcoChainSizes.cpp:199-264). chain: 0 cell,1 edge,2 vertex."""
     arr = (ctypes.c_int * len(chain))(*chain)
     return _load().dawn_b200_ico_chain_size(arr, len(chain), int(include_center))
+
+
+def interface_text(iir_json: str, kind="c") -> str:
+    """C header (kind="c") or Fortran interface module (kind="f90") of an unstructured stencil's C ABI
+    (the reference's --output-c-header / --output-f90-interface)."""
+    lib = _load()
+    data = iir_json.encode() if isinstance(iir_json, str) else iir_json
+    out = ctypes.c_void_p()
+    n = ctypes.c_size_t()
+    rc = lib.dawn_b200_codegen_interface(data, ctypes.c_size_t(len(data)), 0 if kind == "c" else 1,
+                                         ctypes.byref(out), ctypes.byref(n))
+    if rc != 0:
+        raise CodeGenError(lib.dawn_b200_codegen_last_error().decode())
+    try:
+        return ctypes.string_at(out.value, n.value).decode()
+    finally:
+        lib.dawn_b200_free(out)

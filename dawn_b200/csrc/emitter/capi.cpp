@@ -84,6 +84,28 @@ int dawn_b200_codegen_run(const char* const* names, const char* const* iir_json,
   }
 }
 
+int dawn_b200_codegen_interface(const char* iir_json, size_t iir_len, int kind, char** out_text,
+                                size_t* out_len) {
+  try {
+    auto inst = b200::iir::parseInstantiation(iir_len ? std::string(iir_json, iir_len)
+                                                      : std::string(iir_json));
+    if(!inst.unstructured)
+      throw std::invalid_argument("interface files are generated for unstructured instantiations");
+    std::string text = kind == 0 ? b200::codegen::icoCHeader(inst) : b200::codegen::icoF90Interface(inst);
+    char* buf = static_cast<char*>(std::malloc(text.size() + 1));
+    if(!buf)
+      throw std::bad_alloc();
+    std::memcpy(buf, text.c_str(), text.size() + 1);
+    *out_text = buf;
+    if(out_len)
+      *out_len = text.size();
+    return 0;
+  } catch(std::exception& e) {
+    g_error = e.what();
+    return 1;
+  }
+}
+
 void dawn_b200_free(void* p) { std::free(p); }
 const char* dawn_b200_codegen_last_error(void) { return g_error.c_str(); }
 

@@ -63,6 +63,9 @@ TranslationUnit run(const std::map<std::string, std::string>& context, Backend b
 // Per-backend entry points (twins of cuda::run / cudaico::run).
 TranslationUnit runCartesian(const std::map<std::string, iir::Instantiation>& ctx, const Options&);
 TranslationUnit runIco(const std::map<std::string, iir::Instantiation>& ctx, const Options&);
+// interface files of the b200-ico C ABI (twins of --output-c-header / --output-f90-interface)
+std::string icoCHeader(const iir::Instantiation& inst);
+std::string icoF90Interface(const iir::Instantiation& inst);
 
 } // namespace codegen
 } // namespace b200

@@ -679,6 +679,82 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
     os_ << ");\n      ++m_launches;\n    }\n";
   }
   os_ << "    return ::dawn_b200::check_launch();\n  }\n";
+  // ---- host-buffer entry points (reference: run_<N>_from_{c,fort}_host, CudaIcoCodeGen.cpp:896-927;
+  // cuda_utils.hpp:81-125,181-195 do the transposition on one host thread, here it is a GPU kernel) --
+  os_ << "  // number of doubles of API field `a`\n";
+  os_ << "  size_t field_elems(int a) const {\n    switch(a) {\n";
+  for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a) {
+    int f = inst_.apiFieldIDs[a];
+    os_ << "    case " << a << ": return (size_t)m_k_size";
+    if(!isVertical(f))
+      os_ << " * m_mesh.num_" << locName(fieldLoc(f)) << (isSparse(f) ? " * " + std::to_string(sparseSize(f)) : std::string());
+    os_ << ";\n";
+  }
+  os_ << "    default: return 0;\n    }\n  }\n";
+  os_ << "  int run_from_host(double* const* host, bool element_major, void* stream) {\n";
+  os_ << "    const int nf = " << inst_.apiFieldIDs.size() << ";\n";
+  os_ << "    double* dev[" << std::max<size_t>(1, inst_.apiFieldIDs.size()) << "] = {};\n";
+  os_ << "    double* tmp = nullptr;\n    size_t tmp_elems = 0;\n    int err = 0;\n";
+  os_ << "    for(int a = 0; a < nf; ++a) tmp_elems = field_elems(a) > tmp_elems ? field_elems(a) : tmp_elems;\n";
+  os_ << "    if(element_major) err = b200rt_malloc((void**)&tmp, tmp_elems * sizeof(double));\n";
+  os_ << "    b200_field_t f[" << std::max<size_t>(1, inst_.apiFieldIDs.size()) << "];\n";
+  os_ << "    static const int sparse_of[] = {";
+  for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a)
+    os_ << (a ? ", " : "") << (isSparse(inst_.apiFieldIDs[a]) ? sparseSize(inst_.apiFieldIDs[a]) : 1);
+  os_ << "};\n    const int elems_of[] = {";
+  for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a) {
+    int f = inst_.apiFieldIDs[a];
+    os_ << (a ? ", " : "") << (isVertical(f) ? std::string("1") : "m_mesh.num_" + locName(fieldLoc(f)));
+  }
+  os_ << "};\n    static const bool written_of[] = {";
+  {
+    std::set<int> written;
+    for(auto const& g : groups)
+      written.insert(g.fieldsWritten.begin(), g.fieldsWritten.end());
+    for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a)
+      os_ << (a ? ", " : "") << (written.count(inst_.apiFieldIDs[a]) ? "true" : "false");
+  }
+  os_ << "};\n";
+  os_ << "    for(int a = 0; a < nf && !err; ++a) {\n";
+  os_ << "      const size_t bytes = field_elems(a) * sizeof(double);\n";
+  os_ << "      err = b200rt_malloc((void**)&dev[a], bytes);\n";
+  os_ << "      if(err) break;\n";
+  os_ << "      if(element_major && elems_of[a] > 1) {\n";
+  os_ << "        err = b200rt_memcpy_h2d(tmp, host[a], bytes, stream);\n";
+  os_ << "        if(!err) err = b200rt_reshape(tmp, dev[a], m_k_size, elems_of[a], sparse_of[a], stream);\n";
+  os_ << "      } else\n        err = b200rt_memcpy_h2d(dev[a], host[a], bytes, stream);\n";
+  os_ << "      f[a].data = dev[a];\n";
+  os_ << "      f[a].stride_j = sparse_of[a] > 1 ? elems_of[a] : 0;\n";
+  os_ << "      f[a].stride_k = elems_of[a] * sparse_of[a];\n";
+  os_ << "    }\n";
+  os_ << "    if(!err) err = launch(f, stream);\n";
+  os_ << "    for(int a = 0; a < nf && !err; ++a) {\n      if(!written_of[a]) continue;\n";
+  os_ << "      const size_t bytes = field_elems(a) * sizeof(double);\n";
+  os_ << "      if(element_major && elems_of[a] > 1) {\n";
+  os_ << "        err = b200rt_reshape_back(dev[a], tmp, m_k_size, elems_of[a], sparse_of[a], stream);\n";
+  os_ << "        if(!err) err = b200rt_memcpy_d2h(host[a], tmp, bytes, stream);\n";
+  os_ << "        if(!err) err = b200rt_stream_synchronize(stream);\n";
+  os_ << "      } else\n        err = b200rt_memcpy_d2h(host[a], dev[a], bytes, stream);\n";
+  os_ << "    }\n";
+  os_ << "    if(!err) err = b200rt_stream_synchronize(stream);\n";
+  os_ << "    for(int a = 0; a < nf; ++a) b200rt_free(dev[a]);\n    b200rt_free(tmp);\n    return err;\n  }\n";
+  // verification of the written fields against reference copies on the device (reference:
+  // verify_<N>, CudaIcoCodeGen.cpp:949-1028 + cuda_verify.hpp:84-196; defaults rel 1e-12, abs 0)
+  os_ << "  int verify(const b200_field_t* f, const double* const* ref, const double* rel_tol, "
+         "const double* abs_tol, int iteration, b200_verification_metrics* metrics, void* stream) {\n";
+  os_ << "    int w = 0;\n";
+  {
+    std::set<int> written;
+    for(auto const& g : groups)
+      written.insert(g.fieldsWritten.begin(), g.fieldsWritten.end());
+    for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a)
+      if(written.count(inst_.apiFieldIDs[a])) {
+        os_ << "    if(int err = b200rt_verify_field(static_cast<const double*>(f[" << a << "].data), ref[w], field_elems("
+            << a << "), rel_tol ? rel_tol[w] : 1e-12, abs_tol ? abs_tol[w] : 0.0, iteration, &metrics[w], stream)) return err;\n";
+        os_ << "    ++w;\n";
+      }
+  }
+  os_ << "    return 0;\n  }\n";
   os_ << "  void run(const b200_field_t* f) {\n    m_timer.start();\n"
          "    if(launch(f, m_timer.stream())) ::dawn_b200::throw_last_error();\n    m_timer.pause();\n  }\n";
   os_ << "  std::string get_name() const { return \"" << inst_.name << "\"; }\n";
@@ -727,6 +803,22 @@ std::string IcoEmitter::generate() {
       << ") return ::dawn_b200::set_error(B200_ERR_ARG, \"run_" << n << ": expected "
       << inst_.apiFieldIDs.size() << " fields\");\n"
       << "  return static_cast<" << cls << "*>(handle)->launch(fields, stream);\n}\n";
+  os_ << "B200_EXPORT int run_" << n << "_from_c_host(void* handle, double* const* host_fields, int nfields, void* stream) {\n"
+      << "  if(!handle || nfields != " << inst_.apiFieldIDs.size()
+      << ") return ::dawn_b200::set_error(B200_ERR_ARG, \"run_" << n << "_from_c_host: field count\");\n"
+      << "  return static_cast<" << cls << "*>(handle)->run_from_host(host_fields, true, stream);\n}\n";
+  os_ << "B200_EXPORT int run_" << n << "_from_fort_host(void* handle, double* const* host_fields, int nfields, void* stream) {\n"
+      << "  if(!handle || nfields != " << inst_.apiFieldIDs.size()
+      << ") return ::dawn_b200::set_error(B200_ERR_ARG, \"run_" << n << "_from_fort_host: field count\");\n"
+      << "  return static_cast<" << cls << "*>(handle)->run_from_host(host_fields, false, stream);\n}\n";
+  os_ << "B200_EXPORT int verify_" << n << "(void* handle, const b200_field_t* fields, const double* const* ref_outputs, "
+         "const double* rel_tol, const double* abs_tol, int iteration, b200_verification_metrics* metrics, void* stream) {\n"
+      << "  return static_cast<" << cls << "*>(handle)->verify(fields, ref_outputs, rel_tol, abs_tol, iteration, metrics, stream);\n}\n";
+  os_ << "B200_EXPORT int run_and_verify_" << n << "(void* handle, const b200_field_t* fields, int nfields, "
+         "const double* const* ref_outputs, const double* rel_tol, const double* abs_tol, int iteration, "
+         "b200_verification_metrics* metrics, void* stream) {\n"
+      << "  if(int err = run_" << n << "(handle, fields, nfields, stream)) return err;\n"
+      << "  return verify_" << n << "(handle, fields, ref_outputs, rel_tol, abs_tol, iteration, metrics, stream);\n}\n";
   os_ << "B200_EXPORT void free_" << n << "(void* handle) { delete static_cast<" << cls << "*>(handle); }\n";
   os_ << "B200_EXPORT long launches_" << n << "(void* handle) { return static_cast<" << cls
       << "*>(handle)->m_launches; }\n";
@@ -776,6 +868,70 @@ std::string IcoEmitter::generate() {
   return os_.str();
 }
 } // namespace
+
+// C header and Fortran interface of the per-stencil C ABI (reference: --output-c-header /
+// --output-f90-interface, CudaIcoCodeGen.cpp:1525-1853,1869-1892).
+std::string icoCHeader(const iir::Instantiation& inst) {
+  std::string n;
+  for(char c : inst.name)
+    n += (std::isalnum(static_cast<unsigned char>(c)) || c == '_') ? c : '_';
+  std::ostringstream os;
+  os << "/* generated by dawn-b200 (b200-ico): C interface of stencil " << inst.name << " */\n";
+  os << "#pragma once\n#include \"dawn_b200_rt.h\"\n#ifdef __cplusplus\nextern \"C\" {\n#endif\n";
+  os << "/* fields in this order:";
+  for(int f : inst.apiFieldIDs)
+    os << " " << inst.nameOf(f);
+  os << " */\n";
+  os << "int setup_" << n << "(void** handle, const b200_mesh_t* mesh, int k_size, void* stream);\n";
+  os << "int run_" << n << "(void* handle, const b200_field_t* fields, int nfields, void* stream);\n";
+  os << "int run_" << n << "_from_c_host(void* handle, double* const* host_fields, int nfields, void* stream);\n";
+  os << "int run_" << n << "_from_fort_host(void* handle, double* const* host_fields, int nfields, void* stream);\n";
+  os << "int verify_" << n << "(void* handle, const b200_field_t* fields, const double* const* ref_outputs, "
+        "const double* rel_tol, const double* abs_tol, int iteration, b200_verification_metrics* metrics, void* stream);\n";
+  os << "int run_and_verify_" << n << "(void* handle, const b200_field_t* fields, int nfields, "
+        "const double* const* ref_outputs, const double* rel_tol, const double* abs_tol, int iteration, "
+        "b200_verification_metrics* metrics, void* stream);\n";
+  os << "void free_" << n << "(void* handle);\n";
+  for(auto const& g : inst.globals) {
+    os << "void set_" << n << "_" << g.first << "(void* handle, double value);\n";
+    os << "double get_" << n << "_" << g.first << "(void* handle);\n";
+  }
+  os << "#ifdef __cplusplus\n}\n#endif\n";
+  return os.str();
+}
+
+std::string icoF90Interface(const iir::Instantiation& inst) {
+  std::string n;
+  for(char c : inst.name)
+    n += (std::isalnum(static_cast<unsigned char>(c)) || c == '_') ? c : '_';
+  std::ostringstream os;
+  os << "! generated by dawn-b200 (b200-ico): Fortran interface of stencil " << inst.name << "\n";
+  os << "module " << n << "_b200\n  use, intrinsic :: iso_c_binding\n  implicit none\n";
+  os << "  type, bind(c) :: b200_field_t\n    type(c_ptr) :: data\n    integer(c_int) :: stride_j\n"
+        "    integer(c_int) :: stride_k\n  end type b200_field_t\n";
+  os << "  interface\n";
+  os << "    integer(c_int) function setup_" << n << "(handle, mesh, k_size, stream) bind(c)\n"
+        "      import :: c_int, c_ptr\n      type(c_ptr), intent(out) :: handle\n"
+        "      type(c_ptr), value :: mesh, stream\n      integer(c_int), value :: k_size\n"
+        "    end function\n";
+  for(const char* fn : {"run_", "run_from_fort_host_"}) {
+    bool host = std::string(fn) != "run_";
+    std::string name = host ? "run_" + n + "_from_fort_host" : "run_" + n;
+    os << "    integer(c_int) function " << name << "(handle, fields, nfields, stream) bind(c)\n"
+       << "      import :: c_int, c_ptr" << (host ? "" : ", b200_field_t") << "\n"
+       << "      type(c_ptr), value :: handle, stream\n"
+       << (host ? "      type(c_ptr), intent(in) :: fields(*)\n" : "      type(b200_field_t), intent(in) :: fields(*)\n")
+       << "      integer(c_int), value :: nfields\n    end function\n";
+  }
+  os << "    subroutine free_" << n << "(handle) bind(c)\n      import :: c_ptr\n"
+        "      type(c_ptr), value :: handle\n    end subroutine\n";
+  os << "  end interface\n";
+  os << "  ! field order of fields(*):";
+  for(int f : inst.apiFieldIDs)
+    os << " " << inst.nameOf(f);
+  os << "\nend module " << n << "_b200\n";
+  return os.str();
+}
 
 TranslationUnit runIco(const std::map<std::string, iir::Instantiation>& ctx, const Options& options) {
   TranslationUnit tu;

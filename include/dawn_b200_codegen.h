@@ -72,6 +72,12 @@ int dawn_b200_codegen_run(const char* const* names, const char* const* iir_json,
                           const size_t* iir_len, int n, int backend, const dawn_b200_options* opts,
                           char** out_code, size_t* out_len);
 
+/* Interface files for one unstructured instantiation (reference: --output-c-header and
+ * --output-f90-interface of the cuda-ico backend, CudaIcoCodeGen.cpp:1869-1892): kind 0 = C header,
+ * 1 = Fortran 2003 interface module.  Result is malloc'ed like out_code above. */
+int dawn_b200_codegen_interface(const char* iir_json, size_t iir_len, int kind, char** out_text,
+                                size_t* out_len);
+
 void dawn_b200_free(void* p);
 const char* dawn_b200_codegen_last_error(void);
 

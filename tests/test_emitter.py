@@ -173,3 +173,24 @@ def test_reference_unstructured_fixtures_are_accepted():
                 "integration-test/serializer/reference_iir/unstructured_mixed_copies.iir"):
         code = codegen.compile_iir(open(REF + rel).read(), backend="b200-ico")
         assert "__global__" in code
+
+
+def test_unstructured_interface_files():
+    iir = open(iir_path("ICON_laplacian_stencil")).read()
+    h = codegen.interface_text(iir, "c")
+    for sym in ("setup_ICON_laplacian_stencil", "run_ICON_laplacian_stencil_from_c_host",
+                "verify_ICON_laplacian_stencil", "run_and_verify_ICON_laplacian_stencil",
+                "free_ICON_laplacian_stencil"):
+        assert sym in h
+    # the header is valid C against the runtime header
+    import subprocess, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "icon.h"), "w").write(h)
+        open(os.path.join(d, "t.c"), "w").write('#include "icon.h"\nint main(void){return 0;}\n')
+        subprocess.check_call(["gcc", "-std=c99", "-fsyntax-only", "-I", os.path.join(
+            os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include"), "-I", d,
+            os.path.join(d, "t.c")])
+    f = codegen.interface_text(iir, "f90")
+    assert "module ICON_laplacian_stencil_b200" in f and "bind(c)" in f
+    with pytest.raises(codegen.CodeGenError):
+        codegen.interface_text(open(iir_path("copy_stencil")).read(), "c")

@@ -122,3 +122,65 @@ def test_runtime_reshape_and_verify_kernels():
     m = rt.verify_field(x.data_ptr(), y.data_ptr(), 1000, rel_tol=1e-12, abs_tol=0.0, iteration=4)
     assert m.is_valid == 0 and m.n_failed == 1 and m.iteration == 4
     assert abs(m.max_abs_err - 1e-3) < 1e-12
+
+
+def test_from_host_entry_points_and_verify():
+    """run_<N>_from_c_host (element-major host arrays, transposed on the GPU), _from_fort_host
+    (level-major) and verify_<N> / run_and_verify_<N> of the generated C ABI."""
+    import ctypes
+    import torch
+    import dawn_b200
+    from dawn_b200 import runtime as rt
+    m = TriMesh(11, 8)
+    k = 6
+    rng = np.random.default_rng(51)
+    f = _rand(rng, m, k, {"vec": EDGE, "div_vec": CELL, "rot_vec": VERTEX, "nabla2_vec": EDGE,
+                          "primal_edge_length": EDGE, "dual_edge_length": EDGE,
+                          "tangent_orientation": EDGE})
+    f["geofac_rot"] = rng.uniform(-1, 1, (k, m.num_vertices, 6))
+    f["geofac_div"] = rng.uniform(-1, 1, (k, m.num_cells, 3))
+    want = {n: v.copy() for n, v in f.items()}
+    want["__tmp_nab_60"] = np.zeros((k, m.num_edges))
+    want["__tmp_nab_61"] = np.zeros((k, m.num_edges))
+    naive_interp.run_unstructured(iir_path("ICON_laplacian_stencil"), m, k, want)
+    mod = dawn_b200.load_stencil("ICON_laplacian_stencil")
+    st = mod.on_mesh(m, k)
+    dpp = ctypes.POINTER(ctypes.c_double)
+    for entry, element_major in (("_from_c_host", True), ("_from_fort_host", False)):
+        host = []
+        for fd in mod.fields:
+            a = f[fd["name"]]                      # oracle layout [k, n] / [k, n, s]
+            if element_major:                      # [n, k] / [n, s, k]
+                a = a.transpose(1, 0) if a.ndim == 2 else a.transpose(1, 2, 0)
+            else:                                  # [k, n] / [k, s, n]
+                a = a if a.ndim == 2 else a.transpose(0, 2, 1)
+            host.append(np.ascontiguousarray(a))
+        arr = (dpp * len(host))(*[h.ctypes.data_as(dpp) for h in host])
+        fn = getattr(mod.lib, "run_ICON_laplacian_stencil" + entry)
+        fn.argtypes = [ctypes.c_void_p, ctypes.POINTER(dpp), ctypes.c_int, ctypes.c_void_p]
+        rt.check(fn(st.handle, arr, len(host), None))
+        names = [fd["name"] for fd in mod.fields]
+        got = host[names.index("nabla2_vec")]
+        got = got.transpose(1, 0) if element_major else got
+        ev = m.edge_valid
+        assert bit_equal(got[:, ev], want["nabla2_vec"][:, ev]), entry
+    # verify / run_and_verify on device-resident fields
+    tens = []
+    for fd in mod.fields:
+        a = f[fd["name"]]
+        tens.append(torch.from_numpy(np.ascontiguousarray(a if a.ndim == 2 else a.transpose(0, 2, 1))).cuda())
+    descs = (rt.Field * len(tens))(*st.descriptors(tens))
+    written = mod.info["written"]
+    refs = [torch.from_numpy(np.ascontiguousarray(want[n])).cuda() for n in written]
+    vpp = ctypes.c_void_p * len(refs)
+    metrics = (rt.VerificationMetrics * len(refs))()
+    fn = mod.lib.run_and_verify_ICON_laplacian_stencil
+    fn.argtypes = [ctypes.c_void_p, ctypes.POINTER(rt.Field), ctypes.c_int, vpp, ctypes.c_void_p,
+                   ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(rt.VerificationMetrics), ctypes.c_void_p]
+    rt.check(fn(st.handle, descs, len(tens), vpp(*[r.data_ptr() for r in refs]), None, None, 3,
+                metrics, None))
+    # invalid edge slots are written by the kernel but not by the reference loop: poison-free compare
+    # is only guaranteed for cells/vertices (all valid)
+    for n, mtr in zip(written, metrics):
+        if n in ("div_vec", "rot_vec"):
+            assert mtr.is_valid == 1 and mtr.max_abs_err == 0.0 and mtr.iteration == 3, n
