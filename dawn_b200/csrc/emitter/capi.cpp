@@ -27,6 +27,7 @@ b200::codegen::Options convert(const dawn_b200_options* o) {
   r.UseTMA = o->use_tma, r.TmaStages = o->tma_stages;
   r.ColumnCache = o->column_cache, r.PrefetchK = o->prefetch_k;
   r.ColumnRing = o->column_ring, r.RingLevels = o->ring_levels;
+  r.ColsPerThread = o->cols_per_thread;
   return r;
 }
 } // namespace

@@ -32,6 +32,7 @@ struct Options {
   int BlockSizeI = 0;     // tile width in i (threads along i)
   int BlockSizeJ = 0;     // thread rows per block
   int RowsPerThread = 0;  // consecutive j rows computed by one thread (register micro-tile)
+  int ColsPerThread = 0;  // consecutive i columns per thread (1 or 2; plain-tile kernels only)
   int BlockSizeK = 0;     // k levels per block for Parallel multistages
   int InlineTemporaries = 1; // 1: recompute cheap temporaries in registers, 0: stage through memory
   int FuseColumns = 1;    // 1: fuse consecutive horizontally-pointwise multistages into one kernel

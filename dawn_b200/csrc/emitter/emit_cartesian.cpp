@@ -85,7 +85,9 @@ struct KernelPlan {
   bool pointwise = false; // column kernel
   bool zchunk = false;    // blockIdx.z splits k (single Parallel multistage)
   int TI = 32, TJ = 4, RJ = 1, KC = 0;
-  int NT() const { return TI * TJ; }
+  int RI = 1; // consecutive i columns per thread (register micro-tile RI x RJ); tile kernels whose
+              // stages all run on the plain tile only
+  int NT() const { return (TI / RI) * TJ; }
   int tileJ() const { return TJ * RJ; }
   std::set<int> fieldsUsed;   // storage-backed fields referenced by this kernel (pointer args)
   std::set<int> fieldsWritten;
@@ -684,6 +686,16 @@ std::vector<KernelPlan> CartesianEmitter::planKernels(const Stencil& st) {
       kp.TJ = opt_.BlockSizeJ > 0 ? opt_.BlockSizeJ : 4;
       kp.RJ = opt_.RowsPerThread > 0 ? opt_.RowsPerThread : 2;
       kp.KC = opt_.BlockSizeK > 0 ? opt_.BlockSizeK : 20;
+      bool plainTile = true;
+      for(auto const* x : kp.ms)
+        for(auto const& stage : x->stages)
+          if(!droppedStages_.count(stage.id) && !stage.extent.horizontalZero())
+            plainTile = false;
+      // default 2x2 micro-tiles (hori_diff on B200: 2x2 0.344 ms, 1x2 0.362 ms, 2x3 0.338 ms at 124 regs)
+      const int wantRI = opt_.ColsPerThread > 0 ? opt_.ColsPerThread : 2;
+      kp.RI = (plainTile && wantRI > 1 && kp.TI % (2 * wantRI) == 0) ? wantRI : 1;
+      if(kp.RI > 2 || kp.TI % (2 * kp.RI) != 0)
+        throw std::runtime_error("b200: cols_per_thread must be 1 or 2 and divide the tile width");
     }
     if(kp.NT() > 1024 || kp.NT() < 32)
       throw std::runtime_error("b200: block size must be within [32,1024] threads");
@@ -767,6 +779,16 @@ public:
   std::vector<std::string> temps; // inlined temporary evaluations
   std::map<std::string, std::string> valueNo;
   int curRow = 0;
+  int cols = 1, curCol = 0;
+  // predicate guarding the cell (col, row) of the micro-tile
+  std::string cellGuard(int c, int r) const {
+    return cols > 1 ? "v" + std::to_string(c) + "_" + std::to_string(r) : "v" + std::to_string(r);
+  }
+  std::string cellSuffix() const {
+    if(cols > 1)
+      return "_c" + std::to_string(curCol) + "r" + std::to_string(curRow);
+    return rows > 1 ? "_r" + std::to_string(curRow) : "";
+  }
 
   BodyEmitter(const Instantiation& i, const KernelPlan& k, const std::map<int, InlineDef>& inl,
               std::function<MaskClass(int)> m)
@@ -835,6 +857,26 @@ public:
       auto it = valueNo.find(key);
       if(it != valueNo.end())
         return it->second;
+      if(cols == 2) {
+        // lx is even and box rows are 16-byte multiples: adjacent columns come as one LDS.128
+        int off = di - sg->im, base = off & ~1;
+        std::string pkey = "P" + std::to_string(e.accessID) + ":" + std::to_string(base) + ":" +
+                           std::to_string(djAbs);
+        auto pit = valueNo.find(pkey);
+        std::string pvar;
+        if(pit != valueNo.end())
+          pvar = pit->second;
+        else {
+          pvar = fieldName(e.accessID) + "_q" + std::to_string(base) + "_" + offTag(djAbs);
+          loads.push_back("const double2 " + pvar + " = *reinterpret_cast<const double2*>(&s_" +
+                          fieldName(e.accessID) + "[(lyb + (" + std::to_string(djAbs - sg->jm) +
+                          ")) * " + std::to_string(sg->W) + " + lx + (" + std::to_string(base) + ")]);");
+          valueNo[pkey] = pvar;
+        }
+        std::string val = pvar + ((off & 1) ? ".y" : ".x");
+        valueNo[key] = val;
+        return val;
+      }
       std::string var = fieldName(e.accessID) + "_" + offTag(di) + "_" + offTag(djAbs) + "_s";
       // no predicate: rows past the thread's valid rows still lie inside the (padded) ring slot
       loads.push_back("const ::dawn::float_type " + var + " = s_" + fieldName(e.accessID) +
@@ -852,7 +894,7 @@ public:
           return iv->second;
         std::string var = fieldName(e.accessID) + "_" + offTag(di) + "_" + offTag(djAbs) + "_inv";
         int firstRow = std::max(0, std::min(rows - 1, curRow));
-        invariantLoads.push_back("const ::dawn::float_type " + var + " = v" + std::to_string(firstRow) +
+        invariantLoads.push_back("const ::dawn::float_type " + var + " = " + cellGuard(curCol, firstRow) +
                                  " ? __ldg(&" + address(e.accessID, di, djAbs, 0) +
                                  ") : (::dawn::float_type)0;");
         invariantNo[key] = var;
@@ -866,7 +908,7 @@ public:
       // a row beyond the valid rows of this thread may point past the halo: predicate on the first
       // row that needs the value (rows are valid in prefix order)
       int firstRow = std::max(0, std::min(rows - 1, curRow));
-      std::string guard = rowGuards ? "v" + std::to_string(firstRow) + " ? " : "";
+      std::string guard = rowGuards ? cellGuard(curCol, firstRow) + " ? " : "";
       std::string tail = rowGuards ? " : (::dawn::float_type)0" : "";
       loads.push_back("const ::dawn::float_type " + var + " = " + guard + "__ldg(&" +
                       address(e.accessID, di, djAbs, dk) + ")" + tail + ";");
@@ -898,11 +940,11 @@ public:
   std::string varName(const Expr& e) const {
     if(e.isExternal)
       return "g." + cIdent(e.name);
-    return cIdent(e.name) + (rows > 1 ? "_r" + std::to_string(curRow) : "");
+    return cIdent(e.name) + cellSuffix();
   }
 
   // top-level expression of body row `curRow`
-  std::string expr(const ExprPtr& e) { return expr(e, 0, curRow); }
+  std::string expr(const ExprPtr& e) { return expr(e, curCol, curRow); }
 
   // expression evaluated at the thread's point shifted by (shiftI, shiftJ rows from the base row)
   std::string expr(const ExprPtr& e, int shiftI, int shiftJ) {
@@ -955,28 +997,28 @@ public:
       if(rg != rings.end()) {
         std::string r0 = fieldName(lhs.accessID) + "_kc0";
         out.push_back(pad + r0 + " " + s->expr->op + " " + rhs + ";");
-        out.push_back(pad + address(lhs.accessID, 0, curRow, 0) + " = " + r0 + ";");
+        out.push_back(pad + address(lhs.accessID, curCol, curRow, 0) + " = " + r0 + ";");
         if(ccWrite.count(lhs.accessID))
           out.push_back(pad + ccAddress(lhs.accessID, 0) + " = " + r0 + ";");
       } else if(ccWrite.count(lhs.accessID)) {
         std::string tmp = "ccv_" + fieldName(lhs.accessID);
         std::string cur = ccRead.count(lhs.accessID) ? ccAddress(lhs.accessID, 0)
-                                                     : address(lhs.accessID, 0, curRow, 0);
+                                                     : address(lhs.accessID, curCol, curRow, 0);
         if(s->expr->op == "=")
           out.push_back(pad + "{ const ::dawn::float_type " + tmp + " = " + rhs + ";");
         else
           out.push_back(pad + "{ const ::dawn::float_type " + tmp + " = " + cur + " " +
                         s->expr->op.substr(0, 1) + " " + rhs + ";");
-        out.push_back(pad + "  " + address(lhs.accessID, 0, curRow, 0) + " = " + tmp + ";");
+        out.push_back(pad + "  " + address(lhs.accessID, curCol, curRow, 0) + " = " + tmp + ";");
         out.push_back(pad + "  " + ccAddress(lhs.accessID, 0) + " = " + tmp + "; }");
       } else {
-        out.push_back(pad + address(lhs.accessID, 0, curRow, 0) + " " + s->expr->op + " " + rhs +
+        out.push_back(pad + address(lhs.accessID, curCol, curRow, 0) + " " + s->expr->op + " " + rhs +
                       ";");
       }
       break;
     }
     case Stmt::VarDecl: {
-      std::string name = cIdent(s->name) + (rows > 1 ? "_r" + std::to_string(curRow) : "");
+      std::string name = cIdent(s->name) + cellSuffix();
       std::string init = s->expr ? " = " + expr(s->expr) : "";
       out.push_back(pad + cType(s->typeId) + " " + name + init + ";");
       break;
@@ -1183,12 +1225,18 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         if(!droppedStages_.count(stage.id) && !stage.extent.horizontalZero())
           uniformRegion = false;
   if(uniformRegion) {
-    os_ << "  const int lx = tid % " << kp.TI << ";\n";
-    os_ << "  const int lyb = (tid / " << kp.TI << ") * " << kp.RJ << ";\n";
+    os_ << "  const int lx = (tid % " << kp.TI / kp.RI << ") * " << kp.RI << ";\n";
+    os_ << "  const int lyb = (tid / " << kp.TI / kp.RI << ") * " << kp.RJ << ";\n";
     os_ << "  const int i = i0 + lx;\n";
     os_ << "  const int jb = j0 + lyb;\n";
-    for(int r = 0; r < kp.RJ; ++r)
-      os_ << "  const bool v" << r << " = i <= nx - 1 && jb + " << r << " <= ny - 1;\n";
+    for(int r = 0; r < kp.RJ; ++r) {
+      if(kp.RI == 1)
+        os_ << "  const bool v" << r << " = i <= nx - 1 && jb + " << r << " <= ny - 1;\n";
+      else
+        for(int c = 0; c < kp.RI; ++c)
+          os_ << "  const bool v" << c << "_" << r << " = i + " << c << " <= nx - 1 && jb + " << r
+              << " <= ny - 1;\n";
+    }
     for(auto const& c : classes)
       if(c[2] == '0') {
         MaskClass m{c[0] == '1', c[1] == '1', false};
@@ -1516,21 +1564,29 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
               os_ << pad << fname(r.first) << "_kc0 = pfv_" << fname(r.first) << ";\n";
         }
         be.reset();
-        std::vector<std::vector<std::string>> rowLines(rows);
-        for(int r = 0; r < rows; ++r) {
-          be.curRow = r;
-          for(auto const* dm : dms)
-            for(auto const& s : dm->stmts)
-              be.stmt(s, rowLines[r], 0);
-        }
+        const int cols = (uniformRegion ? kp.RI : 1);
+        be.cols = cols;
+        // cells of the micro-tile in row-major order: cellLines[r * cols + c]
+        std::vector<std::vector<std::string>> cellLines(rows * cols);
+        for(int r = 0; r < rows; ++r)
+          for(int c = 0; c < cols; ++c) {
+            be.curRow = r;
+            be.curCol = c;
+            for(auto const* dm : dms)
+              for(auto const& s : dm->stmts)
+                be.stmt(s, cellLines[r * cols + c], 0);
+          }
+        be.curCol = 0;
         for(auto const& l : be.loads)
           os_ << pad << l << "\n";
         for(auto const& l : be.temps)
           os_ << pad << l << "\n";
-        for(int r = 0; r < rows; ++r) {
+        for(int rc = 0; rc < rows * cols; ++rc) {
+          const int r = rc / cols, c = rc % cols;
+          std::vector<std::string>& rowLinesRef = cellLines[rc];
           std::string guard;
           if(!kp.pointwise)
-            guard = "v" + std::to_string(r);
+            guard = be.cellGuard(c, r);
           if(stage.hasIRange)
             guard += std::string(guard.empty() ? "" : " && ") + "(gi0 + i >= s" +
                      std::to_string(stage.id) + "_ilo && gi0 + i < s" + std::to_string(stage.id) +
@@ -1543,7 +1599,7 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
             os_ << pad << "if(" << guard << ") {\n";
           else
             os_ << pad << "{\n";
-          for(auto const& l : rowLines[r])
+          for(auto const& l : rowLinesRef)
             os_ << pad << "  " << l << "\n";
           os_ << pad << "}\n";
         }

@@ -54,6 +54,7 @@ typedef struct dawn_b200_options {
   int column_ring;       /* default 1: sequential column kernels stream inputs through a TMA ring */
   int ring_levels;       /* k levels per ring slot (0 = default 8) */
   int prefetch_k;        /* register prefetch depth of sequential column loops (0 = default 8) */
+  int cols_per_thread;   /* i columns per thread of tile kernels without redundant halo stages (1|2) */
 } dawn_b200_options;
 
 /* Fills `opts` with the defaults above. */

@@ -48,7 +48,9 @@ def test_hori_diff_type2(I, J, K):
                                   dict(block_size_i=32, block_size_j=8, rows_per_thread=2),
                                   dict(inline_temporaries=0), dict(use_tma=0),
                                   dict(tma_stages=2, block_size_k=3),
-                                  dict(inline_temporaries=0, use_tma=0)])
+                                  dict(inline_temporaries=0, use_tma=0), dict(cols_per_thread=1),
+                                  dict(cols_per_thread=2, use_tma=0, rows_per_thread=1),
+                                  dict(rows_per_thread=3)])
 def test_hori_diff_type2_planner_variants(opts):
     I, J, K = 70, 45, 7
     f = hori_diff_type2_inputs(I, J, K)

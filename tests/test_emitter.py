@@ -79,9 +79,9 @@ def test_tridiagonal_plan_fuses_sweeps_with_register_kcaches():
 
 def test_planner_knobs_change_the_tile():
     code = _code("hori_diff_type2_stencil", block_size_i=32, block_size_j=8, rows_per_thread=4)
-    assert "block 32x8 threads, 4 row(s)/thread" in code and "__launch_bounds__(256)" in code
+    assert "block 32x8 threads, 4 row(s)/thread" in code and "__launch_bounds__(128)" in code
     with pytest.raises(codegen.CodeGenError, match="block size"):
-        _code("hori_diff_type2_stencil", block_size_i=64, block_size_j=32)
+        _code("hori_diff_type2_stencil", block_size_i=64, block_size_j=64)
     with pytest.raises(TypeError):
         _code("hori_diff_type2_stencil", no_such_option=1)
 
