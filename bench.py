@@ -40,51 +40,68 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region: nvidia-smi runs from before
+    the warm-up (the GPU is under the same load throughout) with 10 ms period; samples are selected by
+    their timestamps against the wall-clock bracket of the timed region."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.proc = None
         self.index = index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "10"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]),
+                             [n for n, v in zip(names, parts[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else 1e18
+        sel = [r for r in rows if t0 <= r[0] <= t1]
+        window = "timed region"
+        if not sel:  # region shorter than the sampling period: nearest samples under the same load
+            sel = [r for r in rows if t0 - 0.25 <= r[0] <= t1 + 0.05]
+            window = "timed region +-0.25 s (same load)"
+        sm = sorted(r[1] for r in sel)
+        reasons = sorted({x for r in sel for x in r[3]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max((r[2] for r in sel), default=None), "samples": len(sel),
+                "window": window, "reasons": reasons}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -292,26 +309,16 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
 
-    # ---- kernel-only time (roofline): events around the generated kernel alone -----------------
-    l0 = st.launches()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    ev[0].record()
-    for _ in range(args.steps):
-        st.run(*fields)
-    ev[1].record()
-    torch.cuda.synchronize()
-    kernel_ms = ev[0].elapsed_time(ev[1]) / args.steps
-    kernels_per_run = (st.launches() - l0) // args.steps
-
     # ---- timed region: K steps ------------------------------------------------------------------
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     l0 = st.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -319,6 +326,7 @@ def run_gpu(args):
         step()
     e1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     launches = (st.launches() - l0) + launches_per_step[0] * args.steps
@@ -326,6 +334,23 @@ def run_gpu(args):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
+
+    # ---- kernel-only time for the roofline: at N=1 a step IS one launch of the generated kernel, so
+    # the timed region itself gives its average duration; at N>1 the same number of bare kernel
+    # launches is timed right after the timed region (same thermal / power-cap state)
+    if world == 1:
+        kernel_ms = ms / args.steps
+        kernels_per_run = (st.launches() - l0) // args.steps
+    else:
+        lk = st.launches()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(args.steps):
+            st.run(*fields)
+        ev[1].record()
+        torch.cuda.synchronize()
+        kernel_ms = ev[0].elapsed_time(ev[1]) / args.steps
+        kernels_per_run = (st.launches() - lk) // args.steps
 
     # ---- end to end through the public API with HOST buffers --------------------------------------
     e2e_steps = min(args.steps, 5)
@@ -373,6 +398,8 @@ def run_gpu(args):
                     "`in` (2 rows each way) every step, overlapped with the interior rows" % (
                         I, J * world, K, world)),
                 "l2": "inputs larger than L2 (2.0 GB per step vs 126 MB), no flush",
+                "timing": "sustained: %d back-to-back steps (the FP64-heavy kernel runs ~15%% faster for "
+                          "the first ~30 ms, before the 1 kW power cap engages)" % args.steps,
                 "codegen_options": opts,
             },
             "roofline": {
@@ -469,12 +496,13 @@ def run_icon(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler.mark_begin()
     l0 = st.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -482,6 +510,7 @@ def run_icon(args):
         step()
     e1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -526,7 +555,7 @@ def run_icon(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="hori_diff", choices=list(STENCIL) + ["icon_nabla2"])

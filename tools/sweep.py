@@ -38,11 +38,12 @@ def main():
         try:
             mod = dawn_b200.load_stencil(name, **opts)
             st = mod(dom)
-            for _ in range(5):
+            sustained = os.environ.get("SWEEP_SUSTAINED", "0") == "1"
+            for _ in range(400 if sustained else 5):   # sustained: let the power cap settle first
                 st.run(*stor)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n = 30
+            n = 300 if sustained else 30
             e0.record()
             for _ in range(n):
                 st.run(*stor)
