@@ -102,8 +102,12 @@ VARIANTS = {
         dict(block_size_i=32, block_size_j=8, rows_per_thread=2), dict(inline_temporaries=0),
         dict(use_tma=0), dict(tma_stages=2, block_size_k=3), dict(inline_temporaries=0, use_tma=0),
         dict(cols_per_thread=1), dict(cols_per_thread=2, use_tma=0, rows_per_thread=1),
-        dict(rows_per_thread=3),
+        dict(rows_per_thread=3), dict(shared_temporaries=1),
+        dict(shared_temporaries=1, cols_per_thread=1), dict(shared_temporaries=1, rows_per_thread=1),
+        dict(shared_temporaries=1, tma_stages=2, block_size_j=8),
     ],
+    "hori_diff_stencil_01": [dict(shared_temporaries=1)], "hori_diff_stencil": [dict(shared_temporaries=1)],
+    "copy_stencil": [dict(shared_temporaries=1)], "nonoverlapping_stencil": [dict(shared_temporaries=1)],
     "ICON_laplacian_stencil": [dict(fuse_columns=0, levels_per_thread=1), dict(levels_per_thread=8)],
     "kcache_fill": [dict(column_ring=0)], "kcache_flush": [dict(column_ring=0)],
     "kcache_fill_backward": [dict(column_ring=0)], "intervals02": [dict(column_ring=0)],

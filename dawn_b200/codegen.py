@@ -32,7 +32,8 @@ class _Options(ctypes.Structure):
         "max_halo_points", "use_parallel_ep", "max_blocks_per_sm", "nsms", "domain_size_i",
         "domain_size_j", "domain_size_k", "run_with_sync", "block_size_i", "block_size_j",
         "rows_per_thread", "block_size_k", "inline_temporaries", "fuse_columns", "unroll_k",
-        "levels_per_thread", "block_size_ico", "use_tma", "tma_stages", "column_cache", "column_ring", "ring_levels", "prefetch_k", "cols_per_thread")]
+        "levels_per_thread", "block_size_ico", "use_tma", "tma_stages", "column_cache", "column_ring", "ring_levels", "prefetch_k", "cols_per_thread",
+        "shared_temporaries")]
 
 
 _lib = None

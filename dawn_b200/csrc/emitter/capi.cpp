@@ -28,6 +28,7 @@ b200::codegen::Options convert(const dawn_b200_options* o) {
   r.ColumnCache = o->column_cache, r.PrefetchK = o->prefetch_k;
   r.ColumnRing = o->column_ring, r.RingLevels = o->ring_levels;
   r.ColsPerThread = o->cols_per_thread;
+  r.SharedTemporaries = o->shared_temporaries;
   return r;
 }
 } // namespace
@@ -49,6 +50,7 @@ void dawn_b200_default_options(dawn_b200_options* o) {
   o->use_tma = 1;
   o->column_cache = 0;
   o->column_ring = 1;
+  o->shared_temporaries = 0;
 }
 
 int dawn_b200_parse_backend(const char* s) {

@@ -121,6 +121,27 @@ struct KernelPlan {
         return &s;
     return nullptr;
   }
+  // --- shared-memory IJ-cache of the TMA variant: temporaries that many neighbouring points read are
+  // evaluated once per level over (tile + read extent) by the whole block, double-buffered over k
+  struct Cached {
+    int temp;
+    int im, ip, jm, jp; // read extent of the temporary relative to the tile
+    int e;              // first column of the fill sweep (im rounded down to an even column)
+    int NPX;            // column pairs per row of the fill sweep
+    int W, H;           // buffer pitch (even) and rows
+    int offset;         // element offset inside one buffer
+  };
+  std::vector<Cached> cached;
+  int cacheElems = 0; // doubles per buffer (two buffers)
+  const Cached* cachedOf(int t) const {
+    for(auto const& c : cached)
+      if(c.temp == t)
+        return &c;
+    return nullptr;
+  }
+  size_t tmaSmemBytes() const {
+    return 128 + (size_t)stages * stageElems * 8 + (size_t)2 * cacheElems * 8;
+  }
 };
 
 class CartesianEmitter {
@@ -165,6 +186,7 @@ private:
   std::vector<KernelPlan> planKernels(const Stencil& st);
   void collectUse(KernelPlan& kp) const;
   bool planTma(KernelPlan& kp) const;
+  void planSharedTemporaries(KernelPlan& kp) const;
   bool planColumnCache(KernelPlan& kp) const;
   bool planColumnRing(KernelPlan& kp) const;
   std::map<int, int> ringDepths(const MultiStage& ms) const;
@@ -586,12 +608,104 @@ bool CartesianEmitter::planTma(KernelPlan& kp) const {
   kp.tma = true;
   kp.stageElems = offset;
   kp.stages = opt_.TmaStages > 0 ? opt_.TmaStages : 4;
+  if(opt_.SharedTemporaries)
+    planSharedTemporaries(kp);
   // keep at least two blocks per SM resident (227 KB of shared memory per SM)
-  while(kp.stages > 2 && (size_t)kp.stages * kp.stageElems * 8 + 128 > 100 * 1024)
+  while(kp.stages > 2 && kp.tmaSmemBytes() > 100 * 1024)
     --kp.stages;
-  if((size_t)kp.stages * kp.stageElems * 8 + 128 > 200 * 1024)
+  if(kp.tmaSmemBytes() > 200 * 1024) {
+    kp.cached.clear();
+    kp.cacheElems = 0;
+  }
+  if(kp.tmaSmemBytes() > 200 * 1024)
     return false;
   return true;
+}
+
+// Which inlined temporaries of a TMA tile kernel move into the shared-memory IJ-cache (Blackwell
+// replacement of PassSetCaches' IJ decision, Optimizer/PassSetCaches.cpp): leaf temporaries (their
+// definition reads only TMA-staged or k-less inputs) that the expanded stage bodies evaluate at
+// three or more distinct horizontal offsets, i.e. at least 3x redundant work per point.
+void CartesianEmitter::planSharedTemporaries(KernelPlan& kp) const {
+  const MultiStage& ms = *kp.ms[0];
+  for(auto const& stage : ms.stages)
+    if(!droppedStages_.count(stage.id) && !stage.extent.horizontalZero())
+      return; // only kernels whose stages all run on the plain tile
+  std::map<int, std::set<std::pair<int, int>>> offsets;
+  std::function<void(const ExprPtr&, int, int)> walk = [&](const ExprPtr& e, int si, int sj) {
+    if(!e)
+      return;
+    if(e->kind == Expr::Field) {
+      auto inl = inlined_.find(e->accessID);
+      if(inl != inlined_.end()) {
+        MaskClass m = maskOf(e->accessID);
+        int di = m.i ? e->di + si : 0, dj = m.j ? e->dj + sj : 0;
+        offsets[e->accessID].insert({di, dj});
+        walk(inl->second.expr, di, dj);
+      }
+      return;
+    }
+    for(auto const& k : e->kids)
+      walk(k, si, sj);
+  };
+  std::function<void(const StmtPtr&)> ws = [&](const StmtPtr& st) {
+    if(st->kind == Stmt::ExprStmt && st->expr->kind == Expr::Assign) {
+      const Expr& l = *st->expr->kids[0];
+      if(!(l.kind == Expr::Field && inlined_.count(l.accessID)))
+        walk(st->expr->kids[1], 0, 0);
+    } else
+      walk(st->expr, 0, 0);
+    for(auto const& c : st->body)
+      ws(c);
+    for(auto const& c : st->orelse)
+      ws(c);
+  };
+  for(auto const& stage : ms.stages)
+    if(!droppedStages_.count(stage.id))
+      for(auto const& dm : stage.doMethods)
+        for(auto const& st : dm.stmts)
+          ws(st);
+  int offset = 0;
+  for(auto const& op : offsets) {
+    if(op.second.size() < 3)
+      continue;
+    // leaf: only staged / k-less read-only inputs, literals, globals and math calls
+    bool leaf = true;
+    std::function<void(const ExprPtr&)> chk = [&](const ExprPtr& e) {
+      if(!e)
+        return;
+      if(e->kind == Expr::Field) {
+        MaskClass m = maskOf(e->accessID);
+        bool staged = kp.stagedOf(e->accessID) && e->dk == 0;
+        bool invariant = !m.k && !kp.fieldsWritten.count(e->accessID) && !inlined_.count(e->accessID);
+        if(!staged && !invariant)
+          leaf = false;
+      }
+      if(e->kind == Expr::Var && !e->isExternal)
+        leaf = false;
+      for(auto const& k : e->kids)
+        chk(k);
+    };
+    chk(inlined_.at(op.first).expr);
+    MaskClass tm = maskOf(op.first);
+    if(!leaf || !tm.i || !tm.j)
+      continue;
+    KernelPlan::Cached c;
+    c.temp = op.first;
+    c.im = c.ip = c.jm = c.jp = 0;
+    for(auto const& o : op.second)
+      c.im = std::min(c.im, o.first), c.ip = std::max(c.ip, o.first), c.jm = std::min(c.jm, o.second),
+      c.jp = std::max(c.jp, o.second);
+    c.e = -(((-c.im + 1) / 2) * 2);
+    // the fill sweep walks column pairs from the even column e; the buffer's column 0 is column e
+    c.NPX = (kp.TI + c.ip - c.e + 1) / 2;
+    c.W = 2 * c.NPX;
+    c.H = kp.tileJ() + c.jp - c.jm;
+    c.offset = offset;
+    offset += ((c.W * c.H + 15) / 16) * 16;
+    kp.cached.push_back(c);
+  }
+  kp.cacheElems = offset;
 }
 
 std::vector<KernelPlan> CartesianEmitter::planKernels(const Stencil& st) {
@@ -824,6 +938,39 @@ public:
       djAbs = 0;
     if(!m.k)
       dk = 0;
+    // temporary kept in the shared-memory IJ-cache of this level
+    if(const KernelPlan::Cached* cc = kp.cachedOf(e.accessID)) {
+      std::string key = "C" + std::to_string(e.accessID) + ":" + std::to_string(di) + ":" +
+                        std::to_string(djAbs);
+      auto it = valueNo.find(key);
+      if(it != valueNo.end())
+        return it->second;
+      const std::string row = "(lyb + (" + std::to_string(djAbs - cc->jm) + ")) * " +
+                              std::to_string(cc->W) + " + lx + (";
+      if(cols == 2) {
+        int off = di - cc->e, base = off & ~1;
+        std::string pkey = "CP" + std::to_string(e.accessID) + ":" + std::to_string(base) + ":" +
+                           std::to_string(djAbs);
+        auto pit = valueNo.find(pkey);
+        std::string pvar;
+        if(pit != valueNo.end())
+          pvar = pit->second;
+        else {
+          pvar = fieldName(e.accessID) + "_cq" + std::to_string(base) + "_" + offTag(djAbs);
+          loads.push_back("const double2 " + pvar + " = *reinterpret_cast<const double2*>(&ij_" +
+                          fieldName(e.accessID) + "[" + row + std::to_string(base) + ")]);");
+          valueNo[pkey] = pvar;
+        }
+        std::string val = pvar + ((off & 1) ? ".y" : ".x");
+        valueNo[key] = val;
+        return val;
+      }
+      std::string var = fieldName(e.accessID) + "_" + offTag(di) + "_" + offTag(djAbs) + "_c";
+      loads.push_back("const ::dawn::float_type " + var + " = ij_" + fieldName(e.accessID) + "[" +
+                      row + std::to_string(di - cc->e) + ")];");
+      valueNo[key] = var;
+      return var;
+    }
     // inlined temporary: evaluate (once) from its definition shifted to this point
     auto inl = inlined.find(e.accessID);
     if(inl != inlined.end()) {
@@ -1158,6 +1305,9 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
     os_ << "  extern __shared__ __align__(128) unsigned char b200_smem[];\n";
     os_ << "  unsigned long long* tma_full = reinterpret_cast<unsigned long long*>(b200_smem);\n";
     os_ << "  ::dawn::float_type* tma_ring = reinterpret_cast<::dawn::float_type*>(b200_smem + 128);\n";
+    if(!kp.cached.empty())
+      os_ << "  ::dawn::float_type* ij_cache = tma_ring + " << (size_t)kp.stages * kp.stageElems
+          << "; // two buffers of " << kp.cacheElems << " doubles\n";
     os_ << "  if(tid == 0) {\n";
     os_ << "    for(int s = 0; s < " << kp.stages << "; ++s)\n"
         << "      ::dawn_b200::tma::barrier_init(&tma_full[s], 1);\n";
@@ -1368,15 +1518,65 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         os_ << "      for(int it = 0; it < nk_loc; ++it) {\n";
         os_ << "        const int k = " << kOf << "it;\n";
         os_ << "        const unsigned tcur = (tma_it + it) % " << kp.stages << ";\n";
-        os_ << "        if(tid == 0 && it + " << kp.stages - 1 << " < nk_loc)\n";
-        emitTmaIssue("          ", kOf + "(it + " + std::to_string(kp.stages - 1) + ")",
-                     "(tma_it + it + " + std::to_string(kp.stages - 1) + ") % " +
-                         std::to_string(kp.stages));
+        auto emitRefill = [&]() {
+          os_ << "        if(tid == 0 && it + " << kp.stages - 1 << " < nk_loc)\n";
+          emitTmaIssue("          ", kOf + "(it + " + std::to_string(kp.stages - 1) + ")",
+                       "(tma_it + it + " + std::to_string(kp.stages - 1) + ") % " +
+                           std::to_string(kp.stages));
+        };
+        if(kp.cached.empty())
+          emitRefill();
         os_ << "        ::dawn_b200::tma::wait(&tma_full[tcur], ((tma_it + it) / " << kp.stages
             << ") & 1u);\n";
         for(auto const& sg : kp.staged)
           os_ << "        const ::dawn::float_type* s_" << fname(sg.field) << " = tma_ring + tcur * "
               << kp.stageElems << " + " << sg.offset << ";\n";
+        if(!kp.cached.empty()) {
+          // ---- IJ-cache fill: the block evaluates each cached temporary once over tile + extent -----
+          os_ << "        ::dawn::float_type* const ij_buf = ij_cache + ((tma_it + it) & 1u) * "
+              << kp.cacheElems << ";\n";
+          for(auto const& cc : kp.cached) {
+            const int N = cc.NPX * cc.H;
+            os_ << "        // fill " << fname(cc.temp) << " over i[" << cc.e << "," << cc.e + cc.W - 1
+                << "] j[" << cc.jm << "," << kp.tileJ() - 1 + cc.jp << "] of the tile, two columns per item\n";
+            os_ << "#pragma unroll\n";
+            os_ << "        for(int p = tid; p < " << N << "; p += " << kp.NT() << ") {\n";
+            std::string pad = "          ";
+            os_ << pad << "const int lx = (p % " << cc.NPX << ") * 2 + (" << cc.e << ");\n";
+            os_ << pad << "const int lyb = p / " << cc.NPX << " + (" << cc.jm << ");\n";
+            os_ << pad << "const int i = i0 + lx;\n";
+            os_ << pad << "const int jb = j0 + lyb;\n";
+            for(int c = 0; c < 2; ++c)
+              os_ << pad << "const bool v" << c << "_0 = i + " << c << " <= nx - 1 + (" << cc.ip
+                  << ") && jb <= ny - 1 + (" << cc.jp << ");\n";
+            emitIndexBases(pad);
+            be.reset();
+            const bool savedHoist = be.hoistInvariant;
+            be.hoistInvariant = false;
+            be.rows = 1, be.cols = 2, be.curRow = 0, be.rowGuards = true;
+            std::string val[2];
+            for(int c = 0; c < 2; ++c) {
+              be.curCol = c;
+              val[c] = be.expr(inlined_.at(cc.temp).expr, c, 0);
+            }
+            be.curCol = 0;
+            be.hoistInvariant = savedHoist;
+            for(auto const& l : be.loads)
+              os_ << pad << l << "\n";
+            for(auto const& l : be.temps)
+              os_ << pad << l << "\n";
+            os_ << pad << "*reinterpret_cast<double2*>(&ij_buf[" << cc.offset << " + (lyb - (" << cc.jm
+                << ")) * " << cc.W << " + lx - (" << cc.e << ")]) = make_double2(" << val[0] << ", "
+                << val[1] << ");\n";
+            os_ << "        }\n";
+          }
+          os_ << "        __syncthreads(); // IJ-cache of this level complete; every thread is also done "
+                 "with the ring slot of the previous level\n";
+          emitRefill();
+          for(auto const& cc : kp.cached)
+            os_ << "        const ::dawn::float_type* ij_" << fname(cc.temp) << " = ij_buf + " << cc.offset
+                << ";\n";
+        }
       } else if(useRing) {
         const int KB = kp.ringKB, S = kp.stages, NT = kp.NT();
         const size_t bytes = (size_t)be.prefetched.size() * KB * NT * 8;
@@ -1632,7 +1832,7 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
           os_ << "        " << fname(r.first) << "_kc" << n << " = " << fname(r.first) << "_kc"
               << n - 1 << ";\n";
       // a stage of the next level may overwrite scratch another thread still reads
-      if(kp.tma)
+      if(kp.tma && kp.cached.empty())
         os_ << "        __syncthreads(); // every thread is done with this ring slot before its refill\n";
       else if(!kp.pointwise && live.size() > 1 && sequential)
         os_ << "        __syncthreads();\n";
@@ -1645,8 +1845,11 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         os_ << "      }\n"; // chunk loop
         os_ << "      tma_it += (unsigned)nch;\n";
       }
-      if(kp.tma)
+      if(kp.tma) {
         os_ << "      tma_it += nk_loc > 0 ? (unsigned)nk_loc : 0u;\n";
+        if(!kp.cached.empty())
+          os_ << "      __syncthreads(); // last ring slots and IJ-cache buffers are free again\n";
+      }
       os_ << "    }\n";
     }
     os_ << "  }\n";
@@ -1847,7 +2050,7 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
       os_ << pad << "dim3 grid((nx + " << kp.TI - 1 << ") / " << kp.TI << ", (jhi - jlo + "
           << kp.tileJ() - 1 << ") / " << kp.tileJ() << ", "
           << (kp.zchunk ? "(nz + kchunk - 1) / kchunk" : "1") << ");\n";
-      size_t smem = kp.tma ? 128 + (size_t)kp.stages * kp.stageElems * 8 : 0;
+      size_t smem = kp.tma ? kp.tmaSmemBytes() : 0;
       if(kp.colring)
         smem = 128 + (size_t)kp.stages * kp.ringMaxFields * kp.ringKB * kp.NT() * 8;
       if(kp.tma || kp.colring) {

@@ -55,6 +55,8 @@ typedef struct dawn_b200_options {
   int ring_levels;       /* k levels per ring slot (0 = default 8) */
   int prefetch_k;        /* register prefetch depth of sequential column loops (0 = default 8) */
   int cols_per_thread;   /* i columns per thread of tile kernels without redundant halo stages (1|2) */
+  int shared_temporaries; /* default 0; 1: TMA tile kernels keep widely reused temporaries in a shared-memory
+                             IJ-cache (the reference's cache(IJ, local), CudaCodeGen ij_caches) */
 } dawn_b200_options;
 
 /* Fills `opts` with the defaults above. */

@@ -50,7 +50,10 @@ def test_hori_diff_type2(I, J, K):
                                   dict(tma_stages=2, block_size_k=3),
                                   dict(inline_temporaries=0, use_tma=0), dict(cols_per_thread=1),
                                   dict(cols_per_thread=2, use_tma=0, rows_per_thread=1),
-                                  dict(rows_per_thread=3)])
+                                  dict(rows_per_thread=3), dict(shared_temporaries=1),
+                                  dict(shared_temporaries=1, cols_per_thread=1),
+                                  dict(shared_temporaries=1, rows_per_thread=1),
+                                  dict(shared_temporaries=1, tma_stages=2, block_size_j=8)])
 def test_hori_diff_type2_planner_variants(opts):
     I, J, K = 70, 45, 7
     f = hori_diff_type2_inputs(I, J, K)
@@ -110,7 +113,8 @@ def test_tridiagonal_known_answer():
     ("copy_stencil", ["in", "out"]),
     ("nonoverlapping_stencil", ["in", "out"]),
 ])
-def test_small_stencils(name, order):
+@pytest.mark.parametrize("opts", [dict(), dict(shared_temporaries=1)], ids=["default", "ijcache"])
+def test_small_stencils(name, order, opts):
     I, J, K = 33, 20, 24
     ni, nj = I + 2 * HALO, J + 2 * HALO
     rng = np.random.default_rng(7)
@@ -119,7 +123,7 @@ def test_small_stencils(name, order):
         f["out"] = np.full((K + 1, nj, ni), -1.0)
     dom = (ni, nj, K)
     want = run_oracle(name, dom, f)
-    got = _run_gpu(name, dom, f, order)
+    got = _run_gpu(name, dom, f, order, **opts)
     for n in order:
         assert bit_equal(got[n], want[n]), n
 
