@@ -398,8 +398,8 @@ def run_gpu(args):
                     "`in` (2 rows each way) every step, overlapped with the interior rows" % (
                         I, J * world, K, world)),
                 "l2": "inputs larger than L2 (2.0 GB per step vs 126 MB), no flush",
-                "timing": "sustained: %d back-to-back steps (the FP64-heavy kernel runs ~15%% faster for "
-                          "the first ~30 ms, before the 1 kW power cap engages)" % args.steps,
+                "timing": "%d back-to-back steps; at N=1 roofline.achieved uses this same region "
+                          "(a step is one kernel launch), so it is a sustained figure - see clocks" % args.steps,
                 "codegen_options": opts,
             },
             "roofline": {
