@@ -19,7 +19,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_COMMON = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
                       "-cudart", "shared"]
 
-EMITTER_SRCS = ["codegen.cpp", "iir.cpp", "emit_cartesian.cpp", "emit_ico.cpp", "capi.cpp"]
+EMITTER_SRCS = ["codegen.cpp", "iir.cpp", "proto_wire.cpp", "emit_cartesian.cpp", "emit_ico.cpp", "capi.cpp"]
 
 
 def _newer(target, sources):
@@ -40,7 +40,7 @@ def build_emitter(force=False):
     os.makedirs(LIB, exist_ok=True)
     edir = os.path.join(CSRC, "emitter")
     srcs = [os.path.join(edir, s) for s in EMITTER_SRCS]
-    deps = srcs + [os.path.join(edir, h) for h in os.listdir(edir) if h.endswith(".hpp")] + \
+    deps = srcs + [os.path.join(edir, h) for h in os.listdir(edir) if h.endswith((".hpp", ".inc"))] + \
         [os.path.join(ROOT, "include", "dawn_b200_codegen.h")]
     so = os.path.join(LIB, "libdawn_b200_codegen.so")
     exe = os.path.join(LIB, "dawn-b200-codegen")

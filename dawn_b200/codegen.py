@@ -110,3 +110,33 @@ def interface_text(iir_json: str, kind="c") -> str:
         return ctypes.string_at(out.value, n.value).decode()
     finally:
         lib.dawn_b200_free(out)
+
+
+def iir_convert(data, to="byte") -> bytes:
+    """Serialized StencilInstantiation -> the other IIRSerializer format ("json" text or "byte" wire
+    format).  Input format is detected from the data."""
+    lib = _load()
+    raw = data.encode() if isinstance(data, str) else bytes(data)
+    out = ctypes.c_void_p()
+    n = ctypes.c_size_t()
+    rc = lib.dawn_b200_iir_convert(raw, ctypes.c_size_t(len(raw)), 0 if to == "json" else 1,
+                                   ctypes.byref(out), ctypes.byref(n))
+    if rc != 0:
+        raise CodeGenError(lib.dawn_b200_codegen_last_error().decode())
+    try:
+        return ctypes.string_at(out.value, n.value)
+    finally:
+        lib.dawn_b200_free(out)
+
+
+def iir_schema() -> str:
+    """The wire schema the Byte reader implements (one line per field / enumerator)."""
+    lib = _load()
+    out = ctypes.c_void_p()
+    n = ctypes.c_size_t()
+    if lib.dawn_b200_iir_schema(ctypes.byref(out), ctypes.byref(n)) != 0:
+        raise CodeGenError(lib.dawn_b200_codegen_last_error().decode())
+    try:
+        return ctypes.string_at(out.value, n.value).decode()
+    finally:
+        lib.dawn_b200_free(out)

@@ -1,6 +1,7 @@
 // C ABI of the emitter (include/dawn_b200_codegen.h).
 #include "../../../include/dawn_b200_codegen.h"
 #include "codegen.hpp"
+#include "proto_wire.hpp"
 
 #include <cstdlib>
 #include <cstring>
@@ -102,6 +103,53 @@ int dawn_b200_codegen_interface(const char* iir_json, size_t iir_len, int kind, 
     *out_text = buf;
     if(out_len)
       *out_len = text.size();
+    return 0;
+  } catch(std::exception& e) {
+    g_error = e.what();
+    return 1;
+  }
+}
+
+int dawn_b200_iir_convert(const char* data, size_t len, int to_format, char** out, size_t* out_len) {
+  try {
+    if(!data || !out)
+      throw std::invalid_argument("dawn_b200_iir_convert: bad arguments");
+    std::string in(data, len);
+    b200::json::Value dom = b200::proto::looksLikeJson(in)
+                                ? b200::json::parse(in)
+                                : b200::proto::decode(in, "StencilInstantiation");
+    std::string res;
+    if(to_format == DAWN_B200_IIR_JSON)
+      res = b200::json::write(dom);
+    else if(to_format == DAWN_B200_IIR_BYTE)
+      res = b200::proto::encode(dom, "StencilInstantiation");
+    else
+      throw std::invalid_argument("dawn_b200_iir_convert: unknown format");
+    char* buf = static_cast<char*>(std::malloc(res.size() + 1));
+    if(!buf)
+      throw std::bad_alloc();
+    std::memcpy(buf, res.data(), res.size());
+    buf[res.size()] = 0;
+    *out = buf;
+    if(out_len)
+      *out_len = res.size();
+    return 0;
+  } catch(std::exception& e) {
+    g_error = e.what();
+    return 1;
+  }
+}
+
+int dawn_b200_iir_schema(char** out_text, size_t* out_len) {
+  try {
+    std::string res = b200::proto::schemaDump();
+    char* buf = static_cast<char*>(std::malloc(res.size() + 1));
+    if(!buf)
+      throw std::bad_alloc();
+    std::memcpy(buf, res.c_str(), res.size() + 1);
+    *out_text = buf;
+    if(out_len)
+      *out_len = res.size();
     return 0;
   } catch(std::exception& e) {
     g_error = e.what();

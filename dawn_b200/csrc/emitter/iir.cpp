@@ -1,4 +1,5 @@
 #include "iir.hpp"
+#include "proto_wire.hpp"
 
 #include <algorithm>
 #include <stdexcept>
@@ -215,8 +216,10 @@ FieldDims parseDims(const Value& v) {
 
 } // namespace
 
-Instantiation parseInstantiation(const std::string& jsonText) {
-  Value root = json::parse(jsonText);
+Instantiation parseInstantiation(const std::string& data) {
+  // IIRSerializer::Format::Json (proto3 JSON text) or ::Byte (protobuf wire format), told apart by
+  // the first byte: a serialized StencilInstantiation starts with tag 0x0A, never with '{'
+  Value root = proto::looksLikeJson(data) ? json::parse(data) : proto::decode(data, "StencilInstantiation");
   Instantiation inst;
   const Value& meta = root.at("metadata");
   const Value& ir = root.at("internalIR");
@@ -253,6 +256,11 @@ Instantiation parseInstantiation(const std::string& jsonText) {
       gv.valueIsSet = kv.second.getBool("valueIsSet");
       inst.globals.emplace_back(kv.first, gv);
     }
+
+  // the reference keeps globals in a std::map keyed by name (AST/GlobalVariableMap); protobuf map order
+  // is unspecified, so order them the same way
+  std::stable_sort(inst.globals.begin(), inst.globals.end(),
+                   [](auto const& a, auto const& b) { return a.first < b.first; });
 
   if(const Value* sts = ir.find("stencils"))
     for(auto const& sj : sts->arr) {

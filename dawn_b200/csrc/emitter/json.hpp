@@ -1,6 +1,7 @@
 // Minimal JSON reader for the proto3-JSON IIR wire format (no third-party dependency).
 // proto3 JSON omits default-valued scalars, so every getter takes a default.
 #pragma once
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <memory>
@@ -236,6 +237,75 @@ public:
 };
 
 inline Value parse(const std::string& text) { return Parser(text).parse(); }
+
+// Compact JSON text of a DOM (numbers with 17 significant digits round-trip doubles exactly).
+inline void writeTo(const Value& v, std::string& o) {
+  switch(v.kind) {
+  case Value::Null: o += "null"; break;
+  case Value::Bool: o += v.b ? "true" : "false"; break;
+  case Value::Number: {
+    char buf[40];
+    if(v.num == static_cast<double>(static_cast<long long>(v.num)) && v.num > -1e15 && v.num < 1e15)
+      std::snprintf(buf, sizeof buf, "%lld", static_cast<long long>(v.num));
+    else if(v.num != v.num)
+      std::snprintf(buf, sizeof buf, "\"NaN\"");
+    else if(v.num - v.num != 0)
+      std::snprintf(buf, sizeof buf, v.num > 0 ? "\"Infinity\"" : "\"-Infinity\"");
+    else
+      std::snprintf(buf, sizeof buf, "%.17g", v.num);
+    o += buf;
+    break;
+  }
+  case Value::String:
+    o += '"';
+    for(char c : v.str) {
+      switch(c) {
+      case '"': o += "\\\""; break;
+      case '\\': o += "\\\\"; break;
+      case '\n': o += "\\n"; break;
+      case '\t': o += "\\t"; break;
+      case '\r': o += "\\r"; break;
+      default:
+        if(static_cast<unsigned char>(c) < 0x20) {
+          char buf[8];
+          std::snprintf(buf, sizeof buf, "\\u%04x", c);
+          o += buf;
+        } else
+          o += c;
+      }
+    }
+    o += '"';
+    break;
+  case Value::Array:
+    o += '[';
+    for(size_t i = 0; i < v.arr.size(); ++i) {
+      if(i)
+        o += ',';
+      writeTo(v.arr[i], o);
+    }
+    o += ']';
+    break;
+  case Value::Object:
+    o += '{';
+    for(size_t i = 0; i < v.obj.size(); ++i) {
+      if(i)
+        o += ',';
+      Value k;
+      k.kind = Value::String;
+      k.str = v.obj[i].first;
+      writeTo(k, o);
+      o += ':';
+      writeTo(v.obj[i].second, o);
+    }
+    o += '}';
+    break;
+  }
+}
+inline std::string write(const Value& v) {
+  std::string o;
+  writeTo(v, o);
+  return o;
+}
 
 } // namespace json
 } // namespace b200

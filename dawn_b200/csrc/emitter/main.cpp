@@ -1,6 +1,7 @@
 // dawn-b200-codegen: command-line twin of `dawn-codegen` (dawn/src/dawn/dawn-codegen.cpp:71-143)
-// for the two backends this project provides.  Reads optimized IIR (proto3 JSON, as written by
-// `dawn-opt`) from a file or stdin, writes the CUDA translation unit to -o or stdout.
+// for the two backends this project provides.  Reads optimized IIR (proto3 JSON or protobuf bytes,
+// as written by `dawn-opt` / IIRSerializer in either format) from a file or stdin, writes the CUDA
+// translation unit to -o or stdout.
 //   dawn-opt x.sir | dawn-b200-codegen --backend=b200 -o x_b200.cu
 #include "codegen.hpp"
 
@@ -25,6 +26,7 @@ int main(int argc, char** argv) {
     std::string a = argv[n];
     if(a == "-h" || a == "--help") {
       std::cout << "Usage: dawn-b200-codegen [-b|--backend b200|b200-ico] [-o out.cu] [in.iir]\n"
+                   "  in.iir: serialized StencilInstantiation, proto3 JSON or protobuf bytes (auto-detected)\n"
                    "  planner knobs: --block-size-i= --block-size-j= --rows-per-thread= "
                    "--block-size-k= --inline-temporaries= --fuse-columns= --unroll-k= "
                    "--levels-per-thread= --block-size-ico= --max-halo-points= --run-with-sync=\n";
@@ -63,7 +65,7 @@ int main(int argc, char** argv) {
     if(input.empty())
       text.assign(std::istreambuf_iterator<char>(std::cin), std::istreambuf_iterator<char>());
     else {
-      std::ifstream f(input);
+      std::ifstream f(input, std::ios::binary);
       if(!f)
         throw std::runtime_error("cannot open " + input);
       text.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());

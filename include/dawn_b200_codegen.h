@@ -81,6 +81,19 @@ int dawn_b200_codegen_run(const char* const* names, const char* const* iir_json,
 int dawn_b200_codegen_interface(const char* iir_json, size_t iir_len, int kind, char** out_text,
                                 size_t* out_len);
 
+/* Serialized-IIR formats (reference: IIRSerializer::Format { Json, Byte },
+ * dawn/src/dawn/Serialization/IIRSerializer.h).  Every entry point above accepts either format and
+ * tells them apart by the first byte; pass iir_len for Byte input (it may contain NULs). */
+#define DAWN_B200_IIR_JSON 0
+#define DAWN_B200_IIR_BYTE 1
+
+/* Converts one serialized StencilInstantiation to `to_format`; result malloc'ed (dawn_b200_free). */
+int dawn_b200_iir_convert(const char* data, size_t len, int to_format, char** out, size_t* out_len);
+
+/* The wire schema the Byte reader implements, one "Message number name type" line per field and
+ * one "enum Name Value number" line per enumerator (checked against the .proto files in tests). */
+int dawn_b200_iir_schema(char** out_text, size_t* out_len);
+
 void dawn_b200_free(void* p);
 const char* dawn_b200_codegen_last_error(void);
 

@@ -414,7 +414,7 @@ class IIRBuilder:
             d = {"op": e.op, "rhs": self._expr(e.rhs, reads), "init": self._expr(e.init, reads),
                  "iter_space": {"chain": list(e.chain), "include_center": e.include_center},
                  "weights": [self._expr(w, reads) for w in (e.weights or [])],
-                 "loc": LOC, "ID": nid}
+                 "loc": LOC}  # no ID: statements.proto gives ReductionOverNeighborExpr none
             return {"reduction_over_neighbor_expr": d}
         raise TypeError(type(e))
 
