@@ -49,6 +49,13 @@ inline void visitExpr(const ExprPtr& e, const std::function<void(const Expr&, bo
   }
   if(e->kind == Expr::Field || e->kind == Expr::Var) {
     fn(*e, false);
+    if(e->kind == Expr::Field && !e->kFrom.empty()) { // vertical indirection also reads the index field
+      Expr idx;
+      idx.kind = Expr::Field;
+      idx.name = e->kFrom;
+      idx.accessID = e->kFromID;
+      fn(idx, false);
+    }
     return;
   }
   for(auto const& k : e->kids)
@@ -66,7 +73,8 @@ inline void visitStmts(const std::vector<StmtPtr>& stmts,
       visitStmts(s->body, fn);
       visitStmts(s->orelse, fn);
       break;
-    case Stmt::Block: visitStmts(s->body, fn); break;
+    case Stmt::Block:
+    case Stmt::Loop: visitStmts(s->body, fn); break;
     }
   }
 }

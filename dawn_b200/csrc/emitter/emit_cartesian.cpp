@@ -930,6 +930,9 @@ public:
   }
 
   std::string readField(const Expr& e, int shiftI, int shiftJ) {
+    if(!e.kFrom.empty())
+      throw std::runtime_error("b200: vertical indirection is only provided by the b200-ico backend "
+                               "(field " + e.name + "), as in the reference");
     int di = e.di + shiftI, djAbs = e.dj + shiftJ, dk = e.dk;
     MaskClass m = maskOf(e.accessID);
     if(!m.i)
@@ -1188,7 +1191,8 @@ public:
         stmt(c, out, indent + 1);
       out.push_back(pad + "}");
       break;
-    }
+    }    case Stmt::Loop:
+      throw std::runtime_error("b200: loops over neighbour chains require the b200-ico backend");
     }
   }
 };

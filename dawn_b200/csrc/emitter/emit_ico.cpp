@@ -115,6 +115,37 @@ std::string locName(LocationType l) {
   return l == LocationType::Cells ? "cells" : l == LocationType::Edges ? "edges" : "vertices";
 }
 
+// Calls fn(field access, nesting) for every field access of a stage; nesting = number of enclosing
+// neighbour loops / reductions (weights and init of a reduction belong to the enclosing level).
+void forEachAccess(const Stage& stage,
+                   const std::function<void(const Expr&, int nesting, bool inLoop)>& fn) {
+  std::function<void(const ExprPtr&, int, bool)> walk = [&](const ExprPtr& e, int nest, bool loop) {
+    if(!e)
+      return;
+    if(e->kind == Expr::Field)
+      fn(*e, nest, loop);
+    if(e->kind == Expr::Reduce) {
+      walk(e->kids[0], nest + 1, loop);
+      for(size_t n = 1; n < e->kids.size(); ++n)
+        walk(e->kids[n], nest, loop);
+      return;
+    }
+    for(auto const& k : e->kids)
+      walk(k, nest, loop);
+  };
+  std::function<void(const StmtPtr&, int, bool)> ws = [&](const StmtPtr& s, int nest, bool loop) {
+    walk(s->expr, nest, loop);
+    const bool isLoop = s->kind == Stmt::Loop;
+    for(auto const& c : s->body)
+      ws(c, nest + (isLoop ? 1 : 0), loop || isLoop);
+    for(auto const& c : s->orelse)
+      ws(c, nest, loop);
+  };
+  for(auto const& dm : stage.doMethods)
+    for(auto const& s : dm.stmts)
+      ws(s, 0, false);
+}
+
 struct Group {
   std::vector<const Stage*> stages;
   const MultiStage* ms;
@@ -150,36 +181,25 @@ private:
   bool isSparse(int id) const { return dims(id).isSparse(); }
   int sparseSize(int id) const { return icoChainSize(dims(id).chain, dims(id).includeCenter); }
   bool isVertical(int id) const { return dims(id).chain.empty(); }
+  bool hasK(int id) const { return dims(id).maskK; }
+  // does `stage` read, at an element other than its own, any field in `written`?  (has_offset reads,
+  // fields living on another location type, and everything inside a nested reduction)
+  bool readsThroughChain(const Stage& stage, const std::set<int>& written) const {
+    bool hit = false;
+    forEachAccess(stage, [&](const Expr& e, int nest, bool) {
+      if(!written.count(e.accessID) || nest == 0)
+        return;
+      if(e.hasOffset || nest > 1 || fieldLoc(e.accessID) != stage.location)
+        hit = true;
+    });
+    return hit;
+  }
 
   std::vector<Group> plan(const Stencil& st);
   void emitKernel(const Group& g);
   void emitHost(const std::vector<Group>& groups);
   void collect(Group& g);
 };
-
-// does `stage` read, through a neighbour access, any field in `written`?
-bool readsThroughChain(const Stage& stage, const std::set<int>& written) {
-  bool hit = false;
-  std::function<void(const ExprPtr&)> walk = [&](const ExprPtr& e) {
-    if(!e)
-      return;
-    if(e->kind == Expr::Field && e->hasOffset && written.count(e->accessID))
-      hit = true;
-    for(auto const& k : e->kids)
-      walk(k);
-  };
-  std::function<void(const StmtPtr&)> ws = [&](const StmtPtr& s) {
-    walk(s->expr);
-    for(auto const& c : s->body)
-      ws(c);
-    for(auto const& c : s->orelse)
-      ws(c);
-  };
-  for(auto const& dm : stage.doMethods)
-    for(auto const& s : dm.stmts)
-      ws(s);
-  return hit;
-}
 
 void IcoEmitter::collect(Group& g) {
   std::set<std::string> seen;
@@ -205,6 +225,11 @@ void IcoEmitter::collect(Group& g) {
       });
       std::function<void(const StmtPtr&)> ws = [&](const StmtPtr& s) {
         walk(s->expr, false);
+        if(s->kind == Stmt::Loop) {
+          std::string t = chainTag(s->chain, s->includeCenter);
+          if(seen.insert(t).second)
+            g.chains.push_back({s->chain, s->includeCenter});
+        }
         for(auto const& c : s->body)
           ws(c);
         for(auto const& c : s->orelse)
@@ -265,7 +290,7 @@ std::vector<Group> IcoEmitter::plan(const Stencil& st) {
           analysis::visitStmts(dm.stmts, [&](const Expr& e, bool w) {
             if(e.kind != Expr::Field || e.accessID != t)
               return;
-            if(e.hasOffset || e.dk != 0)
+            if(e.hasOffset || e.dk != 0 || !e.kFrom.empty())
               ok = false;
             if(!decided) {
               // visitStmts reports the write of `t = rhs` before the reads inside rhs
@@ -275,6 +300,13 @@ std::vector<Group> IcoEmitter::plan(const Stencil& st) {
           });
       if(!firstIsWrite)
         ok = false;
+      for(auto const* stg : g.stages)
+        forEachAccess(*stg, [&](const Expr& e, int nest, bool inLoop) {
+          if(e.kFromID == t && !e.kFrom.empty())
+            ok = false; // used as a level index
+          if(e.accessID == t && (inLoop || nest > 1 || (nest == 1 && fieldLoc(t) != stg->location)))
+            ok = false; // touched inside a neighbour loop or away from the thread's own element
+        });
       if(g.ms->loopOrder != LoopOrder::Parallel)
         ok = false;
       // conditional writes cannot be forwarded
@@ -325,30 +357,60 @@ public:
       v += ".0";
     return "(::dawn::float_type)" + v;
   }
-  std::string kexpr(int dk) const { return dk ? "(k + (" + std::to_string(dk) + "))" : "k"; }
+  // level expression of an access: k + shift, or (int)index_field(element, k) + shift for a vertical
+  // indirection (reference: Cuda-ico/ASTStencilBody.cpp:193-210)
+  std::string kexpr(const Expr& e, const Ctx& c) {
+    if(e.kFrom.empty())
+      return e.dk ? "(k + (" + std::to_string(e.dk) + "))" : "k";
+    Expr idx;
+    idx.kind = Expr::Field;
+    idx.name = e.kFrom;
+    idx.accessID = e.kFromID;
+    return "((int)(" + read(idx, c) + ") + (" + std::to_string(e.dk) + "))";
+  }
+
+  // Which element does a dense access address?  Outside neighbour loops / reductions the thread's own
+  // element.  Inside: the neighbour if the access carries an offset or the field lives on another
+  // location type than the element the loop runs around (the reference's naive-ico backend resolves
+  // un-flagged accesses by location type, CXXNaive-ico/ASTStencilBody.cpp:237-252; its cuda-ico
+  // backend by the flag alone, Cuda-ico/ASTStencilBody.cpp:153-163 - both agree on valid programs).
+  bool atNeighbour(const Expr& e, const Ctx& c) const {
+    if(c.nbh.empty()) {
+      if(e.hasOffset)
+        throw std::runtime_error("b200-ico: neighbour access to '" + e.name +
+                                 "' outside a reduction or neighbour loop");
+      return false;
+    }
+    auto const& d = dims(e.accessID);
+    return e.hasOffset || (!d.chain.empty() && d.chain.front() != c.centerLoc);
+  }
 
   std::string fieldRef(const Expr& e, const Ctx& c) {
     auto const& d = dims(e.accessID);
     std::string p = fname(e.accessID) + "_p";
     if(d.chain.empty())
-      return p + "[" + kexpr(e.dk) + "]";
+      return p + "[" + kexpr(e, c) + "]";
     LocationType loc = d.chain.front();
+    // horizontal-only fields (mask_k = 0) have no level term
     if(d.isSparse()) {
       if(c.sparseIdx.empty())
-        throw std::runtime_error("b200-ico: sparse field '" + e.name + "' used outside a reduction");
-      return p + "[((size_t)" + kexpr(e.dk) + " * " + std::to_string(sparseSize(e.accessID)) + " + " +
+        throw std::runtime_error("b200-ico: sparse field '" + e.name +
+                                 "' used outside a reduction or neighbour loop");
+      if(!d.maskK)
+        return p + "[(size_t)" + c.sparseIdx + " * " + stride(loc) + " + " + c.center + "]";
+      return p + "[((size_t)" + kexpr(e, c) + " * " + std::to_string(sparseSize(e.accessID)) + " + " +
              c.sparseIdx + ") * " + stride(loc) + " + " + c.center + "]";
     }
-    if(e.hasOffset) {
-      if(c.nbh.empty())
-        throw std::runtime_error("b200-ico: neighbour access to '" + e.name + "' outside a reduction");
-      return p + "[(size_t)" + kexpr(e.dk) + " * " + stride(loc) + " + " + c.nbh + "]";
-    }
-    return p + "[(size_t)" + kexpr(e.dk) + " * " + stride(loc) + " + " + c.center + "]";
+    const std::string elem = atNeighbour(e, c) ? c.nbh : c.center;
+    if(!d.maskK)
+      return p + "[" + elem + "]";
+    return p + "[(size_t)" + kexpr(e, c) + " * " + stride(loc) + " + " + elem + "]";
   }
 
   std::string read(const Expr& e, const Ctx& c) {
-    if(!e.hasOffset && e.dk == 0 && c.center == "pidx") {
+    const bool own = c.center == "pidx" && !dims(e.accessID).isSparse() &&
+                     (dims(e.accessID).chain.empty() || !atNeighbour(e, c));
+    if(own && e.dk == 0 && e.kFrom.empty()) {
       auto it = forwarded.find(e.accessID);
       if(it != forwarded.end())
         return it->second;
@@ -411,6 +473,8 @@ public:
   // expression inside a reduction body: nested reductions run around the neighbour element
   std::string exprIn(const ExprPtr& e, const Ctx& c, std::vector<std::string>& out, int indent) {
     if(e->kind == Expr::Reduce) {
+      if(c.nbh.empty()) // not inside a neighbour loop / reduction: around the context's own element
+        return reduce(*e, c, out, indent);
       Ctx around;
       around.center = c.nbh;
       around.centerLoc = e->chain.front();
@@ -440,16 +504,21 @@ public:
         s += (n ? ", " : "") + expr(e->kids[n], c, out, indent);
       return s + ")";
     }
-    case Expr::Reduce: return reduce(*e, c, out, indent);
+    case Expr::Reduce: return exprIn(e, c, out, indent);
     case Expr::Assign: throw std::runtime_error("b200-ico: nested assignment expressions are not supported");
     }
     return "";
   }
 
   void stmt(const StmtPtr& s, std::vector<std::string>& out, int indent, bool conditional) {
-    std::string pad(indent * 2, ' ');
     Ctx top;
     top.centerLoc = g.loc;
+    stmt(s, out, indent, conditional, top);
+  }
+
+  void stmt(const StmtPtr& s, std::vector<std::string>& out, int indent, bool conditional,
+            const Ctx& top) {
+    std::string pad(indent * 2, ' ');
     switch(s->kind) {
     case Stmt::ExprStmt: {
       if(s->expr->kind != Expr::Assign) {
@@ -462,8 +531,11 @@ public:
         out.push_back(pad + cIdent(lhs.name) + " " + s->expr->op + " " + rhs + ";");
         break;
       }
-      if(lhs.hasOffset || lhs.dk != 0)
+      if(lhs.hasOffset || lhs.dk != 0 || !lhs.kFrom.empty())
         throw std::runtime_error("b200-ico: writes with offsets are not supported (" + lhs.name + ")");
+      if(!top.nbh.empty() && !dims(lhs.accessID).isSparse() && atNeighbour(lhs, top))
+        throw std::runtime_error("b200-ico: a neighbour loop may only write its own element (" +
+                                 lhs.name + ")");
       std::string val = rhs;
       if(s->expr->op != "=")
         val = "(" + read(lhs, top) + " " + s->expr->op.substr(0, 1) + " " + rhs + ")";
@@ -487,11 +559,11 @@ public:
       std::string cond = expr(s->expr, top, out, indent);
       out.push_back(pad + "if(" + cond + ") {");
       for(auto const& c : s->body)
-        stmt(c, out, indent + 1, true);
+        stmt(c, out, indent + 1, true, top);
       if(s->hasElse) {
         out.push_back(pad + "} else {");
         for(auto const& c : s->orelse)
-          stmt(c, out, indent + 1, true);
+          stmt(c, out, indent + 1, true, top);
       }
       out.push_back(pad + "}");
       break;
@@ -499,9 +571,35 @@ public:
     case Stmt::Block:
       out.push_back(pad + "{");
       for(auto const& c : s->body)
-        stmt(c, out, indent + 1, conditional);
+        stmt(c, out, indent + 1, conditional, top);
       out.push_back(pad + "}");
       break;
+    case Stmt::Loop: {
+      // neighbour loop (reference: Cuda-ico/ASTStencilBody.cpp:52-74), unrolled over the chain size;
+      // position n in the neighbour list is the sparse index of the iteration
+      if(!top.nbh.empty())
+        throw std::runtime_error("b200-ico: nested neighbour loops are not supported");
+      const int size = icoChainSize(s->chain, s->includeCenter);
+      const std::string tag = chainTag(s->chain, s->includeCenter);
+      if(s->chain.front() != top.centerLoc)
+        throw std::runtime_error("b200-ico: neighbour loop over " + tag + " in a stage on " +
+                                 std::string(1, locChar(top.centerLoc)));
+      for(int n = 0; n < size; ++n) {
+        Ctx c = top;
+        c.nbh = "nb_" + tag + "_" + std::to_string(n);
+        c.sparseIdx = std::to_string(n);
+        out.push_back(pad + "if(" + c.nbh + " >= 0) {");
+        for(auto const& b : s->body)
+          stmt(b, out, indent + 1, true, c);
+        out.push_back(pad + "}");
+      }
+      for(auto const& b : s->body) // values written in the loop are not forwarded past it
+        analysis::visitStmts({b}, [&](const Expr& e, bool w) {
+          if(w && e.kind == Expr::Field)
+            forwarded.erase(e.accessID);
+        });
+      break;
+    }
     }
   }
 };
@@ -644,10 +742,13 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
     if(!isVertical(f)) {
       std::string n = IcoBody::stride(fieldLoc(f));
       if(isSparse(f))
-        os_ << "    if(f[" << a << "].stride_j != " << n << " || f[" << a << "].stride_k != " << n << " * "
-            << sparseSize(f) << ") return ::dawn_b200::set_error(B200_ERR_LAYOUT, \"sparse field "
+        os_ << "    if(f[" << a << "].stride_j != " << n
+            << (hasK(f) ? " || f[" + std::to_string(a) + "].stride_k != " + n + " * " +
+                              std::to_string(sparseSize(f))
+                        : std::string())
+            << ") return ::dawn_b200::set_error(B200_ERR_LAYOUT, \"sparse field "
             << fname(f) << " must be laid out [k][" << sparseSize(f) << "][" << n << "]\");\n";
-      else
+      else if(hasK(f))
         os_ << "    if(f[" << a << "].stride_k != " << n
             << ") return ::dawn_b200::set_error(B200_ERR_LAYOUT, \"field " << fname(f)
             << " must be laid out [k][" << n << "]\");\n";
@@ -685,7 +786,7 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
   os_ << "  size_t field_elems(int a) const {\n    switch(a) {\n";
   for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a) {
     int f = inst_.apiFieldIDs[a];
-    os_ << "    case " << a << ": return (size_t)m_k_size";
+    os_ << "    case " << a << ": return (size_t)" << (hasK(f) ? "m_k_size" : "1");
     if(!isVertical(f))
       os_ << " * m_mesh.num_" << locName(fieldLoc(f)) << (isSparse(f) ? " * " + std::to_string(sparseSize(f)) : std::string());
     os_ << ";\n";
@@ -706,6 +807,9 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
     int f = inst_.apiFieldIDs[a];
     os_ << (a ? ", " : "") << (isVertical(f) ? std::string("1") : "m_mesh.num_" + locName(fieldLoc(f)));
   }
+  os_ << "};\n    const int levels_of[] = {";
+  for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a)
+    os_ << (a ? ", " : "") << (hasK(inst_.apiFieldIDs[a]) ? "m_k_size" : "1");
   os_ << "};\n    static const bool written_of[] = {";
   {
     std::set<int> written;
@@ -721,7 +825,7 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
   os_ << "      if(err) break;\n";
   os_ << "      if(element_major && elems_of[a] > 1) {\n";
   os_ << "        err = b200rt_memcpy_h2d(tmp, host[a], bytes, stream);\n";
-  os_ << "        if(!err) err = b200rt_reshape(tmp, dev[a], m_k_size, elems_of[a], sparse_of[a], stream);\n";
+  os_ << "        if(!err) err = b200rt_reshape(tmp, dev[a], levels_of[a], elems_of[a], sparse_of[a], stream);\n";
   os_ << "      } else\n        err = b200rt_memcpy_h2d(dev[a], host[a], bytes, stream);\n";
   os_ << "      f[a].data = dev[a];\n";
   os_ << "      f[a].stride_j = sparse_of[a] > 1 ? elems_of[a] : 0;\n";
@@ -731,7 +835,7 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
   os_ << "    for(int a = 0; a < nf && !err; ++a) {\n      if(!written_of[a]) continue;\n";
   os_ << "      const size_t bytes = field_elems(a) * sizeof(double);\n";
   os_ << "      if(element_major && elems_of[a] > 1) {\n";
-  os_ << "        err = b200rt_reshape_back(dev[a], tmp, m_k_size, elems_of[a], sparse_of[a], stream);\n";
+  os_ << "        err = b200rt_reshape_back(dev[a], tmp, levels_of[a], elems_of[a], sparse_of[a], stream);\n";
   os_ << "        if(!err) err = b200rt_memcpy_d2h(host[a], tmp, bytes, stream);\n";
   os_ << "        if(!err) err = b200rt_stream_synchronize(stream);\n";
   os_ << "      } else\n        err = b200rt_memcpy_d2h(host[a], dev[a], bytes, stream);\n";

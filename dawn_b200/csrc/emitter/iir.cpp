@@ -60,8 +60,9 @@ ExprPtr parseExprPayload(const std::string& kind, const Value& v) {
     e->kind = Expr::Field;
     e->name = v.getString("name");
     e->dk = static_cast<int>(v.getInt("vertical_shift"));
-    if(!v.getString("vertical_indirection").empty())
-      throw std::runtime_error("IIR: vertical indirection is not supported (field " + e->name + ")");
+    e->kFrom = v.getString("vertical_indirection");
+    if(!e->kFrom.empty() && v.has("vertical_indirection_data"))
+      e->kFromID = static_cast<int>(v.at("vertical_indirection_data").getInt("accessID"));
     if(v.has("cartesian_offset")) {
       e->di = static_cast<int>(v.at("cartesian_offset").getInt("i_offset"));
       e->dj = static_cast<int>(v.at("cartesian_offset").getInt("j_offset"));
@@ -173,6 +174,26 @@ StmtPtr parseStmt(const Value& node) {
       s->hasElse = true;
       parseBlockInto(v.at("else_part"), s->orelse);
     }
+  } else if(kind == "loop_stmt") {
+    s->kind = Stmt::Loop;
+    const Value* space = nullptr;
+    if(v.has("loop_descriptor") && v.at("loop_descriptor").has("loop_descriptor_chain")) {
+      auto const& d = v.at("loop_descriptor").at("loop_descriptor_chain");
+      if(d.has("iter_space"))
+        space = &d.at("iter_space");
+      else if(d.has("chain")) // older schema revision: chain stored directly
+        space = &d;
+    }
+    if(!space)
+      throw std::runtime_error("IIR: only loops over a neighbour chain are supported (the reference "
+                               "asserts \"general loop concept not implemented yet\")");
+    if(const Value* ch = space->find("chain"))
+      for(auto const& c : ch->arr)
+        s->chain.push_back(parseLocation(c.str));
+    s->includeCenter = space->getBool("include_center");
+    if(s->chain.size() < 2)
+      throw std::runtime_error("IIR: loop statement with a neighbour chain shorter than 2");
+    parseBlockInto(v.at("statements"), s->body);
   } else if(kind == "block_stmt") {
     s->kind = Stmt::Block;
     if(const Value* st = v.find("statements"))

@@ -75,6 +75,10 @@ struct Expr {
   bool isExternal = false;    // Var: global
   int di = 0, dj = 0, dk = 0; // Field: cartesian offsets + vertical shift
   bool hasOffset = false;     // Field (unstructured): read at the neighbour inside a reduction
+  // Field: vertical indirection (statements.proto FieldAccessExpr.vertical_indirection): the level
+  // is the value of this field at the element and level k, plus dk
+  std::string kFrom;
+  int kFromID = 0;
   // Unary / Binary / Assign / Reduce
   std::string op;
   // children: Unary{0}, Binary{l,r}, Ternary{c,l,r}, Assign{l,r}, FunCall{args...},
@@ -88,7 +92,7 @@ struct Expr {
 struct Stmt;
 using StmtPtr = std::shared_ptr<Stmt>;
 struct Stmt {
-  enum Kind { ExprStmt, VarDecl, If, Block };
+  enum Kind { ExprStmt, VarDecl, If, Block, Loop };
   Kind kind = ExprStmt;
   ExprPtr expr;               // ExprStmt; If: condition; VarDecl: initialiser (may be null)
   std::string name;           // VarDecl
@@ -97,6 +101,9 @@ struct Stmt {
   std::vector<StmtPtr> body;  // Block statements / If then-branch
   std::vector<StmtPtr> orelse; // If else-branch
   bool hasElse = false;
+  // Loop over the neighbours of a chain (statements.proto LoopStmt / LoopDescriptorChain); body = body
+  std::vector<LocationType> chain;
+  bool includeCenter = false;
 };
 
 struct DoMethod {

@@ -108,6 +108,7 @@ class FieldAccess(Expr):
     k: int = 0
     unstructured: bool = False
     has_offset: bool = False  # unstructured: value read at the neighbour (inside a reduction)
+    vertical_indirection: Optional["FieldAccess"] = None  # level taken from this field's value
 
 
 @dataclass(eq=False)
@@ -161,8 +162,13 @@ class FieldHandle:
     def __call__(self, i=0, j=0, k=0) -> FieldAccess:
         return FieldAccess(self.name, self.access_id, i, j, k, self.unstructured)
 
-    def at(self, k=0, nbh=False) -> FieldAccess:
-        return FieldAccess(self.name, self.access_id, 0, 0, k, True, nbh)
+    def at(self, k=0, nbh=False, k_from=None) -> FieldAccess:
+        """k_from: field handle whose value at (element, k) is the level to read (vertical indirection,
+        statements.proto FieldAccessExpr.vertical_indirection); k is then added to it."""
+        ind = None
+        if k_from is not None:
+            ind = k_from.at() if isinstance(k_from, FieldHandle) else k_from
+        return FieldAccess(self.name, self.access_id, 0, 0, k, True, nbh, ind)
 
     @property
     def nbh(self) -> FieldAccess:
@@ -214,6 +220,18 @@ class If:
     cond: Expr
     then: List
     otherwise: Optional[List] = None
+
+
+@dataclass(eq=False)
+class Loop:
+    """loop_stmt over a neighbour chain (statements.proto LoopStmt + LoopDescriptorChain)."""
+    chain: List[str]
+    body: List
+    include_center: bool = False
+
+
+def loop_over(chain, *stmts, include_center=False) -> Loop:
+    return Loop(list(chain), list(stmts), include_center)
 
 
 @dataclass
@@ -317,6 +335,8 @@ class IIRBuilder:
                 },
                 "mask_k": 1 if "k" in dims else 0,
             }
+        if location is None and not sparse_chain:  # vertical-only field
+            return {"mask_k": 1}
         chain = sparse_chain if sparse_chain else [location]
         return {
             "unstructured_horizontal_dimension": {
@@ -409,6 +429,8 @@ class IIRBuilder:
                                         "data": {"accessID": e.access_id}, "ID": nid}}
         if isinstance(e, FieldAccess):
             _add(reads, e.access_id, _Ext(e.i, e.j, e.k, e.unstructured, e.has_offset))
+            if e.vertical_indirection is not None:
+                _add(reads, e.vertical_indirection.access_id, _Ext(0, 0, 0, True, False))
             return self._field_json(e, nid)
         if isinstance(e, Reduce):
             d = {"op": e.op, "rhs": self._expr(e.rhs, reads), "init": self._expr(e.init, reads),
@@ -420,6 +442,9 @@ class IIRBuilder:
 
     def _field_json(self, e: FieldAccess, nid: int) -> dict:
         d = {"name": e.name, "vertical_shift": e.k, "vertical_indirection": ""}
+        if e.vertical_indirection is not None:
+            d["vertical_indirection"] = e.vertical_indirection.name
+            d["vertical_indirection_data"] = {"accessID": e.vertical_indirection.access_id}
         if e.unstructured:
             d["unstructured_offset"] = {"has_offset": e.has_offset}
         elif e.i == 0 and e.j == 0:
@@ -478,6 +503,13 @@ class IIRBuilder:
                 d["else_part"] = self._block(s.otherwise, reads, writes)
             d.update({"loc": LOC, "data": self._acc_json(reads, writes), "ID": nid})
             out = {"if_stmt": d}
+        elif isinstance(s, Loop):
+            body = self._block(s.body, reads, writes)
+            out = {"loop_stmt": {
+                "statements": body,
+                "loop_descriptor": {"loop_descriptor_chain": {
+                    "iter_space": {"chain": list(s.chain), "include_center": s.include_center}}},
+                "loc": LOC, "data": self._acc_json(reads, writes), "ID": nid}}
         else:
             raise TypeError(type(s))
         for k, v in reads.items():
