@@ -153,7 +153,13 @@ struct Group {
   std::string name;
   std::set<int> fieldsRead, fieldsWritten;
   std::vector<std::pair<std::vector<LocationType>, bool>> chains; // tables needed
+  std::set<std::string> topChains; // tags of chains walked from the thread's own element: their
+                                   // neighbour indices are loaded once per thread
   bool usesGlobals = false;
+  // unstructured iteration space of the stages (Stage::i_range holds it: levels are the subdomain
+  // magic numbers of driver-includes/unstructured_domain.hpp:23, offsets index into the splitters)
+  bool hasSpace = false;
+  Interval space;
 };
 
 class IcoEmitter {
@@ -203,7 +209,8 @@ private:
 
 void IcoEmitter::collect(Group& g) {
   std::set<std::string> seen;
-  std::function<void(const ExprPtr&, bool)> walk = [&](const ExprPtr& e, bool) {
+  // nested = inside the rhs of a reduction or the body of a neighbour loop
+  std::function<void(const ExprPtr&, bool)> walk = [&](const ExprPtr& e, bool nested) {
     if(!e)
       return;
     if(e->kind == Expr::Var && e->isExternal)
@@ -212,9 +219,15 @@ void IcoEmitter::collect(Group& g) {
       std::string t = chainTag(e->chain, e->includeCenter);
       if(seen.insert(t).second)
         g.chains.push_back({e->chain, e->includeCenter});
+      if(!nested)
+        g.topChains.insert(t);
+      walk(e->kids[0], true);
+      for(size_t n = 1; n < e->kids.size(); ++n)
+        walk(e->kids[n], nested);
+      return;
     }
     for(auto const& k : e->kids)
-      walk(k, false);
+      walk(k, nested);
   };
   for(auto const* st : g.stages)
     for(auto const& dm : st->doMethods) {
@@ -223,20 +236,22 @@ void IcoEmitter::collect(Group& g) {
           return;
         (w ? g.fieldsWritten : g.fieldsRead).insert(e.accessID);
       });
-      std::function<void(const StmtPtr&)> ws = [&](const StmtPtr& s) {
-        walk(s->expr, false);
-        if(s->kind == Stmt::Loop) {
+      std::function<void(const StmtPtr&, bool)> ws = [&](const StmtPtr& s, bool nested) {
+        walk(s->expr, nested);
+        const bool isLoop = s->kind == Stmt::Loop;
+        if(isLoop) {
           std::string t = chainTag(s->chain, s->includeCenter);
           if(seen.insert(t).second)
             g.chains.push_back({s->chain, s->includeCenter});
+          g.topChains.insert(t);
         }
         for(auto const& c : s->body)
-          ws(c);
+          ws(c, nested || isLoop);
         for(auto const& c : s->orelse)
-          ws(c);
+          ws(c, nested);
       };
       for(auto const& s : dm.stmts)
-        ws(s);
+        ws(s, false);
     }
 }
 
@@ -260,12 +275,20 @@ std::vector<Group> IcoEmitter::plan(const Stencil& st) {
       if(stage.location == LocationType::None)
         throw std::runtime_error("b200-ico: stage " + std::to_string(stage.id) +
                                  " has no location type");
-      bool fits = !cur.stages.empty() && cur.loc == stage.location &&
+      bool sameSpace = cur.hasSpace == stage.hasIRange &&
+                       (!stage.hasIRange ||
+                        (cur.space.lowerLevel == stage.iRange.lowerLevel &&
+                         cur.space.upperLevel == stage.iRange.upperLevel &&
+                         cur.space.lowerOffset == stage.iRange.lowerOffset &&
+                         cur.space.upperOffset == stage.iRange.upperOffset));
+      bool fits = !cur.stages.empty() && cur.loc == stage.location && sameSpace &&
                   !readsThroughChain(stage, written) && opt_.FuseColumns != 0;
       if(!fits)
         flush();
       cur.ms = &ms;
       cur.loc = stage.location;
+      cur.hasSpace = stage.hasIRange;
+      cur.space = stage.iRange;
       cur.stages.push_back(&stage);
       StageInfo info = analysis::stageInfo(inst_, stage);
       for(auto const& fp : info.fields)
@@ -612,7 +635,8 @@ void IcoEmitter::emitKernel(const Group& g) {
   os_ << "__global__ void __launch_bounds__(" << block_ << ")\n" << g.name << "(";
   if(g.usesGlobals)
     os_ << "const globals g, ";
-  os_ << "const int k_size, const int n_elem, const int n_cells, const int n_edges, const int n_vertices";
+  os_ << "const int k_size, const int elem_lo, const int elem_hi, const int n_cells, const int n_edges, "
+         "const int n_vertices";
   for(auto const& ch : g.chains)
     os_ << ",\n    const int* __restrict__ tbl_" << chainTag(ch.first, ch.second);
   std::set<int> args = g.fieldsRead;
@@ -624,13 +648,15 @@ void IcoEmitter::emitKernel(const Group& g) {
     os_ << ",\n    " << (ro ? "const " : "") << "::dawn::float_type* __restrict__ " << fname(f) << "_p";
   }
   os_ << ") {\n";
-  os_ << "  const int pidx = blockIdx.x * " << block_ << " + threadIdx.x;\n";
-  os_ << "  if(pidx >= n_elem)\n    return;\n";
+  os_ << "  const int pidx = elem_lo + blockIdx.x * " << block_ << " + threadIdx.x; // elements [elem_lo, elem_hi)\n";
+  os_ << "  if(pidx >= elem_hi)\n    return;\n";
   os_ << "  (void)n_cells; (void)n_edges; (void)n_vertices;\n";
   // neighbour indices, once per thread
   for(auto const& ch : g.chains) {
     int size = icoChainSize(ch.first, ch.second);
     std::string tag = chainTag(ch.first, ch.second);
+    if(!g.topChains.count(tag))
+      continue; // only reached from neighbours: indices are fetched where they are used
     for(int n = 0; n < size; ++n)
       os_ << "  const int nb_" << tag << "_" << n << " = __ldg(&tbl_" << tag << "[pidx + "
           << IcoBody::stride(ch.first.front()) << " * " << n << "]);\n";
@@ -702,10 +728,14 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
   for(int f : scratch_)
     os_ << "  ::dawn_b200::scratch_field m_" << fname(f) << ";\n";
   os_ << "  ::dawn_b200::timer_b200 m_timer;\n";
+  os_ << "  std::vector<b200_splitter_t> m_splitters; // unstructured_domain twin\n";
   os_ << "  int m_error = 0;\npublic:\n  long m_launches = 0;\n";
   os_ << "  " << cls << "(const " << cls << "&) = delete;\n";
   os_ << "  " << cls << "(const b200_mesh_t* mesh, int k_size) : m_mesh(*mesh), m_k_size(k_size), m_timer(\""
       << inst_.name << "\") {\n";
+  os_ << "    for(int n = 0; n < mesh->num_splitters && mesh->splitters; ++n)\n"
+         "      m_splitters.push_back(mesh->splitters[n]);\n"
+         "    m_mesh.num_splitters = 0; m_mesh.splitters = nullptr; // owned copy above\n";
   for(auto const& t : tables) {
     os_ << "    {\n      const int chain[] = {";
     for(size_t n = 0; n < t.first.size(); ++n)
@@ -721,6 +751,15 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
   }
   os_ << "  }\n";
   os_ << "  int error() const { return m_error; }\n";
+  os_ << "  // dawn::unstructured_domain::set_splitter_index (driver-includes/unstructured_domain.hpp:31-33)\n";
+  os_ << "  void set_splitter_index(int loc, int space, int offset, int index) {\n"
+         "    for(auto& s : m_splitters)\n"
+         "      if(s.location == loc && s.subdomain == space && s.offset == offset) { s.index = index; return; }\n"
+         "    m_splitters.push_back(b200_splitter_t{loc, space, offset, index});\n  }\n";
+  os_ << "  bool splitter(int loc, int space, int offset, int* index) const {\n"
+         "    for(auto const& s : m_splitters)\n"
+         "      if(s.location == loc && s.subdomain == space && s.offset == offset) { *index = s.index; return true; }\n"
+         "    return false;\n  }\n";
   os_ << "  void set_stream(void* s) { m_timer.set_stream(s); }\n";
   for(auto const& gl : inst_.globals) {
     std::string t = gl.second.type == "Integer" ? "int" : gl.second.type == "Boolean" ? "bool" : "double";
@@ -763,13 +802,27 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
     bool sequential = g.ms->loopOrder != LoopOrder::Parallel;
     std::string n = IcoBody::stride(g.loc);
     os_ << "    {\n";
-    os_ << "      dim3 grid((" << n << " + " << block_ - 1 << ") / " << block_ << ", "
+    if(g.hasSpace) {
+      const int loc = static_cast<int>(g.loc);
+      os_ << "      int elem_lo = 0, elem_hi = 0;\n";
+      os_ << "      if(!splitter(" << loc << ", " << g.space.lowerLevel << ", " << g.space.lowerOffset
+          << ", &elem_lo) || !splitter(" << loc << ", " << g.space.upperLevel << ", "
+          << g.space.upperOffset << ", &elem_hi))\n"
+          << "        return ::dawn_b200::set_error(B200_ERR_ARG, \"" << inst_.name
+          << ": splitter index of an unstructured iteration space is not set (set_splitter_index)\");\n";
+      os_ << "      if(elem_lo < 0 || elem_hi > " << n << ")\n"
+          << "        return ::dawn_b200::set_error(B200_ERR_ARG, \"" << inst_.name
+          << ": splitter index outside the mesh\");\n";
+    } else
+      os_ << "      const int elem_lo = 0, elem_hi = " << n << ";\n";
+    os_ << "      if(elem_hi > elem_lo) {\n";
+    os_ << "      dim3 grid((elem_hi - elem_lo + " << block_ - 1 << ") / " << block_ << ", "
         << (sequential ? std::string("1") : "(k_size + " + std::to_string(lpt_ - 1) + ") / " + std::to_string(lpt_))
         << ");\n";
     os_ << "      " << g.name << "<<<grid, " << block_ << ", 0, stream>>>(";
     if(g.usesGlobals)
       os_ << "m_globals, ";
-    os_ << "k_size, " << n << ", n_cells, n_edges, n_vertices";
+    os_ << "k_size, elem_lo, elem_hi, n_cells, n_edges, n_vertices";
     for(auto const& ch : g.chains)
       os_ << ", m_tbl_" << chainTag(ch.first, ch.second);
     std::set<int> args = g.fieldsRead;
@@ -777,7 +830,7 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
     for(int f : args)
       if(!registerOnly_.count(f))
         os_ << ", " << fname(f) << "_p";
-    os_ << ");\n      ++m_launches;\n    }\n";
+    os_ << ");\n      ++m_launches;\n      }\n    }\n";
   }
   os_ << "    return ::dawn_b200::check_launch();\n  }\n";
   // ---- host-buffer entry points (reference: run_<N>_from_{c,fort}_host, CudaIcoCodeGen.cpp:896-927;
@@ -926,6 +979,10 @@ std::string IcoEmitter::generate() {
   os_ << "B200_EXPORT void free_" << n << "(void* handle) { delete static_cast<" << cls << "*>(handle); }\n";
   os_ << "B200_EXPORT long launches_" << n << "(void* handle) { return static_cast<" << cls
       << "*>(handle)->m_launches; }\n";
+  // reference: set_splitter_index(GlobalGpuTriMesh*, loc, space, offset, index) (cuda_utils.cpp:3-8)
+  os_ << "B200_EXPORT void set_splitter_index_" << n
+      << "(void* handle, int loc, int space, int offset, int index) { static_cast<" << cls
+      << "*>(handle)->set_splitter_index(loc, space, offset, index); }\n";
   for(auto const& g : inst_.globals) {
     os_ << "B200_EXPORT void set_" << n << "_" << cIdent(g.first) << "(void* handle, double v) { static_cast<"
         << cls << "*>(handle)->set_" << cIdent(g.first) << "(v); }\n";
@@ -941,7 +998,7 @@ std::string IcoEmitter::generate() {
     int f = inst_.apiFieldIDs[a];
     os_ << (a ? ", " : "") << "{\\\"name\\\": \\\"" << inst_.nameOf(f) << "\\\", \\\"location\\\": \\\""
         << (isVertical(f) ? "none" : locName(fieldLoc(f))) << "\\\", \\\"sparse\\\": "
-        << (isSparse(f) ? sparseSize(f) : 0) << "}";
+        << (isSparse(f) ? sparseSize(f) : 0) << ", \\\"k\\\": " << (hasK(f) ? 1 : 0) << "}";
   }
   os_ << "], \\\"written\\\": [";
   bool firstW = true;
@@ -987,6 +1044,7 @@ std::string icoCHeader(const iir::Instantiation& inst) {
     os << " " << inst.nameOf(f);
   os << " */\n";
   os << "int setup_" << n << "(void** handle, const b200_mesh_t* mesh, int k_size, void* stream);\n";
+  os << "void set_splitter_index_" << n << "(void* handle, int loc, int space, int offset, int index);\n";
   os << "int run_" << n << "(void* handle, const b200_field_t* fields, int nfields, void* stream);\n";
   os << "int run_" << n << "_from_c_host(void* handle, double* const* host_fields, int nfields, void* stream);\n";
   os << "int run_" << n << "_from_fort_host(void* handle, double* const* host_fields, int nfields, void* stream);\n";
@@ -1029,6 +1087,9 @@ std::string icoF90Interface(const iir::Instantiation& inst) {
   }
   os << "    subroutine free_" << n << "(handle) bind(c)\n      import :: c_ptr\n"
         "      type(c_ptr), value :: handle\n    end subroutine\n";
+  os << "    subroutine set_splitter_index_" << n << "(handle, loc, space, offset, index) bind(c)\n"
+        "      import :: c_ptr, c_int\n      type(c_ptr), value :: handle\n"
+        "      integer(c_int), value :: loc, space, offset, index\n    end subroutine\n";
   os << "  end interface\n";
   os << "  ! field order of fields(*):";
   for(int f : inst.apiFieldIDs)

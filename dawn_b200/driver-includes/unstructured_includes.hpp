@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <exception>
 #include <string>
+#include <vector>
 
 #include "defs.hpp"
 #include "extent.hpp"

@@ -14,10 +14,16 @@ class NbhTable(ctypes.Structure):
                 ("table", ctypes.c_void_p)]
 
 
+class Splitter(ctypes.Structure):
+    _fields_ = [("location", ctypes.c_int), ("subdomain", ctypes.c_int), ("offset", ctypes.c_int),
+                ("index", ctypes.c_int)]
+
+
 class MeshStruct(ctypes.Structure):
     _fields_ = [("num_cells", ctypes.c_int), ("num_edges", ctypes.c_int),
                 ("num_vertices", ctypes.c_int), ("num_tables", ctypes.c_int),
-                ("tables", ctypes.POINTER(NbhTable))]
+                ("tables", ctypes.POINTER(NbhTable)), ("num_splitters", ctypes.c_int),
+                ("splitters", ctypes.POINTER(Splitter))]
 
 
 class Mesh:
@@ -25,7 +31,7 @@ class Mesh:
     adapter offering num_cells/num_edges/num_vertices and nbh_table(chain, include_center, nbh_size)
     (e.g. dawn_b200.trimesh.TriMesh)."""
 
-    def __init__(self, adapter, tables, device="cuda"):
+    def __init__(self, adapter, tables, device="cuda", splitters=None):
         import torch
         self.adapter = adapter
         self._dev = []
@@ -45,8 +51,10 @@ class Mesh:
             e.chain_len, e.include_center, e.nbh_size, e.table = len(chain), center, size, dev.data_ptr()
             entries.append(e)
         self._entries = (NbhTable * max(1, len(entries)))(*entries)
+        spl = [Splitter(int(l), int(s), int(o), int(i)) for (l, s, o), i in (splitters or {}).items()]
+        self._splitters = (Splitter * max(1, len(spl)))(*spl)
         self.struct = MeshStruct(adapter.num_cells, adapter.num_edges, adapter.num_vertices,
-                                 len(entries), self._entries)
+                                 len(entries), self._entries, len(spl), self._splitters)
 
     def soa_table(self, index):
         """device table `index` back on the host, shaped [nbh, element]"""

@@ -146,10 +146,11 @@ class StencilModule:
     def __call__(self, domain, stream=None):
         return Stencil(self, domain, stream)
 
-    def on_mesh(self, adapter, k_size, stream=None):
+    def on_mesh(self, adapter, k_size, stream=None, splitters=None):
         """Unstructured modules: bind to a mesh adapter (e.g. trimesh.TriMesh) and a level count,
-        like the reference's setup_<N>(mesh, k_size, stream) (CudaIcoCodeGen.cpp:1198-1219)."""
-        return UnstructuredStencil(self, adapter, k_size, stream)
+        like the reference's setup_<N>(mesh, k_size, stream) (CudaIcoCodeGen.cpp:1198-1219).
+        splitters: {(location, subdomain, offset): index} for unstructured iteration spaces."""
+        return UnstructuredStencil(self, adapter, k_size, stream, splitters)
 
 
 class Stencil:
@@ -330,10 +331,10 @@ class UnstructuredStencil:
     """Instance of a generated b200-ico stencil on a mesh.  Fields are torch CUDA tensors (float64):
     dense [k, element], sparse [k, nbh, element], in the module's API order."""
 
-    def __init__(self, module, adapter, k_size, stream=None):
+    def __init__(self, module, adapter, k_size, stream=None, splitters=None):
         from .mesh import Mesh
         self.module = module
-        self.mesh = Mesh(adapter, module.info["tables"])
+        self.mesh = Mesh(adapter, module.info["tables"], splitters=splitters)
         self.k_size = int(k_size)
         self.handle = ctypes.c_void_p()
         _rt.check(module._setup(ctypes.byref(self.handle), ctypes.addressof(self.mesh.struct),
@@ -342,13 +343,22 @@ class UnstructuredStencil:
     def descriptors(self, tensors):
         out = []
         for f, t in zip(self.module.fields, tensors):
-            if t.dim() == 3:   # sparse [k, nbh, n]
-                out.append(_rt.Field(t.data_ptr(), t.shape[2], t.shape[1] * t.shape[2]))
-            elif t.dim() == 2:
-                out.append(_rt.Field(t.data_ptr(), 0, t.shape[1]))
-            else:
+            has_k = bool(f.get("k", 1))
+            if f["location"] == "none":      # vertical [k]
                 out.append(_rt.Field(t.data_ptr(), 0, 1))
+            elif f["sparse"]:                # [k, nbh, n] or horizontal-only [nbh, n]
+                n = t.shape[-1]
+                out.append(_rt.Field(t.data_ptr(), n, t.shape[-2] * n if has_k else 0))
+            else:                            # [k, n] or horizontal-only [n]
+                out.append(_rt.Field(t.data_ptr(), 0, t.shape[-1]))
         return out
+
+    def set_splitter_index(self, location, subdomain, offset, index):
+        """dawn::GlobalGpuTriMesh::set_splitter_index (driver-includes/cuda_utils.hpp:53-56)."""
+        fn = getattr(self.module.lib, "set_splitter_index_" + self.module.name)
+        fn.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4
+        fn.restype = None
+        fn(self.handle, int(location), int(subdomain), int(offset), int(index))
 
     def run(self, *tensors, stream=None):
         n = len(self.module.fields)

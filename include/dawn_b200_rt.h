@@ -118,10 +118,19 @@ typedef struct b200_nbh_table_t {
   const int* table;
 } b200_nbh_table_t;
 
+/* One entry of the reference's dawn::unstructured_domain map (driver-includes/
+ * unstructured_domain.hpp:23-36): first element index of a subdomain.  location: 0 cells, 1 edges,
+ * 2 vertices; subdomain: 0 LateralBoundary, 1000 Nudging, 2000 Interior, 3000 Halo, 4000 End. */
+typedef struct b200_splitter_t {
+  int location, subdomain, offset, index;
+} b200_splitter_t;
+
 typedef struct b200_mesh_t {
   int num_cells, num_edges, num_vertices;
   int num_tables;
   const b200_nbh_table_t* tables;
+  int num_splitters;                 /* may be 0: stencils without iteration spaces need none */
+  const b200_splitter_t* splitters;  /* copied by setup_<N>; set_splitter_index_<N> edits the copy */
 } b200_mesh_t;
 
 /* ---- j-slab halo exchange across the GPUs of one box (new: the reference has no communication

@@ -509,19 +509,40 @@ def _collect_k(node, kext):
 _LOC = {"Cell": 0, "Edge": 1, "Vertex": 2}
 
 
+class _Ctx:
+    """Where an expression is evaluated: `center` = element ids the enclosing neighbour loop /
+    reduction runs around (the stage's own elements at top level), `nb` = current neighbour ids
+    (None outside loops / reductions), `nb_idx` = position in the neighbour list, `center_loc` =
+    location type of `center`."""
+    __slots__ = ("center", "center_loc", "nb", "nb_idx")
+
+    def __init__(self, center, center_loc, nb=None, nb_idx=None):
+        self.center, self.center_loc, self.nb, self.nb_idx = center, center_loc, nb, nb_idx
+
+
 class UnstructuredRun:
     """Executes an unstructured IIR with the semantics of the reference's naive-ico backend
     (dawn/src/dawn/CodeGen/CXXNaive-ico/CXXNaiveCodeGen.cpp:366-617): per multistage, per k of the
-    interval, per stage `for loc in get<Cells|Edges|Vertices>(mesh)`; a reduction iterates the
-    neighbour list of its chain in mesh order starting from `init`, `lhs op= [weight *] rhs`
-    (toylib_interface.hpp:280-323).  Vectorised over the elements of a stage (a stage never reads
-    through a chain what it writes itself).
+    interval, per stage `for loc in get<Cells|Edges|Vertices>(mesh)` (restricted to the stage's
+    iteration space when it has one, :546-583); a reduction iterates the neighbour list of its
+    chain in mesh order starting from `init`, `lhs op= [weight *] rhs` (toylib_interface.hpp:280-323);
+    a nested reduction runs around the current neighbour (ASTStencilBody.cpp:359-368); a loop
+    statement visits the neighbours in the same order with a running sparse index (:114-133).
+    Dense accesses inside a loop / reduction address the neighbour when they carry an offset or when
+    the field lives on another location type than the centre (:237-252), otherwise the centre;
+    sparse accesses address (centre, position).  A vertical indirection reads the level from the
+    index field at (element, k) (:334-349).  Vectorised over the elements of a stage (a stage never
+    reads through a chain what it writes itself).
 
     `mesh` must offer num(loc), valid(loc) and nbh_table(chain, include_center) (row-major, -1
     padded): dawn_b200.trimesh.TriMesh is pinned bit-exactly against the reference's toylib.
-    Fields: dense [k, n]; sparse [k, n, nbh]; vertical-only [k]."""
+    Fields: dense [k, n]; sparse [k, n, nbh]; vertical-only [k]; horizontal-only dense [n] / sparse
+    [n, nbh].  `splitters`: {(location, subdomain, offset): element index} for unstructured
+    iteration spaces (driver-includes/unstructured_domain.hpp:23-36)."""
 
-    def __init__(self, iir, mesh, k_size, globals_=None):
+    SUBDOMAIN = {0: "LateralBoundary", 1000: "Nudging", 2000: "Interior", 3000: "Halo", 4000: "End"}
+
+    def __init__(self, iir, mesh, k_size, globals_=None, splitters=None):
         self.iir = load_iir(iir)
         self.meta = self.iir["metadata"]
         self.ir = self.iir["internalIR"]
@@ -531,10 +552,17 @@ class UnstructuredRun:
         if globals_:
             self.globals.update(globals_)
         self.dims = {int(k): v for k, v in self.meta.get("fieldIDtoDimensions", {}).items()}
+        self.splitters = dict(splitters or {})
+
+    def _chain_of(self, aid):
+        d = self.dims.get(aid, {}).get("unstructured_horizontal_dimension")
+        return d.get("iter_space", {}).get("chain", []) if d else []
 
     def _is_sparse(self, aid):
-        d = self.dims.get(aid, {}).get("unstructured_horizontal_dimension")
-        return bool(d) and len(d.get("iter_space", {}).get("chain", [])) > 1
+        return len(self._chain_of(aid)) > 1
+
+    def _has_k(self, aid):
+        return bool(self.dims.get(aid, {}).get("mask_k", 1))
 
     def run(self, fields):
         self.f = fields
@@ -558,26 +586,47 @@ class UnstructuredRun:
                                 self._stage(stage, dms, k)
         return self.f
 
+    def _space(self, stage):
+        """Element index range of a stage with an unstructured iteration space (stored in i_range:
+        levels are the subdomain magic numbers 0/1000/2000/3000/4000)."""
+        iv = stage.get("i_range")
+        if not iv:
+            return None
+
+        def bound(level_key, special_key, off_key):
+            level = iv.get(level_key, 0)
+            if special_key in iv and level_key not in iv:
+                level = 0
+            return self.splitters[(self.loc, level, iv.get(off_key, 0))]
+        return (bound("lower_level", "special_lower_level", "lower_offset"),
+                bound("upper_level", "special_upper_level", "upper_offset"))
+
     def _stage(self, stage, dms, k):
         self.k = k
         self.loc = _LOC[stage["locationType"]]
-        self.elems = np.nonzero(self.mesh.valid(self.loc))[0]
+        valid = self.mesh.valid(self.loc)
+        space = self._space(stage)
+        if space is not None:
+            sel = np.zeros_like(valid)
+            sel[space[0]:space[1]] = True
+            valid = valid & sel
+        self.elems = np.nonzero(valid)[0]
         self.locals = {}
-        self.nb = None       # neighbour ids of the reduction being evaluated (per element)
-        self.nb_idx = None   # position in the neighbour list
+        top = _Ctx(self.elems, self.loc)
         for dm in dms:
             for s in dm["ast"]["block_stmt"].get("statements", []):
-                self._stmt(s, None)
+                self._stmt(s, None, top)
 
-    def _stmt(self, node, mask):
+    # ---- statements ---------------------------------------------------------------------------
+    def _stmt(self, node, mask, ctx):
         kd, v = _kind(node)
         if kd == "block_stmt":
             for s in v.get("statements", []):
-                self._stmt(s, mask)
+                self._stmt(s, mask, ctx)
         elif kd == "expr_stmt":
             ek, ev = _kind(v["expr"])
             assert ek == "assignment_expr", ek
-            rhs = self._eval(ev["right"])
+            rhs = self._eval(ev["right"], ctx)
             op = ev.get("op", "=")
             lk, lv = _kind(ev["left"])
             if lk == "var_access_expr":
@@ -587,34 +636,84 @@ class UnstructuredRun:
                 self.locals[aid] = np.where(mask, new, cur) if mask is not None else \
                     np.broadcast_to(np.asarray(new, dtype=float), cur.shape).copy()
             else:
+                idx = self._index(lv, ctx, write=True)
                 arr = self.f[lv["name"]]
-                kk = self.k + lv.get("vertical_shift", 0)
-                cur = arr[kk, self.elems] if arr.ndim > 1 else arr[kk]
+                cur = arr[idx]
                 new = rhs if op == "=" else _BIN[op[0]](cur, rhs)
+                new = np.broadcast_to(np.asarray(new, dtype=float), np.shape(cur))
                 if mask is not None:
-                    new = np.where(mask, new, cur)
-                if arr.ndim > 1:
-                    arr[kk, self.elems] = new
+                    if np.ndim(cur) == 0:      # vertical-only field: every element stores the same slot
+                        if np.any(mask):
+                            arr[idx] = np.asarray(new).flat[0] if np.ndim(new) else new
+                        return
+                    sel = tuple(np.asarray(i)[mask] if np.ndim(i) else i for i in idx)
+                    arr[sel] = new[mask]
                 else:
-                    arr[kk] = new
+                    arr[idx] = new
         elif kd == "var_decl_stmt":
             aid = v["var_decl_stmt_data"]["accessID"]
             init = v.get("init_list", [])
-            val = self._eval(init[0]) if init else 0.0
+            val = self._eval(init[0], ctx) if init else 0.0
             tid = v.get("type", {}).get("builtin_type", {}).get("type_id", "Float")
             if tid == "Integer":
                 val = np.trunc(val)
             self.locals[aid] = np.broadcast_to(np.asarray(val, dtype=float), self.elems.shape).copy()
         elif kd == "if_stmt":
             ck, cv = _kind(v["cond_part"])
-            cond = np.broadcast_to(np.asarray(self._eval(cv["expr"])).astype(bool), self.elems.shape)
-            self._stmt(v["then_part"], cond if mask is None else mask & cond)
+            cond = np.broadcast_to(np.asarray(self._eval(cv["expr"], ctx)).astype(bool), self.elems.shape)
+            self._stmt(v["then_part"], cond if mask is None else mask & cond, ctx)
             if v.get("else_part"):
-                self._stmt(v["else_part"], ~cond if mask is None else mask & ~cond)
+                self._stmt(v["else_part"], ~cond if mask is None else mask & ~cond, ctx)
+        elif kd == "loop_stmt":
+            if ctx.nb is not None:
+                raise NotImplementedError("nested neighbour loops")
+            space = v["loop_descriptor"]["loop_descriptor_chain"]["iter_space"]
+            table = self.mesh.nbh_table(space["chain"], space.get("include_center", False))[ctx.center]
+            for idx in range(table.shape[1]):
+                nb = table[:, idx]
+                valid = nb >= 0
+                if not valid.any():
+                    continue
+                inner = _Ctx(ctx.center, ctx.center_loc, nb, idx)
+                self._stmt(v["statements"], valid if mask is None else mask & valid, inner)
         else:
             raise NotImplementedError(kd)
 
-    def _eval(self, node):
+    # ---- field addressing ------------------------------------------------------------------------
+    def _index(self, v, ctx, write=False):
+        aid = v["data"]["accessID"]
+        name = v["name"]
+        kk = self.k + v.get("vertical_shift", 0)
+        if v.get("vertical_indirection"):
+            iname = v["vertical_indirection"]
+            iid = v.get("vertical_indirection_data", {}).get("accessID")
+            if iid is None:
+                iid = next(int(a) for a, n in self.meta["accessIDToName"].items() if n == iname)
+            ind = {"name": iname, "data": {"accessID": iid}, "unstructured_offset": {"has_offset": False}}
+            kk = self.f[iname][self._index(ind, ctx)].astype(np.int64) + v.get("vertical_shift", 0)
+        chain = self._chain_of(aid)
+        has_k = self._has_k(aid)
+        if not chain:                          # vertical-only
+            return (kk,)
+        if len(chain) > 1:                     # sparse: (centre, position in the neighbour list)
+            if ctx.nb_idx is None:
+                raise ValueError("sparse field %s used outside a reduction or neighbour loop" % name)
+            return (kk, ctx.center, ctx.nb_idx) if has_k else (ctx.center, ctx.nb_idx)
+        has_offset = v.get("unstructured_offset", {}).get("has_offset", False)
+        if ctx.nb is None:
+            if has_offset:
+                raise ValueError("neighbour access to %s outside a reduction or neighbour loop" % name)
+            elem = ctx.center
+        elif has_offset or _LOC[chain[0]] != ctx.center_loc:
+            if write:
+                raise ValueError("a neighbour loop may only write its own element (%s)" % name)
+            elem = np.maximum(ctx.nb, 0)
+        else:
+            elem = ctx.center
+        return (kk, elem) if has_k else (elem,)
+
+    # ---- expressions -----------------------------------------------------------------------------
+    def _eval(self, node, ctx):
         kd, v = _kind(node)
         if kd == "literal_access_expr":
             t = v.get("type", {}).get("type_id", "Float")
@@ -625,43 +724,41 @@ class UnstructuredRun:
                 return self.globals[v["name"]]
             return self.locals[v["data"]["accessID"]]
         if kd == "field_access_expr":
-            arr = self.f[v["name"]]
-            kk = self.k + v.get("vertical_shift", 0)
-            if arr.ndim == 1:
-                return arr[kk]
-            if self._is_sparse(v["data"]["accessID"]):
-                return arr[kk, self.elems, self.nb_idx]
-            if v.get("unstructured_offset", {}).get("has_offset", False):
-                return arr[kk, np.maximum(self.nb, 0)]
-            return arr[kk, self.elems]
+            return self.f[v["name"]][self._index(v, ctx)]
         if kd == "binary_operator":
-            a, b = self._eval(v["left"]), self._eval(v["right"])
+            a, b = self._eval(v["left"], ctx), self._eval(v["right"], ctx)
             with np.errstate(all="ignore"):
                 return _BIN[v["op"]](a, b)
         if kd == "unary_operator":
-            a = self._eval(v["operand"])
+            a = self._eval(v["operand"], ctx)
             return np.negative(a) if v["op"] == "-" else (np.logical_not(a) if v["op"] == "!" else a)
         if kd == "ternary_operator":
-            return np.where(self._eval(v["cond"]), self._eval(v["left"]), self._eval(v["right"]))
+            return np.where(self._eval(v["cond"], ctx), self._eval(v["left"], ctx),
+                            self._eval(v["right"], ctx))
         if kd == "fun_call_expr":
             with np.errstate(all="ignore"):
-                return _MATH[v["callee"].split("::")[-1]](*[self._eval(a) for a in v.get("arguments", [])])
+                return _MATH[v["callee"].split("::")[-1]](*[self._eval(a, ctx)
+                                                            for a in v.get("arguments", [])])
         if kd == "reduction_over_neighbor_expr":
-            if self.nb is not None:
-                raise NotImplementedError("nested reductions")
-            chain = v["iter_space"]["chain"]
-            table = self.mesh.nbh_table(chain, v["iter_space"].get("include_center", False))[self.elems]
-            acc = np.broadcast_to(np.asarray(self._eval(v["init"]), dtype=float), self.elems.shape).copy()
+            space = v["iter_space"]
+            chain = space["chain"]
+            # inside a loop / reduction the nested reduction runs around the current neighbour
+            center = ctx.center if ctx.nb is None else np.maximum(ctx.nb, 0)
+            around = _Ctx(center, _LOC[chain[0]])
+            table = self.mesh.nbh_table(chain, space.get("include_center", False))[center]
+            acc = np.broadcast_to(np.asarray(self._eval(v["init"], around), dtype=float),
+                                  center.shape).copy()
             weights = v.get("weights", [])
             op = v.get("op", "+")
             for idx in range(table.shape[1]):
-                self.nb, self.nb_idx = table[:, idx], idx
-                valid = self.nb >= 0
+                nb = table[:, idx]
+                valid = nb >= 0
                 if not valid.any():
                     continue
-                rhs = self._eval(v["rhs"])
+                inner = _Ctx(center, around.center_loc, nb, idx)
+                rhs = self._eval(v["rhs"], inner)
                 if weights:
-                    rhs = np.multiply(self._eval(weights[idx]), rhs)
+                    rhs = np.multiply(self._eval(weights[idx], around), rhs)
                 if op in ("+", "-", "*", "/"):
                     new = _BIN[op](acc, rhs)
                 elif op == "min":
@@ -671,10 +768,9 @@ class UnstructuredRun:
                 else:
                     raise NotImplementedError(op)
                 acc = np.where(valid, new, acc)
-            self.nb = self.nb_idx = None
             return acc
         raise NotImplementedError(kd)
 
 
-def run_unstructured(iir, mesh, k_size, fields, globals_=None):
-    return UnstructuredRun(iir, mesh, k_size, globals_).run(fields)
+def run_unstructured(iir, mesh, k_size, fields, globals_=None, splitters=None):
+    return UnstructuredRun(iir, mesh, k_size, globals_, splitters).run(fields)

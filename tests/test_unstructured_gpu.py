@@ -12,24 +12,39 @@ pytestmark = pytest.mark.gpu
 LOC = {"cells": CELL, "edges": EDGE, "vertices": VERTEX}
 
 
-def _run(name, mesh, k, fields, **opts):
+def _run(name, mesh, k, fields, splitters=None, **opts):
     import torch
     import dawn_b200
     mod = dawn_b200.load_stencil(name, **opts)
-    st = mod.on_mesh(mesh, k)
+    st = mod.on_mesh(mesh, k, splitters=splitters)
     tens = []
     for fd in mod.fields:
         a = fields[fd["name"]]
         if fd["sparse"]:
-            a = np.ascontiguousarray(a.transpose(0, 2, 1))  # oracle [k,n,nbh] -> device [k,nbh,n]
+            a = np.ascontiguousarray(np.swapaxes(a, -1, -2))  # oracle [k,n,nbh] -> device [k,nbh,n]
         tens.append(torch.from_numpy(np.ascontiguousarray(a)).cuda())
     st.run(*tens)
     torch.cuda.synchronize()
     out = {}
     for fd, t in zip(mod.fields, tens):
         a = t.cpu().numpy()
-        out[fd["name"]] = a.transpose(0, 2, 1) if fd["sparse"] else a
+        out[fd["name"]] = np.swapaxes(a, -1, -2) if fd["sparse"] else a
     return out, st
+
+
+def _random_fields(mod, m, k, rng, integer_levels=()):
+    """One random array per API field of a module, in the oracle's layout."""
+    f = {}
+    for fd in mod.fields:
+        shape = []
+        if fd.get("k", 1):
+            shape.append(k)
+        if fd["location"] != "none":
+            shape.append(m.num(LOC[fd["location"]]))
+        if fd["sparse"]:
+            shape.append(fd["sparse"])
+        f[fd["name"]] = rng.uniform(0.5, 1.5, shape)
+    return f
 
 
 def _rand(rng, m, k, spec):
@@ -184,3 +199,98 @@ def test_from_host_entry_points_and_verify():
     for n, mtr in zip(written, metrics):
         if n in ("div_vec", "rot_vec"):
             assert mtr.is_valid == 1 and mtr.max_abs_err == 0.0 and mtr.iteration == 3, n
+
+
+TOYLIB = ["copyCell", "copyEdge", "accumulateEdgeToCell", "verticalSum", "tridiagonalSolve",
+          "sparseDimension", "sparseDimensionTwice", "nestedSimple", "nestedWithField",
+          "nestedWithSparse", "sparseAssignment0", "sparseAssignment1", "sparseAssignment2",
+          "sparseAssignment3", "sparseAssignment4", "sparseAssignment5", "horizontalVertical"]
+
+
+@pytest.mark.parametrize("name", TOYLIB)
+@pytest.mark.parametrize("nx,ny,k", [(10, 10, 1), (13, 7, 11)])
+def test_toylib_integration_stencils(name, nx, ny, k):
+    """Stencils of dawn/test/integration-test/unstructured/GenerateUnstructuredStencils.cpp: nested
+    reductions, sparse dimensions, neighbour loops writing sparse fields, horizontal-only and
+    vertical-only fields.  The oracle is pinned on the reference's expected values
+    (tests/test_unstructured_known_answers.py)."""
+    import dawn_b200
+    m = TriMesh(nx, ny)
+    mod = dawn_b200.load_stencil(name)
+    f = _random_fields(mod, m, k, np.random.default_rng(41))
+    if name == "tridiagonalSolve":
+        f["b"] += 4.0
+    want = naive_interp.run_unstructured(iir_path(name), m, k, {n: v.copy() for n, v in f.items()})
+    got, _ = _run(name, m, k, f)
+    for fd in mod.fields:
+        n = fd["name"]
+        if fd["location"] == "none":
+            assert bit_equal(got[n], want[n]), n
+            continue
+        v = m.valid(LOC[fd["location"]])
+        axis = 1 if fd.get("k", 1) else 0
+        assert bit_equal(np.compress(v, got[n], axis=axis), np.compress(v, want[n], axis=axis)), n
+
+
+def test_toylib_known_answers_on_device():
+    """ToylibIntegrationTestCompareOutput.cpp:381-429,493-526,635-660 on the GPU path itself."""
+    m = TriMesh(10, 10)
+    ones = lambda loc, v: np.full((1, m.num(loc)), float(v))
+    got, _ = _run("nestedWithField", m, 1, {"cell_field": ones(CELL, 0), "edge_field": ones(EDGE, 200),
+                                            "vertex_field": ones(VERTEX, 1)})
+    assert np.all(np.abs(got["cell_field"] - 606.0) < 1e-12)
+    ecv = [EDGE, CELL, VERTEX]
+    got, _ = _run("sparseAssignment0", m, 1, {
+        "vn": np.full((1, m.num_edges, 4), -1.0), "uVert": ones(VERTEX, 1), "vVert": ones(VERTEX, 2),
+        "nx": ones(VERTEX, 3), "ny": ones(VERTEX, 4)})
+    ok = (m.nbh_table(ecv) >= 0) & m.valid(EDGE)[:, None]
+    assert np.all(got["vn"][0][ok] == 11.0)
+    assert np.all(got["vn"][0][~ok & m.valid(EDGE)[:, None]] == -1.0)
+    got, _ = _run("sparseAssignment4", m, 1, {"sparse": np.zeros((1, m.num_cells, 3)), "v": ones(VERTEX, 1)})
+    assert np.all(got["sparse"] == 2.0)
+
+
+def test_vertical_indirection_on_device():
+    # ToylibIntegrationTestCompareOutput.cpp:722-748
+    m = TriMesh(10, 10)
+    k = 10
+    rng = np.random.default_rng(43)
+    lev = np.arange(k, dtype=float)[:, None]
+    f = {"in": rng.uniform(0, 1, (k, m.num_cells)), "out": np.full((k, m.num_cells), -1.0),
+         "kidx": np.zeros((k, m.num_cells)) + lev + 1}
+    f["kidx"][: k - 1] = rng.integers(0, k, (k - 1, m.num_cells)).astype(float)  # any level
+    want = naive_interp.run_unstructured(iir_path("verticalIndirecion"), m, k,
+                                         {n: v.copy() for n, v in f.items()})
+    got, _ = _run("verticalIndirecion", m, k, f)
+    assert bit_equal(got["out"], want["out"])
+    assert np.all(got["out"][k - 1] == -1.0)
+
+
+def test_unstructured_iteration_space_and_splitters():
+    # GenerateUnstructuredStencils.cpp:847-872; driver-includes/unstructured_domain.hpp:23-36
+    import dawn_b200
+    m = TriMesh(8, 8)
+    k = 3
+    n = m.num_cells
+    f = {"out": np.zeros((k, n)), "in_1": np.full((k, n), 1.0), "in_2": np.full((k, n), 2.0)}
+    spl = {(CELL, 2000, 0): 10, (CELL, 3000, 0): 60, (CELL, 4000, 0): 100}
+    want = naive_interp.run_unstructured(iir_path("iterationSpaceUnstructured"), m, k,
+                                         {a: v.copy() for a, v in f.items()}, splitters=spl)
+    got, st = _run("iterationSpaceUnstructured", m, k, f, splitters=spl)
+    assert bit_equal(got["out"], want["out"])
+    assert st.launches() == 2
+    # moving a splitter afterwards (set_splitter_index) changes the ranges of the next run
+    import torch
+    st.set_splitter_index(CELL, 3000, 0, 40)
+    t = [torch.from_numpy(f[a["name"]].copy()).cuda() for a in st.module.fields]
+    st.run(*t)
+    torch.cuda.synchronize()
+    out = t[[a["name"] for a in st.module.fields].index("out")].cpu().numpy()
+    ref = np.zeros(n)
+    ref[40:100] = 1
+    ref[10:40] = 2
+    assert np.array_equal(out, np.broadcast_to(ref, (k, n)))
+    # a missing splitter is an error, not a silent full-range run
+    st2 = dawn_b200.load_stencil("iterationSpaceUnstructured").on_mesh(m, k)
+    with pytest.raises(dawn_b200.runtime.RuntimeError_, match="splitter index"):
+        st2.run(*t)

@@ -23,7 +23,8 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(__file__))
-from iir_builder import FULL, IIRBuilder, Interval, k_cache, reduce_over, where  # noqa: E402
+from iir_builder import (FULL, IIRBuilder, Interval, k_cache, lit, loop_over, reduce_over,  # noqa: E402
+                         where)
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "stencils")
 
@@ -249,6 +250,168 @@ def unstructured_intp():
     return b
 
 
+# ---- reference toylib integration stencils (dawn/test/integration-test/unstructured/
+# GenerateUnstructuredStencils.cpp; expected values: ToylibIntegrationTestCompareOutput.cpp) ---------
+def _ico(name):
+    return IIRBuilder(name, grid="Unstructured")
+
+
+def ico_copy_cell():  # :37-60
+    b = _ico("copyCell")
+    i, o = b.field("in_field", "k", "Cell"), b.field("out_field", "k", "Cell")
+    b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, b.assign(o, i.at())), location="Cell")))
+    return b
+
+
+def ico_copy_edge():  # :62-82
+    b = _ico("copyEdge")
+    i, o = b.field("in_field", "k", "Edge"), b.field("out_field", "k", "Edge")
+    b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, b.assign(o, i.at())), location="Edge")))
+    return b
+
+
+def ico_accumulate_edge_to_cell():  # :84-110
+    b = _ico("accumulateEdgeToCell")
+    i, o = b.field("in_field", "k", "Edge"), b.field("out_field", "k", "Cell")
+    b.stencil(b.multistage("Parallel", b.stage(
+        b.do(FULL, b.assign(o, reduce_over(["Cell", "Edge"], i.nbh))), location="Cell")))
+    return b
+
+
+def ico_vertical_sum():  # :112-137
+    b = _ico("verticalSum")
+    i, o = b.field("in_field", "k", "Cell"), b.field("out_field", "k", "Cell")
+    b.stencil(b.multistage("Parallel", b.stage(
+        b.do(Interval("Start", "End", 1, -1), b.assign(o, i.at(1) + i.at(-1))), location="Cell")))
+    return b
+
+
+def ico_tridiagonal_solve():  # :139-205 (Thomas algorithm on cells, test "verticalSolver")
+    b = _ico("tridiagonalSolve")
+    a, bb, c, d = (b.field(n, "k", "Cell") for n in "abcd")
+    md, m = b.local("m", 1.0 / (bb.at() - a.at() * c.at(-1)))
+    f0 = b.stage(b.do(Interval("Start", "Start", 0, 0), b.assign(c, c.at() / bb.at()),
+                      b.assign(d, d.at() / bb.at())), location="Cell")
+    f1 = b.stage(b.do(Interval("Start", "End", 1, 0), md, b.assign(c, c.at() * m),
+                      b.assign(d, (d.at() - a.at() * d.at(-1)) * m)), location="Cell")
+    f2 = b.stage(b.do(Interval("Start", "End", 0, -1), b.assign(d, d.at() - c.at() * d.at(1))),
+                 location="Cell")
+    b.stencil(b.multistage("Forward", f0, f1), b.multistage("Backward", f2))
+    return b
+
+
+def ico_sparse_dimension(twice=False):  # :382-457 (un-flagged weights longer than the chain)
+    b = _ico("sparseDimensionTwice" if twice else "sparseDimension")
+    cell = b.field("cell_field", "k", "Cell")
+    edge = b.field("edge_field", "k", "Edge")
+    sp = b.field("sparse_dim", "k", sparse_chain=["Cell", "Edge"])
+    red = lambda: reduce_over(["Cell", "Edge"], edge.nbh * sp.nbh, weights=[1.0, 1.0, 1.0, 1.0])
+    stmts = [b.assign(cell, red())] * (2 if twice else 1)
+    if twice:
+        stmts = [b.assign(cell, red()), b.assign(cell, red())]
+    b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, *stmts), location="Cell")))
+    return b
+
+
+def ico_nested_simple():  # :459-490 (accesses carry no offset flag, as in the reference)
+    b = _ico("nestedSimple")
+    cell, edge, vert = (b.field("cell_field", "k", "Cell"), b.field("edge_field", "k", "Edge"),
+                        b.field("vertex_field", "k", "Vertex"))
+    b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, b.assign(
+        cell, reduce_over(["Cell", "Edge"], reduce_over(["Edge", "Vertex"], vert.at())))),
+        location="Cell")))
+    return b
+
+
+def ico_nested_with_field():  # :492-525
+    b = _ico("nestedWithField")
+    cell, edge, vert = (b.field("cell_field", "k", "Cell"), b.field("edge_field", "k", "Edge"),
+                        b.field("vertex_field", "k", "Vertex"))
+    b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, b.assign(
+        cell, reduce_over(["Cell", "Edge"], edge.at() + reduce_over(["Edge", "Vertex"], vert.at())))),
+        location="Cell")))
+    return b
+
+
+def ico_nested_with_sparse():  # :527-569
+    b = _ico("nestedWithSparse")
+    cell, edge, vert = (b.field("cell_field", "k", "Cell"), b.field("edge_field", "k", "Edge"),
+                        b.field("vertex_field", "k", "Vertex"))
+    ce = b.field("ce_sparse", "k", sparse_chain=["Cell", "Edge"])
+    ev = b.field("ev_sparse", "k", sparse_chain=["Edge", "Vertex"])
+    b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, b.assign(
+        cell, reduce_over(["Cell", "Edge"], edge.at() * ce.at() +
+                          reduce_over(["Edge", "Vertex"], vert.at() * ev.at())))), location="Cell")))
+    return b
+
+
+def ico_sparse_assignment(n):  # :571-779
+    b = _ico("sparseAssignment%d" % n)
+    ecv = ["Edge", "Cell", "Vertex"]
+    if n in (0, 1):
+        vn = b.field("vn", "k", sparse_chain=ecv)
+        u, v = b.field("uVert", "k", "Vertex"), b.field("vVert", "k", "Vertex")
+        if n == 0:
+            nx, ny = b.field("nx", "k", "Vertex"), b.field("ny", "k", "Vertex")
+        else:
+            nx, ny = b.field("nx", "k", sparse_chain=ecv), b.field("ny", "k", sparse_chain=ecv)
+        body = loop_over(ecv, b.assign(vn, u.nbh * nx.nbh + v.nbh * ny.nbh))
+        loc = "Edge"
+    elif n == 2:
+        sp = b.field("sparse", "k", sparse_chain=ecv)
+        e, v = b.field("e", "k", "Edge"), b.field("v", "k", "Vertex")
+        body = loop_over(ecv, b.assign(sp, lit(-4.0) * e.at() + v.nbh))
+        loc = "Edge"
+    elif n == 3:
+        chain = ["Cell", "Edge", "Cell", "Edge", "Cell"]
+        sp = b.field("sparse", "k", sparse_chain=chain)
+        A, B = b.field("A", "k", "Cell"), b.field("B", "k", "Cell")
+        body = loop_over(chain, b.assign(sp, A.nbh - B.at()))
+        loc = "Cell"
+    elif n == 4:
+        sp = b.field("sparse", "k", sparse_chain=["Cell", "Edge"])
+        v = b.field("v", "k", "Vertex")
+        body = loop_over(["Cell", "Edge"], b.assign(sp, reduce_over(["Edge", "Vertex"], v.at())))
+        loc = "Cell"
+    else:
+        sp = b.field("sparse", "k", sparse_chain=["Cell", "Edge"])
+        v, c = b.field("v", "k", "Vertex"), b.field("c", "k", "Cell")
+        body = loop_over(["Cell", "Edge"], b.assign(sp, reduce_over(
+            ["Edge", "Vertex"], v.at() * reduce_over(["Vertex", "Cell"], c.at()))))
+        loc = "Cell"
+    b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, body), location=loc)))
+    return b
+
+
+def ico_horizontal_vertical():  # :781-817 (horizontal-only, sparse horizontal-only and vertical fields)
+    b = _ico("horizontalVertical")
+    hor = b.field("horizontal", "", "Edge")
+    sph = b.field("horizontal_sparse", "", sparse_chain=["Edge", "Cell"])
+    ver = b.field("vertical", "k")
+    full, o1, o2 = (b.field(n, "k", "Edge") for n in ("full", "out1", "out2"))
+    b.stencil(b.multistage("Parallel", b.stage(b.do(
+        FULL, b.assign(o1, full.at() + hor.at() + ver.at()),
+        b.assign(o2, reduce_over(["Edge", "Cell"], sph.at()))), location="Edge")))
+    return b
+
+
+def ico_vertical_indirection():  # :819-845 (the reference spells the name "verticalIndirecion")
+    b = _ico("verticalIndirecion")
+    i, o, kidx = (b.field(n, "k", "Cell") for n in ("in", "out", "kidx"))
+    b.stencil(b.multistage("Parallel", b.stage(
+        b.do(Interval("Start", "End", 0, -1), b.assign(o, i.at(k_from=kidx))), location="Cell")))
+    return b
+
+
+def ico_iteration_space():  # :847-872 (Interval levels are the subdomain magic numbers)
+    b = _ico("iterationSpaceUnstructured")
+    o, i1, i2 = (b.field(n, "k", "Cell") for n in ("out", "in_1", "in_2"))
+    s1 = b.stage(b.do(FULL, b.assign(o, i1.at())), location="Cell", i_range=Interval(3000, 4000, 0, 0))
+    s2 = b.stage(b.do(FULL, b.assign(o, i2.at())), location="Cell", i_range=Interval(2000, 3000, 0, 0))
+    b.stencil(b.multistage("Parallel", s1, s2))
+    return b
+
+
 # ---- reference integration-test stencils (gtclang/test/integration-test/CodeGen/<name>.cpp) --------
 def kcache_fill():
     b = IIRBuilder("kcache_fill")
@@ -408,6 +571,25 @@ ALL = {
     "diamond": unstructured_diamond,
     "diamondWeights": unstructured_diamond_weights,
     "intp": unstructured_intp,
+    "copyCell": ico_copy_cell,
+    "copyEdge": ico_copy_edge,
+    "accumulateEdgeToCell": ico_accumulate_edge_to_cell,
+    "verticalSum": ico_vertical_sum,
+    "tridiagonalSolve": ico_tridiagonal_solve,
+    "sparseDimension": ico_sparse_dimension,
+    "sparseDimensionTwice": lambda: ico_sparse_dimension(True),
+    "nestedSimple": ico_nested_simple,
+    "nestedWithField": ico_nested_with_field,
+    "nestedWithSparse": ico_nested_with_sparse,
+    "sparseAssignment0": lambda: ico_sparse_assignment(0),
+    "sparseAssignment1": lambda: ico_sparse_assignment(1),
+    "sparseAssignment2": lambda: ico_sparse_assignment(2),
+    "sparseAssignment3": lambda: ico_sparse_assignment(3),
+    "sparseAssignment4": lambda: ico_sparse_assignment(4),
+    "sparseAssignment5": lambda: ico_sparse_assignment(5),
+    "horizontalVertical": ico_horizontal_vertical,
+    "verticalIndirecion": ico_vertical_indirection,
+    "iterationSpaceUnstructured": ico_iteration_space,
 }
 
 
