@@ -729,6 +729,7 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
     os_ << "  ::dawn_b200::scratch_field m_" << fname(f) << ";\n";
   os_ << "  ::dawn_b200::timer_b200 m_timer;\n";
   os_ << "  std::vector<b200_splitter_t> m_splitters; // unstructured_domain twin\n";
+  os_ << "  b200_metrics_record* m_record = nullptr;  // the json* the reference hands to setup_<N>\n";
   os_ << "  int m_error = 0;\npublic:\n  long m_launches = 0;\n";
   os_ << "  " << cls << "(const " << cls << "&) = delete;\n";
   os_ << "  " << cls << "(const b200_mesh_t* mesh, int k_size) : m_mesh(*mesh), m_k_size(k_size), m_timer(\""
@@ -751,6 +752,7 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
   }
   os_ << "  }\n";
   os_ << "  int error() const { return m_error; }\n";
+  os_ << "  void set_metrics_record(b200_metrics_record* r) { m_record = r; }\n";
   os_ << "  // dawn::unstructured_domain::set_splitter_index (driver-includes/unstructured_domain.hpp:31-33)\n";
   os_ << "  void set_splitter_index(int loc, int space, int offset, int index) {\n"
          "    for(auto& s : m_splitters)\n"
@@ -908,6 +910,10 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
       if(written.count(inst_.apiFieldIDs[a])) {
         os_ << "    if(int err = b200rt_verify_field(static_cast<const double*>(f[" << a << "].data), ref[w], field_elems("
             << a << "), rel_tol ? rel_tol[w] : 1e-12, abs_tol ? abs_tol[w] : 0.0, iteration, &metrics[w], stream)) return err;\n";
+        // reference: MetricsSerialiser(jsonRecord, metrics, "<stencil>", "<field>").writeJson(iteration)
+        // (CudaIcoCodeGen.cpp:1009-1016)
+        os_ << "    if(m_record) b200rt_metrics_record_add(m_record, \"" << inst_.name << "\", \""
+            << inst_.nameOf(inst_.apiFieldIDs[a]) << "\", &metrics[w]);\n";
         os_ << "    ++w;\n";
       }
   }
@@ -979,6 +985,9 @@ std::string IcoEmitter::generate() {
   os_ << "B200_EXPORT void free_" << n << "(void* handle) { delete static_cast<" << cls << "*>(handle); }\n";
   os_ << "B200_EXPORT long launches_" << n << "(void* handle) { return static_cast<" << cls
       << "*>(handle)->m_launches; }\n";
+  os_ << "B200_EXPORT void set_metrics_record_" << n
+      << "(void* handle, b200_metrics_record* record) { static_cast<" << cls
+      << "*>(handle)->set_metrics_record(record); }\n";
   // reference: set_splitter_index(GlobalGpuTriMesh*, loc, space, offset, index) (cuda_utils.cpp:3-8)
   os_ << "B200_EXPORT void set_splitter_index_" << n
       << "(void* handle, int loc, int space, int offset, int index) { static_cast<" << cls
@@ -1045,6 +1054,8 @@ std::string icoCHeader(const iir::Instantiation& inst) {
   os << " */\n";
   os << "int setup_" << n << "(void** handle, const b200_mesh_t* mesh, int k_size, void* stream);\n";
   os << "void set_splitter_index_" << n << "(void* handle, int loc, int space, int offset, int index);\n";
+  os << "/* verification metrics of later verify_/run_and_verify_ calls are also merged into `record` */\n";
+  os << "void set_metrics_record_" << n << "(void* handle, b200_metrics_record* record);\n";
   os << "int run_" << n << "(void* handle, const b200_field_t* fields, int nfields, void* stream);\n";
   os << "int run_" << n << "_from_c_host(void* handle, double* const* host_fields, int nfields, void* stream);\n";
   os << "int run_" << n << "_from_fort_host(void* handle, double* const* host_fields, int nfields, void* stream);\n";

@@ -8,8 +8,15 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
+
+// stencil -> per-iteration {field -> metrics} (std::map: keys sorted like nlohmann::json objects)
+struct b200_metrics_record {
+  std::map<std::string, std::vector<std::map<std::string, b200_verification_metrics>>> stencils;
+  std::string text;
+};
 
 namespace {
 thread_local std::string g_err;
@@ -347,6 +354,90 @@ static int reshape_impl(const double* in, double* out, int k_size, int n_elem, i
   CK(cudaGetLastError());
   return 0;
 }
+int b200rt_metrics_record_create(b200_metrics_record** rec) {
+  if(!rec)
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_metrics_record_create: null argument");
+  *rec = new b200_metrics_record();
+  return 0;
+}
+int b200rt_metrics_record_add(b200_metrics_record* rec, const char* stencil, const char* field,
+                              const b200_verification_metrics* m) {
+  if(!rec || !stencil || !field || !m || m->iteration < 0)
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_metrics_record_add: bad argument");
+  auto& iterations = rec->stencils[stencil];
+  // to_json.cpp:19-24: a new entry is appended when the iteration does not exist yet, otherwise the
+  // field is inserted into the existing entry unless it is already there
+  if((int)iterations.size() < m->iteration + 1)
+    iterations.emplace_back();
+  auto& entry = (int)iterations.size() > m->iteration ? iterations[m->iteration] : iterations.back();
+  entry.emplace(field, *m);
+  return 0;
+}
+const char* b200rt_metrics_record_json(b200_metrics_record* rec) {
+  if(!rec)
+    return "null";
+  auto num = [](double v) {
+    char buf[40];
+    if(v != v || v - v != 0)
+      return std::string("null"); // nlohmann dumps non-finite numbers as null
+    std::snprintf(buf, sizeof buf, "%.17g", v);
+    std::string s(buf);
+    if(s.find_first_of(".eEn") == std::string::npos)
+      s += ".0";
+    return s;
+  };
+  auto quote = [](const std::string& s) {
+    std::string o = "\"";
+    for(char c : s) {
+      if(c == '"' || c == '\\')
+        o += '\\';
+      o += c;
+    }
+    return o + "\"";
+  };
+  std::string& o = rec->text;
+  if(rec->stencils.empty()) {
+    o = "null";
+    return o.c_str();
+  }
+  o = "{";
+  bool firstS = true;
+  for(auto const& st : rec->stencils) {
+    o += (firstS ? "" : ",") + quote(st.first) + ":[";
+    firstS = false;
+    for(size_t it = 0; it < st.second.size(); ++it) {
+      o += it ? ",{" : "{";
+      bool firstF = true;
+      for(auto const& f : st.second[it]) {
+        auto const& m = f.second;
+        o += (firstF ? "" : ",") + quote(f.first) + ":{\"field_is_valid\":" +
+             (m.is_valid ? "true" : "false") + ",\"max_absolute_error\":" + num(m.max_abs_err) +
+             ",\"max_relative_error\":" + num(m.max_rel_err) + ",\"min_absolute_error\":" +
+             num(m.min_abs_err) + ",\"min_relative_error\":" + num(m.min_rel_err) + "}";
+        firstF = false;
+      }
+      o += "}";
+    }
+    o += "]";
+  }
+  o += "}";
+  return o.c_str();
+}
+int b200rt_metrics_record_write(b200_metrics_record* rec, const char* path) {
+  if(!rec || !path)
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_metrics_record_write: null argument");
+  FILE* f = std::fopen(path, "w");
+  if(!f)
+    return b200rt_set_error(B200_ERR_RUNTIME, "b200rt_metrics_record_write: cannot open file");
+  std::fputs(b200rt_metrics_record_json(rec), f);
+  std::fclose(f);
+  return 0;
+}
+int b200rt_metrics_record_destroy(b200_metrics_record* rec) {
+  delete rec;
+  return 0;
+}
+
 int b200rt_reshape(const double* in, double* out, int k, int n, int sp, void* s) {
   return reshape_impl(in, out, k, n, sp, false, s);
 }

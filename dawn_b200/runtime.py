@@ -36,7 +36,8 @@ SYMBOLS = [
     "b200rt_upload_nbh_table", "b200rt_nccl_unique_id", "b200rt_comm_init_rank",
     "b200rt_comm_destroy", "b200rt_halo_plan_create", "b200rt_halo_plan_create2",
     "b200rt_halo_exchange",
-    "b200rt_halo_plan_destroy",
+    "b200rt_halo_plan_destroy", "b200rt_metrics_record_create", "b200rt_metrics_record_add",
+    "b200rt_metrics_record_json", "b200rt_metrics_record_write", "b200rt_metrics_record_destroy",
 ]
 
 
@@ -90,3 +91,42 @@ def verify_field(dsl_ptr, ref_ptr, n, rel_tol=1e-12, abs_tol=0.0, iteration=0, s
     check(lib().b200rt_verify_field(dsl_ptr, ref_ptr, n, rel_tol, abs_tol, iteration,
                                     ctypes.byref(m), stream))
     return m
+
+
+class MetricsRecord:
+    """Verification record with the JSON shape of the reference's MetricsSerialiser
+    (driver-includes/to_json.cpp): {"<stencil>": [{"<field>": {...}} per iteration]}."""
+
+    def __init__(self):
+        self.handle = ctypes.c_void_p()
+        check(lib().b200rt_metrics_record_create(ctypes.byref(self.handle)))
+
+    def add(self, stencil, field, metrics):
+        fn = lib().b200rt_metrics_record_add
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p,
+                       ctypes.POINTER(VerificationMetrics)]
+        check(fn(self.handle, stencil.encode(), field.encode(), ctypes.byref(metrics)))
+
+    def json(self) -> str:
+        fn = lib().b200rt_metrics_record_json
+        fn.argtypes = [ctypes.c_void_p]
+        fn.restype = ctypes.c_char_p
+        return fn(self.handle).decode()
+
+    def write(self, path):
+        fn = lib().b200rt_metrics_record_write
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        check(fn(self.handle, str(path).encode()))
+
+    def close(self):
+        if self.handle:
+            fn = lib().b200rt_metrics_record_destroy
+            fn.argtypes = [ctypes.c_void_p]
+            fn(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

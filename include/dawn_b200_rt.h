@@ -94,6 +94,23 @@ typedef struct b200_verification_metrics {
 int b200rt_verify_field(const double* dsl, const double* ref, size_t n, double rel_tol,
                         double abs_tol, int iteration, b200_verification_metrics* out, void* stream);
 
+/* Verification record: twin of the reference's MetricsSerialiser (driver-includes/to_json.{hpp,cpp}),
+ * which merges per-field metrics into a nlohmann::json object passed to setup_<N>.  Here the record is
+ * an opaque handle; its JSON text has the same shape:
+ *   { "<stencil>": [ { "<field>": { "field_is_valid": b, "max_absolute_error": x, "max_relative_error": x,
+ *                                   "min_absolute_error": x, "min_relative_error": x }, ... }, ... ] }
+ * one array entry per iteration (metrics->iteration); a field already present in an iteration entry is
+ * kept (nlohmann's object insert does not overwrite), exactly like to_json.cpp:9-33. */
+typedef struct b200_metrics_record b200_metrics_record;
+int b200rt_metrics_record_create(b200_metrics_record** rec);
+int b200rt_metrics_record_add(b200_metrics_record* rec, const char* stencil, const char* field,
+                              const b200_verification_metrics* metrics);
+/* JSON text (keys sorted, like nlohmann's default object type); owned by the record, valid until the
+ * next call on it. */
+const char* b200rt_metrics_record_json(b200_metrics_record* rec);
+int b200rt_metrics_record_write(b200_metrics_record* rec, const char* path);
+int b200rt_metrics_record_destroy(b200_metrics_record* rec);
+
 /* Layout transposition element-major [elem][k] <-> level-major [k][elem] on the device
  * (cuda_utils.hpp:81-125 does this on one host thread).  sparse: [elem][sparse][k] <-> [k][sparse][elem]. */
 int b200rt_reshape(const double* in, double* out, int k_size, int num_elements, int sparse_size,

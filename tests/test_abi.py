@@ -55,3 +55,35 @@ def test_options_struct_matches_header():
     fields = re.findall(r"\bint\s+([a-z_0-9, ]+);", body)
     names = [x.strip() for f in fields for x in f.split(",")]
     assert names == [f[0] for f in codegen._Options._fields_]
+
+
+def test_metrics_record_has_the_reference_json_shape():
+    """driver-includes/to_json.cpp:9-53: {"stencil": [{"field": {5 metrics}} per iteration]}, a field
+    already recorded for an iteration is kept, a new iteration is appended."""
+    import json
+    from dawn_b200 import runtime as rt
+    rec = rt.MetricsRecord()
+    assert rec.json() == "null"
+
+    def m(it, valid, x):
+        return rt.VerificationMetrics(it, int(valid), x, x / 2, x * 2, x / 4, 0)
+    rec.add("nabla2", "div_vec", m(0, True, 1e-15))
+    rec.add("nabla2", "rot_vec", m(0, True, 2e-15))
+    rec.add("nabla2", "div_vec", m(0, False, 7.0))      # already there: kept
+    rec.add("nabla2", "div_vec", m(1, False, 0.5))      # next iteration: appended
+    rec.add("diffusion", "out_field", m(0, True, 0.0))
+    d = json.loads(rec.json())
+    assert list(d) == ["diffusion", "nabla2"]            # keys sorted like nlohmann::json objects
+    assert len(d["nabla2"]) == 2 and set(d["nabla2"][0]) == {"div_vec", "rot_vec"}
+    assert d["nabla2"][0]["div_vec"] == {
+        "field_is_valid": True, "max_absolute_error": 2e-15, "max_relative_error": 1e-15,
+        "min_absolute_error": 2.5e-16, "min_relative_error": 5e-16}
+    assert d["nabla2"][1] == {"div_vec": {
+        "field_is_valid": False, "max_absolute_error": 1.0, "max_relative_error": 0.5,
+        "min_absolute_error": 0.125, "min_relative_error": 0.25}}
+    assert d["diffusion"][0]["out_field"]["max_relative_error"] == 0.0
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".json") as f:
+        rec.write(f.name)
+        assert json.load(open(f.name)) == d
+    rec.close()

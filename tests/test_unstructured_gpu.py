@@ -199,6 +199,24 @@ def test_from_host_entry_points_and_verify():
     for n, mtr in zip(written, metrics):
         if n in ("div_vec", "rot_vec"):
             assert mtr.is_valid == 1 and mtr.max_abs_err == 0.0 and mtr.iteration == 3, n
+    # the json record the reference passes to setup_<N> (to_json.cpp): one entry per iteration
+    import json
+    rec = rt.MetricsRecord()
+    setrec = mod.lib.set_metrics_record_ICON_laplacian_stencil
+    setrec.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    setrec.restype = None
+    setrec(st.handle, rec.handle)
+    for it in (0, 1):
+        rt.check(fn(st.handle, descs, len(tens), vpp(*[r.data_ptr() for r in refs]), None, None, it,
+                    metrics, None))
+    d = json.loads(rec.json())
+    assert list(d) == ["ICON_laplacian_stencil"] and len(d["ICON_laplacian_stencil"]) == 2
+    for entry in d["ICON_laplacian_stencil"]:
+        assert set(entry) == set(written)
+        assert entry["div_vec"] == {"field_is_valid": True, "max_absolute_error": 0.0,
+                                    "max_relative_error": 0.0, "min_absolute_error": 0.0,
+                                    "min_relative_error": 0.0}
+    setrec(st.handle, None)
 
 
 TOYLIB = ["copyCell", "copyEdge", "accumulateEdgeToCell", "verticalSum", "tridiagonalSolve",
