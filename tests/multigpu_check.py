@@ -50,6 +50,7 @@ def main():
     rt.check(rt.lib().b200rt_comm_init_rank(ctypes.byref(comm), world, idbuf, rank))
     widths = slabs.exchange_widths(mod.fields, st.written_fields())
     stream = torch.cuda.current_stream().cuda_stream
+    print("rank", rank, "communicator ready", flush=True)
     for name, (wm, wp) in widths.items():
         s = stor[name]
         plan = ctypes.c_void_p()
@@ -66,6 +67,69 @@ def main():
     dist.all_reduce(res, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("MULTIGPU_OK" if int(res) == 1 else "MULTIGPU_MISMATCH", "ranks", world)
+    # ---- the same step (NCCL halo exchange + kernel) recorded once as a CUDA graph and replayed ------
+    graph_ok = True
+    import threading
+    # a replayed NCCL send without its peer never returns: leave the process instead of hanging the box
+    watchdog = threading.Timer(90.0, lambda: (print("rank", rank, "graph step timed out", flush=True),
+                                              os._exit(3)))
+    watchdog.daemon = True
+    watchdog.start()
+    try:
+        plans = []
+        step = dawn_b200.TimeStep()
+        for name, (wm, wp) in widths.items():
+            s = stor[name]
+            plan = ctypes.c_void_p()
+            rt.check(rt.lib().b200rt_halo_plan_create(ctypes.byref(plan), comm, rank, world, ni, njl, K,
+                                                      s.stride_j, s.stride_k, HALO, wm, wp))
+            plans.append(plan)
+            step.exchange(plan, s.buf.data_ptr() + 8 * s.lead)
+        step.run(st, *[stor[fd["name"]] for fd in mod.fields])
+        print("rank", rank, "capturing the step", flush=True)
+        captured = True
+        try:
+            step.capture()
+        except Exception as e:  # noqa: BLE001
+            print("rank", rank, "graph capture failed:", e, flush=True)
+            captured = False
+        # every rank must have a graph before anyone replays (a replayed ncclSend without its peer
+        # would wait forever)
+        flag = torch.tensor([1 if captured else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        print("rank", rank, "captured:", captured, flush=True)
+        if int(flag) != 1:
+            raise RuntimeError("graph capture failed on some rank")
+        for rep in range(3):
+            stor["in"].from_numpy(loc["in"])          # halo rows are NaN again
+            stor["out"].from_numpy(loc["out"])        # -1 everywhere, as in the oracle's input
+            torch.cuda.synchronize()
+            if rep == 0:
+                step.eager()                          # the same sequence, launch by launch
+            else:
+                step.replay()
+            torch.cuda.synchronize()
+            got = stor["out"].to_numpy()
+            a = got[:K, HALO:-HALO, :]
+            b = want[:K, HALO + sl.j0:HALO + sl.j0 + sl.nj_local, :]
+            same = np.array_equal(a, b, equal_nan=True)
+            if not same:
+                bad = ~((a == b) | (np.isnan(a) & np.isnan(b)))
+                print("rank", rank, "rep", rep, "mismatches", int(bad.sum()), "nan", int(np.isnan(a).sum()),
+                      "untouched", int((a == -5.0).sum()), "rows", np.unique(np.nonzero(bad)[1])[:8],
+                      flush=True)
+            graph_ok = graph_ok and same
+        step.close()                                  # graphs holding NCCL nodes go before the communicator
+        for plan in plans:
+            rt.check(rt.lib().b200rt_halo_plan_destroy(plan))
+    except Exception as e:  # noqa: BLE001
+        print("rank", rank, "graph step failed:", e, flush=True)
+        graph_ok = False
+    watchdog.cancel()
+    res3 = torch.tensor([1 if graph_ok else 0], device="cuda")
+    dist.all_reduce(res3, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTIGPU_GRAPH_OK" if int(res3) == 1 else "MULTIGPU_GRAPH_MISMATCH", "ranks", world)
     ok_icon = icon_check(rank, world, comm, stream)
     res2 = torch.tensor([1 if ok_icon else 0], device="cuda")
     dist.all_reduce(res2, op=dist.ReduceOp.MIN)
@@ -73,7 +137,7 @@ def main():
         print("MULTIGPU_ICON_OK" if int(res2) == 1 else "MULTIGPU_ICON_MISMATCH", "ranks", world)
     rt.lib().b200rt_comm_destroy(comm)
     dist.destroy_process_group()
-    sys.exit(0 if int(res) == 1 and int(res2) == 1 else 1)
+    sys.exit(0 if int(res) == 1 and int(res2) == 1 and int(res3) == 1 else 1)
 
 
 def icon_check(rank, world, comm, stream):
