@@ -632,7 +632,12 @@ void IcoEmitter::emitKernel(const Group& g) {
   const bool backward = g.ms->loopOrder == LoopOrder::Backward;
   os_ << "// kernel " << g.name << ": " << g.stages.size() << " fused stage(s) on " << locName(g.loc)
       << ", " << block_ << " threads, " << (sequential ? std::string("sequential k sweep") : std::to_string(lpt_) + " level(s)/thread") << "\n";
-  os_ << "__global__ void __launch_bounds__(" << block_ << ")\n" << g.name << "(";
+  // --max-blocks-sm (CodeGen/Options.inc): resident blocks per SM the register allocator must allow.
+  // Default: full occupancy (2048 threads per SM, i.e. <= 32 registers per thread) - these kernels are
+  // bound by the latency of their gathers, and ICON nabla2 on B200 measured 78 % of the HBM peak at 64
+  // resident warps against 72 % at the 48 warps ptxas' own 40-register allocation allowed.
+  const int minBlocks = opt_.MaxBlocksPerSM > 0 ? opt_.MaxBlocksPerSM : std::max(1, 2048 / block_);
+  os_ << "__global__ void __launch_bounds__(" << block_ << ", " << minBlocks << ")\n" << g.name << "(";
   if(g.usesGlobals)
     os_ << "const globals g, ";
   os_ << "const int k_size, const int elem_lo, const int elem_hi, const int n_cells, const int n_edges, "
@@ -648,6 +653,9 @@ void IcoEmitter::emitKernel(const Group& g) {
     os_ << ",\n    " << (ro ? "const " : "") << "::dawn::float_type* __restrict__ " << fname(f) << "_p";
   }
   os_ << ") {\n";
+  // grid: element blocks fastest (x), level blocks in y.  (Level blocks fastest, so that the blocks
+  // sharing an element range find their neighbour-table rows in L2, measured slower on B200: ICON
+  // nabla2 71 % against 78 % of the HBM peak - too many concurrent DRAM streams.)
   os_ << "  const int pidx = elem_lo + blockIdx.x * " << block_ << " + threadIdx.x; // elements [elem_lo, elem_hi)\n";
   os_ << "  if(pidx >= elem_hi)\n    return;\n";
   os_ << "  (void)n_cells; (void)n_edges; (void)n_vertices;\n";
