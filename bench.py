@@ -539,8 +539,10 @@ def run_icon(args):
                    "mesh_build_s": t_mesh},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None,
-                     "kernel": "3 generated kernels/step (vertices, cells, 5 fused edge stages); "
-                               "%.0f algorithmic bytes/step" % bytes_run, "peak_source": peak_src},
+                     "kernel": "%d generated kernel launches/step (vertex and cell stages co-scheduled in "
+                               "one launch, 5 fused edge stages in the other); %.0f algorithmic "
+                               "bytes/step" % ((st.launches() - l0) // args.steps, bytes_run),
+                     "peak_source": peak_src},
         "gpu_launches": launches, "clocks": clocks,
     }
     if rank == 0:

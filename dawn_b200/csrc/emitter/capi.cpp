@@ -30,6 +30,7 @@ b200::codegen::Options convert(const dawn_b200_options* o) {
   r.ColumnRing = o->column_ring, r.RingLevels = o->ring_levels;
   r.ColsPerThread = o->cols_per_thread;
   r.SharedTemporaries = o->shared_temporaries;
+  r.CoSchedule = o->co_schedule;
   return r;
 }
 } // namespace
@@ -52,6 +53,7 @@ void dawn_b200_default_options(dawn_b200_options* o) {
   o->column_cache = 0;
   o->column_ring = 1;
   o->shared_temporaries = 0;
+  o->co_schedule = 1;
 }
 
 int dawn_b200_parse_backend(const char* s) {

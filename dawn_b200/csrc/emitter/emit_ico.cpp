@@ -160,6 +160,11 @@ struct Group {
   // magic numbers of driver-includes/unstructured_domain.hpp:23, offsets index into the splitters)
   bool hasSpace = false;
   Interval space;
+  // co-scheduling: two independent parallel groups that gather the same field share one launch whose
+  // blocks alternate between them in proportion to their sizes, so that what one fetches the other
+  // finds in L2 (ICON nabla2: `vec` is gathered by the vertex and by the cell stage)
+  int coWith = -1;      // index of the group launched together with this one
+  bool coMember = false; // launched by an earlier group
 };
 
 class IcoEmitter {
@@ -202,7 +207,10 @@ private:
   }
 
   std::vector<Group> plan(const Stencil& st);
-  void emitKernel(const Group& g);
+  void emitKernel(const Group& g, const Group* partner);
+  void emitRole(const Group& g, const std::string& blockExpr, const std::string& lo,
+                const std::string& hi);
+  void planCoScheduling(std::vector<Group>& groups) const;
   void emitHost(const std::vector<Group>& groups);
   void collect(Group& g);
 };
@@ -627,38 +635,55 @@ public:
   }
 };
 
-void IcoEmitter::emitKernel(const Group& g) {
+void IcoEmitter::planCoScheduling(std::vector<Group>& groups) const {
+  if(!opt_.CoSchedule)
+    return;
+  auto disjoint = [](const std::set<int>& a, const std::set<int>& b) {
+    for(int x : a)
+      if(b.count(x))
+        return false;
+    return true;
+  };
+  for(size_t i = 0; i + 1 < groups.size(); ++i) {
+    Group& a = groups[i];
+    Group& b = groups[i + 1];
+    if(a.coMember || a.coWith >= 0 || a.ms != b.ms || a.ms->loopOrder != LoopOrder::Parallel ||
+       a.hasSpace || b.hasSpace || a.usesGlobals != b.usesGlobals)
+      continue;
+    // independent: neither touches what the other writes
+    if(!disjoint(a.fieldsWritten, b.fieldsRead) || !disjoint(a.fieldsWritten, b.fieldsWritten) ||
+       !disjoint(b.fieldsWritten, a.fieldsRead))
+      continue;
+    // worth it: both gather a common field through a chain
+    std::set<int> ga, gb;
+    for(auto const* st : a.stages)
+      forEachAccess(*st, [&](const Expr& e, int nest, bool) {
+        if(nest > 0 && (e.hasOffset || fieldLoc(e.accessID) != a.loc))
+          ga.insert(e.accessID);
+      });
+    for(auto const* st : b.stages)
+      forEachAccess(*st, [&](const Expr& e, int nest, bool) {
+        if(nest > 0 && (e.hasOffset || fieldLoc(e.accessID) != b.loc))
+          gb.insert(e.accessID);
+      });
+    if(disjoint(ga, gb))
+      continue;
+    a.coWith = static_cast<int>(i + 1);
+    b.coMember = true;
+  }
+}
+
+// One role of a launch: the code of a group for the element block `blockExpr` of [lo, hi).
+void IcoEmitter::emitRole(const Group& g, const std::string& blockExpr, const std::string& lo,
+                          const std::string& hi) {
   const bool sequential = g.ms->loopOrder != LoopOrder::Parallel;
   const bool backward = g.ms->loopOrder == LoopOrder::Backward;
-  os_ << "// kernel " << g.name << ": " << g.stages.size() << " fused stage(s) on " << locName(g.loc)
-      << ", " << block_ << " threads, " << (sequential ? std::string("sequential k sweep") : std::to_string(lpt_) + " level(s)/thread") << "\n";
-  // --max-blocks-sm (CodeGen/Options.inc): resident blocks per SM the register allocator must allow.
-  // Default: full occupancy (2048 threads per SM, i.e. <= 32 registers per thread) - these kernels are
-  // bound by the latency of their gathers, and ICON nabla2 on B200 measured 78 % of the HBM peak at 64
-  // resident warps against 72 % at the 48 warps ptxas' own 40-register allocation allowed.
-  const int minBlocks = opt_.MaxBlocksPerSM > 0 ? opt_.MaxBlocksPerSM : std::max(1, 2048 / block_);
-  os_ << "__global__ void __launch_bounds__(" << block_ << ", " << minBlocks << ")\n" << g.name << "(";
-  if(g.usesGlobals)
-    os_ << "const globals g, ";
-  os_ << "const int k_size, const int elem_lo, const int elem_hi, const int n_cells, const int n_edges, "
-         "const int n_vertices";
-  for(auto const& ch : g.chains)
-    os_ << ",\n    const int* __restrict__ tbl_" << chainTag(ch.first, ch.second);
-  std::set<int> args = g.fieldsRead;
-  args.insert(g.fieldsWritten.begin(), g.fieldsWritten.end());
-  for(int f : args) {
-    if(registerOnly_.count(f))
-      continue;
-    bool ro = !g.fieldsWritten.count(f);
-    os_ << ",\n    " << (ro ? "const " : "") << "::dawn::float_type* __restrict__ " << fname(f) << "_p";
-  }
-  os_ << ") {\n";
   // grid: element blocks fastest (x), level blocks in y.  (Level blocks fastest, so that the blocks
   // sharing an element range find their neighbour-table rows in L2, measured slower on B200: ICON
   // nabla2 71 % against 78 % of the HBM peak - too many concurrent DRAM streams.)
-  os_ << "  const int pidx = elem_lo + blockIdx.x * " << block_ << " + threadIdx.x; // elements [elem_lo, elem_hi)\n";
-  os_ << "  if(pidx >= elem_hi)\n    return;\n";
-  os_ << "  (void)n_cells; (void)n_edges; (void)n_vertices;\n";
+  os_ << "  const int pidx = " << lo << " + (int)(" << blockExpr << ") * " << block_
+      << " + threadIdx.x; // elements [" << lo << ", " << hi << ")\n";
+  os_ << "  if(pidx >= " << hi << ")\n    return;\n";
   // neighbour indices, once per thread
   for(auto const& ch : g.chains) {
     int size = icoChainSize(ch.first, ch.second);
@@ -670,14 +695,14 @@ void IcoEmitter::emitKernel(const Group& g) {
           << IcoBody::stride(ch.first.front()) << " * " << n << "]);\n";
   }
   // k range: hull of the DoMethod intervals of the group
-  int lo = Interval::End * 2, hi = -Interval::End;
+  int lo_k = Interval::End * 2, hi_k = -Interval::End;
   for(auto const* st : g.stages)
     for(auto const& dm : st->doMethods) {
-      lo = std::min(lo, dm.interval.lowerBound());
-      hi = std::max(hi, dm.interval.upperBound());
+      lo_k = std::min(lo_k, dm.interval.lowerBound());
+      hi_k = std::max(hi_k, dm.interval.upperBound());
     }
   os_ << "  const int kmin = 0, kmax = k_size - 1;\n";
-  os_ << "  int kb = " << analysis::boundExpr(lo) << ", ke = " << analysis::boundExpr(hi) << ";\n";
+  os_ << "  int kb = " << analysis::boundExpr(lo_k) << ", ke = " << analysis::boundExpr(hi_k) << ";\n";
   os_ << "  kb = kb < 0 ? 0 : kb; ke = ke > kmax ? kmax : ke;\n";
   if(sequential) {
     if(backward)
@@ -698,7 +723,7 @@ void IcoEmitter::emitKernel(const Group& g) {
   for(auto const* st : g.stages) {
     os_ << "    // stage " << st->id << "\n";
     for(auto const& dm : st->doMethods) {
-      bool guard = dm.interval.lowerBound() != lo || dm.interval.upperBound() != hi;
+      bool guard = dm.interval.lowerBound() != lo_k || dm.interval.upperBound() != hi_k;
       std::vector<std::string> lines;
       for(auto const& s : dm.stmts)
         body.stmt(s, lines, 0, guard);
@@ -713,7 +738,65 @@ void IcoEmitter::emitKernel(const Group& g) {
       }
     }
   }
-  os_ << "  }\n}\n\n";
+  os_ << "  }\n";
+}
+
+void IcoEmitter::emitKernel(const Group& g, const Group* partner) {
+  const bool sequential = g.ms->loopOrder != LoopOrder::Parallel;
+  os_ << "// kernel " << g.name << ": " << g.stages.size() << " fused stage(s) on " << locName(g.loc);
+  if(partner)
+    os_ << " co-scheduled with " << partner->stages.size() << " stage(s) on " << locName(partner->loc);
+  os_ << ", " << block_ << " threads, "
+      << (sequential ? std::string("sequential k sweep") : std::to_string(lpt_) + " level(s)/thread") << "\n";
+  // --max-blocks-sm (CodeGen/Options.inc): resident blocks per SM the register allocator must allow.
+  // Default: full occupancy (2048 threads per SM, i.e. <= 32 registers per thread) - these kernels are
+  // bound by the latency of their gathers, and ICON nabla2 on B200 measured 78 % of the HBM peak at 64
+  // resident warps against 72 % at the 48 warps ptxas' own 40-register allocation allowed.
+  const int minBlocks = opt_.MaxBlocksPerSM > 0 ? opt_.MaxBlocksPerSM : std::max(1, 2048 / block_);
+  os_ << "__global__ void __launch_bounds__(" << block_ << ", " << minBlocks << ")\n" << g.name << "(";
+  if(g.usesGlobals)
+    os_ << "const globals g, ";
+  os_ << "const int k_size, const int elem_lo, const int elem_hi, const int n_cells, const int n_edges, "
+         "const int n_vertices";
+  if(partner)
+    os_ << ", const int elem_lo1, const int elem_hi1, const unsigned nb0, const unsigned nb1";
+  std::set<std::string> tags;
+  std::vector<const Group*> roles{&g};
+  if(partner)
+    roles.push_back(partner);
+  for(auto const* r : roles)
+    for(auto const& ch : r->chains)
+      if(tags.insert(chainTag(ch.first, ch.second)).second)
+        os_ << ",\n    const int* __restrict__ tbl_" << chainTag(ch.first, ch.second);
+  std::set<int> args, written;
+  for(auto const* r : roles) {
+    args.insert(r->fieldsRead.begin(), r->fieldsRead.end());
+    args.insert(r->fieldsWritten.begin(), r->fieldsWritten.end());
+    written.insert(r->fieldsWritten.begin(), r->fieldsWritten.end());
+  }
+  for(int f : args) {
+    if(registerOnly_.count(f))
+      continue;
+    bool ro = !written.count(f);
+    os_ << ",\n    " << (ro ? "const " : "") << "::dawn::float_type* __restrict__ " << fname(f) << "_p";
+  }
+  os_ << ") {\n";
+  os_ << "  (void)n_cells; (void)n_edges; (void)n_vertices;\n";
+  if(!partner) {
+    emitRole(g, "blockIdx.x", "elem_lo", "elem_hi");
+  } else {
+    // blocks alternate between the two roles in proportion nb0 : nb1 (role 0 owns the blocks where
+    // floor((b+1) nb0 / tot) steps), so both sweep their element ranges at the same relative pace
+    os_ << "  const unsigned long long tot = (unsigned long long)nb0 + nb1;\n";
+    os_ << "  const unsigned r0 = (unsigned)(((unsigned long long)blockIdx.x * nb0) / tot);\n";
+    os_ << "  const unsigned r0n = (unsigned)(((unsigned long long)(blockIdx.x + 1) * nb0) / tot);\n";
+    os_ << "  if(r0n > r0) {\n";
+    emitRole(g, "r0", "elem_lo", "elem_hi");
+    os_ << "  } else {\n";
+    emitRole(*partner, "blockIdx.x - r0", "elem_lo1", "elem_hi1");
+    os_ << "  }\n";
+  }
+  os_ << "}\n\n";
 }
 
 void IcoEmitter::emitHost(const std::vector<Group>& groups) {
@@ -809,6 +892,9 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
     os_ << "    ::dawn::float_type* " << fname(f) << "_p = m_" << fname(f) << ".data;\n";
   }
   for(auto const& g : groups) {
+    if(g.coMember)
+      continue;
+    const Group* partner = g.coWith >= 0 ? &groups[g.coWith] : nullptr;
     bool sequential = g.ms->loopOrder != LoopOrder::Parallel;
     std::string n = IcoBody::stride(g.loc);
     os_ << "    {\n";
@@ -825,18 +911,39 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
           << ": splitter index outside the mesh\");\n";
     } else
       os_ << "      const int elem_lo = 0, elem_hi = " << n << ";\n";
-    os_ << "      if(elem_hi > elem_lo) {\n";
-    os_ << "      dim3 grid((elem_hi - elem_lo + " << block_ - 1 << ") / " << block_ << ", "
-        << (sequential ? std::string("1") : "(k_size + " + std::to_string(lpt_ - 1) + ") / " + std::to_string(lpt_))
-        << ");\n";
+    const std::string levelBlocks =
+        sequential ? std::string("1")
+                   : "(k_size + " + std::to_string(lpt_ - 1) + ") / " + std::to_string(lpt_);
+    if(partner) {
+      os_ << "      const int elem_lo1 = 0, elem_hi1 = " << IcoBody::stride(partner->loc) << ";\n";
+      os_ << "      const unsigned nb0 = (unsigned)((elem_hi - elem_lo + " << block_ - 1 << ") / " << block_
+          << "), nb1 = (unsigned)((elem_hi1 - elem_lo1 + " << block_ - 1 << ") / " << block_ << ");\n";
+      os_ << "      if(nb0 + nb1 > 0) {\n";
+      os_ << "      dim3 grid(nb0 + nb1, " << levelBlocks << ");\n";
+    } else {
+      os_ << "      if(elem_hi > elem_lo) {\n";
+      os_ << "      dim3 grid((elem_hi - elem_lo + " << block_ - 1 << ") / " << block_ << ", " << levelBlocks
+          << ");\n";
+    }
     os_ << "      " << g.name << "<<<grid, " << block_ << ", 0, stream>>>(";
     if(g.usesGlobals)
       os_ << "m_globals, ";
     os_ << "k_size, elem_lo, elem_hi, n_cells, n_edges, n_vertices";
-    for(auto const& ch : g.chains)
-      os_ << ", m_tbl_" << chainTag(ch.first, ch.second);
-    std::set<int> args = g.fieldsRead;
-    args.insert(g.fieldsWritten.begin(), g.fieldsWritten.end());
+    if(partner)
+      os_ << ", elem_lo1, elem_hi1, nb0, nb1";
+    std::set<std::string> tags;
+    std::vector<const Group*> roles{&g};
+    if(partner)
+      roles.push_back(partner);
+    for(auto const* r : roles)
+      for(auto const& ch : r->chains)
+        if(tags.insert(chainTag(ch.first, ch.second)).second)
+          os_ << ", m_tbl_" << chainTag(ch.first, ch.second);
+    std::set<int> args;
+    for(auto const* r : roles) {
+      args.insert(r->fieldsRead.begin(), r->fieldsRead.end());
+      args.insert(r->fieldsWritten.begin(), r->fieldsWritten.end());
+    }
     for(int f : args)
       if(!registerOnly_.count(f))
         os_ << ", " << fname(f) << "_p";
@@ -955,8 +1062,12 @@ std::string IcoEmitter::generate() {
     os_ << "  globals()" << init << " {}\n};\n\n";
   }
   auto groups = plan(inst_.stencils[0]);
-  for(auto const& g : groups)
-    emitKernel(g);
+  planCoScheduling(groups);
+  for(auto const& g : groups) {
+    if(g.coMember)
+      continue;
+    emitKernel(g, g.coWith >= 0 ? &groups[g.coWith] : nullptr);
+  }
   emitHost(groups);
   os_ << "} // namespace b200ico\n} // namespace dawn_generated\n\n";
 
@@ -1039,7 +1150,12 @@ std::string IcoEmitter::generate() {
           firstT = false;
         }
   }
-  os_ << "], \\\"kernels\\\": " << groups.size() << ", \\\"globals\\\": [";
+  {
+    size_t launches = 0;
+    for(auto const& g : groups)
+      launches += g.coMember ? 0 : 1;
+    os_ << "], \\\"kernels\\\": " << launches << ", \\\"globals\\\": [";
+  }
   for(size_t g = 0; g < inst_.globals.size(); ++g)
     os_ << (g ? ", " : "") << "\\\"" << inst_.globals[g].first << "\\\"";
   os_ << "]}\";\n}\n} // extern \"C\"\n";

@@ -57,6 +57,8 @@ typedef struct dawn_b200_options {
   int cols_per_thread;   /* i columns per thread of tile kernels without redundant halo stages (1|2) */
   int shared_temporaries; /* default 0; 1: TMA tile kernels keep widely reused temporaries in a shared-memory
                              IJ-cache (the reference's cache(IJ, local), CudaCodeGen ij_caches) */
+  int co_schedule;        /* default 1: unstructured groups that are independent and gather a common field are
+                             launched as one kernel whose blocks alternate between them (L2 reuse) */
 } dawn_b200_options;
 
 /* Fills `opts` with the defaults above. */
