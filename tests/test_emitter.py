@@ -153,12 +153,16 @@ def test_ico_chain_sizes_known_answers():
 
 
 def test_icon_laplacian_plan_fuses_edge_stages():
-    code = _code("ICON_laplacian_stencil", backend="b200-ico")
+    code = _code("ICON_laplacian_stencil", backend="b200-ico", co_schedule=0)
     kernels = re.findall(r"^// kernel (\S+): (\d+) fused stage\(s\) on (\w+)", code, flags=re.M)
     assert [(k[1], k[2]) for k in kernels] == [("1", "vertices"), ("1", "cells"), ("5", "edges")]
+    # default: the independent vertex and cell groups (both gather `vec`) share one launch
+    code = _code("ICON_laplacian_stencil", backend="b200-ico")
+    heads = re.findall(r"^// kernel .*$", code, flags=re.M)
+    assert len(heads) == 2 and "on vertices co-scheduled with 1 stage(s) on cells" in heads[0]
     assert "__tmp_nab_60_p" not in code and "scratch_field" not in code  # temporaries stay in registers
     assert "setup_ICON_laplacian_stencil(void** handle, const b200_mesh_t* mesh, int k_size" in code
-    unfused = _code("ICON_laplacian_stencil", backend="b200-ico", fuse_columns=0)
+    unfused = _code("ICON_laplacian_stencil", backend="b200-ico", fuse_columns=0, co_schedule=0)
     assert len(re.findall(r"^// kernel ", unfused, flags=re.M)) == 7
     assert "scratch_field m___tmp_nab_60" in unfused
     with pytest.raises(codegen.CodeGenError, match="unstructured"):
