@@ -538,7 +538,7 @@ def run_icon(args):
                    "l2": "inputs larger than L2 (%.1f GB per step), no flush" % (bytes_run / 1e9),
                    "mesh_build_s": t_mesh},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None,
+                     "frac": achieved / peak, "traffic": icon_traffic(E),
                      "kernel": "%d generated kernel launches/step (vertex and cell stages co-scheduled in "
                                "one launch, 5 fused edge stages in the other); %.0f algorithmic "
                                "bytes/step" % ((st.launches() - l0) // args.steps, bytes_run),
@@ -552,6 +552,18 @@ def run_icon(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def icon_traffic(num_edges):
+    """DRAM bytes per step (sum over the kernels of one step) from the committed ncu capture, only when
+    it was taken on this mesh size."""
+    tp = os.path.join(ROOT, "profiles", "traffic_icon_nabla2.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            d = json.load(f)
+        if d.get("num_edges") == num_edges:
+            return d.get("dram_bytes_per_step")
+    return None
 
 
 def main():
