@@ -114,6 +114,9 @@ VARIANTS = {
     "kcache_fill_backward": [dict(column_ring=0)], "intervals02": [dict(column_ring=0)],
     "intervals03": [dict(column_ring=0)], "kparallel_solver": [dict(column_ring=0)],
     "asymmetric_stencil": [dict(use_tma=0)], "coriolis_stencil": [dict(use_tma=0)],
+    **{n: [dict(use_tma=0, inline_temporaries=0)] for n in (
+        "intervals_stencil", "intervals01", "kcache_fill_kparallel", "kcache_epflush", "lap",
+        "hori_diff_stencil_02", "hd_smagorinsky_stencil", "p_grad_c")},
     "tridiagonal_solve": [dict(fuse_columns=0), dict(column_ring=0), dict(column_ring=0, column_cache=1, prefetch_k=3),
                           dict(ring_levels=2, tma_stages=2), dict(block_size_i=32, block_size_j=2)],
 }

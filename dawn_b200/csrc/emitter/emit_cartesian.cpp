@@ -197,6 +197,8 @@ private:
   void emitGlobalsStruct();
   void emitKernel(const Stencil& st, const KernelPlan& kp);
   void emitWrapperClass(const std::vector<std::vector<KernelPlan>>& plans);
+  void emitControlFlow(const std::vector<std::vector<KernelPlan>>& plans,
+                       const std::function<void(size_t sidx, const std::string& pad)>& call);
   void emitCAbi();
 
   std::vector<int> stencilArgs(const Stencil& st, const std::vector<KernelPlan>& kps) const;
@@ -1193,6 +1195,8 @@ public:
       break;
     }    case Stmt::Loop:
       throw std::runtime_error("b200: loops over neighbour chains require the b200-ico backend");
+    case Stmt::StencilCall:
+      throw std::runtime_error("b200: stencil call inside a stage body");
     }
   }
 };
@@ -2254,13 +2258,13 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
   for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a)
     os_ << (a ? ", " : "") << storageType(inst_.apiFieldIDs[a]) << " " << fname(inst_.apiFieldIDs[a]);
   os_ << ") {\n";
-  for(size_t sidx = 0; sidx < inst_.stencils.size(); ++sidx) {
+  emitControlFlow(plans, [&](size_t sidx, const std::string& pad) {
     auto sargs = stencilArgs(inst_.stencils[sidx], plans[sidx]);
-    os_ << "    m_stencil_" << inst_.stencils[sidx].id << ".run(";
+    os_ << pad << "m_stencil_" << inst_.stencils[sidx].id << ".run(";
     for(size_t a = 0; a < sargs.size(); ++a)
       os_ << (a ? ", " : "") << (inst_.isAllocated(sargs[a]) ? "m_" : "") << fname(sargs[a]);
     os_ << ");\n";
-  }
+  });
   if(opt_.RunWithSync && !inst_.apiFieldIDs.empty()) {
     os_ << "    sync_storages(";
     for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a)
@@ -2272,21 +2276,21 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
   os_ << "  int run_raw(const b200_field_t* f, void* stream) { return run_raw_rows(f, stream, 0, "
          "1 << 30); }\n";
   os_ << "  int run_raw_rows(const b200_field_t* f, void* stream, int j_begin, int j_end) {\n";
-  for(size_t sidx = 0; sidx < inst_.stencils.size(); ++sidx) {
+  emitControlFlow(plans, [&](size_t sidx, const std::string& pad) {
     auto sargs = stencilArgs(inst_.stencils[sidx], plans[sidx]);
-    os_ << "    {\n      b200_field_t a[" << std::max<size_t>(1, sargs.size()) << "];\n";
+    os_ << pad << "{\n" << pad << "  b200_field_t a[" << std::max<size_t>(1, sargs.size()) << "];\n";
     for(size_t a = 0; a < sargs.size(); ++a) {
       if(inst_.isAllocated(sargs[a]))
-        os_ << "      a[" << a << "] = m_" << fname(sargs[a]) << ".device_descriptor();\n";
+        os_ << pad << "  a[" << a << "] = m_" << fname(sargs[a]) << ".device_descriptor();\n";
       else {
         size_t pos = std::find(inst_.apiFieldIDs.begin(), inst_.apiFieldIDs.end(), sargs[a]) -
                      inst_.apiFieldIDs.begin();
-        os_ << "      a[" << a << "] = f[" << pos << "];\n";
+        os_ << pad << "  a[" << a << "] = f[" << pos << "];\n";
       }
     }
-    os_ << "      if(int err = m_stencil_" << inst_.stencils[sidx].id
-        << ".launch_rows(a, stream, j_begin, j_end)) return err;\n    }\n";
-  }
+    os_ << pad << "  if(int err = m_stencil_" << inst_.stencils[sidx].id
+        << ".launch_rows(a, stream, j_begin, j_end)) return err;\n" << pad << "}\n";
+  });
   os_ << "    return 0;\n  }\n\n";
   os_ << "  long launches() const { return 0";
   for(auto const& st : inst_.stencils)
@@ -2306,6 +2310,83 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
     os_ << "    res += m_stencil_" << st.id << ".get_time();\n";
   os_ << "    return res;\n  }\n";
   os_ << "};\n";
+}
+
+// The stencil description's control flow around the stencil calls (reference: ASTStencilDesc +
+// generateStencilWrapperRun, CudaCodeGen.cpp:412-452): if-statements and local variables over
+// globals decide at run time which stencils execute.  Without recorded control flow every stencil
+// runs in order.
+void CartesianEmitter::emitControlFlow(
+    const std::vector<std::vector<KernelPlan>>& plans,
+    const std::function<void(size_t sidx, const std::string& pad)>& call) {
+  (void)plans;
+  auto indexOf = [&](int stencilID) -> size_t {
+    for(size_t s = 0; s < inst_.stencils.size(); ++s)
+      if(inst_.stencils[s].id == stencilID)
+        return s;
+    throw std::runtime_error("b200: control flow calls unknown stencil " + std::to_string(stencilID));
+  };
+  bool plain = true;
+  for(auto const& s : inst_.controlFlow)
+    plain = plain && s->kind == Stmt::StencilCall;
+  if(inst_.controlFlow.empty() || (plain && inst_.controlFlow.size() == inst_.stencils.size())) {
+    if(inst_.controlFlow.empty())
+      for(size_t s = 0; s < inst_.stencils.size(); ++s)
+        call(s, "    ");
+    else
+      for(auto const& s : inst_.controlFlow)
+        call(indexOf(s->accessID), "    ");
+    return;
+  }
+  std::function<std::string(const ExprPtr&)> ex = [&](const ExprPtr& e) -> std::string {
+    switch(e->kind) {
+    case Expr::Literal: return BodyEmitter::literal(*e);
+    case Expr::Var: return e->isExternal ? "m_globals." + cIdent(e->name) : cIdent(e->name);
+    case Expr::Unary: return "(" + e->op + ex(e->kids[0]) + ")";
+    case Expr::Binary: return "(" + ex(e->kids[0]) + " " + e->op + " " + ex(e->kids[1]) + ")";
+    case Expr::Ternary:
+      return "(" + ex(e->kids[0]) + " ? " + ex(e->kids[1]) + " : " + ex(e->kids[2]) + ")";
+    case Expr::FunCall: {
+      std::string s = BodyEmitter::mathName(e->name) + "(";
+      for(size_t n = 0; n < e->kids.size(); ++n)
+        s += (n ? ", " : "") + ex(e->kids[n]);
+      return s + ")";
+    }
+    case Expr::Assign: return ex(e->kids[0]) + " " + e->op + " " + ex(e->kids[1]);
+    default: throw std::runtime_error("b200: field access in the control flow of a stencil description");
+    }
+  };
+  std::function<void(const StmtPtr&, const std::string&)> st = [&](const StmtPtr& s,
+                                                                  const std::string& pad) {
+    switch(s->kind) {
+    case Stmt::StencilCall: call(indexOf(s->accessID), pad); break;
+    case Stmt::ExprStmt: os_ << pad << ex(s->expr) << ";\n"; break;
+    case Stmt::VarDecl:
+      os_ << pad << cType(s->typeId) << " " << cIdent(s->name)
+          << (s->expr ? " = " + ex(s->expr) : std::string()) << ";\n";
+      break;
+    case Stmt::If:
+      os_ << pad << "if(" << ex(s->expr) << ") {\n";
+      for(auto const& c : s->body)
+        st(c, pad + "  ");
+      if(s->hasElse) {
+        os_ << pad << "} else {\n";
+        for(auto const& c : s->orelse)
+          st(c, pad + "  ");
+      }
+      os_ << pad << "}\n";
+      break;
+    case Stmt::Block:
+      os_ << pad << "{\n";
+      for(auto const& c : s->body)
+        st(c, pad + "  ");
+      os_ << pad << "}\n";
+      break;
+    case Stmt::Loop: throw std::runtime_error("b200: neighbour loop in the control flow");
+    }
+  };
+  for(auto const& s : inst_.controlFlow)
+    st(s, "    ");
 }
 
 void CartesianEmitter::emitCAbi() {

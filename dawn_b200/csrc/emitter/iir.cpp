@@ -174,6 +174,16 @@ StmtPtr parseStmt(const Value& node) {
       s->hasElse = true;
       parseBlockInto(v.at("else_part"), s->orelse);
     }
+  } else if(kind == "stencil_call_decl_stmt") {
+    s->kind = Stmt::StencilCall;
+    std::string callee = v.has("stencil_call") ? v.at("stencil_call").getString("callee") : "";
+    size_t us = callee.rfind('_');
+    if(callee.compare(0, 11, "__code_gen_") != 0 || us == std::string::npos)
+      throw std::runtime_error("IIR: unexpected stencil call '" + callee + "'");
+    s->accessID = std::stoi(callee.substr(us + 1));
+  } else if(kind == "boundary_condition_decl_stmt") {
+    throw std::runtime_error("IIR: boundary condition declarations are not supported by the b200 "
+                             "backends (the reference's CUDA backend does not generate them either)");
   } else if(kind == "loop_stmt") {
     s->kind = Stmt::Loop;
     const Value* space = nullptr;
@@ -336,6 +346,9 @@ Instantiation parseInstantiation(const std::string& data) {
         }
       inst.stencils.push_back(std::move(st));
     }
+  if(const Value* cf = ir.find("controlFlowStatements"))
+    for(auto const& s : cf->arr)
+      inst.controlFlow.push_back(parseStmt(s));
   if(inst.stencils.empty())
     throw std::runtime_error("IIR: instantiation '" + inst.name + "' contains no stencil");
   return inst;

@@ -87,12 +87,13 @@ struct Expr {
   // Reduce
   std::vector<LocationType> chain;
   bool includeCenter = false;
+  // StencilCall (control flow of the stencil description only): accessID = stencil ID
 };
 
 struct Stmt;
 using StmtPtr = std::shared_ptr<Stmt>;
 struct Stmt {
-  enum Kind { ExprStmt, VarDecl, If, Block, Loop };
+  enum Kind { ExprStmt, VarDecl, If, Block, Loop, StencilCall };
   Kind kind = ExprStmt;
   ExprPtr expr;               // ExprStmt; If: condition; VarDecl: initialiser (may be null)
   std::string name;           // VarDecl
@@ -183,6 +184,9 @@ struct Instantiation {
   std::vector<int> globalVariableIDs;
   std::vector<std::pair<std::string, GlobalValue>> globals; // declaration order
   std::vector<Stencil> stencils;
+  // statements of the stencil description around the stencil calls (IIR.controlFlowStatements); empty
+  // or a plain list of calls = run every stencil in order
+  std::vector<StmtPtr> controlFlow;
 
   bool isTemporary(int id) const {
     for(int t : temporaryFieldIDs)

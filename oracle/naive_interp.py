@@ -251,7 +251,7 @@ class CartesianRun:
         self.jMin, self.jMax = jm, nj - jp - 1
         self.kMin, self.kMax = km, nk - kp - 1
         self.f = dict(fields)
-        for st in self.ir["stencils"]:
+        for st in self._stencil_sequence():
             exts = stage_extents(st)
             # temporaries: full 3-D storages (CXXNaiveCodeGen.cpp:318-345), +1 safety level
             for aid in self.tmp_ids:
@@ -265,6 +265,65 @@ class CartesianRun:
                 sidx += len(stages)
                 self._run_ms(ms, stages, s_exts)
         return self.f
+
+    def _stencil_sequence(self):
+        """Stencils in the order the wrapper's run() executes them: the controlFlowStatements of the
+        IIR (stencil calls, possibly inside if-statements over globals and local variables of the
+        stencil description; reference: CodeGen::generateStencilWrapperRun + ASTStencilDesc,
+        CXXNaiveCodeGen.cpp:232-259), or all stencils in order when there are none."""
+        by_id = {st["stencilID"]: st for st in self.ir["stencils"]}
+        flow = self.ir.get("controlFlowStatements", [])
+        if not flow:
+            return list(self.ir["stencils"])
+        seq = []
+        local = {}
+
+        def ev(node):
+            kd, v = _kind(node)
+            if kd == "literal_access_expr":
+                t = v.get("type", {}).get("type_id", "Float")
+                return int(v["value"]) if t == "Integer" else (v["value"] in ("true", "1") if t == "Boolean"
+                                                               else float(v["value"]))
+            if kd == "var_access_expr":
+                return self.globals[v["name"]] if v.get("is_external", False) else local[v["name"]]
+            if kd == "binary_operator":
+                return _BIN[v["op"]](ev(v["left"]), ev(v["right"]))
+            if kd == "unary_operator":
+                a = ev(v["operand"])
+                return -a if v["op"] == "-" else ((not a) if v["op"] == "!" else a)
+            if kd == "ternary_operator":
+                return ev(v["left"]) if ev(v["cond"]) else ev(v["right"])
+            raise NotImplementedError("control flow expression " + kd)
+
+        def ex(node):
+            kd, v = _kind(node)
+            if kd == "stencil_call_decl_stmt":
+                seq.append(by_id[int(v["stencil_call"]["callee"].rsplit("_", 1)[1])])
+            elif kd == "block_stmt":
+                for s in v.get("statements", []):
+                    ex(s)
+            elif kd == "if_stmt":
+                _, cv = _kind(v["cond_part"])
+                if ev(cv["expr"]):
+                    ex(v["then_part"])
+                elif v.get("else_part"):
+                    ex(v["else_part"])
+            elif kd == "var_decl_stmt":
+                init = v.get("init_list", [])
+                local[v["name"]] = ev(init[0]) if init else 0.0
+            elif kd == "expr_stmt":
+                ek, e2 = _kind(v["expr"])
+                assert ek == "assignment_expr", ek
+                _, lv = _kind(e2["left"])
+                rhs = ev(e2["right"])
+                op = e2.get("op", "=")
+                local[lv["name"]] = rhs if op == "=" else _BIN[op[0]](local[lv["name"]], rhs)
+            else:
+                raise NotImplementedError("control flow statement " + kd)
+
+        for s in flow:
+            ex(s)
+        return seq
 
     def _run_ms(self, ms, stages, s_exts):
         backward = ms.get("loopOrder", "Forward") == "Backward"

@@ -223,6 +223,12 @@ class If:
 
 
 @dataclass(eq=False)
+class Call:
+    """stencil_call_decl_stmt of the n-th stencil() of the builder (control flow of the description)."""
+    index: int
+
+
+@dataclass(eq=False)
 class Loop:
     """loop_stmt over a neighbour chain (statements.proto LoopStmt + LoopDescriptorChain)."""
     chain: List[str]
@@ -395,6 +401,13 @@ class IIRBuilder:
 
     def stencil(self, *multistages):
         self.stencils.append({"ms": list(multistages)})
+        return Call(len(self.stencils) - 1)
+
+    def control_flow(self, *stmts):
+        """Statements of the stencil description around the stencil calls (if / local variables over
+        globals), as gtclang records them in controlFlowStatements.  Without it the stencils run in
+        order, unconditionally."""
+        self.flow = list(stmts)
 
     # -- serialization ----------------------------------------------------------------------------
     def _lit_id(self, value):
@@ -518,6 +531,24 @@ class IIRBuilder:
             _add(up_writes, k, _copy_ext(v))
         return out
 
+    def _flow_stmt(self, s) -> dict:
+        if isinstance(s, Call):
+            return self.stencils[s.index]["call_json"]
+        if isinstance(s, If):
+            d = {"cond_part": {"expr_stmt": {"expr": self._expr(s.cond, {}), "loc": LOC, "data": {},
+                                             "ID": self._node()}},
+                 "then_part": {"block_stmt": {"statements": [self._flow_stmt(x) for x in s.then],
+                                              "loc": LOC, "data": {}, "ID": self._node()}}}
+            if s.otherwise is not None:
+                d["else_part"] = {"block_stmt": {"statements": [self._flow_stmt(x) for x in s.otherwise],
+                                                 "loc": LOC, "data": {}, "ID": self._node()}}
+            d.update({"loc": LOC, "data": {}, "ID": self._node()})
+            return {"if_stmt": d}
+        if isinstance(s, (VarDecl, Assign)):
+            out = self._stmt(s, {}, {})
+            return out
+        raise TypeError(type(s))
+
     def _block(self, stmts, up_reads, up_writes) -> dict:
         reads: Dict[int, _Ext] = {}
         writes: Dict[int, _Ext] = {}
@@ -566,6 +597,9 @@ class IIRBuilder:
                 "loc": LOC, "data": {}, "ID": self._node()}}
             id_to_call[str(sid)] = call
             control_flow.append(call)
+            st["call_json"] = call
+        if getattr(self, "flow", None):
+            control_flow = [self._flow_stmt(s) for s in self.flow]
 
         meta = {
             "accessIDToName": {str(k): v for k, v in self.names.items()},

@@ -546,6 +546,153 @@ def kparallel_solver():
     return b
 
 
+# ---- the rest of gtclang/test/integration-test/CodeGen/CMakeLists.txt:169-198 ------------------------
+def intervals_stencil():  # intervals_stencil.cpp:17-42 (k_flat = k_start + 4)
+    b = IIRBuilder("intervals_stencil")
+    i, o = b.field("in"), b.field("out")
+    st = b.stage(b.do(Interval("Start", 4, 0, 0), b.assign(o, i() + 1)),
+                 b.do(Interval(4, 4, 1, 1), b.assign(o, i() + 2)),
+                 b.do(Interval(4, "End", 2, 0), b.assign(o, i() + 3)))
+    b.stencil(b.multistage("Parallel", st))
+    return b
+
+
+def intervals01():  # intervals01.cpp: levels k_start and k_flat+1 and k_end are never written
+    b = IIRBuilder("intervals01")
+    i, o = b.field("in"), b.field("out")
+    st = b.stage(b.do(Interval("Start", 4, 1, 0), b.assign(o, i() + 1)),
+                 b.do(Interval(4, "End", 2, -1), b.assign(o, i() + 3)))
+    b.stencil(b.multistage("Parallel", st))
+    return b
+
+
+def kcache_fill_kparallel():  # kcache_fill_kparallel.cpp: overlapping intervals, reads k-1 and k+1
+    b = IIRBuilder("kcache_fill_kparallel")
+    i, o = b.field("in"), b.field("out")
+    st = b.stage(b.do(Interval("Start", "Start", 0, 1), b.assign(o, i() + i(0, 0, 1))),
+                 b.do(Interval("Start", "End", 1, -1), b.assign(o, i() + i(0, 0, -1) + i(0, 0, 1))),
+                 b.do(Interval("End", "End", -1, 0), b.assign(o, i() + i(0, 0, -1))))
+    b.stencil(b.multistage("Parallel", st))
+    return b
+
+
+def kcache_epflush():  # kcache_epflush.cpp: temporaries with vertical offsets across two multistages
+    b = IIRBuilder("kcache_epflush")
+    i, o = b.field("in"), b.field("out")
+    bb, tmp = b.tmp("b"), b.tmp("tmp")
+    fwd = b.stage(b.do(Interval("Start", "Start", 0, 0), b.assign(tmp, i())),
+                  b.do(Interval("Start", "End", 1, 0), b.assign(tmp, i() * 2), b.assign(bb, tmp(0, 0, -1))))
+    bwd = b.stage(b.do(Interval("End", "End", -2, 0), b.assign(o, 2.2)),
+                  b.do(Interval("End", "End", -3, -3),
+                       b.assign(o, tmp(0, 0, 3) + tmp(0, 0, 2) + tmp(0, 0, 1))),
+                  b.do(Interval("Start", "End", 0, -4), b.assign(tmp, bb()), b.assign(o, tmp(0, 0, 1))))
+    b.stencil(b.multistage("Forward", fwd, caches={tmp.access_id: k_cache("CP_EPFlush")}),
+              b.multistage("Backward", bwd))
+    return b
+
+
+def lap_stencil():  # lap.cpp: temporary read at +-1 of a stage reading +-2
+    b = IIRBuilder("lap")
+    i, o = b.field("in"), b.field("out")
+    tmp = b.tmp("tmp")
+    s1 = b.stage(b.do(FULL, b.assign(tmp, i(0, -2) + i(0, 2) + i(-2, 0) + i(2, 0))))
+    s2 = b.stage(b.do(FULL, b.assign(o, tmp(0, -1) + tmp(0, 1) + tmp(-1, 0) + tmp(1, 0))))
+    b.stencil(b.multistage("Parallel", s1, s2))
+    return b
+
+
+def hori_diff_02():  # hori_diff_stencil_02.cpp: laplacian of a laplacian
+    b = IIRBuilder("hori_diff_stencil_02")
+    u, o = b.field("u"), b.field("out")
+    lap = b.tmp("lap")
+
+    def laplacian(f):
+        return f(1, 0) + f(-1, 0) + f(0, 1) + f(0, -1) - 4.0 * f()
+    s1 = b.stage(b.do(FULL, b.assign(lap, laplacian(u))))
+    s2 = b.stage(b.do(FULL, b.assign(o, laplacian(lap))))
+    b.stencil(b.multistage("Parallel", s1, s2))
+    return b
+
+
+def hd_smagorinsky():  # hd_smagorinsky.cpp:47-100 (stencil functions inlined, two stages)
+    from iir_builder import call
+    b = IIRBuilder("hd_smagorinsky_stencil")
+    u_out, v_out, u_in, v_in, hdmaskvel = (b.field(n) for n in ("u_out", "v_out", "u_in", "v_in", "hdmaskvel"))
+    crlavo, crlavu, crlato, crlatu, acrlat0 = (b.field(n, "j") for n in
+                                               ("crlavo", "crlavu", "crlato", "crlatu", "acrlat0"))
+    eddlon, eddlat, tau_smag, weight_smag = (b.field(n) for n in ("eddlon", "eddlat", "tau_smag", "weight_smag"))
+    T_sqr_s, S_sqr_uv = b.tmp("T_sqr_s"), b.tmp("S_sqr_uv")
+
+    def delta(di, dj, f):
+        return f(di, dj) - f()
+
+    def avg(di, dj, f):
+        return 0.5 * (f(di, dj) + f())
+
+    def laplacian(f, lo, lu):
+        return f(1, 0) + f(-1, 0) - 2.0 * f() + lo() * delta(0, 1, f) + lu() * delta(0, -1, f)
+    d1, fdx = b.local("frac_1_dx", acrlat0() * eddlon(), "Double", True)
+    d2, fdy = b.local("frac_1_dy", eddlat() / lit(6371.229e3), "Double", True)
+    d3, T_s = b.local("T_s", delta(0, -1, v_in) * fdy - delta(-1, 0, u_in) * fdx, "Double", True)
+    d4, S_uv = b.local("S_uv", delta(0, 1, u_in) * fdy + delta(1, 0, v_in) * fdx, "Double", True)
+    s1 = b.stage(b.do(FULL, d1, d2, d3, b.assign(T_sqr_s, T_s * T_s), d4, b.assign(S_sqr_uv, S_uv * S_uv)))
+    d5, hdw = b.local("hdweight", weight_smag() * hdmaskvel(), "Double", True)
+    d6, smag_u = b.local("smag_u", tau_smag() * call("gridtools::dawn::math::sqrt",
+                                                     avg(1, 0, T_sqr_s) + avg(0, -1, S_sqr_uv)) - hdw, "Double")
+    d7, smag_v = b.local("smag_v", tau_smag() * call("gridtools::dawn::math::sqrt",
+                                                     avg(0, 1, T_sqr_s) + avg(-1, 0, S_sqr_uv)) - hdw, "Double")
+    clamp = lambda x: call("gridtools::dawn::math::min", lit(0.5), call("gridtools::dawn::math::max", lit(0.0), x))
+    d8, lapu = b.local("lapu", laplacian(u_in, crlato, crlatu), "Double", True)
+    d9, lapv = b.local("lapv", laplacian(v_in, crlavo, crlavu), "Double", True)
+    s2 = b.stage(b.do(FULL, d5, d6, b.assign(smag_u, clamp(smag_u)), d7, b.assign(smag_v, clamp(smag_v)),
+                      d8, d9, b.assign(u_out, u_in() + smag_u * lapu), b.assign(v_out, v_in() + smag_v * lapv)))
+    b.stencil(b.multistage("Parallel", s1, s2))
+    return b
+
+
+def p_grad_c():  # p_grad_c.cpp: conditional ij temporary, mixed horizontal + vertical offsets, +=
+    b = IIRBuilder("p_grad_c")
+    dt2 = b.global_var("dt2", "Double", 0.5)
+    hyd = b.global_var("hydrostatic", "Boolean", 1)
+    delpc = b.field("delpc", "ij")
+    pkc, gz, uc, vc, rdxc, rdyc = (b.field(n) for n in ("pkc", "gz", "uc", "vc", "rdxc", "rdyc"))
+    wk = b.tmp("wk")
+    s1 = b.stage(b.do(Interval("Start", "End", 0, -1),
+                      b.if_(hyd, [b.assign(wk, pkc(0, 0, 1) - pkc())], [b.assign(wk, delpc())])))
+    s2 = b.stage(b.do(
+        Interval("Start", "End", 0, -1),
+        b.assign(uc, dt2 * rdxc() / (wk(-1, 0) + wk()) *
+                 ((gz(-1, 0, 1) - gz()) * (pkc(0, 0, 1) - pkc(-1, 0)) +
+                  (gz(-1, 0) - gz(0, 0, 1)) * (pkc(-1, 0, 1) - pkc())), op="+="),
+        b.assign(vc, dt2 * rdyc() / (wk(0, -1) + wk()) *
+                 ((gz(0, -1, 1) - gz()) * (pkc(0, 0, 1) - pkc(0, -1)) +
+                  (gz(0, -1) - gz(0, 0, 1)) * (pkc(0, -1, 1) - pkc())), op="+=")))
+    b.stencil(b.multistage("Parallel", s1, s2))
+    return b
+
+
+def stencil_desc_ast(n):  # stencil_desc_ast.cpp: control flow of the stencil description
+    from iir_builder import If, VarDecl
+    b = IIRBuilder("stencil_desc_ast_%02d" % n)
+    vr = b.global_var("var_runtime", "Integer", 1)
+    vc = b.global_var("var_compiletime", "Integer", 2)
+    i, o = b.field("in"), b.field("out")
+    if n == 3:    # nested ifs around one stencil
+        c0 = b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, b.assign(o, i() + vr + vc)))))
+        b.control_flow(If(vr.eq(1), [If(vc.eq(2), [c0])]))
+    elif n == 4:  # two stencils, the second one level deeper
+        c0 = b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, b.assign(o, 0.0)))))
+        c1 = b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, b.assign(o, 2 + i(), op="+=")))))
+        b.control_flow(If(vc.eq(2), [If(vc.ne(1), [c0, If(vc.ne(1), [c1])])]))
+    else:         # 7: local variables of the description feed the condition
+        c0 = b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, b.assign(o, 2 * i())))))
+        d1, some = b.local("some_var", 5.0, "Double")
+        d2, other = b.local("some_other_var", vc, "Double")
+        b.control_flow(If(vc.eq(2), [d1, d2, b.assign(some, 1.0, op="+="),
+                                     If((vc + some + other).eq(10), [c0])]))
+    return b
+
+
 ALL = {
     "hori_diff_type2_stencil": hori_diff_type2,
     "hori_diff_stencil_01": hori_diff_01,
@@ -571,6 +718,17 @@ ALL = {
     "diamond": unstructured_diamond,
     "diamondWeights": unstructured_diamond_weights,
     "intp": unstructured_intp,
+    "intervals_stencil": intervals_stencil,
+    "intervals01": intervals01,
+    "kcache_fill_kparallel": kcache_fill_kparallel,
+    "kcache_epflush": kcache_epflush,
+    "lap": lap_stencil,
+    "hori_diff_stencil_02": hori_diff_02,
+    "hd_smagorinsky_stencil": hd_smagorinsky,
+    "p_grad_c": p_grad_c,
+    "stencil_desc_ast_03": lambda: stencil_desc_ast(3),
+    "stencil_desc_ast_04": lambda: stencil_desc_ast(4),
+    "stencil_desc_ast_07": lambda: stencil_desc_ast(7),
     "copyCell": ico_copy_cell,
     "copyEdge": ico_copy_edge,
     "accumulateEdgeToCell": ico_accumulate_edge_to_cell,
