@@ -217,6 +217,47 @@ private:
 // ------------------------------------------------------------------------------------------------
 // Temporary planning (Blackwell replacement of PassSetCaches' IJ-cache decision)
 // ------------------------------------------------------------------------------------------------
+// Local variables of a DoMethod that are initialised once and never assigned again (`const double
+// frac_1_dx = acrlat0 * eddlon;`) are pure names for their initialiser: a temporary defined through
+// them can still be recomputed at its uses once they are substituted (hd_smagorinsky's T_sqr_s).
+// Integer locals are left alone (their initialiser is truncated on assignment).
+static std::map<int, ExprPtr> pureLocals(const DoMethod& dm) {
+  std::map<int, ExprPtr> defs;
+  std::set<int> assigned;
+  for(auto const& s : dm.stmts)
+    if(s->kind == Stmt::VarDecl && s->expr && s->typeId != "Integer" && s->typeId != "Boolean")
+      defs[s->accessID] = s->expr;
+  analysis::visitStmts(dm.stmts, [&](const Expr& e, bool w) {
+    if(e.kind == Expr::Var && w)
+      assigned.insert(e.accessID);
+  });
+  for(int a : assigned)
+    defs.erase(a);
+  return defs;
+}
+
+static ExprPtr substituteLocals(const ExprPtr& e, const std::map<int, ExprPtr>& defs, int depth = 0) {
+  if(!e)
+    return e;
+  if(e->kind == Expr::Var && !e->isExternal) {
+    auto it = defs.find(e->accessID);
+    if(it != defs.end() && depth < 32)
+      return substituteLocals(it->second, defs, depth + 1);
+    return e;
+  }
+  bool changed = false;
+  std::vector<ExprPtr> kids;
+  for(auto const& k : e->kids) {
+    kids.push_back(substituteLocals(k, defs, depth));
+    changed = changed || kids.back() != k;
+  }
+  if(!changed)
+    return e;
+  auto c = std::make_shared<Expr>(*e);
+  c->kids = kids;
+  return c;
+}
+
 void CartesianEmitter::planTemporaries(const Stencil& st) {
   for(int tid : inst_.temporaryFieldIDs) {
     // where is it accessed?
@@ -256,7 +297,7 @@ void CartesianEmitter::planTemporaries(const Stencil& st) {
                  s->expr->kids[0]->kind != Expr::Field)
                 ok = false;
               else
-                def = s->expr->kids[1];
+                def = substituteLocals(s->expr->kids[1], pureLocals(dm));
             }
         }
         if(it->second.read && it->second.hasReadExtent &&
@@ -333,14 +374,18 @@ void CartesianEmitter::planTemporaries(const Stencil& st) {
     for(auto const& stage : ms.stages) {
       bool all = true;
       int n = 0;
-      for(auto const& dm : stage.doMethods)
+      for(auto const& dm : stage.doMethods) {
+        auto pure = pureLocals(dm);
         for(auto const& s : dm.stmts) {
           ++n;
           bool isDef = s->kind == Stmt::ExprStmt && s->expr->kind == Expr::Assign &&
                        s->expr->kids[0]->kind == Expr::Field &&
                        inlined_.count(s->expr->kids[0]->accessID);
-          all = all && isDef;
+          // declarations of pure locals only serve the definitions that absorbed them
+          bool isPureDecl = s->kind == Stmt::VarDecl && pure.count(s->accessID);
+          all = all && (isDef || isPureDecl);
         }
+      }
       if(all && n > 0)
         droppedStages_.insert(stage.id);
     }

@@ -13,6 +13,12 @@ import dawn_b200  # noqa: E402
 import bench  # noqa: E402
 
 HALO = 3
+# further stencils of the reference's test list, with their algorithmic bytes per point
+bench.STENCIL.update({"hd_smagorinsky": "hd_smagorinsky_stencil", "hori_diff_02": "hori_diff_stencil_02",
+                      "lap": "lap"})
+bench.SHAPE.update({"hd_smagorinsky": (1024, 1024, 80), "hori_diff_02": (1024, 1024, 80),
+                    "lap": (1024, 1024, 80)})
+bench.BYTES_PER_POINT.update({"hd_smagorinsky": 72, "hori_diff_02": 16, "lap": 16})
 
 
 def main():
