@@ -31,7 +31,10 @@
 
 #include <algorithm>
 #include <functional>
+#include <cstdio>
+#include <cstdlib>
 #include <sstream>
+#include <tuple>
 #include <stdexcept>
 
 namespace b200 {
@@ -187,6 +190,7 @@ private:
   void collectUse(KernelPlan& kp) const;
   bool planTma(KernelPlan& kp) const;
   void planSharedTemporaries(KernelPlan& kp) const;
+  int microTileFootprint(const KernelPlan& kp, int RI, int RJ) const;
   bool planColumnCache(KernelPlan& kp) const;
   bool planColumnRing(KernelPlan& kp) const;
   std::map<int, int> ringDepths(const MultiStage& ms) const;
@@ -755,6 +759,57 @@ void CartesianEmitter::planSharedTemporaries(KernelPlan& kp) const {
   kp.cacheElems = offset;
 }
 
+// Number of distinct double values a thread holds for an RI x RJ micro-tile: field values at distinct
+// (field, di, dj, dk) after expanding inlined temporaries, plus the distinct evaluations of those
+// temporaries.  Two registers each; the planner keeps the micro-tile under the point where ptxas'
+// allocation (measured: hori_diff_type2 2x3 -> 124, hd_smagorinsky 2x2 -> 185 registers) starts to
+// cost residency.
+int CartesianEmitter::microTileFootprint(const KernelPlan& kp, int RI, int RJ) const {
+  std::set<std::tuple<int, int, int, int>> values;
+  std::set<std::tuple<int, int, int>> temps;
+  std::function<void(const ExprPtr&, int, int)> walk = [&](const ExprPtr& e, int si, int sj) {
+    if(!e)
+      return;
+    if(e->kind == Expr::Field) {
+      MaskClass m = maskOf(e->accessID);
+      int di = m.i ? e->di + si : 0, dj = m.j ? e->dj + sj : 0;
+      auto inl = inlined_.find(e->accessID);
+      if(inl != inlined_.end()) {
+        if(temps.insert({e->accessID, di, dj}).second)
+          walk(inl->second.expr, di, dj);
+      } else
+        values.insert({e->accessID, di, dj, m.k ? e->dk : 0});
+      return;
+    }
+    for(auto const& k : e->kids)
+      walk(k, si, sj);
+  };
+  std::function<void(const StmtPtr&, int, int)> ws = [&](const StmtPtr& s, int c, int r) {
+    if(s->kind == Stmt::ExprStmt && s->expr->kind == Expr::Assign) {
+      const Expr& l = *s->expr->kids[0];
+      if(!(l.kind == Expr::Field && inlined_.count(l.accessID))) {
+        walk(s->expr->kids[1], c, r);
+        if(s->expr->op != "=")
+          walk(s->expr->kids[0], c, r);
+      }
+    } else
+      walk(s->expr, c, r);
+    for(auto const& b : s->body)
+      ws(b, c, r);
+    for(auto const& b : s->orelse)
+      ws(b, c, r);
+  };
+  for(auto const* ms : kp.ms)
+    for(auto const& stage : ms->stages)
+      if(!droppedStages_.count(stage.id))
+        for(auto const& dm : stage.doMethods)
+          for(int r = 0; r < RJ; ++r)
+            for(int c = 0; c < RI; ++c)
+              for(auto const& s : dm.stmts)
+                ws(s, c, r);
+  return static_cast<int>(values.size() + temps.size());
+}
+
 std::vector<KernelPlan> CartesianEmitter::planKernels(const Stencil& st) {
   auto msPointwise = [&](const MultiStage& ms) {
     for(auto const& stage : ms.stages) {
@@ -852,8 +907,28 @@ std::vector<KernelPlan> CartesianEmitter::planKernels(const Stencil& st) {
         for(auto const& stage : x->stages)
           if(!droppedStages_.count(stage.id) && !stage.extent.horizontalZero())
             plainTile = false;
-      // default 2x2 micro-tiles (hori_diff on B200: 2x2 0.344 ms, 1x2 0.362 ms, 2x3 0.338 ms at 124 regs)
-      const int wantRI = opt_.ColsPerThread > 0 ? opt_.ColsPerThread : 2;
+      if(std::getenv("DAWN_B200_DEBUG_PLAN"))
+        for(auto rc : {std::pair<int, int>{2, 3}, {2, 2}, {2, 1}, {1, 2}, {1, 1}})
+          std::fprintf(stderr, "plan %s: %dx%d footprint %d\n", inst_.name.c_str(), rc.first, rc.second,
+                       microTileFootprint(kp, rc.first, rc.second));
+      int wantRI = opt_.ColsPerThread > 0 ? opt_.ColsPerThread : 2;
+      // Micro-tile choice when the user fixed nothing: the largest of 2x3, 2x2, 2x1 (on 8 thread rows)
+      // and 1x1 whose value footprint stays at <= 64 doubles per thread.  Measured on B200 at
+      // 1024^2 x 80: hori_diff_type2 2x3 (62 values, 124 registers) 0.360 ms vs 2x2 0.365; lap 2x3 82 %
+      // of the HBM peak vs 2x2 71 %; hd_smagorinsky 2x1 (57 values) 83 % vs 2x2 (90 values, 185
+      // registers) 72 %.
+      if(plainTile && opt_.ColsPerThread == 0 && opt_.RowsPerThread == 0 && opt_.BlockSizeJ == 0 &&
+         kp.TI % 4 == 0) {
+        struct Cand { int ri, rj, tj; };
+        const Cand cands[] = {{2, 3, 4}, {2, 2, 4}, {2, 1, 8}, {1, 1, 8}};
+        Cand pick = cands[3];
+        for(auto const& c : cands)
+          if(microTileFootprint(kp, c.ri, c.rj) <= 64) {
+            pick = c;
+            break;
+          }
+        wantRI = pick.ri, kp.RJ = pick.rj, kp.TJ = pick.tj;
+      }
       kp.RI = (plainTile && wantRI > 1 && kp.TI % (2 * wantRI) == 0) ? wantRI : 1;
       if(kp.RI > 2 || kp.TI % (2 * kp.RI) != 0)
         throw std::runtime_error("b200: cols_per_thread must be 1 or 2 and divide the tile width");
