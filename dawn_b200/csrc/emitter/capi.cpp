@@ -31,6 +31,7 @@ b200::codegen::Options convert(const dawn_b200_options* o) {
   r.ColsPerThread = o->cols_per_thread;
   r.SharedTemporaries = o->shared_temporaries;
   r.CoSchedule = o->co_schedule;
+  r.RingDrain = o->ring_drain;
   return r;
 }
 } // namespace
@@ -54,6 +55,7 @@ void dawn_b200_default_options(dawn_b200_options* o) {
   o->column_ring = 1;
   o->shared_temporaries = 0;
   o->co_schedule = 1;
+  o->ring_drain = 1;
 }
 
 int dawn_b200_parse_backend(const char* s) {

@@ -538,9 +538,10 @@ bool CartesianEmitter::planColumnRing(KernelPlan& kp) const {
   kp.colring = true;
   kp.ringFields.assign(fields.begin(), fields.end());
   kp.ringMaxFields = maxFields;
-  // measured on B200 (tridiagonal 512x512x80): 64x1 threads, 8 levels/slot, 3 slots -> 77 % of the
-  // measured HBM peak; 4 blocks (8 warps) per SM keep the c/d hand-over between sweeps in L2
-  kp.stages = opt_.TmaStages > 0 ? opt_.TmaStages : 3;
+  // measured on B200 (tridiagonal 512x512x80): 64x1 threads, 8 levels/slot; 3 slots refilled after the
+  // sweep of a slot -> 77 % of the measured HBM peak, slots drained into registers on arrival and
+  // refilled at once -> 80 % with 3 slots, 81 % with 4 (3 blocks per SM)
+  kp.stages = opt_.TmaStages > 0 ? opt_.TmaStages : (opt_.RingDrain ? 4 : 3);
   kp.TI = opt_.BlockSizeI > 0 ? opt_.BlockSizeI : 64;
   kp.TJ = opt_.BlockSizeJ > 0 ? opt_.BlockSizeJ : 1;
   if((kp.TI * 8) % 16 != 0 || kp.TI > 256 || kp.TJ > 256 || kp.ringKB > 256)
@@ -1727,16 +1728,38 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         };
         os_ << "      const int nk_loc = ke - kb + 1;\n";
         os_ << "      const int nch = nk_loc > 0 ? (nk_loc + " << KB - 1 << ") / " << KB << " : 0;\n";
+        // ring_drain: every thread copies its column of the slot into registers as soon as the slot
+        // arrives, the block synchronises and the slot is refilled at once - all S slots stay in flight
+        // while the levels are computed from registers (without it a slot sits idle for the whole
+        // 8-level sweep and at most S-1 are in flight: ncu showed 24 % of the warp samples waiting on
+        // the full-barrier)
+        const bool drain = opt_.RingDrain != 0;
+        const int ahead = drain ? S : S - 1;
         os_ << "      if(tid == 0) {\n";
-        os_ << "        for(int c = 0; c < " << S - 1 << " && c < nch; ++c)\n";
+        os_ << "        for(int c = 0; c < " << ahead << " && c < nch; ++c)\n";
         issue("          ", "c");
         os_ << "      }\n";
         os_ << "      for(int ch = 0; ch < nch; ++ch) {\n";
-        os_ << "        if(tid == 0 && ch + " << S - 1 << " < nch)\n";
-        issue("          ", "ch + " + std::to_string(S - 1));
+        if(!drain) {
+          os_ << "        if(tid == 0 && ch + " << S - 1 << " < nch)\n";
+          issue("          ", "ch + " + std::to_string(S - 1));
+        }
         os_ << "        const unsigned tcur = (tma_it + ch) % " << S << ";\n";
         os_ << "        ::dawn_b200::tma::wait(&tma_full[tcur], ((tma_it + ch) / " << S << ") & 1u);\n";
         os_ << "        const ::dawn::float_type* slot = tma_ring + tcur * " << ringSlotElems << ";\n";
+        if(drain) {
+          int fi = 0;
+          for(int f : be.prefetched) {
+            os_ << "        ::dawn::float_type rv_" << fname(f) << "[" << KB << "];\n";
+            os_ << "#pragma unroll\n";
+            os_ << "        for(int q = 0; q < " << KB << "; ++q)\n";
+            os_ << "          rv_" << fname(f) << "[q] = slot[(" << fi * KB << " + q) * " << NT << " + tid];\n";
+            ++fi;
+          }
+          os_ << "        __syncthreads(); // slot drained by every thread: refill it right away\n";
+          os_ << "        if(tid == 0 && ch + " << S << " < nch)\n";
+          issue("          ", "ch + " + std::to_string(S));
+        }
         os_ << "#pragma unroll\n";
         os_ << "      for(int q = 0; q < " << KB << "; ++q) {\n";
         os_ << "      const int k = " << (backward ? "ke - ch * " : "kb + ch * ") << KB
@@ -1861,9 +1884,13 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         if(useRing && sn == 0) {
           int fi = 0;
           for(int f : be.prefetched) {
-            os_ << pad << "const ::dawn::float_type pfv_" << fname(f) << " = slot[("
-                << fi * kp.ringKB << " + " << (backward ? std::to_string(kp.ringKB - 1) + " - q" : "q")
-                << ") * " << kp.NT() << " + tid];\n";
+            const std::string lvl = backward ? std::to_string(kp.ringKB - 1) + " - q" : "q";
+            if(opt_.RingDrain)
+              os_ << pad << "const ::dawn::float_type pfv_" << fname(f) << " = rv_" << fname(f) << "["
+                  << lvl << "];\n";
+            else
+              os_ << pad << "const ::dawn::float_type pfv_" << fname(f) << " = slot[("
+                  << fi * kp.ringKB << " + " << lvl << ") * " << kp.NT() << " + tid];\n";
             ++fi;
           }
           for(auto const& r : be.rings)
@@ -1969,7 +1996,8 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         os_ << "      }\n      }\n";
       if(useRing) {
         os_ << "      }\n"; // q loop
-        os_ << "        __syncthreads(); // slot consumed by every thread before it is refilled\n";
+        if(!opt_.RingDrain)
+          os_ << "        __syncthreads(); // slot consumed by every thread before it is refilled\n";
         os_ << "      }\n"; // chunk loop
         os_ << "      tma_it += (unsigned)nch;\n";
       }

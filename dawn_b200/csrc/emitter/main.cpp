@@ -49,7 +49,7 @@ int main(int argc, char** argv) {
             intOpt(a, "column-ring", opts.ColumnRing) || intOpt(a, "ring-levels", opts.RingLevels) ||
             intOpt(a, "cols-per-thread", opts.ColsPerThread) ||
             intOpt(a, "shared-temporaries", opts.SharedTemporaries) ||
-            intOpt(a, "co-schedule", opts.CoSchedule) ||
+            intOpt(a, "co-schedule", opts.CoSchedule) || intOpt(a, "ring-drain", opts.RingDrain) ||
             intOpt(a, "max-blocks-sm", opts.MaxBlocksPerSM) ||
             intOpt(a, "max-halo-points", opts.MaxHaloSize)) {
     } else if(a.compare(0, 16, "--run-with-sync=") == 0)
