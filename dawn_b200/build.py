@@ -102,7 +102,7 @@ VARIANTS = {
         dict(block_size_i=32, block_size_j=8, rows_per_thread=2), dict(inline_temporaries=0),
         dict(use_tma=0), dict(tma_stages=2, block_size_k=3), dict(inline_temporaries=0, use_tma=0),
         dict(cols_per_thread=1), dict(cols_per_thread=2, use_tma=0, rows_per_thread=1),
-        dict(rows_per_thread=3), dict(shared_temporaries=1),
+        dict(rows_per_thread=3), dict(ring_drain=2), dict(shared_temporaries=1),
         dict(shared_temporaries=1, cols_per_thread=1), dict(shared_temporaries=1, rows_per_thread=1),
         dict(shared_temporaries=1, tma_stages=2, block_size_j=8),
     ],

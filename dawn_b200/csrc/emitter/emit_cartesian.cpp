@@ -1605,6 +1605,8 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
       be.prefetched.clear();
       bool usePrefetch = false;
       bool useRing = false;
+      bool drainTile = false;
+      std::function<void(const std::string&)> drainRefill;
       if(kp.colring) {
         be.prefetched = streamedFields(kp, *ms, part, msDepths);
         useRing = !be.prefetched.empty();
@@ -1637,11 +1639,27 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
           usePrefetch = !be.prefetched.empty();
         }
       }
+      // A tile kernel with one live stage reads its ring slot only through the hoisted loads at the
+      // top of the body: the block can synchronise right after them and refill the slot at once (all
+      // slots in flight during the arithmetic of the level) instead of at the end of the level.
+      int liveStages = 0;
+      for(auto const& stage : ms->stages) {
+        if(droppedStages_.count(stage.id))
+          continue;
+        bool any = false;
+        for(auto const& dm : stage.doMethods)
+          any = any || dm.interval.overlaps(part.lo, part.hi);
+        liveStages += any ? 1 : 0;
+      }
+      // (ring_drain=2 only: measured on B200 it is a wash - hori_diff_type2 0.347 vs 0.343 ms without,
+      // hd_smagorinsky 1.075 vs 1.108 ms - because the slot of a tile kernel is busy for one level only)
+      drainTile = kp.tma && opt_.RingDrain >= 2 && kp.cached.empty() && uniformRegion && liveStages == 1;
       if(kp.tma) {
         const std::string kOf = backward ? "ke - " : "kb + ";
+        const int ahead = drainTile ? kp.stages : kp.stages - 1;
         os_ << "      const int nk_loc = ke - kb + 1;\n";
         os_ << "      if(tid == 0) {\n";
-        os_ << "        for(int q = 0; q < " << kp.stages - 1 << " && q < nk_loc; ++q)\n";
+        os_ << "        for(int q = 0; q < " << ahead << " && q < nk_loc; ++q)\n";
         emitTmaIssue("          ", kOf + "q", "(tma_it + q) % " + std::to_string(kp.stages));
         os_ << "      }\n";
         os_ << "      for(int it = 0; it < nk_loc; ++it) {\n";
@@ -1653,7 +1671,12 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
                        "(tma_it + it + " + std::to_string(kp.stages - 1) + ") % " +
                            std::to_string(kp.stages));
         };
-        if(kp.cached.empty())
+        drainRefill = [&, kOf](const std::string& pad) {
+          os_ << pad << "__syncthreads(); // slot read by every thread: refill it right away\n";
+          os_ << pad << "if(tid == 0 && it + " << kp.stages << " < nk_loc)\n";
+          emitTmaIssue(pad + "  ", kOf + "(it + " + std::to_string(kp.stages) + ")", "tcur");
+        };
+        if(kp.cached.empty() && !drainTile)
           emitRefill();
         os_ << "        ::dawn_b200::tma::wait(&tma_full[tcur], ((tma_it + it) / " << kp.stages
             << ") & 1u);\n";
@@ -1934,6 +1957,8 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         be.curCol = 0;
         for(auto const& l : be.loads)
           os_ << pad << l << "\n";
+        if(drainTile)
+          drainRefill(pad);
         for(auto const& l : be.temps)
           os_ << pad << l << "\n";
         for(int rc = 0; rc < rows * cols; ++rc) {
@@ -1987,7 +2012,7 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
           os_ << "        " << fname(r.first) << "_kc" << n << " = " << fname(r.first) << "_kc"
               << n - 1 << ";\n";
       // a stage of the next level may overwrite scratch another thread still reads
-      if(kp.tma && kp.cached.empty())
+      if(kp.tma && kp.cached.empty() && !drainTile)
         os_ << "        __syncthreads(); // every thread is done with this ring slot before its refill\n";
       else if(!kp.pointwise && live.size() > 1 && sequential)
         os_ << "        __syncthreads();\n";

@@ -60,7 +60,8 @@ typedef struct dawn_b200_options {
   int co_schedule;        /* default 1: unstructured groups that are independent and gather a common field are
                              launched as one kernel whose blocks alternate between them (L2 reuse) */
   int ring_drain;         /* default 1: column-ring kernels drain an arrived slot into registers and refill
-                             it at once (all slots in flight during the sweep) */
+                             it at once (all slots in flight during the sweep); 2: TMA tile kernels with one
+                             live stage also refill right after their hoisted loads */
 } dawn_b200_options;
 
 /* Fills `opts` with the defaults above. */

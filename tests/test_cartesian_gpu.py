@@ -50,7 +50,7 @@ def test_hori_diff_type2(I, J, K):
                                   dict(tma_stages=2, block_size_k=3),
                                   dict(inline_temporaries=0, use_tma=0), dict(cols_per_thread=1),
                                   dict(cols_per_thread=2, use_tma=0, rows_per_thread=1),
-                                  dict(rows_per_thread=3), dict(shared_temporaries=1),
+                                  dict(rows_per_thread=3), dict(ring_drain=2), dict(shared_temporaries=1),
                                   dict(shared_temporaries=1, cols_per_thread=1),
                                   dict(shared_temporaries=1, rows_per_thread=1),
                                   dict(shared_temporaries=1, tma_stages=2, block_size_j=8)])
