@@ -136,12 +136,16 @@ def variant_tag(options):
     return "_".join("%s%s" % (k[:2] + k.split("_")[-1][:1], v) for k, v in sorted(options.items()))
 
 
-def build_all(force=False):
-    """Everything bench/tests need: emitter, runtime, and a module per stencils/*.iir fixture."""
+def build_all(force=False, jobs=None):
+    """Everything bench/tests need: emitter, runtime, and a module per stencils/*.iir fixture (plus the
+    planner variants above).  Code generation is serial (milliseconds each); the nvcc compilations run
+    `jobs` at a time (default: one per core)."""
+    from concurrent.futures import ThreadPoolExecutor
+
     from . import codegen
     build_emitter(force)
     build_runtime(force)
-    built = []
+    work = []  # (name, code, tag)
     sdir = os.path.join(ROOT, "stencils")
     for fn in sorted(os.listdir(sdir)):
         if not fn.endswith(".iir"):
@@ -156,21 +160,21 @@ def build_all(force=False):
             if "not yet supported" in str(e):
                 continue
             raise
-        built.append(compile_module(name, code, force=force))
+        work.append((name, code, ""))
         for opts in VARIANTS.get(name, []):
-            vcode = codegen.compile_iir(iir, backend=backend, **opts)
-            built.append(compile_module(name, vcode, tag=variant_tag(opts), force=force))
+            work.append((name, codegen.compile_iir(iir, backend=backend, **opts), variant_tag(opts)))
     for name, rel in REFERENCE_IIR.items():
         path = os.path.join(REFERENCE_ROOT, rel)
         if not os.path.exists(path):
             continue
         with open(path) as f:
             iir = f.read()
-        built.append(compile_module(name, codegen.compile_iir(iir, backend="b200"), tag="ref",
-                                    force=force))
-        built.append(compile_module(name, codegen.compile_iir(iir, backend="b200", use_tma=0,
-                                                              inline_temporaries=0),
-                                    tag="ref_plain", force=force))
+        work.append((name, codegen.compile_iir(iir, backend="b200"), "ref"))
+        work.append((name, codegen.compile_iir(iir, backend="b200", use_tma=0, inline_temporaries=0),
+                     "ref_plain"))
+    jobs = jobs or os.cpu_count() or 1
+    with ThreadPoolExecutor(max_workers=jobs) as pool:
+        built = list(pool.map(lambda w: compile_module(w[0], w[1], tag=w[2], force=force), work))
     return built
 
 
