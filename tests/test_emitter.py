@@ -198,3 +198,45 @@ def test_unstructured_interface_files():
     assert "module ICON_laplacian_stencil_b200" in f and "bind(c)" in f
     with pytest.raises(codegen.CodeGenError):
         codegen.interface_text(open(iir_path("copy_stencil")).read(), "c")
+
+
+def test_unstructured_loops_sparse_and_indirection_are_emitted():
+    """Constructs of Cuda-ico/ASTStencilBody.cpp: neighbour loops writing sparse fields, nested
+    reductions fetched where they are used, vertical indirection, horizontal-only fields, iteration
+    spaces with splitter indices."""
+    code = _code("sparseAssignment2", backend="b200-ico")
+    assert code.count("if(nb_ecv_") == 4                      # loop over e->c->v unrolled 4 times
+    assert "sparse_p[((size_t)k * 4 + 3) * n_edges + pidx]" in code
+    nested = _code("sparseAssignment5", backend="b200-ico")
+    assert "nb_ce_0" in nested and "nb_ev_0" not in nested    # only the loop's chain is preloaded
+    assert "__ldg(&tbl_vc[" in nested
+    ind = _code("verticalIndirecion", backend="b200-ico")
+    assert "(int)(__ldg(&kidx_p[(size_t)k * n_cells + pidx])) + (0)" in ind
+    hv = _code("horizontalVertical", backend="b200-ico")
+    assert "horizontal_p[pidx]" in hv and "vertical_p[k]" in hv
+    assert "horizontal_sparse_p[(size_t)0 * n_edges + pidx]" in hv
+    sp = _code("iterationSpaceUnstructured", backend="b200-ico")
+    assert "splitter(0, 3000, 0, &elem_lo)" in sp and "splitter(0, 4000, 0, &elem_hi)" in sp
+    assert "set_splitter_index_iterationSpaceUnstructured" in sp
+    assert len(re.findall(r"^// kernel ", sp, flags=re.M)) == 2   # different spaces are not fused
+    with pytest.raises(codegen.CodeGenError, match="b200-ico"):
+        _code("verticalIndirecion", backend="b200")
+
+
+def test_control_flow_of_the_description_is_emitted():
+    code = _code("stencil_desc_ast_04")
+    run = code[code.index("  void run(storage_ijk_t in, storage_ijk_t out) {"):]
+    run = run[:run.index("sync_storages(")]
+    assert run.count("if(") == 3 and run.count(".run(in, out);") == 2
+    assert "m_globals.var_compiletime != (int)1" in run
+    plain = _code("hori_diff_type2_stencil")
+    run = plain[plain.index("  void run(storage_ijk_t out, storage_ijk_t in, storage_j_t crlato"):]
+    assert "if(" not in run[:run.index("sync_storages(")]
+
+
+def test_pure_locals_are_substituted_into_inlined_temporaries():
+    code = _code("hd_smagorinsky_stencil")
+    assert len(re.findall(r"^// kernel .*_kernel:", code, flags=re.M)) == 2   # plain + tma twin, one multistage
+    assert "scratch_field" not in code and not re.search(r"\bT_sqr_s_p\b", code)
+    staged = _code("hd_smagorinsky_stencil", inline_temporaries=0)
+    assert "scratch_field" in staged
