@@ -32,6 +32,7 @@ b200::codegen::Options convert(const dawn_b200_options* o) {
   r.SharedTemporaries = o->shared_temporaries;
   r.CoSchedule = o->co_schedule;
   r.RingDrain = o->ring_drain;
+  r.IcoFullBlocks = o->ico_full_blocks;
   return r;
 }
 } // namespace

@@ -711,34 +711,43 @@ void IcoEmitter::emitRole(const Group& g, const std::string& blockExpr, const st
       os_ << "  for(int k = kb; k <= ke; ++k) {\n";
   } else {
     os_ << "  const int k0 = kb + blockIdx.y * " << lpt_ << ";\n";
-    os_ << "#pragma unroll\n";
-    os_ << "  for(int kk = 0; kk < " << lpt_ << "; ++kk) {\n";
-    os_ << "    const int k = k0 + kk;\n";
-    os_ << "    if(k > ke)\n      break;\n";
   }
+  const std::string loopHead = "#pragma unroll\n  for(int kk = 0; kk < " + std::to_string(lpt_) +
+                               "; ++kk) {\n    const int k = k0 + kk;\n";
+  if(!sequential && !opt_.IcoFullBlocks)
+    os_ << loopHead << "    if(k > ke)\n      break;\n";
+  std::ostringstream bodyText;
   IcoBody body{inst_, g, registerOnly_,
                [this](int id) { return fname(id); },
                [this](int id) -> const FieldDims& { return dims(id); },
                [this](int id) { return sparseSize(id); }, {}, 0};
   for(auto const* st : g.stages) {
-    os_ << "    // stage " << st->id << "\n";
+    bodyText << "    // stage " << st->id << "\n";
     for(auto const& dm : st->doMethods) {
       bool guard = dm.interval.lowerBound() != lo_k || dm.interval.upperBound() != hi_k;
       std::vector<std::string> lines;
       for(auto const& s : dm.stmts)
         body.stmt(s, lines, 0, guard);
       if(guard)
-        os_ << "    if(k >= " << analysis::boundExpr(dm.interval.lowerBound()) << " && k <= "
+        bodyText << "    if(k >= " << analysis::boundExpr(dm.interval.lowerBound()) << " && k <= "
             << analysis::boundExpr(dm.interval.upperBound()) << ") {\n";
       for(auto const& l : lines)
-        os_ << (guard ? "      " : "    ") << l << "\n";
+        bodyText << (guard ? "      " : "    ") << l << "\n";
       if(guard) {
-        os_ << "    }\n";
+        bodyText << "    }\n";
         body.forwarded.clear();
       }
     }
   }
-  os_ << "  }\n";
+  if(sequential || !opt_.IcoFullBlocks) {
+    os_ << bodyText.str() << "  }\n";
+    return;
+  }
+  // ico_full_blocks: blocks of levels that lie completely inside the range run the unrolled loop
+  // without a bound check per level (loads of several levels may be scheduled together); the last,
+  // partial block takes a plain loop
+  os_ << "  if(k0 + " << lpt_ - 1 << " <= ke) {\n" << loopHead << bodyText.str() << "  }\n  } else {\n";
+  os_ << "  for(int k = k0; k <= ke; ++k) {\n" << bodyText.str() << "  }\n  }\n";
 }
 
 void IcoEmitter::emitKernel(const Group& g, const Group* partner) {

@@ -50,6 +50,7 @@ int main(int argc, char** argv) {
             intOpt(a, "cols-per-thread", opts.ColsPerThread) ||
             intOpt(a, "shared-temporaries", opts.SharedTemporaries) ||
             intOpt(a, "co-schedule", opts.CoSchedule) || intOpt(a, "ring-drain", opts.RingDrain) ||
+            intOpt(a, "ico-full-blocks", opts.IcoFullBlocks) ||
             intOpt(a, "max-blocks-sm", opts.MaxBlocksPerSM) ||
             intOpt(a, "max-halo-points", opts.MaxHaloSize)) {
     } else if(a.compare(0, 16, "--run-with-sync=") == 0)
