@@ -938,6 +938,49 @@ std::vector<KernelPlan> CartesianEmitter::planKernels(const Stencil& st) {
       throw std::runtime_error("b200: block size must be within [32,1024] threads");
     kp.name = cIdent(inst_.name) + "_stencil" + std::to_string(st.id) + "_k" +
               std::to_string(kidx++) + "_kernel";
+    // A stage with a horizontal extent is computed redundantly over tile + extent by every block.  For
+    // temporaries that is the point; a stored field written there is also written into the tiles of
+    // neighbouring blocks, which is harmless (same value) unless a later stage of the same kernel
+    // touches the field again - then the two blocks race.  The reference's CUDA backend has the same
+    // hazard and stays silent; here it is an error (such a multistage has to be split).
+    if(!kp.pointwise)
+      for(auto const* x : kp.ms) {
+        std::vector<const Stage*> live;
+        for(auto const& stage : x->stages)
+          if(!droppedStages_.count(stage.id))
+            live.push_back(&stage);
+        for(size_t a = 0; a < live.size(); ++a) {
+          if(live[a]->extent.horizontalZero())
+            continue;
+          StageInfo ia = analysis::stageInfo(inst_, *live[a]);
+          for(auto const& fp : ia.fields) {
+            if(inst_.isTemporary(fp.first) || inlined_.count(fp.first))
+              continue;
+            // ... and a stored field READ there is read in the neighbours' tiles too, so a later stage
+            // of the same kernel must not write it (Dawn's field versioning breaks such cycles)
+            if(!fp.second.written) {
+              for(size_t b2 = a + 1; b2 < live.size(); ++b2) {
+                StageInfo ib = analysis::stageInfo(inst_, *live[b2]);
+                auto it = ib.fields.find(fp.first);
+                if(it != ib.fields.end() && it->second.written)
+                  throw std::runtime_error(
+                      "b200: field '" + inst_.nameOf(fp.first) + "' is read by stage " +
+                      std::to_string(live[a]->id) + ", which is computed redundantly in the halo of "
+                      "every tile, and written by stage " + std::to_string(live[b2]->id) +
+                      " of the same multistage: blocks would race on it (version the field)");
+              }
+              continue;
+            }
+            for(size_t b2 = a + 1; b2 < live.size(); ++b2)
+              if(analysis::stageInfo(inst_, *live[b2]).fields.count(fp.first))
+                throw std::runtime_error(
+                    "b200: field '" + inst_.nameOf(fp.first) + "' is written by stage " +
+                    std::to_string(live[a]->id) + ", which is computed redundantly in the halo of every "
+                    "tile, and accessed again by stage " + std::to_string(live[b2]->id) +
+                    " of the same multistage: blocks would race on it (split the multistage)");
+          }
+        }
+      }
     collectUse(kp);
     out.push_back(kp);
     if(opt_.ColumnRing && kp.pointwise && !kp.zchunk) {
@@ -1035,6 +1078,37 @@ public:
     loads.clear();
     temps.clear();
     valueNo.clear();
+    for(auto it = guardOf.begin(); it != guardOf.end();) // invariant loads outlive the stage
+      it = it->first[0] == 'I' ? std::next(it) : guardOf.erase(it);
+  }
+
+  // ---- guards of hoisted global loads ------------------------------------------------------------
+  std::map<std::string, int> guardOf;                       // value key -> guard id
+  std::vector<std::set<std::pair<int, int>>> guardUsers;    // guard id -> cells (col, row) using it
+  int newGuard(const std::string& key, std::pair<int, int> user) {
+    guardUsers.push_back({user});
+    guardOf[key] = static_cast<int>(guardUsers.size()) - 1;
+    return guardOf[key];
+  }
+  static std::string guardToken(int id) { return "@G" + std::to_string(id) + "@"; }
+  // Replaces the guard placeholders of a line: a value is needed iff one of its user cells is inside
+  // the domain; cells are valid in prefix order in both directions, so the minimal users decide.
+  std::string finalize(const std::string& line) const {
+    size_t a = line.find("@G");
+    if(a == std::string::npos)
+      return line;
+    size_t b = line.find('@', a + 2);
+    const auto& users = guardUsers[std::stoi(line.substr(a + 2, b - a - 2))];
+    std::string g;
+    for(auto const& u : users) {
+      bool dominated = false;
+      for(auto const& o : users)
+        if(o != u && o.first <= u.first && o.second <= u.second)
+          dominated = true;
+      if(!dominated)
+        g += (g.empty() ? "" : " || ") + cellGuard(u.first, u.second);
+    }
+    return line.substr(0, a) + "(" + g + ")" + line.substr(b + 1);
   }
 
   std::string fieldName(int id) const { return cIdent(inst.nameOf(id)); }
@@ -1161,27 +1235,34 @@ public:
     if(readOnly) {
       std::string key = "F" + std::to_string(e.accessID) + ":" + std::to_string(di) + ":" +
                         std::to_string(djAbs) + ":" + std::to_string(dk);
+      // A cell outside the domain may point past the halo, so a hoisted load is predicated on the
+      // cells that use its value: the guard placeholder is resolved once all users are known
+      // (finalize()).  Predicating on the first user alone is wrong for 2-column micro-tiles: cell
+      // (1,0) can be outside the domain while cell (0,1), which shares the value, is inside.
+      const std::pair<int, int> user{curCol, std::max(0, std::min(rows - 1, curRow))};
       if(hoistInvariant && !m.k) {
         auto iv = invariantNo.find(key);
-        if(iv != invariantNo.end())
+        if(iv != invariantNo.end()) {
+          guardUsers[guardOf.at("I" + key)].insert(user);
           return iv->second;
+        }
         std::string var = fieldName(e.accessID) + "_" + offTag(di) + "_" + offTag(djAbs) + "_inv";
-        int firstRow = std::max(0, std::min(rows - 1, curRow));
-        invariantLoads.push_back("const ::dawn::float_type " + var + " = " + cellGuard(curCol, firstRow) +
+        const int gid = newGuard("I" + key, user);
+        invariantLoads.push_back("const ::dawn::float_type " + var + " = " + guardToken(gid) +
                                  " ? __ldg(&" + address(e.accessID, di, djAbs, 0) +
                                  ") : (::dawn::float_type)0;");
         invariantNo[key] = var;
         return var;
       }
       auto it = valueNo.find(key);
-      if(it != valueNo.end())
+      if(it != valueNo.end()) {
+        if(rowGuards)
+          guardUsers[guardOf.at(key)].insert(user);
         return it->second;
+      }
       std::string var = fieldName(e.accessID) + "_" + offTag(di) + "_" + offTag(djAbs) + "_" +
                         offTag(dk);
-      // a row beyond the valid rows of this thread may point past the halo: predicate on the first
-      // row that needs the value (rows are valid in prefix order)
-      int firstRow = std::max(0, std::min(rows - 1, curRow));
-      std::string guard = rowGuards ? cellGuard(curCol, firstRow) + " ? " : "";
+      std::string guard = rowGuards ? guardToken(newGuard(key, user)) + " ? " : "";
       std::string tail = rowGuards ? " : (::dawn::float_type)0" : "";
       loads.push_back("const ::dawn::float_type " + var + " = " + guard + "__ldg(&" +
                       address(e.accessID, di, djAbs, dk) + ")" + tail + ";");
@@ -1714,7 +1795,7 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
             be.curCol = 0;
             be.hoistInvariant = savedHoist;
             for(auto const& l : be.loads)
-              os_ << pad << l << "\n";
+              os_ << pad << be.finalize(l) << "\n";
             for(auto const& l : be.temps)
               os_ << pad << l << "\n";
             os_ << pad << "*reinterpret_cast<double2*>(&ij_buf[" << cc.offset << " + (lyb - (" << cc.jm
@@ -1956,7 +2037,7 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
           }
         be.curCol = 0;
         for(auto const& l : be.loads)
-          os_ << pad << l << "\n";
+          os_ << pad << be.finalize(l) << "\n";
         if(drainTile)
           drainRefill(pad);
         for(auto const& l : be.temps)
@@ -2048,7 +2129,7 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
     os_.str("");
     os_ << kernelHead;
     for(auto const& l : be.invariantLoads)
-      os_ << "  " << l << "\n";
+      os_ << "  " << be.finalize(l) << "\n";
     os_ << body;
   }
   os_ << "}\n\n";

@@ -240,3 +240,28 @@ def test_pure_locals_are_substituted_into_inlined_temporaries():
     assert "scratch_field" not in code and not re.search(r"\bT_sqr_s_p\b", code)
     staged = _code("hd_smagorinsky_stencil", inline_temporaries=0)
     assert "scratch_field" in staged
+
+
+def test_racy_halo_accesses_to_stored_fields_are_rejected():
+    """A stage with a horizontal extent runs redundantly over tile + extent in every block; a stored
+    field it writes (or reads) must not be touched again (written) by a later stage of the same
+    multistage - the reference's CUDA backend races silently on this, here it is an error."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from iir_builder import FULL, IIRBuilder
+    b = IIRBuilder("racy_write")
+    i, o = b.field("in"), b.field("out")
+    t = b.tmp("t")
+    s1 = b.stage(b.do(FULL, b.assign(t, i(1, 0)), b.assign(o, i())))     # extent from t(-1,0) below
+    s2 = b.stage(b.do(FULL, b.assign(o, t(-1, 0) + t(1, 0))))
+    b.stencil(b.multistage("Forward", s1, s2))                           # Forward: t cannot be inlined away
+    with pytest.raises(codegen.CodeGenError, match="blocks would race"):
+        codegen.compile_iir(b.dumps(), inline_temporaries=0)
+    b = IIRBuilder("racy_read")
+    i, o = b.field("in"), b.field("out")
+    t = b.tmp("t")
+    s1 = b.stage(b.do(FULL, b.assign(t, o() * 2.0)))                     # reads out in the halo ...
+    s2 = b.stage(b.do(FULL, b.assign(o, t(-1, 0) + i())))                # ... which this stage rewrites
+    b.stencil(b.multistage("Parallel", s1, s2))
+    with pytest.raises(codegen.CodeGenError, match="version the field"):
+        codegen.compile_iir(b.dumps(), inline_temporaries=0)
