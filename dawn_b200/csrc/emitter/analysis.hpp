@@ -103,6 +103,30 @@ inline void accumulate(const iir::Instantiation& inst, const std::vector<StmtPtr
   (void)inst;
 }
 
+// A Parallel multistage executes its levels in any order (level blocks of different thread blocks run
+// concurrently), so a field it writes must not be read at another level inside it - Dawn's
+// PassSetLoopOrder would have made such a multistage Forward or Backward.  Diagnosed instead of racing.
+inline void checkParallelLevels(const iir::Instantiation& inst, const iir::MultiStage& ms) {
+  if(ms.loopOrder != iir::LoopOrder::Parallel)
+    return;
+  std::set<int> written;
+  for(auto const& st : ms.stages)
+    for(auto const& dm : st.doMethods)
+      visitStmts(dm.stmts, [&](const Expr& e, bool w) {
+        if(w && e.kind == Expr::Field)
+          written.insert(e.accessID);
+      });
+  for(auto const& st : ms.stages)
+    for(auto const& dm : st.doMethods)
+      visitStmts(dm.stmts, [&](const Expr& e, bool w) {
+        if(!w && e.kind == Expr::Field && e.dk != 0 && written.count(e.accessID))
+          throw std::runtime_error("IIR: field '" + inst.nameOf(e.accessID) +
+                                   "' is written by Parallel multistage " + std::to_string(ms.id) +
+                                   " and read at a vertical offset inside it (the loop order must "
+                                   "be Forward or Backward)");
+      });
+}
+
 inline StageInfo stageInfo(const iir::Instantiation& inst, const iir::Stage& st) {
   StageInfo info;
   for(auto const& dm : st.doMethods)

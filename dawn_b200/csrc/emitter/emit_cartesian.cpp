@@ -263,6 +263,8 @@ static ExprPtr substituteLocals(const ExprPtr& e, const std::map<int, ExprPtr>& 
 }
 
 void CartesianEmitter::planTemporaries(const Stencil& st) {
+  for(auto const& ms : st.multiStages)
+    analysis::checkParallelLevels(inst_, ms);
   for(int tid : inst_.temporaryFieldIDs) {
     // where is it accessed?
     const MultiStage* onlyMs = nullptr;

@@ -267,6 +267,7 @@ std::vector<Group> IcoEmitter::plan(const Stencil& st) {
   std::vector<Group> groups;
   int n = 0;
   for(auto const& ms : st.multiStages) {
+    analysis::checkParallelLevels(inst_, ms);
     Group cur;
     std::set<int> written;
     auto flush = [&]() {

@@ -265,3 +265,25 @@ def test_racy_halo_accesses_to_stored_fields_are_rejected():
     b.stencil(b.multistage("Parallel", s1, s2))
     with pytest.raises(codegen.CodeGenError, match="version the field"):
         codegen.compile_iir(b.dumps(), inline_temporaries=0)
+
+
+def test_vertical_dependency_in_a_parallel_multistage_is_rejected():
+    """Level blocks of a Parallel multistage run concurrently: reading, at another level, a field the
+    multistage writes is a race (found by the random unstructured stencils) - diagnosed for both
+    backends."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from iir_builder import FULL, IIRBuilder, Interval
+    b = IIRBuilder("kdep", grid="Unstructured")
+    i, t, o = (b.field(n, "k", "Edge") for n in ("in", "mid", "out"))
+    s1 = b.stage(b.do(FULL, b.assign(t, i.at() * 2.0)), location="Edge")
+    s2 = b.stage(b.do(Interval("Start", "End", 0, -1), b.assign(o, t.at(1))), location="Edge")
+    b.stencil(b.multistage("Parallel", s1, s2))
+    with pytest.raises(codegen.CodeGenError, match="read at a vertical offset"):
+        codegen.compile_iir(b.dumps(), backend="b200-ico")
+    b = IIRBuilder("kdep_cart")
+    i, t, o = b.field("in"), b.field("mid"), b.field("out")
+    b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, b.assign(t, i() * 2.0))),
+                           b.stage(b.do(Interval("Start", "End", 0, -1), b.assign(o, t(0, 0, 1))))))
+    with pytest.raises(codegen.CodeGenError, match="read at a vertical offset"):
+        codegen.compile_iir(b.dumps())

@@ -4,7 +4,8 @@ dimensions, nested reductions, neighbour loops writing sparse fields, conditiona
 vertical-only fields, level offsets.  Writes stencils/fuzzico_<nn>.iir.
 
 Validity rules kept: a stage never reads through a chain (or at a neighbour) what it writes itself;
-level offsets stay inside [k_start + 1, k_end - 1] intervals; chains are taken from the table the
+level offsets stay inside [k_start + 1, k_end - 1] intervals and never touch a field the (Parallel)
+multistage writes; chains are taken from the table the
 reference's ICOChainSize knows (dawn/src/dawn/CodeGen/IcoChainSizes.cpp)."""
 import os
 import random
@@ -35,6 +36,7 @@ def make(seed):
     vert = b.field("vert", "k") if rng.random() < 0.4 else None
     sparse = {}
     outs = []
+    produced = []   # fields written by earlier stages of the multistage
     g = b.global_var("beta", "Double", 0.5) if rng.random() < 0.5 else None
 
     def sparse_of(chain):
@@ -46,7 +48,9 @@ def make(seed):
     def center(loc, allow_k, written):
         """expression at the stage's own element"""
         cands = [f for f in dense[loc] if f not in written]
-        x = rng.choice(cands).at(rng.choice([0, 0, 1, -1]) if allow_k else 0)
+        f = rng.choice(cands)
+        # level offsets only on fields nobody in this (Parallel) multistage writes
+        x = f.at(rng.choice([0, 0, 1, -1]) if (allow_k and f not in produced) else 0)
         if loc in hor and rng.random() < 0.3:
             x = x + hor[loc].at()
         if vert is not None and rng.random() < 0.3:
@@ -62,7 +66,7 @@ def make(seed):
         f = rng.choice(cands)
         # flagged or resolved by location type (chains that end where they start need the flag)
         if chain[0] == chain[-1] or rng.random() < 0.6:
-            x = f.at(rng.choice([0, 0, 1]) if allow_k else 0, nbh=True)
+            x = f.at(rng.choice([0, 0, 1]) if (allow_k and f not in produced) else 0, nbh=True)
         else:
             x = f.at(0)
         r = rng.random()
@@ -123,6 +127,7 @@ def make(seed):
             stmts.append(b.assign(o, center(loc, allow_k, written)))
         stages.append(b.stage(b.do(iv, *stmts), location=loc))
         dense[loc].append(o)       # later stages may consume it (forces kernel splits / forwarding)
+        produced.append(o)
     b.stencil(b.multistage("Parallel", *stages))
     return b
 
