@@ -287,3 +287,26 @@ def test_vertical_dependency_in_a_parallel_multistage_is_rejected():
                            b.stage(b.do(Interval("Start", "End", 0, -1), b.assign(o, t(0, 0, 1))))))
     with pytest.raises(codegen.CodeGenError, match="read at a vertical offset"):
         codegen.compile_iir(b.dumps())
+
+
+def test_one_translation_unit_for_several_instantiations_in_either_format():
+    """codegen::run takes a map of instantiations (Driver.h:38-40): one TU, one include block, every
+    stencil class; inputs may mix the Json and Byte formats."""
+    import ctypes
+    lib = codegen._load()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    datas = [open(os.path.join(root, "stencils", "copy_stencil.iir"), "rb").read(),
+             open(os.path.join(root, "tests", "golden", "proto", "lap.iirb"), "rb").read()]
+    names = (ctypes.c_char_p * 2)(b"copy_stencil", b"lap")
+    bufs = (ctypes.c_char_p * 2)(*datas)
+    lens = (ctypes.c_size_t * 2)(*[len(d) for d in datas])
+    out, n = ctypes.c_void_p(), ctypes.c_size_t()
+    opts = codegen.default_options()
+    rc = lib.dawn_b200_codegen_run(names, bufs, lens, 2, int(codegen.CodeGenBackend.B200),
+                                   ctypes.byref(opts), ctypes.byref(out), ctypes.byref(n))
+    assert rc == 0, lib.dawn_b200_codegen_last_error()
+    code = ctypes.string_at(out.value, n.value).decode()
+    lib.dawn_b200_free(out)
+    assert re.findall(r"^class (\w+) \{", code, flags=re.M) == ["copy_stencil", "lap"]
+    assert code.count("#include <driver-includes/gridtools_includes.hpp>") == 1
+    assert "setup_copy_stencil" in code and "setup_lap" in code
