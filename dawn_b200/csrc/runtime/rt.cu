@@ -12,6 +12,10 @@
 #include <string>
 #include <vector>
 
+struct b200_graph {
+  cudaGraphExec_t exec;
+};
+
 // stencil -> per-iteration {field -> metrics} (std::map: keys sorted like nlohmann::json objects)
 struct b200_metrics_record {
   std::map<std::string, std::vector<std::map<std::string, b200_verification_metrics>>> stencils;
@@ -354,6 +358,39 @@ static int reshape_impl(const double* in, double* out, int k_size, int n_elem, i
   CK(cudaGetLastError());
   return 0;
 }
+int b200rt_graph_begin(void* stream) {
+  // thread-local capture mode: helper threads of the process (NCCL proxies, a framework's watchdog) keep
+  // making CUDA calls while this thread records
+  CK(cudaStreamBeginCapture(S(stream), cudaStreamCaptureModeThreadLocal));
+  return 0;
+}
+int b200rt_graph_end(void* stream, b200_graph** graph) {
+  if(!graph)
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_graph_end: null argument");
+  cudaGraph_t g = nullptr;
+  CK(cudaStreamEndCapture(S(stream), &g));
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&exec, g, 0);
+  cudaGraphDestroy(g);
+  if(e != cudaSuccess)
+    return cudaFail(e, "cudaGraphInstantiate");
+  *graph = new b200_graph{exec};
+  return 0;
+}
+int b200rt_graph_launch(b200_graph* graph, void* stream) {
+  if(!graph)
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_graph_launch: null graph");
+  CK(cudaGraphLaunch(graph->exec, S(stream)));
+  return 0;
+}
+int b200rt_graph_destroy(b200_graph* graph) {
+  if(graph) {
+    cudaGraphExecDestroy(graph->exec);
+    delete graph;
+  }
+  return 0;
+}
+
 int b200rt_metrics_record_create(b200_metrics_record** rec) {
   if(!rec)
     return b200rt_set_error(B200_ERR_ARG, "b200rt_metrics_record_create: null argument");

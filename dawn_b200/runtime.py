@@ -38,6 +38,7 @@ SYMBOLS = [
     "b200rt_halo_exchange",
     "b200rt_halo_plan_destroy", "b200rt_metrics_record_create", "b200rt_metrics_record_add",
     "b200rt_metrics_record_json", "b200rt_metrics_record_write", "b200rt_metrics_record_destroy",
+    "b200rt_graph_begin", "b200rt_graph_end", "b200rt_graph_launch", "b200rt_graph_destroy",
 ]
 
 

@@ -150,6 +150,18 @@ typedef struct b200_mesh_t {
   const b200_splitter_t* splitters;  /* copied by setup_<N>; set_splitter_index_<N> edits the copy */
 } b200_mesh_t;
 
+/* ---- a time step as one CUDA graph (the reference synchronises the device around
+ * every generated run(), CudaCodeGen.cpp:435-450).  Everything the C ABI enqueues on `stream` between
+ * begin and end - generated kernels, halo pack/unpack kernels, the ncclSend/ncclRecv group - becomes one
+ * graph; launch replays it.  Run the sequence once eagerly first: the first call of a generated module
+ * sets kernel attributes and allocates scratch temporaries, which must not happen while capturing.
+ * A graph holding NCCL nodes has to be destroyed before its communicator. ---- */
+typedef struct b200_graph b200_graph;
+int b200rt_graph_begin(void* stream);
+int b200rt_graph_end(void* stream, b200_graph** graph);
+int b200rt_graph_launch(b200_graph* graph, void* stream);
+int b200rt_graph_destroy(b200_graph* graph);
+
 /* ---- j-slab halo exchange across the GPUs of one box (new: the reference has no communication
  * layer at all).  One process per GPU.  `comm` is an ncclComm_t created by the host
  * (e.g. from torch.distributed's unique id) or by b200rt_comm_init_rank. ---- */

@@ -449,3 +449,53 @@ def test_random_stencils_match_the_oracle(seed, opts):
         got = _run_gpu(name, (ni, nj, K), f, order, globals_=g, **opts)
         for n in order:
             assert bit_equal(got[n], want[n]), (name, n, (I, J, K))
+
+
+def test_graph_capture_through_the_c_abi():
+    """b200rt_graph_begin/end/launch: what a C++ or Fortran host uses to replay a step as one graph."""
+    import ctypes
+    import torch
+    import dawn_b200
+    from dawn_b200 import runtime as rt
+    I, J, K = 40, 24, 12
+    ni, nj = I + 2 * HALO, J + 2 * HALO
+    dom = dawn_b200.Domain(ni, nj, K)
+    dom.set_halos(HALO, HALO, HALO, HALO, 0, 0)
+    f = hori_diff_type2_inputs(I, J, K)
+    hd = dawn_b200.load_stencil("hori_diff_type2_stencil")(dom)
+    cp = dawn_b200.load_stencil("copy_stencil")(dom)
+    order = ["out", "in", "crlato", "crlatu", "hdmask"]
+    dims = {"out": "ijk", "in": "ijk", "crlato": "j", "crlatu": "j", "hdmask": "ijk"}
+    stor = {n: dawn_b200.Storage(ni, nj, K + 1, dims[n]).from_numpy(f[n]) for n in order}
+    side = torch.cuda.Stream()
+    sp = ctypes.c_void_p(side.cuda_stream)
+
+    def step():
+        hd.run(*[stor[n] for n in order], stream=side.cuda_stream)
+        cp.run(stor["out"], stor["in"], stream=side.cuda_stream)
+
+    torch.cuda.synchronize()
+    step()                                   # warm-up: attributes, scratch
+    side.synchronize()
+    lib = rt.lib()
+    rt.check(lib.b200rt_graph_begin(sp))
+    step()
+    graph = ctypes.c_void_p()
+    rt.check(lib.b200rt_graph_end(sp, ctypes.byref(graph)))
+    lib.b200rt_graph_launch.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.b200rt_graph_destroy.argtypes = [ctypes.c_void_p]
+    stor["in"].from_numpy(f["in"])
+    stor["out"].from_numpy(f["out"])
+    torch.cuda.synchronize()
+    for _ in range(3):
+        step()
+    side.synchronize()
+    want = stor["in"].to_numpy().copy()
+    stor["in"].from_numpy(f["in"])
+    stor["out"].from_numpy(f["out"])
+    torch.cuda.synchronize()
+    for _ in range(3):
+        rt.check(lib.b200rt_graph_launch(graph, sp))
+    side.synchronize()
+    assert bit_equal(stor["in"].to_numpy(), want)
+    rt.check(lib.b200rt_graph_destroy(graph))
