@@ -310,3 +310,23 @@ def test_one_translation_unit_for_several_instantiations_in_either_format():
     assert re.findall(r"^class (\w+) \{", code, flags=re.M) == ["copy_stencil", "lap"]
     assert code.count("#include <driver-includes/gridtools_includes.hpp>") == 1
     assert "setup_copy_stencil" in code and "setup_lap" in code
+
+
+def test_generated_c_header_is_valid_c(tmp_path):
+    """--output-c-header twin: the header of an unstructured stencil must compile as plain C against
+    include/dawn_b200_rt.h and declare every entry point the module exports."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = codegen.interface_text(open(iir_path("ICON_laplacian_stencil")).read(), "c")
+    hdr = tmp_path / "ICON_laplacian_stencil.h"
+    hdr.write_text(text)
+    src = tmp_path / "use.c"
+    src.write_text('#include "ICON_laplacian_stencil.h"\nint main(void) { return 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"),
+                    "-I", str(tmp_path), str(src)], check=True)
+    for sym in ("setup_", "run_", "free_", "verify_", "run_and_verify_", "set_splitter_index_",
+                "set_metrics_record_"):
+        assert sym + "ICON_laplacian_stencil" in text, sym
+    f90 = codegen.interface_text(open(iir_path("ICON_laplacian_stencil")).read(), "f90")
+    assert "module ICON_laplacian_stencil_b200" in f90 and "bind(c)" in f90
+    assert "set_splitter_index_ICON_laplacian_stencil" in f90
