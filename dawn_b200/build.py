@@ -179,6 +179,55 @@ def build_all(force=False, jobs=None):
     return built
 
 
+def build_reference_tree(force=False, jobs=None):
+    """Compiles a module for every optimized-IIR fixture of the reference tree the emitters accept
+    (only where /root/reference exists; the modules travel to the GPU box).  Returns and writes the
+    manifest dawn_b200/lib/stencils/reftree_manifest.json: file (relative to the reference root),
+    backend, stencil name, module path, or the diagnostic the emitter gave."""
+    import glob
+    import json
+    import re
+    from concurrent.futures import ThreadPoolExecutor
+
+    from . import codegen
+    if not os.path.isdir(REFERENCE_ROOT):
+        return []
+    build_emitter(force)
+    build_runtime(force)
+    entries, work = [], []
+    for path in sorted(glob.glob(os.path.join(REFERENCE_ROOT, "**", "*.iir"), recursive=True)):
+        rel = os.path.relpath(path, REFERENCE_ROOT)
+        with open(path) as f:
+            iir = f.read()
+        backend = "b200-ico" if re.search(r'"gridType"\s*:\s*"Unstructured"', iir) else "b200"
+        mod = "reftree_" + re.sub(r"[^A-Za-z0-9]", "_", rel)[-60:]
+        try:
+            code = codegen.compile_iir(iir, backend=backend)
+        except codegen.CodeGenError as e:
+            entries.append({"file": rel, "backend": backend, "rejected": str(e)})
+            continue
+        m = re.search(r'setup_(\w+)\(void\*\* handle', code)
+        entries.append({"file": rel, "backend": backend, "stencil": m.group(1), "module": mod})
+        work.append((mod, code))
+    def _compile(w):
+        try:
+            compile_module(w[0], w[1], force=force)
+            return None
+        except RuntimeError as e:
+            return str(e)[-400:]
+    with ThreadPoolExecutor(max_workers=jobs or os.cpu_count() or 1) as pool:
+        errors = list(pool.map(_compile, work))
+    for (mod, _), err in zip(work, errors):
+        if err:
+            for e in entries:
+                if e.get("module") == mod:
+                    e["rejected"] = "nvcc: " + err
+                    del e["module"]
+    with open(os.path.join(LIB, "stencils", "reftree_manifest.json"), "w") as f:
+        json.dump(entries, f, indent=1)
+    return [e for e in entries if "module" in e]
+
+
 def build_cpp_driver(force=False):
     """tests/cpp/hori_diff_driver.cu: a reference-style C++ driver that #includes the generated TU."""
     from . import codegen

@@ -127,6 +127,26 @@ inline void checkParallelLevels(const iir::Instantiation& inst, const iir::Multi
       });
 }
 
+// The invariant every Dawn backend relies on (PassStageSplitter / PassFieldVersioning establish it): a
+// stage never reads, at a horizontal offset, a field it writes itself - the points of a stage run in
+// parallel.  IIR that has not been through those passes (e.g. the inputs of the optimizer's own unit
+// tests) violates it and would race; it is rejected.
+inline void checkStageIndependence(const iir::Instantiation& inst, const iir::Stage& st) {
+  std::set<int> written;
+  for(auto const& dm : st.doMethods)
+    visitStmts(dm.stmts, [&](const Expr& e, bool w) {
+      if(w && e.kind == Expr::Field)
+        written.insert(e.accessID);
+    });
+  for(auto const& dm : st.doMethods)
+    visitStmts(dm.stmts, [&](const Expr& e, bool w) {
+      if(!w && e.kind == Expr::Field && (e.di != 0 || e.dj != 0) && written.count(e.accessID))
+        throw std::runtime_error("IIR: stage " + std::to_string(st.id) + " reads field '" +
+                                 inst.nameOf(e.accessID) + "' at a horizontal offset and writes it "
+                                 "(the stage has to be split / the field versioned first)");
+    });
+}
+
 inline StageInfo stageInfo(const iir::Instantiation& inst, const iir::Stage& st) {
   StageInfo info;
   for(auto const& dm : st.doMethods)

@@ -263,8 +263,11 @@ static ExprPtr substituteLocals(const ExprPtr& e, const std::map<int, ExprPtr>& 
 }
 
 void CartesianEmitter::planTemporaries(const Stencil& st) {
-  for(auto const& ms : st.multiStages)
+  for(auto const& ms : st.multiStages) {
     analysis::checkParallelLevels(inst_, ms);
+    for(auto const& stage : ms.stages)
+      analysis::checkStageIndependence(inst_, stage);
+  }
   for(int tid : inst_.temporaryFieldIDs) {
     // where is it accessed?
     const MultiStage* onlyMs = nullptr;
@@ -955,7 +958,7 @@ std::vector<KernelPlan> CartesianEmitter::planKernels(const Stencil& st) {
     // A stage with a horizontal extent is computed redundantly over tile + extent by every block.  For
     // temporaries that is the point; a stored field written there is also written into the tiles of
     // neighbouring blocks, which is harmless (same value) unless a later stage of the same kernel
-    // touches the field again - then the two blocks race.  The reference's CUDA backend has the same
+    // writes the field again - then the two blocks race.  The reference's CUDA backend has the same
     // hazard and stays silent; here it is an error (such a multistage has to be split).
     if(!kp.pointwise)
       for(auto const* x : kp.ms) {
@@ -985,13 +988,18 @@ std::vector<KernelPlan> CartesianEmitter::planKernels(const Stencil& st) {
               }
               continue;
             }
-            for(size_t b2 = a + 1; b2 < live.size(); ++b2)
-              if(analysis::stageInfo(inst_, *live[b2]).fields.count(fp.first))
+            // (a later stage that only READS the field is the ordinary case - PassSetNonTempCaches' and
+            // the stage extents' reason to exist: every block wrote the points it reads itself)
+            for(size_t b2 = a + 1; b2 < live.size(); ++b2) {
+              StageInfo ib = analysis::stageInfo(inst_, *live[b2]);
+              auto it = ib.fields.find(fp.first);
+              if(it != ib.fields.end() && it->second.written)
                 throw std::runtime_error(
                     "b200: field '" + inst_.nameOf(fp.first) + "' is written by stage " +
                     std::to_string(live[a]->id) + ", which is computed redundantly in the halo of every "
-                    "tile, and accessed again by stage " + std::to_string(live[b2]->id) +
+                    "tile, and written again by stage " + std::to_string(live[b2]->id) +
                     " of the same multistage: blocks would race on it (split the multistage)");
+            }
           }
         }
       }
@@ -1906,6 +1914,20 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         os_ << "      const int k = " << (backward ? "ke - ch * " : "kb + ch * ") << KB
             << (backward ? " - q" : " + q") << ";\n";
         os_ << "      if(active && " << (backward ? "k >= kb" : "k <= ke") << ") {\n";
+        // values of this level, visible to every stage of the multistage
+        {
+          int fi = 0;
+          for(int f : be.prefetched) {
+            const std::string lvl = backward ? std::to_string(kp.ringKB - 1) + " - q" : "q";
+            if(opt_.RingDrain)
+              os_ << "        const ::dawn::float_type pfv_" << fname(f) << " = rv_" << fname(f) << "["
+                  << lvl << "];\n";
+            else
+              os_ << "        const ::dawn::float_type pfv_" << fname(f) << " = slot[("
+                  << fi * kp.ringKB << " + " << lvl << ") * " << kp.NT() << " + tid];\n";
+            ++fi;
+          }
+        }
       } else if(usePrefetch) {
         const int P = kp.prefetch;
         const std::string sgn = backward ? "-" : "+";
@@ -1941,6 +1963,8 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         os_ << "      for(int q = 0; q < " << P << "; ++q) {\n";
         os_ << "      const int k = k0 " << sgn << " q;\n";
         os_ << "      if(" << inRange << ") {\n";
+        for(int f : be.prefetched) // visible to every stage of the multistage
+          os_ << "        const ::dawn::float_type pfv_" << fname(f) << " = pf_" << fname(f) << "[q];\n";
       } else {
         if(kp.colring)
           os_ << "      if(active)\n";
@@ -2023,26 +2047,12 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
             os_ << pad << fname(r.first) << "_kc0 = " << be.columnRead(r.first, 0) << ";\n";
         }
         if(useRing && sn == 0) {
-          int fi = 0;
-          for(int f : be.prefetched) {
-            const std::string lvl = backward ? std::to_string(kp.ringKB - 1) + " - q" : "q";
-            if(opt_.RingDrain)
-              os_ << pad << "const ::dawn::float_type pfv_" << fname(f) << " = rv_" << fname(f) << "["
-                  << lvl << "];\n";
-            else
-              os_ << pad << "const ::dawn::float_type pfv_" << fname(f) << " = slot[("
-                  << fi * kp.ringKB << " + " << lvl << ") * " << kp.NT() << " + tid];\n";
-            ++fi;
-          }
           for(auto const& r : be.rings)
             if(be.prefetched.count(r.first))
               os_ << pad << fname(r.first) << "_kc0 = pfv_" << fname(r.first) << ";\n";
         }
         if(usePrefetch && sn == 0) {
           const int P = kp.prefetch;
-          for(int f : be.prefetched)
-            os_ << pad << "const ::dawn::float_type pfv_" << fname(f) << " = pf_" << fname(f)
-                << "[q];\n";
           os_ << pad << "{\n";
           os_ << pad << "  const int kn = "
               << (backward ? "(k - " + std::to_string(P) + " > kb ? k - " + std::to_string(P) + " : kb)"
@@ -2643,7 +2653,11 @@ void CartesianEmitter::emitControlFlow(
         s += (n ? ", " : "") + ex(e->kids[n]);
       return s + ")";
     }
-    case Expr::Assign: return ex(e->kids[0]) + " " + e->op + " " + ex(e->kids[1]);
+    case Expr::Assign:
+      if(e->kids[0]->kind != Expr::Var)
+        throw std::runtime_error("b200: assignment to something that is not a variable in the control "
+                                 "flow of a stencil description");
+      return ex(e->kids[0]) + " " + e->op + " " + ex(e->kids[1]);
     default: throw std::runtime_error("b200: field access in the control flow of a stencil description");
     }
   };

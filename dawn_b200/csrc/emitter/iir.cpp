@@ -251,6 +251,8 @@ Instantiation parseInstantiation(const std::string& data) {
   // IIRSerializer::Format::Json (proto3 JSON text) or ::Byte (protobuf wire format), told apart by
   // the first byte: a serialized StencilInstantiation starts with tag 0x0A, never with '{'
   Value root = proto::looksLikeJson(data) ? json::parse(data) : proto::decode(data, "StencilInstantiation");
+  if(proto::looksLikeJson(data))
+    proto::normalizeJson(root, "StencilInstantiation");
   Instantiation inst;
   const Value& meta = root.at("metadata");
   const Value& ir = root.at("internalIR");

@@ -1,6 +1,7 @@
 #include "proto_wire.hpp"
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -566,6 +567,51 @@ std::string encodeMessage(const Value& v, const Message& msg) {
 }
 
 } // namespace
+
+namespace {
+// protobuf's default JSON name of a field: underscores dropped, the following letter upper-cased
+std::string jsonName(const std::string& protoName) {
+  std::string o;
+  bool up = false;
+  for(char c : protoName) {
+    if(c == '_') {
+      up = true;
+      continue;
+    }
+    o += up ? static_cast<char>(std::toupper(static_cast<unsigned char>(c))) : c;
+    up = false;
+  }
+  return o;
+}
+
+void normalizeMessage(Value& v, const Message& msg) {
+  if(v.kind != Value::Object)
+    return;
+  for(auto& kv : v.obj) {
+    const Field* f = msg.byName(kv.first);
+    if(!f)
+      for(auto const& cand : msg.fields)
+        if(jsonName(cand.name) == kv.first) {
+          f = &cand;
+          kv.first = cand.name;
+          break;
+        }
+    if(!f || f->type.t != T::Msg)
+      continue;
+    const Message& sub = messageOf(f->type.ref);
+    if(isMap(*f)) {
+      for(auto& e : kv.second.obj)
+        normalizeMessage(e.second, sub);
+    } else if(f->repeated) {
+      for(auto& e : kv.second.arr)
+        normalizeMessage(e, sub);
+    } else
+      normalizeMessage(kv.second, sub);
+  }
+}
+} // namespace
+
+void normalizeJson(json::Value& v, const std::string& message) { normalizeMessage(v, messageOf(message)); }
 
 json::Value decode(const std::string& bytes, const std::string& message) {
   Reader r{reinterpret_cast<const unsigned char*>(bytes.data()),

@@ -18,6 +18,11 @@ json::Value decode(const std::string& bytes, const std::string& message);
 // round-trip tests and by tools that hand IIR bytes to other dawn binaries.
 std::string encode(const json::Value& v, const std::string& message);
 
+// proto3 JSON parsers accept a field under its proto name (i_range, block_stmt: what IIRSerializer
+// writes) and under its lowerCamelCase JSON name (iRange, blockStmt: what other protobuf runtimes write
+// by default).  Renames the latter to the former throughout a DOM of message type `message`.
+void normalizeJson(json::Value& v, const std::string& message);
+
 // True if `data` looks like proto3 JSON text (first non-blank byte is '{').
 bool looksLikeJson(const std::string& data);
 

@@ -51,11 +51,43 @@ _HALF = 1 << 19
 # ------------------------------------------------------------------------------------------------
 # IIR helpers
 # ------------------------------------------------------------------------------------------------
+# proto field names that contain an underscore (IIR.proto / statements.proto): proto3 JSON writers other
+# than Dawn's IIRSerializer emit them in lowerCamelCase (block_stmt -> blockStmt), readers accept both
+# (VerticalRegion.loop_order is left out on purpose: MultiStage has a field spelled loopOrder)
+_SNAKE_FIELDS = """
+mask_cart_i mask_cart_j iter_space cartesian_horizontal_dimension unstructured_horizontal_dimension mask_k
+is_temporary field_dimensions field_value direction_value offset_value special_lower_level lower_level
+special_upper_level upper_level lower_offset upper_offset type_id builtin_type is_const is_volatile
+i_range j_range i_extent j_extent has_extent cartesian_extent unstructured_extent zero_extent vertical_extent
+include_center block_stmt expr_stmt return_stmt var_decl_stmt stencil_call_decl_stmt
+vertical_region_decl_stmt boundary_condition_decl_stmt if_stmt loop_stmt unary_operator binary_operator
+assignment_expr ternary_operator fun_call_expr stencil_fun_call_expr stencil_fun_arg_expr var_access_expr
+field_access_expr literal_access_expr reduction_over_neighbor_expr loop_descriptor_chain
+loop_descriptor_general loop_descriptor init_list var_decl_stmt_data vertical_region stencil_call cond_part
+then_part else_part argument_index is_external i_offset j_offset has_offset vertical_shift
+vertical_indirection vertical_indirection_data cartesian_offset unstructured_offset zero_offset argument_map
+argument_offset negate_offset boolean_value integer_value double_value string_value float_value is_constexpr
+dense_location_type sparse_part
+""".split()
+_CAMEL = {}
+for _n in _SNAKE_FIELDS:
+    _p = _n.split("_")
+    _CAMEL[_p[0] + "".join(w[:1].upper() + w[1:] for w in _p[1:])] = _n
+
+
+def _normalize_keys(x):
+    if isinstance(x, dict):
+        return {_CAMEL.get(k, k): _normalize_keys(v) for k, v in x.items()}
+    if isinstance(x, list):
+        return [_normalize_keys(v) for v in x]
+    return x
+
+
 def load_iir(path_or_dict):
     if isinstance(path_or_dict, dict):
         return path_or_dict
     with open(path_or_dict) as f:
-        return json.load(f)
+        return _normalize_keys(json.load(f))
 
 
 def _kind(node: dict) -> Tuple[str, dict]:
@@ -274,8 +306,8 @@ class CartesianRun:
         by_id = {st["stencilID"]: st for st in self.ir["stencils"]}
         flow = self.ir.get("controlFlowStatements", [])
         if not flow:
-            return list(self.ir["stencils"])
-        seq = []
+            yield from self.ir["stencils"]
+            return
         local = {}
 
         def ev(node):
@@ -296,18 +328,20 @@ class CartesianRun:
             raise NotImplementedError("control flow expression " + kd)
 
         def ex(node):
+            # a generator: the caller runs each stencil as it is reached, so assignments to globals
+            # between two calls (globals_dependencies_issue401) take effect in order
             kd, v = _kind(node)
             if kd == "stencil_call_decl_stmt":
-                seq.append(by_id[int(v["stencil_call"]["callee"].rsplit("_", 1)[1])])
+                yield by_id[int(v["stencil_call"]["callee"].rsplit("_", 1)[1])]
             elif kd == "block_stmt":
                 for s in v.get("statements", []):
-                    ex(s)
+                    yield from ex(s)
             elif kd == "if_stmt":
                 _, cv = _kind(v["cond_part"])
                 if ev(cv["expr"]):
-                    ex(v["then_part"])
+                    yield from ex(v["then_part"])
                 elif v.get("else_part"):
-                    ex(v["else_part"])
+                    yield from ex(v["else_part"])
             elif kd == "var_decl_stmt":
                 init = v.get("init_list", [])
                 local[v["name"]] = ev(init[0]) if init else 0.0
@@ -317,13 +351,13 @@ class CartesianRun:
                 _, lv = _kind(e2["left"])
                 rhs = ev(e2["right"])
                 op = e2.get("op", "=")
-                local[lv["name"]] = rhs if op == "=" else _BIN[op[0]](local[lv["name"]], rhs)
+                store = self.globals if lv.get("is_external", False) else local
+                store[lv["name"]] = rhs if op == "=" else _BIN[op[0]](store[lv["name"]], rhs)
             else:
                 raise NotImplementedError("control flow statement " + kd)
 
         for s in flow:
-            ex(s)
-        return seq
+            yield from ex(s)
 
     def _run_ms(self, ms, stages, s_exts):
         backward = ms.get("loopOrder", "Forward") == "Backward"
