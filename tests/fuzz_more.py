@@ -3,7 +3,7 @@ tools/make_fuzz_ico.py) compared bit for bit with the oracle.  The IIR files and
 generated and compiled in the build container first (see the header of DESIGN.md section 6); failing
 seeds become committed fixtures.  Test infrastructure: uses oracle/ as the checker."""
 import sys, os
-ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in tests/)
 sys.path.insert(0,ROOT); sys.path.insert(0,ROOT+'/tests')
 import numpy as np, torch, ctypes, traceback
 import dawn_b200
