@@ -228,26 +228,5 @@ def build_reference_tree(force=False, jobs=None):
     return [e for e in entries if "module" in e]
 
 
-def build_cpp_driver(force=False):
-    """tests/cpp/hori_diff_driver.cu: a reference-style C++ driver that #includes the generated TU."""
-    from . import codegen
-    src = os.path.join(ROOT, "tests", "cpp", "hori_diff_driver.cu")
-    exe = os.path.join(LIB, "hori_diff_driver")
-    gen = os.path.join(GEN, "hori_diff_type2_stencil.cu")
-    if not os.path.exists(gen):
-        with open(os.path.join(ROOT, "stencils", "hori_diff_type2_stencil.iir")) as f:
-            code = codegen.compile_iir(f.read())
-        compile_module("hori_diff_type2_stencil", code)
-    oracle_so = os.path.join(ROOT, "oracle", "liboracle.so")
-    if not os.path.exists(oracle_so):
-        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
-    if force or _newer(exe, [src, gen, oracle_so]):
-        _run([NVCC] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-cudart", "shared",
-                              "-I", PKG, '-DGENERATED_FILE="%s"' % gen, "-o", exe, src,
-                              "-L", LIB, "-ldawn_b200rt", "-Xlinker", "-rpath,$ORIGIN",
-                              oracle_so, "-Xlinker", "-rpath," + os.path.join(ROOT, "oracle")])
-    return exe
-
-
 def clean():
     shutil.rmtree(LIB, ignore_errors=True)

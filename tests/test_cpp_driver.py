@@ -2,14 +2,18 @@
 (gtclang/test/integration-test/CodeGen/hori_diff_type2_stencil_benchmark.cpp)."""
 import os
 import subprocess
+import sys
 
 import pytest
 
 from dawn_b200 import build
 
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp"))
+from build_driver import build_cpp_driver  # noqa: E402
+
 
 def test_cpp_driver_compiles_against_generated_code():
-    exe = build.build_cpp_driver()
+    exe = build_cpp_driver()
     assert os.path.exists(exe)
 
 
@@ -18,6 +22,6 @@ def test_cpp_driver_compiles_against_generated_code():
 def test_cpp_driver_verifies_on_gpu(size):
     exe = os.path.join(build.LIB, "hori_diff_driver")
     if not os.path.exists(exe):
-        exe = build.build_cpp_driver()
+        exe = build_cpp_driver()
     r = subprocess.run([exe] + [str(x) for x in size], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "VERIFIED" in r.stdout, r.stdout + r.stderr
