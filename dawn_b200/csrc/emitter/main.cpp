@@ -4,6 +4,8 @@
 // translation unit to -o or stdout.
 //   dawn-opt x.sir | dawn-b200-codegen --backend=b200 -o x_b200.cu
 #include "codegen.hpp"
+#include "iir.hpp"
+#include "proto_wire.hpp"
 
 #include <fstream>
 #include <iostream>
@@ -12,7 +14,7 @@
 
 int main(int argc, char** argv) {
   using namespace b200::codegen;
-  std::string backend = "b200", input, output;
+  std::string backend = "b200", input, output, cHeader, f90Interface, convertTo;
   Options opts;
   auto intOpt = [&](const std::string& a, const char* name, int& dst) {
     std::string p = std::string("--") + name + "=";
@@ -27,6 +29,8 @@ int main(int argc, char** argv) {
     if(a == "-h" || a == "--help") {
       std::cout << "Usage: dawn-b200-codegen [-b|--backend b200|b200-ico] [-o out.cu] [in.iir]\n"
                    "  in.iir: serialized StencilInstantiation, proto3 JSON or protobuf bytes (auto-detected)\n"
+                   "  --output-c-header=FILE --output-f90-interface=FILE  (b200-ico) interface files\n"
+                   "  --convert=json|byte  re-serialize the IIR instead of generating code\n"
                    "  planner knobs: --block-size-i= --block-size-j= --rows-per-thread= "
                    "--block-size-k= --inline-temporaries= --fuse-columns= --unroll-k= "
                    "--levels-per-thread= --block-size-ico= --max-halo-points= --run-with-sync=\n";
@@ -37,6 +41,14 @@ int main(int argc, char** argv) {
       backend = a.substr(10);
     else if(a == "-o" && n + 1 < argc)
       output = argv[++n];
+    // reference: --output-c-header / --output-f90-interface of the cuda-ico backend
+    // (CudaIcoCodeGen.cpp:1869-1892, dawn-codegen.cpp)
+    else if(a.compare(0, 18, "--output-c-header=") == 0)
+      cHeader = a.substr(18);
+    else if(a.compare(0, 23, "--output-f90-interface=") == 0)
+      f90Interface = a.substr(23);
+    else if(a.compare(0, 10, "--convert=") == 0) // json | byte: re-serialize the IIR instead of generating code
+      convertTo = a.substr(10);
     else if(intOpt(a, "block-size-i", opts.BlockSizeI) || intOpt(a, "block-size-j", opts.BlockSizeJ) ||
             intOpt(a, "rows-per-thread", opts.RowsPerThread) ||
             intOpt(a, "block-size-k", opts.BlockSizeK) ||
@@ -71,6 +83,40 @@ int main(int argc, char** argv) {
       if(!f)
         throw std::runtime_error("cannot open " + input);
       text.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+    }
+    if(!convertTo.empty()) {
+      b200::json::Value dom = b200::proto::looksLikeJson(text)
+                                  ? b200::json::parse(text)
+                                  : b200::proto::decode(text, "StencilInstantiation");
+      if(b200::proto::looksLikeJson(text))
+        b200::proto::normalizeJson(dom, "StencilInstantiation");
+      std::string res;
+      if(convertTo == "json")
+        res = b200::json::write(dom);
+      else if(convertTo == "byte")
+        res = b200::proto::encode(dom, "StencilInstantiation");
+      else
+        throw std::runtime_error("--convert takes json or byte");
+      if(output.empty())
+        std::cout << res;
+      else {
+        std::ofstream o(output, std::ios::binary);
+        o << res;
+      }
+      return 0;
+    }
+    if(!cHeader.empty() || !f90Interface.empty()) {
+      auto inst = b200::iir::parseInstantiation(text);
+      if(!inst.unstructured)
+        throw std::runtime_error("interface files are generated for unstructured instantiations");
+      if(!cHeader.empty()) {
+        std::ofstream o(cHeader);
+        o << icoCHeader(inst);
+      }
+      if(!f90Interface.empty()) {
+        std::ofstream o(f90Interface);
+        o << icoF90Interface(inst);
+      }
     }
     auto tu = run({{"restoredIIR", text}}, parseBackendString(backend), opts);
     std::string code = tu.str();

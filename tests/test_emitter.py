@@ -330,3 +330,20 @@ def test_generated_c_header_is_valid_c(tmp_path):
     f90 = codegen.interface_text(open(iir_path("ICON_laplacian_stencil")).read(), "f90")
     assert "module ICON_laplacian_stencil_b200" in f90 and "bind(c)" in f90
     assert "set_splitter_index_ICON_laplacian_stencil" in f90
+
+
+def test_cli_interface_files_and_conversion(tmp_path):
+    """dawn-b200-codegen: --output-c-header / --output-f90-interface (cuda-ico's options) and --convert."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dawn_b200", "lib",
+                       "dawn-b200-codegen")
+    h, f90, cu = tmp_path / "s.h", tmp_path / "s.f90", tmp_path / "s.cu"
+    subprocess.run([exe, "-b", "b200-ico", "--output-c-header=%s" % h, "--output-f90-interface=%s" % f90,
+                    "-o", str(cu), iir_path("ICON_laplacian_stencil")], check=True)
+    assert "setup_ICON_laplacian_stencil" in h.read_text() and "bind(c)" in f90.read_text()
+    assert "__global__" in cu.read_text()
+    b = tmp_path / "s.iirb"
+    subprocess.run([exe, "--convert=byte", "-o", str(b), iir_path("hori_diff_type2_stencil")], check=True)
+    assert b.read_bytes() == codegen.iir_convert(open(iir_path("hori_diff_type2_stencil")).read(), "byte")
+    back = subprocess.run([exe, "--convert=json", str(b)], check=True, capture_output=True).stdout
+    assert codegen.compile_iir(back.decode()) == codegen.compile_iir(open(iir_path("hori_diff_type2_stencil")).read())
