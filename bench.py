@@ -382,7 +382,7 @@ def run_gpu(args):
         achieved = BYTES_PER_POINT[workload] * pts / (kernel_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % workload)
-        if os.path.exists(tp):
+        if os.path.exists(tp) and not args.shape:  # the committed ncu capture is of the default shape
             with open(tp) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
         line = {
@@ -397,7 +397,8 @@ def run_gpu(args):
                     "" if world == 1 else ", global %dx%dx%d in %d j-slabs, NCCL halo exchange of "
                     "`in` (2 rows each way) every step, overlapped with the interior rows" % (
                         I, J * world, K, world)),
-                "l2": "inputs larger than L2 (2.0 GB per step vs 126 MB), no flush",
+                "l2": "inputs larger than L2 (%.1f GB per step vs 126 MB), no flush" % (
+                    BYTES_PER_POINT[workload] * pts / 1e9),
                 "timing": "%d back-to-back steps; at N=1 roofline.achieved uses this same region "
                           "(a step is one kernel launch), so it is a sustained figure - see clocks" % args.steps,
                 "codegen_options": opts,
@@ -454,7 +455,14 @@ def run_icon(args):
     from dawn_b200 import runtime as rt, slabs
     sl = slabs.mesh_slab(nx, ny * world, world, rank)
     mesh = TriMesh(nx, sl.local_ny)
-    mod = dawn_b200.load_stencil("ICON_laplacian_stencil")
+    nabla4 = args.workload == "icon_nabla4"
+    stencil_name = "ICON_nabla4_stencil" if nabla4 else "ICON_laplacian_stencil"
+    passes = 2 if nabla4 else 1  # nabla4 = nabla2(nabla2(vec)): the nabla2 data flow twice
+    if nabla4 and world > 1:
+        # the slab plan below keeps one halo quad row and exchanges `vec` only; nabla4 would need a second
+        # exchange (of nabla2_vec) between its passes
+        raise SystemExit("icon_nabla4 is a 1-GPU bench line; use icon_nabla2 for the multi-GPU runs")
+    mod = dawn_b200.load_stencil(stencil_name)
     st = mod.on_mesh(mesh, K)
     t_mesh = time.perf_counter() - t0
     E, C, V = mesh.num_edges, mesh.num_cells, mesh.num_vertices
@@ -522,7 +530,7 @@ def run_icon(args):
     own = TriMesh(nx, ny)
     E, C, V = own.num_edges, own.num_cells, own.num_vertices
     units = E * K * world
-    bytes_run = K * (40 * E + 56 * V + 32 * C) + 4 * (6 * V + 3 * C + 2 * E + 2 * E)
+    bytes_run = passes * (K * (40 * E + 56 * V + 32 * C) + 4 * (6 * V + 3 * C + 2 * E + 2 * E))
     peak, peak_src = measured_peak()
     achieved = bytes_run / (ms * 1e-3) / 1e9
     line = {
@@ -530,18 +538,22 @@ def run_icon(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (uniform random fields generated on device; regular triangle mesh)",
-        "config": {"workload": "ICON_laplacian_stencil (nabla2) on TriMesh %dx%d per GPU: %d edge slots, "
+        "config": {"workload": "%s on TriMesh %dx%d per GPU: %d edge slots, "
                                "%d cells, %d vertices x %d levels%s" % (
+                                   "ICON_nabla4_stencil (nabla2 of nabla2; not in the reference, parity "
+                                   "anchored on two passes of the nabla2 oracle)" if nabla4 else
+                                   "ICON_laplacian_stencil (nabla2)",
                                    nx, ny, E, C, V, K, "" if world == 1 else
                                    "; global mesh %dx%d in %d row slabs, 1 halo quad row, NCCL exchange "
                                    "of `vec` every step" % (nx, ny * world, world)),
                    "l2": "inputs larger than L2 (%.1f GB per step), no flush" % (bytes_run / 1e9),
                    "mesh_build_s": t_mesh},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": icon_traffic(E),
+                     "frac": achieved / peak, "traffic": None if nabla4 else icon_traffic(E),
                      "kernel": "%d generated kernel launches/step (vertex and cell stages co-scheduled in "
-                               "one launch, 5 fused edge stages in the other); %.0f algorithmic "
-                               "bytes/step" % ((st.launches() - l0) // args.steps, bytes_run),
+                               "one launch, 5 fused edge stages in the other%s); %.0f algorithmic "
+                               "bytes/step" % ((st.launches() - l0) // args.steps,
+                                               ", both twice" if nabla4 else "", bytes_run),
                      "peak_source": peak_src},
         "gpu_launches": launches, "clocks": clocks,
     }
@@ -572,12 +584,16 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="hori_diff", choices=list(STENCIL) + ["icon_nabla2"])
+    ap.add_argument("--workload", default="hori_diff", choices=list(STENCIL) + ["icon_nabla2", "icon_nabla4"])
     ap.add_argument("--icon-n", type=int, default=2582, help="TriMesh nx=ny (2582 -> ~20 M edges)")
     ap.add_argument("--opt", action="append", default=[], help="codegen option key=value (sweeps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shape", default=None, help="IxJxK interior of the Cartesian workloads per GPU "
+                    "(default: the BASELINE.json config, e.g. 1024x1024x80)")
     args = ap.parse_args()
-    if args.workload == "icon_nabla2":
+    if args.shape and args.workload in SHAPE:
+        SHAPE[args.workload] = tuple(int(v) for v in args.shape.lower().split("x"))
+    if args.workload in ("icon_nabla2", "icon_nabla4"):
         if args.impl == "reference":
             print(json.dumps({"impl": "reference", "unavailable": "icon_nabla2 reference arm not wired"}))
         else:

@@ -110,6 +110,7 @@ VARIANTS = {
     "copy_stencil": [dict(shared_temporaries=1)], "nonoverlapping_stencil": [dict(shared_temporaries=1)],
     "ICON_laplacian_stencil": [dict(fuse_columns=0, levels_per_thread=1), dict(levels_per_thread=8),
                                dict(co_schedule=0)],
+    "ICON_nabla4_stencil": [dict(fuse_columns=0, levels_per_thread=1), dict(co_schedule=0)],
     "kcache_fill": [dict(column_ring=0)], "kcache_flush": [dict(column_ring=0)],
     "kcache_fill_backward": [dict(column_ring=0)], "intervals02": [dict(column_ring=0)],
     "intervals03": [dict(column_ring=0)], "kparallel_solver": [dict(column_ring=0)],

@@ -87,6 +87,28 @@ def test_icon_laplacian(nx, ny, k, opts):
     assert st.launches() == want_launches
 
 
+@pytest.mark.parametrize("nx,ny,k", [(7, 5, 3), (33, 20, 9), (64, 64, 65)])
+@pytest.mark.parametrize("opts", [dict(), dict(co_schedule=0), dict(fuse_columns=0, levels_per_thread=1)])
+def test_icon_nabla4(nx, ny, k, opts):
+    # nabla4 = nabla2(nabla2(vec)): not in the reference; the oracle side is anchored on two passes of
+    # the reference-pinned nabla2 oracle (tests/test_unstructured_oracle.py)
+    from test_unstructured_oracle import _nabla_inputs, nabla4_by_two_nabla2_passes, nabla4_oracle
+    m = TriMesh(nx, ny)
+    f = _nabla_inputs(m, k, 43)
+    f["nabla2_vec"] = np.full((k, m.num_edges), -1.0)
+    f["nabla4_vec"] = np.full((k, m.num_edges), -1.0)
+    want = nabla4_oracle(m, k, f)
+    got, st = _run("ICON_nabla4_stencil", m, k, f, **opts)
+    _check(got, want, m, {"nabla2_vec": EDGE, "nabla4_vec": EDGE})
+    if k <= 9:
+        n2, n4 = nabla4_by_two_nabla2_passes(m, k, f)
+        _check(got, {"nabla2_vec": n2, "nabla4_vec": n4}, m, {"nabla2_vec": EDGE, "nabla4_vec": EDGE})
+    # 14 stages -> 6 fused groups (vertices, cells, 5 edge stages; twice); each independent
+    # vertex/cell pair shares one launch unless co_schedule=0
+    want_launches = (6 if opts.get("fuse_columns", 1) else 14) - (2 if opts.get("co_schedule", 1) else 0)
+    assert st.launches() == want_launches
+
+
 @pytest.mark.parametrize("name,spec,outs", [
     ("diffusion", {"in_field": CELL, "out_field": CELL}, {"out_field": CELL}),
     ("gradient", {"cell_field": CELL, "edge_field": EDGE}, {"cell_field": CELL, "edge_field": EDGE}),

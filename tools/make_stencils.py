@@ -188,6 +188,42 @@ def icon_laplacian():
     return b
 
 
+def icon_nabla4():
+    # BASELINE.json configs[3] names "nabla2/nabla4" reductions; the reference holds no nabla4 stencil
+    # ("parity unpinned"): it is defined here as ICON does, nabla4 = nabla2(nabla2(vec)),
+    # i.e. the seven stages of ICON_laplacian_stencil.py:36-131 applied a second time to nabla2_vec
+    b = IIRBuilder("ICON_nabla4_stencil", grid="Unstructured")
+    vec = b.field("vec", "k", "Edge")
+    nabla2 = b.field("nabla2_vec", "k", "Edge")
+    nabla4 = b.field("nabla4_vec", "k", "Edge")
+    pel = b.field("primal_edge_length", "k", "Edge")
+    del_ = b.field("dual_edge_length", "k", "Edge")
+    tang = b.field("tangent_orientation", "k", "Edge")
+    geofac_rot = b.field("geofac_rot", "k", sparse_chain=["Vertex", "Edge"])
+    geofac_div = b.field("geofac_div", "k", sparse_chain=["Cell", "Edge"])
+    s = []
+    for n, (src, dst) in enumerate(((vec, nabla2), (nabla2, nabla4))):
+        rot = b.tmp("__tmp_rot_%d" % n, "k", "Vertex")
+        div = b.tmp("__tmp_div_%d" % n, "k", "Cell")
+        t60 = b.tmp("__tmp_nab_6%d" % (2 * n), "k", "Edge")
+        t61 = b.tmp("__tmp_nab_6%d" % (2 * n + 1), "k", "Edge")
+        s += [
+            b.stage(b.do(FULL, b.assign(rot, reduce_over(["Vertex", "Edge"], src.nbh * geofac_rot.at()))),
+                    location="Vertex"),
+            b.stage(b.do(FULL, b.assign(div, reduce_over(["Cell", "Edge"], src.nbh * geofac_div.at()))),
+                    location="Cell"),
+            b.stage(b.do(FULL, b.assign(t60, reduce_over(["Edge", "Vertex"], rot.nbh, weights=[-1.0, 1.0]))),
+                    location="Edge"),
+            b.stage(b.do(FULL, b.assign(t60, (tang.at() * t60.at()) / pel.at())), location="Edge"),
+            b.stage(b.do(FULL, b.assign(t61, reduce_over(["Edge", "Cell"], div.nbh, weights=[-1.0, 1.0]))),
+                    location="Edge"),
+            b.stage(b.do(FULL, b.assign(t61, t61.at() / del_.at())), location="Edge"),
+            b.stage(b.do(FULL, b.assign(dst, t61.at() - t60.at())), location="Edge"),
+        ]
+    b.stencil(b.multistage("Parallel", *s))
+    return b
+
+
 def unstructured_diffusion():
     # dawn/test/integration-test/unstructured/reference/reference_diffusion.hpp:31-69
     b = IIRBuilder("diffusion", grid="Unstructured")
@@ -713,6 +749,7 @@ ALL = {
     "globals_stencil": globals_stencil,
     "kparallel_solver": kparallel_solver,
     "ICON_laplacian_stencil": icon_laplacian,
+    "ICON_nabla4_stencil": icon_nabla4,
     "diffusion": unstructured_diffusion,
     "gradient": unstructured_gradient,
     "diamond": unstructured_diamond,
