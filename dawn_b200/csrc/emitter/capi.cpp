@@ -32,6 +32,7 @@ b200::codegen::Options convert(const dawn_b200_options* o) {
   r.SharedTemporaries = o->shared_temporaries;
   r.CoSchedule = o->co_schedule;
   r.RingDrain = o->ring_drain;
+  r.RingEarly = o->ring_early;
   r.IcoFullBlocks = o->ico_full_blocks;
   return r;
 }
@@ -57,6 +58,7 @@ void dawn_b200_default_options(dawn_b200_options* o) {
   o->shared_temporaries = 0;
   o->co_schedule = 1;
   o->ring_drain = 1;
+  o->ring_early = 1;
 }
 
 int dawn_b200_parse_backend(const char* s) {

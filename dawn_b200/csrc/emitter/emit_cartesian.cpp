@@ -1702,9 +1702,7 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
             << "    __threadfence_block();\n    ::dawn_b200::tma::fence_proxy_async();\n"
             << "    __syncthreads();\n";
     }
-    for(auto const& part : parts) {
-      os_ << "    { // k in [" << analysis::boundExpr(part.lo) << ", "
-          << analysis::boundExpr(part.hi) << "]\n";
+    auto emitRangeBounds = [&](const KRange& part) {
       os_ << "      int kb = " << analysis::boundExpr(part.lo)
           << ", ke = " << analysis::boundExpr(part.hi) << ";\n";
       os_ << "      kb = kb < 0 ? 0 : kb; ke = ke > kmax ? kmax : ke;\n";
@@ -1712,6 +1710,64 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         os_ << "      { const int zb = blockIdx.z * kchunk; kb = kb > zb ? kb : zb; "
                "ke = ke < zb + kchunk - 1 ? ke : zb + kchunk - 1; }\n";
       }
+    };
+    // TMA prologue of one streamed k range: the first `ahead` chunks of `fields`
+    auto emitRingIssue = [&](const std::set<int>& fields, const std::string& pad,
+                             const std::string& chunk) {
+      const int KB = kp.ringKB, S = kp.stages, NT = kp.NT();
+      const size_t bytes = fields.size() * (size_t)KB * NT * 8;
+      os_ << pad << "{\n";
+      os_ << pad << "  const unsigned ts = (tma_it + " << chunk << ") % " << S << ";\n";
+      os_ << pad << "  const int k0 = "
+          << (backward ? "ke - (" + chunk + ") * " + std::to_string(KB) + " - " + std::to_string(KB - 1)
+                       : "kb + (" + chunk + ") * " + std::to_string(KB))
+          << ";\n";
+      os_ << pad << "  ::dawn_b200::tma::expect_bytes(&tma_full[ts], " << bytes << "u);\n";
+      int fi = 0;
+      for(int f : fields) {
+        os_ << pad << "  ::dawn_b200::tma::load_3d(tma_ring + ts * " << ringSlotElems << " + "
+            << fi * KB * NT << ", &tm_" << fname(f) << ", i0, j0, k0, &tma_full[ts]);\n";
+        ++fi;
+      }
+      os_ << pad << "}\n";
+    };
+    auto emitRingPrologue = [&](const std::set<int>& fields) {
+      const int ahead = opt_.RingDrain != 0 ? kp.stages : kp.stages - 1;
+      os_ << "      const int nk_loc = ke - kb + 1;\n";
+      os_ << "      const int nch = nk_loc > 0 ? (nk_loc + " << kp.ringKB - 1 << ") / " << kp.ringKB
+          << " : 0;\n";
+      os_ << "      if(tid == 0) {\n";
+      os_ << "        for(int c = 0; c < " << ahead << " && c < nch; ++c)\n";
+      emitRingIssue(fields, "          ", "c");
+      os_ << "      }\n";
+    };
+    // ring_early: the first streamed range of the kernel's first sweep sends its TMA prologue before
+    // the short ranges that precede it run (e.g. the first level of a solver, read with plain loads
+    // whose latency would otherwise delay the block's first bulk requests).  Safe: the ranges of a
+    // partition are disjoint in k, fields are only ever written at the centre level, and ring chunks
+    // that reach past their range only overlap ranges that run later (values never used).
+    int earlyPart = -1;
+    if(kp.colring && opt_.RingEarly && ms == kp.ms.front() && writtenSoFar.empty()) {
+      for(size_t p = 0; p < parts.size(); ++p)
+        if(!streamedFields(kp, *ms, parts[p], msDepths).empty()) {
+          if(p > 0)
+            earlyPart = (int)p;
+          break;
+        }
+      if(earlyPart >= 0) {
+        os_ << "    { // TMA prologue of k range [" << analysis::boundExpr(parts[earlyPart].lo) << ", "
+            << analysis::boundExpr(parts[earlyPart].hi) << "], ahead of the ranges before it\n";
+        emitRangeBounds(parts[earlyPart]);
+        emitRingPrologue(streamedFields(kp, *ms, parts[earlyPart], msDepths));
+        os_ << "    }\n";
+      }
+    }
+    int partIdx = -1;
+    for(auto const& part : parts) {
+      ++partIdx;
+      os_ << "    { // k in [" << analysis::boundExpr(part.lo) << ", "
+          << analysis::boundExpr(part.hi) << "]\n";
+      emitRangeBounds(part);
       // ring pre-fill at the first level the multistage touches
       if(first && !be.rings.empty()) {
         os_ << "      if(" << (kp.colring ? "active && " : "") << "kb <= ke) {\n";
@@ -1857,37 +1913,21 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         }
       } else if(useRing) {
         const int KB = kp.ringKB, S = kp.stages, NT = kp.NT();
-        const size_t bytes = (size_t)be.prefetched.size() * KB * NT * 8;
         auto issue = [&](const std::string& pad, const std::string& chunk) {
-          os_ << pad << "{\n";
-          os_ << pad << "  const unsigned ts = (tma_it + " << chunk << ") % " << S << ";\n";
-          os_ << pad << "  const int k0 = "
-              << (backward ? "ke - (" + chunk + ") * " + std::to_string(KB) + " - " +
-                                 std::to_string(KB - 1)
-                           : "kb + (" + chunk + ") * " + std::to_string(KB))
-              << ";\n";
-          os_ << pad << "  ::dawn_b200::tma::expect_bytes(&tma_full[ts], " << bytes << "u);\n";
-          int fi = 0;
-          for(int f : be.prefetched) {
-            os_ << pad << "  ::dawn_b200::tma::load_3d(tma_ring + ts * " << ringSlotElems << " + "
-                << fi * KB * NT << ", &tm_" << fname(f) << ", i0, j0, k0, &tma_full[ts]);\n";
-            ++fi;
-          }
-          os_ << pad << "}\n";
+          emitRingIssue(be.prefetched, pad, chunk);
         };
-        os_ << "      const int nk_loc = ke - kb + 1;\n";
-        os_ << "      const int nch = nk_loc > 0 ? (nk_loc + " << KB - 1 << ") / " << KB << " : 0;\n";
         // ring_drain: every thread copies its column of the slot into registers as soon as the slot
         // arrives, the block synchronises and the slot is refilled at once - all S slots stay in flight
         // while the levels are computed from registers (without it a slot sits idle for the whole
         // 8-level sweep and at most S-1 are in flight: ncu showed 24 % of the warp samples waiting on
         // the full-barrier)
         const bool drain = opt_.RingDrain != 0;
-        const int ahead = drain ? S : S - 1;
-        os_ << "      if(tid == 0) {\n";
-        os_ << "        for(int c = 0; c < " << ahead << " && c < nch; ++c)\n";
-        issue("          ", "c");
-        os_ << "      }\n";
+        if(partIdx == earlyPart) {
+          os_ << "      const int nk_loc = ke - kb + 1; // prologue already issued at the top of the sweep\n";
+          os_ << "      const int nch = nk_loc > 0 ? (nk_loc + " << KB - 1 << ") / " << KB << " : 0;\n";
+        } else {
+          emitRingPrologue(be.prefetched);
+        }
         os_ << "      for(int ch = 0; ch < nch; ++ch) {\n";
         if(!drain) {
           os_ << "        if(tid == 0 && ch + " << S - 1 << " < nch)\n";

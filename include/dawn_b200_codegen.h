@@ -62,6 +62,8 @@ typedef struct dawn_b200_options {
   int ring_drain;         /* default 1: column-ring kernels drain an arrived slot into registers and refill
                              it at once (all slots in flight during the sweep); 2: TMA tile kernels with one
                              live stage also refill right after their hoisted loads */
+  int ring_early;         /* default 1: the first TMA prologue of a column-ring kernel is issued at kernel
+                             start, ahead of the short k ranges that precede the streamed range */
   int ico_full_blocks;    /* default 0: unstructured kernels run full blocks of levels through an unrolled
                              loop without per-level bound checks (more loads in flight per thread) */
 } dawn_b200_options;

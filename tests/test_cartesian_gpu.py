@@ -76,7 +76,7 @@ def test_tridiagonal_solve(I, J, K):
     assert bit_equal(got["c"], want["c"])
 
 
-@pytest.mark.parametrize("opts", [dict(fuse_columns=0), dict(column_ring=0),
+@pytest.mark.parametrize("opts", [dict(fuse_columns=0), dict(column_ring=0), dict(ring_early=0),
                                   dict(column_ring=0, column_cache=1, prefetch_k=3),
                                   dict(ring_levels=2, tma_stages=2),
                                   dict(block_size_i=32, block_size_j=2)])
