@@ -119,7 +119,7 @@ VARIANTS = {
         "intervals_stencil", "intervals01", "kcache_fill_kparallel", "kcache_epflush", "lap",
         "hori_diff_stencil_02", "hd_smagorinsky_stencil", "p_grad_c")},
     **{"fuzz_%02d" % n: [dict(use_tma=0, inline_temporaries=0)] for n in range(16)},
-    "tridiagonal_solve": [dict(ring_early=0), dict(ring_drain=0), dict(ring_drain=1, tma_stages=2), dict(ring_drain=1, tma_stages=4),
+    "tridiagonal_solve": [dict(ring_early=0), dict(ring_stagger=-1), dict(ring_drain=0), dict(ring_drain=1, tma_stages=2), dict(ring_drain=1, tma_stages=4),
                           dict(ring_drain=1, ring_levels=4, tma_stages=4), dict(fuse_columns=0), dict(column_ring=0), dict(column_ring=0, column_cache=1, prefetch_k=3),
                           dict(ring_levels=2, tma_stages=2), dict(block_size_i=32, block_size_j=2)],
 }

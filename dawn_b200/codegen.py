@@ -33,7 +33,7 @@ class _Options(ctypes.Structure):
         "domain_size_j", "domain_size_k", "run_with_sync", "block_size_i", "block_size_j",
         "rows_per_thread", "block_size_k", "inline_temporaries", "fuse_columns", "unroll_k",
         "levels_per_thread", "block_size_ico", "use_tma", "tma_stages", "column_cache", "column_ring", "ring_levels", "prefetch_k", "cols_per_thread",
-        "shared_temporaries", "co_schedule", "ring_drain", "ring_early",
+        "shared_temporaries", "co_schedule", "ring_drain", "ring_early", "ring_stagger",
         "ico_full_blocks")]
 
 

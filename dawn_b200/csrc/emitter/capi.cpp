@@ -33,6 +33,7 @@ b200::codegen::Options convert(const dawn_b200_options* o) {
   r.CoSchedule = o->co_schedule;
   r.RingDrain = o->ring_drain;
   r.RingEarly = o->ring_early;
+  r.RingStagger = o->ring_stagger;
   r.IcoFullBlocks = o->ico_full_blocks;
   return r;
 }

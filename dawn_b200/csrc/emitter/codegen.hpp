@@ -34,6 +34,7 @@ struct Options {
   int RowsPerThread = 0;  // consecutive j rows computed by one thread (register micro-tile)
   int ColsPerThread = 0;  // consecutive i columns per thread (1 or 2; plain-tile kernels only)
   int IcoFullBlocks = 0;   // unstructured: full level blocks run an unrolled loop without per-level bound checks
+  int RingStagger = 0;     // ns of start delay per phase for first-wave blocks of column-ring kernels (-1: env)
   int RingEarly = 1;       // column-ring kernels issue their first TMA prologue at kernel start
   int RingDrain = 1;       // column-ring kernels copy a slot to registers on arrival and refill it at once
   int CoSchedule = 1;      // unstructured: independent groups gathering a common field share a launch

@@ -1542,6 +1542,9 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
     os_ << ",\n    const __grid_constant__ CUtensorMap tm_" << fname(sg.field);
   for(int f : kp.ringFields)
     os_ << ",\n    const __grid_constant__ CUtensorMap tm_" << fname(f);
+  const bool stagger = kp.colring && opt_.RingStagger != 0;
+  if(stagger)
+    os_ << ",\n    const int stagger_cycles, const int stagger_phases, const int stagger_blocks";
   os_ << ") {\n";
   os_ << "  const int tid = threadIdx.x;\n";
   os_ << "  const int i0 = blockIdx.x * " << kp.TI << ";\n";
@@ -1566,7 +1569,19 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
     os_ << "  if(tid == 0) {\n";
     os_ << "    for(int s = 0; s < " << kp.stages << "; ++s)\n"
         << "      ::dawn_b200::tma::barrier_init(&tma_full[s], 1);\n";
-    os_ << "    ::dawn_b200::tma::fence_barrier_init();\n  }\n";
+    os_ << "    ::dawn_b200::tma::fence_barrier_init();\n";
+    if(stagger) {
+      // ring_stagger: the blocks of the first wave start their sweeps out of phase.  Left alone they
+      // all stream their forward sweep together and then all run their (L2-fed) backward sweep
+      // together, and HBM idles during the latter; blocks that share the bandwidth equally stay in
+      // lock-step for many waves.
+      os_ << "    const int lin = blockIdx.x + gridDim.x * blockIdx.y;\n";
+      os_ << "    if(stagger_cycles > 0 && lin < stagger_blocks) {\n";
+      os_ << "      const long long t_end = clock64() + (long long)(lin % stagger_phases) * stagger_cycles;\n";
+      os_ << "      while(clock64() < t_end)\n        __nanosleep(100);\n";
+      os_ << "    }\n";
+    }
+    os_ << "  }\n";
     os_ << "  __syncthreads();\n";
     os_ << "  unsigned tma_it = 0; // k iterations consumed so far: stage = it % " << kp.stages
         << ", parity = (it / " << kp.stages << ") & 1\n";
@@ -2413,6 +2428,28 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
             << "), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);\n";
         os_ << pad << "  smem_set = true;\n" << pad << "}\n";
       }
+      const bool stagger = kp.colring && opt_.RingStagger != 0;
+      if(stagger) {
+        os_ << pad << "static int stagger_phases = 0, stagger_blocks = 0, stagger_mhz = 0;\n";
+        os_ << pad << "if(!stagger_phases) {\n";
+        os_ << pad << "  int dev = 0, sms = 0, occ = 0;\n";
+        os_ << pad << "  cudaGetDevice(&dev);\n";
+        os_ << pad << "  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);\n";
+        os_ << pad << "  cudaDeviceGetAttribute(&stagger_mhz, cudaDevAttrClockRate, dev); stagger_mhz /= 1000;\n";
+        os_ << pad << "  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, " << kp.name << ", "
+            << kp.NT() << ", " << smem << ");\n";
+        os_ << pad << "  stagger_phases = occ > 0 ? occ : 1;\n";
+        os_ << pad << "  stagger_blocks = stagger_phases * sms;\n";
+        os_ << pad << "}\n";
+        if(opt_.RingStagger < 0) {
+          os_ << pad << "const char* stagger_env = getenv(\"DAWN_B200_STAGGER_NS\"); // probing only\n";
+          os_ << pad << "const int stagger_ns = stagger_env ? atoi(stagger_env) : 0;\n";
+          os_ << pad << "if(const char* pe = getenv(\"DAWN_B200_STAGGER_PHASES\")) stagger_phases = atoi(pe) > 0 ? atoi(pe) : stagger_phases;\n";
+        } else {
+          os_ << pad << "const int stagger_ns = " << opt_.RingStagger << ";\n";
+        }
+        os_ << pad << "const int stagger_cycles = (int)((long long)stagger_ns * stagger_mhz / 1000);\n";
+      }
       os_ << pad << kp.name << "<<<grid, " << kp.NT() << ", "
           << (smemExpr.empty() ? std::to_string(smem) : smemExpr) << ", stream>>>(";
       if(kp.usesGlobals)
@@ -2447,6 +2484,8 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
         os_ << ", tm_" << fname(sg.field);
       for(int f : kp.ringFields)
         os_ << ", tm_" << fname(f);
+      if(stagger)
+        os_ << ", stagger_cycles, stagger_phases, stagger_blocks";
       os_ << ");\n";
       os_ << pad << "++m_launches;\n";
     };

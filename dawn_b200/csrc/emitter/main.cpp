@@ -62,7 +62,7 @@ int main(int argc, char** argv) {
             intOpt(a, "cols-per-thread", opts.ColsPerThread) ||
             intOpt(a, "shared-temporaries", opts.SharedTemporaries) ||
             intOpt(a, "co-schedule", opts.CoSchedule) || intOpt(a, "ring-drain", opts.RingDrain) ||
-            intOpt(a, "ring-early", opts.RingEarly) ||
+            intOpt(a, "ring-early", opts.RingEarly) || intOpt(a, "ring-stagger", opts.RingStagger) ||
             intOpt(a, "ico-full-blocks", opts.IcoFullBlocks) ||
             intOpt(a, "max-blocks-sm", opts.MaxBlocksPerSM) ||
             intOpt(a, "max-halo-points", opts.MaxHaloSize)) {

@@ -64,6 +64,9 @@ typedef struct dawn_b200_options {
                              live stage also refill right after their hoisted loads */
   int ring_early;         /* default 1: the first TMA prologue of a column-ring kernel is issued at kernel
                              start, ahead of the short k ranges that precede the streamed range */
+  int ring_stagger;       /* default 0; N > 0: the first-wave blocks of a column-ring kernel delay their start by
+                             (block % resident blocks per SM) * N ns so that their forward (HBM-fed) and
+                             backward (L2-fed) sweeps interleave; -1: N from $DAWN_B200_STAGGER_NS (probing) */
   int ico_full_blocks;    /* default 0: unstructured kernels run full blocks of levels through an unrolled
                              loop without per-level bound checks (more loads in flight per thread) */
 } dawn_b200_options;
