@@ -347,3 +347,43 @@ def test_cli_interface_files_and_conversion(tmp_path):
     assert b.read_bytes() == codegen.iir_convert(open(iir_path("hori_diff_type2_stencil")).read(), "byte")
     back = subprocess.run([exe, "--convert=json", str(b)], check=True, capture_output=True).stdout
     assert codegen.compile_iir(back.decode()) == codegen.compile_iir(open(iir_path("hori_diff_type2_stencil")).read())
+
+
+def _ring_kernel(code):
+    start = code.index("_ring_kernel(")
+    return code[start:code.index("\n}\n", start)]
+
+
+def test_column_ring_issues_its_first_prologue_at_kernel_start():
+    # tridiagonal_solve: level 0 is its own k range (plain loads); the ring range [1, kmax] must have its
+    # TMA prologue in flight before that range runs, and must not issue it a second time
+    body = _ring_kernel(_code("tridiagonal_solve"))
+    early = body.index("TMA prologue of k range [kmin + 1, kmax + 0], ahead of the ranges before it")
+    assert early < body.index("{ // k in [kmin + 0, kmin + 0]") < body.index("{ // k in [kmin + 1, kmax + 0]")
+    fwd = body[:body.index("(Backward)")]
+    assert fwd.count("for(int c = 0; c < 4 && c < nch; ++c)") == 1
+    assert "prologue already issued at the top of the sweep" in fwd
+    # the backward sweep streams what the forward sweep stored: its prologue stays behind the proxy fence
+    bwd = body[body.index("(Backward)"):]
+    assert bwd.index("fence_proxy_async") < bwd.index("for(int c = 0; c < 4 && c < nch; ++c)")
+    old = _ring_kernel(_code("tridiagonal_solve", ring_early=0))
+    assert "ahead of the ranges before it" not in old
+    assert old.index("{ // k in [kmin + 0, kmin + 0]") < old.index("for(int c = 0; c < 4 && c < nch; ++c)")
+
+
+def test_ring_stagger_is_off_by_default():
+    assert "stagger" not in _code("tridiagonal_solve")
+    code = _code("tridiagonal_solve", ring_stagger=3000)
+    assert "const int stagger_ns = 3000;" in code and "stagger_cycles, stagger_phases, stagger_blocks" in code
+
+
+def test_icon_nabla4_plan():
+    # nabla2 applied twice: (vertices | cells) co-scheduled + 5 fused edge stages, both twice; the second
+    # vertex/cell launch gathers nabla2_vec, which the first edge kernel must therefore store
+    code = _code("ICON_nabla4_stencil", backend="b200-ico")
+    heads = re.findall(r"^// kernel .*$", code, flags=re.M)
+    assert len(heads) == 4
+    assert "co-scheduled" in heads[0] and "co-scheduled" in heads[2]
+    assert "5 fused stage(s) on edges" in heads[1] and "5 fused stage(s) on edges" in heads[3]
+    for t in ("__tmp_nab_60", "__tmp_nab_61", "__tmp_nab_62", "__tmp_nab_63"):
+        assert t + "_p" not in code  # edge temporaries never leave registers
