@@ -557,6 +557,11 @@ def run_icon(args):
                      "peak_source": peak_src},
         "gpu_launches": launches, "clocks": clocks,
     }
+    if rank == 0 and world == 1 and not nabla4 and not args.no_cpu_baseline:
+        r = icon_reference(64, K, 3, 1)
+        if r is not None:
+            line["cpu_baseline"] = {"value": r[0], "unit": "edge-level updates/s", "cores": 1,
+                                    "kind": "reference", "sample": r[2]}
     if rank == 0:
         print(json.dumps(line))
     if plan is not None:
@@ -564,6 +569,44 @@ def run_icon(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def icon_reference(nx, K, reps, warm):
+    """The reference's own generated naive-ico nabla2 (ICON_laplacian_stencil_ref.cpp, compiled unmodified
+    into oracle/_ref) on the toylib mesh, single thread as the naive backend runs: (updates/s, ms per
+    run, sample text) or None if oracle/_ref is not there."""
+    from oracle import capi
+    r = capi.icon_laplacian_reference_timed(nx, nx, K, warm + reps)
+    if r is None:
+        return None
+    ne, t = r
+    t = sorted(t[warm:])
+    med = t[len(t) // 2]
+    return ne * K / med, med * 1e3, (
+        "ICON_laplacian_stencil_ref.cpp (reference's generated naive-ico code, unmodified) on a toylib "
+        "%dx%d mesh: %d edges x %d levels per run, %d warm-up + %d timed runs, median %.2f s; "
+        "g++ -O2 -ffp-contract=off" % (nx, nx, ne, K, warm, reps, med))
+
+
+def run_icon_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, nx = 65, 64
+    r = icon_reference(nx, K, max(1, args.steps), max(0, args.warmup))
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference naive-ico build) missing"}))
+        return
+    val, ms, sample = r
+    print(json.dumps({
+        "impl": "reference", "metric": "edge-level updates/s", "value": val, "unit": "edge-level updates/s",
+        "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(0, args.warmup), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "ICON_laplacian_stencil (nabla2), reference naive-ico code on host cores"},
+        "cpu_baseline": {"value": val, "unit": "edge-level updates/s", "cores": 1, "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": "edge-level updates/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
 
 def icon_traffic(num_edges):
@@ -594,8 +637,10 @@ def main():
     if args.shape and args.workload in SHAPE:
         SHAPE[args.workload] = tuple(int(v) for v in args.shape.lower().split("x"))
     if args.workload in ("icon_nabla2", "icon_nabla4"):
-        if args.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "icon_nabla2 reference arm not wired"}))
+        if args.impl == "reference" and args.workload == "icon_nabla2":
+            run_icon_reference(args)
+        elif args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference has no nabla4 stencil"}))
         else:
             run_icon(args)
     elif args.impl == "reference":

@@ -119,3 +119,15 @@ def tutorial_laplacian(out, inn, dx, nk, halo=3):
     lib().oracle_tutorial_laplacian(ni, nj, nk, halo, ctypes.c_size_t(ni), ctypes.c_double(dx),
                                     _ptr(out), _ptr(inn))
     return out
+
+
+def icon_laplacian_reference_timed(nx, ny, k_size, reps):
+    """Wall time of `reps` calls of run() of the reference's generated naive-ico nabla2
+    (ICON_laplacian_stencil_ref.cpp on toylib, oracle/_ref); returns (valid edges, seconds[reps]) or
+    None when oracle/_ref was never built."""
+    R = ref()
+    if R is None or not hasattr(R, "ref_icon_laplacian_timed"):
+        return None
+    t = np.zeros(reps)
+    ne = R.ref_icon_laplacian_timed(nx, ny, k_size, reps, _ptr(t))
+    return (ne, t) if ne > 0 else None

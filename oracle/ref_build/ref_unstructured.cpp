@@ -11,6 +11,7 @@
 // (edges: id in the all_edges() slot numbering, invalid slots simply unused); sparse fields are
 // [k][n][sparse].
 #include <cassert>
+#include <chrono>
 #include <cstring>
 #include <vector>
 
@@ -235,5 +236,43 @@ int ref_icon_laplacian(int nx, int ny, int k_size, const double* vec, double* di
   store(fnab, nabla2_vec, ne);
   toylibInterface::g_current_grid = nullptr;
   return 0;
+}
+
+// CPU baseline of bench.py's ICON workload: the reference's generated naive-ico nabla2 exactly as it
+// ships (single thread, toylib mesh), `reps` calls of run() timed on their own - mesh construction and
+// field set-up stay outside.  Returns the number of edges (negative on failure); seconds[r] = wall
+// time of call r.  Edge count = valid edges, the unit of bench.py's metric.
+int ref_icon_laplacian_timed(int nx, int ny, int k_size, int reps, double* seconds) {
+  auto g = make_grid(nx, ny, 0, 0, 0);
+  toylibInterface::g_current_grid = &g;
+  toylib::EdgeData<double> fvec(g, k_size), fnab(g, k_size), fpel(g, k_size), fdel(g, k_size),
+      ftan(g, k_size);
+  toylib::FaceData<double> fdiv(g, k_size);
+  toylib::VertexData<double> frot(g, k_size);
+  toylib::SparseVertexData<double> grot(g, 6, k_size);
+  toylib::SparseFaceData<double> gdiv(g, 3, k_size);
+  for(int k = 0; k < k_size; ++k) {
+    for(toylib::Edge const& e : g.edges()) {
+      fvec(e, k) = 1.0 + 1e-3 * (e.id() % 97) + 1e-2 * k;
+      fpel(e, k) = 1.0 + 1e-3 * (e.id() % 89);
+      fdel(e, k) = 1.0 + 1e-3 * (e.id() % 83);
+      ftan(e, k) = (e.id() & 1) ? 1.0 : -1.0;
+    }
+    for(auto const& v : g.vertices())
+      for(int s = 0; s < 6; ++s)
+        grot(v, s, k) = 0.1 * (s + 1);
+    for(auto const& f : g.faces())
+      for(int s = 0; s < 3; ++s)
+        gdiv(f, s, k) = 0.2 * (s + 1);
+  }
+  dawn_generated::cxxnaiveico::ICON_laplacian_stencil<toylibTag> st(
+      g, k_size, fvec, fdiv, frot, fnab, fpel, fdel, ftan, grot, gdiv);
+  for(int r = 0; r < reps; ++r) {
+    auto t0 = std::chrono::steady_clock::now();
+    st.run();
+    seconds[r] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  toylibInterface::g_current_grid = nullptr;
+  return (int)g.edges().size();
 }
 }

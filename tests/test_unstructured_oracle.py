@@ -199,3 +199,12 @@ def test_nabla4_is_nabla2_applied_twice(nx, ny, k):
     v = m.valid(EDGE)
     assert bit_equal(w["nabla2_vec"][:, v], n2[:, v])
     assert bit_equal(w["nabla4_vec"][:, v], n4[:, v])
+
+
+@needs_ref
+def test_timed_reference_entry_counts_valid_edges():
+    # bench.py's ICON cpu_baseline / reference arm: unit of work = valid edges x levels
+    r = capi.icon_laplacian_reference_timed(8, 6, 3, 2)
+    assert r is not None
+    ne, t = r
+    assert ne == int(TriMesh(8, 6).edge_valid.sum()) and len(t) == 2 and (t > 0).all()
