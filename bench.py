@@ -354,8 +354,10 @@ def run_gpu(args):
 
     # ---- end to end through the public API with HOST buffers --------------------------------------
     e2e_steps = min(args.steps, 5)
-    host = [torch.empty(s.shape[2], s.shape[1], s.shape[0], dtype=torch.float64).pin_memory()
-            for s in fields]
+    from dawn_b200 import runtime as rt_
+    with rt_.near_device(local) as near:  # pinned staging buffers on the GPU's own NUMA node
+        host = [torch.empty(s.shape[2], s.shape[1], s.shape[0], dtype=torch.float64).pin_memory()
+                for s in fields]
     for h, s in zip(host, fields):
         h.copy_(s.view())
     st2 = mod(dom)
@@ -413,6 +415,7 @@ def run_gpu(args):
             },
             "e2e": {"value": pts * world * e2e_steps / e2e_s, "unit": "grid-point updates/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "numa_local_host_buffers": bool(near.cpus),
                     "api": "dawn_b200.Stencil.run_from_host(pinned host buffers, upload_outputs=False, "
                            "k_chunk=8): inputs H2D + result D2H every step, pipelined over k chunks"},
             "gpu_launches": launches,

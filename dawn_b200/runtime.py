@@ -131,3 +131,47 @@ class MetricsRecord:
             self.close()
         except Exception:
             pass
+
+
+def device_numa_cpus(device_index):
+    """CPUs of the NUMA node the GPU hangs off (PCI bus id -> sysfs), intersected with what this
+    process may run on; None when the platform does not say (no NUMA information, container mask)."""
+    import torch
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except (OSError, ValueError, AttributeError, RuntimeError, AssertionError):
+        return None
+
+
+class near_device:
+    """Context manager: runs the enclosed host code on the CPUs next to the GPU, so that host buffers
+    allocated (first touched, pinned) inside are local to the socket the GPU's PCIe link belongs to.
+    With one process per GPU on a two-socket box this keeps every rank's staging traffic off the
+    inter-socket link.  A no-op where the platform exposes no NUMA topology."""
+
+    def __init__(self, device_index):
+        self.cpus = device_numa_cpus(device_index)
+        self.saved = None
+
+    def __enter__(self):
+        if self.cpus:
+            self.saved = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, self.cpus)
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            os.sched_setaffinity(0, self.saved)
+        return False

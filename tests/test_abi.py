@@ -87,3 +87,17 @@ def test_metrics_record_has_the_reference_json_shape():
         rec.write(f.name)
         assert json.load(open(f.name)) == d
     rec.close()
+
+
+def test_near_device_is_a_no_op_without_numa_information():
+    # no GPU here: the topology lookup must give up quietly and leave the affinity mask alone
+    import os
+    import torch
+    from dawn_b200 import runtime as rt
+    if torch.cuda.is_available():
+        pytest.skip("a GPU box may well know its topology")
+    before = os.sched_getaffinity(0)
+    assert rt.device_numa_cpus(0) is None
+    with rt.near_device(0) as near:
+        assert near.cpus is None and os.sched_getaffinity(0) == before
+    assert os.sched_getaffinity(0) == before
