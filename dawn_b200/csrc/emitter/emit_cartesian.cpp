@@ -2418,15 +2418,19 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
       if(kp.colring)
         smem = 128 + (size_t)kp.stages * kp.ringMaxFields * kp.ringKB * kp.NT() * 8;
       if(kp.tma || kp.colring) {
-        os_ << pad << "static bool smem_set = false;\n";
-        os_ << pad << "if(!smem_set) {\n";
+        // function attributes are per device: a host that drives several GPUs from one process sets
+        // them once on each
+        os_ << pad << "static unsigned long long smem_set = 0ull;\n";
+        os_ << pad << "int smem_dev = 0;\n";
+        os_ << pad << "cudaGetDevice(&smem_dev);\n";
+        os_ << pad << "if(!((smem_set >> (smem_dev & 63)) & 1ull)) {\n";
         os_ << pad << "  cudaError_t ae = cudaFuncSetAttribute(reinterpret_cast<const void*>(&" << kp.name
             << "), cudaFuncAttributeMaxDynamicSharedMemorySize, " << smem << ");\n";
         os_ << pad << "  if(ae != cudaSuccess) return ::dawn_b200::set_error(B200_ERR_CUDA, "
             << "cudaGetErrorString(ae));\n";
         os_ << pad << "  cudaFuncSetAttribute(reinterpret_cast<const void*>(&" << kp.name
             << "), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);\n";
-        os_ << pad << "  smem_set = true;\n" << pad << "}\n";
+        os_ << pad << "  smem_set |= 1ull << (smem_dev & 63);\n" << pad << "}\n";
       }
       const bool stagger = kp.colring && opt_.RingStagger != 0;
       if(stagger) {
@@ -2518,7 +2522,10 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
         os_ << "        const size_t cc_bytes = (size_t)" << cc->carried.size() << " * nz * "
             << cc->NT() << " * sizeof(::dawn::float_type);\n";
         os_ << "        if(m_use_colcache && cc_bytes <= 200 * 1024) {\n";
-        os_ << "          static size_t cc_set = 0;\n";
+        os_ << "          static size_t cc_set_dev[64] = {};\n";
+        os_ << "          int cc_dev = 0;\n";
+        os_ << "          cudaGetDevice(&cc_dev);\n";
+        os_ << "          size_t& cc_set = cc_set_dev[cc_dev & 63];\n";
         os_ << "          if(cc_bytes > cc_set) {\n";
         os_ << "            cudaFuncSetAttribute(reinterpret_cast<const void*>(&" << cc->name
             << "), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);\n";
