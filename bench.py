@@ -145,8 +145,12 @@ def run_reference(args):
         return
     workload = args.workload
     I, J, K = SHAPE[workload]
-    Ks = min(K, 16)  # bounded sample per step: the first 16 levels of the domain
-    threads = os.cpu_count() or 1
+    # every host thread this process may use; the hori_diff sample is split over k, so it takes at least
+    # as many levels as there are threads (bounded sample: 16 levels on a 16-thread host, never > K)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    Ks = min(K, max(16, threads))
+    if workload == "hori_diff":
+        threads = min(threads, Ks)
     f = cpu_inputs(workload, I, J, Ks)
     for _ in range(args.warmup):
         cpu_run(workload, f, Ks, threads)
