@@ -270,6 +270,14 @@ def run_gpu(args):
                     ctypes.byref(plan), comm, rank, world, ni, nj, K, s.stride_j, s.stride_k, HALO,
                     jm, jp))
                 plans.append((plan, s))
+        if args.halo == "p2p":
+            def gather(b):
+                out = [None] * world
+                dist.all_gather_object(out, b)
+                return out
+            for plan, _ in plans:
+                rt.connect_halo_plan(plan, rank, world, gather)
+            dist.barrier()
 
     stream = torch.cuda.current_stream().cuda_stream
     launches_per_step = [0]
@@ -292,9 +300,14 @@ def run_gpu(args):
         comm_stream.wait_event(ev_ready)
         n = 0
         for plan, s in plans:
-            rt.check(rt.lib().b200rt_halo_exchange(plan, s.buf.data_ptr() + 8 * s.lead,
-                                                   comm_stream.cuda_stream))
-            n += (2 if rank > 0 else 0) + (2 if rank + 1 < world else 0)
+            if args.halo == "p2p":  # pack + NVLink stores in one kernel, wait + unpack in a second one
+                rt.check(rt.lib().b200rt_halo_exchange_p2p(plan, s.buf.data_ptr() + 8 * s.lead,
+                                                           comm_stream.cuda_stream))
+                n += 2
+            else:
+                rt.check(rt.lib().b200rt_halo_exchange(plan, s.buf.data_ptr() + 8 * s.lead,
+                                                       comm_stream.cuda_stream))
+                n += (2 if rank > 0 else 0) + (2 if rank + 1 < world else 0)
         lo = dep_lo if rank > 0 else 0
         hi = J - (dep_hi if rank + 1 < world else 0)
         # boundary strips follow the exchange on the (high-priority) communication stream ...
@@ -334,6 +347,9 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     launches = (st.launches() - l0) + launches_per_step[0] * args.steps
+    if args.halo == "p2p":
+        for plan, _ in plans:  # a wait that gave up means halos were stale: not a valid run
+            rt.check(rt.lib().b200rt_halo_plan_p2p_status(plan))
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -400,9 +416,11 @@ def run_gpu(args):
             "config": {
                 "workload": "%s %dx%dx%d double per GPU (halo 3, storages %dx%dx%d)%s" % (
                     name, I, J, K, ni, nj, K + 1,
-                    "" if world == 1 else ", global %dx%dx%d in %d j-slabs, NCCL halo exchange of "
+                    "" if world == 1 else ", global %dx%dx%d in %d j-slabs, %s halo exchange of "
                     "`in` (2 rows each way) every step, overlapped with the interior rows" % (
-                        I, J * world, K, world)),
+                        I, J * world, K, world,
+                        "peer-memory (NVLink stores into the neighbour's landing buffer, device-side "
+                        "flags)" if args.halo == "p2p" else "NCCL")),
                 "l2": "inputs larger than L2 (%.1f GB per step vs 126 MB), no flush" % (
                     BYTES_PER_POINT[workload] * pts / 1e9),
                 "timing": "%d back-to-back steps; at N=1 roofline.achieved uses this same region "
@@ -638,6 +656,8 @@ def main():
     ap.add_argument("--icon-n", type=int, default=2582, help="TriMesh nx=ny (2582 -> ~20 M edges)")
     ap.add_argument("--opt", action="append", default=[], help="codegen option key=value (sweeps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"],
+                    help="multi-GPU halo exchange: pack -> ncclSend/Recv -> unpack, or peer-memory stores")
     ap.add_argument("--shape", default=None, help="IxJxK interior of the Cartesian workloads per GPU "
                     "(default: the BASELINE.json config, e.g. 1024x1024x80)")
     args = ap.parse_args()

@@ -316,6 +316,128 @@ halo_pack_kernel(const double* __restrict__ field, double* __restrict__ buf, int
       buf[idx] = __ldg(&field[f]);
   }
 }
+
+// ---- peer-memory halo exchange: flags at the head of every plan's IPC-shared arena ----------------
+// (one 32-byte sector each; epochs count exchanges from 1)
+enum : int {
+  HF_ARRIVED_LO = 0,    // written by rank-1: its push of this epoch has landed in my recv_lo
+  HF_ARRIVED_HI = 4,    // written by rank+1: ... in my recv_hi
+  HF_CREDIT_LO = 8,     // written by rank-1: it has consumed its recv_hi up to epoch-1, push `epoch` may go
+  HF_CREDIT_HI = 12,    // written by rank+1: same for its recv_lo
+  HF_PUSH_EPOCH = 16,   // local: epoch of the next push
+  HF_UNPACK_EPOCH = 20, // local: epoch of the next unpack
+  HF_PUSH_DONE = 24,    // local: blocks of the running push kernel that have finished
+  HF_UNPACK_DONE = 28,
+  HF_ERROR = 32,        // local: a wait ran into its time limit (the neighbour never showed up)
+  HF_WORDS = 64
+};
+constexpr long long kSpinLimitCycles = 20ll << 30; // ~11 s at 2 GHz: never hang the device on a lost peer
+
+__device__ __forceinline__ void spin_until(volatile unsigned long long* flag, unsigned long long want,
+                                           unsigned long long* err) {
+  const long long t0 = clock64();
+  while(*flag < want) {
+    __nanosleep(40);
+    if(clock64() - t0 > kSpinLimitCycles) {
+      atomicExch(err, 1ull);
+      return;
+    }
+  }
+}
+
+// Pack + transfer in one kernel: the boundary rows of my slab are stored straight into the landing
+// buffers of the slab neighbours (peer memory over NVLink), then the last block raises `arrived` there.
+__global__ void __launch_bounds__(256)
+halo_push_kernel(const double* __restrict__ field, unsigned long long* my, double* peer_lo_buf,
+                 unsigned long long* peer_lo_flags, double* peer_hi_buf,
+                 unsigned long long* peer_hi_flags, int ni, int nk, int sj, int sk, int j_lo_first,
+                 int rows_lo, int j_hi_first, int rows_hi) {
+  volatile unsigned long long* vmy = my;
+  const unsigned long long epoch = vmy[HF_PUSH_EPOCH];
+  if(threadIdx.x == 0) {
+    // the neighbour must be done reading what the previous push left in its landing buffer
+    if(peer_lo_buf)
+      spin_until(&vmy[HF_CREDIT_LO], epoch, &my[HF_ERROR]);
+    if(peer_hi_buf)
+      spin_until(&vmy[HF_CREDIT_HI], epoch, &my[HF_ERROR]);
+  }
+  __syncthreads();
+  const size_t total_lo = peer_lo_buf ? (size_t)ni * rows_lo * nk : 0;
+  const size_t total_hi = peer_hi_buf ? (size_t)ni * rows_hi * nk : 0;
+  for(size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total_lo + total_hi;
+      idx += (size_t)gridDim.x * blockDim.x) {
+    const bool lo = idx < total_lo;
+    const size_t e = lo ? idx : idx - total_lo;
+    const int rows = lo ? rows_lo : rows_hi;
+    const int i = (int)(e % ni);
+    const int r = (int)((e / ni) % rows);
+    const int k = (int)(e / ((size_t)ni * rows));
+    const size_t f = (size_t)i + (size_t)((lo ? j_lo_first : j_hi_first) + r) * sj + (size_t)k * sk;
+    (lo ? peer_lo_buf : peer_hi_buf)[e] = __ldg(&field[f]);
+  }
+  __threadfence_system(); // my peer stores are visible system-wide before this block counts as done
+  __syncthreads();
+  if(threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(reinterpret_cast<unsigned*>(&my[HF_PUSH_DONE]), 1u);
+    if(prev == gridDim.x - 1) {
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned*>(&my[HF_PUSH_DONE]) = 0u;
+      vmy[HF_PUSH_EPOCH] = epoch + 1;
+      if(peer_lo_flags) // I am the HIGH neighbour of rank-1
+        *static_cast<volatile unsigned long long*>(&peer_lo_flags[HF_ARRIVED_HI]) = epoch;
+      if(peer_hi_flags)
+        *static_cast<volatile unsigned long long*>(&peer_hi_flags[HF_ARRIVED_LO]) = epoch;
+      __threadfence_system();
+    }
+  }
+}
+
+// Waits for the neighbours' rows of this epoch, moves them from the landing buffers into the halo rows
+// of the field, then tells the neighbours that the buffers are free again.
+__global__ void __launch_bounds__(256)
+halo_unpack_p2p_kernel(double* __restrict__ field, unsigned long long* my, const double* recv_lo,
+                       const double* recv_hi, unsigned long long* peer_lo_flags,
+                       unsigned long long* peer_hi_flags, int ni, int nk, int sj, int sk,
+                       int j_lo_first, int rows_lo, int j_hi_first, int rows_hi) {
+  volatile unsigned long long* vmy = my;
+  const unsigned long long epoch = vmy[HF_UNPACK_EPOCH];
+  if(threadIdx.x == 0) {
+    if(recv_lo)
+      spin_until(&vmy[HF_ARRIVED_LO], epoch, &my[HF_ERROR]);
+    if(recv_hi)
+      spin_until(&vmy[HF_ARRIVED_HI], epoch, &my[HF_ERROR]);
+    __threadfence_system();
+  }
+  __syncthreads();
+  const size_t total_lo = recv_lo ? (size_t)ni * rows_lo * nk : 0;
+  const size_t total_hi = recv_hi ? (size_t)ni * rows_hi * nk : 0;
+  for(size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total_lo + total_hi;
+      idx += (size_t)gridDim.x * blockDim.x) {
+    const bool lo = idx < total_lo;
+    const size_t e = lo ? idx : idx - total_lo;
+    const int rows = lo ? rows_lo : rows_hi;
+    const int i = (int)(e % ni);
+    const int r = (int)((e / ni) % rows);
+    const int k = (int)(e / ((size_t)ni * rows));
+    const size_t f = (size_t)i + (size_t)((lo ? j_lo_first : j_hi_first) + r) * sj + (size_t)k * sk;
+    field[f] = __ldcg(&(lo ? recv_lo : recv_hi)[e]); // written by a peer: read at L2, never from L1
+  }
+  __threadfence_system();
+  __syncthreads();
+  if(threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(reinterpret_cast<unsigned*>(&my[HF_UNPACK_DONE]), 1u);
+    if(prev == gridDim.x - 1) {
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned*>(&my[HF_UNPACK_DONE]) = 0u;
+      vmy[HF_UNPACK_EPOCH] = epoch + 1;
+      if(peer_lo_flags) // rank-1 pushes into my recv_lo and waits on ITS credit from the high side
+        *static_cast<volatile unsigned long long*>(&peer_lo_flags[HF_CREDIT_HI]) = epoch + 1;
+      if(peer_hi_flags)
+        *static_cast<volatile unsigned long long*>(&peer_hi_flags[HF_CREDIT_LO]) = epoch + 1;
+      __threadfence_system();
+    }
+  }
+}
 } // namespace
 
 extern "C" {
@@ -586,7 +708,21 @@ struct b200_halo_plan {
   void* comm;
   int rank, nranks, ni, nj, nk, sj, sk, halo, halo_hi, wminus, wplus;
   double *send_lo = nullptr, *send_hi = nullptr, *recv_lo = nullptr, *recv_hi = nullptr;
+  // flags + both landing buffers live in ONE allocation that the slab neighbours map through CUDA IPC
+  unsigned long long* arena = nullptr;
+  size_t cap = 0; // bytes of one landing buffer (a multiple of 256)
+  void *peer_lo = nullptr, *peer_hi = nullptr; // mapped arenas of rank-1 / rank+1
+  bool connected = false;
 };
+namespace {
+constexpr size_t kArenaHead = HF_WORDS * sizeof(unsigned long long);
+inline double* arenaRecvLo(void* arena) {
+  return reinterpret_cast<double*>(static_cast<char*>(arena) + kArenaHead);
+}
+inline double* arenaRecvHi(void* arena, size_t cap) {
+  return reinterpret_cast<double*>(static_cast<char*>(arena) + kArenaHead + cap);
+}
+} // namespace
 
 extern "C" {
 int b200rt_halo_plan_create(b200_halo_plan** plan, void* comm, int rank, int nranks, int ni, int nj,
@@ -612,9 +748,91 @@ int b200rt_halo_plan_create2(b200_halo_plan** plan, void* comm, int rank, int nr
     lo = sizeof(double);
   CK(cudaMalloc(&p->send_lo, lo));
   CK(cudaMalloc(&p->send_hi, lo));
-  CK(cudaMalloc(&p->recv_lo, lo));
-  CK(cudaMalloc(&p->recv_hi, lo));
+  p->cap = (lo + 255) / 256 * 256;
+  CK(cudaMalloc(&p->arena, kArenaHead + 2 * p->cap));
+  p->recv_lo = arenaRecvLo(p->arena);
+  p->recv_hi = arenaRecvHi(p->arena, p->cap);
+  unsigned long long head[HF_WORDS] = {};
+  head[HF_CREDIT_LO] = head[HF_CREDIT_HI] = 1; // both landing buffers are free for epoch 1
+  head[HF_PUSH_EPOCH] = head[HF_UNPACK_EPOCH] = 1;
+  CK(cudaMemcpy(p->arena, head, sizeof(head), cudaMemcpyHostToDevice));
   *plan = p;
+  return 0;
+}
+
+int b200rt_halo_plan_ipc_handle(b200_halo_plan* p, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  if(!p || !handle64)
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_halo_plan_ipc_handle: null argument");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, p->arena));
+  std::memcpy(handle64, &h, sizeof(h));
+  return 0;
+}
+
+int b200rt_halo_plan_connect(b200_halo_plan* p, const void* handle_lo, const void* handle_hi) {
+  if(!p)
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_halo_plan_connect: null plan");
+  const bool has_lo = p->rank > 0, has_hi = p->rank + 1 < p->nranks;
+  if((has_lo && !handle_lo) || (has_hi && !handle_hi))
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_halo_plan_connect: a neighbour's handle is missing");
+  cudaIpcMemHandle_t h;
+  if(has_lo) {
+    std::memcpy(&h, handle_lo, sizeof(h));
+    CK(cudaIpcOpenMemHandle(&p->peer_lo, h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  if(has_hi) {
+    std::memcpy(&h, handle_hi, sizeof(h));
+    CK(cudaIpcOpenMemHandle(&p->peer_hi, h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  p->connected = true;
+  return 0;
+}
+
+int b200rt_halo_exchange_p2p(b200_halo_plan* p, double* field, void* stream) {
+  if(!p || !field)
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_halo_exchange_p2p: null argument");
+  if(p->nranks > 1 && !p->connected)
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_halo_exchange_p2p: plan not connected to its neighbours");
+  const bool has_lo = p->rank > 0, has_hi = p->rank + 1 < p->nranks;
+  if(!has_lo && !has_hi)
+    return 0;
+  const int j_int0 = p->halo, j_int1 = p->nj - p->halo_hi; // interior rows [j_int0, j_int1)
+  auto* flo = static_cast<unsigned long long*>(p->peer_lo);
+  auto* fhi = static_cast<unsigned long long*>(p->peer_hi);
+  // at most one block per SM: a block that waits for a neighbour must not crowd out the stencil kernel
+  // running beside it, and 148 x 256 threads saturate an NVLink port several times over
+  auto blocksFor = [&](size_t total) {
+    return (int)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, 148));
+  };
+  { // my first `wplus` interior rows -> high landing buffer of rank-1; my last `wminus` -> low one of rank+1
+    const bool to_lo = has_lo && p->wplus, to_hi = has_hi && p->wminus;
+    size_t total = (size_t)p->ni * p->nk * ((to_lo ? p->wplus : 0) + (to_hi ? p->wminus : 0));
+    halo_push_kernel<<<blocksFor(total), 256, 0, S(stream)>>>(
+        field, p->arena, to_lo ? arenaRecvHi(p->peer_lo, p->cap) : nullptr, to_lo ? flo : nullptr,
+        to_hi ? arenaRecvLo(p->peer_hi) : nullptr, to_hi ? fhi : nullptr, p->ni, p->nk, p->sj, p->sk, j_int0,
+        p->wplus, j_int1 - p->wminus, p->wminus);
+  }
+  { // rank-1's rows -> my low halo rows; rank+1's rows -> my high halo rows
+    const bool from_lo = has_lo && p->wminus, from_hi = has_hi && p->wplus;
+    size_t total = (size_t)p->ni * p->nk * ((from_lo ? p->wminus : 0) + (from_hi ? p->wplus : 0));
+    halo_unpack_p2p_kernel<<<blocksFor(total), 256, 0, S(stream)>>>(
+        field, p->arena, from_lo ? p->recv_lo : nullptr, from_hi ? p->recv_hi : nullptr,
+        from_lo ? flo : nullptr, from_hi ? fhi : nullptr, p->ni, p->nk, p->sj, p->sk,
+        j_int0 - p->wminus, p->wminus, j_int1, p->wplus);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b200rt_halo_plan_p2p_status(b200_halo_plan* p) {
+  if(!p)
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_halo_plan_p2p_status: null plan");
+  unsigned long long err = 0;
+  CK(cudaMemcpy(&err, p->arena + HF_ERROR, sizeof(err), cudaMemcpyDeviceToHost));
+  if(err)
+    return b200rt_set_error(B200_ERR_RUNTIME, "peer-memory halo exchange: a wait for a slab neighbour ran "
+                                              "into its time limit");
   return 0;
 }
 
@@ -665,7 +883,11 @@ int b200rt_halo_exchange(b200_halo_plan* p, double* field, void* stream) {
 int b200rt_halo_plan_destroy(b200_halo_plan* p) {
   if(!p)
     return 0;
-  cudaFree(p->send_lo), cudaFree(p->send_hi), cudaFree(p->recv_lo), cudaFree(p->recv_hi);
+  if(p->peer_lo)
+    cudaIpcCloseMemHandle(p->peer_lo);
+  if(p->peer_hi)
+    cudaIpcCloseMemHandle(p->peer_hi);
+  cudaFree(p->send_lo), cudaFree(p->send_hi), cudaFree(p->arena);
   delete p;
   return 0;
 }

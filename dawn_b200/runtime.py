@@ -35,7 +35,8 @@ SYMBOLS = [
     "b200rt_check_last_launch", "b200rt_tensor_map_3d", "b200rt_verify_field", "b200rt_reshape", "b200rt_reshape_back",
     "b200rt_upload_nbh_table", "b200rt_nccl_unique_id", "b200rt_comm_init_rank",
     "b200rt_comm_destroy", "b200rt_halo_plan_create", "b200rt_halo_plan_create2",
-    "b200rt_halo_exchange",
+    "b200rt_halo_exchange", "b200rt_halo_plan_ipc_handle", "b200rt_halo_plan_connect",
+    "b200rt_halo_exchange_p2p", "b200rt_halo_plan_p2p_status",
     "b200rt_halo_plan_destroy", "b200rt_metrics_record_create", "b200rt_metrics_record_add",
     "b200rt_metrics_record_json", "b200rt_metrics_record_write", "b200rt_metrics_record_destroy",
     "b200rt_graph_begin", "b200rt_graph_end", "b200rt_graph_launch", "b200rt_graph_destroy",
@@ -77,6 +78,10 @@ def lib():
             ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p] + [ctypes.c_int] * 11
         _lib.b200rt_halo_exchange.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _lib.b200rt_halo_plan_destroy.argtypes = [ctypes.c_void_p]
+        _lib.b200rt_halo_plan_ipc_handle.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        _lib.b200rt_halo_plan_connect.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
+        _lib.b200rt_halo_exchange_p2p.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _lib.b200rt_halo_plan_p2p_status.argtypes = [ctypes.c_void_p]
     return _lib
 
 
@@ -131,6 +136,19 @@ class MetricsRecord:
             self.close()
         except Exception:
             pass
+
+
+def connect_halo_plan(plan, rank, world, all_gather):
+    """Peer-memory set-up of a halo plan (include/dawn_b200_rt.h, b200rt_halo_exchange_p2p): every rank
+    publishes the CUDA IPC handle of its landing buffers and maps those of its slab neighbours.
+    `all_gather(bytes) -> [bytes of rank 0, ...]` is the host's collective, e.g.
+    torch.distributed.all_gather_object wrapped in a lambda.  Collective: every rank must call it."""
+    buf = ctypes.create_string_buffer(64)
+    check(lib().b200rt_halo_plan_ipc_handle(plan, buf))
+    handles = all_gather(buf.raw)
+    lo = handles[rank - 1] if rank > 0 else None
+    hi = handles[rank + 1] if rank + 1 < world else None
+    check(lib().b200rt_halo_plan_connect(plan, lo, hi))
 
 
 def device_numa_cpus(device_index):

@@ -186,6 +186,23 @@ int b200rt_halo_plan_create2(b200_halo_plan** plan, void* comm, int rank, int nr
 int b200rt_halo_exchange(b200_halo_plan* plan, double* field, void* stream);
 int b200rt_halo_plan_destroy(b200_halo_plan* plan);
 
+/* Peer-memory variant of the same exchange (NVLink / NVSwitch, no NCCL on the data path): the landing
+ * buffers of a plan are mapped by its slab neighbours through CUDA IPC.  One kernel packs my boundary
+ * rows and stores them straight into the neighbours' landing buffers, then raises an `arrived` flag
+ * there; a second kernel waits for the neighbours' flag, moves their rows into my halo rows and
+ * returns a `credit` so that the next push may overwrite the buffer.  Flags are epoch counters kept
+ * in device memory, so the two launches can be replayed from a CUDA graph.  Set-up, once:
+ *   every rank:  b200rt_halo_plan_ipc_handle(plan, h)        -> 64 opaque bytes
+ *   host:        hand every rank the handles of rank-1 and rank+1 (e.g. an all-gather)
+ *   every rank:  b200rt_halo_plan_connect(plan, h_lo, h_hi)   (NULL at the ends of the slab chain)
+ * All ranks must call b200rt_halo_exchange_p2p the same number of times, and must synchronise among
+ * themselves (a host barrier) before any of them destroys its plan.  A wait that sees no neighbour
+ * for ~10 s gives up instead of hanging the device; b200rt_halo_plan_p2p_status reports that. */
+int b200rt_halo_plan_ipc_handle(b200_halo_plan* plan, void* handle64 /* 64 bytes out */);
+int b200rt_halo_plan_connect(b200_halo_plan* plan, const void* handle_lo, const void* handle_hi);
+int b200rt_halo_exchange_p2p(b200_halo_plan* plan, double* field, void* stream);
+int b200rt_halo_plan_p2p_status(b200_halo_plan* plan);
+
 #ifdef __cplusplus
 }
 #endif

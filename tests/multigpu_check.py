@@ -130,6 +130,11 @@ def main():
     dist.all_reduce(res3, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("MULTIGPU_GRAPH_OK" if int(res3) == 1 else "MULTIGPU_GRAPH_MISMATCH", "ranks", world)
+    ok_p2p = p2p_check(rank, world, comm, stream, st, mod, stor, loc, widths, want, sl, (ni, njl, K))
+    res4 = torch.tensor([1 if ok_p2p else 0], device="cuda")
+    dist.all_reduce(res4, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTIGPU_P2P_OK" if int(res4) == 1 else "MULTIGPU_P2P_MISMATCH", "ranks", world)
     ok_icon = icon_check(rank, world, comm, stream)
     res2 = torch.tensor([1 if ok_icon else 0], device="cuda")
     dist.all_reduce(res2, op=dist.ReduceOp.MIN)
@@ -138,6 +143,51 @@ def main():
     rt.lib().b200rt_comm_destroy(comm)
     dist.destroy_process_group()
     sys.exit(0 if int(res) == 1 and int(res2) == 1 and int(res3) == 1 else 1)
+
+
+def p2p_check(rank, world, comm, stream, st, mod, stor, loc, widths, want, sl, dims):
+    """The peer-memory halo exchange (b200rt_halo_exchange_p2p): three exchanges in a row - the second and
+    third need the credit returned by the neighbour's unpack - each followed by the kernel, bit-exact."""
+    ni, njl, K = dims
+    ok = True
+    try:
+        def gather(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        plans = []
+        for name, (wm, wp) in widths.items():
+            s = stor[name]
+            plan = ctypes.c_void_p()
+            rt.check(rt.lib().b200rt_halo_plan_create(ctypes.byref(plan), comm, rank, world, ni, njl, K,
+                                                      s.stride_j, s.stride_k, HALO, wm, wp))
+            rt.connect_halo_plan(plan, rank, world, gather)
+            plans.append((plan, s))
+        dist.barrier()
+        for rep in range(3):
+            stor["in"].from_numpy(loc["in"])          # halo rows are NaN again
+            stor["out"].from_numpy(loc["out"])
+            torch.cuda.synchronize()
+            for plan, s in plans:
+                rt.check(rt.lib().b200rt_halo_exchange_p2p(plan, s.buf.data_ptr() + 8 * s.lead, stream))
+            st.run(*[stor[fd["name"]] for fd in mod.fields])
+            torch.cuda.synchronize()
+            a = stor["out"].to_numpy()[:K, HALO:-HALO, :]
+            b = want[:K, HALO + sl.j0:HALO + sl.j0 + sl.nj_local, :]
+            same = np.array_equal(a, b, equal_nan=True)
+            if not same:
+                print("rank", rank, "p2p rep", rep, "mismatches", int((~((a == b) | (np.isnan(a) & np.isnan(b)))).sum()),
+                      flush=True)
+            ok = ok and same
+        for plan, _ in plans:
+            rt.check(rt.lib().b200rt_halo_plan_p2p_status(plan))
+        dist.barrier()                                # nobody unmaps a buffer a neighbour may still write
+        for plan, _ in plans:
+            rt.check(rt.lib().b200rt_halo_plan_destroy(plan))
+    except Exception as e:  # noqa: BLE001
+        print("rank", rank, "p2p exchange failed:", e, flush=True)
+        ok = False
+    return ok
 
 
 def icon_check(rank, world, comm, stream):
