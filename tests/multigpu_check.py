@@ -67,6 +67,19 @@ def main():
     dist.all_reduce(res, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("MULTIGPU_OK" if int(res) == 1 else "MULTIGPU_MISMATCH", "ranks", world)
+    if os.environ.get("MULTIGPU_QUICK") == "1":
+        # short form for a tight GPU budget: base parity (above), the peer-memory exchange, and the time
+        # of one exchange of either kind at the bench shape
+        ok_p2p = p2p_check(rank, world, comm, stream, st, mod, stor, loc, widths, want, sl, (ni, njl, K))
+        res4 = torch.tensor([1 if ok_p2p else 0], device="cuda")
+        dist.all_reduce(res4, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("MULTIGPU_P2P_OK" if int(res4) == 1 else "MULTIGPU_P2P_MISMATCH", "ranks", world, flush=True)
+        if int(res4) == 1:
+            exchange_times(rank, world, comm)
+        rt.lib().b200rt_comm_destroy(comm)
+        dist.destroy_process_group()
+        sys.exit(0 if int(res) == 1 and int(res4) == 1 else 1)
     # ---- the same step (NCCL halo exchange + kernel) recorded once as a CUDA graph and replayed ------
     graph_ok = True
     import threading
@@ -188,6 +201,44 @@ def p2p_check(rank, world, comm, stream, st, mod, stor, loc, widths, want, sl, d
         print("rank", rank, "p2p exchange failed:", e, flush=True)
         ok = False
     return ok
+
+
+def exchange_times(rank, world, comm, reps=200):
+    """Device time of one halo exchange of `in` at the bench shape (1030 x 1030 x 80 storage, 2 rows each
+    way), NCCL (pack, ncclSend/Recv, unpack) against peer memory (push, wait + unpack), max over ranks."""
+    ni = nj = 1024 + 2 * HALO
+    K = 80
+    s = dawn_b200.Storage(ni, nj, K + 1, "ijk")
+    s.buf.uniform_(0.0, 1.0)
+    plan = ctypes.c_void_p()
+    rt.check(rt.lib().b200rt_halo_plan_create(ctypes.byref(plan), comm, rank, world, ni, nj, K, s.stride_j,
+                                              s.stride_k, HALO, 2, 2))
+
+    def gather(b):
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+    rt.connect_halo_plan(plan, rank, world, gather)
+    stream = torch.cuda.current_stream().cuda_stream
+    ptr = s.buf.data_ptr() + 8 * s.lead
+    for label, fn in (("nccl", rt.lib().b200rt_halo_exchange), ("p2p", rt.lib().b200rt_halo_exchange_p2p)):
+        for _ in range(10):
+            rt.check(fn(plan, ptr, stream))
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            rt.check(fn(plan, ptr, stream))
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps * 1e3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print("EXCHANGE_US %s %.2f (back-to-back exchanges, %d ranks)" % (label, float(t), world), flush=True)
+    rt.check(rt.lib().b200rt_halo_plan_p2p_status(plan))
+    dist.barrier()
+    rt.check(rt.lib().b200rt_halo_plan_destroy(plan))
 
 
 def icon_check(rank, world, comm, stream):
