@@ -172,3 +172,57 @@ def test_unstructured_iteration_space():  # GenerateUnstructuredStencils.cpp:847
     want[60:100] = 1
     want[10:60] = 2
     assert np.array_equal(got, np.broadcast_to(want, (k, n)))
+
+
+# ---- the stencils only the reference's Atlas suite runs (AtlasIntegrationTestCompareOutput.cpp:1081-1370):
+# their expected values are closed forms in the number of interior edges of a cell, so they hold on the
+# toylib-numbered TriMesh as well ------------------------------------------------------------------
+def _interior_edges_per_cell(m):
+    ce, ec = m.nbh_table([CELL, EDGE]), m.nbh_table([EDGE, CELL])
+    boundary = (ec < 0).any(axis=1)
+    return boundary, np.array([sum(1 for e in row if e >= 0 and not boundary[e]) for row in ce], dtype=float)
+
+
+def test_global_var():  # :1082-1105 (dt = 2 set at run time over the default 0.5)
+    m, k = TriMesh(10, 10), 10
+    f = run("globalVar", m, k, {"in_field": full(m, CELL, k, 1.0), "out_field": full(m, CELL, k, -1.0)},
+            globals_={"dt": 2.0})
+    assert np.all(f["out_field"] == 2.0)
+    f = run("globalVar", m, k, {"in_field": full(m, CELL, k, 1.0), "out_field": full(m, CELL, k, -1.0)})
+    assert np.all(f["out_field"] == 0.5)
+
+
+def test_temp_field_allocation():  # :1111-1131 and :1137-1158
+    m, k = TriMesh(10, 10), 10
+    f = run("tempFieldAllocation", m, k, {"in_field": full(m, CELL, k, 1.0), "out_field": full(m, CELL, k, -1.0),
+                                          "tmp_field": full(m, CELL, k, 0.0)})
+    assert np.all(f["out_field"] == 2.0)
+    f = run("sparseTempFieldAllocation", m, k,
+            {"in_field": full(m, CELL, k, 1.0), "out_field": full(m, CELL, k, -1.0),
+             "tmp_field": sparse(m, [CELL, EDGE], k, 0.0)})
+    assert np.all(f["out_field"] == 3.0)
+
+
+def test_reduction_in_if_conditional():  # :1165-1216
+    m, k = TriMesh(10, 10), 1
+    boundary, n_int = _interior_edges_per_cell(m)
+    e = np.where(boundary, 0.0, 1.0)[None, :]
+    f = run("reductionInIfConditional", m, k,
+            {"c_field": full(m, CELL, k, 1.0), "sparse_field": sparse(m, [CELL, EDGE], k, 1.0),
+             "e_field": e.copy(), "out_field": full(m, CELL, k, -1.0)})
+    assert np.array_equal(f["out_field"][0], np.where(n_int < 3, 6.0, 12.0))
+    assert set(np.unique(f["out_field"])) == {6.0, 12.0}   # both branches are taken on this mesh
+
+
+@pytest.mark.parametrize("name,scale", [("reductionWithCenter", 1.0), ("reductionWithCenterSparse", 2.0),
+                                        ("reductionAndFillWithCenterSparse", 2.0)])
+def test_reductions_with_center(name, scale):  # :1222-1370: value = scale * (#cell neighbours + 1)
+    m, k = TriMesh(10, 10), 1
+    _, n_int = _interior_edges_per_cell(m)
+    f = {"cin_field": full(m, CELL, k, 1.0), "cout_field": full(m, CELL, k, 0.0)}
+    if name != "reductionWithCenter":
+        size = m.nbh_table([CELL, EDGE, CELL], True).shape[1]
+        assert size == 4                                    # CEC_SIZE + 1
+        f["sparse"] = np.full((k, m.num_cells, size), 2.0 if name == "reductionWithCenterSparse" else 0.0)
+    f = run(name, m, k, f)
+    assert np.array_equal(f["cout_field"][0], scale * n_int + scale)

@@ -332,7 +332,7 @@ class IIRBuilder:
         return self._nid
 
     # -- declarations -----------------------------------------------------------------------------
-    def _dims_json(self, dims, location=None, sparse_chain=None):
+    def _dims_json(self, dims, location=None, sparse_chain=None, include_center=False):
         if self.grid == "Cartesian":
             return {
                 "cartesian_horizontal_dimension": {
@@ -346,22 +346,22 @@ class IIRBuilder:
         chain = sparse_chain if sparse_chain else [location]
         return {
             "unstructured_horizontal_dimension": {
-                "iter_space": {"chain": list(chain), "include_center": False}},
+                "iter_space": {"chain": list(chain), "include_center": bool(include_center)}},
             "mask_k": 1 if "k" in dims else 0,
         }
 
-    def field(self, name, dims="ijk", location=None, sparse_chain=None) -> FieldHandle:
+    def field(self, name, dims="ijk", location=None, sparse_chain=None, include_center=False) -> FieldHandle:
         aid = self._new()
         self.names[aid], self.types[aid] = name, T_APIFIELD
-        self.dims[aid] = self._dims_json(dims, location, sparse_chain)
+        self.dims[aid] = self._dims_json(dims, location, sparse_chain, include_center)
         self.api.append(aid)
         self.fields.append(aid)
         return FieldHandle(name, aid, self.grid != "Cartesian")
 
-    def tmp(self, name, dims="ijk", location=None) -> FieldHandle:
+    def tmp(self, name, dims="ijk", location=None, sparse_chain=None, include_center=False) -> FieldHandle:
         aid = self._new()
         self.names[aid], self.types[aid] = name, T_TMP
-        self.dims[aid] = self._dims_json(dims, location)
+        self.dims[aid] = self._dims_json(dims, location, sparse_chain, include_center)
         self.tmps.append(aid)
         self.fields.append(aid)
         return FieldHandle(name, aid, self.grid != "Cartesian")

@@ -448,6 +448,68 @@ def ico_iteration_space():  # :847-872 (Interval levels are the subdomain magic 
     return b
 
 
+def ico_global_var():  # :874-899 (test globalVar: dt set to 2 at run time)
+    b = _ico("globalVar")
+    i, o = b.field("in_field", "k", "Cell"), b.field("out_field", "k", "Cell")
+    dt = b.global_var("dt", "Double", 0.5)
+    b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, b.assign(o, dt * i.at())), location="Cell")))
+    return b
+
+
+def ico_temp_field_allocation():  # :941-966
+    b = _ico("tempFieldAllocation")
+    i = b.field("in_field", "k", "Cell")
+    t = b.tmp("tmp_field", "k", "Cell")
+    o = b.field("out_field", "k", "Cell")
+    b.stencil(b.multistage("Parallel", b.stage(
+        b.do(FULL, b.assign(t, lit(1.0)), b.assign(o, t.at() + i.at())), location="Cell")))
+    return b
+
+
+def ico_sparse_temp_field_allocation():  # :968-998 (a temporary with a sparse dimension)
+    b = _ico("sparseTempFieldAllocation")
+    i = b.field("in_field", "k", "Cell")
+    t = b.tmp("tmp_field", "k", sparse_chain=["Cell", "Edge"])
+    o = b.field("out_field", "k", "Cell")
+    b.stencil(b.multistage("Parallel", b.stage(b.do(
+        FULL, loop_over(["Cell", "Edge"], b.assign(t, lit(1.0))),
+        b.assign(o, reduce_over(["Cell", "Edge"], t.at() * i.at()))), location="Cell")))
+    return b
+
+
+def ico_reduction_in_if_conditional():  # :1000-1036 (a reduction as the condition of an if)
+    b = _ico("reductionInIfConditional")
+    c = b.field("c_field", "k", "Cell")
+    sp = b.field("sparse_field", "k", sparse_chain=["Cell", "Edge"])
+    e = b.field("e_field", "k", "Edge")
+    o = b.field("out_field", "k", "Cell")
+    ce = ["Cell", "Edge"]
+    b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, b.if_(
+        reduce_over(ce, e.at()) < lit(3.0),
+        [b.assign(o, reduce_over(ce, sp.at() * lit(2.0)))],
+        [b.assign(o, reduce_over(ce, sp.at() * lit(4.0)))])), location="Cell")))
+    return b
+
+
+def ico_reduction_with_center(kind):  # :1038-1134 (chains that include the centre element)
+    cec = ["Cell", "Edge", "Cell"]
+    name = {0: "reductionWithCenter", 1: "reductionWithCenterSparse",
+            2: "reductionAndFillWithCenterSparse"}[kind]
+    b = _ico(name)
+    cin, cout = b.field("cin_field", "k", "Cell"), b.field("cout_field", "k", "Cell")
+    if kind == 0:
+        body = [b.assign(cout, reduce_over(cec, cin.nbh, include_center=True))]
+    elif kind == 1:
+        sp = b.field("sparse", "k", sparse_chain=cec, include_center=True)
+        body = [b.assign(cout, reduce_over(cec, cin.nbh * sp.at(), include_center=True))]
+    else:
+        sp = b.tmp("sparse", "k", sparse_chain=cec, include_center=True)
+        body = [loop_over(cec, b.assign(sp, lit(2.0)), include_center=True),
+                b.assign(cout, reduce_over(cec, cin.nbh * sp.at(), include_center=True))]
+    b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, *body), location="Cell")))
+    return b
+
+
 # ---- reference integration-test stencils (gtclang/test/integration-test/CodeGen/<name>.cpp) --------
 def kcache_fill():
     b = IIRBuilder("kcache_fill")
@@ -785,6 +847,13 @@ ALL = {
     "horizontalVertical": ico_horizontal_vertical,
     "verticalIndirecion": ico_vertical_indirection,
     "iterationSpaceUnstructured": ico_iteration_space,
+    "globalVar": ico_global_var,
+    "tempFieldAllocation": ico_temp_field_allocation,
+    "sparseTempFieldAllocation": ico_sparse_temp_field_allocation,
+    "reductionInIfConditional": ico_reduction_in_if_conditional,
+    "reductionWithCenter": lambda: ico_reduction_with_center(0),
+    "reductionWithCenterSparse": lambda: ico_reduction_with_center(1),
+    "reductionAndFillWithCenterSparse": lambda: ico_reduction_with_center(2),
 }
 
 
