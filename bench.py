@@ -480,6 +480,13 @@ def run_icon(args):
     from dawn_b200 import runtime as rt, slabs
     sl = slabs.mesh_slab(nx, ny * world, world, rank)
     mesh = TriMesh(nx, sl.local_ny)
+    if args.icon_reorder != "none":
+        # locality-preserving renumbering (dawn_b200/reorder.py): the kernels are the same, only the
+        # neighbour tables change; results map back bit for bit (tests/test_reorder.py)
+        if world > 1:
+            raise SystemExit("--icon-reorder is a 1-GPU option: the slab halo plan needs row-contiguous ids")
+        from dawn_b200 import reorder as ro
+        mesh = ro.reorder(mesh, args.icon_reorder)
     nabla4 = args.workload == "icon_nabla4"
     stencil_name = "ICON_nabla4_stencil" if nabla4 else "ICON_laplacian_stencil"
     passes = 2 if nabla4 else 1  # nabla4 = nabla2(nabla2(vec)): the nabla2 data flow twice
@@ -572,7 +579,7 @@ def run_icon(args):
                                    "; global mesh %dx%d in %d row slabs, 1 halo quad row, NCCL exchange "
                                    "of `vec` every step" % (nx, ny * world, world)),
                    "l2": "inputs larger than L2 (%.1f GB per step), no flush" % (bytes_run / 1e9),
-                   "mesh_build_s": t_mesh},
+                   "mesh_build_s": t_mesh, "numbering": args.icon_reorder},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None if nabla4 else icon_traffic(E),
                      "kernel": "%d generated kernel launches/step (vertex and cell stages co-scheduled in "
@@ -654,6 +661,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="hori_diff", choices=list(STENCIL) + ["icon_nabla2", "icon_nabla4"])
     ap.add_argument("--icon-n", type=int, default=2582, help="TriMesh nx=ny (2582 -> ~20 M edges)")
+    ap.add_argument("--icon-reorder", default="none", choices=["none", "rcm", "morton"],
+                    help="renumber the ICON mesh before the run (none = toylib's structured numbering)")
     ap.add_argument("--opt", action="append", default=[], help="codegen option key=value (sweeps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"],

@@ -168,38 +168,49 @@ class TriMesh:
         return out
 
     def _chain_rows(self, chain, include_center):
-        target = chain[-1]
-        same = chain[0] == chain[-1]
-        n0 = self.num(chain[0])
-        valid0 = self.valid(chain[0])
-        rows = []
-        base = self._base
-        for elem in range(n0):
-            if not valid0[elem]:
-                rows.append([])
+        return chain_rows(self._base, chain, include_center, self.num(chain[0]), self.valid(chain[0]))
+
+    def centroids(self):
+        """cell centroids (x, y) from the vertex coordinates"""
+        c2v = self._base[(CELL, VERTEX)]
+        return self.vertex_x[c2v].mean(axis=1), self.vertex_y[c2v].mean(axis=1)
+
+
+def chain_rows(base, chain, include_center, n0, valid0):
+    """Neighbour lists of every element of chain[0] over `chain`, composed from the two-element tables
+    `base[(from, to)]` in the reference's order (`toylib_interface.hpp:95-274`): walking the chain front
+    by front, every element of the TARGET type adjacent to the current front is collected, then
+    duplicates (and the origin, if the chain starts and ends on the same type) are dropped keeping
+    first occurrences."""
+    target = chain[-1]
+    same = chain[0] == chain[-1]
+    rows = []
+    for elem in range(n0):
+        if not valid0[elem]:
+            rows.append([])
+            continue
+        front = [elem]
+        result = []
+        for hop in range(len(chain) - 1):
+            frm, to = chain[hop], chain[hop + 1]
+            new_front = []
+            for idx in front:
+                new_front.extend(int(x) for x in base[(frm, to)][idx] if x >= 0)
+                if (frm, target) in base and frm != target:
+                    result.extend(int(x) for x in base[(frm, target)][idx] if x >= 0)
+            front = new_front
+        seen = set()
+        uniq = []
+        for x in result:
+            if same and x == elem:
                 continue
-            front = [elem]
-            result = []
-            for hop in range(len(chain) - 1):
-                frm, to = chain[hop], chain[hop + 1]
-                new_front = []
-                for idx in front:
-                    new_front.extend(int(x) for x in base[(frm, to)][idx] if x >= 0)
-                    if (frm, target) in base and frm != target:
-                        result.extend(int(x) for x in base[(frm, target)][idx] if x >= 0)
-                front = new_front
-            seen = set()
-            uniq = []
-            for x in result:
-                if same and x == elem:
-                    continue
-                if x not in seen:
-                    seen.add(x)
-                    uniq.append(x)
-            if include_center:
-                uniq = [elem] + uniq
-            rows.append(uniq)
-        return rows
+            if x not in seen:
+                seen.add(x)
+                uniq.append(x)
+        if include_center:
+            uniq = [elem] + uniq
+        rows.append(uniq)
+    return rows
 
 
 def _compact(cand):
