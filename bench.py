@@ -488,12 +488,14 @@ def run_icon(args):
         from dawn_b200 import reorder as ro
         mesh = ro.reorder(mesh, args.icon_reorder)
     nabla4 = args.workload == "icon_nabla4"
-    stencil_name = "ICON_nabla4_stencil" if nabla4 else "ICON_laplacian_stencil"
+    diamond = args.workload == "icon_diamond"
+    stencil_name = {"icon_nabla4": "ICON_nabla4_stencil", "icon_diamond": "ICON_laplacian_diamond_stencil"}.get(
+        args.workload, "ICON_laplacian_stencil")
     passes = 2 if nabla4 else 1  # nabla4 = nabla2(nabla2(vec)): the nabla2 data flow twice
-    if nabla4 and world > 1:
+    if (nabla4 or diamond) and world > 1:
         # the slab plan below keeps one halo quad row and exchanges `vec` only; nabla4 would need a second
-        # exchange (of nabla2_vec) between its passes
-        raise SystemExit("icon_nabla4 is a 1-GPU bench line; use icon_nabla2 for the multi-GPU runs")
+        # exchange (of nabla2_vec) between its passes, the diamond stencil one of u_vert / v_vert
+        raise SystemExit("%s is a 1-GPU bench line; use icon_nabla2 for the multi-GPU runs" % args.workload)
     mod = dawn_b200.load_stencil(stencil_name)
     st = mod.on_mesh(mesh, K)
     t_mesh = time.perf_counter() - t0
@@ -524,7 +526,7 @@ def run_icon(args):
         plan = ctypes.c_void_p()
         rt.check(rt.lib().b200rt_halo_plan_create2(ctypes.byref(plan), comm, rank, world, per,
                                                    sl.local_ny, K, per, E, sl.halo_lo, sl.halo_hi, 1, 1))
-    vec = tens[[fd["name"] for fd in mod.fields].index("vec")]
+    vec = None if diamond else tens[[fd["name"] for fd in mod.fields].index("vec")]
 
     def step():
         if plan is not None:
@@ -563,6 +565,10 @@ def run_icon(args):
     E, C, V = own.num_edges, own.num_cells, own.num_vertices
     units = E * K * world
     bytes_run = passes * (K * (40 * E + 56 * V + 32 * C) + 4 * (6 * V + 3 * C + 2 * E + 2 * E))
+    if diamond:
+        # per edge and level: read 5 dense edge fields + 4 sparse ones (4 diamond slots each), write the
+        # sparse vn_vert and 6 dense results = 31 doubles; per vertex: u_vert, v_vert once; E->C->V table once
+        bytes_run = K * (248 * E + 16 * V) + 4 * 4 * E
     peak, peak_src = measured_peak()
     achieved = bytes_run / (ms * 1e-3) / 1e9
     line = {
@@ -574,6 +580,8 @@ def run_icon(args):
                                "%d cells, %d vertices x %d levels%s" % (
                                    "ICON_nabla4_stencil (nabla2 of nabla2; not in the reference, parity "
                                    "anchored on two passes of the nabla2 oracle)" if nabla4 else
+                                   "ICON_laplacian_diamond_stencil (diamond nabla2 + Smagorinsky, "
+                                   "dawn4py-tests/ICON_laplacian_diamond_stencil.py)" if diamond else
                                    "ICON_laplacian_stencil (nabla2)",
                                    nx, ny, E, C, V, K, "" if world == 1 else
                                    "; global mesh %dx%d in %d row slabs, 1 halo quad row, NCCL exchange "
@@ -581,15 +589,17 @@ def run_icon(args):
                    "l2": "inputs larger than L2 (%.1f GB per step), no flush" % (bytes_run / 1e9),
                    "mesh_build_s": t_mesh, "numbering": args.icon_reorder},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None if nabla4 else icon_traffic(E),
-                     "kernel": "%d generated kernel launches/step (vertex and cell stages co-scheduled in "
+                     "frac": achieved / peak, "traffic": None if (nabla4 or diamond) else icon_traffic(E),
+                     "kernel": ("%d generated kernel launch/step (13 fused edge stages); %.0f algorithmic "
+                                "bytes/step" % ((st.launches() - l0) // args.steps, bytes_run)) if diamond else
+                               "%d generated kernel launches/step (vertex and cell stages co-scheduled in "
                                "one launch, 5 fused edge stages in the other%s); %.0f algorithmic "
                                "bytes/step" % ((st.launches() - l0) // args.steps,
                                                ", both twice" if nabla4 else "", bytes_run),
                      "peak_source": peak_src},
         "gpu_launches": launches, "clocks": clocks,
     }
-    if rank == 0 and world == 1 and not nabla4 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not nabla4 and not diamond and not args.no_cpu_baseline:
         r = icon_reference(64, K, 3, 1)
         if r is not None:
             line["cpu_baseline"] = {"value": r[0], "unit": "edge-level updates/s", "cores": 1,
@@ -659,8 +669,10 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="hori_diff", choices=list(STENCIL) + ["icon_nabla2", "icon_nabla4"])
-    ap.add_argument("--icon-n", type=int, default=2582, help="TriMesh nx=ny (2582 -> ~20 M edges)")
+    ap.add_argument("--workload", default="hori_diff", choices=list(STENCIL) + ["icon_nabla2", "icon_nabla4", "icon_diamond"])
+    ap.add_argument("--icon-n", type=int, default=None,
+                    help="TriMesh nx=ny (default 2582 -> ~20 M edges; icon_diamond: 1500 -> 6.8 M edges, its "
+                         "31 edge fields x 65 levels fill 110 GB)")
     ap.add_argument("--icon-reorder", default="none", choices=["none", "rcm", "morton"],
                     help="renumber the ICON mesh before the run (none = toylib's structured numbering)")
     ap.add_argument("--opt", action="append", default=[], help="codegen option key=value (sweeps)")
@@ -672,11 +684,13 @@ def main():
     args = ap.parse_args()
     if args.shape and args.workload in SHAPE:
         SHAPE[args.workload] = tuple(int(v) for v in args.shape.lower().split("x"))
-    if args.workload in ("icon_nabla2", "icon_nabla4"):
+    if args.icon_n is None:
+        args.icon_n = 1500 if args.workload == "icon_diamond" else 2582
+    if args.workload in ("icon_nabla2", "icon_nabla4", "icon_diamond"):
         if args.impl == "reference" and args.workload == "icon_nabla2":
             run_icon_reference(args)
         elif args.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "the reference has no nabla4 stencil"}))
+            print(json.dumps({"impl": "reference", "unavailable": "no compiled reference text for this stencil"}))
         else:
             run_icon(args)
     elif args.impl == "reference":

@@ -387,3 +387,12 @@ def test_icon_nabla4_plan():
     assert "5 fused stage(s) on edges" in heads[1] and "5 fused stage(s) on edges" in heads[3]
     for t in ("__tmp_nab_60", "__tmp_nab_61", "__tmp_nab_62", "__tmp_nab_63"):
         assert t + "_p" not in code  # edge temporaries never leave registers
+
+
+def test_icon_diamond_laplacian_is_one_kernel():
+    # 13 edge stages (ICON_laplacian_diamond_stencil.py): everything but the sparse vn_vert and the API
+    # outputs stays in registers, one launch
+    code = _code("ICON_laplacian_diamond_stencil", backend="b200-ico")
+    heads = re.findall(r"^// kernel .*$", code, flags=re.M)
+    assert len(heads) == 1 and "13 fused stage(s) on edges" in heads[0]
+    assert code.count("<<<") == 1 and "sqrt(" in code

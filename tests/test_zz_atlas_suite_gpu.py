@@ -99,3 +99,19 @@ def test_icon_nabla2_on_a_renumbered_mesh(method):
     for n, loc in (("rot_vec", VERTEX), ("div_vec", CELL), ("nabla2_vec", EDGE)):
         v = m.valid(loc)
         assert bit_equal(r.to_old(loc, got[n], axis=1)[:, v], want[n][:, v]), n
+
+
+@inproc
+@pytest.mark.parametrize("nx,ny,k", [(9, 7, 3), (33, 20, 9)])
+def test_icon_diamond_laplacian(nx, ny, k):
+    """ICON_laplacian_diamond_stencil.py (diamond nabla2 + Smagorinsky): 13 fused edge stages, one launch."""
+    from test_unstructured_oracle import diamond_fields
+    m = TriMesh(nx, ny)
+    f = diamond_fields(m, k, 54)
+    want = naive_interp.run_unstructured(iir_path("ICON_laplacian_diamond_stencil"), m, k,
+                                         {n: v.copy() for n, v in f.items()})
+    got, st = _run("ICON_laplacian_diamond_stencil", m, k, f)
+    v = m.valid(EDGE)
+    for n in ("vn_vert", "dvt_tang", "dvt_norm", "kh_smag_1", "kh_smag_2", "kh_smag", "nabla2"):
+        assert bit_equal(got[n][:, v], want[n][:, v]), n
+    assert st.launches() == 1

@@ -224,6 +224,48 @@ def icon_nabla4():
     return b
 
 
+def icon_laplacian_diamond():
+    # dawn/test/integration-test/dawn4py-tests/ICON_laplacian_diamond_stencil.py:37-245 (ICON's diamond
+    # nabla2 with the Smagorinsky coefficient; one statement per stage like the optimizer leaves them,
+    # all on edges; field order of the script :252-376)
+    from iir_builder import call
+    b = IIRBuilder("ICON_laplacian_diamond_stencil", grid="Unstructured")
+    ecv = ["Edge", "Cell", "Vertex"]
+    smag = b.field("diff_multfac_smag", "k", "Edge")
+    tang = b.field("tangent_orientation", "k", "Edge")
+    ipel = b.field("inv_primal_edge_length", "k", "Edge")
+    ivvl = b.field("inv_vert_vert_length", "k", "Edge")
+    u, v = b.field("u_vert", "k", "Vertex"), b.field("v_vert", "k", "Vertex")
+    pnx, pny = b.field("primal_normal_x", "k", sparse_chain=ecv), b.field("primal_normal_y", "k", sparse_chain=ecv)
+    dnx, dny = b.field("dual_normal_x", "k", sparse_chain=ecv), b.field("dual_normal_y", "k", sparse_chain=ecv)
+    vn_vert = b.field("vn_vert", "k", sparse_chain=ecv)
+    vn = b.field("vn", "k", "Edge")
+    dvt_tang, dvt_norm = b.field("dvt_tang", "k", "Edge"), b.field("dvt_norm", "k", "Edge")
+    k1, k2, kh = b.field("kh_smag_1", "k", "Edge"), b.field("kh_smag_2", "k", "Edge"), b.field("kh_smag", "k", "Edge")
+    nabla2 = b.field("nabla2", "k", "Edge")
+    dual = lambda: u.nbh * dnx.nbh + v.nbh * dny.nbh  # noqa: E731
+    first, second = [-1.0, 1.0, 0.0, 0.0], [0.0, 0.0, -1.0, 1.0]
+    stmts = [
+        loop_over(ecv, b.assign(vn_vert, u.nbh * pnx.nbh + v.nbh * pny.nbh)),
+        b.assign(dvt_tang, reduce_over(ecv, dual(), weights=first)),
+        b.assign(dvt_tang, dvt_tang.at() * tang.at()),
+        b.assign(dvt_norm, reduce_over(ecv, dual(), weights=second)),
+        b.assign(k1, reduce_over(ecv, vn_vert.at(), weights=first)),
+        b.assign(k1, ((k1.at() * tang.at()) * ipel.at()) + (dvt_norm.at() * ivvl.at())),
+        b.assign(k1, k1.at() * k1.at()),
+        b.assign(k2, reduce_over(ecv, vn_vert.at(), weights=second)),
+        b.assign(k2, (k2.at() * ivvl.at()) + (dvt_tang.at() * ipel.at())),
+        b.assign(k2, k2.at() * k2.at()),
+        b.assign(kh, smag.at() * call("gridtools::dawn::math::sqrt", k1.at() + k2.at())),
+        b.assign(nabla2, reduce_over(ecv, lit(4.0) * vn_vert.at(), weights=[
+            ipel.at() * ipel.at(), ipel.at() * ipel.at(), ivvl.at() * ivvl.at(), ivvl.at() * ivvl.at()])),
+        b.assign(nabla2, nabla2.at() - (((lit(8.0) * vn.at()) * (ipel.at() * ipel.at())) +
+                                        ((lit(8.0) * vn.at()) * (ivvl.at() * ivvl.at())))),
+    ]
+    b.stencil(b.multistage("Parallel", *[b.stage(b.do(FULL, st), location="Edge") for st in stmts]))
+    return b
+
+
 def unstructured_diffusion():
     # dawn/test/integration-test/unstructured/reference/reference_diffusion.hpp:31-69
     b = IIRBuilder("diffusion", grid="Unstructured")
@@ -812,6 +854,7 @@ ALL = {
     "kparallel_solver": kparallel_solver,
     "ICON_laplacian_stencil": icon_laplacian,
     "ICON_nabla4_stencil": icon_nabla4,
+    "ICON_laplacian_diamond_stencil": icon_laplacian_diamond,
     "diffusion": unstructured_diffusion,
     "gradient": unstructured_gradient,
     "diamond": unstructured_diamond,

@@ -18,6 +18,9 @@ d = json.loads(open("gpurun_out/bench_icon_nabla2_$r.json").read().strip().split
 print("icon_nabla2 numbering=$r ms", round(d["ms_per_step"], 3), "frac", round(d["roofline"]["frac"], 3), d["clocks"])
 PY
   done
+  # A3: ICON's diamond nabla2 + Smagorinsky (13 fused edge stages, one launch, 248 B per edge-level)
+  timeout 200 python bench.py --workload icon_diamond --steps 20 > gpurun_out/bench_icon_diamond.json 2> gpurun_out/bench_icon_diamond.err
+  tail -c 900 gpurun_out/bench_icon_diamond.json
 else
   N=${2:-2}
   T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
