@@ -226,3 +226,17 @@ def test_reductions_with_center(name, scale):  # :1222-1370: value = scale * (#c
         f["sparse"] = np.full((k, m.num_cells, size), 2.0 if name == "reductionWithCenterSparse" else 0.0)
     f = run(name, m, k, f)
     assert np.array_equal(f["cout_field"][0], scale * n_int + scale)
+
+
+def test_icon_gradient():  # dawn4py-tests/ICON_gradient.py: p_grad = sum over (self + cell neighbours) of 2 * p_ccpr
+    m, k = TriMesh(9, 6), 2
+    rng = np.random.default_rng(9)
+    p = rng.uniform(0.5, 1.5, (k, m.num_cells))
+    f = run("ICON_gradient", m, k, {"p_grad": full(m, CELL, k, -1.0), "p_ccpr": p.copy(),
+                                    "geofac_grg": np.zeros((k, m.num_cells, 4))})
+    t = m.nbh_table([CELL, EDGE, CELL], True)
+    want = np.zeros((k, m.num_cells))
+    for i in range(4):                                       # chain order, centre first
+        want = want + np.where(t[:, i] >= 0, 2.0 * p[:, np.maximum(t[:, i], 0)], 0.0)
+    assert np.array_equal(f["p_grad"], want)
+    assert np.all(f["geofac_grg"][:, t >= 0] == 2.0) and np.all(f["geofac_grg"][:, t < 0] == 0.0)

@@ -115,3 +115,17 @@ def test_icon_diamond_laplacian(nx, ny, k):
     for n in ("vn_vert", "dvt_tang", "dvt_norm", "kh_smag_1", "kh_smag_2", "kh_smag", "nabla2"):
         assert bit_equal(got[n][:, v], want[n][:, v]), n
     assert st.launches() == 1
+
+
+@inproc
+def test_icon_gradient():
+    """dawn4py-tests/ICON_gradient.py: sparse API field with centre filled by a loop, then reduced."""
+    m, k = TriMesh(14, 9), 5
+    rng = np.random.default_rng(55)
+    f = {"p_grad": rng.uniform(0.5, 1.5, (k, m.num_cells)), "p_ccpr": rng.uniform(0.5, 1.5, (k, m.num_cells)),
+         "geofac_grg": np.zeros((k, m.num_cells, 4))}
+    want = naive_interp.run_unstructured(iir_path("ICON_gradient"), m, k, {n: v.copy() for n, v in f.items()})
+    got, _ = _run("ICON_gradient", m, k, f)
+    assert bit_equal(got["p_grad"], want["p_grad"])
+    t = m.nbh_table([CELL, EDGE, CELL], True)
+    assert bit_equal(got["geofac_grg"][:, t >= 0], want["geofac_grg"][:, t >= 0])

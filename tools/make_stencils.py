@@ -266,6 +266,22 @@ def icon_laplacian_diamond():
     return b
 
 
+def icon_gradient():
+    # dawn/test/integration-test/dawn4py-tests/ICON_gradient.py:38-63 (the script compiles it with the
+    # cuda-ico backend): a loop with centre fills the sparse geofac_grg, a reduction with centre uses it
+    b = IIRBuilder("ICON_gradient", grid="Unstructured")
+    cec = ["Cell", "Edge", "Cell"]
+    p_grad, p_ccpr = b.field("p_grad", "k", "Cell"), b.field("p_ccpr", "k", "Cell")
+    grg = b.field("geofac_grg", "k", sparse_chain=cec, include_center=True)
+    b.stencil(b.multistage("Parallel",
+                           b.stage(b.do(FULL, loop_over(cec, b.assign(grg, lit(2.0)), include_center=True)),
+                                   location="Cell"),
+                           b.stage(b.do(FULL, b.assign(p_grad, reduce_over(cec, grg.at() * p_ccpr.nbh,
+                                                                           include_center=True))),
+                                   location="Cell")))
+    return b
+
+
 def unstructured_diffusion():
     # dawn/test/integration-test/unstructured/reference/reference_diffusion.hpp:31-69
     b = IIRBuilder("diffusion", grid="Unstructured")
@@ -855,6 +871,7 @@ ALL = {
     "ICON_laplacian_stencil": icon_laplacian,
     "ICON_nabla4_stencil": icon_nabla4,
     "ICON_laplacian_diamond_stencil": icon_laplacian_diamond,
+    "ICON_gradient": icon_gradient,
     "diffusion": unstructured_diffusion,
     "gradient": unstructured_gradient,
     "diamond": unstructured_diamond,
