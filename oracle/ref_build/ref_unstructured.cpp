@@ -6,6 +6,8 @@
 //   dawn/test/integration-test/unstructured/reference/reference_{diffusion,gradient,diamond,
 //        diamondWeights,intp}.hpp
 //   dawn/test/integration-test/dawn4py-tests/data/ICON_laplacian_stencil_ref.cpp  (nabla2)
+//   dawn/test/integration-test/dawn4py-tests/data/generate_versioned_field_ref.cpp (versioned field,
+//        nested conditionals on field values)
 //
 // Plain-buffer conventions: dense fields are level-major [k][n] with n = toylib element id
 // (edges: id in the all_edges() slot numbering, invalid slots simply unused); sparse fields are
@@ -34,6 +36,7 @@ inline toylib::EdgeData<double> allocateField(toylibTag, std::size_t, int k_size
 #include REF_UNSTR(reference_diamondWeights.hpp)
 #include REF_UNSTR(reference_intp.hpp)
 #include REF_ICONLAP
+#include REF_VERSIONED
 
 namespace {
 using dawn::LocationType;
@@ -234,6 +237,26 @@ int ref_icon_laplacian(int nx, int ny, int k_size, const double* vec, double* di
   store(fdiv, div_vec, nc);
   store(frot, rot_vec, nv);
   store(fnab, nabla2_vec, ne);
+  toylibInterface::g_current_grid = nullptr;
+  return 0;
+}
+
+// generate_versioned_field_ref.cpp:103-111: five edge fields, the versioned copy c_0 is allocated inside.
+int ref_generate_versioned_field(int nx, int ny, int k_size, double* a, const double* b, double* c,
+                                 const double* d, const double* e) {
+  auto g = make_grid(nx, ny, 0, 0, 0);
+  toylibInterface::g_current_grid = &g;
+  int ne = (int)g.all_edges().size();
+  toylib::EdgeData<double> fa(g, k_size), fb(g, k_size), fc(g, k_size), fd(g, k_size), fe(g, k_size);
+  load(fa, a, ne, k_size);
+  load(fb, b, ne, k_size);
+  load(fc, c, ne, k_size);
+  load(fd, d, ne, k_size);
+  load(fe, e, ne, k_size);
+  dawn_generated::cxxnaiveico::generate_versioned_field<toylibTag> st(g, k_size, fa, fb, fc, fd, fe);
+  st.run();
+  store(fa, a, ne);
+  store(fc, c, ne);
   toylibInterface::g_current_grid = nullptr;
   return 0;
 }

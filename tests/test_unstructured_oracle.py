@@ -255,3 +255,43 @@ def test_icon_diamond_laplacian_against_a_direct_restatement():
     for name, want in (("vn_vert", vn_vert), ("dvt_tang", dvt_tang), ("dvt_norm", dvt_norm), ("kh_smag_1", k1),
                        ("kh_smag_2", k2), ("kh_smag", kh), ("nabla2", nabla2)):
         assert bit_equal(w[name][:, full], want), name
+
+
+def versioned_fields(m, k, seed):
+    rng = np.random.default_rng(seed)
+    f = {n: rng.uniform(0.5, 1.5, (k, m.num_edges)) for n in "abc"}
+    f["d"] = (rng.uniform(0, 1, (k, m.num_edges)) < 0.4).astype(float)        # conditions: zero / non-zero
+    f["e"] = (rng.uniform(0, 1, (k, m.num_edges)) < 0.5).astype(float) * 3.0
+    f["c_0"] = np.zeros((k, m.num_edges))
+    return f
+
+
+@needs_ref
+def test_interpreter_matches_reference_versioned_field():
+    # the reference's own generated text data/generate_versioned_field_ref.cpp, compiled unmodified
+    nx, ny, k = 7, 5, 4
+    m = TriMesh(nx, ny)
+    f = versioned_fields(m, k, 3)
+    w = {n: f[n].copy() for n in "ac"}
+    R.ref_generate_versioned_field(nx, ny, k, P(w["a"]), P(f["b"]), P(w["c"]), P(f["d"]), P(f["e"]))
+    got = naive_interp.run_unstructured(iir_path("generate_versioned_field"), m, k, {n: v.copy() for n, v in f.items()})
+    ev = m.edge_valid
+    assert bit_equal(got["a"][:, ev], w["a"][:, ev]) and bit_equal(got["c"][:, ev], w["c"][:, ev])
+    changed = (got["c"][:, ev] != f["c"][:, ev]).mean()
+    assert 0.1 < changed < 0.6 and 0.2 < (got["a"][:, ev] == f["b"][:, ev]).mean() < 0.7   # every branch taken
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "versioned_field.npz")
+    if not os.path.exists(path):
+        np.savez_compressed(path, seed=3, dims=(nx, ny, k), a=w["a"], c=w["c"])
+
+
+def test_interpreter_matches_versioned_field_golden():
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "versioned_field.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden not generated yet")
+    g = np.load(path)
+    nx, ny, k = (int(x) for x in g["dims"])
+    m = TriMesh(nx, ny)
+    got = naive_interp.run_unstructured(iir_path("generate_versioned_field"), m, k,
+                                        versioned_fields(m, k, int(g["seed"])))
+    ev = m.edge_valid
+    assert bit_equal(got["a"][:, ev], g["a"][:, ev]) and bit_equal(got["c"][:, ev], g["c"][:, ev])

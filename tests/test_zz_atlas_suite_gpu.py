@@ -129,3 +129,18 @@ def test_icon_gradient():
     assert bit_equal(got["p_grad"], want["p_grad"])
     t = m.nbh_table([CELL, EDGE, CELL], True)
     assert bit_equal(got["geofac_grg"][:, t >= 0], want["geofac_grg"][:, t >= 0])
+
+
+@inproc
+def test_versioned_field_against_the_reference_golden():
+    """generate_versioned_field: golden made by the reference's own generated text (oracle/_ref build)."""
+    import os
+    from test_unstructured_oracle import versioned_fields
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "versioned_field.npz"))
+    nx, ny, k = (int(x) for x in g["dims"])
+    m = TriMesh(nx, ny)
+    f = versioned_fields(m, k, int(g["seed"]))
+    f.pop("c_0")
+    got, _ = _run("generate_versioned_field", m, k, f)
+    ev = m.edge_valid
+    assert bit_equal(got["a"][:, ev], g["a"][:, ev]) and bit_equal(got["c"][:, ev], g["c"][:, ev])

@@ -282,6 +282,21 @@ def icon_gradient():
     return b
 
 
+def generate_versioned_field():
+    # dawn/test/integration-test/dawn4py-tests/generate_versioned_field.py after PassFieldVersioning, as
+    # the reference's own generated text shows it (data/generate_versioned_field_ref.cpp:42-66): c is
+    # copied to its version c_0 in a first multistage, the second reads c_0 and conditionally writes c
+    b = IIRBuilder("generate_versioned_field", grid="Unstructured")
+    a, bb, c, d, e = (b.field(n, "k", "Edge") for n in "abcde")
+    c0 = b.tmp("c_0", "k", "Edge")
+    s1 = b.stage(b.do(FULL, b.assign(c0, c.at())), location="Edge")
+    s2 = b.stage(b.do(FULL, b.assign(a, (bb.at() / c0.at()) + lit(5)),
+                      b.if_(d.at(), [b.assign(a, bb.at())],
+                            [b.if_(e.at(), [b.assign(c, a.at() + lit(1))])])), location="Edge")
+    b.stencil(b.multistage("Parallel", s1), b.multistage("Parallel", s2))
+    return b
+
+
 def unstructured_diffusion():
     # dawn/test/integration-test/unstructured/reference/reference_diffusion.hpp:31-69
     b = IIRBuilder("diffusion", grid="Unstructured")
@@ -872,6 +887,7 @@ ALL = {
     "ICON_nabla4_stencil": icon_nabla4,
     "ICON_laplacian_diamond_stencil": icon_laplacian_diamond,
     "ICON_gradient": icon_gradient,
+    "generate_versioned_field": generate_versioned_field,
     "diffusion": unstructured_diffusion,
     "gradient": unstructured_gradient,
     "diamond": unstructured_diamond,
