@@ -31,7 +31,7 @@ inproc = pytest.mark.skipif(not INPROC, reason="runs inside the child process of
 def test_pending_cases_in_a_child_process():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu",
                         "-p", "no:cacheprovider"], env=dict(os.environ, B200_PENDING_INPROC="1"),
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=180)
     print(r.stdout[-3000:], r.stderr[-1500:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1500:]
 
