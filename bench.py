@@ -445,6 +445,10 @@ def run_gpu(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(workload)
+            if not args.shape:
+                # reported beside the CPU baseline, not a target either: what the reference's CUDA backend
+                # output does on this GPU when it is merely recompiled
+                line["reference_cuda_kernel"] = refcuda_baseline(workload)
         print(json.dumps(line))
     for plan, _ in plans:
         rt.lib().b200rt_halo_plan_destroy(plan)
@@ -613,6 +617,71 @@ def run_icon(args):
         dist.destroy_process_group()
 
 
+def refcuda_child(workload):
+    """Child process of the main bench line: times the reference's OWN pre-generated CUDA code, recompiled
+    unmodified for sm_100a (oracle/ref_build/ref_cuda.cu -> oracle/_ref/libdawn_refcuda.so), on buffers of
+    the bench shape.  hori_diff: dawn4py-tests/data/hori_diff_stencil_ref.cpp (4th-order diffusion with a
+    coefficient field: in, out, coeff - the same 24 compulsory B/point as the headline stencil, whose
+    CUDA text the reference does not ship); tridiagonal: data/tridiagonal_solve_stencil_ref.cpp (forward
+    and backward sweep as two kernels).  Prints one JSON object."""
+    import ctypes
+
+    import torch
+
+    import dawn_b200
+    from oracle import capi
+    lib = capi.refcuda()
+    if lib is None:
+        print(json.dumps({"unavailable": "oracle/_ref/libdawn_refcuda.so missing"}))
+        return
+    torch.cuda.set_device(0)
+    I, J, K = SHAPE[workload]
+    ni, nj = I + 2 * HALO, J + 2 * HALO
+    n_fields = 3 if workload == "hori_diff" else 4
+    stor = [dawn_b200.Storage(ni, nj, K + 1, "ijk") for _ in range(n_fields)]
+    for n, st in enumerate(stor):
+        st.buf.uniform_(0.5, 1.5)
+        if workload == "tridiagonal" and n == 1:
+            st.buf.add_(4.0)                                  # b: diagonally dominant
+    torch.cuda.synchronize()
+    ptrs = [ctypes.c_void_p(st.buf.data_ptr() + 8 * st.lead) for st in stor]
+    fn = lib.refcuda_hori_diff if workload == "hori_diff" else lib.refcuda_tridiagonal_solve
+    sec = ctypes.c_double(0.0)
+    head = (ni, nj, K, HALO, stor[0].stride_j, stor[0].stride_k)
+    rc = fn(*head, *ptrs, 3, ctypes.byref(sec))               # warm-up
+    reps = 50
+    rc = rc or fn(*head, *ptrs, reps, ctypes.byref(sec))
+    if rc:
+        print(json.dumps({"error": "reference CUDA kernel failed with code %d" % rc}))
+        return
+    ms = sec.value * 1e3 / reps
+    peak, _ = measured_peak()
+    gbs = BYTES_PER_POINT[workload] * I * J * K / (ms * 1e-3) / 1e9
+    print(json.dumps({
+        "ms_per_run": ms, "reps": reps, "achieved_gbs": gbs, "frac_of_peak": gbs / peak,
+        "updates_per_s": I * J * K / (ms * 1e-3),
+        "what": ("the reference's pre-generated CUDA code, unmodified, recompiled for sm_100a (-fmad=false): "
+                 + ("dawn4py-tests/data/hori_diff_stencil_ref.cpp (in, out, coeff; 32x4 blocks + halo warps, "
+                    "lap in a shared-memory IJ-cache)" if workload == "hori_diff" else
+                    "dawn4py-tests/data/tridiagonal_solve_stencil_ref.cpp (two kernels, 32x1 blocks, "
+                    "register K-caches)")
+                 + "; %dx%dx%d, kernel time from its own timer_cuda events" % (I, J, K))}))
+
+
+def refcuda_baseline(workload):
+    """Runs refcuda_child in its own process (a fault in code nobody has run on this GPU before must not
+    reach the measured process) and returns its JSON object, or a reason."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--refcuda-child", workload],
+                           capture_output=True, text=True, timeout=180)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": "child exited with %d: %s" % (r.returncode, r.stderr.strip()[-200:])}
+        return json.loads(lines[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
+
+
 def icon_reference(nx, K, reps, warm):
     """The reference's own generated naive-ico nabla2 (ICON_laplacian_stencil_ref.cpp, compiled unmodified
     into oracle/_ref) on the toylib mesh, single thread as the naive backend runs: (updates/s, ms per
@@ -679,11 +748,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"],
                     help="multi-GPU halo exchange: pack -> ncclSend/Recv -> unpack, or peer-memory stores")
+    ap.add_argument("--refcuda-child", default=None, choices=list(STENCIL), help=argparse.SUPPRESS)
     ap.add_argument("--shape", default=None, help="IxJxK interior of the Cartesian workloads per GPU "
                     "(default: the BASELINE.json config, e.g. 1024x1024x80)")
     args = ap.parse_args()
     if args.shape and args.workload in SHAPE:
         SHAPE[args.workload] = tuple(int(v) for v in args.shape.lower().split("x"))
+    if args.refcuda_child:
+        refcuda_child(args.refcuda_child)
+        return
     if args.icon_n is None:
         args.icon_n = 1500 if args.workload == "icon_diamond" else 2582
     if args.workload in ("icon_nabla2", "icon_nabla4", "icon_diamond"):

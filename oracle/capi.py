@@ -131,3 +131,22 @@ def icon_laplacian_reference_timed(nx, ny, k_size, reps):
     t = np.zeros(reps)
     ne = R.ref_icon_laplacian_timed(nx, ny, k_size, reps, _ptr(t))
     return (ne, t) if ne > 0 else None
+
+
+_refcuda = None
+
+
+def refcuda():
+    """The reference's own pre-generated CUDA code recompiled for sm_100a (oracle/ref_build/ref_cuda.cu),
+    or None when oracle/_ref was never built.  Entry points take device pointers."""
+    global _refcuda
+    if _refcuda is None:
+        p = os.path.join(HERE, "_ref", "libdawn_refcuda.so")
+        if not os.path.exists(p):
+            return None
+        _refcuda = ctypes.CDLL(p)
+        _refcuda.refcuda_hori_diff.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 3 + [
+            ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+        _refcuda.refcuda_tridiagonal_solve.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 4 + [
+            ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    return _refcuda

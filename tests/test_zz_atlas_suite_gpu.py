@@ -144,3 +144,38 @@ def test_versioned_field_against_the_reference_golden():
     got, _ = _run("generate_versioned_field", m, k, f)
     ev = m.edge_valid
     assert bit_equal(got["a"][:, ev], g["a"][:, ev]) and bit_equal(got["c"][:, ev], g["c"][:, ev])
+
+
+@inproc
+@pytest.mark.parametrize("I,J,K", [(12, 12, 10), (70, 41, 9), (128, 64, 20)])
+def test_reference_cuda_kernel_and_ours_agree_bit_for_bit(I, J, K):
+    """hori_diff (dawn4py flavour: in, out, coeff): the reference's own pre-generated CUDA code, recompiled
+    unmodified for sm_100a (oracle/_ref/libdawn_refcuda.so), against the b200 kernel and the oracle."""
+    import ctypes
+    import torch
+    import dawn_b200
+    from oracle import capi
+    from util import HALO, run_oracle
+    lib = capi.refcuda()
+    if lib is None:
+        pytest.skip("oracle/_ref/libdawn_refcuda.so not built")
+    ni, nj = I + 2 * HALO, J + 2 * HALO
+    rng = np.random.default_rng(56)
+    f = {n: rng.uniform(0.5, 1.5, (K + 1, nj, ni)) for n in ("in", "out", "coeff")}
+    f["out"] = np.full((K + 1, nj, ni), -1.0)
+    want = run_oracle("hori_diff_stencil", (ni, nj, K), f)["out"]
+    mod = dawn_b200.load_stencil("hori_diff_stencil")
+    assert [fd["name"] for fd in mod.fields] == ["in", "out", "coeff"]
+    dom = dawn_b200.Domain(ni, nj, K)
+    dom.set_halos(HALO, HALO, HALO, HALO, 0, 0)
+    ours = [dawn_b200.Storage(ni, nj, K + 1, "ijk").from_numpy(f[n]) for n in ("in", "out", "coeff")]
+    mod(dom).run(*ours)
+    theirs = [dawn_b200.Storage(ni, nj, K + 1, "ijk").from_numpy(f[n]) for n in ("in", "out", "coeff")]
+    sec = ctypes.c_double()
+    rc = lib.refcuda_hori_diff(ni, nj, K, HALO, theirs[0].stride_j, theirs[0].stride_k,
+                               *[ctypes.c_void_p(s.buf.data_ptr() + 8 * s.lead) for s in theirs], 1,
+                               ctypes.byref(sec))
+    torch.cuda.synchronize()
+    assert rc == 0
+    a, b = ours[1].to_numpy(), theirs[1].to_numpy()
+    assert bit_equal(a, want) and bit_equal(b, want)

@@ -18,6 +18,16 @@ d = json.loads(open("gpurun_out/bench_icon_nabla2_$r.json").read().strip().split
 print("icon_nabla2 numbering=$r ms", round(d["ms_per_step"], 3), "frac", round(d["roofline"]["frac"], 3), d["clocks"])
 PY
   done
+  # A0: the default bench line now carries "reference_cuda_kernel" (the reference's own CUDA text recompiled
+  #     for sm_100a, timed in a child process): hori_diff and tridiagonal
+  for w in hori_diff tridiagonal; do
+    timeout 200 python bench.py --workload $w > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
+    python - <<PY
+import json
+d = json.loads(open("gpurun_out/bench_$w.json").read().strip().splitlines()[-1])
+print("$w ours ms", round(d["ms_per_step"], 4), "frac", round(d["roofline"]["frac"], 3), "| reference CUDA text:", d.get("reference_cuda_kernel"))
+PY
+  done
   # A3: ICON's diamond nabla2 + Smagorinsky (13 fused edge stages, one launch, 248 B per edge-level)
   timeout 200 python bench.py --workload icon_diamond --steps 20 > gpurun_out/bench_icon_diamond.json 2> gpurun_out/bench_icon_diamond.err
   tail -c 900 gpurun_out/bench_icon_diamond.json
