@@ -150,3 +150,21 @@ def refcuda():
         _refcuda.refcuda_tridiagonal_solve.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 4 + [
             ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     return _refcuda
+
+
+_refcuda_small = {}
+
+
+def refcuda_small(name):
+    """One of the reference's small pre-generated CUDA texts recompiled for sm_100a
+    (oracle/ref_build/ref_cuda_small.cu): conditional_stencil, global_indexing, nonoverlapping_stencil,
+    copy_stencil.  `refcuda_run(ni, nj, nk, halo, stride_j, stride_k, in_dev, out_dev, var1)`; None when
+    oracle/_ref was never built."""
+    if name not in _refcuda_small:
+        p = os.path.join(HERE, "_ref", "libdawn_refcuda_%s.so" % name)
+        if not os.path.exists(p):
+            return None
+        lib = ctypes.CDLL(p)
+        lib.refcuda_run.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 2 + [ctypes.c_int]
+        _refcuda_small[name] = lib
+    return _refcuda_small[name]

@@ -179,3 +179,46 @@ def test_reference_cuda_kernel_and_ours_agree_bit_for_bit(I, J, K):
     assert rc == 0
     a, b = ours[1].to_numpy(), theirs[1].to_numpy()
     assert bit_equal(a, want) and bit_equal(b, want)
+
+
+@inproc
+@pytest.mark.parametrize("case", ["conditional_var1_1", "conditional_var1_0", "global_indexing",
+                                  "nonoverlapping", "copy"])
+def test_reference_cuda_texts_reproduce_the_reference_naive_goldens(case):
+    """The reference's pre-generated CUDA texts (CodeGen/reference/*.cu, copy_stencil_ref.cpp), recompiled
+    unmodified for sm_100a, against the goldens its own generated NAIVE code produced (tests/golden):
+    reference naive == reference CUDA on a B200 == ours (tests/test_cartesian_gpu.py)."""
+    import ctypes
+    import os
+    import torch
+    import dawn_b200
+    from oracle import capi
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    name = {"conditional_var1_1": "conditional_stencil", "conditional_var1_0": "conditional_stencil",
+            "nonoverlapping": "nonoverlapping_stencil", "copy": "copy_stencil"}.get(case, case)
+    lib = capi.refcuda_small(name)
+    if lib is None:
+        pytest.skip("oracle/_ref/libdawn_refcuda_%s.so not built" % name)
+    g = np.load(os.path.join(gold, "conditional_stencil.npz" if name == "conditional_stencil" else "indexing.npz"))
+    ni, nj, nk = (int(x) for x in g["dims"])
+    inn = np.random.default_rng(int(g["seed"])).uniform(-1, 1, (nk + 1, nj, ni))
+    s_in = dawn_b200.Storage(ni, nj, nk + 1).from_numpy(inn)
+    s_out = dawn_b200.Storage(ni, nj, nk + 1).fill(-1.0)
+    var1 = 0 if case.endswith("_0") else 1
+    rc = lib.refcuda_run(ni, nj, nk, 3, s_in.stride_j, s_in.stride_k,
+                         ctypes.c_void_p(s_in.buf.data_ptr() + 8 * s_in.lead),
+                         ctypes.c_void_p(s_out.buf.data_ptr() + 8 * s_out.lead), var1)
+    torch.cuda.synchronize()
+    assert rc == 0
+    out = s_out.to_numpy()
+    if name == "conditional_stencil":
+        assert bit_equal(out, g["out_var1_%d" % var1])
+    elif name == "global_indexing":
+        assert bit_equal(out, g["global_indexing"])
+    elif name == "nonoverlapping_stencil":
+        assert bit_equal(out[11:], g["nonoverlapping_from_k11"])   # below: an uninitialised local in the text
+    else:
+        h = 3
+        want = np.full_like(inn, -1.0)
+        want[:nk, h:-h, h:-h] = inn[:nk, h:-h, h:-h]
+        assert bit_equal(out, want)
