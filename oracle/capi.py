@@ -158,13 +158,17 @@ _refcuda_small = {}
 def refcuda_small(name):
     """One of the reference's small pre-generated CUDA texts recompiled for sm_100a
     (oracle/ref_build/ref_cuda_small.cu): conditional_stencil, global_indexing, nonoverlapping_stencil,
-    copy_stencil.  `refcuda_run(ni, nj, nk, halo, stride_j, stride_k, in_dev, out_dev, var1)`; None when
+    copy_stencil (`refcuda_run(ni, nj, nk, halo, stride_j, stride_k, in_dev, out_dev, var1)`) and update_dz_c
+    (`refcuda_update_dz_c`, ref_cuda_dzc.cu); None when
     oracle/_ref was never built."""
     if name not in _refcuda_small:
         p = os.path.join(HERE, "_ref", "libdawn_refcuda_%s.so" % name)
         if not os.path.exists(p):
             return None
         lib = ctypes.CDLL(p)
-        lib.refcuda_run.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 2 + [ctypes.c_int]
+        if name == "update_dz_c":   # refcuda_update_dz_c(ni, nj, nk, halo, dt, double* const fields[9]): dense buffers
+            lib.refcuda_update_dz_c.argtypes = [ctypes.c_int] * 4 + [ctypes.c_double, ctypes.c_void_p]
+        else:
+            lib.refcuda_run.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 2 + [ctypes.c_int]
         _refcuda_small[name] = lib
     return _refcuda_small[name]

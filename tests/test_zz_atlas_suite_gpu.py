@@ -222,3 +222,31 @@ def test_reference_cuda_texts_reproduce_the_reference_naive_goldens(case):
         want = np.full_like(inn, -1.0)
         want[:nk, h:-h, h:-h] = inn[:nk, h:-h, h:-h]
         assert bit_equal(out, want)
+
+
+@inproc
+def test_reference_cuda_update_dz_c_reproduces_the_reference_naive_golden():
+    """update_dz_c.cu (7 kernels, block-private temporaries in global memory, a versioned field), recompiled
+    unmodified for sm_100a, against the golden of the reference's generated naive code."""
+    import ctypes
+    import os
+    import torch
+    from oracle import capi
+    lib = capi.refcuda_small("update_dz_c")
+    if lib is None:
+        pytest.skip("oracle/_ref/libdawn_refcuda_update_dz_c.so not built")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "update_dz_c.npz"))
+    ni, nj, nk = (int(x) for x in g["dims"])
+    names = ["dp_ref", "zs", "area", "ut", "vt", "gz", "gz_x", "gz_y", "ws3"]
+    rng = np.random.default_rng(int(g["seed"]))
+    f = {n: rng.uniform(0.5, 1.5, (nk + 1, nj, ni)) for n in names}
+    dev = [torch.from_numpy(f[n]).cuda().contiguous() for n in names]
+    ptrs = (ctypes.c_void_p * 9)(*[t.data_ptr() for t in dev])
+    rc = lib.refcuda_update_dz_c(ni, nj, nk, 3, float(g["dt"]), ptrs)
+    torch.cuda.synchronize()
+    assert rc == 0
+    got = {n: t.cpu().numpy() for n, t in zip(names, dev)}
+    assert bit_equal(got["gz"], g["gz"]) and bit_equal(got["ws3"], g["ws3"])
+    for n in names:
+        if n not in ("gz", "ws3"):
+            assert bit_equal(got[n], f[n]), n
