@@ -673,7 +673,7 @@ def refcuda_baseline(workload):
     reach the measured process) and returns its JSON object, or a reason."""
     try:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--refcuda-child", workload],
-                           capture_output=True, text=True, timeout=180)
+                           capture_output=True, text=True, timeout=90)
         lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
         if r.returncode != 0 or not lines:
             return {"error": "child exited with %d: %s" % (r.returncode, r.stderr.strip()[-200:])}
