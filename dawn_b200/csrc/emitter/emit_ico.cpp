@@ -898,7 +898,10 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
   }
   for(int f : scratch_) {
     std::string n = IcoBody::stride(fieldLoc(f));
-    os_ << "    if(int err = m_" << fname(f) << ".ensure(0, " << n << ", k_size)) return err;\n";
+    // a sparse temporary holds sparseSize values per element and level: [k][nbh][element]
+    const std::string levelStride = isSparse(f) ? n + " * " + std::to_string(sparseSize(f)) : n;
+    os_ << "    if(int err = m_" << fname(f) << ".ensure(" << (isSparse(f) ? n : std::string("0")) << ", "
+        << levelStride << ", k_size)) return err;\n";
     os_ << "    ::dawn::float_type* " << fname(f) << "_p = m_" << fname(f) << ".data;\n";
   }
   for(auto const& g : groups) {

@@ -1,0 +1,125 @@
+"""TEST INFRASTRUCTURE: compiles a translation unit emitted by the b200-ico backend for the CPU emulation
+(tests/cpu_emu/emu_cuda.hpp) and runs it on host memory through the module's own C ABI."""
+import ctypes
+import hashlib
+import os
+import re
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+OUT = os.path.join(HERE, "_build")
+
+LAUNCH = re.compile(r"(\w+)<<<\s*([^,>]+?)\s*,\s*([^,>]+?)\s*,[^>]*>>>\(")
+
+
+def emulated_source(code):
+    """`kernel<<<grid, block, smem, stream>>>(args)` -> `EMU_LAUNCH(kernel, grid, block, args)`"""
+    out, n = LAUNCH.subn(r"EMU_LAUNCH(\1, \2, \3, ", code)
+    if n != code.count("<<<"):
+        raise RuntimeError("a kernel launch was not recognised")
+    return out
+
+
+def build(name, code):
+    os.makedirs(OUT, exist_ok=True)
+    src = emulated_source(code)
+    with open(os.path.join(HERE, "emu_rt.cpp")) as f, open(os.path.join(HERE, "emu_cuda.hpp")) as g:
+        tag = hashlib.sha256((src + f.read() + g.read() + "Bsymbolic").encode()).hexdigest()[:12]
+    so = os.path.join(OUT, "%s_%s.so" % (name, tag))
+    if not os.path.exists(so):
+        cpp = os.path.join(OUT, "%s_%s.cpp" % (name, tag))
+        with open(cpp, "w") as f:
+            f.write(src)
+        # one IEEE operation per node, like nvcc -fmad=false
+        # -Bsymbolic: the module must call ITS stand-in runtime even when the real libdawn_b200rt.so has
+        # been loaded into the process with RTLD_GLOBAL by another test
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w",
+                               "-Wl,-Bsymbolic",
+                               "-include", os.path.join(HERE, "emu_cuda.hpp"), "-I", os.path.join(ROOT, "dawn_b200"),
+                               "-o", so, cpp, os.path.join(HERE, "emu_rt.cpp")])
+    return ctypes.CDLL(so)
+
+
+class NbhTable(ctypes.Structure):
+    _fields_ = [("chain", ctypes.c_int * 8), ("chain_len", ctypes.c_int), ("include_center", ctypes.c_int),
+                ("nbh_size", ctypes.c_int), ("table", ctypes.c_void_p)]
+
+
+class Splitter(ctypes.Structure):
+    _fields_ = [("location", ctypes.c_int), ("subdomain", ctypes.c_int), ("offset", ctypes.c_int),
+                ("index", ctypes.c_int)]
+
+
+class MeshStruct(ctypes.Structure):
+    _fields_ = [("num_cells", ctypes.c_int), ("num_edges", ctypes.c_int), ("num_vertices", ctypes.c_int),
+                ("num_tables", ctypes.c_int), ("tables", ctypes.POINTER(NbhTable)), ("num_splitters", ctypes.c_int),
+                ("splitters", ctypes.POINTER(Splitter))]
+
+
+class Field(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("stride_j", ctypes.c_int), ("stride_k", ctypes.c_int)]
+
+
+def run(name, code, info, mesh, k, fields, globals_=None, splitters=None):
+    """Runs module `name` (emitted `code`, module info dict `info`) on `mesh` with `fields` in the oracle's
+    layout (dense [k, n], sparse [k, n, nbh], vertical [k], horizontal [n]); returns the fields afterwards
+    and the number of kernel launches."""
+    lib = build(name, code)
+    keep, entries = [], []
+    for t in info["tables"]:
+        host = np.ascontiguousarray(mesh.nbh_table(list(t["chain"]), bool(t["include_center"]), nbh_size=int(t["size"])),
+                                    dtype=np.int32)
+        soa = np.ascontiguousarray(host.T)                      # [nbh][element], like b200rt_upload_nbh_table
+        keep.append(soa)
+        e = NbhTable()
+        for n, c in enumerate(t["chain"]):
+            e.chain[n] = c
+        e.chain_len, e.include_center, e.nbh_size, e.table = len(t["chain"]), int(t["include_center"]), int(t["size"]), soa.ctypes.data
+        entries.append(e)
+    tabs = (NbhTable * max(1, len(entries)))(*entries)
+    spl = [Splitter(int(l), int(s), int(o), int(i)) for (l, s, o), i in (splitters or {}).items()]
+    spls = (Splitter * max(1, len(spl)))(*spl)
+    ms = MeshStruct(mesh.num_cells, mesh.num_edges, mesh.num_vertices, len(entries), tabs, len(spl), spls)
+    handle = ctypes.c_void_p()
+    lib.b200rt_last_error.restype = ctypes.c_char_p
+    setup = getattr(lib, "setup_" + name)
+    setup.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(MeshStruct), ctypes.c_int, ctypes.c_void_p]
+    if setup(ctypes.byref(handle), ctypes.byref(ms), k, None):
+        raise RuntimeError(lib.b200rt_last_error().decode())
+    for g, v in (globals_ or {}).items():
+        fn = getattr(lib, "set_%s_%s" % (name, g))
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_double]
+        fn(handle, float(v))
+    n_of = {"cells": mesh.num_cells, "edges": mesh.num_edges, "vertices": mesh.num_vertices, "none": 1}
+    dev, fs = [], []
+    for fd in info["fields"]:
+        a = np.array(fields[fd["name"]], dtype=np.float64)
+        if fd["sparse"]:
+            a = np.swapaxes(a, -1, -2)                           # [k, n, nbh] -> [k, nbh, n]
+        a = np.ascontiguousarray(a)
+        dev.append(a)
+        n = n_of[fd["location"]]
+        sp = fd["sparse"] or 1
+        fs.append(Field(a.ctypes.data, n if fd["sparse"] else 0, n * sp))
+    arr = (Field * len(fs))(*fs)
+    runf = getattr(lib, "run_" + name)
+    runf.argtypes = [ctypes.c_void_p, ctypes.POINTER(Field), ctypes.c_int, ctypes.c_void_p]
+    if runf(handle, arr, len(fs), None):
+        raise RuntimeError(lib.b200rt_last_error().decode())
+    launches = getattr(lib, "launches_" + name)
+    launches.restype = ctypes.c_long
+    launches.argtypes = [ctypes.c_void_p]
+    nl = launches(handle)
+    freef = getattr(lib, "free_" + name)
+    freef.argtypes = [ctypes.c_void_p]
+    freef(handle)
+    lib.emu_guard_violations.restype = ctypes.c_long
+    if lib.emu_guard_violations():
+        raise RuntimeError("a kernel of %s wrote outside a scratch allocation" % name)
+    out = {}
+    for fd, a in zip(info["fields"], dev):
+        out[fd["name"]] = np.swapaxes(a, -1, -2) if fd["sparse"] else a
+    return out, nl

@@ -1,0 +1,88 @@
+// TEST INFRASTRUCTURE: host-memory stand-in for the entry points of include/dawn_b200_rt.h that generated
+// b200-ico modules call ("device" memory is plain host memory in the emulation, tests/cpu_emu/emu_cuda.hpp).
+#include "../../include/dawn_b200_rt.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+static thread_local std::string g_err;
+extern "C" {
+const char* b200rt_last_error(void) { return g_err.c_str(); }
+int b200rt_set_error(int code, const char* msg) {
+  g_err = msg ? msg : "";
+  return code;
+}
+// every "device" allocation sits between two guard bands; a kernel that writes past either end of its
+// scratch is counted (emu_guard_violations) when the buffer is freed
+static const size_t kGuard = 4096;
+static long g_violations = 0;
+long emu_guard_violations(void) { return g_violations; }
+int b200rt_malloc(void** p, size_t bytes) {
+  unsigned char* raw = static_cast<unsigned char*>(std::malloc(bytes + 2 * kGuard + sizeof(size_t)));
+  if(!raw)
+    return b200rt_set_error(B200_ERR_CUDA, "emu: out of memory");
+  std::memcpy(raw, &bytes, sizeof(size_t));
+  std::memset(raw + sizeof(size_t), 0xA5, kGuard);
+  std::memset(raw + sizeof(size_t) + kGuard + bytes, 0xA5, kGuard);
+  *p = raw + sizeof(size_t) + kGuard;
+  return 0;
+}
+int b200rt_free(void* p) {
+  if(!p)
+    return 0;
+  unsigned char* user = static_cast<unsigned char*>(p);
+  unsigned char* raw = user - kGuard - sizeof(size_t);
+  size_t bytes;
+  std::memcpy(&bytes, raw, sizeof(size_t));
+  for(size_t n = 0; n < kGuard; ++n)
+    if(raw[sizeof(size_t) + n] != 0xA5 || user[bytes + n] != 0xA5) {
+      ++g_violations;
+      break;
+    }
+  std::free(raw);
+  return 0;
+}
+int b200rt_memset(void* p, int v, size_t bytes, void*) {
+  std::memset(p, v, bytes);
+  return 0;
+}
+int b200rt_memcpy_h2d(void* d, const void* s, size_t n, void*) {
+  std::memcpy(d, s, n);
+  return 0;
+}
+int b200rt_memcpy_d2h(void* d, const void* s, size_t n, void*) {
+  std::memcpy(d, s, n);
+  return 0;
+}
+int b200rt_stream_synchronize(void*) { return 0; }
+int b200rt_check_last_launch(void) { return 0; }
+int b200rt_event_create(void** e) {
+  *e = std::malloc(1);
+  return 0;
+}
+int b200rt_event_destroy(void* e) {
+  std::free(e);
+  return 0;
+}
+int b200rt_event_record(void*, void*) { return 0; }
+int b200rt_event_synchronize(void*) { return 0; }
+int b200rt_event_elapsed_ms(void*, void*, float* ms) {
+  *ms = 0.f;
+  return 0;
+}
+// the *_from_host / verify paths are GPU-tested (tests/test_unstructured_gpu.py); not part of the emulation
+int b200rt_reshape(const double*, double*, int, int, int, void*) {
+  return b200rt_set_error(B200_ERR_RUNTIME, "emu: b200rt_reshape is not emulated");
+}
+int b200rt_reshape_back(const double*, double*, int, int, int, void*) {
+  return b200rt_set_error(B200_ERR_RUNTIME, "emu: b200rt_reshape_back is not emulated");
+}
+int b200rt_verify_field(const double*, const double*, size_t, double, double, int, b200_verification_metrics*,
+                        void*) {
+  return b200rt_set_error(B200_ERR_RUNTIME, "emu: b200rt_verify_field is not emulated");
+}
+int b200rt_metrics_record_add(b200_metrics_record*, const char*, const char*, const b200_verification_metrics*) {
+  return 0;
+}
+}

@@ -1,0 +1,151 @@
+"""CPU emulation of EMITTED b200-ico kernels (tests/cpu_emu): every unstructured stencil fixture is
+generated, compiled with g++ behind a thin CUDA stand-in and executed thread by thread on host memory
+through the module's own C ABI, then compared with the oracle bit for bit.  This checks the logic of the
+emitted code - indexing, neighbour order, stage fusion and co-scheduling, register forwarding, scratch
+temporaries, splitter ranges, centre-including chains - on machines without a GPU; the GPU tests check the
+same modules as the hardware runs them."""
+import glob
+import json
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+from util import ROOT, bit_equal, iir_path
+from oracle import naive_interp
+from dawn_b200 import codegen, reorder as ro
+from dawn_b200.trimesh import CELL, EDGE, VERTEX, TriMesh
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpu_emu"))
+import build as emu  # noqa: E402
+
+LOC = {"cells": CELL, "edges": EDGE, "vertices": VERTEX}
+UNSTRUCTURED = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(ROOT, "stencils", "*.iir"))
+                      if '"gridType": "Unstructured"' in open(p).read())
+
+
+def emitted(name, **opts):
+    code = codegen.compile_iir(open(iir_path(name)).read(), backend="b200-ico", **opts)
+    info = json.loads(re.search(r'return "(\{.*\})";', code).group(1).encode().decode("unicode_escape"))
+    return code, info
+
+
+def random_fields(info, m, k, rng):
+    f = {}
+    for fd in info["fields"]:
+        shape = []
+        if fd.get("k", 1):
+            shape.append(k)
+        if fd["location"] != "none":
+            shape.append(m.num(LOC[fd["location"]]))
+        if fd["sparse"]:
+            shape.append(fd["sparse"])
+        f[fd["name"]] = rng.uniform(0.5, 1.5, shape)
+    return f
+
+
+def with_temporaries(name, m, k, fields):
+    """the oracle wants storage for the stencil's temporaries as well"""
+    d = json.load(open(iir_path(name)))["metadata"]
+    out = {n: v.copy() for n, v in fields.items()}
+    for aid in d.get("temporaryFieldIDs", []):
+        dims = d["fieldIDtoDimensions"][str(aid)]
+        chain = dims["unstructured_horizontal_dimension"]["iter_space"]["chain"]
+        shape = [k] if dims.get("mask_k", 1) else []
+        shape.append(m.num(chain[0]))
+        if len(chain) > 1:
+            center = dims["unstructured_horizontal_dimension"]["iter_space"].get("include_center", False)
+            shape.append(m.nbh_table(chain, center).shape[1])
+        out.setdefault(d["accessIDToName"][str(aid)], np.zeros(shape))
+    return out
+
+
+def compare(info, m, got, want):
+    for fd in info["fields"]:
+        n = fd["name"]
+        if fd["location"] == "none":
+            assert bit_equal(got[n], want[n]), n
+            continue
+        v = m.valid(LOC[fd["location"]])
+        axis = 1 if fd.get("k", 1) else 0
+        assert bit_equal(np.compress(v, got[n], axis=axis), np.compress(v, want[n], axis=axis)), n
+
+
+def test_the_fixture_list_is_what_we_think_it_is():
+    assert len(UNSTRUCTURED) >= 50 and {"ICON_laplacian_stencil", "ICON_nabla4_stencil", "fuzzico_15",
+                                        "ICON_laplacian_diamond_stencil", "reductionWithCenterSparse",
+                                        "generate_versioned_field", "sparseAssignment5"} <= set(UNSTRUCTURED)
+
+
+@pytest.mark.parametrize("name", UNSTRUCTURED)
+def test_emitted_kernels_match_the_oracle_on_the_cpu(name):
+    code, info = emitted(name)
+    for (nx, ny, k) in ((9, 7, 5), (13, 10, 9)):
+        m = TriMesh(nx, ny)
+        rng = np.random.default_rng(300 + len(name))
+        f = random_fields(info, m, k, rng)
+        g, spl = None, None
+        if name == "tridiagonalSolve":
+            f["b"] += 4.0
+        if name == "verticalIndirecion":
+            f["kidx"] = np.zeros((k, m.num_cells)) + np.arange(k, dtype=float)[:, None] + 1
+            f["kidx"][: k - 1] = rng.integers(0, k, (k - 1, m.num_cells)).astype(float)
+        if name == "iterationSpaceUnstructured":
+            spl = {(CELL, 2000, 0): 10, (CELL, 3000, 0): 60, (CELL, 4000, 0): 100}
+        if name == "generate_versioned_field":
+            f["d"] = (f["d"] < 0.9).astype(float)
+            f["e"] = (f["e"] < 1.0).astype(float) * 3.0
+        if info.get("globals"):
+            g = {n: 0.625 for n in info["globals"]}
+        want = naive_interp.run_unstructured(iir_path(name), m, k, with_temporaries(name, m, k, f),
+                                             globals_=g, splitters=spl)
+        got, launches = emu.run(name, code, info, m, k, f, globals_=g, splitters=spl)
+        compare(info, m, got, want)
+        assert launches == info["kernels"] or launches <= info["kernels"]
+
+
+@pytest.mark.parametrize("opts", [dict(fuse_columns=0, levels_per_thread=1), dict(co_schedule=0),
+                                  dict(levels_per_thread=3)])
+@pytest.mark.parametrize("name", ["ICON_laplacian_stencil", "ICON_nabla4_stencil", "ICON_laplacian_diamond_stencil",
+                                  "fuzzico_03", "fuzzico_11", "sparseAssignment5", "nestedWithSparse"])
+def test_emitter_variants_on_the_cpu(name, opts):
+    code, info = emitted(name, **opts)
+    m, k = TriMesh(11, 8), 7
+    f = random_fields(info, m, k, np.random.default_rng(17))
+    g = {n: 0.625 for n in info["globals"]} if info.get("globals") else None
+    want = naive_interp.run_unstructured(iir_path(name), m, k, with_temporaries(name, m, k, f), globals_=g)
+    got, _ = emu.run(name, code, info, m, k, f, globals_=g)
+    compare(info, m, got, want)
+
+
+@pytest.mark.parametrize("method", ["random", "rcm", "morton"])
+def test_renumbered_mesh_through_the_emitted_kernels(method):
+    # same kernels, renumbered tables (dawn_b200/reorder.py): maps back to the undivided oracle run
+    name = "ICON_laplacian_stencil"
+    code, info = emitted(name)
+    m, k = TriMesh(12, 9), 4
+    f = random_fields(info, m, k, np.random.default_rng(18))
+    want = naive_interp.run_unstructured(iir_path(name), m, k, with_temporaries(name, m, k, f))
+    rm = ro.ReorderedMesh(m, ro.Renumbering.random(m, 19)) if method == "random" else ro.reorder(m, method)
+    r = rm.renumbering
+    loc_of = {fd["name"]: LOC[fd["location"]] for fd in info["fields"]}
+    got, _ = emu.run(name, code, info, rm, k, {n: np.ascontiguousarray(r.to_new(loc_of[n], v, axis=1))
+                                               for n, v in f.items()})
+    for n in ("rot_vec", "div_vec", "nabla2_vec"):
+        v = m.valid(loc_of[n])
+        assert bit_equal(r.to_old(loc_of[n], got[n], axis=1)[:, v], want[n][:, v]), n
+
+
+def test_the_emulation_catches_an_undersized_scratch():
+    # regression for a defect this emulation found: a sparse temporary's scratch was sized like a dense one
+    # ([k][element] instead of [k][nbh][element]) - on a GPU a silent out-of-bounds write
+    name = "sparseTempFieldAllocation"
+    code, info = emitted(name)
+    assert "m_tmp_field.ensure(n_cells, n_cells * 3, k_size)" in code
+    bad = code.replace("m_tmp_field.ensure(n_cells, n_cells * 3, k_size)", "m_tmp_field.ensure(0, n_cells, k_size)")
+    m, k = TriMesh(6, 5), 2
+    f = {"in_field": np.ones((k, m.num_cells)), "out_field": np.zeros((k, m.num_cells))}
+    with pytest.raises(RuntimeError, match="outside a scratch allocation"):
+        emu.run(name, bad, info, m, k, f)
