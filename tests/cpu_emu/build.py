@@ -123,3 +123,48 @@ def run(name, code, info, mesh, k, fields, globals_=None, splitters=None):
     for fd, a in zip(info["fields"], dev):
         out[fd["name"]] = np.swapaxes(a, -1, -2) if fd["sparse"] else a
     return out, nl
+
+
+def run_cartesian(name, code, info, dims, halos, fields, globals_=None):
+    """Runs an emitted Cartesian module (plain kernels: no TMA, no barriers) on dense host arrays
+    [k][j][i] (masked dimensions have length 1) and returns them with the launch count."""
+    if "__syncthreads" in code or "tma::" in code:
+        raise RuntimeError("only barrier-free plain kernels can be run thread by thread")
+    lib = build(name, code)
+    ni, nj, nk = dims
+    handle = ctypes.c_void_p()
+    lib.b200rt_last_error.restype = ctypes.c_char_p
+    setup = getattr(lib, "setup_" + name)
+    setup.argtypes = [ctypes.POINTER(ctypes.c_void_p)] + [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
+    if setup(ctypes.byref(handle), ni, nj, nk, (ctypes.c_int * 6)(*halos), None):
+        raise RuntimeError(lib.b200rt_last_error().decode())
+    for g, v in (globals_ or {}).items():
+        fn = getattr(lib, "set_%s_%s" % (name, g))
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_double]
+        fn(handle, float(v))
+    dev, fs = [], []
+    for fd in info["fields"]:
+        a = np.ascontiguousarray(np.array(fields[fd["name"]], dtype=np.float64))
+        dev.append(a)
+        d = fd["dims"]
+        li = a.shape[2] if "i" in d else 1
+        lj = a.shape[1] if "j" in d else 1
+        sj = (li if "j" in d else 0)
+        sk = (li * lj if "k" in d else 0)
+        fs.append(Field(a.ctypes.data, sj, sk))
+    arr = (Field * len(fs))(*fs)
+    runf = getattr(lib, "run_" + name)
+    runf.argtypes = [ctypes.c_void_p, ctypes.POINTER(Field), ctypes.c_int, ctypes.c_void_p]
+    if runf(handle, arr, len(fs), None):
+        raise RuntimeError(lib.b200rt_last_error().decode())
+    launches = getattr(lib, "launches_" + name)
+    launches.restype = ctypes.c_long
+    launches.argtypes = [ctypes.c_void_p]
+    nl = launches(handle)
+    freef = getattr(lib, "free_" + name)
+    freef.argtypes = [ctypes.c_void_p]
+    freef(handle)
+    lib.emu_guard_violations.restype = ctypes.c_long
+    if lib.emu_guard_violations():
+        raise RuntimeError("a kernel of %s wrote outside a scratch allocation" % name)
+    return {fd["name"]: a for fd, a in zip(info["fields"], dev)}, nl

@@ -1,5 +1,5 @@
-"""CPU emulation of EMITTED b200-ico kernels (tests/cpu_emu): every unstructured stencil fixture is
-generated, compiled with g++ behind a thin CUDA stand-in and executed thread by thread on host memory
+"""CPU emulation of EMITTED kernels (tests/cpu_emu): every unstructured stencil fixture - and, at the end of
+this file, the plain (barrier-free) kernels of the Cartesian ones - is generated, compiled with g++ behind a thin CUDA stand-in and executed thread by thread on host memory
 through the module's own C ABI, then compared with the oracle bit for bit.  This checks the logic of the
 emitted code - indexing, neighbour order, stage fusion and co-scheduling, register forwarding, scratch
 temporaries, splitter ranges, centre-including chains - on machines without a GPU; the GPU tests check the
@@ -149,3 +149,47 @@ def test_the_emulation_catches_an_undersized_scratch():
     f = {"in_field": np.ones((k, m.num_cells)), "out_field": np.zeros((k, m.num_cells))}
     with pytest.raises(RuntimeError, match="outside a scratch allocation"):
         emu.run(name, bad, info, m, k, f)
+
+
+# ---- Cartesian: the PLAIN kernels (no TMA staging, temporaries recomputed in registers, no barriers) of
+# every Cartesian fixture run thread by thread as well; the TMA / shared-memory variants are GPU-only ---------
+from util import HALO, run_oracle  # noqa: E402
+
+CARTESIAN = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(ROOT, "stencils", "*.iir"))
+                   if '"gridType": "Cartesian"' in open(p).read())
+CART_GLOBALS = {"p_grad_c": {"hydrostatic": 1, "dt2": 0.5}, "laplacian_stencil": {"dx": 0.25},
+                "globals_stencil": {"var_runtime": 1, "var_default": 2.0, "var_compiletime": 1},
+                "stencil_desc_ast_03": {"var_runtime": 1, "var_compiletime": 2},
+                "stencil_desc_ast_04": {"var_runtime": 1, "var_compiletime": 2},
+                "stencil_desc_ast_07": {"var_runtime": 1, "var_compiletime": 2}}
+
+
+def emitted_cartesian(name):
+    code = codegen.compile_iir(open(iir_path(name)).read(), backend="b200", use_tma=0, column_ring=0)
+    info = json.loads(re.search(r'return "(\{.*\})";', code).group(1).encode().decode("unicode_escape"))
+    return code, info
+
+
+@pytest.mark.parametrize("name", CARTESIAN)
+def test_plain_cartesian_kernels_match_the_oracle_on_the_cpu(name):
+    code, info = emitted_cartesian(name)
+    if "__syncthreads" in code:
+        pytest.skip("stages hand temporaries over through scratch behind a block barrier: GPU-only")
+    for (I, J, K) in ((17, 11, 12), (29, 19, 24)):   # the interval fixtures name levels up to k_start + 11
+        ni, nj = I + 2 * HALO, J + 2 * HALO
+        rng = np.random.default_rng(400 + len(name))
+        f = {}
+        for fd in info["fields"]:
+            d = fd["dims"]
+            f[fd["name"]] = rng.uniform(0.5, 1.5, (K + 1 if "k" in d else 1, nj if "j" in d else 1,
+                                                   ni if "i" in d else 1))
+        if name in ("tridiagonal_solve", "kparallel_solver") and "b" in f:
+            f["b"] += 4.0
+        g = CART_GLOBALS.get(name)
+        if g is None and info.get("globals"):
+            g = {n: 0.375 for n in info["globals"]}
+        want = run_oracle(name, (ni, nj, K), f, globals_=g)
+        got, _ = emu.run_cartesian(name, code, info, (ni, nj, K), (HALO, HALO, HALO, HALO, 0, 0), f, globals_=g)
+        for fd in info["fields"]:
+            n = fd["name"]
+            assert bit_equal(got[n].reshape(want[n].shape), want[n]), (name, n, (I, J, K))
