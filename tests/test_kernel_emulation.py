@@ -151,8 +151,9 @@ def test_the_emulation_catches_an_undersized_scratch():
         emu.run(name, bad, info, m, k, f)
 
 
-# ---- Cartesian: the PLAIN kernels (no TMA staging, temporaries recomputed in registers, no barriers) of
-# every Cartesian fixture run thread by thread as well; the TMA / shared-memory variants are GPU-only ---------
+# ---- Cartesian: the PLAIN kernels (no TMA staging) of every Cartesian fixture run on the CPU as well - thread
+# by thread, or, where stages hand temporaries over through scratch behind __syncthreads(), with the threads of
+# a block as host threads meeting at a barrier; the TMA / shared-memory variants are GPU-only ---------
 from util import HALO, run_oracle  # noqa: E402
 
 CARTESIAN = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(ROOT, "stencils", "*.iir"))
@@ -172,9 +173,7 @@ def emitted_cartesian(name):
 
 @pytest.mark.parametrize("name", CARTESIAN)
 def test_plain_cartesian_kernels_match_the_oracle_on_the_cpu(name):
-    code, info = emitted_cartesian(name)
-    if "__syncthreads" in code:
-        pytest.skip("stages hand temporaries over through scratch behind a block barrier: GPU-only")
+    code, info = emitted_cartesian(name)   # kernels with __syncthreads() run their blocks as host threads
     for (I, J, K) in ((17, 11, 12), (29, 19, 24)):   # the interval fixtures name levels up to k_start + 11
         ni, nj = I + 2 * HALO, J + 2 * HALO
         rng = np.random.default_rng(400 + len(name))
@@ -193,3 +192,25 @@ def test_plain_cartesian_kernels_match_the_oracle_on_the_cpu(name):
         for fd in info["fields"]:
             n = fd["name"]
             assert bit_equal(got[n].reshape(want[n].shape), want[n]), (name, n, (I, J, K))
+
+
+@pytest.mark.parametrize("name", ["hori_diff_type2_stencil", "lap", "hd_smagorinsky_stencil", "hori_diff_stencil_02",
+                                  "kcache_epflush", "fuzz_02", "fuzz_07", "fuzz_11"])
+def test_staged_temporaries_variant_on_the_cpu(name):
+    # inline_temporaries=0: temporaries go through global scratch, computed redundantly on each tile's stage
+    # extent, consumers behind a block barrier (the general fallback of the planner)
+    code = codegen.compile_iir(open(iir_path(name)).read(), backend="b200", use_tma=0, column_ring=0,
+                               inline_temporaries=0)
+    info = json.loads(re.search(r'return "(\{.*\})";', code).group(1).encode().decode("unicode_escape"))
+    I, J, K = 37, 21, 12
+    ni, nj = I + 2 * HALO, J + 2 * HALO
+    rng = np.random.default_rng(23)
+    f = {}
+    for fd in info["fields"]:
+        d = fd["dims"]
+        f[fd["name"]] = rng.uniform(0.5, 1.5, (K + 1 if "k" in d else 1, nj if "j" in d else 1, ni if "i" in d else 1))
+    g = {n: 0.375 for n in info["globals"]} if info.get("globals") else None
+    want = run_oracle(name, (ni, nj, K), f, globals_=g)
+    got, _ = emu.run_cartesian(name, code, info, (ni, nj, K), (HALO, HALO, HALO, HALO, 0, 0), f, globals_=g)
+    for fd in info["fields"]:
+        assert bit_equal(got[fd["name"]].reshape(want[fd["name"]].shape), want[fd["name"]]), fd["name"]
