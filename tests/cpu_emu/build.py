@@ -12,12 +12,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, "_build")
 
-LAUNCH = re.compile(r"(\w+)<<<\s*([^,>]+?)\s*,\s*([^,>]+?)\s*,[^>]*>>>\(")
+LAUNCH = re.compile(r"(\w+)<<<\s*([^,>]+?)\s*,\s*([^,>]+?)\s*,\s*([^,>]+?)\s*,[^>]*>>>\(")
+DYN_SMEM = "extern __shared__ __align__(128) unsigned char b200_smem[];"
 
 
 def emulated_source(code):
-    """`kernel<<<grid, block, smem, stream>>>(args)` -> `EMU_LAUNCH(kernel, grid, block, args)`"""
-    out, n = LAUNCH.subn(r"EMU_LAUNCH(\1, \2, \3, ", code)
+    """`kernel<<<grid, block, smem, stream>>>(args)` -> `EMU_LAUNCH(kernel, grid, block, smem, args)`; the
+    dynamic shared memory of a kernel becomes the per-block buffer the launcher provides"""
+    out, n = LAUNCH.subn(r"EMU_LAUNCH(\1, \2, \3, \4, ", code)
+    out = out.replace(DYN_SMEM, "unsigned char* const b200_smem = emu_dynamic_smem;")
+    out = out.replace("extern __shared__ ::dawn::float_type cc_smem[];",
+                      "::dawn::float_type* const cc_smem = reinterpret_cast<::dawn::float_type*>(emu_dynamic_smem);")
+    if "extern __shared__" in out:
+        raise RuntimeError("a dynamic shared memory declaration was not recognised")
     if n != code.count("<<<"):
         raise RuntimeError("a kernel launch was not recognised")
     return out
@@ -27,7 +34,7 @@ def build(name, code):
     os.makedirs(OUT, exist_ok=True)
     src = emulated_source(code)
     # kernels with block barriers run their threads as host threads (EMU_BLOCK_THREADS), the others serially
-    threads = ["-DEMU_BLOCK_THREADS", "-pthread"] if "__syncthreads" in src else []
+    threads = ["-DEMU_BLOCK_THREADS", "-pthread"] if ("__syncthreads" in src or "tma::" in src) else []
     with open(os.path.join(HERE, "emu_rt.cpp")) as f, open(os.path.join(HERE, "emu_cuda.hpp")) as g:
         tag = hashlib.sha256((src + f.read() + g.read() + "Bsymbolic" + "".join(threads)).encode()).hexdigest()[:12]
     so = os.path.join(OUT, "%s_%s.so" % (name, tag))
@@ -130,8 +137,6 @@ def run(name, code, info, mesh, k, fields, globals_=None, splitters=None):
 def run_cartesian(name, code, info, dims, halos, fields, globals_=None):
     """Runs an emitted Cartesian module (plain kernels: no TMA, no barriers) on dense host arrays
     [k][j][i] (masked dimensions have length 1) and returns them with the launch count."""
-    if "tma::" in code:
-        raise RuntimeError("TMA kernels are GPU-only")
     lib = build(name, code)
     ni, nj, nk = dims
     handle = ctypes.c_void_p()
@@ -144,9 +149,18 @@ def run_cartesian(name, code, info, dims, halos, fields, globals_=None):
         fn = getattr(lib, "set_%s_%s" % (name, g))
         fn.argtypes = [ctypes.c_void_p, ctypes.c_double]
         fn(handle, float(v))
-    dev, fs = [], []
+    dev, fs, keep = [], [], []
     for fd in info["fields"]:
-        a = np.ascontiguousarray(np.array(fields[fd["name"]], dtype=np.float64))
+        src = np.ascontiguousarray(np.array(fields[fd["name"]], dtype=np.float64))
+        # like dawn_b200.Storage: a lead pad puts the first interior point (i = halo) on a 16-byte boundary,
+        # which the TMA variants ask for (the launcher falls back to the plain kernel otherwise)
+        raw = np.zeros(src.size + 4)
+        lead = 0
+        while (raw.ctypes.data + 8 * (lead + (halos[0] if "i" in fd["dims"] else 0))) % 16:
+            lead += 1
+        a = raw[lead:lead + src.size].reshape(src.shape)
+        a[...] = src
+        keep.append(raw)
         dev.append(a)
         d = fd["dims"]
         li = a.shape[2] if "i" in d else 1
@@ -169,4 +183,6 @@ def run_cartesian(name, code, info, dims, halos, fields, globals_=None):
     lib.emu_guard_violations.restype = ctypes.c_long
     if lib.emu_guard_violations():
         raise RuntimeError("a kernel of %s wrote outside a scratch allocation" % name)
+    lib.emu_tensor_maps_encoded.restype = ctypes.c_long
+    run_cartesian.tensor_maps = lib.emu_tensor_maps_encoded()   # > 0: the TMA variant of a kernel was chosen
     return {fd["name"]: a for fd, a in zip(info["fields"], dev)}, nl

@@ -71,6 +71,24 @@ int b200rt_event_elapsed_ms(void*, void*, float* ms) {
   *ms = 0.f;
   return 0;
 }
+// CUtensorMap stand-in: the geometry itself (struct emu_tensor_map of emu_cuda.hpp)
+struct emu_tensor_map_rt {
+  const double* base;
+  int size[3];
+  long long stride[3];
+  int box[3];
+};
+static long g_tensor_maps = 0;
+long emu_tensor_maps_encoded(void) { return g_tensor_maps; }
+int b200rt_tensor_map_3d(void* map, const void* base, int size_i, int size_j, int size_k, int stride_j,
+                         int stride_k, int box_i, int box_j, int box_k) {
+  ++g_tensor_maps;
+  emu_tensor_map_rt m{static_cast<const double*>(base), {size_i, size_j, size_k}, {1, stride_j, stride_k},
+                      {box_i, box_j, box_k}};
+  std::memset(map, 0, 128);
+  std::memcpy(map, &m, sizeof(m));
+  return 0;
+}
 // the *_from_host / verify paths are GPU-tested (tests/test_unstructured_gpu.py); not part of the emulation
 int b200rt_reshape(const double*, double*, int, int, int, void*) {
   return b200rt_set_error(B200_ERR_RUNTIME, "emu: b200rt_reshape is not emulated");

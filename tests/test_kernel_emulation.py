@@ -214,3 +214,52 @@ def test_staged_temporaries_variant_on_the_cpu(name):
     got, _ = emu.run_cartesian(name, code, info, (ni, nj, K), (HALO, HALO, HALO, HALO, 0, 0), f, globals_=g)
     for fd in info["fields"]:
         assert bit_equal(got[fd["name"]].reshape(want[fd["name"]].shape), want[fd["name"]]), fd["name"]
+
+
+# ---- the DEFAULT kernels: TMA-staged tiles and column rings.  The emulation stands in for the hardware pieces
+# (tests/cpu_emu/emu_cuda.hpp): a bulk tensor load copies its box at once with zero fill outside the tensor and
+# completes its bytes on an mbarrier word, wait(parity) blocks on the phase, dynamic shared memory is a per-block
+# buffer, the threads of a block are host threads.  What is checked is the emitted logic - slot arithmetic,
+# phase parities, box origins and extents, micro-tile indexing, drain / refill order, prologue placement. --------
+def _cartesian_case(name, code, info, size, seed, globals_=None):
+    I, J, K = size
+    ni, nj = I + 2 * HALO, J + 2 * HALO
+    rng = np.random.default_rng(seed)
+    f = {}
+    for fd in info["fields"]:
+        d = fd["dims"]
+        f[fd["name"]] = rng.uniform(0.5, 1.5, (K + 1 if "k" in d else 1, nj if "j" in d else 1, ni if "i" in d else 1))
+    if name in ("tridiagonal_solve", "kparallel_solver") and "b" in f:
+        f["b"] += 4.0
+    g = globals_ if globals_ is not None else CART_GLOBALS.get(name)
+    if g is None and info.get("globals"):
+        g = {n: 0.375 for n in info["globals"]}
+    want = run_oracle(name, (ni, nj, K), f, globals_=g)
+    got, _ = emu.run_cartesian(name, code, info, (ni, nj, K), (HALO, HALO, HALO, HALO, 0, 0), f, globals_=g)
+    for fd in info["fields"]:
+        n = fd["name"]
+        assert bit_equal(got[n].reshape(want[n].shape), want[n]), (name, n, size)
+    return emu.run_cartesian.tensor_maps
+
+
+@pytest.mark.parametrize("name", CARTESIAN)
+def test_default_cartesian_kernels_match_the_oracle_on_the_cpu(name):
+    code = codegen.compile_iir(open(iir_path(name)).read(), backend="b200")
+    info = json.loads(re.search(r'return "(\{.*\})";', code).group(1).encode().decode("unicode_escape"))
+    maps = 0
+    for size in ((34, 11, 12), (70, 26, 24)):            # even row lengths: TMA needs 16-byte aligned rows
+        maps = _cartesian_case(name, code, info, size, 500 + len(name))
+    if "tma::" in code:
+        assert maps > 0, "the TMA variant was emitted but the plain one ran"
+
+
+@pytest.mark.parametrize("name,opts", [(n, o) for n in ("hori_diff_type2_stencil", "tridiagonal_solve")
+                                       for o in __import__("dawn_b200.build", fromlist=["VARIANTS"]).VARIANTS[n]],
+                         ids=lambda v: v if isinstance(v, str) else ",".join("%s=%s" % kv for kv in v.items()))
+def test_planner_variants_of_the_headline_kernels_on_the_cpu(name, opts):
+    if opts.get("ring_stagger"):
+        pytest.skip("reads the environment and sleeps: timing knob, not logic")
+    code = codegen.compile_iir(open(iir_path(name)).read(), backend="b200", **opts)
+    info = json.loads(re.search(r'return "(\{.*\})";', code).group(1).encode().decode("unicode_escape"))
+    for size in ((70, 26, 12), (130, 13, 37)):
+        _cartesian_case(name, code, info, size, 600)
