@@ -30,9 +30,14 @@ def emulated_source(code):
     return out
 
 
-def build(name, code):
+def build(name, code, keep_k_chunks=True):
     os.makedirs(OUT, exist_ok=True)
     src = emulated_source(code)
+    if keep_k_chunks:
+        # generated launchers split k finer while a launch has fewer than 2 blocks per SM (296 blocks): on the
+        # small domains an emulation can afford that leaves 2 levels per block and the steady state of the
+        # TMA ring (refill while consuming) would never run - keep the planned chunk instead
+        src = src.replace(" < 296) kchunk = (kchunk + 1) / 2;", " < 0) kchunk = (kchunk + 1) / 2;")
     # kernels with block barriers run their threads as host threads (EMU_BLOCK_THREADS), the others serially
     threads = ["-DEMU_BLOCK_THREADS", "-pthread"] if ("__syncthreads" in src or "tma::" in src) else []
     with open(os.path.join(HERE, "emu_rt.cpp")) as f, open(os.path.join(HERE, "emu_cuda.hpp")) as g:
@@ -134,10 +139,10 @@ def run(name, code, info, mesh, k, fields, globals_=None, splitters=None):
     return out, nl
 
 
-def run_cartesian(name, code, info, dims, halos, fields, globals_=None):
+def run_cartesian(name, code, info, dims, halos, fields, globals_=None, keep_k_chunks=True):
     """Runs an emitted Cartesian module (plain kernels: no TMA, no barriers) on dense host arrays
     [k][j][i] (masked dimensions have length 1) and returns them with the launch count."""
-    lib = build(name, code)
+    lib = build(name, code, keep_k_chunks)
     ni, nj, nk = dims
     handle = ctypes.c_void_p()
     lib.b200rt_last_error.restype = ctypes.c_char_p

@@ -263,3 +263,35 @@ def test_planner_variants_of_the_headline_kernels_on_the_cpu(name, opts):
     info = json.loads(re.search(r'return "(\{.*\})";', code).group(1).encode().decode("unicode_escape"))
     for size in ((70, 26, 12), (130, 13, 37)):
         _cartesian_case(name, code, info, size, 600)
+
+
+@pytest.mark.parametrize("mutation", ["prefetch level", "box row", "hdmask slot offset"])
+def test_the_emulation_notices_a_broken_tma_pipeline(mutation):
+    # the harness must have teeth: a wrong level in the refill, a shifted box or a wrong slot offset in the
+    # emitted TMA code has to show up as a mismatch against the oracle
+    name = "hori_diff_type2_stencil"
+    code = codegen.compile_iir(open(iir_path(name)).read(), backend="b200")
+    info = json.loads(re.search(r'return "(\{.*\})";', code).group(1).encode().decode("unicode_escape"))
+    bad = {"prefetch level": code.replace("&tm_in, i0 + (0), j0 + (0), kb + (it + 2),", "&tm_in, i0 + (0), j0 + (0), kb + (it + 1),"),
+           "box row": code.replace("&tm_in, i0 + (0), j0 + (0), kb + q,", "&tm_in, i0 + (0), j0 + (1), kb + q,"),
+           "hdmask slot offset": code.replace("tma_ring + ts * 2128 + 1232, &tm_hdmask", "tma_ring + ts * 2128 + 1230, &tm_hdmask")}[mutation]
+    assert bad != code
+    _cartesian_case(name, code, info, (70, 26, 12), 700)
+    with pytest.raises(AssertionError):
+        _cartesian_case(name, bad, info, (70, 26, 12), 700)
+
+
+def test_small_launch_k_split_on_the_cpu():
+    # the launcher's own rule for small launches (k split finer until 2 blocks per SM exist) stays covered too
+    for name in ("hori_diff_type2_stencil", "lap"):
+        code = codegen.compile_iir(open(iir_path(name)).read(), backend="b200")
+        info = json.loads(re.search(r'return "(\{.*\})";', code).group(1).encode().decode("unicode_escape"))
+        I, J, K = 70, 26, 12
+        ni, nj = I + 2 * HALO, J + 2 * HALO
+        rng = np.random.default_rng(800)
+        f = {fd["name"]: rng.uniform(0.5, 1.5, (K + 1 if "k" in fd["dims"] else 1, nj if "j" in fd["dims"] else 1,
+                                                ni if "i" in fd["dims"] else 1)) for fd in info["fields"]}
+        want = run_oracle(name, (ni, nj, K), f)
+        got, _ = emu.run_cartesian(name, code, info, (ni, nj, K), (HALO, HALO, HALO, HALO, 0, 0), f, keep_k_chunks=False)
+        for fd in info["fields"]:
+            assert bit_equal(got[fd["name"]].reshape(want[fd["name"]].shape), want[fd["name"]]), fd["name"]
