@@ -154,25 +154,35 @@ def run_cartesian(name, code, info, dims, halos, fields, globals_=None, keep_k_c
         fn = getattr(lib, "set_%s_%s" % (name, g))
         fn.argtypes = [ctypes.c_void_p, ctypes.c_double]
         fn(handle, float(v))
-    dev, fs, keep = [], [], []
+    dev, fs, keep, views = [], [], [], []
     for fd in info["fields"]:
         src = np.ascontiguousarray(np.array(fields[fd["name"]], dtype=np.float64))
-        # like dawn_b200.Storage: a lead pad puts the first interior point (i = halo) on a 16-byte boundary,
-        # which the TMA variants ask for (the launcher falls back to the plain kernel otherwise)
-        raw = np.zeros(src.size + 4)
-        lead = 0
-        while (raw.ctypes.data + 8 * (lead + (halos[0] if "i" in fd["dims"] else 0))) % 16:
-            lead += 1
-        a = raw[lead:lead + src.size].reshape(src.shape)
-        a[...] = src
-        keep.append(raw)
-        dev.append(a)
+        # the layout of dawn_b200.Storage / driver-includes storage_info: rows padded to 16 elements, a lead pad
+        # that puts the first interior point (i = halo) on a 128-byte line; wrapper-allocated fields of a
+        # generated class get exactly this layout and the launchers insist that all ijk fields share strides
         d = fd["dims"]
-        li = a.shape[2] if "i" in d else 1
-        lj = a.shape[1] if "j" in d else 1
-        sj = (li if "j" in d else 0)
-        sk = (li * lj if "k" in d else 0)
-        fs.append(Field(a.ctypes.data, sj, sk))
+        lk, lj, li = src.shape
+        h = halos[0]
+        s_, lead, sj, sk = 1, 0, 0, 0
+        if "i" in d:
+            lead = (16 - h % 16) % 16
+            s_ = (li + 15) // 16 * 16
+        if "j" in d:
+            sj = s_
+            s_ *= lj
+        if "k" in d:
+            sk = s_
+            s_ *= lk
+        raw = np.zeros(s_ + lead + 16 + 32)
+        off = 0
+        while (raw.ctypes.data + 8 * off) % 256:
+            off += 1
+        base = raw[off + lead:]
+        view = np.lib.stride_tricks.as_strided(base, shape=(lk, lj, li), strides=(8 * sk, 8 * sj, 8))
+        view[...] = src
+        keep.append(raw)
+        views.append(view)
+        fs.append(Field(base.ctypes.data, sj, sk))
     arr = (Field * len(fs))(*fs)
     runf = getattr(lib, "run_" + name)
     runf.argtypes = [ctypes.c_void_p, ctypes.POINTER(Field), ctypes.c_int, ctypes.c_void_p]
@@ -190,4 +200,4 @@ def run_cartesian(name, code, info, dims, halos, fields, globals_=None, keep_k_c
         raise RuntimeError("a kernel of %s wrote outside a scratch allocation" % name)
     lib.emu_tensor_maps_encoded.restype = ctypes.c_long
     run_cartesian.tensor_maps = lib.emu_tensor_maps_encoded()   # > 0: the TMA variant of a kernel was chosen
-    return {fd["name"]: a for fd, a in zip(info["fields"], dev)}, nl
+    return {fd["name"]: np.array(v) for fd, v in zip(info["fields"], views)}, nl

@@ -43,6 +43,12 @@ int b200rt_free(void* p) {
   std::free(raw);
   return 0;
 }
+int b200rt_malloc_host(void** p, size_t bytes) { return b200rt_malloc(p, bytes); }
+int b200rt_free_host(void* p) { return b200rt_free(p); }
+int b200rt_memcpy_d2d(void* d, const void* s, size_t n, void*) {
+  std::memmove(d, s, n);
+  return 0;
+}
 int b200rt_memset(void* p, int v, size_t bytes, void*) {
   std::memset(p, v, bytes);
   return 0;

@@ -295,3 +295,55 @@ def test_small_launch_k_split_on_the_cpu():
         got, _ = emu.run_cartesian(name, code, info, (ni, nj, K), (HALO, HALO, HALO, HALO, 0, 0), f, keep_k_chunks=False)
         for fd in info["fields"]:
             assert bit_equal(got[fd["name"]].reshape(want[fd["name"]].shape), want[fd["name"]]), fd["name"]
+
+
+# ---- the optimized-IIR fixtures of the reference tree itself (dawn/test/**/*.iir), emitted where they lie and
+# emulated against the goldens of tests/golden/reftree.npz (the GPU twin: tests/test_reference_tree_gpu.py) -----
+import zlib  # noqa: E402
+
+from test_reference_tree_gpu import CART_DOM, ENTRIES, GOLD, MESH  # noqa: E402
+
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference tree not present")
+@pytest.mark.parametrize("entry", ENTRIES, ids=[os.path.basename(e["file"]) for e in ENTRIES])
+def test_reference_tree_fixture_on_the_cpu(entry):
+    rel = entry["file"]
+    gold = np.load(GOLD)
+    code = codegen.compile_iir(open(os.path.join(REFERENCE, rel)).read(), backend=entry["backend"])
+    info = json.loads(re.search(r'return "(\{.*\})";', code).group(1).encode().decode("unicode_escape"))
+    name = entry["stencil"]
+    rng = np.random.default_rng(zlib.crc32(rel.encode()) & 0x7FFFFFFF)
+    changed = [k2.split("::", 1)[1] for k2 in gold.files if k2.startswith(rel + "::")]
+    f = {}
+    if entry["backend"] == "b200":
+        I, J, K = CART_DOM
+        ni, nj = I + 2 * HALO, J + 2 * HALO
+        for fd in info["fields"]:
+            d = fd["dims"]
+            f[fd["name"]] = rng.uniform(0.5, 1.5, (K + 1 if "k" in d else 1, nj if "j" in d else 1, ni if "i" in d else 1))
+        got, _ = emu.run_cartesian(name, code, info, (ni, nj, K), (HALO, HALO, HALO, HALO, 0, 0), f)
+        for fd in info["fields"]:
+            n = fd["name"]
+            want = gold[rel + "::" + n] if n in changed else f[n]
+            assert bit_equal(got[n].reshape(want.shape), want), (rel, n)
+    else:
+        m, k = TriMesh(MESH[0], MESH[1]), MESH[2]
+        for fd in info["fields"]:
+            shape = [k] if fd.get("k", 1) else []
+            if fd["location"] != "none":
+                shape.append(m.num(LOC[fd["location"]]))
+            if fd["sparse"]:
+                shape.append(fd["sparse"])
+            f[fd["name"]] = rng.uniform(0.5, 1.5, shape)
+        got, _ = emu.run(name, code, info, m, k, f)
+        for fd in info["fields"]:
+            n = fd["name"]
+            want = gold[rel + "::" + n] if n in changed else f[n]
+            if fd["location"] == "none":
+                assert bit_equal(got[n], want), (rel, n)
+            else:
+                v = m.valid(LOC[fd["location"]])
+                axis = 1 if fd.get("k", 1) else 0
+                assert bit_equal(np.compress(v, got[n], axis=axis), np.compress(v, want, axis=axis)), (rel, n)
