@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 if [ "${1:-single}" = "single" ]; then
   # A1: first run of the pending parity tests (Atlas-suite stencils, nabla2 on renumbered meshes):
   #     run in-process here to see every case; once green, drop the child-process wrapper and the xfail mark
-  B200_PENDING_INPROC=1 timeout 120 python -m pytest tests/test_zz_atlas_suite_gpu.py -q -m gpu -rfE 2>&1 | tail -30 | tee gpurun_out/pending_tests.log
+  B200_PENDING_INPROC=1 timeout 120 python -m pytest tests/test_zz_pending_gpu.py -q -m gpu -rfE 2>&1 | tail -30 | tee gpurun_out/pending_tests.log
   # A2: does the RCM numbering (28 % fewer gather sectors per warp, tests/test_reorder.py) show up as time?
   for r in none rcm morton; do
     timeout 200 python bench.py --workload icon_nabla2 --steps 20 --no-cpu-baseline --icon-reorder $r \
