@@ -347,3 +347,13 @@ def test_reference_tree_fixture_on_the_cpu(entry):
                 v = m.valid(LOC[fd["location"]])
                 axis = 1 if fd.get("k", 1) else 0
                 assert bit_equal(np.compress(v, got[n], axis=axis), np.compress(v, want, axis=axis)), (rel, n)
+
+
+@pytest.mark.parametrize("name", ["hori_diff_type2_stencil", "tridiagonal_solve", "lap", "hd_smagorinsky_stencil",
+                                  "kcache_fill", "fuzz_03", "fuzz_07", "fuzz_12"])
+def test_tiny_and_ragged_domains_through_the_default_kernels(name):
+    # one point, a sliver, more than four tiles in i with three rows, a single column pair
+    code = codegen.compile_iir(open(iir_path(name)).read(), backend="b200")
+    info = json.loads(re.search(r'return "(\{.*\})";', code).group(1).encode().decode("unicode_escape"))
+    for size in ((1, 1, 12), (3, 2, 12), (129, 3, 21), (2, 65, 12)):
+        _cartesian_case(name, code, info, size, 900)
