@@ -169,7 +169,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s %dx%dx%d double (reference naive C++ algorithm on host cores)" % (
-            STENCIL[workload], I, J, K)},
+            STENCIL[workload], I, J, K),
+                   "sample": "a step of this arm is a bounded SAMPLE of the workload, the value is a rate: " + sample},
         "cpu_baseline": {"value": val, "unit": "grid-point updates/s", "cores": threads,
                          "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "grid-point updates/s", "h2d_bytes_per_step": 0,
@@ -233,16 +234,20 @@ def run_gpu(args):
         s.view().copy_(v.expand(nk_, nj_, ni_))
 
     gnj = J * world + 2 * HALO
-    for fd in mod.fields:
-        s = stor[fd["name"]]
-        key = keymap.get(fd["name"], fd["name"])
-        if key is None:
-            s.fill(-1.0)
-        else:
-            dev_fill(s, FILL[key], rank * J, gnj)
-            if workload == "tridiagonal" and fd["name"] == "b":
-                s.buf.add_(12.0)
-    torch.cuda.synchronize()
+
+    def fill_inputs():
+        for fd in mod.fields:
+            s = stor[fd["name"]]
+            key = keymap.get(fd["name"], fd["name"])
+            if key is None:
+                s.fill(-1.0)
+            else:
+                dev_fill(s, FILL[key], rank * J, gnj)
+                if workload == "tridiagonal" and fd["name"] == "b":
+                    s.buf.add_(12.0)
+        torch.cuda.synchronize()
+
+    fill_inputs()
     fields = [stor[fd["name"]] for fd in mod.fields]
 
     # halo exchange plan for every input with a j extent (multi-GPU only)
@@ -355,6 +360,19 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
 
+    # ---- parity self-check: the launch shape that was just timed, against the oracle ----------------
+    parity = parity_check(workload, mod, stor, fill_inputs, step, (I, J, K), rank, world,
+                          max([w[0] for w in widths.values()], default=0),
+                          max([w[1] for w in widths.values()], default=0))
+    flag = torch.tensor([0 if parity["max_abs_diff"] == 0.0 and parity["differing_values"] == 0 else 1],
+                        device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if float(flag.item()) != 0.0:
+        # a fast kernel with different results is not a result: no value is printed
+        sys.stderr.write("bench.py: rank %d parity check against the oracle: %s\n" % (rank, json.dumps(parity)))
+        raise SystemExit(3)
+
     # ---- kernel-only time for the roofline: at N=1 a step IS one launch of the generated kernel, so
     # the timed region itself gives its average duration; at N>1 the same number of bare kernel
     # launches is timed right after the timed region (same thermal / power-cap state)
@@ -423,13 +441,19 @@ def run_gpu(args):
                         "flags)" if args.halo == "p2p" else "NCCL")),
                 "l2": "inputs larger than L2 (%.1f GB per step vs 126 MB), no flush" % (
                     BYTES_PER_POINT[workload] * pts / 1e9),
-                "timing": "%d back-to-back steps; at N=1 roofline.achieved uses this same region "
-                          "(a step is one kernel launch), so it is a sustained figure - see clocks" % args.steps,
+                "timing": "%d back-to-back steps = %.1f ms timed (%s); at N=1 roofline.achieved uses this "
+                          "same region (a step is one kernel launch) - see clocks" % (
+                              args.steps, ms_max,
+                              "sustained figure" if ms_max >= 50.0 else
+                              "a burst figure: shorter than the ~50 ms it takes the power cap to engage"),
                 "codegen_options": opts,
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": None if traffic is None else
+                "committed ncu capture profiles/traffic_%s.json (dram__bytes_read+write per launch), not "
+                "measured in this run" % workload,
                 "kernel": "%s (generated), %d launch(es)/step, %.4f ms/launch, %d algorithmic B/point"
                           % (name, kernels_per_run, kernel_ms / max(1, kernels_per_run),
                              BYTES_PER_POINT[workload]),
@@ -442,6 +466,8 @@ def run_gpu(args):
                            "k_chunk=8): inputs H2D + result D2H every step, pipelined over k chunks"},
             "gpu_launches": launches,
             "clocks": clocks,
+            "parity_checked": True, "max_abs_diff": parity["max_abs_diff"], "parity": parity,
+            "last_launch": st.last_launch(),
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(workload)
@@ -449,12 +475,81 @@ def run_gpu(args):
                 # reported beside the CPU baseline, not a target either: what the reference's CUDA backend
                 # output does on this GPU when it is merely recompiled
                 line["reference_cuda_kernel"] = refcuda_baseline(workload)
+        if world == 1 and workload == "hori_diff" and not args.shape and not args.opt and not args.no_sub_workloads:
+            # the other two configurations the target names (BASELINE.json configs[2], [3]): measured in
+            # the same run, each in its own process with its own roofline / clocks / cpu_baseline / e2e
+            line["workloads"] = sub_workloads(args)
         print(json.dumps(line))
     for plan, _ in plans:
         rt.lib().b200rt_halo_plan_destroy(plan)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def parity_check(workload, mod, stor, fill_inputs, step, shape, rank, world, dep_lo, dep_hi):
+    """One more step of the timed configuration on fresh inputs, compared bit for bit with the oracle
+    (oracle/naive_stencils.c as the CHECKER) on a sample of the domain: hori_diff on whole k planes (levels
+    are independent), the solver on bands of whole columns (columns are independent).  With slab neighbours
+    the halo rows of the exchanged inputs are overwritten with NaN first, so a result that matches the
+    oracle proves the exchange delivered them.  Returns a record for the JSON line."""
+    import numpy as np
+    import torch
+    from oracle import capi
+    I, J, K = shape
+    fill_inputs()
+    names = [fd["name"] for fd in mod.fields]
+    if workload == "hori_diff":
+        planes = sorted({0, 1, 19, 20, 21, K // 2, K - 2, K - 1} & set(range(K)))
+        idx = torch.as_tensor(planes, device="cuda")
+        take = lambda s: s.view().index_select(0, idx).cpu().numpy()  # noqa: E731
+        before = {n: take(stor[n]) for n in ("in", "hdmask", "out")}
+        vec = {n: stor[n].view().cpu().numpy().copy() for n in ("crlato", "crlatu")}
+        if world > 1:   # poison what the exchange has to deliver
+            v = stor["in"].view()
+            if rank > 0:
+                v[:, HALO - dep_lo:HALO, :] = float("nan")
+            if rank + 1 < world:
+                v[:, HALO + J:HALO + J + dep_hi, :] = float("nan")
+        step()
+        torch.cuda.synchronize()
+        got = take(stor["out"])
+        want = capi.hori_diff_type2(before["out"].copy(), before["in"], vec["crlato"].reshape(-1),
+                                    vec["crlatu"].reshape(-1), before["hdmask"], halo=HALO, nk=len(planes))
+        checks = [(got, want), (take(stor["in"]), before["in"])]
+        what = "out on k planes %s (whole planes incl. halo ring)%s" % (
+            planes, "; halo rows of `in` poisoned with NaN before the exchange" if world > 1 else "")
+    else:
+        bands = sorted({0, (J // 2 // 8) * 8, J - 8})
+        rows = [r for b in bands for r in range(b, b + 8 + 2 * HALO)]  # band + its own halo rows
+        idx = torch.as_tensor(rows, device="cuda")
+        take = lambda s: s.view().index_select(1, idx).cpu().numpy()  # noqa: E731
+        before = {n: take(stor[n]) for n in names}
+        step()
+        torch.cuda.synchronize()
+        checks = []
+        nb = 8 + 2 * HALO
+        for q in range(len(bands)):
+            sl = slice(q * nb, (q + 1) * nb)
+            sub = {n: np.ascontiguousarray(before[n][:, sl, :]) for n in names}
+            wd, wc = capi.tridiagonal_solve(sub["d"], sub["a"], sub["b"], sub["c"], halo=HALO, nk=K)
+            # only the band's own interior rows were computed from complete data on both sides
+            for n, w in (("d", wd), ("c", wc)):
+                g = take(stor[n])[:, sl, :]
+                checks.append((g[:, HALO:-HALO, :], w[:, HALO:-HALO, :]))
+        what = "d and c on 8-row bands of whole columns at interior rows %s" % bands
+    ndiff, maxdiff, nvals = 0, 0.0, 0
+    for g, w in checks:
+        bad = g.view(np.int64) != w.view(np.int64)
+        bad &= ~(np.isnan(g) & np.isnan(w))
+        ndiff += int(bad.sum())
+        nvals += g.size
+        if bad.any():
+            d = np.abs(g[bad] - w[bad])
+            maxdiff = max(maxdiff, float(np.nanmax(d)) if np.isfinite(d).any() else float("inf"))
+    return {"checked": what, "values_compared": nvals, "differing_values": ndiff, "max_abs_diff": maxdiff,
+            "oracle": "oracle/naive_stencils.c (C restatement of the naive backend, bit-equal to the pinned "
+                      "interpreter)"}
 
 
 def run_icon(args):
@@ -564,6 +659,48 @@ def run_icon(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     launches = st.launches() - l0 + (0 if plan is None else args.steps * 2 * (sl.halo_lo + sl.halo_hi))
+
+    # ---- parity self-check of the launch shape just timed: all K levels run on the GPU, a sample of
+    # levels is compared with the oracle (the stencils have no vertical dependency, so a level can be
+    # checked on its own); with slab neighbours the halo rows of `vec` are poisoned first
+    parity = None
+    if not nabla4:
+        from util import unstructured_oracle_on_levels
+        levels = [0, 8, K - 1]
+        if plan is not None:
+            per = sl.slots_per_row(1)
+            if sl.halo_lo:
+                vec[:, :per * sl.halo_lo] = float("nan")
+            if sl.halo_hi:
+                vec[:, E - per * sl.halo_hi:] = float("nan")
+        step()
+        torch.cuda.synchronize()
+        written = set(mod.info.get("written", []))
+        got = {fd["name"]: t.index_select(0, torch.as_tensor(levels, device="cuda")).cpu().numpy()
+               for fd, t in zip(mod.fields, tens) if fd["name"] in written and not fd["sparse"]}
+        want = unstructured_oracle_on_levels(stencil_name, mesh, mod.fields, tens, levels)
+        loc_of = {"cells": 0, "edges": 1, "vertices": 2}   # dawn_b200.trimesh CELL, EDGE, VERTEX
+        ndiff = nvals = 0
+        for fd in mod.fields:
+            if fd["name"] not in got:
+                continue
+            v = mesh.valid(loc_of[fd["location"]])
+            g, w = got[fd["name"]][:, v], want[fd["name"]][:, v]
+            ndiff += int((g.view(np.int64) != w.view(np.int64)).sum())
+            nvals += g.size
+        nan_in_vec = 0 if vec is None else int(torch.isnan(vec).sum().item())
+        parity = {"checked": "%s on levels %s of %d, all valid elements%s" % (
+                      sorted(got), levels, K, "" if plan is None else
+                      "; halo rows of `vec` poisoned with NaN before the exchange"),
+                  "values_compared": nvals, "differing_values": ndiff + nan_in_vec,
+                  "max_abs_diff": 0.0 if ndiff + nan_in_vec == 0 else float("nan"),
+                  "oracle": "oracle/naive_interp.py (pinned against the reference's generated naive-ico text)"}
+        flag = torch.tensor([float(ndiff + nan_in_vec != 0)], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if float(flag.item()) != 0.0:
+            sys.stderr.write("bench.py: rank %d parity check against the oracle: %s\n" % (rank, json.dumps(parity)))
+            raise SystemExit(3)
     # work and bytes of the OWNED rows of one rank (halo rows are redundant work)
     own = TriMesh(nx, ny)
     E, C, V = own.num_edges, own.num_cells, own.num_vertices
@@ -602,7 +739,13 @@ def run_icon(args):
                                                ", both twice" if nabla4 else "", bytes_run),
                      "peak_source": peak_src},
         "gpu_launches": launches, "clocks": clocks,
+        "parity_checked": parity is not None, "max_abs_diff": None if parity is None else parity["max_abs_diff"],
+        "parity": parity if parity is not None else
+        "not checked in this run: nabla4 has a second pass whose inputs the first pass produces "
+        "(tests/test_unstructured_gpu.py checks it at test sizes)",
     }
+    if rank == 0 and world == 1 and not nabla4 and not diamond and not args.no_e2e:
+        line["e2e"] = icon_e2e(mod, K, args.icon_e2e_n)
     if rank == 0 and world == 1 and not nabla4 and not diamond and not args.no_cpu_baseline:
         r = icon_reference(64, K, 3, 1)
         if r is not None:
@@ -615,6 +758,70 @@ def run_icon(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def sub_workloads(args):
+    """Runs `bench.py --workload tridiagonal` and `--workload icon_nabla2` as child processes (the main
+    process keeps only ~3 GB of HBM; ICON at 20 M edges x 65 levels needs ~125 GB) and returns their JSON
+    lines keyed by workload."""
+    out = {}
+    me = os.path.abspath(__file__)
+    for key, extra, limit in (
+            ("tridiagonal_solve_512x512x80", ["--workload", "tridiagonal", "--steps", str(max(args.steps, 50))], 300),
+            ("icon_nabla2_20M_edges_x65", ["--workload", "icon_nabla2", "--steps", str(min(max(args.steps, 5), 20))], 600)):
+        cmd = [sys.executable, me, "--gpus", "1", "--warmup", str(args.warmup)] + extra
+        if args.no_cpu_baseline:
+            cmd.append("--no-cpu-baseline")
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=limit)
+            lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if r.returncode != 0 or not lines:
+                out[key] = {"error": "exit code %d: %s" % (r.returncode, r.stderr.strip()[-300:])}
+            else:
+                out[key] = json.loads(lines[-1])
+        except Exception as e:  # noqa: BLE001
+            out[key] = {"error": str(e)[:300]}
+    return out
+
+
+def icon_e2e(mod, K, nx):
+    """The same metric end to end through the reference-facing entry point run_<N>_from_c_host (twin of the
+    reference's, CudaIcoCodeGen.cpp:949-1028: element-major HOST arrays; device buffers allocated, inputs
+    copied up and transposed to level-major on the GPU, kernels, results transposed back and copied down -
+    every call).  Host buffers are pinned.  Measured on a smaller mesh than the device-resident line: the
+    call is PCIe-bound, so its rate does not depend on the mesh size, and 20 M edges would need 110 GB of
+    pinned host memory."""
+    import ctypes
+    import torch
+    from dawn_b200.trimesh import TriMesh
+    mesh = TriMesh(nx, nx)
+    st = mod.on_mesh(mesh, K)
+    n_of = {"cells": mesh.num_cells, "edges": mesh.num_edges, "vertices": mesh.num_vertices}
+    host, h2d, d2h = [], 0, 0
+    written = set(mod.info.get("written", []))
+    for fd in mod.fields:
+        n = n_of[fd["location"]] * max(1, fd["sparse"]) * K
+        t = torch.empty(n, dtype=torch.float64).pin_memory()
+        t.fill_(1.0)
+        host.append(t)
+        h2d += n * 8
+        d2h += n * 8 if fd["name"] in written else 0
+    fn = getattr(mod.lib, "run_%s_from_c_host" % mod.name)
+    fn.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p]
+    ptrs = (ctypes.c_void_p * len(host))(*[t.data_ptr() for t in host])
+    stream = torch.cuda.current_stream().cuda_stream
+    from dawn_b200 import runtime as rt
+    rt.check(fn(st.handle, ptrs, len(host), stream))      # warm-up
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        rt.check(fn(st.handle, ptrs, len(host), stream))  # returns after the results are in the host buffers
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": mesh.num_edges * K / dt, "unit": "edge-level updates/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "steps": reps, "ms_per_step": dt * 1e3,
+            "api": "run_%s_from_c_host (generated C ABI): pinned element-major host arrays of a TriMesh %dx%d "
+                   "(%d edge slots) x %d levels; cudaMalloc + H2D + transpose + kernels + transpose + D2H "
+                   "every call, as the reference's *_from_c_host does" % (mod.name, nx, nx, mesh.num_edges, K)}
 
 
 def refcuda_child(workload):
@@ -746,6 +953,11 @@ def main():
                     help="renumber the ICON mesh before the run (none = toylib's structured numbering)")
     ap.add_argument("--opt", action="append", default=[], help="codegen option key=value (sweeps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="ICON lines: skip the host-buffer leg")
+    ap.add_argument("--icon-e2e-n", type=int, default=1024,
+                    help="TriMesh nx=ny of the ICON end-to-end leg (1024 -> 3.1 M edges, 16 GB of pinned host arrays)")
+    ap.add_argument("--no-sub-workloads", action="store_true",
+                    help="default line only: do not append the vertical-solve and ICON records")
     ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"],
                     help="multi-GPU halo exchange: pack -> ncclSend/Recv -> unpack, or peer-memory stores")
     ap.add_argument("--refcuda-child", default=None, choices=list(STENCIL), help=argparse.SUPPRESS)

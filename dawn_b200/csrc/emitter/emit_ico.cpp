@@ -205,6 +205,13 @@ private:
     });
     return hit;
   }
+  // fields `stage` touches at an element other than the thread's own (same rule as above)
+  void fieldsTouchedAway(const Stage& stage, std::set<int>& out) const {
+    forEachAccess(stage, [&](const Expr& e, int nest, bool) {
+      if(nest > 0 && (e.hasOffset || nest > 1 || fieldLoc(e.accessID) != stage.location))
+        out.insert(e.accessID);
+    });
+  }
 
   std::vector<Group> plan(const Stencil& st);
   void emitKernel(const Group& g, const Group* partner);
@@ -269,7 +276,7 @@ std::vector<Group> IcoEmitter::plan(const Stencil& st) {
   for(auto const& ms : st.multiStages) {
     analysis::checkParallelLevels(inst_, ms);
     Group cur;
-    std::set<int> written;
+    std::set<int> written, readAway;
     auto flush = [&]() {
       if(cur.stages.empty())
         return;
@@ -279,6 +286,7 @@ std::vector<Group> IcoEmitter::plan(const Stencil& st) {
       groups.push_back(cur);
       cur = Group{};
       written.clear();
+      readAway.clear();
     };
     for(auto const& stage : ms.stages) {
       if(stage.location == LocationType::None)
@@ -290,8 +298,15 @@ std::vector<Group> IcoEmitter::plan(const Stencil& st) {
                          cur.space.upperLevel == stage.iRange.upperLevel &&
                          cur.space.lowerOffset == stage.iRange.lowerOffset &&
                          cur.space.upperOffset == stage.iRange.upperOffset));
+      StageInfo info = analysis::stageInfo(inst_, stage);
+      // write-after-read: what the group gathered from other elements must not be overwritten inside
+      // the same launch (the reference runs one kernel per stage, CudaIcoCodeGen.cpp:1316-1464, so the
+      // gathers of stage A are complete before stage B stores)
+      bool overwritesGathered = false;
+      for(auto const& fp : info.fields)
+        overwritesGathered = overwritesGathered || (fp.second.written && readAway.count(fp.first));
       bool fits = !cur.stages.empty() && cur.loc == stage.location && sameSpace &&
-                  !readsThroughChain(stage, written) && opt_.FuseColumns != 0;
+                  !readsThroughChain(stage, written) && !overwritesGathered && opt_.FuseColumns != 0;
       if(!fits)
         flush();
       cur.ms = &ms;
@@ -299,7 +314,7 @@ std::vector<Group> IcoEmitter::plan(const Stencil& st) {
       cur.hasSpace = stage.hasIRange;
       cur.space = stage.iRange;
       cur.stages.push_back(&stage);
-      StageInfo info = analysis::stageInfo(inst_, stage);
+      fieldsTouchedAway(stage, readAway);
       for(auto const& fp : info.fields)
         if(fp.second.written)
           written.insert(fp.first);

@@ -80,6 +80,7 @@ struct buffers {
   size_t elems = 0;
   bool host_dirty = false; // host has newer data than the device
   bool dev_dirty = false;  // device has newer data than the host
+  void* stream = nullptr;  // stream of the last device-side producer (kernel or upload) of `dev`
   ~buffers() {
     b200rt_free_host(host);
     b200rt_free(dev);
@@ -126,17 +127,19 @@ public:
   const Info* get_storage_info_ptr() const { return info_.get(); }
   const std::array<int, 3>& strides() const { return info_->strides(); }
 
-  // make both copies coherent (GridTools' data_store::sync)
+  // make both copies coherent (GridTools' data_store::sync).  Copies are ordered on the stream that
+  // last produced the device copy - generated stencils launch on their own (possibly non-blocking)
+  // stream, which the legacy null stream does not wait for - and the host waits for that stream.
   void sync() const {
     if(!buf_)
       return;
     if(buf_->dev_dirty && buf_->dev) {
-      ::dawn_b200::check(b200rt_memcpy_d2h(buf_->host, buf_->dev, buf_->elems * sizeof(T), nullptr));
-      ::dawn_b200::check(b200rt_stream_synchronize(nullptr));
+      ::dawn_b200::check(b200rt_memcpy_d2h(buf_->host, buf_->dev, buf_->elems * sizeof(T), buf_->stream));
+      ::dawn_b200::check(b200rt_stream_synchronize(buf_->stream));
       buf_->dev_dirty = false;
     } else if(buf_->host_dirty && buf_->dev) {
-      ::dawn_b200::check(b200rt_memcpy_h2d(buf_->dev, buf_->host, buf_->elems * sizeof(T), nullptr));
-      ::dawn_b200::check(b200rt_stream_synchronize(nullptr));
+      ::dawn_b200::check(b200rt_memcpy_h2d(buf_->dev, buf_->host, buf_->elems * sizeof(T), buf_->stream));
+      ::dawn_b200::check(b200rt_stream_synchronize(buf_->stream));
       buf_->host_dirty = false;
     }
   }
@@ -148,19 +151,27 @@ public:
       buf_->host_dirty = true;
     return buf_->host + info_->lead();
   }
-  // descriptor of the up-to-date device copy (uploads the host copy if it is newer)
-  b200_field_t device_descriptor() const {
+  // descriptor of the up-to-date device copy for work on `stream` (uploads the host copy on that stream
+  // if it is newer; if another stream produced the device copy, the host waits for it first)
+  b200_field_t device_descriptor(void* stream = nullptr) const {
     ensure_device();
+    if(buf_->dev_dirty && buf_->stream != stream)
+      ::dawn_b200::check(b200rt_stream_synchronize(buf_->stream));
     if(buf_->host_dirty) {
-      ::dawn_b200::check(b200rt_memcpy_h2d(buf_->dev, buf_->host, buf_->elems * sizeof(T), nullptr));
-      ::dawn_b200::check(b200rt_stream_synchronize(nullptr));
+      ::dawn_b200::check(b200rt_memcpy_h2d(buf_->dev, buf_->host, buf_->elems * sizeof(T), stream));
+      ::dawn_b200::check(b200rt_stream_synchronize(stream));
       buf_->host_dirty = false;
+      buf_->stream = stream;
     }
     return b200_field_t{buf_->dev + info_->lead(), info_->template stride<1>(),
                         info_->template stride<2>()};
   }
   T* device_ptr() const { return static_cast<T*>(device_descriptor().data); }
-  void mark_device_dirty() const { buf_->dev_dirty = true; }
+  // a kernel on `stream` writes the device copy
+  void mark_device_dirty(void* stream = nullptr) const {
+    buf_->dev_dirty = true;
+    buf_->stream = stream;
+  }
 };
 
 template <class Store, access_mode Mode = access_mode::read_write>

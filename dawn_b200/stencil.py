@@ -142,6 +142,10 @@ class StencilModule:
         self._launches = getattr(self.lib, "launches_" + name)
         self._launches.argtypes = [ctypes.c_void_p]
         self._launches.restype = ctypes.c_long
+        if not self.unstructured:
+            self._last_launch = getattr(self.lib, "last_launch_" + name)
+            self._last_launch.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
+            self._last_launch.restype = None
 
     def __call__(self, domain, stream=None):
         return Stencil(self, domain, stream)
@@ -314,6 +318,13 @@ class Stencil:
 
     def launches(self):
         return int(self.module._launches(self.handle))
+
+    def last_launch(self):
+        """Shape of the most recent kernel launch (last_launch_<N> of the C ABI)."""
+        out = (ctypes.c_int * 5)()
+        self.module._last_launch(self.handle, out)
+        return {"grid": (out[0], out[1], out[2]), "k_chunk": out[3],
+                "kernel": ("plain", "tma", "ring", "column_cache")[out[4]]}
 
     def close(self):
         if self.handle:

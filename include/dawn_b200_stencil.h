@@ -42,6 +42,12 @@ void free_NAME(void* handle);
 /* Number of kernel launches issued by this instance so far. */
 long launches_NAME(void* handle);
 
+/* Cartesian modules: shape of the most recent kernel launch - out5 = {grid.x, grid.y, grid.z, levels per
+ * block (k chunk), kernel kind: 0 plain, 1 TMA-staged tile kernel, 2 TMA column ring, 3 column cache}.
+ * Diagnostic (the reference has no twin); tests use it to assert which kernel ran and that the
+ * shared-memory ring over k reached its steady state. */
+void last_launch_NAME(void* handle, int* out5);
+
 /* One pair per global variable G of the stencil (reference: get_G()/set_G(), CodeGen.cpp:110-136). */
 void set_NAME_G(void* handle, double value);
 double get_NAME_G(void* handle);

@@ -71,7 +71,23 @@ int main(int argc, char** argv) {
     for(int j = 0; j < nj; ++j)
       for(int i = 0; i < ni; ++i)
         diff += vg(i, j, k) != vn(i, j, k);
-  std::printf("%s %s total_time=%.6f s, %ld differing values\n", hd.get_name().c_str(),
-              (ok && diff == 0) ? "VERIFIED" : "FAILED", hd.get_total_time(), diff);
-  return (ok && diff == 0) ? 0 : 1;
+  // the same on a stream of the caller's (non-blocking: the legacy null stream does not wait for it):
+  // host views and sync() must still see the finished result (the reference's run() synchronises
+  // the device, CudaCodeGen.cpp:435-450; here the storage remembers the producing stream)
+  void* user_stream = nullptr;
+  if(b200rt_stream_create(&user_stream)) return 2;
+  storage_t u_out2(meta_data, "u_out2");
+  verif.fill(-1.0, u_out2);
+  dawn_generated::b200::hori_diff_type2_stencil hd2(dom);
+  hd2.set_stream(user_stream);
+  hd2.run(u_out2, u, crlato, crlatu, hdmask);
+  auto vg2 = gridtools::make_host_view<gridtools::access_mode::read_only>(u_out2);
+  long diff2 = 0;
+  for(int k = 0; k < nka; ++k)
+    for(int j = 0; j < nj; ++j)
+      for(int i = 0; i < ni; ++i)
+        diff2 += vg2(i, j, k) != vn(i, j, k);
+  std::printf("%s %s total_time=%.6f s, %ld differing values, %ld on a user stream\n", hd.get_name().c_str(),
+              (ok && diff == 0 && diff2 == 0) ? "VERIFIED" : "FAILED", hd.get_total_time(), diff, diff2);
+  return (ok && diff == 0 && diff2 == 0) ? 0 : 1;
 }

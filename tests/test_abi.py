@@ -43,7 +43,7 @@ def test_generated_module_exports_stencil_abi(name):
         pytest.skip("generated modules not built (run __graft_entry__.build())")
     ctypes.CDLL(build.build_runtime(), mode=ctypes.RTLD_GLOBAL)
     lib = ctypes.CDLL(so)
-    for sym in ("setup_", "run_", "run_rows_", "free_", "launches_", "b200_module_info_"):
+    for sym in ("setup_", "run_", "run_rows_", "free_", "launches_", "last_launch_", "b200_module_info_"):
         assert hasattr(lib, sym + name), sym + name
     if name == "laplacian_stencil":
         assert hasattr(lib, "set_laplacian_stencil_dx") and hasattr(lib, "get_laplacian_stencil_dx")

@@ -44,6 +44,61 @@ def test_hori_diff_type2(I, J, K):
     assert bit_equal(got["in"], f["in"])  # inputs untouched
 
 
+def _run_gpu_dense(name, dom_dims, fields, **options):
+    """Same through Storage, returning the bound stencil as well (for last_launch)."""
+    import torch
+    import dawn_b200
+    mod = dawn_b200.load_stencil(name, **options)
+    dom = dawn_b200.Domain(*dom_dims)
+    dom.set_halos(HALO, HALO, HALO, HALO, 0, 0)
+    st = mod(dom)
+    stor = [dawn_b200.Storage(dom_dims[0], dom_dims[1], fields[f["name"]].shape[0], f["dims"]).from_numpy(
+        fields[f["name"]]) for f in mod.fields]
+    st.run(*stor)
+    torch.cuda.synchronize()
+    return {f["name"]: s.to_numpy() for f, s in zip(mod.fields, stor)}, st
+
+
+def test_hori_diff_type2_at_the_benchmark_shape():
+    """BASELINE.json configs[1]: 1024 x 1024 x 80 double through the DEFAULT module - the launch the bench
+    times.  At this size the launcher keeps 20 levels per block, so the 3-slot TMA ring runs in its
+    steady state (refill, slot reuse, phase flips); compared bit for bit with oracle/naive_stencils.c."""
+    from oracle import capi
+    I, J, K = 1024, 1024, 80
+    f = hori_diff_type2_inputs(I, J, K)
+    want = capi.hori_diff_type2(f["out"].copy(), f["in"], f["crlato"], f["crlatu"], f["hdmask"], halo=HALO, nk=K)
+    got, st = _run_gpu_dense("hori_diff_type2_stencil", (I + 2 * HALO, J + 2 * HALO, K), f)
+    ll = st.last_launch()
+    assert ll["kernel"] == "tma" and ll["k_chunk"] >= 3 and ll["grid"] == (16, 86, 4), ll
+    assert bit_equal(got["out"], want)
+    assert bit_equal(got["in"], f["in"]) and bit_equal(got["hdmask"], f["hdmask"])
+
+
+@pytest.mark.parametrize("I,J,K", [(256, 120, 41), (200, 37, 80), (1024, 512, 23)])
+def test_hori_diff_type2_ring_steady_state_on_ragged_shapes(I, J, K):
+    """enough tiles that k stays in chunks of >= 3 levels: ragged last chunk, odd level counts, partial tiles"""
+    from oracle import capi
+    f = hori_diff_type2_inputs(I, J, K)
+    want = capi.hori_diff_type2(f["out"].copy(), f["in"], f["crlato"], f["crlatu"], f["hdmask"], halo=HALO, nk=K)
+    got, st = _run_gpu_dense("hori_diff_type2_stencil", (I + 2 * HALO, J + 2 * HALO, K), f)
+    ll = st.last_launch()
+    assert ll["kernel"] == "tma" and ll["k_chunk"] >= 3, ll
+    assert bit_equal(got["out"], want)
+
+
+@pytest.mark.parametrize("I,J,K", [(512, 512, 80), (1024, 1024, 80)])
+def test_tridiagonal_solve_at_the_benchmark_shapes(I, J, K):
+    """BASELINE.json configs[2] (512 x 512 x 80) and the north-star size: default module (fused sweeps, TMA
+    ring over k), bit for bit against oracle/naive_stencils.c."""
+    from oracle import capi
+    f = tridiagonal_inputs(I, J, K)
+    wd, wc = capi.tridiagonal_solve(f["d"].copy(), f["a"], f["b"], f["c"].copy(), halo=HALO, nk=K)
+    got, st = _run_gpu_dense("tridiagonal_solve", (I + 2 * HALO, J + 2 * HALO, K), f)
+    assert st.last_launch()["kernel"] == "ring", st.last_launch()
+    assert bit_equal(got["d"], wd) and bit_equal(got["c"], wc)
+    assert bit_equal(got["a"], f["a"]) and bit_equal(got["b"], f["b"])
+
+
 @pytest.mark.parametrize("opts", [dict(rows_per_thread=1), dict(rows_per_thread=4),
                                   dict(block_size_i=32, block_size_j=8, rows_per_thread=2),
                                   dict(inline_temporaries=0), dict(use_tma=0),

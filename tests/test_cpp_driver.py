@@ -18,7 +18,7 @@ def test_cpp_driver_compiles_against_generated_code():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("size", [(12, 12, 10), (70, 33, 7)])
+@pytest.mark.parametrize("size", [(12, 12, 10), (70, 33, 7), (512, 512, 40)])
 def test_cpp_driver_verifies_on_gpu(size):
     exe = os.path.join(build.LIB, "hori_diff_driver")
     if not os.path.exists(exe):

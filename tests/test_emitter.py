@@ -267,6 +267,32 @@ def test_racy_halo_accesses_to_stored_fields_are_rejected():
         codegen.compile_iir(b.dumps(), inline_temporaries=0)
 
 
+def test_write_after_read_at_an_offset_is_not_fused():
+    """A later stage overwriting what an earlier stage read at ANOTHER point (horizontal offset /
+    neighbour chain).  The naive backend runs stage after stage over the whole plane, so the earlier
+    stage sees the old values everywhere.  b200-ico: the overwrite starts a new launch; Cartesian: the
+    multistage is rejected (Dawn's field versioning removes such cycles before code generation)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from iir_builder import FULL, IIRBuilder
+    code = codegen.compile_iir(open(iir_path("overwriteGathered")).read(), backend="b200-ico")
+    groups = re.findall(r"(\d+) fused stage\(s\) on cells", code)
+    assert len(re.findall(r"^__global__", code, flags=re.M)) == 2, groups
+    b = IIRBuilder("war_cart")
+    g, h, o = b.field("g"), b.field("h"), b.field("o")
+    s1 = b.stage(b.do(FULL, b.assign(o, g(1, 0) + g(0, 1))))   # zero stage extent, reads g at offsets
+    s2 = b.stage(b.do(FULL, b.assign(g, h() * 2.0)))
+    b.stencil(b.multistage("Parallel", s1, s2))
+    with pytest.raises(codegen.CodeGenError, match="at a horizontal offset and written by stage"):
+        codegen.compile_iir(b.dumps())
+    # pointwise read + later overwrite stays legal (every thread touches only its own point)
+    b = IIRBuilder("war_ok")
+    g, h, o = b.field("g"), b.field("h"), b.field("o")
+    b.stencil(b.multistage("Parallel", b.stage(b.do(FULL, b.assign(o, g() + h(1, 0)))),
+                           b.stage(b.do(FULL, b.assign(g, h() * 2.0)))))
+    codegen.compile_iir(b.dumps())
+
+
 def test_vertical_dependency_in_a_parallel_multistage_is_rejected():
     """Level blocks of a Parallel multistage run concurrently: reading, at another level, a field the
     multistage writes is a race (found by the random unstructured stencils) - diagnosed for both

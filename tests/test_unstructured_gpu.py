@@ -346,7 +346,53 @@ def test_unstructured_iteration_space_and_splitters():
         st2.run(*t)
 
 
-@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("nx", [1024])
+def test_icon_laplacian_at_benchmark_scale(nx):
+    """ICON nabla2 on 3.15 M edges x 65 levels (BASELINE.json configs[3] is the same launch shape on 20 M
+    edges): the default module, all 65 levels on the GPU, compared bit for bit with the oracle on a sample
+    of levels (nabla2 has no vertical dependency, so a level is checked independently of the others:
+    first / last level, both sides of a level-block boundary, the ragged last block)."""
+    import torch
+    import dawn_b200
+    from util import unstructured_oracle_on_levels
+    name, K = "ICON_laplacian_stencil", 65
+    m = TriMesh(nx, nx)
+    assert m.num_edges > 3_000_000
+    mod = dawn_b200.load_stencil(name)
+    st = mod.on_mesh(m, K)
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    n_of = {"cells": m.num_cells, "edges": m.num_edges, "vertices": m.num_vertices}
+    tens = []
+    for fd in mod.fields:
+        shape = (K, fd["sparse"], n_of[fd["location"]]) if fd["sparse"] else (K, n_of[fd["location"]])
+        tens.append(torch.empty(shape, dtype=torch.float64, device="cuda").uniform_(0.5, 1.5, generator=gen))
+    levels = [0, 7, 8, 33, 63, 64]
+    want = unstructured_oracle_on_levels(name, m, mod.fields, tens, levels)
+    st.run(*tens)
+    torch.cuda.synchronize()
+    idx = torch.as_tensor(levels, device="cuda")
+    for fd, t in zip(mod.fields, tens):
+        if fd["name"] not in ("rot_vec", "div_vec", "nabla2_vec"):
+            continue
+        got = t.index_select(0, idx).cpu().numpy()
+        v = m.valid(LOC[fd["location"]])
+        assert bit_equal(got[:, v], want[fd["name"]][:, v]), fd["name"]
+
+
+def test_overwriting_a_gathered_field_is_not_fused_into_the_gathering_launch():
+    """stencils/overwriteGathered.iir: stage 1 gathers g over C>E>C, stage 2 overwrites g, stage 3 reads
+    both results (write-after-read through a chain; seeds 16-19 of the random programs do the same)."""
+    name = "overwriteGathered"
+    for (nx, ny, k) in ((9, 7, 5), (200, 150, 9)):
+        m = TriMesh(nx, ny)
+        f = _rand(np.random.default_rng(61), m, k, {"g": CELL, "h": CELL, "o": CELL, "o2": CELL})
+        want = naive_interp.run_unstructured(iir_path(name), m, k, {n: v.copy() for n, v in f.items()})
+        got, st = _run(name, m, k, f)
+        _check(got, want, m, {"g": CELL, "o": CELL, "o2": CELL})
+        assert st.launches() == 2
+
+
+@pytest.mark.parametrize("seed", range(20))
 def test_random_unstructured_stencils_match_the_oracle(seed):
     """Differential test of the b200-ico emitter on seeded random programs (tools/make_fuzz_ico.py):
     reductions over random chains with weights / min / max / product, sparse dimensions, nested
@@ -371,3 +417,112 @@ def test_random_unstructured_stencils_match_the_oracle(seed):
             axis = 1 if fd.get("k", 1) else 0
             same = bit_equal(np.compress(v, got[n], axis=axis), np.compress(v, want[n], axis=axis))
             assert same, (name, n, (nx, ny, k))
+
+
+# ---- the seven stencils only the reference's Atlas suite runs (GenerateUnstructuredStencils.cpp:874-1134),
+# ICON's diamond nabla2 + Smagorinsky, ICON_gradient, generate_versioned_field (dawn4py-tests), nabla2 on
+# renumbered meshes (dawn_b200/reorder.py).  First GPU run: round 2, all green. ----------------------------
+def _fields(name, m, k, rng):
+    nc, ne = m.num_cells, m.num_edges
+    cell = lambda: rng.uniform(0.5, 1.5, (k, nc))  # noqa: E731
+    if name == "globalVar":
+        return {"in_field": cell(), "out_field": cell()}, {"out_field": CELL}, {}
+    if name == "tempFieldAllocation":
+        return {"in_field": cell(), "out_field": cell()}, {"out_field": CELL}, {"tmp_field": np.zeros((k, nc))}
+    if name == "sparseTempFieldAllocation":
+        return ({"in_field": cell(), "out_field": cell()}, {"out_field": CELL},
+                {"tmp_field": np.zeros((k, nc, 3))})
+    if name == "reductionInIfConditional":
+        return ({"c_field": cell(), "sparse_field": rng.uniform(0.5, 1.5, (k, nc, 3)),
+                 "e_field": rng.uniform(0.5, 1.5, (k, ne)), "out_field": cell()}, {"out_field": CELL}, {})
+    f = {"cin_field": cell(), "cout_field": cell()}
+    if name == "reductionWithCenterSparse":
+        f["sparse"] = rng.uniform(0.5, 1.5, (k, nc, 4))
+    extra = {"sparse": np.zeros((k, nc, 4))} if name == "reductionAndFillWithCenterSparse" else {}
+    return f, {"cout_field": CELL}, extra
+
+
+@pytest.mark.parametrize("nx,ny,k", [(10, 10, 3), (13, 7, 11)])
+@pytest.mark.parametrize("name", ["globalVar", "tempFieldAllocation", "sparseTempFieldAllocation",
+                                  "reductionInIfConditional", "reductionWithCenter",
+                                  "reductionWithCenterSparse", "reductionAndFillWithCenterSparse"])
+def test_atlas_suite_stencils(name, nx, ny, k):
+    m = TriMesh(nx, ny)
+    f, outs, temporaries = _fields(name, m, k, np.random.default_rng(51))
+    g = {"dt": 2.0} if name == "globalVar" else None
+    want = {n: v.copy() for n, v in f.items()}
+    want.update(temporaries)
+    naive_interp.run_unstructured(iir_path(name), m, k, want, globals_=g)
+    got, _ = _run(name, m, k, f, globals_=g)
+    for n, loc in outs.items():
+        v = m.valid(loc)
+        assert bit_equal(got[n][:, v], want[n][:, v]), n
+
+
+@pytest.mark.parametrize("method", ["random", "rcm", "morton"])
+def test_icon_nabla2_on_a_renumbered_mesh(method):
+    """Same kernels, renumbered neighbour tables (dawn_b200/reorder.py): the result mapped back to the
+    original numbering equals the oracle's on the original mesh bit for bit."""
+    from dawn_b200 import reorder as ro
+    from dawn_b200.trimesh import VERTEX
+    m, k = TriMesh(21, 13), 9
+    rng = np.random.default_rng(52)
+    loc_of = {"vec": EDGE, "div_vec": CELL, "rot_vec": VERTEX, "nabla2_vec": EDGE, "primal_edge_length": EDGE,
+              "dual_edge_length": EDGE, "tangent_orientation": EDGE, "geofac_rot": VERTEX, "geofac_div": CELL}
+    f = {n: rng.uniform(0.5, 1.5, (k, m.num(loc))) for n, loc in loc_of.items() if not n.startswith("geofac")}
+    f["geofac_rot"] = rng.uniform(-1, 1, (k, m.num_vertices, 6))
+    f["geofac_div"] = rng.uniform(-1, 1, (k, m.num_cells, 3))
+    want = {n: v.copy() for n, v in f.items()}
+    want["__tmp_nab_60"] = np.zeros((k, m.num_edges))
+    want["__tmp_nab_61"] = np.zeros((k, m.num_edges))
+    naive_interp.run_unstructured(iir_path("ICON_laplacian_stencil"), m, k, want)
+    rm = ro.ReorderedMesh(m, ro.Renumbering.random(m, 53)) if method == "random" else ro.reorder(m, method)
+    r = rm.renumbering
+    got, _ = _run("ICON_laplacian_stencil", rm, k, {n: np.ascontiguousarray(r.to_new(loc_of[n], v, axis=1))
+                                                    for n, v in f.items()})
+    for n, loc in (("rot_vec", VERTEX), ("div_vec", CELL), ("nabla2_vec", EDGE)):
+        v = m.valid(loc)
+        assert bit_equal(r.to_old(loc, got[n], axis=1)[:, v], want[n][:, v]), n
+
+
+@pytest.mark.parametrize("nx,ny,k", [(9, 7, 3), (33, 20, 9)])
+def test_icon_diamond_laplacian(nx, ny, k):
+    """ICON_laplacian_diamond_stencil.py (diamond nabla2 + Smagorinsky): 13 fused edge stages, one launch."""
+    from test_unstructured_oracle import diamond_fields
+    m = TriMesh(nx, ny)
+    f = diamond_fields(m, k, 54)
+    want = naive_interp.run_unstructured(iir_path("ICON_laplacian_diamond_stencil"), m, k,
+                                         {n: v.copy() for n, v in f.items()})
+    got, st = _run("ICON_laplacian_diamond_stencil", m, k, f)
+    v = m.valid(EDGE)
+    for n in ("vn_vert", "dvt_tang", "dvt_norm", "kh_smag_1", "kh_smag_2", "kh_smag", "nabla2"):
+        assert bit_equal(got[n][:, v], want[n][:, v]), n
+    assert st.launches() == 1
+
+
+def test_icon_gradient():
+    """dawn4py-tests/ICON_gradient.py: sparse API field with centre filled by a loop, then reduced."""
+    m, k = TriMesh(14, 9), 5
+    rng = np.random.default_rng(55)
+    f = {"p_grad": rng.uniform(0.5, 1.5, (k, m.num_cells)), "p_ccpr": rng.uniform(0.5, 1.5, (k, m.num_cells)),
+         "geofac_grg": np.zeros((k, m.num_cells, 4))}
+    want = naive_interp.run_unstructured(iir_path("ICON_gradient"), m, k, {n: v.copy() for n, v in f.items()})
+    got, _ = _run("ICON_gradient", m, k, f)
+    assert bit_equal(got["p_grad"], want["p_grad"])
+    t = m.nbh_table([CELL, EDGE, CELL], True)
+    assert bit_equal(got["geofac_grg"][:, t >= 0], want["geofac_grg"][:, t >= 0])
+
+
+def test_versioned_field_against_the_reference_golden():
+    """generate_versioned_field: golden made by the reference's own generated text (oracle/_ref build)."""
+    import os
+    from test_unstructured_oracle import versioned_fields
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "versioned_field.npz"))
+    nx, ny, k = (int(x) for x in g["dims"])
+    m = TriMesh(nx, ny)
+    f = versioned_fields(m, k, int(g["seed"]))
+    f.pop("c_0")
+    got, _ = _run("generate_versioned_field", m, k, f)
+    ev = m.edge_valid
+    assert bit_equal(got["a"][:, ev], g["a"][:, ev]) and bit_equal(got["c"][:, ev], g["c"][:, ev])
+

@@ -64,3 +64,25 @@ def run_oracle(name, dom, fields, globals_=None):
 
 def bit_equal(a, b):
     return np.array_equal(a, b, equal_nan=True)
+
+
+def unstructured_oracle_on_levels(name, mesh, module_fields, device_tensors, levels):
+    """Oracle run of a level-independent unstructured stencil (no vertical offsets: ICON nabla2) on a SAMPLE
+    of levels of device-resident fields: copies the sampled levels to the host (sparse fields come as
+    [k, nbh, n] from the device and go to the oracle as [k, n, nbh]), runs the interpreter with
+    k_size = len(levels) and returns {field: array[len(levels), ...]} in the oracle's layout.  Lets the
+    benchmark-scale runs (65 levels, millions of elements) be checked in seconds."""
+    import json
+    import torch
+    idx = torch.as_tensor(list(levels), device=device_tensors[0].device)
+    f = {}
+    for fd, t in zip(module_fields, device_tensors):
+        a = t.index_select(0, idx).cpu().numpy()
+        f[fd["name"]] = np.ascontiguousarray(np.swapaxes(a, -1, -2)) if fd["sparse"] else a
+    d = json.load(open(iir_path(name)))["metadata"]
+    for aid in d.get("temporaryFieldIDs", []):     # the interpreter wants storage for temporaries too
+        dims = d["fieldIDtoDimensions"][str(aid)]
+        chain = dims["unstructured_horizontal_dimension"]["iter_space"]["chain"]
+        assert len(chain) == 1
+        f.setdefault(d["accessIDToName"][str(aid)], np.zeros((len(levels), mesh.num(chain[0]))))
+    return naive_interp.run_unstructured(iir_path(name), mesh, len(levels), f)

@@ -98,7 +98,7 @@ def make(seed):
     n_st = rng.randint(1, 3)
     for s in range(n_st):
         loc = rng.choice(LOCS)
-        allow_k = rng.random() < 0.3
+        allow_k = rng.random() < 0.3 and seed < 16
         iv = Interval("Start", "End", 1, -1) if allow_k else FULL
         o = b.field("out%d_%s" % (s, loc[0].lower()), "k", loc)
         outs.append(o)
@@ -128,12 +128,26 @@ def make(seed):
         stages.append(b.stage(b.do(iv, *stmts), location=loc))
         dense[loc].append(o)       # later stages may consume it (forces kernel splits / forwarding)
         produced.append(o)
+    if seed >= 16:
+        # seeds 16..: later stages OVERWRITE input fields that earlier stages read - at the element or
+        # gathered through a chain (write-after-read: the emitter must not fuse such a stage into the
+        # launch that still gathers the old values), then consume the new values through a chain again
+        inputs = {loc: dense[loc][:2] for loc in LOCS}
+        for _ in range(rng.randint(1, 2)):
+            loc = rng.choice(LOCS)
+            f, other = rng.sample(inputs[loc], 2) if rng.random() < 0.5 else (inputs[loc][0], inputs[loc][1])
+            stages.append(b.stage(b.do(FULL, b.assign(f, other.at() * 2.0 + f.at())), location=loc))
+            chain = rng.choice([c for c in CHAINS[loc] if c[-1] == loc] or CHAINS[loc])
+            tgt = chain[-1]
+            o = b.field("post%d_%s" % (len(stages), loc[0].lower()), "k", loc)
+            stages.append(b.stage(b.do(FULL, b.assign(o, reduce_over(chain, inputs[tgt][0].at(0, nbh=True)))),
+                                  location=loc))
     b.stencil(b.multistage("Parallel", *stages))
     return b
 
 
 def main():
-    count = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    count = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     os.makedirs(OUT, exist_ok=True)
     for seed in range(count):
         with open(os.path.join(OUT, "fuzzico_%02d.iir" % seed), "w") as f:

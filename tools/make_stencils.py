@@ -583,6 +583,20 @@ def ico_reduction_with_center(kind):  # :1038-1134 (chains that include the cent
     return b
 
 
+def ico_overwrite_gathered():
+    """Not from the reference: a later stage overwrites a field an earlier stage of the same location type
+    gathered through a chain (write-after-read).  cuda-ico runs one kernel per stage
+    (CudaIcoCodeGen.cpp:1316-1464), so this is valid and deterministic there; a backend that fuses stages
+    must keep the overwrite out of the launch that still gathers the old values."""
+    b = _ico("overwriteGathered")
+    g, h, o, o2 = (b.field(n, "k", "Cell") for n in ("g", "h", "o", "o2"))
+    s1 = b.stage(b.do(FULL, b.assign(o, reduce_over(["Cell", "Edge", "Cell"], g.nbh))), location="Cell")
+    s2 = b.stage(b.do(FULL, b.assign(g, h.at() * 2.0)), location="Cell")
+    s3 = b.stage(b.do(FULL, b.assign(o2, o.at() + g.at())), location="Cell")
+    b.stencil(b.multistage("Parallel", s1, s2, s3))
+    return b
+
+
 # ---- reference integration-test stencils (gtclang/test/integration-test/CodeGen/<name>.cpp) --------
 def kcache_fill():
     b = IIRBuilder("kcache_fill")
@@ -904,6 +918,7 @@ ALL = {
     "stencil_desc_ast_03": lambda: stencil_desc_ast(3),
     "stencil_desc_ast_04": lambda: stencil_desc_ast(4),
     "stencil_desc_ast_07": lambda: stencil_desc_ast(7),
+    "overwriteGathered": ico_overwrite_gathered,
     "copyCell": ico_copy_cell,
     "copyEdge": ico_copy_edge,
     "accumulateEdgeToCell": ico_accumulate_edge_to_cell,
