@@ -125,6 +125,11 @@ VARIANTS = {
 }
 
 
+# single-precision builds (codegen option single_precision=1) the GPU tests load
+PRECISION_VARIANTS = {n: [dict(single_precision=1)] for n in (
+    "hori_diff_type2_stencil", "tridiagonal_solve", "hori_diff_stencil_02", "ICON_laplacian_stencil", "diffusion",
+    "ICON_laplacian_diamond_stencil")}
+
 # optimized IIR fixtures shipped by the reference itself: compiled where they lie when the reference
 # tree is present (build container); only the built modules travel to the GPU box
 REFERENCE_IIR = {
@@ -163,7 +168,7 @@ def build_all(force=False, jobs=None):
                 continue
             raise
         work.append((name, code, ""))
-        for opts in VARIANTS.get(name, []):
+        for opts in VARIANTS.get(name, []) + PRECISION_VARIANTS.get(name, []):
             work.append((name, codegen.compile_iir(iir, backend=backend, **opts), variant_tag(opts)))
     for name, rel in REFERENCE_IIR.items():
         path = os.path.join(REFERENCE_ROOT, rel)

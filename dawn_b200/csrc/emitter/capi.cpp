@@ -35,6 +35,7 @@ b200::codegen::Options convert(const dawn_b200_options* o) {
   r.RingEarly = o->ring_early;
   r.RingStagger = o->ring_stagger;
   r.IcoFullBlocks = o->ico_full_blocks;
+  r.SinglePrecision = o->single_precision;
   return r;
 }
 } // namespace

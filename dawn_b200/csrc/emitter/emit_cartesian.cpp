@@ -142,8 +142,9 @@ struct KernelPlan {
         return &c;
     return nullptr;
   }
+  int ftBytes = 8; // sizeof(::dawn::float_type) of the translation unit (4 with single_precision)
   size_t tmaSmemBytes() const {
-    return 128 + (size_t)stages * stageElems * 8 + (size_t)2 * cacheElems * 8;
+    return 128 + (size_t)stages * stageElems * ftBytes + (size_t)2 * cacheElems * ftBytes;
   }
 };
 
@@ -549,7 +550,7 @@ bool CartesianEmitter::planColumnRing(KernelPlan& kp) const {
   kp.stages = opt_.TmaStages > 0 ? opt_.TmaStages : (opt_.RingDrain ? 4 : 3);
   kp.TI = opt_.BlockSizeI > 0 ? opt_.BlockSizeI : 64;
   kp.TJ = opt_.BlockSizeJ > 0 ? opt_.BlockSizeJ : 1;
-  if((kp.TI * 8) % 16 != 0 || kp.TI > 256 || kp.TJ > 256 || kp.ringKB > 256)
+  if((kp.TI * kp.ftBytes) % 16 != 0 || kp.TI > 256 || kp.TJ > 256 || kp.ringKB > 256)
     return false;
   return true;
 }
@@ -646,18 +647,21 @@ bool CartesianEmitter::planTma(KernelPlan& kp) const {
       continue;
     KernelPlan::Staged sg;
     sg.field = f;
-    // the box starts on an even i coordinate: every row segment TMA reads begins 16-byte aligned
-    sg.im = -(((std::max(0, -b.im) + 1) / 2) * 2), sg.ip = std::max(0, b.ip);
+    // the box starts on a 16-byte boundary (an even i coordinate for doubles, a multiple of 4 for
+    // floats): every row segment TMA reads begins 16-byte aligned
+    const int A = 16 / kp.ftBytes;
+    sg.im = -(((std::max(0, -b.im) + A - 1) / A) * A), sg.ip = std::max(0, b.ip);
     sg.jm = std::min(0, b.jm), sg.jp = std::max(0, b.jp);
     sg.W = kp.TI + sg.ip - sg.im;
-    sg.W += sg.W & 1; // 16-byte multiple rows for the TMA box
+    sg.W = ((sg.W + A - 1) / A) * A; // 16-byte multiple rows for the TMA box
     sg.H = kp.tileJ() + sg.jp - sg.jm;
     if(sg.W > 256 || sg.H > 256)
       return false;
     sg.offset = offset;
     // keep every field 128-byte aligned; RJ-1 spare rows so that unpredicated reads of a thread's
     // invalid rows stay inside the slot
-    offset += ((sg.W * (sg.H + kp.RJ - 1) + 15) / 16) * 16;
+    const int L = 128 / kp.ftBytes;
+    offset += ((sg.W * (sg.H + kp.RJ - 1) + L - 1) / L) * L;
     kp.staged.push_back(sg);
   }
   if(kp.staged.empty())
@@ -882,6 +886,7 @@ std::vector<KernelPlan> CartesianEmitter::planKernels(const Stencil& st) {
       continue;
     }
     KernelPlan kp;
+    kp.ftBytes = opt_.SinglePrecision ? 4 : 8;
     bool pw = msPointwise(ms);
     kp.ms.push_back(&ms);
     size_t e = m + 1;
@@ -1202,7 +1207,7 @@ public:
           pvar = pit->second;
         else {
           pvar = fieldName(e.accessID) + "_cq" + std::to_string(base) + "_" + offTag(djAbs);
-          loads.push_back("const double2 " + pvar + " = *reinterpret_cast<const double2*>(&ij_" +
+          loads.push_back("const ::dawn::float_type2 " + pvar + " = *reinterpret_cast<const ::dawn::float_type2*>(&ij_" +
                           fieldName(e.accessID) + "[" + row + std::to_string(base) + ")]);");
           valueNo[pkey] = pvar;
         }
@@ -1270,7 +1275,7 @@ public:
           pvar = pit->second;
         else {
           pvar = fieldName(e.accessID) + "_q" + std::to_string(base) + "_" + offTag(djAbs);
-          loads.push_back("const double2 " + pvar + " = *reinterpret_cast<const double2*>(&s_" +
+          loads.push_back("const ::dawn::float_type2 " + pvar + " = *reinterpret_cast<const ::dawn::float_type2*>(&s_" +
                           fieldName(e.accessID) + "[(lyb + (" + std::to_string(djAbs - sg->jm) +
                           ")) * " + std::to_string(sg->W) + " + lx + (" + std::to_string(base) + ")]);");
           valueNo[pkey] = pvar;
@@ -1567,7 +1572,7 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
   // ---- TMA ring: one mbarrier per pipeline stage, thread 0 is the producer ----------------------
   size_t tmaBytes = 0;
   for(auto const& sg : kp.staged)
-    tmaBytes += (size_t)sg.W * sg.H * 8;
+    tmaBytes += (size_t)sg.W * sg.H * kp.ftBytes;
   const int ringSlotElems = kp.ringMaxFields * kp.ringKB * kp.NT();
   if(kp.tma || kp.colring) {
     os_ << "  extern __shared__ __align__(128) unsigned char b200_smem[];\n";
@@ -1602,9 +1607,7 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
     os_ << pad << "  const unsigned ts = " << stageExpr << ";\n";
     os_ << pad << "  ::dawn_b200::tma::expect_bytes(&tma_full[ts], " << tmaBytes << "u);\n";
     for(auto const& sg : kp.staged) {
-      int EI = ((-sg.im + 1) / 2) * 2;
-      if(EI < 0)
-        EI = 0;
+      int EI = -sg.im; // a multiple of 16 bytes (planTma)
       int EJ = sg.jm < 0 ? -sg.jm : 0;
       os_ << pad << "  ::dawn_b200::tma::load_3d(tma_ring + ts * " << kp.stageElems << " + "
           << sg.offset << ", &tm_" << fname(sg.field) << ", i0 + (" << sg.im + EI << "), j0 + ("
@@ -1740,7 +1743,7 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
     auto emitRingIssue = [&](const std::set<int>& fields, const std::string& pad,
                              const std::string& chunk) {
       const int KB = kp.ringKB, S = kp.stages, NT = kp.NT();
-      const size_t bytes = fields.size() * (size_t)KB * NT * 8;
+      const size_t bytes = fields.size() * (size_t)KB * NT * kp.ftBytes;
       os_ << pad << "{\n";
       os_ << pad << "  const unsigned ts = (tma_it + " << chunk << ") % " << S << ";\n";
       os_ << pad << "  const int k0 = "
@@ -1924,8 +1927,8 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
               os_ << pad << be.finalize(l) << "\n";
             for(auto const& l : be.temps)
               os_ << pad << l << "\n";
-            os_ << pad << "*reinterpret_cast<double2*>(&ij_buf[" << cc.offset << " + (lyb - (" << cc.jm
-                << ")) * " << cc.W << " + lx - (" << cc.e << ")]) = make_double2(" << val[0] << ", "
+            os_ << pad << "*reinterpret_cast<::dawn::float_type2*>(&ij_buf[" << cc.offset << " + (lyb - (" << cc.jm
+                << ")) * " << cc.W << " + lx - (" << cc.e << ")]) = ::dawn::make_float_type2(" << val[0] << ", "
                 << val[1] << ");\n";
             os_ << "        }\n";
           }
@@ -2426,7 +2429,7 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
           << (kp.zchunk ? "(nz + kchunk - 1) / kchunk" : "1") << ");\n";
       size_t smem = kp.tma ? kp.tmaSmemBytes() : 0;
       if(kp.colring)
-        smem = 128 + (size_t)kp.stages * kp.ringMaxFields * kp.ringKB * kp.NT() * 8;
+        smem = 128 + (size_t)kp.stages * kp.ringMaxFields * kp.ringKB * kp.NT() * kp.ftBytes;
       if(kp.tma || kp.colring) {
         // function attributes are per device: a host that drives several GPUs from one process sets
         // them once on each
@@ -2514,7 +2517,8 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
       const KernelPlan* ring = (n + 1 < kps.size() && kps[n + 1].colring) ? &kps[n + 1] : nullptr;
       os_ << "      {\n";
       if(ring) {
-        os_ << "        bool ring_ok = m_use_tma && sj_111 % 2 == 0 && sk_111 % 2 == 0";
+        os_ << "        bool ring_ok = m_use_tma && sj_111 % " << 16 / ring->ftBytes << " == 0 && sk_111 % "
+            << 16 / ring->ftBytes << " == 0";
         for(int f : ring->ringFields)
           os_ << " && (reinterpret_cast<uintptr_t>(" << fname(f) << "_p) % 16 == 0)";
         os_ << ";\n";
@@ -2522,9 +2526,9 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
           os_ << "        alignas(64) CUtensorMap tm_" << fname(f) << ";\n";
         os_ << "        if(ring_ok) {\n";
         for(int f : ring->ringFields)
-          os_ << "          if(b200rt_tensor_map_3d(&tm_" << fname(f) << ", " << fname(f)
+          os_ << "          if(b200rt_tensor_map_3d_es(&tm_" << fname(f) << ", " << fname(f)
               << "_p, nx, ny, nz, sj_111, sk_111, " << ring->TI << ", " << ring->TJ << ", "
-              << ring->ringKB << ")) ring_ok = false;\n";
+              << ring->ringKB << ", " << ring->ftBytes << ")) ring_ok = false;\n";
         os_ << "        }\n";
         os_ << "        if(ring_ok) {\n";
         emitLaunch(*ring, "          ");
@@ -2555,7 +2559,8 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
         ++n;
       } else if(twin) {
         // TMA needs 16-byte aligned rows: interior origin 16 B aligned, even j/k strides
-        os_ << "        bool tma_ok = m_use_tma && sj_111 % 2 == 0 && sk_111 % 2 == 0";
+        os_ << "        bool tma_ok = m_use_tma && sj_111 % " << 16 / twin->ftBytes << " == 0 && sk_111 % "
+            << 16 / twin->ftBytes << " == 0";
         for(auto const& sg : twin->staged)
           os_ << " && (reinterpret_cast<uintptr_t>(" << fname(sg.field) << "_p) % 16 == 0)";
         os_ << ";\n";
@@ -2563,14 +2568,12 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
           os_ << "        alignas(64) CUtensorMap tm_" << fname(sg.field) << ";\n";
         os_ << "        if(tma_ok) {\n";
         for(auto const& sg : twin->staged) {
-          int EI = ((-sg.im + 1) / 2) * 2;
-          if(EI < 0)
-            EI = 0;
+          int EI = -sg.im; // a multiple of 16 bytes (planTma)
           int EJ = sg.jm < 0 ? -sg.jm : 0;
-          os_ << "          if(b200rt_tensor_map_3d(&tm_" << fname(sg.field) << ", " << fname(sg.field)
+          os_ << "          if(b200rt_tensor_map_3d_es(&tm_" << fname(sg.field) << ", " << fname(sg.field)
               << "_p - " << EI << " - (ptrdiff_t)" << EJ << " * sj_111, " << EI
               << " + nx + (int)m_dom.iplus(), " << EJ << " + ny + (int)m_dom.jplus(), nz, sj_111, "
-              << "sk_111, " << sg.W << ", " << sg.H << ", 1)) tma_ok = false;\n";
+              << "sk_111, " << sg.W << ", " << sg.H << ", 1, " << twin->ftBytes << ")) tma_ok = false;\n";
         }
         os_ << "        }\n";
         os_ << "        if(tma_ok) {\n";
@@ -2837,7 +2840,8 @@ void CartesianEmitter::emitCAbi() {
   }
   // module description for generic hosts (Python ctypes, Fortran)
   os_ << "B200_EXPORT const char* b200_module_info_" << n << "() {\n  return \"{\\\"name\\\": \\\"" << inst_.name
-      << "\\\", \\\"grid\\\": \\\"Cartesian\\\", \\\"fields\\\": [";
+      << "\\\", \\\"grid\\\": \\\"Cartesian\\\", \\\"float_type\\\": \\\""
+      << (opt_.SinglePrecision ? "float" : "double") << "\\\", \\\"fields\\\": [";
   auto fext = inst_.stencils.size() == 1 ? analysis::fieldExtents(inst_, inst_.stencils[0])
                                          : std::map<int, Extent>{};
   for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a) {
@@ -2921,7 +2925,14 @@ TranslationUnit runCartesian(const std::map<std::string, iir::Instantiation>& ct
       "#define DAWN_BACKEND_T B200",
       "#ifndef GRIDTOOLS_DAWN_HALO_EXTENT\n#define GRIDTOOLS_DAWN_HALO_EXTENT " +
           std::to_string(options.MaxHaloSize) + "\n#endif",
+      // the element size shapes TMA boxes and shared-memory pairs, so the precision is fixed when the code
+      // is GENERATED (option single_precision) and checked when it is compiled
+      options.SinglePrecision ? "#ifndef DAWN_PRECISION\n#define DAWN_PRECISION 0 /* DAWN_SINGLE_PRECISION */\n#endif"
+                              : "#ifndef DAWN_PRECISION\n#define DAWN_PRECISION 1 /* DAWN_DOUBLE_PRECISION */\n#endif",
       "#include <driver-includes/gridtools_includes.hpp>",
+      std::string("static_assert(sizeof(::dawn::float_type) == ") + (options.SinglePrecision ? "4" : "8") +
+          ", \"this translation unit was generated for " + (options.SinglePrecision ? "single" : "double") +
+          " precision (b200 codegen option single_precision)\");",
       "using namespace gridtools::dawn;",
   };
   return tu;

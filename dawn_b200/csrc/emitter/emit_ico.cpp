@@ -980,7 +980,9 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
   os_ << "    return ::dawn_b200::check_launch();\n  }\n";
   // ---- host-buffer entry points (reference: run_<N>_from_{c,fort}_host, CudaIcoCodeGen.cpp:896-927;
   // cuda_utils.hpp:81-125,181-195 do the transposition on one host thread, here it is a GPU kernel) --
-  os_ << "  // number of doubles of API field `a`\n";
+  // the emitted host code names ::dawn::float_type; the runtime's typed entry points carry a suffix
+  const std::string sfx = opt_.SinglePrecision ? "_f32" : "";
+  os_ << "  // number of elements of API field `a`\n";
   os_ << "  size_t field_elems(int a) const {\n    switch(a) {\n";
   for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a) {
     int f = inst_.apiFieldIDs[a];
@@ -990,12 +992,12 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
     os_ << ";\n";
   }
   os_ << "    default: return 0;\n    }\n  }\n";
-  os_ << "  int run_from_host(double* const* host, bool element_major, void* stream) {\n";
+  os_ << "  int run_from_host(::dawn::float_type* const* host, bool element_major, void* stream) {\n";
   os_ << "    const int nf = " << inst_.apiFieldIDs.size() << ";\n";
-  os_ << "    double* dev[" << std::max<size_t>(1, inst_.apiFieldIDs.size()) << "] = {};\n";
-  os_ << "    double* tmp = nullptr;\n    size_t tmp_elems = 0;\n    int err = 0;\n";
+  os_ << "    ::dawn::float_type* dev[" << std::max<size_t>(1, inst_.apiFieldIDs.size()) << "] = {};\n";
+  os_ << "    ::dawn::float_type* tmp = nullptr;\n    size_t tmp_elems = 0;\n    int err = 0;\n";
   os_ << "    for(int a = 0; a < nf; ++a) tmp_elems = field_elems(a) > tmp_elems ? field_elems(a) : tmp_elems;\n";
-  os_ << "    if(element_major) err = b200rt_malloc((void**)&tmp, tmp_elems * sizeof(double));\n";
+  os_ << "    if(element_major) err = b200rt_malloc((void**)&tmp, tmp_elems * sizeof(::dawn::float_type));\n";
   os_ << "    b200_field_t f[" << std::max<size_t>(1, inst_.apiFieldIDs.size()) << "];\n";
   os_ << "    static const int sparse_of[] = {";
   for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a)
@@ -1018,12 +1020,12 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
   }
   os_ << "};\n";
   os_ << "    for(int a = 0; a < nf && !err; ++a) {\n";
-  os_ << "      const size_t bytes = field_elems(a) * sizeof(double);\n";
+  os_ << "      const size_t bytes = field_elems(a) * sizeof(::dawn::float_type);\n";
   os_ << "      err = b200rt_malloc((void**)&dev[a], bytes);\n";
   os_ << "      if(err) break;\n";
   os_ << "      if(element_major && elems_of[a] > 1) {\n";
   os_ << "        err = b200rt_memcpy_h2d(tmp, host[a], bytes, stream);\n";
-  os_ << "        if(!err) err = b200rt_reshape(tmp, dev[a], levels_of[a], elems_of[a], sparse_of[a], stream);\n";
+  os_ << "        if(!err) err = b200rt_reshape" << sfx << "(tmp, dev[a], levels_of[a], elems_of[a], sparse_of[a], stream);\n";
   os_ << "      } else\n        err = b200rt_memcpy_h2d(dev[a], host[a], bytes, stream);\n";
   os_ << "      f[a].data = dev[a];\n";
   os_ << "      f[a].stride_j = sparse_of[a] > 1 ? elems_of[a] : 0;\n";
@@ -1031,9 +1033,9 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
   os_ << "    }\n";
   os_ << "    if(!err) err = launch(f, stream);\n";
   os_ << "    for(int a = 0; a < nf && !err; ++a) {\n      if(!written_of[a]) continue;\n";
-  os_ << "      const size_t bytes = field_elems(a) * sizeof(double);\n";
+  os_ << "      const size_t bytes = field_elems(a) * sizeof(::dawn::float_type);\n";
   os_ << "      if(element_major && elems_of[a] > 1) {\n";
-  os_ << "        err = b200rt_reshape_back(dev[a], tmp, levels_of[a], elems_of[a], sparse_of[a], stream);\n";
+  os_ << "        err = b200rt_reshape_back" << sfx << "(dev[a], tmp, levels_of[a], elems_of[a], sparse_of[a], stream);\n";
   os_ << "        if(!err) err = b200rt_memcpy_d2h(host[a], tmp, bytes, stream);\n";
   os_ << "        if(!err) err = b200rt_stream_synchronize(stream);\n";
   os_ << "      } else\n        err = b200rt_memcpy_d2h(host[a], dev[a], bytes, stream);\n";
@@ -1042,7 +1044,7 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
   os_ << "    for(int a = 0; a < nf; ++a) b200rt_free(dev[a]);\n    b200rt_free(tmp);\n    return err;\n  }\n";
   // verification of the written fields against reference copies on the device (reference:
   // verify_<N>, CudaIcoCodeGen.cpp:949-1028 + cuda_verify.hpp:84-196; defaults rel 1e-12, abs 0)
-  os_ << "  int verify(const b200_field_t* f, const double* const* ref, const double* rel_tol, "
+  os_ << "  int verify(const b200_field_t* f, const ::dawn::float_type* const* ref, const double* rel_tol, "
          "const double* abs_tol, int iteration, b200_verification_metrics* metrics, void* stream) {\n";
   os_ << "    int w = 0;\n";
   {
@@ -1051,8 +1053,8 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
       written.insert(g.fieldsWritten.begin(), g.fieldsWritten.end());
     for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a)
       if(written.count(inst_.apiFieldIDs[a])) {
-        os_ << "    if(int err = b200rt_verify_field(static_cast<const double*>(f[" << a << "].data), ref[w], field_elems("
-            << a << "), rel_tol ? rel_tol[w] : 1e-12, abs_tol ? abs_tol[w] : 0.0, iteration, &metrics[w], stream)) return err;\n";
+        os_ << "    if(int err = b200rt_verify_field" << sfx << "(static_cast<const ::dawn::float_type*>(f[" << a << "].data), ref[w], field_elems("
+            << a << "), rel_tol ? rel_tol[w] : " << (opt_.SinglePrecision ? "1e-5" : "1e-12") << ", abs_tol ? abs_tol[w] : 0.0, iteration, &metrics[w], stream)) return err;\n";
         // reference: MetricsSerialiser(jsonRecord, metrics, "<stencil>", "<field>").writeJson(iteration)
         // (CudaIcoCodeGen.cpp:1009-1016)
         os_ << "    if(m_record) b200rt_metrics_record_add(m_record, \"" << inst_.name << "\", \""
@@ -1113,19 +1115,19 @@ std::string IcoEmitter::generate() {
       << ") return ::dawn_b200::set_error(B200_ERR_ARG, \"run_" << n << ": expected "
       << inst_.apiFieldIDs.size() << " fields\");\n"
       << "  return static_cast<" << cls << "*>(handle)->launch(fields, stream);\n}\n";
-  os_ << "B200_EXPORT int run_" << n << "_from_c_host(void* handle, double* const* host_fields, int nfields, void* stream) {\n"
+  os_ << "B200_EXPORT int run_" << n << "_from_c_host(void* handle, ::dawn::float_type* const* host_fields, int nfields, void* stream) {\n"
       << "  if(!handle || nfields != " << inst_.apiFieldIDs.size()
       << ") return ::dawn_b200::set_error(B200_ERR_ARG, \"run_" << n << "_from_c_host: field count\");\n"
       << "  return static_cast<" << cls << "*>(handle)->run_from_host(host_fields, true, stream);\n}\n";
-  os_ << "B200_EXPORT int run_" << n << "_from_fort_host(void* handle, double* const* host_fields, int nfields, void* stream) {\n"
+  os_ << "B200_EXPORT int run_" << n << "_from_fort_host(void* handle, ::dawn::float_type* const* host_fields, int nfields, void* stream) {\n"
       << "  if(!handle || nfields != " << inst_.apiFieldIDs.size()
       << ") return ::dawn_b200::set_error(B200_ERR_ARG, \"run_" << n << "_from_fort_host: field count\");\n"
       << "  return static_cast<" << cls << "*>(handle)->run_from_host(host_fields, false, stream);\n}\n";
-  os_ << "B200_EXPORT int verify_" << n << "(void* handle, const b200_field_t* fields, const double* const* ref_outputs, "
+  os_ << "B200_EXPORT int verify_" << n << "(void* handle, const b200_field_t* fields, const ::dawn::float_type* const* ref_outputs, "
          "const double* rel_tol, const double* abs_tol, int iteration, b200_verification_metrics* metrics, void* stream) {\n"
       << "  return static_cast<" << cls << "*>(handle)->verify(fields, ref_outputs, rel_tol, abs_tol, iteration, metrics, stream);\n}\n";
   os_ << "B200_EXPORT int run_and_verify_" << n << "(void* handle, const b200_field_t* fields, int nfields, "
-         "const double* const* ref_outputs, const double* rel_tol, const double* abs_tol, int iteration, "
+         "const ::dawn::float_type* const* ref_outputs, const double* rel_tol, const double* abs_tol, int iteration, "
          "b200_verification_metrics* metrics, void* stream) {\n"
       << "  if(int err = run_" << n << "(handle, fields, nfields, stream)) return err;\n"
       << "  return verify_" << n << "(handle, fields, ref_outputs, rel_tol, abs_tol, iteration, metrics, stream);\n}\n";
@@ -1146,7 +1148,8 @@ std::string IcoEmitter::generate() {
         << cls << "*>(handle)->get_" << cIdent(g.first) << "(); }\n";
   }
   os_ << "B200_EXPORT const char* b200_module_info_" << n << "() {\n  return \"{\\\"name\\\": \\\"" << inst_.name
-      << "\\\", \\\"grid\\\": \\\"Unstructured\\\", \\\"fields\\\": [";
+      << "\\\", \\\"grid\\\": \\\"Unstructured\\\", \\\"float_type\\\": \\\""
+      << (opt_.SinglePrecision ? "float" : "double") << "\\\", \\\"fields\\\": [";
   std::set<int> written;
   for(auto const& g : groups)
     written.insert(g.fieldsWritten.begin(), g.fieldsWritten.end());
@@ -1199,7 +1202,10 @@ std::string icoCHeader(const iir::Instantiation& inst) {
     n += (std::isalnum(static_cast<unsigned char>(c)) || c == '_') ? c : '_';
   std::ostringstream os;
   os << "/* generated by dawn-b200 (b200-ico): C interface of stencil " << inst.name << " */\n";
-  os << "#pragma once\n#include \"dawn_b200_rt.h\"\n#ifdef __cplusplus\nextern \"C\" {\n#endif\n";
+  os << "#pragma once\n#include \"dawn_b200_rt.h\"\n";
+  os << "/* element type of the fields: double, or float for a module generated with single_precision=1 */\n";
+  os << "#ifndef DAWN_B200_FLOAT_TYPE\n#define DAWN_B200_FLOAT_TYPE double\n#endif\n";
+  os << "#ifdef __cplusplus\nextern \"C\" {\n#endif\n";
   os << "/* fields in this order:";
   for(int f : inst.apiFieldIDs)
     os << " " << inst.nameOf(f);
@@ -1209,12 +1215,12 @@ std::string icoCHeader(const iir::Instantiation& inst) {
   os << "/* verification metrics of later verify_/run_and_verify_ calls are also merged into `record` */\n";
   os << "void set_metrics_record_" << n << "(void* handle, b200_metrics_record* record);\n";
   os << "int run_" << n << "(void* handle, const b200_field_t* fields, int nfields, void* stream);\n";
-  os << "int run_" << n << "_from_c_host(void* handle, double* const* host_fields, int nfields, void* stream);\n";
-  os << "int run_" << n << "_from_fort_host(void* handle, double* const* host_fields, int nfields, void* stream);\n";
-  os << "int verify_" << n << "(void* handle, const b200_field_t* fields, const double* const* ref_outputs, "
+  os << "int run_" << n << "_from_c_host(void* handle, DAWN_B200_FLOAT_TYPE* const* host_fields, int nfields, void* stream);\n";
+  os << "int run_" << n << "_from_fort_host(void* handle, DAWN_B200_FLOAT_TYPE* const* host_fields, int nfields, void* stream);\n";
+  os << "int verify_" << n << "(void* handle, const b200_field_t* fields, const DAWN_B200_FLOAT_TYPE* const* ref_outputs, "
         "const double* rel_tol, const double* abs_tol, int iteration, b200_verification_metrics* metrics, void* stream);\n";
   os << "int run_and_verify_" << n << "(void* handle, const b200_field_t* fields, int nfields, "
-        "const double* const* ref_outputs, const double* rel_tol, const double* abs_tol, int iteration, "
+        "const DAWN_B200_FLOAT_TYPE* const* ref_outputs, const double* rel_tol, const double* abs_tol, int iteration, "
         "b200_verification_metrics* metrics, void* stream);\n";
   os << "void free_" << n << "(void* handle);\n";
   for(auto const& g : inst.globals) {
@@ -1276,7 +1282,14 @@ TranslationUnit runIco(const std::map<std::string, iir::Instantiation>& ctx, con
       "#define DAWN_GENERATED 1",
       "#undef DAWN_BACKEND_T",
       "#define DAWN_BACKEND_T B200ICO",
+      // precision: chosen at generation time (option single_precision), checked at compile time; cf. the
+      // Cartesian emitter
+      options.SinglePrecision ? "#ifndef DAWN_PRECISION\n#define DAWN_PRECISION 0 /* DAWN_SINGLE_PRECISION */\n#endif"
+                              : "#ifndef DAWN_PRECISION\n#define DAWN_PRECISION 1 /* DAWN_DOUBLE_PRECISION */\n#endif",
       "#include <driver-includes/unstructured_includes.hpp>",
+      std::string("static_assert(sizeof(::dawn::float_type) == ") + (options.SinglePrecision ? "4" : "8") +
+          ", \"this translation unit was generated for " + (options.SinglePrecision ? "single" : "double") +
+          " precision (b200-ico codegen option single_precision)\");",
   };
   return tu;
 }

@@ -64,6 +64,7 @@ int main(int argc, char** argv) {
             intOpt(a, "co-schedule", opts.CoSchedule) || intOpt(a, "ring-drain", opts.RingDrain) ||
             intOpt(a, "ring-early", opts.RingEarly) || intOpt(a, "ring-stagger", opts.RingStagger) ||
             intOpt(a, "ico-full-blocks", opts.IcoFullBlocks) ||
+            intOpt(a, "single-precision", opts.SinglePrecision) ||
             intOpt(a, "max-blocks-sm", opts.MaxBlocksPerSM) ||
             intOpt(a, "max-halo-points", opts.MaxHaloSize)) {
     } else if(a.compare(0, 16, "--run-with-sync=") == 0)

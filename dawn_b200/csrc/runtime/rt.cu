@@ -142,6 +142,16 @@ int b200rt_check_last_launch(void) {
 
 int b200rt_tensor_map_3d(void* map, const void* base, int size_i, int size_j, int size_k,
                          int stride_j, int stride_k, int box_i, int box_j, int box_k) {
+  return b200rt_tensor_map_3d_es(map, base, size_i, size_j, size_k, stride_j, stride_k, box_i, box_j,
+                                 box_k, 8);
+}
+
+int b200rt_tensor_map_3d_es(void* map, const void* base, int size_i, int size_j, int size_k,
+                            int stride_j, int stride_k, int box_i, int box_j, int box_k,
+                            int elem_bytes) {
+  if(elem_bytes != 8 && elem_bytes != 4)
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_tensor_map_3d_es: elem_bytes must be 4 or 8");
+  const int per16 = 16 / elem_bytes; // elements per 16-byte unit
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                 const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -155,14 +165,15 @@ int b200rt_tensor_map_3d(void* map, const void* base, int size_i, int size_j, in
       return b200rt_set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled not available");
     encode = reinterpret_cast<encode_fn>(fn);
   }
-  if((reinterpret_cast<uintptr_t>(base) & 15) || (stride_j & 1) || (stride_k & 1) || box_i > 256 ||
-     box_j > 256 || box_k > 256 || box_k < 1 || ((box_i * 8) & 15))
+  if((reinterpret_cast<uintptr_t>(base) & 15) || (stride_j % per16) || (stride_k % per16) || box_i > 256 ||
+     box_j > 256 || box_k > 256 || box_k < 1 || ((box_i * elem_bytes) & 15))
     return b200rt_set_error(B200_ERR_LAYOUT, "b200rt_tensor_map_3d: TMA alignment rules violated");
   cuuint64_t dims[3] = {(cuuint64_t)size_i, (cuuint64_t)size_j, (cuuint64_t)size_k};
-  cuuint64_t strides[2] = {(cuuint64_t)stride_j * 8, (cuuint64_t)stride_k * 8};
+  cuuint64_t strides[2] = {(cuuint64_t)stride_j * elem_bytes, (cuuint64_t)stride_k * elem_bytes};
   cuuint32_t box[3] = {(cuuint32_t)box_i, (cuuint32_t)box_j, (cuuint32_t)box_k};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = encode(static_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+  CUresult r = encode(static_cast<CUtensorMap*>(map),
+                      elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                       const_cast<void*>(base), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -208,19 +219,22 @@ __device__ inline double atomicMinD(double* addr, double v) {
   return __longlong_as_double(old);
 }
 
+template <class T>
 __global__ void __launch_bounds__(256)
-verify_kernel(const double* __restrict__ dsl, const double* __restrict__ ref, size_t n,
+verify_kernel(const T* __restrict__ dsl, const T* __restrict__ ref, size_t n,
               double rel_tol, double abs_tol, VerifyAcc* acc) {
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
   double mxr = 0, mnr = inf, mxa = 0, mna = inf;
   unsigned long long bad = 0;
   for(size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n;
       idx += (size_t)gridDim.x * blockDim.x) {
-    const double a = __ldg(&dsl[idx]), b = __ldg(&ref[idx]);
+    const T a = __ldg(&dsl[idx]), b = __ldg(&ref[idx]);
     // cuda_verify.hpp:25-45 (expected = reference value b, actual = a): both errors are 0 for equal
     // values, else |b - a| and |(b - a) / b| - so a zero reference with a nonzero value gives inf
-    const double ae = (b != a) ? fabs(b - a) : 0.0;
-    const double re = (b != a) ? fabs((b - a) / b) : 0.0;
+    // (FieldType arithmetic where the reference's templates use it: the absolute error and isclose's
+    // difference are formed in T, the relative error in double)
+    const double ae = (b != a) ? (double)fabs(b - a) : 0.0;
+    const double re = (b != a) ? fabs(((double)b - a) / b) : 0.0;
     // isclose_kernel (cuda_verify.hpp:58-69): false whenever a NaN is involved
     const bool close = fabs(a - b) <= (abs_tol + rel_tol * fabs(b));
     // thrust's maximum / minimum leave the result open when NaN errors are reduced; here they are
@@ -259,10 +273,11 @@ verify_kernel(const double* __restrict__ dsl, const double* __restrict__ ref, si
 
 // [elem][sparse][k] (k fastest)  ->  [k][sparse][elem] (elem fastest); 32x32 smem transpose per
 // sparse slot so that both the read and the write are coalesced.
+template <class T>
 __global__ void __launch_bounds__(256)
-reshape_kernel(const double* __restrict__ in, double* __restrict__ out, int k_size, int n_elem,
+reshape_kernel(const T* __restrict__ in, T* __restrict__ out, int k_size, int n_elem,
                int sparse, bool back) {
-  __shared__ double tile[32][33];
+  __shared__ T tile[32][33];
   const int s = blockIdx.z;
   const int e0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 x 8
@@ -443,10 +458,9 @@ halo_unpack_p2p_kernel(double* __restrict__ field, unsigned long long* my, const
 }
 } // namespace
 
-extern "C" {
-
-int b200rt_verify_field(const double* dsl, const double* ref, size_t n, double rel_tol,
-                        double abs_tol, int iteration, b200_verification_metrics* out, void* stream) {
+template <class T>
+static int verify_impl(const T* dsl, const T* ref, size_t n, double rel_tol, double abs_tol, int iteration,
+                       b200_verification_metrics* out, void* stream) {
   if(!out)
     return b200rt_set_error(B200_ERR_ARG, "b200rt_verify_field: out is null");
   const double inf = std::numeric_limits<double>::infinity(); // thrust::reduce's initial values
@@ -474,8 +488,8 @@ int b200rt_verify_field(const double* dsl, const double* ref, size_t n, double r
   out->is_valid = h.n_failed == 0;
   return 0;
 }
-
-static int reshape_impl(const double* in, double* out, int k_size, int n_elem, int sparse,
+template <class T>
+static int reshape_impl(const T* in, T* out, int k_size, int n_elem, int sparse,
                         bool back, void* stream) {
   if(k_size <= 0 || n_elem <= 0 || sparse <= 0)
     return 0;
@@ -484,6 +498,18 @@ static int reshape_impl(const double* in, double* out, int k_size, int n_elem, i
   CK(cudaGetLastError());
   return 0;
 }
+
+extern "C" {
+
+int b200rt_verify_field(const double* dsl, const double* ref, size_t n, double rel_tol,
+                        double abs_tol, int iteration, b200_verification_metrics* out, void* stream) {
+  return verify_impl(dsl, ref, n, rel_tol, abs_tol, iteration, out, stream);
+}
+int b200rt_verify_field_f32(const float* dsl, const float* ref, size_t n, double rel_tol,
+                            double abs_tol, int iteration, b200_verification_metrics* out, void* stream) {
+  return verify_impl(dsl, ref, n, rel_tol, abs_tol, iteration, out, stream);
+}
+
 int b200rt_graph_begin(void* stream) {
   // thread-local capture mode: helper threads of the process (NCCL proxies, a framework's watchdog) keep
   // making CUDA calls while this thread records
@@ -605,6 +631,12 @@ int b200rt_reshape(const double* in, double* out, int k, int n, int sp, void* s)
   return reshape_impl(in, out, k, n, sp, false, s);
 }
 int b200rt_reshape_back(const double* in, double* out, int k, int n, int sp, void* s) {
+  return reshape_impl(in, out, k, n, sp, true, s);
+}
+int b200rt_reshape_f32(const float* in, float* out, int k, int n, int sp, void* s) {
+  return reshape_impl(in, out, k, n, sp, false, s);
+}
+int b200rt_reshape_back_f32(const float* in, float* out, int k, int n, int sp, void* s) {
   return reshape_impl(in, out, k, n, sp, true, s);
 }
 

@@ -1,6 +1,7 @@
 // C++ conveniences over the C-ABI runtime (include/dawn_b200_rt.h) used by generated host code.
 #pragma once
 #include "../../include/dawn_b200_rt.h"
+#include "defs.hpp"
 
 #include <stdexcept>
 #include <string>
@@ -20,7 +21,7 @@ inline void check(int err) {
 // Device scratch for temporaries that cannot be kept in registers; (re)allocated on first use with
 // the strides of the ijk fields it is used with.
 struct scratch_field {
-  double* data = nullptr;
+  ::dawn::float_type* data = nullptr;
   int stride_j = 0, stride_k = 0, levels = 0;
   scratch_field() = default;
   scratch_field(const scratch_field&) = delete;
@@ -31,12 +32,12 @@ struct scratch_field {
     b200rt_free(data);
     data = nullptr;
     void* p = nullptr;
-    size_t bytes = (size_t)sk * (size_t)(nlevels + 1) * sizeof(double);
+    size_t bytes = (size_t)sk * (size_t)(nlevels + 1) * sizeof(::dawn::float_type);
     if(int e = b200rt_malloc(&p, bytes))
       return e;
     if(int e = b200rt_memset(p, 0, bytes, nullptr))
       return e;
-    data = static_cast<double*>(p);
+    data = static_cast<::dawn::float_type*>(p);
     stride_j = sj, stride_k = sk, levels = nlevels;
     return 0;
   }

@@ -20,8 +20,21 @@ using float_type = double;
 #endif
 } // namespace dawn
 
+// pair of adjacent values: what generated tile kernels read from shared memory in one LDS.128 / LDS.64
+#if defined(__CUDACC__) || defined(B200_EMU_VECTOR_TYPES)
+#if defined(__CUDACC__)
+#include <vector_types.h>
+#include <vector_functions.h>
+#endif
+namespace dawn {
 #if DAWN_PRECISION == DAWN_SINGLE_PRECISION
-#error "the b200 backend currently emits double precision only (b200_field_t carries doubles)"
+using float_type2 = float2;
+__host__ __device__ inline float2 make_float_type2(float x, float y) { return make_float2(x, y); }
+#else
+using float_type2 = double2;
+__host__ __device__ inline double2 make_float_type2(double x, double y) { return make_double2(x, y); }
+#endif
+} // namespace dawn
 #endif
 
 #ifndef GRIDTOOLS_DAWN_HALO_EXTENT

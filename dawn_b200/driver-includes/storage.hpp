@@ -3,8 +3,8 @@
 //   meta_data_t md(i, j, k);  storage_t f(md, "name");  auto v = make_host_view(f); v(i,j,k) = ..;
 //   f.sync();  f.strides();  f.get_storage_info_ptr()->index(i,j,k) / total_length<D>();
 // A storage owns a pinned host mirror and an HBM buffer (allocated lazily through the C-ABI
-// runtime).  Layout: i fastest, rows padded to a multiple of 16 doubles and shifted so that the first
-// interior point (i = halo) of every row starts a 128-byte line -> warps reading a row issue full,
+// runtime).  Layout: i fastest, rows padded to a multiple of 128 bytes and shifted so that the first
+// interior point (i = halo) of every row starts a 128-byte line (16 doubles / 32 floats) -> warps reading a row issue full,
 // aligned 128 B transactions.  Masked dimensions have stride 0.
 #pragma once
 #include "b200_runtime.hpp"
@@ -44,10 +44,11 @@ public:
     len_ = {MI ? i : 1u, MJ ? j : 1u, MK ? k : 1u};
     const int h = ::gridtools::dawn::halo::value;
     size_t s = 1;
+    const int line = 128 / (int)sizeof(::dawn::float_type); // elements per 128-byte line
     if(MI) {
       str_[0] = 1;
-      lead_ = (16 - h % 16) % 16;
-      s = ((size_t)len_[0] + 15) / 16 * 16;
+      lead_ = (line - h % line) % line;
+      s = ((size_t)len_[0] + line - 1) / line * line;
     }
     if(MJ) {
       str_[1] = (int)s;
@@ -57,7 +58,7 @@ public:
       str_[2] = (int)s;
       s *= len_[2];
     }
-    elems_ = s + lead_ + 16;
+    elems_ = s + lead_ + line;
   }
   template <int D>
   uint_t total_length() const {

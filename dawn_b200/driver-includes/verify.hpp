@@ -27,7 +27,9 @@ class verifier {
   }
 
 public:
-  explicit verifier(const domain& dom, double precision = 1e-10) : dom_(dom), precision_(precision) {}
+  // default precision as the reference's (verify.hpp:30-32): 1e-10 for double, 1e-4 for float
+  explicit verifier(const domain& dom, double precision = sizeof(::dawn::float_type) == 8 ? 1e-10 : 1e-4)
+      : dom_(dom), precision_(precision) {}
 
   template <class V, class... Storages>
   void fill(V value, Storages&... storages) const {

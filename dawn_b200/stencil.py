@@ -45,11 +45,15 @@ def _round_up(x, m):
 class Storage:
     """Device-resident storage with the layout of driver-includes/storage.hpp: i fastest, rows padded
     to 16 doubles, first interior point of each row 128-byte aligned.  `dims` in {"ijk","ij","i","j",
-    "k"}.  Backed by a torch CUDA tensor (float64)."""
+    "k"}.  Backed by a torch CUDA tensor; dtype "float64" (::dawn::float_type = double) or "float32" (modules
+    generated with single_precision=1): rows are padded to 128 bytes either way."""
 
-    def __init__(self, ni, nj, nk, dims="ijk", device="cuda", halo=HALO):
+    def __init__(self, ni, nj, nk, dims="ijk", device="cuda", halo=HALO, dtype="float64"):
         import torch
         self.dims = dims
+        self.dtype = getattr(torch, dtype) if isinstance(dtype, str) else dtype
+        self.itemsize = 4 if self.dtype == torch.float32 else 8
+        line = 128 // self.itemsize   # elements per 128-byte line
         mi, mj, mk = "i" in dims, "j" in dims, "k" in dims
         self.shape = (ni if mi else 1, nj if mj else 1, nk if mk else 1)
         s = 1
@@ -57,16 +61,16 @@ class Storage:
         self.stride_i = self.stride_j = self.stride_k = 0
         if mi:
             self.stride_i = 1
-            self.lead = (16 - halo % 16) % 16
-            s = _round_up(self.shape[0], 16)
+            self.lead = (line - halo % line) % line
+            s = _round_up(self.shape[0], line)
         if mj:
             self.stride_j = s
             s *= self.shape[1]
         if mk:
             self.stride_k = s
             s *= self.shape[2]
-        self.elems = s + self.lead + 16
-        self.buf = torch.zeros(self.elems, dtype=torch.float64, device=device)
+        self.elems = s + self.lead + line
+        self.buf = torch.zeros(self.elems, dtype=self.dtype, device=device)
 
     # -- views --------------------------------------------------------------------------------
     def _strided(self, t):
@@ -82,8 +86,8 @@ class Storage:
     def from_numpy(self, arr):
         """arr indexed [k, j, i] (length 1 along masked dimensions)."""
         import torch
-        arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(self.shape[2], self.shape[1],
-                                                                  self.shape[0])
+        arr = np.ascontiguousarray(arr, dtype=np.float32 if self.itemsize == 4 else np.float64).reshape(
+            self.shape[2], self.shape[1], self.shape[0])
         self.view().copy_(torch.from_numpy(arr))
         return self
 
@@ -95,7 +99,7 @@ class Storage:
         return self
 
     def descriptor(self):
-        return _rt.Field(self.buf.data_ptr() + 8 * self.lead, self.stride_j, self.stride_k)
+        return _rt.Field(self.buf.data_ptr() + self.itemsize * self.lead, self.stride_j, self.stride_k)
 
 
 def dense_descriptor(ptr, ni, nj, dims="ijk"):
@@ -123,6 +127,8 @@ class StencilModule:
         self.info = json.loads(info().decode())
         self.fields = self.info["fields"]
         self.unstructured = self.info.get("grid") == "Unstructured"
+        # ::dawn::float_type of the translation unit (codegen option single_precision)
+        self.dtype = "float32" if self.info.get("float_type") == "float" else "float64"
         self._setup = getattr(self.lib, "setup_" + name)
         if self.unstructured:
             self._setup.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int,
@@ -211,7 +217,7 @@ class Stencil:
         import torch
         dom = self.domain
         if self._host_storages is None:
-            self._host_storages = [Storage(dom.isize, dom.jsize, a.shape[0], f["dims"])
+            self._host_storages = [Storage(dom.isize, dom.jsize, a.shape[0], f["dims"], dtype=self.module.dtype)
                                    for f, a in zip(self.module.fields, arrays)]
             self._pinned = [None] * len(arrays)
             self._uploaded_once = False
@@ -222,7 +228,7 @@ class Stencil:
                 pin = a
             else:
                 if self._pinned[n] is None:
-                    self._pinned[n] = torch.empty(tuple(a.shape), dtype=torch.float64).pin_memory()
+                    self._pinned[n] = torch.empty(tuple(a.shape), dtype=getattr(torch, self.module.dtype)).pin_memory()
                 pin = self._pinned[n]
                 pin.copy_(a if isinstance(a, torch.Tensor) else torch.from_numpy(a))
             staged.append(pin)
@@ -241,13 +247,13 @@ class Stencil:
                 if needs_upload(f):
                     st.view().copy_(pin.reshape(st.shape[2], st.shape[1], st.shape[0]),
                                     non_blocking=True)
-                    h2d += pin.numel() * 8
+                    h2d += pin.numel() * pin.element_size()
             self.run(*self._host_storages, stream=stream)
             for f, st, pin in zip(self.module.fields, self._host_storages, staged):
                 if f["name"] in written:
                     pin.reshape(st.shape[2], st.shape[1], st.shape[0]).copy_(st.view(),
                                                                              non_blocking=True)
-                    d2h += pin.numel() * 8
+                    d2h += pin.numel() * pin.element_size()
             torch.cuda.current_stream().synchronize()
         self._uploaded_once = True
         for f, a, pin in zip(self.module.fields, arrays, staged):
@@ -278,7 +284,7 @@ class Stencil:
                 if "k" not in f["dims"] and needs_upload(f):
                     st.view().copy_(pin.reshape(st.shape[2], st.shape[1], st.shape[0]),
                                     non_blocking=True)
-                    h2d += pin.numel() * 8
+                    h2d += pin.numel() * pin.element_size()
         for k0 in range(0, nz, k_chunk):
             kc = min(k_chunk, nz - k0)
             ev_up, ev_run = torch.cuda.Event(), torch.cuda.Event()
@@ -286,7 +292,7 @@ class Stencil:
                 for f, st, pin in zip(fields, self._host_storages, staged):
                     if "k" in f["dims"] and needs_upload(f):
                         st.view()[k0:k0 + kc].copy_(pin[k0:k0 + kc], non_blocking=True)
-                        h2d += pin[k0:k0 + kc].numel() * 8
+                        h2d += pin[k0:k0 + kc].numel() * pin.element_size()
                 ev_up.record(s_up)
             inst = self._chunk_instances.get(kc)
             if inst is None:
@@ -297,7 +303,7 @@ class Stencil:
             for f, st in zip(fields, self._host_storages):
                 fd = st.descriptor()
                 if "k" in f["dims"]:
-                    fd = _rt.Field(fd.data + 8 * k0 * st.stride_k, fd.stride_j, fd.stride_k)
+                    fd = _rt.Field(fd.data + st.itemsize * k0 * st.stride_k, fd.stride_j, fd.stride_k)
                 descs.append(fd)
             s_run.wait_event(ev_up)
             inst.run(*descs, stream=s_run.cuda_stream)
@@ -307,7 +313,7 @@ class Stencil:
                 for f, st, pin in zip(fields, self._host_storages, staged):
                     if f["name"] in written and "k" in f["dims"]:
                         pin[k0:k0 + kc].copy_(st.view()[k0:k0 + kc], non_blocking=True)
-                        d2h += pin[k0:k0 + kc].numel() * 8
+                        d2h += pin[k0:k0 + kc].numel() * pin.element_size()
         for s in self._chunk_streams:
             main.wait_stream(s)
         main.synchronize()

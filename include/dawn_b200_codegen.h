@@ -69,6 +69,11 @@ typedef struct dawn_b200_options {
                              backward (L2-fed) sweeps interleave; -1: N from $DAWN_B200_STAGGER_NS (probing) */
   int ico_full_blocks;    /* default 0: unstructured kernels run full blocks of levels through an unrolled
                              loop without per-level bound checks (more loads in flight per thread) */
+  int single_precision;   /* default 0: ::dawn::float_type is double; 1: the translation unit is generated for
+                             float (the reference selects the type when the generated code is COMPILED,
+                             driver-includes/defs.hpp:47-81; here the TMA box geometry and the shared-memory
+                             pairs depend on the element size, so the emitter has to know - the emitted text
+                             defines DAWN_PRECISION itself and static_asserts the size) */
 } dawn_b200_options;
 
 /* Fills `opts` with the defaults above. */

@@ -78,6 +78,11 @@ int b200rt_check_last_launch(void); /* cudaGetLastError -> B200_ERR_CUDA */
  * both strides (in elements) even.  Out-of-range box elements are zero-filled and never read. */
 int b200rt_tensor_map_3d(void* map, const void* base, int size_i, int size_j, int size_k,
                          int stride_j, int stride_k, int box_i, int box_j, int box_k);
+/* Same for elements of `elem_bytes` (8: double, 4: float); strides are in elements and must be multiples
+ * of 16 bytes, like box_i. */
+int b200rt_tensor_map_3d_es(void* map, const void* base, int size_i, int size_j, int size_k,
+                            int stride_j, int stride_k, int box_i, int box_j, int box_k,
+                            int elem_bytes);
 
 /* VerificationMetrics twin (driver-includes/verification_metrics.hpp:3-10), computed in ONE pass
  * over the two device arrays (the reference runs 2 kernels + 8 thrust reductions + 2 cudaMallocs per
@@ -89,10 +94,14 @@ typedef struct b200_verification_metrics {
   long long n_failed;
 } b200_verification_metrics;
 
-/* isclose semantics of cuda_verify.hpp:58-80: |a-b| <= abs_tol + rel_tol*|b| (NaN==NaN is close).
- * `dsl` is the tested field, `ref` the reference one; both device pointers of n doubles. */
+/* isclose semantics of cuda_verify.hpp:58-80: |a-b| <= abs_tol + rel_tol*|b|, false whenever a NaN is
+ * involved; errors as cuda_verify.hpp:25-45 (0 for equal values, else |b-a| and |(b-a)/b|: inf for a zero
+ * reference value; initial values of the reductions as thrust's: max 0, min inf).
+ * `dsl` is the tested field, `ref` the reference one; both device pointers of n elements. */
 int b200rt_verify_field(const double* dsl, const double* ref, size_t n, double rel_tol,
                         double abs_tol, int iteration, b200_verification_metrics* out, void* stream);
+int b200rt_verify_field_f32(const float* dsl, const float* ref, size_t n, double rel_tol,
+                            double abs_tol, int iteration, b200_verification_metrics* out, void* stream);
 
 /* Verification record: twin of the reference's MetricsSerialiser (driver-includes/to_json.{hpp,cpp}),
  * which merges per-field metrics into a nlohmann::json object passed to setup_<N>.  Here the record is
@@ -117,6 +126,10 @@ int b200rt_reshape(const double* in, double* out, int k_size, int num_elements, 
                    void* stream);
 int b200rt_reshape_back(const double* in, double* out, int k_size, int num_elements, int sparse_size,
                         void* stream);
+int b200rt_reshape_f32(const float* in, float* out, int k_size, int num_elements, int sparse_size,
+                       void* stream);
+int b200rt_reshape_back_f32(const float* in, float* out, int k_size, int num_elements, int sparse_size,
+                            void* stream);
 
 /* Neighbour table: row-major host table [elem][nbh] -> device SoA table [nbh][elem] (int32, -1
  * padded), bit-exact with generateNbhTable (cuda_utils.hpp:212-263). */

@@ -283,13 +283,16 @@ class CartesianRun:
         self.jMin, self.jMax = jm, nj - jp - 1
         self.kMin, self.kMax = km, nk - kp - 1
         self.f = dict(fields)
+        # ::dawn::float_type of this run: float if the caller's storages are (driver-includes/defs.hpp:47-81);
+        # temporaries and float_type locals follow it, literals are weak scalars (`(float_type)2.0 * x`)
+        self.ft = _float_type(fields)
         for st in self._stencil_sequence():
             exts = stage_extents(st)
             # temporaries: full 3-D storages (CXXNaiveCodeGen.cpp:318-345), +1 safety level
             for aid in self.tmp_ids:
                 nm = self.names[aid]
                 if nm not in self.f:
-                    self.f[nm] = np.zeros((nk + 1, nj + 1, ni + 1))
+                    self.f[nm] = np.zeros((nk + 1, nj + 1, ni + 1), dtype=self.ft)
             sidx = 0
             for ms in st["multiStages"]:
                 stages = ms["stages"]
@@ -436,6 +439,8 @@ class CartesianRun:
             val = self._eval(init[0]) if init else 0.0
             tid = v.get("type", {}).get("builtin_type", {}).get("type_id", "Float")
             val = self._cast(val, tid)
+            if tid in ("Float", "Double") and not isinstance(val, (bool, np.bool_)):
+                val = np.asarray(val, dtype=self.ft)   # both spell ::dawn::float_type (ASTCodeGenCXX.cpp:163-181)
             shape = (self.j1 - self.j0 + 1, self.i1 - self.i0 + 1)
             self.locals[aid] = np.broadcast_to(np.asarray(val), shape).copy()
         elif k == "if_stmt":
@@ -509,7 +514,7 @@ class CartesianRun:
             return float(s)
         if k == "var_access_expr":
             if v.get("is_external", False):
-                return self.globals[v["name"]]
+                return _global_value(self.globals[v["name"]])
             return self.locals[v["data"]["accessID"]]
         if k == "binary_operator":
             a, b = self._eval(v["left"]), self._eval(v["right"])
@@ -540,6 +545,19 @@ class CartesianRun:
             with np.errstate(all="ignore"):
                 return _MATH[callee](*args)
         raise NotImplementedError(k)
+
+
+def _global_value(g):
+    """A global of type double stays a C `double` whatever ::dawn::float_type is (the globals struct keeps
+    the declared types, CodeGen.cpp:110-136), so `field * global` is evaluated in double even in a single-
+    precision build: a NumPy scalar (strong type), not a weak Python float."""
+    return np.float64(g) if isinstance(g, float) else g
+
+
+def _float_type(fields):
+    """float32 if any floating-point storage of the run is single precision, else float64."""
+    return np.float32 if any(isinstance(a, np.ndarray) and a.dtype == np.float32 for a in fields.values()) \
+        else np.float64
 
 
 def _overlap(a, b):
@@ -659,6 +677,7 @@ class UnstructuredRun:
 
     def run(self, fields):
         self.f = fields
+        self.ft = _float_type(fields)
         kmin, kmax = 0, self.k_size - 1
         for st in self.ir["stencils"]:
             for ms in st["multiStages"]:
@@ -750,7 +769,7 @@ class UnstructuredRun:
             tid = v.get("type", {}).get("builtin_type", {}).get("type_id", "Float")
             if tid == "Integer":
                 val = np.trunc(val)
-            self.locals[aid] = np.broadcast_to(np.asarray(val, dtype=float), self.elems.shape).copy()
+            self.locals[aid] = np.broadcast_to(np.asarray(val, dtype=self.ft), self.elems.shape).copy()
         elif kd == "if_stmt":
             ck, cv = _kind(v["cond_part"])
             cond = np.broadcast_to(np.asarray(self._eval(cv["expr"], ctx)).astype(bool), self.elems.shape)
@@ -814,7 +833,7 @@ class UnstructuredRun:
                                                            else float(v["value"]))
         if kd == "var_access_expr":
             if v.get("is_external", False):
-                return self.globals[v["name"]]
+                return _global_value(self.globals[v["name"]])
             return self.locals[v["data"]["accessID"]]
         if kd == "field_access_expr":
             return self.f[v["name"]][self._index(v, ctx)]
@@ -839,8 +858,8 @@ class UnstructuredRun:
             center = ctx.center if ctx.nb is None else np.maximum(ctx.nb, 0)
             around = _Ctx(center, _LOC[chain[0]])
             table = self.mesh.nbh_table(chain, space.get("include_center", False))[center]
-            acc = np.broadcast_to(np.asarray(self._eval(v["init"], around), dtype=float),
-                                  center.shape).copy()
+            acc = np.broadcast_to(np.asarray(self._eval(v["init"], around), dtype=self.ft),
+                                  center.shape).copy()   # `::dawn::float_type lhs = init` in the reference text
             weights = v.get("weights", [])
             op = v.get("op", "+")
             for idx in range(table.shape[1]):

@@ -110,7 +110,7 @@ def run(name, code, info, mesh, k, fields, globals_=None, splitters=None):
     n_of = {"cells": mesh.num_cells, "edges": mesh.num_edges, "vertices": mesh.num_vertices, "none": 1}
     dev, fs = [], []
     for fd in info["fields"]:
-        a = np.array(fields[fd["name"]], dtype=np.float64)
+        a = np.array(fields[fd["name"]], dtype=np.float32 if info.get("float_type") == "float" else np.float64)
         if fd["sparse"]:
             a = np.swapaxes(a, -1, -2)                           # [k, n, nbh] -> [k, nbh, n]
         a = np.ascontiguousarray(a)
@@ -155,8 +155,11 @@ def run_cartesian(name, code, info, dims, halos, fields, globals_=None, keep_k_c
         fn.argtypes = [ctypes.c_void_p, ctypes.c_double]
         fn(handle, float(v))
     dev, fs, keep, views = [], [], [], []
+    ft = np.float32 if info.get("float_type") == "float" else np.float64   # ::dawn::float_type of the module
+    es = np.dtype(ft).itemsize
+    line = 128 // es
     for fd in info["fields"]:
-        src = np.ascontiguousarray(np.array(fields[fd["name"]], dtype=np.float64))
+        src = np.ascontiguousarray(np.array(fields[fd["name"]], dtype=ft))
         # the layout of dawn_b200.Storage / driver-includes storage_info: rows padded to 16 elements, a lead pad
         # that puts the first interior point (i = halo) on a 128-byte line; wrapper-allocated fields of a
         # generated class get exactly this layout and the launchers insist that all ijk fields share strides
@@ -165,20 +168,20 @@ def run_cartesian(name, code, info, dims, halos, fields, globals_=None, keep_k_c
         h = halos[0]
         s_, lead, sj, sk = 1, 0, 0, 0
         if "i" in d:
-            lead = (16 - h % 16) % 16
-            s_ = (li + 15) // 16 * 16
+            lead = (line - h % line) % line
+            s_ = (li + line - 1) // line * line
         if "j" in d:
             sj = s_
             s_ *= lj
         if "k" in d:
             sk = s_
             s_ *= lk
-        raw = np.zeros(s_ + lead + 16 + 32)
+        raw = np.zeros(s_ + lead + line + 2 * line, dtype=ft)
         off = 0
-        while (raw.ctypes.data + 8 * off) % 256:
+        while (raw.ctypes.data + es * off) % 256:
             off += 1
         base = raw[off + lead:]
-        view = np.lib.stride_tricks.as_strided(base, shape=(lk, lj, li), strides=(8 * sk, 8 * sj, 8))
+        view = np.lib.stride_tricks.as_strided(base, shape=(lk, lj, li), strides=(es * sk, es * sj, es))
         view[...] = src
         keep.append(raw)
         views.append(view)

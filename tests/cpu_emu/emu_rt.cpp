@@ -79,21 +79,29 @@ int b200rt_event_elapsed_ms(void*, void*, float* ms) {
 }
 // CUtensorMap stand-in: the geometry itself (struct emu_tensor_map of emu_cuda.hpp)
 struct emu_tensor_map_rt {
-  const double* base;
+  const void* base;
   int size[3];
   long long stride[3];
   int box[3];
+  int elem_bytes;
 };
 static long g_tensor_maps = 0;
 long emu_tensor_maps_encoded(void) { return g_tensor_maps; }
-int b200rt_tensor_map_3d(void* map, const void* base, int size_i, int size_j, int size_k, int stride_j,
-                         int stride_k, int box_i, int box_j, int box_k) {
+int b200rt_tensor_map_3d_es(void* map, const void* base, int size_i, int size_j, int size_k, int stride_j,
+                            int stride_k, int box_i, int box_j, int box_k, int elem_bytes) {
+  // the alignment rules of the real encoder (rt.cu): what the emitted launchers promise
+  const int per16 = 16 / elem_bytes;
+  if((reinterpret_cast<uintptr_t>(base) & 15) || stride_j % per16 || stride_k % per16 || (box_i * elem_bytes) % 16)
+    return b200rt_set_error(B200_ERR_LAYOUT, "emu: TMA alignment rules violated");
   ++g_tensor_maps;
-  emu_tensor_map_rt m{static_cast<const double*>(base), {size_i, size_j, size_k}, {1, stride_j, stride_k},
-                      {box_i, box_j, box_k}};
+  emu_tensor_map_rt m{base, {size_i, size_j, size_k}, {1, stride_j, stride_k}, {box_i, box_j, box_k}, elem_bytes};
   std::memset(map, 0, 128);
   std::memcpy(map, &m, sizeof(m));
   return 0;
+}
+int b200rt_tensor_map_3d(void* map, const void* base, int size_i, int size_j, int size_k, int stride_j,
+                         int stride_k, int box_i, int box_j, int box_k) {
+  return b200rt_tensor_map_3d_es(map, base, size_i, size_j, size_k, stride_j, stride_k, box_i, box_j, box_k, 8);
 }
 // the *_from_host / verify paths are GPU-tested (tests/test_unstructured_gpu.py); not part of the emulation
 int b200rt_reshape(const double*, double*, int, int, int, void*) {
@@ -105,6 +113,16 @@ int b200rt_reshape_back(const double*, double*, int, int, int, void*) {
 int b200rt_verify_field(const double*, const double*, size_t, double, double, int, b200_verification_metrics*,
                         void*) {
   return b200rt_set_error(B200_ERR_RUNTIME, "emu: b200rt_verify_field is not emulated");
+}
+int b200rt_reshape_f32(const float*, float*, int, int, int, void*) {
+  return b200rt_set_error(B200_ERR_RUNTIME, "emu: b200rt_reshape_f32 is not emulated");
+}
+int b200rt_reshape_back_f32(const float*, float*, int, int, int, void*) {
+  return b200rt_set_error(B200_ERR_RUNTIME, "emu: b200rt_reshape_back_f32 is not emulated");
+}
+int b200rt_verify_field_f32(const float*, const float*, size_t, double, double, int, b200_verification_metrics*,
+                            void*) {
+  return b200rt_set_error(B200_ERR_RUNTIME, "emu: b200rt_verify_field_f32 is not emulated");
 }
 int b200rt_metrics_record_add(b200_metrics_record*, const char*, const char*, const b200_verification_metrics*) {
   return 0;

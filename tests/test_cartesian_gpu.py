@@ -99,6 +99,45 @@ def test_tridiagonal_solve_at_the_benchmark_shapes(I, J, K):
     assert bit_equal(got["a"], f["a"]) and bit_equal(got["b"], f["b"])
 
 
+@pytest.mark.parametrize("I,J,K", [(64, 64, 80), (132, 70, 9), (256, 120, 41), (37, 19, 5)])
+@pytest.mark.parametrize("name", ["hori_diff_type2_stencil", "tridiagonal_solve", "hori_diff_stencil_02"])
+def test_single_precision_modules(name, I, J, K):
+    """codegen option single_precision=1 (::dawn::float_type = float; the reference's DAWN_PRECISION switch,
+    driver-includes/defs.hpp:47-81): TMA boxes of floats, float2 shared-memory pairs, float storages.
+    Bar: 1e-5 relative against the naive backend evaluated in float (north star); with -fmad=false every
+    node is one IEEE single operation, so the comparison with the float32 oracle is in fact bit for bit.
+    (37 x 19: rows that are not 16-byte multiples of floats - the plain kernels run.)"""
+    import torch
+    import dawn_b200
+    f = {"hori_diff_type2_stencil": hori_diff_type2_inputs, "tridiagonal_solve": tridiagonal_inputs,
+         "hori_diff_stencil_02": lambda i, j, k: {"in": np.random.default_rng(5).uniform(0.5, 1.5, (k + 1, j + 6, i + 6)),
+                                                   "out": np.full((k + 1, j + 6, i + 6), -1.0)}}[name](I, J, K)
+    f32 = {n: v.astype(np.float32) for n, v in f.items()}
+    dom_dims = (I + 2 * HALO, J + 2 * HALO, K)
+    want = run_oracle(name, dom_dims, f32)
+    mod = dawn_b200.load_stencil(name, single_precision=1)
+    assert mod.dtype == "float32"
+    dom = dawn_b200.Domain(*dom_dims)
+    dom.set_halos(HALO, HALO, HALO, HALO, 0, 0)
+    st = mod(dom)
+    stor = [dawn_b200.Storage(dom_dims[0], dom_dims[1], f32[fd["name"]].shape[0], fd["dims"], dtype="float32").from_numpy(
+        f32[fd["name"]]) for fd in mod.fields]
+    st.run(*stor)
+    torch.cuda.synchronize()
+    if I % 4 == 0:
+        assert st.last_launch()["kernel"] in ("tma", "ring"), st.last_launch()
+    for fd, s in zip(mod.fields, stor):
+        got = s.to_numpy()
+        assert got.dtype == np.float32
+        w = want[fd["name"]]
+        assert np.allclose(got, w, rtol=1e-5, atol=0.0), fd["name"]
+        assert bit_equal(got, w), fd["name"]
+    if name == "tridiagonal_solve":   # smooth in its inputs: also close to the double-precision result
+        wd = run_oracle(name, dom_dims, f)
+        got = stor[0].to_numpy()[:K, HALO:-HALO, HALO:-HALO]
+        assert np.allclose(got, wd["d"][:K, HALO:-HALO, HALO:-HALO], rtol=1e-4)
+
+
 @pytest.mark.parametrize("opts", [dict(rows_per_thread=1), dict(rows_per_thread=4),
                                   dict(block_size_i=32, block_size_j=8, rows_per_thread=2),
                                   dict(inline_temporaries=0), dict(use_tma=0),

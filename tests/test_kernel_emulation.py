@@ -357,3 +357,77 @@ def test_tiny_and_ragged_domains_through_the_default_kernels(name):
     info = json.loads(re.search(r'return "(\{.*\})";', code).group(1).encode().decode("unicode_escape"))
     for size in ((1, 1, 12), (3, 2, 12), (129, 3, 21), (2, 65, 12)):
         _cartesian_case(name, code, info, size, 900)
+
+
+# ---- single precision (codegen option single_precision=1: ::dawn::float_type = float, the reference's
+# DAWN_PRECISION switch, driver-includes/defs.hpp:47-81).  The oracle interprets the same IIR on float32
+# storages; with -ffp-contract=off / -fmad=false every node is one IEEE single operation on both sides, so
+# the comparison stays bit for bit (math calls excepted: libm and CUDA differ in the last place there) ------
+F32_CARTESIAN = ["hori_diff_type2_stencil", "tridiagonal_solve", "hori_diff_stencil", "hori_diff_stencil_02", "lap",
+                 "copy_stencil", "kcache_fill_backward", "intervals_stencil", "p_grad_c", "fuzz_03", "fuzz_09"]
+
+
+def _f32_case(name, code, info, size, seed):
+    I, J, K = size
+    ni, nj = I + 2 * HALO, J + 2 * HALO
+    rng = np.random.default_rng(seed)
+    f = {}
+    for fd in info["fields"]:
+        d = fd["dims"]
+        f[fd["name"]] = rng.uniform(0.5, 1.5, (K + 1 if "k" in d else 1, nj if "j" in d else 1,
+                                               ni if "i" in d else 1)).astype(np.float32)
+    if name in ("tridiagonal_solve", "kparallel_solver") and "b" in f:
+        f["b"] += np.float32(4.0)
+    g = CART_GLOBALS.get(name)
+    if g is None and info.get("globals"):
+        g = {n: 0.375 for n in info["globals"]}
+    want = run_oracle(name, (ni, nj, K), f, globals_=g)
+    got, _ = emu.run_cartesian(name, code, info, (ni, nj, K), (HALO, HALO, HALO, HALO, 0, 0), f, globals_=g)
+    for fd in info["fields"]:
+        n = fd["name"]
+        assert got[n].dtype == np.float32 and want[n].dtype == np.float32
+        assert bit_equal(got[n].reshape(want[n].shape), want[n]), (name, n, size)
+    return emu.run_cartesian.tensor_maps
+
+
+@pytest.mark.parametrize("plain", [False, True], ids=["default", "plain"])
+@pytest.mark.parametrize("name", F32_CARTESIAN)
+def test_single_precision_cartesian_kernels_on_the_cpu(name, plain):
+    opts = dict(use_tma=0, column_ring=0) if plain else {}
+    code = codegen.compile_iir(open(iir_path(name)).read(), backend="b200", single_precision=1, **opts)
+    info = json.loads(re.search(r'return "(\{.*\})";', code).group(1).encode().decode("unicode_escape"))
+    assert info["float_type"] == "float" and "sizeof(::dawn::float_type) == 4" in code
+    maps = 0
+    for size in ((36, 11, 12), (72, 26, 24)):    # row lengths that are multiples of 4: 16-byte rows of floats
+        maps = _f32_case(name, code, info, size, 600 + len(name))
+    if "tma::" in code and not plain:
+        assert maps > 0, "the TMA variant was emitted but the plain one ran"
+
+
+@pytest.mark.parametrize("name", ["ICON_laplacian_stencil", "ICON_nabla4_stencil", "diffusion", "gradient", "fuzzico_02",
+                                  "fuzzico_07", "sparseAssignment3", "tridiagonalSolve", "verticalSum"])
+def test_single_precision_unstructured_kernels_on_the_cpu(name):
+    code, info = emitted(name, single_precision=1)
+    assert info["float_type"] == "float"
+    m, k = TriMesh(11, 8), 7
+    f = {n: v.astype(np.float32) for n, v in random_fields(info, m, k, np.random.default_rng(19)).items()}
+    if name == "tridiagonalSolve":
+        f["b"] += np.float32(4.0)
+    g = {n: 0.625 for n in info["globals"]} if info.get("globals") else None
+    w = {n: v.astype(np.float32) for n, v in with_temporaries(name, m, k, f).items()}
+    want = naive_interp.run_unstructured(iir_path(name), m, k, w, globals_=g)
+    got, _ = emu.run(name, code, info, m, k, f, globals_=g)
+    for fd in info["fields"]:
+        assert got[fd["name"]].dtype == np.float32
+    if not info.get("globals"):
+        compare(info, m, got, want)
+        return
+    # a `double` global makes the reference evaluate the expression around it in double; the emitter's
+    # value-numbered sub-results are ::dawn::float_type, so the last place may differ: the stated
+    # single-precision tolerance (1e-5 relative) applies
+    for fd in info["fields"]:
+        n = fd["name"]
+        v = m.valid(LOC[fd["location"]]) if fd["location"] != "none" else None
+        a, b = (got[n], want[n]) if v is None else (np.compress(v, got[n], axis=1 if fd.get("k", 1) else 0),
+                                                   np.compress(v, want[n], axis=1 if fd.get("k", 1) else 0))
+        assert np.allclose(a, b, rtol=1e-5, atol=0.0, equal_nan=True), n

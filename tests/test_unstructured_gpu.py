@@ -379,6 +379,49 @@ def test_icon_laplacian_at_benchmark_scale(nx):
         assert bit_equal(got[:, v], want[fd["name"]][:, v]), fd["name"]
 
 
+@pytest.mark.parametrize("nx,ny,k", [(33, 20, 9), (64, 64, 65)])
+@pytest.mark.parametrize("name", ["ICON_laplacian_stencil", "diffusion", "ICON_laplacian_diamond_stencil"])
+def test_single_precision_unstructured_modules(name, nx, ny, k):
+    """single_precision=1 on the unstructured side: float fields in the reference's device layout, results
+    within 1e-5 relative of (in fact bit-identical to) the naive-ico oracle evaluated on float32 storages
+    (sqrt is correctly rounded on both sides; the diamond stencil uses it)."""
+    import json
+    import torch
+    import dawn_b200
+    m = TriMesh(nx, ny)
+    mod = dawn_b200.load_stencil(name, single_precision=1)
+    assert mod.dtype == "float32"
+    rng = np.random.default_rng(77)
+    f = {n: v.astype(np.float32) for n, v in _random_fields(mod, m, k, rng).items()}
+    w = {n: v.copy() for n, v in f.items()}
+    d = json.load(open(iir_path(name)))["metadata"]
+    for aid in d.get("temporaryFieldIDs", []):
+        chain = d["fieldIDtoDimensions"][str(aid)]["unstructured_horizontal_dimension"]["iter_space"]["chain"]
+        shape = [k, m.num(chain[0])] + ([m.nbh_table(chain).shape[1]] if len(chain) > 1 else [])
+        w.setdefault(d["accessIDToName"][str(aid)], np.zeros(shape, dtype=np.float32))
+    want = naive_interp.run_unstructured(iir_path(name), m, k, w)
+    st = mod.on_mesh(m, k)
+    tens = []
+    for fd in mod.fields:
+        a = f[fd["name"]]
+        if fd["sparse"]:
+            a = np.swapaxes(a, -1, -2)
+        tens.append(torch.from_numpy(np.ascontiguousarray(a)).cuda())
+    st.run(*tens)
+    torch.cuda.synchronize()
+    written = set(mod.info["written"])
+    for fd, t in zip(mod.fields, tens):
+        if fd["name"] not in written:
+            continue
+        got = t.cpu().numpy()
+        got = np.swapaxes(got, -1, -2) if fd["sparse"] else got
+        assert got.dtype == np.float32
+        v = m.valid(LOC[fd["location"]])
+        a, b = got[:, v], want[fd["name"]][:, v]
+        assert np.allclose(a, b, rtol=1e-5, atol=0.0, equal_nan=True), fd["name"]
+        assert bit_equal(a, b), fd["name"]
+
+
 def test_overwriting_a_gathered_field_is_not_fused_into_the_gathering_launch():
     """stencils/overwriteGathered.iir: stage 1 gathers g over C>E>C, stage 2 overwrites g, stage 3 reads
     both results (write-after-read through a chain; seeds 16-19 of the random programs do the same)."""

@@ -1,5 +1,7 @@
 """GPU sweep of planner knobs for one workload: prints kernel ms per variant (kernel-only timing,
-CUDA events, inputs resident).  Usage: python tools/sweep.py hori_diff 'rows_per_thread=1,2' 'max_blocks_per_sm=0,4,5' ..."""
+CUDA events, inputs resident).  Usage: python tools/sweep.py hori_diff 'rows_per_thread=1,2' 'max_blocks_per_sm=0,4,5' ...  (product of the axes)
+       python tools/sweep.py tridiagonal list '' 'ring_levels=4,tma_stages=4' ...  (explicit variants, see
+       tools/precompile.py to build them without a GPU first)"""
 import itertools
 import os
 import sys
@@ -24,9 +26,16 @@ bench.BYTES_PER_POINT.update({"hd_smagorinsky": 72, "hori_diff_02": 16, "lap": 1
 def main():
     workload = sys.argv[1]
     axes = []
-    for a in sys.argv[2:]:
-        k, vs = a.split("=")
-        axes.append([(k, int(v)) for v in vs.split(",")])
+    combos = None
+    if len(sys.argv) > 2 and sys.argv[2] == "list":   # explicit variants: 'k=v,k=v' each ('' = default)
+        combos = [[(kv.split("=")[0], int(kv.split("=")[1])) for kv in spec.split(",") if kv]
+                  for spec in sys.argv[3:]]
+    else:
+        for a in sys.argv[2:]:
+            k, vs = a.split("=")
+            axes.append([(k, int(v)) for v in vs.split(",")])
+    if os.environ.get("SWEEP_SHAPE"):
+        bench.SHAPE[workload] = tuple(int(v) for v in os.environ["SWEEP_SHAPE"].lower().split("x"))
     I, J, K = bench.SHAPE[workload]
     name = bench.STENCIL[workload]
     ni, nj = I + 2 * HALO, J + 2 * HALO
@@ -39,7 +48,7 @@ def main():
         if workload == "tridiagonal":
             s.buf.add_(4.0)
     pts = I * J * K
-    for combo in itertools.product(*axes):
+    for combo in (combos if combos is not None else itertools.product(*axes)):
         opts = {k: v for k, v in combo}
         try:
             mod = dawn_b200.load_stencil(name, **opts)

@@ -7,8 +7,12 @@ import dawn_b200
 from dawn_b200.trimesh import TriMesh
 n = int(sys.argv[1]); K = 65
 axes = []
-for a in sys.argv[2:]:
-    k, vs = a.split("="); axes.append([(k, int(v)) for v in vs.split(",")])
+combos = None
+if len(sys.argv) > 2 and sys.argv[2] == "list":   # explicit variants 'k=v,k=v' ('' = default), cf. tools/precompile.py
+    combos = [[(kv.split("=")[0], int(kv.split("=")[1])) for kv in spec.split(",") if kv] for spec in sys.argv[3:]]
+else:
+    for a in sys.argv[2:]:
+        k, vs = a.split("="); axes.append([(k, int(v)) for v in vs.split(",")])
 mesh = TriMesh(n, n)
 E, C, V = mesh.num_edges, mesh.num_cells, mesh.num_vertices
 nof = {"cells": C, "edges": E, "vertices": V}
@@ -18,7 +22,7 @@ for fd in base.fields:
     shape = (K, fd["sparse"], nof[fd["location"]]) if fd["sparse"] else (K, nof[fd["location"]])
     tens.append(torch.rand(shape, dtype=torch.float64, device="cuda") + 0.5)
 bytes_run = K * (40 * E + 56 * V + 32 * C) + 4 * (6 * V + 3 * C + 4 * E)
-for combo in itertools.product(*axes):
+for combo in (combos if combos is not None else itertools.product(*axes)):
     opts = dict(combo)
     mod = dawn_b200.load_stencil("ICON_laplacian_stencil", **opts)
     st = mod.on_mesh(mesh, K)
