@@ -109,14 +109,16 @@ def test_single_precision_modules(name, I, J, K):
     (37 x 19: rows that are not 16-byte multiples of floats - the plain kernels run.)"""
     import torch
     import dawn_b200
-    f = {"hori_diff_type2_stencil": hori_diff_type2_inputs, "tridiagonal_solve": tridiagonal_inputs,
-         "hori_diff_stencil_02": lambda i, j, k: {"in": np.random.default_rng(5).uniform(0.5, 1.5, (k + 1, j + 6, i + 6)),
-                                                   "out": np.full((k + 1, j + 6, i + 6), -1.0)}}[name](I, J, K)
+    mod = dawn_b200.load_stencil(name, single_precision=1)
+    assert mod.dtype == "float32"
+    if name == "hori_diff_stencil_02":
+        rng = np.random.default_rng(5)
+        f = {fd["name"]: rng.uniform(0.5, 1.5, (K + 1, J + 2 * HALO, I + 2 * HALO)) for fd in mod.fields}
+    else:
+        f = (hori_diff_type2_inputs if name == "hori_diff_type2_stencil" else tridiagonal_inputs)(I, J, K)
     f32 = {n: v.astype(np.float32) for n, v in f.items()}
     dom_dims = (I + 2 * HALO, J + 2 * HALO, K)
     want = run_oracle(name, dom_dims, f32)
-    mod = dawn_b200.load_stencil(name, single_precision=1)
-    assert mod.dtype == "float32"
     dom = dawn_b200.Domain(*dom_dims)
     dom.set_halos(HALO, HALO, HALO, HALO, 0, 0)
     st = mod(dom)
