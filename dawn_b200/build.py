@@ -121,7 +121,8 @@ VARIANTS = {
     **{"fuzz_%02d" % n: [dict(use_tma=0, inline_temporaries=0)] for n in range(16)},
     "tridiagonal_solve": [dict(ring_early=0), dict(ring_stagger=-1), dict(ring_drain=0), dict(ring_drain=1, tma_stages=2), dict(ring_drain=1, tma_stages=4),
                           dict(ring_drain=1, ring_levels=4, tma_stages=4), dict(fuse_columns=0), dict(column_ring=0), dict(column_ring=0, column_cache=1, prefetch_k=3),
-                          dict(ring_levels=2, tma_stages=2), dict(block_size_i=32, block_size_j=2)],
+                          dict(ring_levels=2, tma_stages=2), dict(block_size_i=32, block_size_j=2),
+                          dict(ring_producer=1), dict(ring_producer=1, ring_levels=4, tma_stages=3, block_size_i=32)],
 }
 
 

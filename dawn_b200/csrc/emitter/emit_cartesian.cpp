@@ -111,6 +111,10 @@ struct KernelPlan {
   // --- column-ring variant: the centre reads of sequential sweeps arrive through a TMA ring of
   // (TI x TJ x ringKB)-level boxes; later sweeps re-read what earlier ones wrote from L2
   bool colring = false;
+  // a dedicated producer warp (threads NT..NT+31, one elected lane) issues the ring's TMA loads: consumers
+  // wait on a slot's `full` barrier, drain it into registers and hand it back through its `empty` barrier
+  bool producer = false;
+  int ringHeaderBytes() const { return producer ? 256 : 128; }
   int ringKB = 4;
   std::vector<int> ringFields; // every field that may be streamed (tensor-map kernel args)
   int ringMaxFields = 0;       // largest number of fields streamed by one k range
@@ -550,6 +554,10 @@ bool CartesianEmitter::planColumnRing(KernelPlan& kp) const {
   kp.stages = opt_.TmaStages > 0 ? opt_.TmaStages : (opt_.RingDrain ? 4 : 3);
   kp.TI = opt_.BlockSizeI > 0 ? opt_.BlockSizeI : 64;
   kp.TJ = opt_.BlockSizeJ > 0 ? opt_.BlockSizeJ : 1;
+  // the producer warp needs the drain order (a slot is free as soon as it has been copied to registers),
+  // full warps of consumers and at most 8 slots (barrier words in the 256-byte header)
+  kp.producer = opt_.RingProducer != 0 && opt_.RingDrain != 0 && opt_.RingStagger == 0 && kp.stages <= 8 &&
+                (kp.TI * kp.TJ) % 32 == 0;
   if((kp.TI * kp.ftBytes) % 16 != 0 || kp.TI > 256 || kp.TJ > 256 || kp.ringKB > 256)
     return false;
   return true;
@@ -1525,7 +1533,7 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
   os_ << "// kernel " << kp.name << ": " << (kp.pointwise ? "column" : "tile") << " kernel over "
       << kp.ms.size() << " multistage(s), block " << kp.TI << "x" << kp.TJ << " threads, "
       << kp.RJ << " row(s)/thread" << (kp.zchunk ? ", k split over blockIdx.z" : "") << "\n";
-  os_ << "__global__ void __launch_bounds__(" << kp.NT()
+  os_ << "__global__ void __launch_bounds__(" << kp.NT() + (kp.producer ? 32 : 0)
       << (opt_.MaxBlocksPerSM > 0 ? ", " + std::to_string(opt_.MaxBlocksPerSM) : std::string()) << ")\n"
       << kp.name << "(";
   if(kp.usesGlobals)
@@ -1577,13 +1585,23 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
   if(kp.tma || kp.colring) {
     os_ << "  extern __shared__ __align__(128) unsigned char b200_smem[];\n";
     os_ << "  unsigned long long* tma_full = reinterpret_cast<unsigned long long*>(b200_smem);\n";
-    os_ << "  ::dawn::float_type* tma_ring = reinterpret_cast<::dawn::float_type*>(b200_smem + 128);\n";
+    if(kp.producer) {
+      os_ << "  unsigned long long* tma_empty = tma_full + 8;  // slot handed back by every consumer warp\n";
+      os_ << "  unsigned long long* sweep_done = tma_full + 16; // consumers' stores of a sweep are fenced\n";
+    }
+    os_ << "  ::dawn::float_type* tma_ring = reinterpret_cast<::dawn::float_type*>(b200_smem + "
+        << (kp.colring ? kp.ringHeaderBytes() : 128) << ");\n";
     if(!kp.cached.empty())
       os_ << "  ::dawn::float_type* ij_cache = tma_ring + " << (size_t)kp.stages * kp.stageElems
           << "; // two buffers of " << kp.cacheElems << " doubles\n";
     os_ << "  if(tid == 0) {\n";
     os_ << "    for(int s = 0; s < " << kp.stages << "; ++s)\n"
         << "      ::dawn_b200::tma::barrier_init(&tma_full[s], 1);\n";
+    if(kp.producer) {
+      os_ << "    for(int s = 0; s < " << kp.stages << "; ++s)\n"
+          << "      ::dawn_b200::tma::barrier_init(&tma_empty[s], " << kp.NT() / 32 << ");\n";
+      os_ << "    ::dawn_b200::tma::barrier_init(sweep_done, " << kp.NT() / 32 << ");\n";
+    }
     os_ << "    ::dawn_b200::tma::fence_barrier_init();\n";
     if(stagger) {
       // ring_stagger: the blocks of the first wave start their sweeps out of phase.  Left alone they
@@ -1647,6 +1665,7 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
   }
   std::set<int> producedSoFar;
   std::set<int> writtenSoFar; // fields stored by earlier multistages of this kernel
+  std::ostringstream prod;    // program of the producer warp's elected lane (kp.producer)
 
   // Tile kernels whose live stages all run on the plain tile (no redundant halo computation): the
   // thread -> point map is the same for every stage and level, so it is set up once and loads that
@@ -1725,39 +1744,68 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
       for(auto const& part : parts)
         for(int f : streamedFields(kp, *ms, part, msDepths))
           needFence = needFence || writtenSoFar.count(f);
-      if(needFence)
+      if(needFence && !kp.producer)
         os_ << "    // this sweep streams (async proxy) what an earlier sweep stored (generic proxy)\n"
             << "    __threadfence_block();\n    ::dawn_b200::tma::fence_proxy_async();\n"
             << "    __syncthreads();\n";
+      if(needFence && kp.producer) {
+        os_ << "    // this sweep streams (async proxy) what an earlier sweep stored (generic proxy): every\n"
+            << "    // consumer fences its stores, each warp tells the producer\n"
+            << "    __threadfence_block();\n    ::dawn_b200::tma::fence_proxy_async();\n"
+            << "    __syncwarp();\n    if((tid & 31) == 0)\n      ::dawn_b200::tma::arrive(sweep_done);\n";
+        prod << "      // the next sweep streams what the consumers stored: wait until every warp has fenced\n"
+             << "      ::dawn_b200::tma::wait(sweep_done, sweep_it & 1u);\n      ++sweep_it;\n"
+             << "      ::dawn_b200::tma::fence_proxy_async();\n";
+      }
     }
-    auto emitRangeBounds = [&](const KRange& part) {
-      os_ << "      int kb = " << analysis::boundExpr(part.lo)
-          << ", ke = " << analysis::boundExpr(part.hi) << ";\n";
-      os_ << "      kb = kb < 0 ? 0 : kb; ke = ke > kmax ? kmax : ke;\n";
+    auto emitRangeBoundsTo = [&](std::ostream& o, const KRange& part) {
+      o << "      int kb = " << analysis::boundExpr(part.lo)
+        << ", ke = " << analysis::boundExpr(part.hi) << ";\n";
+      o << "      kb = kb < 0 ? 0 : kb; ke = ke > kmax ? kmax : ke;\n";
       if(kp.zchunk) {
-        os_ << "      { const int zb = blockIdx.z * kchunk; kb = kb > zb ? kb : zb; "
-               "ke = ke < zb + kchunk - 1 ? ke : zb + kchunk - 1; }\n";
+        o << "      { const int zb = blockIdx.z * kchunk; kb = kb > zb ? kb : zb; "
+             "ke = ke < zb + kchunk - 1 ? ke : zb + kchunk - 1; }\n";
       }
     };
+    auto emitRangeBounds = [&](const KRange& part) { emitRangeBoundsTo(os_, part); };
     // TMA prologue of one streamed k range: the first `ahead` chunks of `fields`
-    auto emitRingIssue = [&](const std::set<int>& fields, const std::string& pad,
-                             const std::string& chunk) {
+    auto emitRingIssueTo = [&](std::ostream& o, const std::set<int>& fields, const std::string& pad,
+                               const std::string& chunk) {
       const int KB = kp.ringKB, S = kp.stages, NT = kp.NT();
       const size_t bytes = fields.size() * (size_t)KB * NT * kp.ftBytes;
-      os_ << pad << "{\n";
-      os_ << pad << "  const unsigned ts = (tma_it + " << chunk << ") % " << S << ";\n";
-      os_ << pad << "  const int k0 = "
-          << (backward ? "ke - (" + chunk + ") * " + std::to_string(KB) + " - " + std::to_string(KB - 1)
-                       : "kb + (" + chunk + ") * " + std::to_string(KB))
-          << ";\n";
-      os_ << pad << "  ::dawn_b200::tma::expect_bytes(&tma_full[ts], " << bytes << "u);\n";
+      o << pad << "{\n";
+      o << pad << "  const unsigned ts = (tma_it + " << chunk << ") % " << S << ";\n";
+      o << pad << "  const int k0 = "
+        << (backward ? "ke - (" + chunk + ") * " + std::to_string(KB) + " - " + std::to_string(KB - 1)
+                     : "kb + (" + chunk + ") * " + std::to_string(KB))
+        << ";\n";
+      o << pad << "  ::dawn_b200::tma::expect_bytes(&tma_full[ts], " << bytes << "u);\n";
       int fi = 0;
       for(int f : fields) {
-        os_ << pad << "  ::dawn_b200::tma::load_3d(tma_ring + ts * " << ringSlotElems << " + "
-            << fi * KB * NT << ", &tm_" << fname(f) << ", i0, j0, k0, &tma_full[ts]);\n";
+        o << pad << "  ::dawn_b200::tma::load_3d(tma_ring + ts * " << ringSlotElems << " + "
+          << fi * KB * NT << ", &tm_" << fname(f) << ", i0, j0, k0, &tma_full[ts]);\n";
         ++fi;
       }
-      os_ << pad << "}\n";
+      o << pad << "}\n";
+    };
+    auto emitRingIssue = [&](const std::set<int>& fields, const std::string& pad,
+                             const std::string& chunk) { emitRingIssueTo(os_, fields, pad, chunk); };
+    // producer warp: all chunks of one streamed k range, each behind the `empty` barrier of its slot
+    auto emitProducerRange = [&](const KRange& part, const std::set<int>& fields) {
+      const int KB = kp.ringKB, S = kp.stages;
+      prod << "      { // k in [" << analysis::boundExpr(part.lo) << ", " << analysis::boundExpr(part.hi)
+           << "]" << (backward ? ", downwards" : "") << "\n";
+      emitRangeBoundsTo(prod, part);
+      prod << "      const int nk_loc = ke - kb + 1;\n";
+      prod << "      const int nch = nk_loc > 0 ? (nk_loc + " << KB - 1 << ") / " << KB << " : 0;\n";
+      prod << "      for(int ch = 0; ch < nch; ++ch) {\n";
+      prod << "        const unsigned use = (tma_it + ch) / " << S << "; // n-th use of this slot\n";
+      prod << "        if(use > 0)\n          ::dawn_b200::tma::wait(&tma_empty[(tma_it + ch) % " << S
+           << "], (use - 1) & 1u);\n";
+      emitRingIssueTo(prod, fields, "        ", "ch");
+      prod << "      }\n";
+      prod << "      tma_it += (unsigned)nch;\n";
+      prod << "      }\n";
     };
     auto emitRingPrologue = [&](const std::set<int>& fields) {
       const int ahead = opt_.RingDrain != 0 ? kp.stages : kp.stages - 1;
@@ -1775,7 +1823,7 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
     // partition are disjoint in k, fields are only ever written at the centre level, and ring chunks
     // that reach past their range only overlap ranges that run later (values never used).
     int earlyPart = -1;
-    if(kp.colring && opt_.RingEarly && ms == kp.ms.front() && writtenSoFar.empty()) {
+    if(kp.colring && !kp.producer && opt_.RingEarly && ms == kp.ms.front() && writtenSoFar.empty()) {
       for(size_t p = 0; p < parts.size(); ++p)
         if(!streamedFields(kp, *ms, parts[p], msDepths).empty()) {
           if(p > 0)
@@ -1950,7 +1998,11 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         // 8-level sweep and at most S-1 are in flight: ncu showed 24 % of the warp samples waiting on
         // the full-barrier)
         const bool drain = opt_.RingDrain != 0;
-        if(partIdx == earlyPart) {
+        if(kp.producer) {
+          os_ << "      const int nk_loc = ke - kb + 1; // the producer warp streams this range\n";
+          os_ << "      const int nch = nk_loc > 0 ? (nk_loc + " << KB - 1 << ") / " << KB << " : 0;\n";
+          emitProducerRange(part, be.prefetched);
+        } else if(partIdx == earlyPart) {
           os_ << "      const int nk_loc = ke - kb + 1; // prologue already issued at the top of the sweep\n";
           os_ << "      const int nch = nk_loc > 0 ? (nk_loc + " << KB - 1 << ") / " << KB << " : 0;\n";
         } else {
@@ -1973,9 +2025,14 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
             os_ << "          rv_" << fname(f) << "[q] = slot[(" << fi * KB << " + q) * " << NT << " + tid];\n";
             ++fi;
           }
-          os_ << "        __syncthreads(); // slot drained by every thread: refill it right away\n";
-          os_ << "        if(tid == 0 && ch + " << S << " < nch)\n";
-          issue("          ", "ch + " + std::to_string(S));
+          if(kp.producer) {
+            os_ << "        __syncwarp(); // slot drained by this warp: hand it back to the producer\n";
+            os_ << "        if((tid & 31) == 0)\n          ::dawn_b200::tma::arrive(&tma_empty[tcur]);\n";
+          } else {
+            os_ << "        __syncthreads(); // slot drained by every thread: refill it right away\n";
+            os_ << "        if(tid == 0 && ch + " << S << " < nch)\n";
+            issue("          ", "ch + " + std::to_string(S));
+          }
         }
         os_ << "#pragma unroll\n";
         os_ << "      for(int q = 0; q < " << KB << "; ++q) {\n";
@@ -2243,6 +2300,15 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
     const std::string body = os_.str();
     os_.str("");
     os_ << kernelHead;
+    if(kp.producer) {
+      if(body.find("__syncthreads") != std::string::npos)
+        throw std::runtime_error("b200: internal error, block-wide barrier in a producer/consumer column kernel");
+      os_ << "  if(tid >= " << kp.NT() << ") { // producer warp: one elected lane feeds the ring\n";
+      os_ << "    if(tid == " << kp.NT() << ") {\n";
+      os_ << "      unsigned sweep_it = 0; (void)sweep_it;\n";
+      os_ << prod.str();
+      os_ << "    }\n    return;\n  }\n";
+    }
     for(auto const& l : be.invariantLoads)
       os_ << "  " << be.finalize(l) << "\n";
     os_ << body;
@@ -2429,7 +2495,7 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
           << (kp.zchunk ? "(nz + kchunk - 1) / kchunk" : "1") << ");\n";
       size_t smem = kp.tma ? kp.tmaSmemBytes() : 0;
       if(kp.colring)
-        smem = 128 + (size_t)kp.stages * kp.ringMaxFields * kp.ringKB * kp.NT() * kp.ftBytes;
+        smem = kp.ringHeaderBytes() + (size_t)kp.stages * kp.ringMaxFields * kp.ringKB * kp.NT() * kp.ftBytes;
       if(kp.tma || kp.colring) {
         // function attributes are per device: a host that drives several GPUs from one process sets
         // them once on each
@@ -2467,7 +2533,7 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
         }
         os_ << pad << "const int stagger_cycles = (int)((long long)stagger_ns * stagger_mhz / 1000);\n";
       }
-      os_ << pad << kp.name << "<<<grid, " << kp.NT() << ", "
+      os_ << pad << kp.name << "<<<grid, " << kp.NT() + (kp.producer ? 32 : 0) << ", "
           << (smemExpr.empty() ? std::to_string(smem) : smemExpr) << ", stream>>>(";
       if(kp.usesGlobals)
         os_ << "m_globals, ";

@@ -26,6 +26,11 @@ __device__ __forceinline__ void expect_bytes(unsigned long long* bar, unsigned b
                                        cuda::ptx::space_shared, reinterpret_cast<uint64_t*>(bar),
                                        bytes);
 }
+// plain arrival (release at CTA scope): consumers hand a drained ring slot back to the producer warp
+__device__ __forceinline__ void arrive(unsigned long long* bar) {
+  (void)cuda::ptx::mbarrier_arrive(cuda::ptx::sem_release, cuda::ptx::scope_cta, cuda::ptx::space_shared,
+                                   reinterpret_cast<uint64_t*>(bar));
+}
 __device__ __forceinline__ void load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
                                         int c2, unsigned long long* bar) {
   const int32_t coords[3] = {c0, c1, c2};

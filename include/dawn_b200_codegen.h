@@ -69,6 +69,11 @@ typedef struct dawn_b200_options {
                              backward (L2-fed) sweeps interleave; -1: N from $DAWN_B200_STAGGER_NS (probing) */
   int ico_full_blocks;    /* default 0: unstructured kernels run full blocks of levels through an unrolled
                              loop without per-level bound checks (more loads in flight per thread) */
+  int ring_producer;      /* default 0; 1: column-ring kernels get a dedicated producer warp that issues the TMA loads
+                             (full / empty mbarriers per slot, no block-wide barrier in the sweeps) instead of
+                             thread 0 between __syncthreads().  Measured on B200 (tridiagonal_solve): the lone-block
+                             latency drops from 18.0 to 16.0 us, but full waves get slower (1024^2 x 80: 87.4 %
+                             against 90.7 % of the HBM peak), so it stays off */
   int single_precision;   /* default 0: ::dawn::float_type is double; 1: the translation unit is generated for
                              float (the reference selects the type when the generated code is COMPILED,
                              driver-includes/defs.hpp:47-81; here the TMA box geometry and the shared-memory

@@ -175,7 +175,8 @@ def test_tridiagonal_solve(I, J, K):
 @pytest.mark.parametrize("opts", [dict(fuse_columns=0), dict(column_ring=0), dict(ring_early=0),
                                   dict(column_ring=0, column_cache=1, prefetch_k=3),
                                   dict(ring_levels=2, tma_stages=2),
-                                  dict(block_size_i=32, block_size_j=2)])
+                                  dict(block_size_i=32, block_size_j=2), dict(ring_producer=1),
+                                  dict(ring_producer=1, ring_levels=4, tma_stages=3, block_size_i=32)])
 @pytest.mark.parametrize("K", [1, 2, 12, 37])
 def test_tridiagonal_planner_variants(opts, K):
     I, J = 40, 33
