@@ -586,6 +586,15 @@ def run_icon(args):
             raise SystemExit("--icon-reorder is a 1-GPU option: the slab halo plan needs row-contiguous ids")
         from dawn_b200 import reorder as ro
         mesh = ro.reorder(mesh, args.icon_reorder)
+    part = None
+    if args.icon_partition != "none" and world > 1:
+        # general partition (dawn_b200/partition.py) of the renumbered GLOBAL mesh instead of row slabs: cells
+        # owned in contiguous id ranges, edges / vertices by the lowest-owner rule, one ring of halo cells,
+        # splitter indices [Interior, Halo) = owned; `vec` halo copies refreshed point to point every step
+        from dawn_b200 import partition as pt, reorder as ro
+        gm = ro.reorder(TriMesh(nx, ny * world), args.icon_partition)
+        part = pt.partition(gm, world)[rank]
+        mesh = part.mesh
     nabla4 = args.workload == "icon_nabla4"
     diamond = args.workload == "icon_diamond"
     stencil_name = {"icon_nabla4": "ICON_nabla4_stencil", "icon_diamond": "ICON_laplacian_diamond_stencil"}.get(
@@ -596,7 +605,7 @@ def run_icon(args):
         # exchange (of nabla2_vec) between its passes, the diamond stencil one of u_vert / v_vert
         raise SystemExit("%s is a 1-GPU bench line; use icon_nabla2 for the multi-GPU runs" % args.workload)
     mod = dawn_b200.load_stencil(stencil_name)
-    st = mod.on_mesh(mesh, K)
+    st = mod.on_mesh(mesh, K, splitters=None if part is None else part.splitters())
     t_mesh = time.perf_counter() - t0
     E, C, V = mesh.num_edges, mesh.num_cells, mesh.num_vertices
     n_of = {"cells": C, "edges": E, "vertices": V}
@@ -611,7 +620,7 @@ def run_icon(args):
     torch.cuda.synchronize()
     plan = comm = None
     stream = torch.cuda.current_stream().cuda_stream
-    if world > 1:
+    if world > 1 and part is None:
         import ctypes
         idbuf = (ctypes.c_char * 128)()
         if rank == 0:
@@ -630,6 +639,8 @@ def run_icon(args):
     def step():
         if plan is not None:
             rt.check(rt.lib().b200rt_halo_exchange(plan, vec.data_ptr(), stream))
+        if part is not None:
+            part.exchange(1, vec, dist)       # 1 = EDGE: gather at the owners, NCCL send / recv, scatter
         st.run(*tens)
 
     def barrier():
@@ -673,6 +684,8 @@ def run_icon(args):
                 vec[:, :per * sl.halo_lo] = float("nan")
             if sl.halo_hi:
                 vec[:, E - per * sl.halo_hi:] = float("nan")
+        if part is not None:
+            vec[:, part.n_owned[1]:] = float("nan")   # every halo copy of an edge
         step()
         torch.cuda.synchronize()
         written = set(mod.info.get("written", []))
@@ -685,10 +698,15 @@ def run_icon(args):
             if fd["name"] not in got:
                 continue
             v = mesh.valid(loc_of[fd["location"]])
+            if part is not None:   # owned elements: complete neighbourhoods, the values that count
+                v = v & (np.arange(v.shape[0]) < part.n_owned[loc_of[fd["location"]]])
             g, w = got[fd["name"]][:, v], want[fd["name"]][:, v]
             ndiff += int((g.view(np.int64) != w.view(np.int64)).sum())
             nvals += g.size
         nan_in_vec = 0 if vec is None else int(torch.isnan(vec).sum().item())
+        if part is not None:   # halo slots nobody owns (invalid edge slots) are never refreshed
+            ev = torch.as_tensor(mesh.valid(1), device="cuda")
+            nan_in_vec = int(torch.isnan(vec[:, ev]).sum().item())
         parity = {"checked": "%s on levels %s of %d, all valid elements%s" % (
                       sorted(got), levels, K, "" if plan is None else
                       "; halo rows of `vec` poisoned with NaN before the exchange"),
@@ -704,6 +722,11 @@ def run_icon(args):
     # work and bytes of the OWNED rows of one rank (halo rows are redundant work)
     own = TriMesh(nx, ny)
     E, C, V = own.num_edges, own.num_cells, own.num_vertices
+    if part is not None:
+        E, C, V = part.n_owned[1], part.n_owned[0], part.n_owned[2]
+        cnt = torch.tensor([E, C, V], device="cuda", dtype=torch.float64)
+        dist.all_reduce(cnt)                       # whole-job totals over the parts
+        E, C, V = (int(x) // world for x in cnt.tolist())
     units = E * K * world
     bytes_run = passes * (K * (40 * E + 56 * V + 32 * C) + 4 * (6 * V + 3 * C + 2 * E + 2 * E))
     if diamond:
@@ -725,6 +748,11 @@ def run_icon(args):
                                    "dawn4py-tests/ICON_laplacian_diamond_stencil.py)" if diamond else
                                    "ICON_laplacian_stencil (nabla2)",
                                    nx, ny, E, C, V, K, "" if world == 1 else
+                                   "; global mesh %dx%d, %s numbering, cut into %d parts of contiguous cell "
+                                   "ranges (dawn_b200/partition.py: lowest-owner edges / vertices, one halo "
+                                   "ring, splitter indices), `vec` halo copies refreshed point to point over "
+                                   "NCCL every step; counts are per-part averages of OWNED elements" % (
+                                       nx, ny * world, args.icon_partition, world) if part is not None else
                                    "; global mesh %dx%d in %d row slabs, 1 halo quad row, NCCL exchange "
                                    "of `vec` every step" % (nx, ny * world, world)),
                    "l2": "inputs larger than L2 (%.1f GB per step), no flush" % (bytes_run / 1e9),
@@ -951,6 +979,8 @@ def main():
                          "31 edge fields x 65 levels fill 110 GB)")
     ap.add_argument("--icon-reorder", default="none", choices=["none", "rcm", "morton"],
                     help="renumber the ICON mesh before the run (none = toylib's structured numbering)")
+    ap.add_argument("--icon-partition", default="none", choices=["none", "rcm", "morton"],
+                    help="multi-GPU ICON lines: general partition of the renumbered global mesh instead of row slabs")
     ap.add_argument("--opt", action="append", default=[], help="codegen option key=value (sweeps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="ICON lines: skip the host-buffer leg")

@@ -82,10 +82,18 @@ class Part:
         loc = NAMES[loc]
         ops, landing = [], []
         dev = tensor.device
+        cache = self.__dict__.setdefault("_dev_ids", {})   # index lists live on the device after the first call
+
+        def on_dev(kind, peer, ids):
+            key = (kind, loc, peer, str(dev))
+            if key not in cache:
+                cache[key] = torch.as_tensor(ids, device=dev)
+            return cache[key]
+
         for p in self.peers():
             ids = self.send.get(loc, {}).get(p)
             if ids is not None and len(ids):
-                buf = tensor.index_select(axis, torch.as_tensor(ids, device=dev)).contiguous()
+                buf = tensor.index_select(axis, on_dev("send", p, ids)).contiguous()
                 ops.append(dist.P2POp(dist.isend, buf, p))
             ids = self.recv.get(loc, {}).get(p)
             if ids is not None and len(ids):
@@ -93,12 +101,12 @@ class Part:
                 shape[axis] = len(ids)
                 buf = torch.empty(shape, dtype=tensor.dtype, device=dev)
                 ops.append(dist.P2POp(dist.irecv, buf, p))
-                landing.append((ids, buf))
+                landing.append((on_dev("recv", p, ids), buf))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
         for ids, buf in landing:
-            tensor.index_copy_(axis, torch.as_tensor(ids, device=dev), buf)
+            tensor.index_copy_(axis, ids, buf)
         return tensor
 
 
