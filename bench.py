@@ -682,8 +682,8 @@ def run_icon(args):
             per = sl.slots_per_row(1)
             if sl.halo_lo:
                 vec[:, :per * sl.halo_lo] = float("nan")
-            if sl.halo_hi:
-                vec[:, E - per * sl.halo_hi:] = float("nan")
+            if sl.halo_hi:   # the slot rows of the upper halo quad row (one more row of slots follows them)
+                vec[:, per * (sl.halo_lo + sl.nrows):per * (sl.halo_lo + sl.nrows + sl.halo_hi)] = float("nan")
         if part is not None:
             vec[:, part.n_owned[1]:] = float("nan")   # every halo copy of an edge
         step()
@@ -708,8 +708,10 @@ def run_icon(args):
             ev = torch.as_tensor(mesh.valid(1), device="cuda")
             nan_in_vec = int(torch.isnan(vec[:, ev]).sum().item())
         parity = {"checked": "%s on levels %s of %d, all valid elements%s" % (
-                      sorted(got), levels, K, "" if plan is None else
-                      "; halo rows of `vec` poisoned with NaN before the exchange"),
+                      sorted(got), levels, K,
+                      "; halo rows of `vec` poisoned with NaN before the exchange" if plan is not None else
+                      " this part owns; every halo copy of `vec` poisoned with NaN before the refresh"
+                      if part is not None else ""),
                   "values_compared": nvals, "differing_values": ndiff + nan_in_vec,
                   "max_abs_diff": 0.0 if ndiff + nan_in_vec == 0 else float("nan"),
                   "oracle": "oracle/naive_interp.py (pinned against the reference's generated naive-ico text)"}

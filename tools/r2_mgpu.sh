@@ -21,5 +21,6 @@ PY
 run hd_default --steps 50
 J=$((4096 / N))
 run hd_c5 --steps 20 --shape 4096x${J}x80
-run icon_slabs --workload icon_nabla2 --steps 10 --icon-n 1024
-run icon_partition --workload icon_nabla2 --steps 10 --icon-n 1024 --icon-partition rcm
+IN=${2:-1024}   # TriMesh nx = ny per GPU (the global mesh is built, renumbered and cut on every rank)
+run icon_slabs --workload icon_nabla2 --steps 10 --icon-n $IN
+run icon_partition --workload icon_nabla2 --steps 10 --icon-n $IN --icon-partition rcm
