@@ -313,8 +313,13 @@ def run_gpu(args):
                 rt.check(rt.lib().b200rt_halo_exchange(plan, s.buf.data_ptr() + 8 * s.lead,
                                                        comm_stream.cuda_stream))
                 n += (2 if rank > 0 else 0) + (2 if rank + 1 < world else 0)
-        lo = dep_lo if rank > 0 else 0
-        hi = J - (dep_hi if rank + 1 < world else 0)
+        # the strips are whole tiles of the kernel (module info "tile"): a 2-row strip would still occupy - and
+        # load the inputs of - a full 12-row tile, work the interior launch then repeats
+        tile_j = (mod.info.get("tile") or [0, 0])[1]
+        lo = max(dep_lo, tile_j) if rank > 0 else 0
+        hi = J - (max(dep_hi, tile_j) if rank + 1 < world else 0)
+        if hi - lo < tile_j:
+            lo, hi = (dep_lo if rank > 0 else 0), J - (dep_hi if rank + 1 < world else 0)
         # boundary strips follow the exchange on the (high-priority) communication stream ...
         if lo > 0:
             st.run(*fields, rows=(0, lo), stream=comm_stream.cuda_stream)
@@ -475,6 +480,9 @@ def run_gpu(args):
                 # reported beside the CPU baseline, not a target either: what the reference's CUDA backend
                 # output does on this GPU when it is merely recompiled
                 line["reference_cuda_kernel"] = refcuda_baseline(workload)
+                if workload == "hori_diff" and "ms_per_run" in line["reference_cuda_kernel"]:
+                    # like for like: the b200 backend on the SAME stencil the reference text implements
+                    line["reference_cuda_kernel"]["b200_same_stencil"] = same_stencil_as_reference_text()
         if world == 1 and workload == "hori_diff" and not args.shape and not args.opt and not args.no_sub_workloads:
             # the other two configurations the target names (BASELINE.json configs[2], [3]): measured in
             # the same run, each in its own process with its own roofline / clocks / cpu_baseline / e2e
@@ -903,6 +911,40 @@ def refcuda_child(workload):
                     "dawn4py-tests/data/tridiagonal_solve_stencil_ref.cpp (two kernels, 32x1 blocks, "
                     "register K-caches)")
                  + "; %dx%dx%d, kernel time from its own timer_cuda events" % (I, J, K))}))
+
+
+def same_stencil_as_reference_text():
+    """The b200 module generated from stencils/hori_diff_stencil.iir - the dawn4py hori_diff (in, out, coeff)
+    whose pre-generated CUDA text `reference_cuda_kernel` times - on the same shape, same storages layout,
+    kernel-only timing with CUDA events."""
+    import torch
+    import dawn_b200
+    I, J, K = SHAPE["hori_diff"]
+    ni, nj = I + 2 * HALO, J + 2 * HALO
+    mod = dawn_b200.load_stencil("hori_diff_stencil")
+    dom = dawn_b200.Domain(ni, nj, K)
+    dom.set_halos(HALO, HALO, HALO, HALO, 0, 0)
+    st = mod(dom)
+    stor = [dawn_b200.Storage(ni, nj, K + 1, fd["dims"]) for fd in mod.fields]
+    for s_ in stor:
+        s_.buf.uniform_(0.5, 1.5)
+    for _ in range(5):
+        st.run(*stor)
+    torch.cuda.synchronize()
+    reps = 50
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        st.run(*stor)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    peak, _ = measured_peak()
+    gbs = 24 * I * J * K / (ms * 1e-3) / 1e9
+    return {"ms_per_run": ms, "reps": reps, "achieved_gbs": gbs, "frac_of_peak": gbs / peak,
+            "stencil": "hori_diff_stencil (dawn4py-tests/hori_diff_stencil.py: in, out, coeff), fields %s, 24 "
+                       "algorithmic B/point, %dx%dx%d; bit-identical results: tests/test_reference_cuda_texts_gpu.py"
+                       % ([fd["name"] for fd in mod.fields], I, J, K)}
 
 
 def refcuda_baseline(workload):

@@ -160,6 +160,7 @@ class CartesianEmitter {
   std::set<int> scratch_;            // temporaries backed by global scratch
   std::set<int> droppedStages_;      // stage ids fully absorbed by inlining
   std::set<int> writtenFields_;      // storage fields written by any kernel
+  int tileI_ = 0, tileJ_ = 0;        // points per block of the first tile kernel (module info "tile")
 
 public:
   CartesianEmitter(const Instantiation& inst, const Options& opt) : inst_(inst), opt_(opt) {}
@@ -2346,6 +2347,8 @@ std::string CartesianEmitter::generate() {
     planTemporaries(st);
     plans.push_back(planKernels(st));
     for(auto const& kp : plans.back()) {
+      if(!kp.pointwise && tileJ_ == 0)
+        tileI_ = kp.TI, tileJ_ = kp.tileJ();
       emitKernel(st, kp);
       writtenFields_.insert(kp.fieldsWritten.begin(), kp.fieldsWritten.end());
     }
@@ -2962,7 +2965,10 @@ void CartesianEmitter::emitCAbi() {
           }
         }
       }
-    os_ << "], \\\"k_parallel\\\": " << (kParallel ? "true" : "false") << ", \\\"globals\\\": [";
+    // "tile": points per block of the tile kernels (i, j); a driver that splits a run by rows (run_rows_<N>)
+    // wastes nothing when its pieces are whole tiles
+    os_ << "], \\\"k_parallel\\\": " << (kParallel ? "true" : "false") << ", \\\"tile\\\": [" << tileI_ << ", "
+        << tileJ_ << "], \\\"globals\\\": [";
   }
   for(size_t g = 0; g < inst_.globals.size(); ++g)
     os_ << (g ? ", " : "") << "\\\"" << inst_.globals[g].first << "\\\"";

@@ -52,9 +52,11 @@ void last_launch_NAME(void* handle, int* out5);
 void set_NAME_G(void* handle, double value);
 double get_NAME_G(void* handle);
 
-/* JSON description: {"name", "grid", "fields":[{"name","dims","extent":[i-,i+,j-,j+,k-,k+]}],
- * "written":[...], "globals":[...]} — field order is the run() order; `extent` equals the
- * reference's `static constexpr cartesian_extent <field>_extent` (CodeGen.cpp:509-522). */
+/* JSON description: {"name", "grid", "float_type": "double"|"float", "fields":[{"name","dims",
+ * "extent":[i-,i+,j-,j+,k-,k+]}], "written":[...], "k_parallel": bool, "tile": [points per block in i, j],
+ * "globals":[...]} — field order is the run() order; `extent` equals the reference's `static constexpr
+ * cartesian_extent <field>_extent` (CodeGen.cpp:509-522); `tile` lets a driver that splits a run by rows
+ * (run_rows_NAME) cut along whole tiles. */
 const char* b200_module_info_NAME(void);
 
 #ifdef __cplusplus
