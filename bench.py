@@ -612,7 +612,11 @@ def run_icon(args):
         # the slab plan below keeps one halo quad row and exchanges `vec` only; nabla4 would need a second
         # exchange (of nabla2_vec) between its passes, the diamond stencil one of u_vert / v_vert
         raise SystemExit("%s is a 1-GPU bench line; use icon_nabla2 for the multi-GPU runs" % args.workload)
-    mod = dawn_b200.load_stencil(stencil_name)
+    opts = {}
+    for kv in args.opt:
+        k_, v_ = kv.split("=")
+        opts[k_] = int(v_)
+    mod = dawn_b200.load_stencil(stencil_name, **opts)
     st = mod.on_mesh(mesh, K, splitters=None if part is None else part.splitters())
     t_mesh = time.perf_counter() - t0
     E, C, V = mesh.num_edges, mesh.num_cells, mesh.num_vertices
@@ -766,7 +770,7 @@ def run_icon(args):
                                    "; global mesh %dx%d in %d row slabs, 1 halo quad row, NCCL exchange "
                                    "of `vec` every step" % (nx, ny * world, world)),
                    "l2": "inputs larger than L2 (%.1f GB per step), no flush" % (bytes_run / 1e9),
-                   "mesh_build_s": t_mesh, "numbering": args.icon_reorder},
+                   "mesh_build_s": t_mesh, "numbering": args.icon_reorder, "codegen_options": opts},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None if (nabla4 or diamond) else icon_traffic(E),
                      "kernel": ("%d generated kernel launch/step (13 fused edge stages); %.0f algorithmic "

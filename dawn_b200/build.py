@@ -109,8 +109,11 @@ VARIANTS = {
     "hori_diff_stencil_01": [dict(shared_temporaries=1)], "hori_diff_stencil": [dict(shared_temporaries=1)],
     "copy_stencil": [dict(shared_temporaries=1)], "nonoverlapping_stencil": [dict(shared_temporaries=1)],
     "ICON_laplacian_stencil": [dict(fuse_columns=0, levels_per_thread=1), dict(levels_per_thread=8),
-                               dict(co_schedule=0)],
-    "ICON_nabla4_stencil": [dict(fuse_columns=0, levels_per_thread=1), dict(co_schedule=0)],
+                               dict(co_schedule=0), dict(ico_chain=1), dict(ico_chain=1, co_schedule=0),
+                               dict(ico_chain=1, ico_chain_lag=1), dict(ico_chain=1, ico_chain_lag=100000)],
+    "ICON_nabla4_stencil": [dict(fuse_columns=0, levels_per_thread=1), dict(co_schedule=0), dict(ico_chain=1)],
+    "overwriteGathered": [dict(ico_chain=1)],
+    **{"fuzzico_%02d" % n: [dict(ico_chain=1)] for n in range(16, 20)},
     "kcache_fill": [dict(column_ring=0)], "kcache_flush": [dict(column_ring=0)],
     "kcache_fill_backward": [dict(column_ring=0)], "intervals02": [dict(column_ring=0)],
     "intervals03": [dict(column_ring=0)], "kparallel_solver": [dict(column_ring=0)],

@@ -35,6 +35,8 @@ b200::codegen::Options convert(const dawn_b200_options* o) {
   r.RingEarly = o->ring_early;
   r.RingStagger = o->ring_stagger;
   r.IcoFullBlocks = o->ico_full_blocks;
+  r.IcoChain = o->ico_chain;
+  r.IcoChainLag = o->ico_chain_lag;
   r.RingProducer = o->ring_producer;
   r.SinglePrecision = o->single_precision;
   return r;
@@ -63,6 +65,7 @@ void dawn_b200_default_options(dawn_b200_options* o) {
   o->ring_drain = 1;
   o->ring_early = 1;
   o->ring_producer = 0;
+  o->ico_chain = 0;
 }
 
 int dawn_b200_parse_backend(const char* s) {

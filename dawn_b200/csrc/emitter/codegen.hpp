@@ -53,6 +53,9 @@ struct Options {
   int ColumnRing = 1;      // 1: sequential column kernels stream their inputs through a TMA ring
   int RingLevels = 0;      // k levels per ring slot (0 = default 4)
   int PrefetchK = 0;       // register prefetch depth of sequential column loops (0 = default 8)
+  int IcoChain = 0;        // 1: unstructured: fuse a launch with the next one that gathers its results (L2 hand-over;
+                           // measured: less DRAM traffic but slower on B200, see dawn_b200_codegen.h)
+  int IcoChainLag = 0;     // schedule distance between a consumer block and its producers (0 = 2048 blocks)
   int RingProducer = 0;    // 1: column-ring kernels get a dedicated TMA producer warp instead of thread 0 +
                            // __syncthreads (measured slower in full waves on B200, see dawn_b200_codegen.h)
   int SinglePrecision = 0; // 1: generate for ::dawn::float_type = float (element size 4)

@@ -165,6 +165,11 @@ struct Group {
   // finds in L2 (ICON nabla2: `vec` is gathered by the vertex and by the cell stage)
   int coWith = -1;      // index of the group launched together with this one
   bool coMember = false; // launched by an earlier group
+  // chaining (ico_chain): the launch of this group (and its co-scheduled partner) also runs the NEXT group,
+  // which gathers through a chain what this launch writes: consumer blocks follow their producers in a
+  // host-built block order and read the handed-over fields from L2
+  int chainNext = -1;       // index of the consumer group run by this launch
+  bool chainMember = false; // run by the launch of an earlier group
 };
 
 class IcoEmitter {
@@ -214,10 +219,22 @@ private:
   }
 
   std::vector<Group> plan(const Stencil& st);
-  void emitKernel(const Group& g, const Group* partner);
+  // how one role of a launch is emitted
+  struct RoleOpts {
+    std::string levelBlock = "blockIdx.y"; // index of the block of levels
+    bool noReturn = false;                 // threads past the element range skip the body instead of returning
+    std::set<int> cg;                      // fields another role of the launch wrote: ld.global.cg
+    std::set<int> streamOnce;              // read-only fields every role reads at its own element only: evict-first
+    std::set<int> storeStream;             // written fields nobody in the launch reads again: st.global.cs
+  };
+  void emitKernel(const Group& g, const Group* partner, const Group* consumer);
   void emitRole(const Group& g, const std::string& blockExpr, const std::string& lo,
-                const std::string& hi);
+                const std::string& hi, const RoleOpts& ro);
   void planCoScheduling(std::vector<Group>& groups) const;
+  void planChains(std::vector<Group>& groups) const;
+  // tables through which consumer `c` gathers fields written by producer role `p` (top-level chains only);
+  // false if it reaches them in a way the chain plan does not cover
+  bool chainTables(const Group& c, const Group& p, std::vector<std::pair<std::vector<LocationType>, bool>>& out) const;
   void emitHost(const std::vector<Group>& groups);
   void collect(Group& g);
 };
@@ -382,6 +399,8 @@ public:
   std::function<int(int)> sparseSize;
   std::map<int, std::string> forwarded; // field -> variable with its current value at (pidx, k)
   int uid = 0;
+  // chained launches (IcoEmitter::RoleOpts): cache policy per field
+  std::set<int> cg, streamOnce, storeStream;
 
   struct Ctx {
     std::string center = "pidx"; // index of the element the reduction runs on
@@ -465,8 +484,10 @@ public:
     if(registerOnly.count(e.accessID))
       throw std::runtime_error("b200-ico: internal error, register-only temporary read from memory");
     std::string ref = fieldRef(e, c);
+    if(cg.count(e.accessID))
+      return "__ldcg(&" + ref + ")"; // written by another role of this launch: L2 is the point of coherence
     if(!g.fieldsWritten.count(e.accessID))
-      return "__ldg(&" + ref + ")";
+      return (streamOnce.count(e.accessID) ? "__ldcs(&" : "__ldg(&") + ref + ")";
     return ref;
   }
 
@@ -588,8 +609,12 @@ public:
         val = "(" + read(lhs, top) + " " + s->expr->op.substr(0, 1) + " " + rhs + ")";
       std::string var = fname(lhs.accessID) + "_v" + std::to_string(uid++);
       out.push_back(pad + "const ::dawn::float_type " + var + " = " + val + ";");
-      if(!registerOnly.count(lhs.accessID))
-        out.push_back(pad + fieldRef(lhs, top) + " = " + var + ";");
+      if(!registerOnly.count(lhs.accessID)) {
+        if(storeStream.count(lhs.accessID))
+          out.push_back(pad + "__stcs(&" + fieldRef(lhs, top) + ", " + var + ");");
+        else
+          out.push_back(pad + fieldRef(lhs, top) + " = " + var + ";");
+      }
       if(!conditional)
         forwarded[lhs.accessID] = var;
       else
@@ -691,7 +716,7 @@ void IcoEmitter::planCoScheduling(std::vector<Group>& groups) const {
 
 // One role of a launch: the code of a group for the element block `blockExpr` of [lo, hi).
 void IcoEmitter::emitRole(const Group& g, const std::string& blockExpr, const std::string& lo,
-                          const std::string& hi) {
+                          const std::string& hi, const RoleOpts& ro) {
   const bool sequential = g.ms->loopOrder != LoopOrder::Parallel;
   const bool backward = g.ms->loopOrder == LoopOrder::Backward;
   // grid: element blocks fastest (x), level blocks in y.  (Level blocks fastest, so that the blocks
@@ -699,7 +724,10 @@ void IcoEmitter::emitRole(const Group& g, const std::string& blockExpr, const st
   // nabla2 71 % against 78 % of the HBM peak - too many concurrent DRAM streams.)
   os_ << "  const int pidx = " << lo << " + (int)(" << blockExpr << ") * " << block_
       << " + threadIdx.x; // elements [" << lo << ", " << hi << ")\n";
-  os_ << "  if(pidx >= " << hi << ")\n    return;\n";
+  if(ro.noReturn)
+    os_ << "  if(pidx < " << hi << ") {\n";
+  else
+    os_ << "  if(pidx >= " << hi << ")\n    return;\n";
   // neighbour indices, once per thread
   for(auto const& ch : g.chains) {
     int size = icoChainSize(ch.first, ch.second);
@@ -726,7 +754,7 @@ void IcoEmitter::emitRole(const Group& g, const std::string& blockExpr, const st
     else
       os_ << "  for(int k = kb; k <= ke; ++k) {\n";
   } else {
-    os_ << "  const int k0 = kb + blockIdx.y * " << lpt_ << ";\n";
+    os_ << "  const int k0 = kb + " << ro.levelBlock << " * " << lpt_ << ";\n";
   }
   const std::string loopHead = "#pragma unroll\n  for(int kk = 0; kk < " + std::to_string(lpt_) +
                                "; ++kk) {\n    const int k = k0 + kk;\n";
@@ -736,7 +764,7 @@ void IcoEmitter::emitRole(const Group& g, const std::string& blockExpr, const st
   IcoBody body{inst_, g, registerOnly_,
                [this](int id) { return fname(id); },
                [this](int id) -> const FieldDims& { return dims(id); },
-               [this](int id) { return sparseSize(id); }, {}, 0};
+               [this](int id) { return sparseSize(id); }, {}, 0, ro.cg, ro.streamOnce, ro.storeStream};
   for(auto const* st : g.stages) {
     bodyText << "    // stage " << st->id << "\n";
     for(auto const& dm : st->doMethods) {
@@ -757,6 +785,8 @@ void IcoEmitter::emitRole(const Group& g, const std::string& blockExpr, const st
   }
   if(sequential || !opt_.IcoFullBlocks) {
     os_ << bodyText.str() << "  }\n";
+    if(ro.noReturn)
+      os_ << "  }\n";
     return;
   }
   // ico_full_blocks: blocks of levels that lie completely inside the range run the unrolled loop
@@ -764,13 +794,122 @@ void IcoEmitter::emitRole(const Group& g, const std::string& blockExpr, const st
   // partial block takes a plain loop
   os_ << "  if(k0 + " << lpt_ - 1 << " <= ke) {\n" << loopHead << bodyText.str() << "  }\n  } else {\n";
   os_ << "  for(int k = k0; k <= ke; ++k) {\n" << bodyText.str() << "  }\n  }\n";
+  if(ro.noReturn)
+    os_ << "  }\n";
 }
 
-void IcoEmitter::emitKernel(const Group& g, const Group* partner) {
+// Tables (top-level chains from the consumer's own element) through which `c` reads fields `p` writes.
+bool IcoEmitter::chainTables(const Group& c, const Group& p,
+                             std::vector<std::pair<std::vector<LocationType>, bool>>& out) const {
+  bool ok = true;
+  std::set<std::string> seen;
+  std::function<void(const ExprPtr&, const Expr*, int)> walk = [&](const ExprPtr& e, const Expr* red, int nest) {
+    if(!e)
+      return;
+    if(e->kind == Expr::Field && p.fieldsWritten.count(e->accessID)) {
+      if(nest == 0) {
+        if(fieldLoc(e->accessID) != c.loc)
+          ok = false; // a dense field of another location type read outside a reduction: not a valid access
+      } else if(nest == 1 && red && (e->hasOffset || fieldLoc(e->accessID) != c.loc)) {
+        if(fieldLoc(e->accessID) != red->chain.back() || fieldLoc(e->accessID) != p.loc)
+          ok = false;
+        else if(seen.insert(chainTag(red->chain, red->includeCenter)).second)
+          out.push_back({red->chain, red->includeCenter});
+      } else if(nest > 1)
+        ok = false; // reached through a nested reduction: the dependence range is not a single table
+    }
+    if(e->kind == Expr::Reduce) {
+      walk(e->kids[0], e.get(), nest + 1);
+      for(size_t n = 1; n < e->kids.size(); ++n)
+        walk(e->kids[n], red, nest);
+      return;
+    }
+    for(auto const& k : e->kids)
+      walk(k, red, nest);
+  };
+  std::function<void(const StmtPtr&)> ws = [&](const StmtPtr& st) {
+    if(st->kind == Stmt::Loop) { // neighbour loops touching produced fields: not covered
+      analysis::visitStmts(st->body, [&](const Expr& e, bool) {
+        if(e.kind == Expr::Field && p.fieldsWritten.count(e.accessID))
+          ok = false;
+      });
+      return;
+    }
+    walk(st->expr, nullptr, 0);
+    for(auto const& b : st->body)
+      ws(b);
+    for(auto const& b : st->orelse)
+      ws(b);
+  };
+  for(auto const* stg : c.stages)
+    for(auto const& dm : stg->doMethods)
+      for(auto const& st : dm.stmts)
+        ws(st);
+  return ok;
+}
+
+void IcoEmitter::planChains(std::vector<Group>& groups) const {
+  if(!opt_.IcoChain)
+    return;
+  auto disjoint = [](const std::set<int>& a, const std::set<int>& b) {
+    for(int x : a)
+      if(b.count(x))
+        return false;
+    return true;
+  };
+  for(size_t i = 0; i < groups.size(); ++i) {
+    Group& a = groups[i];
+    if(a.coMember || a.chainMember || a.chainNext >= 0)
+      continue;
+    const Group* partner = a.coWith >= 0 ? &groups[a.coWith] : nullptr;
+    const size_t j = partner ? (size_t)a.coWith + 1 : i + 1;
+    if(j >= groups.size())
+      continue;
+    Group& c = groups[j];
+    if(c.coWith >= 0 || c.coMember || c.chainMember || c.ms != a.ms || a.ms->loopOrder != LoopOrder::Parallel ||
+       a.hasSpace || c.hasSpace || (partner && partner->hasSpace) || c.usesGlobals != a.usesGlobals)
+      continue;
+    // the consumer must not write what the producers touch, and at its own element it may only read produced
+    // fields of its own location type (register forwarding does not cross roles, flags cover neighbourhoods)
+    std::set<int> prodTouched = a.fieldsRead, prodWritten = a.fieldsWritten;
+    prodTouched.insert(a.fieldsWritten.begin(), a.fieldsWritten.end());
+    if(partner) {
+      prodTouched.insert(partner->fieldsRead.begin(), partner->fieldsRead.end());
+      prodTouched.insert(partner->fieldsWritten.begin(), partner->fieldsWritten.end());
+      prodWritten.insert(partner->fieldsWritten.begin(), partner->fieldsWritten.end());
+    }
+    if(!disjoint(c.fieldsWritten, prodTouched) || disjoint(c.fieldsRead, prodWritten))
+      continue;
+    bool temporaries = false; // produced temporaries live in scratch with the same layout: fine; register-only ones never cross
+    (void)temporaries;
+    std::vector<std::pair<std::vector<LocationType>, bool>> t0, t1;
+    if(!chainTables(c, a, t0) || (partner && !chainTables(c, *partner, t1)))
+      continue;
+    if(t0.empty() && t1.empty())
+      continue;
+    // a produced field of the consumer's own location read at the own element would need the producer block
+    // of the same index: keep such programs as two launches
+    bool ownRead = false;
+    for(auto const* stg : c.stages)
+      forEachAccess(*stg, [&](const Expr& e, int nest, bool) {
+        if(prodWritten.count(e.accessID) && (nest == 0 || (!e.hasOffset && fieldLoc(e.accessID) == c.loc)))
+          ownRead = true;
+      });
+    if(ownRead)
+      continue;
+    a.chainNext = (int)j;
+    c.chainMember = true;
+  }
+}
+
+void IcoEmitter::emitKernel(const Group& g, const Group* partner, const Group* consumer) {
   const bool sequential = g.ms->loopOrder != LoopOrder::Parallel;
   os_ << "// kernel " << g.name << ": " << g.stages.size() << " fused stage(s) on " << locName(g.loc);
   if(partner)
     os_ << " co-scheduled with " << partner->stages.size() << " stage(s) on " << locName(partner->loc);
+  if(consumer)
+    os_ << ", chained with " << consumer->stages.size() << " stage(s) on " << locName(consumer->loc)
+        << " that gather their results (flags + L2 hand-over)";
   os_ << ", " << block_ << " threads, "
       << (sequential ? std::string("sequential k sweep") : std::to_string(lpt_) + " level(s)/thread") << "\n";
   // --max-blocks-sm (CodeGen/Options.inc): resident blocks per SM the register allocator must allow.
@@ -785,10 +924,14 @@ void IcoEmitter::emitKernel(const Group& g, const Group* partner) {
          "const int n_vertices";
   if(partner)
     os_ << ", const int elem_lo1, const int elem_hi1, const unsigned nb0, const unsigned nb1";
+  if(consumer)
+    os_ << ", const int elem_lo2, const int elem_hi2, const b200_chain_view cv, const unsigned epoch";
   std::set<std::string> tags;
   std::vector<const Group*> roles{&g};
   if(partner)
     roles.push_back(partner);
+  if(consumer)
+    roles.push_back(consumer);
   for(auto const* r : roles)
     for(auto const& ch : r->chains)
       if(tags.insert(chainTag(ch.first, ch.second)).second)
@@ -807,20 +950,71 @@ void IcoEmitter::emitKernel(const Group& g, const Group* partner) {
   }
   os_ << ") {\n";
   os_ << "  (void)n_cells; (void)n_edges; (void)n_vertices;\n";
-  if(!partner) {
-    emitRole(g, "blockIdx.x", "elem_lo", "elem_hi");
-  } else {
-    // blocks alternate between the two roles in proportion nb0 : nb1 (role 0 owns the blocks where
-    // floor((b+1) nb0 / tot) steps), so both sweep their element ranges at the same relative pace
-    os_ << "  const unsigned long long tot = (unsigned long long)nb0 + nb1;\n";
-    os_ << "  const unsigned r0 = (unsigned)(((unsigned long long)blockIdx.x * nb0) / tot);\n";
-    os_ << "  const unsigned r0n = (unsigned)(((unsigned long long)(blockIdx.x + 1) * nb0) / tot);\n";
-    os_ << "  if(r0n > r0) {\n";
-    emitRole(g, "r0", "elem_lo", "elem_hi");
-    os_ << "  } else {\n";
-    emitRole(*partner, "blockIdx.x - r0", "elem_lo1", "elem_hi1");
-    os_ << "  }\n";
+  RoleOpts plain;
+  if(!consumer) {
+    if(!partner) {
+      emitRole(g, "blockIdx.x", "elem_lo", "elem_hi", plain);
+    } else {
+      // blocks alternate between the two roles in proportion nb0 : nb1 (role 0 owns the blocks where
+      // floor((b+1) nb0 / tot) steps), so both sweep their element ranges at the same relative pace
+      os_ << "  const unsigned long long tot = (unsigned long long)nb0 + nb1;\n";
+      os_ << "  const unsigned r0 = (unsigned)(((unsigned long long)blockIdx.x * nb0) / tot);\n";
+      os_ << "  const unsigned r0n = (unsigned)(((unsigned long long)(blockIdx.x + 1) * nb0) / tot);\n";
+      os_ << "  if(r0n > r0) {\n";
+      emitRole(g, "r0", "elem_lo", "elem_hi", plain);
+      os_ << "  } else {\n";
+      emitRole(*partner, "blockIdx.x - r0", "elem_lo1", "elem_hi1", plain);
+      os_ << "  }\n";
+    }
+    os_ << "}\n\n";
+    return;
   }
+  // ---- chained launch: blockIdx.x = level block * sched_len + position in the host-built schedule ----------
+  // cache policy: fields every role only reads at its own element stream through (evict-first) so that the
+  // handed-over fields stay in L2 until their consumers arrive; final results nobody re-reads stream out
+  RoleOpts prod, cons;
+  prod.levelBlock = cons.levelBlock = "lb";
+  prod.noReturn = cons.noReturn = true;
+  std::set<int> gathered, producedSet = g.fieldsWritten;
+  if(partner)
+    producedSet.insert(partner->fieldsWritten.begin(), partner->fieldsWritten.end());
+  for(auto const* r : roles)
+    for(auto const* stg : r->stages)
+      forEachAccess(*stg, [&](const Expr& e, int nest, bool) {
+        if(nest > 0 && (e.hasOffset || nest > 1 || fieldLoc(e.accessID) != r->loc))
+          gathered.insert(e.accessID);
+      });
+  for(int f : args)
+    if(!written.count(f) && !gathered.count(f) && !isVertical(f) && hasK(f))
+      prod.streamOnce.insert(f), cons.streamOnce.insert(f);
+  for(int f : consumer->fieldsWritten)
+    cons.storeStream.insert(f);
+  for(int f : consumer->fieldsRead)
+    if(producedSet.count(f))
+      cons.cg.insert(f);
+  os_ << "  const unsigned lb = blockIdx.x / cv.sched_len;   // block of levels\n";
+  os_ << "  const unsigned item = __ldg(&cv.sched[blockIdx.x - lb * cv.sched_len]);\n";
+  os_ << "  const unsigned role = item >> 30, bidx = item & 0x3fffffffu;\n";
+  os_ << "  unsigned* const flags = cv.flags + (size_t)lb * (cv.nb0 + cv.nb1);\n";
+  os_ << "  if(role == 0u) {\n";
+  emitRole(g, "bidx", "elem_lo", "elem_hi", prod);
+  os_ << "    __syncthreads();\n    if(threadIdx.x == 0)\n      ::dawn_b200::chain::publish(&flags[bidx], epoch);\n";
+  if(partner) {
+    os_ << "  } else if(role == 1u) {\n";
+    emitRole(*partner, "bidx", "elem_lo1", "elem_hi1", prod);
+    os_ << "    __syncthreads();\n    if(threadIdx.x == 0)\n      ::dawn_b200::chain::publish(&flags[cv.nb0 + bidx], epoch);\n";
+  }
+  os_ << "  } else {\n";
+  os_ << "    // wait for the producer blocks this block's elements reach through the neighbour tables\n";
+  os_ << "    const int lo0 = __ldg(&cv.need[4 * bidx]), hi0 = __ldg(&cv.need[4 * bidx + 1]);\n";
+  os_ << "    const int lo1 = __ldg(&cv.need[4 * bidx + 2]), hi1 = __ldg(&cv.need[4 * bidx + 3]);\n";
+  os_ << "    for(int q = lo0 + (int)threadIdx.x; q < hi0; q += " << block_ << ")\n"
+      << "      ::dawn_b200::chain::wait(&flags[q], epoch, cv.error);\n";
+  os_ << "    for(int q = lo1 + (int)threadIdx.x; q < hi1; q += " << block_ << ")\n"
+      << "      ::dawn_b200::chain::wait(&flags[cv.nb0 + q], epoch, cv.error);\n";
+  os_ << "    __syncthreads();\n";
+  emitRole(*consumer, "bidx", "elem_lo2", "elem_hi2", cons);
+  os_ << "  }\n";
   os_ << "}\n\n";
 }
 
@@ -844,6 +1038,9 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
   for(int f : scratch_)
     os_ << "  ::dawn_b200::scratch_field m_" << fname(f) << ";\n";
   os_ << "  ::dawn_b200::timer_b200 m_timer;\n";
+  for(size_t gi = 0; gi < groups.size(); ++gi)
+    if(groups[gi].chainNext >= 0)
+      os_ << "  b200_chain_plan* m_chain_" << gi << " = nullptr; // block schedule + flags of the chained launch\n";
   os_ << "  std::vector<b200_splitter_t> m_splitters; // unstructured_domain twin\n";
   os_ << "  b200_metrics_record* m_record = nullptr;  // the json* the reference hands to setup_<N>\n";
   os_ << "  int m_error = 0;\npublic:\n  long m_launches = 0;\n";
@@ -867,7 +1064,18 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
     os_ << "    }\n";
   }
   os_ << "  }\n";
+  os_ << "  ~" << cls << "() {";
+  for(size_t gi = 0; gi < groups.size(); ++gi)
+    if(groups[gi].chainNext >= 0)
+      os_ << " b200rt_chain_plan_destroy(m_chain_" << gi << ");";
+  os_ << " }\n";
   os_ << "  int error() const { return m_error; }\n";
+  os_ << "  // chained launches: did every consumer block see its producers?  (synchronises the stream)\n";
+  os_ << "  int chain_status(void* stream) {\n";
+  for(size_t gi = 0; gi < groups.size(); ++gi)
+    if(groups[gi].chainNext >= 0)
+      os_ << "    if(int err = b200rt_chain_plan_status(m_chain_" << gi << ", stream)) return err;\n";
+  os_ << "    (void)stream;\n    return 0;\n  }\n";
   os_ << "  void set_metrics_record(b200_metrics_record* r) { m_record = r; }\n";
   os_ << "  // dawn::unstructured_domain::set_splitter_index (driver-includes/unstructured_domain.hpp:31-33)\n";
   os_ << "  void set_splitter_index(int loc, int space, int offset, int index) {\n"
@@ -919,10 +1127,12 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
         << levelStride << ", k_size)) return err;\n";
     os_ << "    ::dawn::float_type* " << fname(f) << "_p = m_" << fname(f) << ".data;\n";
   }
-  for(auto const& g : groups) {
-    if(g.coMember)
+  for(size_t gi = 0; gi < groups.size(); ++gi) {
+    const Group& g = groups[gi];
+    if(g.coMember || g.chainMember)
       continue;
     const Group* partner = g.coWith >= 0 ? &groups[g.coWith] : nullptr;
+    const Group* consumer = g.chainNext >= 0 ? &groups[g.chainNext] : nullptr;
     bool sequential = g.ms->loopOrder != LoopOrder::Parallel;
     std::string n = IcoBody::stride(g.loc);
     os_ << "    {\n";
@@ -946,6 +1156,41 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
       os_ << "      const int elem_lo1 = 0, elem_hi1 = " << IcoBody::stride(partner->loc) << ";\n";
       os_ << "      const unsigned nb0 = (unsigned)((elem_hi - elem_lo + " << block_ - 1 << ") / " << block_
           << "), nb1 = (unsigned)((elem_hi1 - elem_lo1 + " << block_ - 1 << ") / " << block_ << ");\n";
+    }
+    if(consumer) {
+      // the schedule and the flags of the chained launch: built on first use from the device tables
+      os_ << "      const int elem_lo2 = 0, elem_hi2 = " << IcoBody::stride(consumer->loc) << ";\n";
+      os_ << "      if(!m_chain_" << gi << ") {\n";
+      std::vector<std::pair<std::vector<LocationType>, bool>> t0, t1;
+      chainTables(*consumer, g, t0);
+      if(partner)
+        chainTables(*consumer, *partner, t1);
+      os_ << "        const int n_prod[2] = {elem_hi, " << (partner ? "elem_hi1" : "0") << "};\n";
+      os_ << "        const int* tabs[] = {";
+      for(auto const& t : t0)
+        os_ << "m_tbl_" << chainTag(t.first, t.second) << ", ";
+      for(auto const& t : t1)
+        os_ << "m_tbl_" << chainTag(t.first, t.second) << ", ";
+      os_ << "};\n        const int tab_role[] = {";
+      for(size_t q = 0; q < t0.size(); ++q)
+        os_ << "0, ";
+      for(size_t q = 0; q < t1.size(); ++q)
+        os_ << "1, ";
+      os_ << "};\n        const int tab_nbh[] = {";
+      for(auto const& t : t0)
+        os_ << icoChainSize(t.first, t.second) << ", ";
+      for(auto const& t : t1)
+        os_ << icoChainSize(t.first, t.second) << ", ";
+      os_ << "};\n";
+      os_ << "        if(int err = b200rt_chain_plan_create(&m_chain_" << gi << ", elem_hi2, " << block_ << ", "
+          << (partner ? 2 : 1) << ", n_prod, tabs, tab_role, tab_nbh, " << t0.size() + t1.size() << ", "
+          << levelBlocks << ", " << opt_.IcoChainLag << ", stream)) return err;\n";
+      os_ << "      }\n";
+      os_ << "      b200_chain_view cv;\n      b200rt_chain_plan_view(m_chain_" << gi << ", &cv);\n";
+      os_ << "      const unsigned epoch = b200rt_chain_plan_next_epoch(m_chain_" << gi << ");\n";
+      os_ << "      if(cv.sched_len > 0) {\n";
+      os_ << "      dim3 grid(cv.sched_len * cv.level_blocks);\n";
+    } else if(partner) {
       os_ << "      if(nb0 + nb1 > 0) {\n";
       os_ << "      dim3 grid(nb0 + nb1, " << levelBlocks << ");\n";
     } else {
@@ -959,10 +1204,14 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
     os_ << "k_size, elem_lo, elem_hi, n_cells, n_edges, n_vertices";
     if(partner)
       os_ << ", elem_lo1, elem_hi1, nb0, nb1";
+    if(consumer)
+      os_ << ", elem_lo2, elem_hi2, cv, epoch";
     std::set<std::string> tags;
     std::vector<const Group*> roles{&g};
     if(partner)
       roles.push_back(partner);
+    if(consumer)
+      roles.push_back(consumer);
     for(auto const* r : roles)
       for(auto const& ch : r->chains)
         if(tags.insert(chainTag(ch.first, ch.second)).second)
@@ -1093,10 +1342,11 @@ std::string IcoEmitter::generate() {
   }
   auto groups = plan(inst_.stencils[0]);
   planCoScheduling(groups);
+  planChains(groups);
   for(auto const& g : groups) {
-    if(g.coMember)
+    if(g.coMember || g.chainMember)
       continue;
-    emitKernel(g, g.coWith >= 0 ? &groups[g.coWith] : nullptr);
+    emitKernel(g, g.coWith >= 0 ? &groups[g.coWith] : nullptr, g.chainNext >= 0 ? &groups[g.chainNext] : nullptr);
   }
   emitHost(groups);
   os_ << "} // namespace b200ico\n} // namespace dawn_generated\n\n";
@@ -1134,6 +1384,8 @@ std::string IcoEmitter::generate() {
   os_ << "B200_EXPORT void free_" << n << "(void* handle) { delete static_cast<" << cls << "*>(handle); }\n";
   os_ << "B200_EXPORT long launches_" << n << "(void* handle) { return static_cast<" << cls
       << "*>(handle)->m_launches; }\n";
+  os_ << "B200_EXPORT int chain_status_" << n << "(void* handle, void* stream) { return static_cast<" << cls
+      << "*>(handle)->chain_status(stream); }\n";
   os_ << "B200_EXPORT void set_metrics_record_" << n
       << "(void* handle, b200_metrics_record* record) { static_cast<" << cls
       << "*>(handle)->set_metrics_record(record); }\n";
@@ -1184,7 +1436,7 @@ std::string IcoEmitter::generate() {
   {
     size_t launches = 0;
     for(auto const& g : groups)
-      launches += g.coMember ? 0 : 1;
+      launches += (g.coMember || g.chainMember) ? 0 : 1;
     os_ << "], \\\"kernels\\\": " << launches << ", \\\"globals\\\": [";
   }
   for(size_t g = 0; g < inst_.globals.size(); ++g)
@@ -1214,6 +1466,9 @@ std::string icoCHeader(const iir::Instantiation& inst) {
   os << "void set_splitter_index_" << n << "(void* handle, int loc, int space, int offset, int index);\n";
   os << "/* verification metrics of later verify_/run_and_verify_ calls are also merged into `record` */\n";
   os << "void set_metrics_record_" << n << "(void* handle, b200_metrics_record* record);\n";
+  os << "/* chained launches (several stages in one launch with an in-launch hand-over): 0 if every block saw its\n"
+        " * producers so far; synchronises `stream` */\n";
+  os << "int chain_status_" << n << "(void* handle, void* stream);\n";
   os << "int run_" << n << "(void* handle, const b200_field_t* fields, int nfields, void* stream);\n";
   os << "int run_" << n << "_from_c_host(void* handle, DAWN_B200_FLOAT_TYPE* const* host_fields, int nfields, void* stream);\n";
   os << "int run_" << n << "_from_fort_host(void* handle, DAWN_B200_FLOAT_TYPE* const* host_fields, int nfields, void* stream);\n";

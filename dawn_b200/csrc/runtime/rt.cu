@@ -1,5 +1,6 @@
 // libdawn_b200rt.so — implementation of include/dawn_b200_rt.h (sm_100a).
 #include "../../../include/dawn_b200_rt.h"
+#include "chain_schedule.hpp"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -736,6 +737,86 @@ int b200rt_comm_destroy(void* comm) {
   if(int e = loadNccl())
     return e;
   NK(g_nccl.CommDestroy(comm));
+  return 0;
+}
+
+// ---- chained unstructured launches ------------------------------------------------------------------
+struct b200_chain_plan {
+  b200_chain_view v{};
+  unsigned epoch = 0;
+};
+
+int b200rt_chain_plan_create(b200_chain_plan** plan, int n_consumer, int block, int n_roles,
+                             const int* n_producer, const int* const* tables, const int* table_role,
+                             const int* table_nbh, int n_tables, int level_blocks, int lag_blocks,
+                             void* stream) {
+  if(!plan || n_consumer < 0 || block <= 0 || n_roles < 1 || n_roles > 2 || !n_producer || level_blocks < 1)
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_chain_plan_create: bad argument");
+  // host copies of the neighbour tables (index work, once per stencil instance)
+  std::vector<std::vector<int>> host(n_tables);
+  std::vector<dawn_b200::ChainTable> tabs;
+  for(int t = 0; t < n_tables; ++t) {
+    if(!tables[t] || table_role[t] < 0 || table_role[t] >= n_roles || table_nbh[t] <= 0)
+      return b200rt_set_error(B200_ERR_ARG, "b200rt_chain_plan_create: bad table");
+    host[t].resize((size_t)table_nbh[t] * n_consumer);
+    CK(cudaMemcpyAsync(host[t].data(), tables[t], host[t].size() * sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+    tabs.push_back({host[t].data(), table_nbh[t], table_role[t]});
+  }
+  CK(cudaStreamSynchronize(S(stream)));
+  dawn_b200::ChainSchedule sc =
+      dawn_b200::buildChainSchedule(n_consumer, block, n_roles, n_producer, tabs, lag_blocks > 0 ? lag_blocks : 2048);
+  auto* p = new b200_chain_plan();
+  p->v.sched_len = (unsigned)sc.sched.size();
+  p->v.nb0 = sc.nb[0], p->v.nb1 = sc.nb[1], p->v.nc = sc.nc, p->v.level_blocks = (unsigned)level_blocks;
+  unsigned *d_sched = nullptr, *d_flags = nullptr, *d_err = nullptr;
+  int* d_need = nullptr;
+  const size_t nflags = (size_t)level_blocks * (sc.nb[0] + sc.nb[1]);
+  cudaError_t e = cudaMalloc(&d_sched, std::max<size_t>(1, sc.sched.size()) * sizeof(unsigned));
+  if(e == cudaSuccess) e = cudaMalloc(&d_need, std::max<size_t>(1, sc.need.size()) * sizeof(int));
+  if(e == cudaSuccess) e = cudaMalloc(&d_flags, std::max<size_t>(1, nflags) * sizeof(unsigned));
+  if(e == cudaSuccess) e = cudaMalloc(&d_err, sizeof(unsigned));
+  if(e == cudaSuccess) e = cudaMemcpyAsync(d_sched, sc.sched.data(), sc.sched.size() * sizeof(unsigned), cudaMemcpyHostToDevice, S(stream));
+  if(e == cudaSuccess) e = cudaMemcpyAsync(d_need, sc.need.data(), sc.need.size() * sizeof(int), cudaMemcpyHostToDevice, S(stream));
+  if(e == cudaSuccess) e = cudaMemsetAsync(d_flags, 0, std::max<size_t>(1, nflags) * sizeof(unsigned), S(stream));
+  if(e == cudaSuccess) e = cudaMemsetAsync(d_err, 0, sizeof(unsigned), S(stream));
+  if(e == cudaSuccess) e = cudaStreamSynchronize(S(stream)); // the host vectors go out of scope
+  if(e != cudaSuccess) {
+    cudaFree(d_sched), cudaFree(d_need), cudaFree(d_flags), cudaFree(d_err);
+    delete p;
+    return cudaFail(e, "b200rt_chain_plan_create");
+  }
+  p->v.sched = d_sched, p->v.need = d_need, p->v.flags = d_flags, p->v.error = d_err;
+  *plan = p;
+  return 0;
+}
+int b200rt_chain_plan_view(const b200_chain_plan* plan, b200_chain_view* view) {
+  if(!plan || !view)
+    return b200rt_set_error(B200_ERR_ARG, "b200rt_chain_plan_view: null argument");
+  *view = plan->v;
+  return 0;
+}
+unsigned b200rt_chain_plan_next_epoch(b200_chain_plan* plan) {
+  if(++plan->epoch == 0) // wrapped: 0 is the "never published" value of the flags
+    ++plan->epoch;
+  return plan->epoch;
+}
+int b200rt_chain_plan_status(b200_chain_plan* plan, void* stream) {
+  if(!plan)
+    return 0;
+  unsigned err = 0;
+  CK(cudaMemcpyAsync(&err, plan->v.error, sizeof(err), cudaMemcpyDeviceToHost, S(stream)));
+  CK(cudaStreamSynchronize(S(stream)));
+  if(err)
+    return b200rt_set_error(B200_ERR_RUNTIME, "chained launch: a consumer block gave up waiting for its producers "
+                                              "(blocks were not dispatched in index order?); results are invalid");
+  return 0;
+}
+int b200rt_chain_plan_destroy(b200_chain_plan* plan) {
+  if(!plan)
+    return 0;
+  cudaFree(const_cast<unsigned*>(plan->v.sched)), cudaFree(const_cast<int*>(plan->v.need));
+  cudaFree(plan->v.flags), cudaFree(plan->v.error);
+  delete plan;
   return 0;
 }
 } // extern "C"

@@ -13,6 +13,7 @@
 #include "math.hpp"
 #include "b200_runtime.hpp"
 #include "timer_b200.hpp"
+#include "b200_chain.hpp"
 
 namespace dawn_b200 {
 

@@ -69,6 +69,21 @@ typedef struct dawn_b200_options {
                              backward (L2-fed) sweeps interleave; -1: N from $DAWN_B200_STAGGER_NS (probing) */
   int ico_full_blocks;    /* default 0: unstructured kernels run full blocks of levels through an unrolled
                              loop without per-level bound checks (more loads in flight per thread) */
+  int ico_chain;          /* default 0; 1: an unstructured launch whose results the NEXT launch gathers through a chain
+                             (ICON nabla2: rot_vec / div_vec of the vertex + cell launch, read by the edge launch)
+                             is fused with it into ONE launch: blocks follow a host-built schedule in which every
+                             consumer block comes `ico_chain_lag` blocks after the last producer block it needs,
+                             producers publish a per-block flag (st.release.gpu), consumers wait for the flags
+                             of their neighbourhood (ld.acquire.gpu, bounded spin) and read the handed-over
+                             fields from L2 (ld.global.cg) instead of HBM.  Measured on B200 (ICON nabla2, 20 M
+                             edges x 65 levels, lag 2048): DRAM traffic 124.9 -> 115.2 GB per run (the re-read of
+                             rot_vec / div_vec is gone, 1.10 x the algorithmic bytes), but the three roles mixed
+                             in one launch reach only 61 % DRAM throughput against ~80 % of the two separate
+                             launches: 23.2 ms against 20.7 ms.  Bit-exact, tested, off by default */
+  int ico_chain_lag;      /* producer blocks between a consumer block and the last producer it needs (0 = 2048:
+                             below the ~1600 producer blocks of one residency generation - 148 SMs x 16 blocks -
+                             consumers are dispatched before their producers finish and spin in their slots:
+                             37.8 ms at 512) */
   int ring_producer;      /* default 0; 1: column-ring kernels get a dedicated producer warp that issues the TMA loads
                              (full / empty mbarriers per slot, no block-wide barrier in the sweeps) instead of
                              thread 0 between __syncthreads().  Measured on B200 (tridiagonal_solve): the lone-block

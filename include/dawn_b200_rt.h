@@ -216,6 +216,31 @@ int b200rt_halo_plan_connect(b200_halo_plan* plan, const void* handle_lo, const 
 int b200rt_halo_exchange_p2p(b200_halo_plan* plan, double* field, void* stream);
 int b200rt_halo_plan_p2p_status(b200_halo_plan* plan);
 
+/* ---- chained unstructured launches (codegen option ico_chain) -------------------------------------------
+ * One launch holds up to two producer roles and a consumer role that gathers what they wrote; blocks run
+ * in a host-built order (blockIdx.x = level block * sched_len + position) in which every consumer block
+ * follows the producer blocks its elements reach through `tables` (device SoA tables
+ * [nbh][n_consumer], consumer element -> producer element of role table_role[t]) by `lag_blocks` more
+ * producer blocks.  Producers publish flags[level block][role offset + block] = epoch, consumers wait for
+ * the flag range need[4 c .. 4 c + 3] = {lo0, hi0, lo1, hi1} of their block c.  A wait that gives up
+ * (bounded spin) raises *error; b200rt_chain_plan_status synchronises the stream and reports it. */
+typedef struct b200_chain_plan b200_chain_plan;
+typedef struct b200_chain_view {
+  const unsigned* sched; /* device */
+  const int* need;       /* device */
+  unsigned* flags;       /* device, level_blocks x (nb0 + nb1) */
+  unsigned* error;       /* device */
+  unsigned sched_len, nb0, nb1, nc, level_blocks;
+} b200_chain_view;
+int b200rt_chain_plan_create(b200_chain_plan** plan, int n_consumer, int block, int n_roles,
+                             const int* n_producer, const int* const* tables, const int* table_role,
+                             const int* table_nbh, int n_tables, int level_blocks, int lag_blocks,
+                             void* stream);
+int b200rt_chain_plan_view(const b200_chain_plan* plan, b200_chain_view* view);
+unsigned b200rt_chain_plan_next_epoch(b200_chain_plan* plan); /* 1, 2, 3, ... one per launch */
+int b200rt_chain_plan_status(b200_chain_plan* plan, void* stream);
+int b200rt_chain_plan_destroy(b200_chain_plan* plan);
+
 #ifdef __cplusplus
 }
 #endif

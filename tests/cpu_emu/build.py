@@ -127,6 +127,10 @@ def run(name, code, info, mesh, k, fields, globals_=None, splitters=None):
     launches.restype = ctypes.c_long
     launches.argtypes = [ctypes.c_void_p]
     nl = launches(handle)
+    status = getattr(lib, "chain_status_" + name)   # chained launches: every consumer block saw its producers
+    status.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    if status(handle, None):
+        raise RuntimeError(lib.b200rt_last_error().decode())
     freef = getattr(lib, "free_" + name)
     freef.argtypes = [ctypes.c_void_p]
     freef(handle)

@@ -1,10 +1,12 @@
 // TEST INFRASTRUCTURE: host-memory stand-in for the entry points of include/dawn_b200_rt.h that generated
 // b200-ico modules call ("device" memory is plain host memory in the emulation, tests/cpu_emu/emu_cuda.hpp).
 #include "../../include/dawn_b200_rt.h"
+#include "../../dawn_b200/csrc/runtime/chain_schedule.hpp" // the schedule the GPU runtime builds
 
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 static thread_local std::string g_err;
 extern "C" {
@@ -125,6 +127,45 @@ int b200rt_verify_field_f32(const float*, const float*, size_t, double, double, 
   return b200rt_set_error(B200_ERR_RUNTIME, "emu: b200rt_verify_field_f32 is not emulated");
 }
 int b200rt_metrics_record_add(b200_metrics_record*, const char*, const char*, const b200_verification_metrics*) {
+  return 0;
+}
+// chained unstructured launches: the same schedule as the GPU runtime, arrays in host memory
+struct b200_chain_plan {
+  b200_chain_view v{};
+  unsigned epoch = 0;
+  std::vector<unsigned> sched, flags;
+  std::vector<int> need;
+  unsigned error = 0;
+};
+int b200rt_chain_plan_create(b200_chain_plan** plan, int n_consumer, int block, int n_roles, const int* n_producer,
+                             const int* const* tables, const int* table_role, const int* table_nbh, int n_tables,
+                             int level_blocks, int lag_blocks, void*) {
+  std::vector<dawn_b200::ChainTable> tabs;
+  for(int t = 0; t < n_tables; ++t)
+    tabs.push_back({tables[t], table_nbh[t], table_role[t]});
+  dawn_b200::ChainSchedule sc =
+      dawn_b200::buildChainSchedule(n_consumer, block, n_roles, n_producer, tabs, lag_blocks > 0 ? lag_blocks : 2048);
+  auto* p = new b200_chain_plan();
+  p->sched = sc.sched, p->need = sc.need;
+  p->flags.assign((size_t)level_blocks * (sc.nb[0] + sc.nb[1]) + 1, 0u);
+  p->v.sched = p->sched.data(), p->v.need = p->need.data(), p->v.flags = p->flags.data(), p->v.error = &p->error;
+  p->v.sched_len = (unsigned)sc.sched.size(), p->v.nb0 = sc.nb[0], p->v.nb1 = sc.nb[1], p->v.nc = sc.nc;
+  p->v.level_blocks = (unsigned)level_blocks;
+  *plan = p;
+  return 0;
+}
+int b200rt_chain_plan_view(const b200_chain_plan* plan, b200_chain_view* view) {
+  *view = plan->v;
+  return 0;
+}
+unsigned b200rt_chain_plan_next_epoch(b200_chain_plan* plan) { return ++plan->epoch; }
+int b200rt_chain_plan_status(b200_chain_plan* plan, void*) {
+  if(plan && plan->error)
+    return b200rt_set_error(B200_ERR_RUNTIME, "emu: a consumer block ran before one of its producers");
+  return 0;
+}
+int b200rt_chain_plan_destroy(b200_chain_plan* plan) {
+  delete plan;
   return 0;
 }
 }

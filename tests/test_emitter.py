@@ -156,10 +156,18 @@ def test_icon_laplacian_plan_fuses_edge_stages():
     code = _code("ICON_laplacian_stencil", backend="b200-ico", co_schedule=0)
     kernels = re.findall(r"^// kernel (\S+): (\d+) fused stage\(s\) on (\w+)", code, flags=re.M)
     assert [(k[1], k[2]) for k in kernels] == [("1", "vertices"), ("1", "cells"), ("5", "edges")]
-    # default: the independent vertex and cell groups (both gather `vec`) share one launch
+    # the independent vertex and cell groups (both gather `vec`) share one launch
     code = _code("ICON_laplacian_stencil", backend="b200-ico")
     heads = re.findall(r"^// kernel .*$", code, flags=re.M)
     assert len(heads) == 2 and "on vertices co-scheduled with 1 stage(s) on cells" in heads[0]
+    # ico_chain=1: the edge stages, which gather rot_vec / div_vec, are chained into that launch - producers
+    # publish flags, consumers wait for them and read the handed-over fields with ld.global.cg
+    code = _code("ICON_laplacian_stencil", backend="b200-ico", ico_chain=1)
+    heads = re.findall(r"^// kernel .*$", code, flags=re.M)
+    assert len(heads) == 1 and "chained with 5 stage(s) on edges" in heads[0]
+    assert "chain::publish(&flags[bidx], epoch)" in code and "chain::wait(&flags[q], epoch, cv.error)" in code
+    assert "__ldcg(&rot_vec_p[" in code and "__ldcg(&div_vec_p[" in code and "__ldg(&rot_vec_p[" not in code
+    assert "__ldcs(&geofac_rot_p[" in code and "__stcs(&nabla2_vec_p[" in code and "__ldg(&vec_p[" in code
     assert "__tmp_nab_60_p" not in code and "scratch_field" not in code  # temporaries stay in registers
     assert "setup_ICON_laplacian_stencil(void** handle, const b200_mesh_t* mesh, int k_size" in code
     unfused = _code("ICON_laplacian_stencil", backend="b200-ico", fuse_columns=0, co_schedule=0)
@@ -406,6 +414,9 @@ def test_ring_stagger_is_off_by_default():
 def test_icon_nabla4_plan():
     # nabla2 applied twice: (vertices | cells) co-scheduled + 5 fused edge stages, both twice; the second
     # vertex/cell launch gathers nabla2_vec, which the first edge kernel must therefore store
+    code = _code("ICON_nabla4_stencil", backend="b200-ico", ico_chain=1)
+    heads = re.findall(r"^// kernel .*$", code, flags=re.M)
+    assert len(heads) == 2 and all("chained with 5 stage(s) on edges" in h for h in heads)
     code = _code("ICON_nabla4_stencil", backend="b200-ico")
     heads = re.findall(r"^// kernel .*$", code, flags=re.M)
     assert len(heads) == 4

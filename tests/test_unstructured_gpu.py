@@ -37,6 +37,15 @@ def _run(name, mesh, k, fields, splitters=None, globals_=None, **opts):
     return out, st
 
 
+def _chain_ok(st):
+    """chained launches: every consumer block saw the flags of its producers (chain_status_<N>)"""
+    import ctypes
+    import torch
+    fn = getattr(st.module.lib, "chain_status_" + st.module.name)
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    assert fn(st.handle, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+
+
 def _random_fields(mod, m, k, rng, integer_levels=()):
     """One random array per API field of a module, in the oracle's layout."""
     f = {}
@@ -64,7 +73,9 @@ def _check(got, want, m, names):
 
 @pytest.mark.parametrize("nx,ny,k", [(7, 5, 3), (33, 20, 9), (64, 64, 65)])
 @pytest.mark.parametrize("opts", [dict(), dict(fuse_columns=0, levels_per_thread=1),
-                                  dict(levels_per_thread=8), dict(co_schedule=0)])
+                                  dict(levels_per_thread=8), dict(co_schedule=0), dict(ico_chain=1),
+                                  dict(ico_chain=1, co_schedule=0), dict(ico_chain=1, ico_chain_lag=1),
+                                  dict(ico_chain=1, ico_chain_lag=100000)])
 def test_icon_laplacian(nx, ny, k, opts):
     m = TriMesh(nx, ny)
     rng = np.random.default_rng(31)
@@ -80,15 +91,18 @@ def test_icon_laplacian(nx, ny, k, opts):
     got, st = _run("ICON_laplacian_stencil", m, k, f, **opts)
     _check(got, want, m, {"rot_vec": VERTEX, "div_vec": CELL, "nabla2_vec": EDGE})
     # 7 stages -> 3 fused groups (vertices, cells, edges); the independent vertex and cell groups both
-    # gather `vec` and share one launch unless co_schedule=0
-    want_launches = 3 if opts.get("fuse_columns", 1) else 7
-    if opts.get("co_schedule", 1):
-        want_launches -= 1
-    assert st.launches() == want_launches
+    # gather `vec` and share one launch unless co_schedule=0; the edge group, which gathers their results,
+    # is chained into that launch with ico_chain=1 (flags + L2 hand-over): ONE launch then
+    assert st.launches() == st.module.info["kernels"]
+    if opts.get("fuse_columns", 1):
+        want_launches = 3 - (1 if opts.get("co_schedule", 1) else 0) - (1 if opts.get("ico_chain", 0) else 0)
+        assert st.launches() == want_launches
+    _chain_ok(st)
 
 
 @pytest.mark.parametrize("nx,ny,k", [(7, 5, 3), (33, 20, 9), (64, 64, 65)])
-@pytest.mark.parametrize("opts", [dict(), dict(co_schedule=0), dict(fuse_columns=0, levels_per_thread=1)])
+@pytest.mark.parametrize("opts", [dict(), dict(co_schedule=0), dict(fuse_columns=0, levels_per_thread=1),
+                                  dict(ico_chain=1)])
 def test_icon_nabla4(nx, ny, k, opts):
     # nabla4 = nabla2(nabla2(vec)): not in the reference; the oracle side is anchored on two passes of
     # the reference-pinned nabla2 oracle (tests/test_unstructured_oracle.py)
@@ -104,9 +118,12 @@ def test_icon_nabla4(nx, ny, k, opts):
         n2, n4 = nabla4_by_two_nabla2_passes(m, k, f)
         _check(got, {"nabla2_vec": n2, "nabla4_vec": n4}, m, {"nabla2_vec": EDGE, "nabla4_vec": EDGE})
     # 14 stages -> 6 fused groups (vertices, cells, 5 edge stages; twice); each independent
-    # vertex/cell pair shares one launch unless co_schedule=0
-    want_launches = (6 if opts.get("fuse_columns", 1) else 14) - (2 if opts.get("co_schedule", 1) else 0)
-    assert st.launches() == want_launches
+    # vertex/cell pair shares one launch unless co_schedule=0, and with ico_chain=1 each edge group is chained
+    # into the launch that produces what it gathers: 2 launches then
+    assert st.launches() == st.module.info["kernels"]
+    if opts.get("fuse_columns", 1):
+        assert st.launches() == 6 - (2 if opts.get("co_schedule", 1) else 0) - (2 if opts.get("ico_chain", 0) else 0)
+    _chain_ok(st)
 
 
 @pytest.mark.parametrize("name,spec,outs", [
@@ -346,8 +363,9 @@ def test_unstructured_iteration_space_and_splitters():
         st2.run(*t)
 
 
+@pytest.mark.parametrize("opts", [dict(), dict(ico_chain=1)], ids=["default", "chained"])
 @pytest.mark.parametrize("nx", [1024])
-def test_icon_laplacian_at_benchmark_scale(nx):
+def test_icon_laplacian_at_benchmark_scale(nx, opts):
     """ICON nabla2 on 3.15 M edges x 65 levels (BASELINE.json configs[3] is the same launch shape on 20 M
     edges): the default module, all 65 levels on the GPU, compared bit for bit with the oracle on a sample
     of levels (nabla2 has no vertical dependency, so a level is checked independently of the others:
@@ -358,7 +376,7 @@ def test_icon_laplacian_at_benchmark_scale(nx):
     name, K = "ICON_laplacian_stencil", 65
     m = TriMesh(nx, nx)
     assert m.num_edges > 3_000_000
-    mod = dawn_b200.load_stencil(name)
+    mod = dawn_b200.load_stencil(name, **opts)
     st = mod.on_mesh(m, K)
     gen = torch.Generator(device="cuda").manual_seed(11)
     n_of = {"cells": m.num_cells, "edges": m.num_edges, "vertices": m.num_vertices}
@@ -369,7 +387,10 @@ def test_icon_laplacian_at_benchmark_scale(nx):
     levels = [0, 7, 8, 33, 63, 64]
     want = unstructured_oracle_on_levels(name, m, mod.fields, tens, levels)
     st.run(*tens)
+    st.run(*tens)        # a second run (chained variant: flags carry the epoch of the launch, nothing is reset)
     torch.cuda.synchronize()
+    _chain_ok(st)
+    assert st.launches() == 2 * st.module.info["kernels"]
     idx = torch.as_tensor(levels, device="cuda")
     for fd, t in zip(mod.fields, tens):
         if fd["name"] not in ("rot_vec", "div_vec", "nabla2_vec"):
@@ -433,6 +454,9 @@ def test_overwriting_a_gathered_field_is_not_fused_into_the_gathering_launch():
         got, st = _run(name, m, k, f)
         _check(got, want, m, {"g": CELL, "o": CELL, "o2": CELL})
         assert st.launches() == 2
+        got, st = _run(name, m, k, f, ico_chain=1)   # the overwrite and its gathering consumer in one launch
+        _check(got, want, m, {"g": CELL, "o": CELL, "o2": CELL})
+        _chain_ok(st)
 
 
 @pytest.mark.parametrize("seed", range(20))
@@ -450,7 +474,8 @@ def test_random_unstructured_stencils_match_the_oracle(seed):
         g = {"beta": 0.625} if "beta" in mod.info.get("globals", []) else None
         want = naive_interp.run_unstructured(iir_path(name), m, k, {n: v.copy() for n, v in f.items()},
                                              globals_=g)
-        got, st = _run(name, m, k, f, globals_=g)
+        got, st = _run(name, m, k, f, globals_=g, **({"ico_chain": 1} if seed >= 16 else {}))
+        _chain_ok(st)
         for fd in mod.fields:
             n = fd["name"]
             if fd["location"] == "none":

@@ -1,0 +1,15 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+for o in "levels_per_thread=4 ico_chain_lag=4096" "levels_per_thread=4 ico_chain_lag=2048" "block_size_ico=256 ico_chain_lag=1024" "block_size_ico=64 ico_chain_lag=4096" "levels_per_thread=4 ico_chain=0"; do
+  a=""; for kv in $o; do a="$a --opt $kv"; done
+  timeout 300 python bench.py --workload icon_nabla2 --steps 10 --no-cpu-baseline --no-e2e $a > gpurun_out/icon_tmp.json 2> gpurun_out/icon_tmp.err
+  python - "$o" <<'PY'
+import json, sys
+try:
+    d = json.loads(open("gpurun_out/icon_tmp.json").read().strip().splitlines()[-1])
+    print("icon_nabla2 [%s] ms %.3f frac %.3f parity %s launches/step %d clocks %s" % (sys.argv[1], d["ms_per_step"], d["roofline"]["frac"], d["parity_checked"], d["gpu_launches"] // d["steps"], d["clocks"]["sm_mhz"]))
+except Exception as e:
+    print("icon_nabla2 [%s] FAILED" % sys.argv[1], e); print(open("gpurun_out/icon_tmp.err").read()[-800:])
+PY
+done | tee gpurun_out/r2_icon_chain3.log
