@@ -35,6 +35,7 @@ b200::codegen::Options convert(const dawn_b200_options* o) {
   r.RingEarly = o->ring_early;
   r.RingStagger = o->ring_stagger;
   r.IcoFullBlocks = o->ico_full_blocks;
+  r.IcoCacheHints = o->ico_cache_hints;
   r.IcoChain = o->ico_chain;
   r.IcoChainLag = o->ico_chain_lag;
   r.RingProducer = o->ring_producer;

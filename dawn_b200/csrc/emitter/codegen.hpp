@@ -53,6 +53,7 @@ struct Options {
   int ColumnRing = 1;      // 1: sequential column kernels stream their inputs through a TMA ring
   int RingLevels = 0;      // k levels per ring slot (0 = default 4)
   int PrefetchK = 0;       // register prefetch depth of sequential column loops (0 = default 8)
+  int IcoCacheHints = 0;   // unstructured: evict-first loads of read-once fields, streaming stores of final results
   int IcoChain = 0;        // 1: unstructured: fuse a launch with the next one that gathers its results (L2 hand-over;
                            // measured: less DRAM traffic but slower on B200, see dawn_b200_codegen.h)
   int IcoChainLag = 0;     // schedule distance between a consumer block and its producers (0 = 2048 blocks)

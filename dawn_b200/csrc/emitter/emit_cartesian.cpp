@@ -203,6 +203,7 @@ private:
   std::set<int> streamedFields(const KernelPlan& kp, const MultiStage& ms, const KRange& part,
                                const std::map<int, int>& depths) const;
   std::set<int> fullyWritten(const MultiStage& ms) const;
+  bool levelsIndependent() const; // every stage on every level, no vertical offsets: k chunks can run on their own
 
   void emitGlobalsStruct();
   void emitKernel(const Stencil& st, const KernelPlan& kp);
@@ -447,6 +448,27 @@ void CartesianEmitter::collectUse(KernelPlan& kp) const {
             kp.fieldsWritten.insert(e.accessID);
         });
     }
+}
+
+bool CartesianEmitter::levelsIndependent() const {
+  for(auto const& st : inst_.stencils)
+    for(auto const& ms : st.multiStages) {
+      if(ms.loopOrder != LoopOrder::Parallel)
+        return false;
+      for(auto const& stage : ms.stages)
+        for(auto const& dm : stage.doMethods) {
+          if(dm.interval.lowerBound() != 0 || dm.interval.upperBound() != Interval::End)
+            return false;
+          bool ok = true;
+          analysis::visitStmts(dm.stmts, [&](const Expr& e, bool) {
+            if(e.kind == Expr::Field && e.dk != 0)
+              ok = false;
+          });
+          if(!ok)
+            return false;
+        }
+    }
+  return true;
 }
 
 // Fields a multistage writes unconditionally on every level [Start, End].
@@ -2727,11 +2749,119 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
   os_ << "\n  template <typename S>\n  void sync_storages(S field) { field.sync(); }\n";
   os_ << "  template <typename S0, typename... S>\n  void sync_storages(S0 f0, S... fields) {\n"
          "    f0.sync();\n    sync_storages(fields...);\n  }\n\n";
+  // ---- host <-> device pipeline of run() (the reference's run() is sync - kernel - sync with whole
+  // storages, CudaCodeGen.cpp:435-450): when the levels are independent, a run() whose inputs are newer on the
+  // host streams the domain through the device in chunks of levels on three streams - uploads, kernels and
+  // downloads of different chunks overlap (PCIe is full duplex) - and leaves every storage coherent
+  bool pipelined = inst_.stencils.size() == 1 && inst_.allocatedFieldIDs.empty() && levelsIndependent() &&
+                   !inst_.apiFieldIDs.empty();
+  if(pipelined) {
+    for(int f : inst_.apiFieldIDs) {
+      MaskClass m = maskOf(f);
+      if(m.k && !(m.i && m.j))
+        pipelined = false; // k-only / ik / jk fields: keep the plain path
+    }
+    if(stencilArgs(inst_.stencils[0], plans[0]) != inst_.apiFieldIDs)
+      pipelined = false;
+  }
+  if(pipelined) {
+    const std::string sid = std::to_string(inst_.stencils[0].id);
+    os_ << "  int m_pipe_levels = 0;\n  void* m_pipe_up = nullptr;\n  void* m_pipe_dn = nullptr;\n";
+    os_ << "  std::vector<void*> m_pipe_events;\n";
+    os_ << "  std::map<int, std::unique_ptr<stencil_" << sid << ">> m_pipe_inst; // one per chunk height\n";
+    os_ << "  // levels per chunk of the host <-> device pipeline of run(); 0 (default) = whole storages\n";
+    os_ << "  void set_host_pipeline(int levels) { m_pipe_levels = levels; }\n";
+    os_ << "  void* pipe_event(size_t n) {\n    while(m_pipe_events.size() <= n) {\n      void* e = nullptr;\n"
+           "      ::dawn_b200::check(b200rt_event_create(&e));\n      m_pipe_events.push_back(e);\n    }\n"
+           "    return m_pipe_events[n];\n  }\n";
+    os_ << "  void run_pipelined(";
+    for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a)
+      os_ << (a ? ", " : "") << storageType(inst_.apiFieldIDs[a]) << " " << fname(inst_.apiFieldIDs[a]);
+    os_ << ") {\n";
+    os_ << "    const gridtools::dawn::domain& dom = m_stencil_" << sid << ".m_dom;\n";
+    os_ << "    void* compute = m_stencil_" << sid << ".stream();\n";
+    os_ << "    if(!m_pipe_up) ::dawn_b200::check(b200rt_stream_create(&m_pipe_up));\n";
+    os_ << "    if(!m_pipe_dn) ::dawn_b200::check(b200rt_stream_create(&m_pipe_dn));\n";
+    os_ << "    const int kfirst = (int)dom.kminus(), nz = (int)(dom.ksize() - dom.kminus() - dom.kplus());\n";
+    // which fields are written (download) - by name over all kernels
+    std::set<int> writtenApi;
+    for(auto const& kp : plans[0])
+      for(int f : kp.fieldsWritten)
+        writtenApi.insert(f);
+    size_t nf = inst_.apiFieldIDs.size();
+    os_ << "    bool up[" << nf << "];\n";
+    for(size_t a = 0; a < nf; ++a)
+      os_ << "    up[" << a << "] = " << fname(inst_.apiFieldIDs[a]) << ".host_is_newer();\n";
+    os_ << "    // fields without a k dimension travel whole, ahead of the first chunk\n";
+    for(size_t a = 0; a < nf; ++a)
+      if(!maskOf(inst_.apiFieldIDs[a]).k)
+        os_ << "    if(up[" << a << "]) " << fname(inst_.apiFieldIDs[a]) << ".upload_levels(0, 1, m_pipe_up);\n";
+    os_ << "    size_t ev = 0;\n";
+    os_ << "    for(int k0 = 0; k0 < nz; k0 += m_pipe_levels) {\n";
+    os_ << "      const int kc = nz - k0 < m_pipe_levels ? nz - k0 : m_pipe_levels;\n";
+    os_ << "      const bool firstChunk = k0 == 0, lastChunk = k0 + kc >= nz;\n";
+    for(size_t a = 0; a < nf; ++a)
+      if(maskOf(inst_.apiFieldIDs[a]).k) {
+        const std::string n = fname(inst_.apiFieldIDs[a]);
+        os_ << "      if(up[" << a << "]) " << n << ".upload_levels(firstChunk ? 0 : kfirst + k0, lastChunk ? (int)"
+            << n << ".get_storage_info_ptr()->template total_length<2>() : kfirst + k0 + kc, m_pipe_up);\n";
+      }
+    os_ << "      void* e_up = pipe_event(ev++);\n";
+    os_ << "      ::dawn_b200::check(b200rt_event_record(e_up, m_pipe_up));\n";
+    os_ << "      ::dawn_b200::check(b200rt_stream_wait_event(compute, e_up));\n";
+    os_ << "      auto& inst = m_pipe_inst[kc];\n";
+    os_ << "      if(!inst) {\n        gridtools::dawn::domain d(dom.isize(), dom.jsize(), kc);\n"
+           "        d.set_halos(dom.iminus(), dom.iplus(), dom.jminus(), dom.jplus(), 0, 0);\n"
+           "        inst.reset(new stencil_" << sid << "(d, " << (hasGlobals ? "m_globals, " : "") << "1, 1, 1));\n      }\n";
+    os_ << "      inst->set_stream(compute);\n";
+    os_ << "      b200_field_t f[" << nf << "];\n";
+    for(size_t a = 0; a < nf; ++a) {
+      const std::string n = fname(inst_.apiFieldIDs[a]);
+      os_ << "      f[" << a << "] = " << n << ".device_descriptor_no_upload();\n";
+      if(maskOf(inst_.apiFieldIDs[a]).k)
+        os_ << "      f[" << a << "].data = static_cast<::dawn::float_type*>(f[" << a << "].data) + (size_t)(kfirst + k0) * f["
+            << a << "].stride_k;\n";
+    }
+    os_ << "      if(inst->launch(f, compute)) ::dawn_b200::throw_last_error();\n";
+    os_ << "      m_stencil_" << sid << ".m_launches += inst->m_launches; inst->m_launches = 0;\n";
+    os_ << "      void* e_run = pipe_event(ev++);\n";
+    os_ << "      ::dawn_b200::check(b200rt_event_record(e_run, compute));\n";
+    os_ << "      ::dawn_b200::check(b200rt_stream_wait_event(m_pipe_dn, e_run));\n";
+    for(size_t a = 0; a < nf; ++a)
+      if(writtenApi.count(inst_.apiFieldIDs[a]) && maskOf(inst_.apiFieldIDs[a]).k)
+        os_ << "      " << fname(inst_.apiFieldIDs[a]) << ".download_levels(kfirst + k0, kfirst + k0 + kc, m_pipe_dn);\n";
+    os_ << "    }\n";
+    os_ << "    ::dawn_b200::check(b200rt_stream_synchronize(m_pipe_dn));\n";
+    os_ << "    ::dawn_b200::check(b200rt_stream_synchronize(compute));\n";
+    os_ << "    ::dawn_b200::check(b200rt_stream_synchronize(m_pipe_up));\n";
+    for(size_t a = 0; a < nf; ++a)
+      if(writtenApi.count(inst_.apiFieldIDs[a]) && !maskOf(inst_.apiFieldIDs[a]).k)
+        os_ << "    " << fname(inst_.apiFieldIDs[a]) << ".mark_device_dirty(compute); // no k dimension: synced below\n";
+      else
+        os_ << "    " << fname(inst_.apiFieldIDs[a]) << ".mark_coherent(compute);\n";
+    os_ << "  }\n\n";
+  }
   // run(): API fields in order
   os_ << "  void run(";
   for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a)
     os_ << (a ? ", " : "") << storageType(inst_.apiFieldIDs[a]) << " " << fname(inst_.apiFieldIDs[a]);
   os_ << ") {\n";
+  if(pipelined) {
+    os_ << "    if(m_pipe_levels > 0 && (";
+    for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a)
+      os_ << (a ? " || " : "") << fname(inst_.apiFieldIDs[a]) << ".host_is_newer()";
+    os_ << ")) {\n      run_pipelined(";
+    for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a)
+      os_ << (a ? ", " : "") << fname(inst_.apiFieldIDs[a]);
+    os_ << ");\n";
+    if(opt_.RunWithSync) {
+      os_ << "      sync_storages(";
+      for(size_t a = 0; a < inst_.apiFieldIDs.size(); ++a)
+        os_ << (a ? ", " : "") << fname(inst_.apiFieldIDs[a]);
+      os_ << ");\n";
+    }
+    os_ << "      return;\n    }\n";
+  }
   emitControlFlow(plans, [&](size_t sidx, const std::string& pad) {
     auto sargs = stencilArgs(inst_.stencils[sidx], plans[sidx]);
     os_ << pad << "m_stencil_" << inst_.stencils[sidx].id << ".run(";

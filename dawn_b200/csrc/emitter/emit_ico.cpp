@@ -177,6 +177,7 @@ class IcoEmitter {
   const Options& opt_;
   std::ostringstream os_;
   std::set<int> registerOnly_; // temporaries that never leave their kernel group
+  std::set<std::pair<const Group*, int>> laterReads_; // (launching group, field) read by a later group of the stencil
   std::set<int> scratch_;      // temporaries that need storage
   int block_, lpt_;
 
@@ -951,6 +952,21 @@ void IcoEmitter::emitKernel(const Group& g, const Group* partner, const Group* c
   os_ << ") {\n";
   os_ << "  (void)n_cells; (void)n_edges; (void)n_vertices;\n";
   RoleOpts plain;
+  if(opt_.IcoCacheHints && !consumer) {
+    std::set<int> gathered;
+    for(auto const* r : roles)
+      for(auto const* stg : r->stages)
+        forEachAccess(*stg, [&](const Expr& e, int nest, bool) {
+          if(nest > 0 && (e.hasOffset || nest > 1 || fieldLoc(e.accessID) != r->loc))
+            gathered.insert(e.accessID);
+        });
+    for(int f : args)
+      if(!written.count(f) && !gathered.count(f) && !isVertical(f) && hasK(f))
+        plain.streamOnce.insert(f);
+    for(int f : written)
+      if(!laterReads_.count({&g, f}) && !isVertical(f))
+        plain.storeStream.insert(f);
+  }
   if(!consumer) {
     if(!partner) {
       emitRole(g, "blockIdx.x", "elem_lo", "elem_hi", plain);
@@ -1343,6 +1359,16 @@ std::string IcoEmitter::generate() {
   auto groups = plan(inst_.stencils[0]);
   planCoScheduling(groups);
   planChains(groups);
+  for(size_t a = 0; a < groups.size(); ++a)   // which results of a launch does a later launch read again?
+    for(size_t b = a + 1; b < groups.size(); ++b) {
+      if(b == (size_t)groups[a].coWith || (groups[a].coMember && b == a))
+        continue;
+      for(int f : groups[b].fieldsRead) {
+        laterReads_.insert({&groups[a], f});
+        if(a > 0 && groups[a].coMember)
+          laterReads_.insert({&groups[a - 1], f}); // the launch of a co-scheduled pair belongs to its first group
+      }
+    }
   for(auto const& g : groups) {
     if(g.coMember || g.chainMember)
       continue;

@@ -114,6 +114,10 @@ int b200rt_stream_synchronize(void* s) {
   CK(cudaStreamSynchronize(S(s)));
   return 0;
 }
+int b200rt_stream_wait_event(void* s, void* e) {
+  CK(cudaStreamWaitEvent(S(s), static_cast<cudaEvent_t>(e), 0));
+  return 0;
+}
 int b200rt_event_create(void** e) {
   cudaEvent_t ev;
   CK(cudaEventCreate(&ev));

@@ -6,7 +6,10 @@
 #pragma once
 #include <cassert>
 #include <exception>
+#include <map>
+#include <memory>
 #include <string>
+#include <vector>
 #include "defs.hpp"
 #include "domain.hpp"
 #include "extent.hpp"

@@ -168,6 +168,42 @@ public:
                         info_->template stride<2>()};
   }
   T* device_ptr() const { return static_cast<T*>(device_descriptor().data); }
+
+  // ---- pieces of the host <-> device pipeline of generated run() methods (set_host_pipeline): levels
+  // [k0, k1) of a field with a k dimension are one contiguous range (k is the slowest dimension); fields
+  // without one travel whole.  All copies are asynchronous on `stream`; the caller orders and waits.
+  bool host_is_newer() const { return buf_ && (buf_->host_dirty || !buf_->dev); }
+  b200_field_t device_descriptor_no_upload() const {
+    ensure_device();
+    return b200_field_t{buf_->dev + info_->lead(), info_->template stride<1>(), info_->template stride<2>()};
+  }
+  void level_range(int k0, int k1, size_t& first, size_t& count) const {
+    if(Info::has_k) {
+      const size_t sk = (size_t)info_->template stride<2>();
+      first = (size_t)info_->lead() + (size_t)k0 * sk, count = (size_t)(k1 - k0) * sk;
+      if(k0 == 0)
+        first = 0, count += (size_t)info_->lead(); // the lead pad travels with the first level
+    } else
+      first = 0, count = buf_->elems;
+    if(first + count > buf_->elems)
+      count = buf_->elems - first;
+  }
+  void upload_levels(int k0, int k1, void* stream) const {
+    ensure_device();
+    size_t first, count;
+    level_range(k0, k1, first, count);
+    ::dawn_b200::check(b200rt_memcpy_h2d(buf_->dev + first, buf_->host + first, count * sizeof(T), stream));
+  }
+  void download_levels(int k0, int k1, void* stream) const {
+    size_t first, count;
+    level_range(k0, k1, first, count);
+    ::dawn_b200::check(b200rt_memcpy_d2h(buf_->host + first, buf_->dev + first, count * sizeof(T), stream));
+  }
+  // both copies hold the same data (after the pipeline has moved every level); `stream` = last device producer
+  void mark_coherent(void* stream) const {
+    buf_->host_dirty = buf_->dev_dirty = false;
+    buf_->stream = stream;
+  }
   // a kernel on `stream` writes the device copy
   void mark_device_dirty(void* stream = nullptr) const {
     buf_->dev_dirty = true;

@@ -34,7 +34,7 @@ SYMBOLS = [
     "b200rt_event_record", "b200rt_event_synchronize", "b200rt_event_elapsed_ms",
     "b200rt_check_last_launch", "b200rt_tensor_map_3d", "b200rt_tensor_map_3d_es", "b200rt_verify_field", "b200rt_verify_field_f32",
     "b200rt_reshape", "b200rt_reshape_back", "b200rt_reshape_f32", "b200rt_reshape_back_f32",
-    "b200rt_chain_plan_create", "b200rt_chain_plan_view", "b200rt_chain_plan_next_epoch", "b200rt_chain_plan_status",
+    "b200rt_stream_wait_event", "b200rt_chain_plan_create", "b200rt_chain_plan_view", "b200rt_chain_plan_next_epoch", "b200rt_chain_plan_status",
     "b200rt_chain_plan_destroy",
     "b200rt_upload_nbh_table", "b200rt_nccl_unique_id", "b200rt_comm_init_rank",
     "b200rt_comm_destroy", "b200rt_halo_plan_create", "b200rt_halo_plan_create2",

@@ -69,6 +69,10 @@ typedef struct dawn_b200_options {
                              backward (L2-fed) sweeps interleave; -1: N from $DAWN_B200_STAGGER_NS (probing) */
   int ico_full_blocks;    /* default 0: unstructured kernels run full blocks of levels through an unrolled
                              loop without per-level bound checks (more loads in flight per thread) */
+  int ico_cache_hints;    /* unstructured kernels: fields that every stage of a launch reads at its own element only
+                             (each value is needed once) are loaded evict-first (ld.global.cs) and results no later
+                             launch reads are stored streaming (st.global.cs), so that the GATHERED fields keep
+                             their lines in L2 for the neighbours that come back to them */
   int ico_chain;          /* default 0; 1: an unstructured launch whose results the NEXT launch gathers through a chain
                              (ICON nabla2: rot_vec / div_vec of the vertex + cell launch, read by the edge launch)
                              is fused with it into ONE launch: blocks follow a host-built schedule in which every

@@ -70,6 +70,7 @@ int b200rt_event_create(void** event);
 int b200rt_event_destroy(void* event);
 int b200rt_event_record(void* event, void* stream);
 int b200rt_event_synchronize(void* event);
+int b200rt_stream_wait_event(void* stream, void* event); /* later work of `stream` waits for `event` */
 int b200rt_event_elapsed_ms(void* start, void* stop, float* ms);
 int b200rt_check_last_launch(void); /* cudaGetLastError -> B200_ERR_CUDA */
 

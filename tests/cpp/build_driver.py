@@ -30,5 +30,22 @@ def build_cpp_driver(force=False):
     return exe
 
 
+def build_e2e_driver(force=False):
+    """tests/cpp/hori_diff_e2e.cu: the end-to-end benchmark through the generated C++ class (bench.py's e2e leg)."""
+    src = os.path.join(HERE, "hori_diff_e2e.cu")
+    exe = os.path.join(_b.LIB, "hori_diff_e2e")
+    gen = os.path.join(_b.GEN, "hori_diff_type2_stencil.cu")
+    build_cpp_driver()      # makes sure the generated file and liboracle.so exist
+    oracle_so = os.path.join(ROOT, "oracle", "liboracle.so")
+    hdrs = [os.path.join(_b.PKG, "driver-includes", h) for h in os.listdir(os.path.join(_b.PKG, "driver-includes"))]
+    if force or _b._newer(exe, [src, gen, oracle_so] + hdrs):
+        _b._run([_b.NVCC] + _b.ARCH + ["-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-cudart", "shared",
+                                      "-I", _b.PKG, '-DGENERATED_FILE="%s"' % gen, "-o", exe, src,
+                                      "-L", _b.LIB, "-ldawn_b200rt", "-Xlinker", "-rpath,$ORIGIN",
+                                      oracle_so, "-Xlinker", "-rpath," + os.path.join(ROOT, "oracle")])
+    return exe
+
+
 if __name__ == "__main__":
     print(build_cpp_driver())
+    print(build_e2e_driver())

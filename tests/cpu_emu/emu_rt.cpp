@@ -74,6 +74,7 @@ int b200rt_event_destroy(void* e) {
   return 0;
 }
 int b200rt_event_record(void*, void*) { return 0; }
+int b200rt_stream_wait_event(void*, void*) { return 0; }
 int b200rt_event_synchronize(void*) { return 0; }
 int b200rt_event_elapsed_ms(void*, void*, float* ms) {
   *ms = 0.f;

@@ -1,7 +1,7 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-for o in "levels_per_thread=4 ico_chain_lag=4096" "levels_per_thread=4 ico_chain_lag=2048" "block_size_ico=256 ico_chain_lag=1024" "block_size_ico=64 ico_chain_lag=4096" "levels_per_thread=4 ico_chain=0"; do
+for o in "" "ico_cache_hints=1" "ico_cache_hints=1 levels_per_thread=16"; do
   a=""; for kv in $o; do a="$a --opt $kv"; done
   timeout 300 python bench.py --workload icon_nabla2 --steps 10 --no-cpu-baseline --no-e2e $a > gpurun_out/icon_tmp.json 2> gpurun_out/icon_tmp.err
   python - "$o" <<'PY'
@@ -12,4 +12,4 @@ try:
 except Exception as e:
     print("icon_nabla2 [%s] FAILED" % sys.argv[1], e); print(open("gpurun_out/icon_tmp.err").read()[-800:])
 PY
-done | tee gpurun_out/r2_icon_chain3.log
+done | tee gpurun_out/r2_icon_hints.log
