@@ -239,7 +239,13 @@ def test_control_flow_of_the_description_is_emitted():
     assert "m_globals.var_compiletime != (int)1" in run
     plain = _code("hori_diff_type2_stencil")
     run = plain[plain.index("  void run(storage_ijk_t out, storage_ijk_t in, storage_j_t crlato"):]
-    assert "if(" not in run[:run.index("sync_storages(")]
+    run = run[:run.index("m_stencil_23.run(")]
+    # no control flow of the description; the only branch is the dispatch to the host <-> device pipeline
+    assert run.count("if(") == 1 and "if(m_pipe_levels > 0 && (out.host_is_newer()" in run
+    # the pipeline exists for stencils whose levels are independent, and only for them
+    assert "void set_host_pipeline(int levels)" in plain and "run_pipelined(" in plain
+    assert "set_host_pipeline" not in _code("tridiagonal_solve")
+    assert "set_host_pipeline" not in code    # stencil_desc_ast_04: two stencil calls
 
 
 def test_pure_locals_are_substituted_into_inlined_temporaries():
