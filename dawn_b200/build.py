@@ -110,7 +110,8 @@ VARIANTS = {
     "copy_stencil": [dict(shared_temporaries=1)], "nonoverlapping_stencil": [dict(shared_temporaries=1)],
     "ICON_laplacian_stencil": [dict(fuse_columns=0, levels_per_thread=1), dict(levels_per_thread=8),
                                dict(co_schedule=0), dict(ico_chain=1), dict(ico_chain=1, co_schedule=0),
-                               dict(ico_chain=1, ico_chain_lag=1), dict(ico_chain=1, ico_chain_lag=100000)],
+                               dict(ico_chain=1, ico_chain_lag=1), dict(ico_chain=1, ico_chain_lag=100000),
+                               dict(ico_chain=1, ico_chain_l1=1), dict(ico_chain=1, ico_cache_hints=1)],
     "ICON_nabla4_stencil": [dict(fuse_columns=0, levels_per_thread=1), dict(co_schedule=0), dict(ico_chain=1)],
     "overwriteGathered": [dict(ico_chain=1)],
     **{"fuzzico_%02d" % n: [dict(ico_chain=1)] for n in range(16, 20)},

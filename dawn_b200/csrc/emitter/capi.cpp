@@ -37,6 +37,7 @@ b200::codegen::Options convert(const dawn_b200_options* o) {
   r.IcoFullBlocks = o->ico_full_blocks;
   r.IcoCacheHints = o->ico_cache_hints;
   r.IcoChain = o->ico_chain;
+  r.IcoChainL1 = o->ico_chain_l1;
   r.IcoChainLag = o->ico_chain_lag;
   r.RingProducer = o->ring_producer;
   r.SinglePrecision = o->single_precision;
@@ -67,6 +68,7 @@ void dawn_b200_default_options(dawn_b200_options* o) {
   o->ring_early = 1;
   o->ring_producer = 0;
   o->ico_chain = 0;
+  o->ico_chain_l1 = 0;
 }
 
 int dawn_b200_parse_backend(const char* s) {

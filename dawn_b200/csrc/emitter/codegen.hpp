@@ -56,6 +56,7 @@ struct Options {
   int IcoCacheHints = 0;   // unstructured: evict-first loads of read-once fields, streaming stores of final results
   int IcoChain = 0;        // 1: unstructured: fuse a launch with the next one that gathers its results (L2 hand-over;
                            // measured: less DRAM traffic but slower on B200, see dawn_b200_codegen.h)
+  int IcoChainL1 = 0;      // chained consumers: L1-cached hand-over reads behind a wait widened by one block each side
   int IcoChainLag = 0;     // schedule distance between a consumer block and its producers (0 = 2048 blocks)
   int RingProducer = 0;    // 1: column-ring kernels get a dedicated TMA producer warp instead of thread 0 +
                            // __syncthreads (measured slower in full waves on B200, see dawn_b200_codegen.h)

@@ -227,6 +227,7 @@ private:
     std::set<int> cg;                      // fields another role of the launch wrote: ld.global.cg
     std::set<int> streamOnce;              // read-only fields every role reads at its own element only: evict-first
     std::set<int> storeStream;             // written fields nobody in the launch reads again: st.global.cs
+    std::set<int> plainLoad;               // fields another role wrote, complete line-wise: ordinary (L1-cached) loads
   };
   void emitKernel(const Group& g, const Group* partner, const Group* consumer);
   void emitRole(const Group& g, const std::string& blockExpr, const std::string& lo,
@@ -401,7 +402,7 @@ public:
   std::map<int, std::string> forwarded; // field -> variable with its current value at (pidx, k)
   int uid = 0;
   // chained launches (IcoEmitter::RoleOpts): cache policy per field
-  std::set<int> cg, streamOnce, storeStream;
+  std::set<int> cg, streamOnce, storeStream, plainLoad;
 
   struct Ctx {
     std::string center = "pidx"; // index of the element the reduction runs on
@@ -487,6 +488,16 @@ public:
     std::string ref = fieldRef(e, c);
     if(cg.count(e.accessID))
       return "__ldcg(&" + ref + ")"; // written by another role of this launch: L2 is the point of coherence
+    if(plainLoad.count(e.accessID)) {
+      // same, but every line the block touches is complete, so L1 may keep it - except the lines at either end of
+      // a level, which a level of ANOTHER block of levels shares: those elements are always read through L2
+      auto const& d = dims(e.accessID);
+      if(d.isSparse() || d.chain.empty() || !d.maskK)
+        return "__ldcg(&" + ref + ")";
+      const std::string elem = atNeighbour(e, c) ? c.nbh : c.center;
+      return "::dawn_b200::chain::load(&" + fname(e.accessID) + "_p[(size_t)" + kexpr(e, c) + " * " +
+             stride(d.chain.front()) + "], " + elem + ", " + stride(d.chain.front()) + ")";
+    }
     if(!g.fieldsWritten.count(e.accessID))
       return (streamOnce.count(e.accessID) ? "__ldcs(&" : "__ldg(&") + ref + ")";
     return ref;
@@ -765,7 +776,7 @@ void IcoEmitter::emitRole(const Group& g, const std::string& blockExpr, const st
   IcoBody body{inst_, g, registerOnly_,
                [this](int id) { return fname(id); },
                [this](int id) -> const FieldDims& { return dims(id); },
-               [this](int id) { return sparseSize(id); }, {}, 0, ro.cg, ro.streamOnce, ro.storeStream};
+               [this](int id) { return sparseSize(id); }, {}, 0, ro.cg, ro.streamOnce, ro.storeStream, ro.plainLoad};
   for(auto const* st : g.stages) {
     bodyText << "    // stage " << st->id << "\n";
     for(auto const& dm : st->doMethods) {
@@ -1000,14 +1011,24 @@ void IcoEmitter::emitKernel(const Group& g, const Group* partner, const Group* c
         if(nest > 0 && (e.hasOffset || nest > 1 || fieldLoc(e.accessID) != r->loc))
           gathered.insert(e.accessID);
       });
-  for(int f : args)
-    if(!written.count(f) && !gathered.count(f) && !isVertical(f) && hasK(f))
-      prod.streamOnce.insert(f), cons.streamOnce.insert(f);
-  for(int f : consumer->fieldsWritten)
-    cons.storeStream.insert(f);
+  if(opt_.IcoCacheHints) {
+    for(int f : args)
+      if(!written.count(f) && !gathered.count(f) && !isVertical(f) && hasK(f))
+        prod.streamOnce.insert(f), cons.streamOnce.insert(f);
+    for(int f : consumer->fieldsWritten)
+      cons.storeStream.insert(f);
+  }
+  // hand-over reads.  ico_chain_l1=0: ld.global.cg (L2 is the point of coherence).  Default: ordinary loads
+  // that may stay in L1 - safe because the consumer also waits for the producer block on either side of its
+  // range, so every 128-byte line it touches holds final values only (a line spans at most two neighbouring
+  // producer blocks; the handed-over fields are written once per launch and L1 does not outlive a launch)
   for(int f : consumer->fieldsRead)
-    if(producedSet.count(f))
-      cons.cg.insert(f);
+    if(producedSet.count(f)) {
+      if(opt_.IcoChainL1)
+        cons.plainLoad.insert(f);
+      else
+        cons.cg.insert(f);
+    }
   os_ << "  const unsigned lb = blockIdx.x / cv.sched_len;   // block of levels\n";
   os_ << "  const unsigned item = __ldg(&cv.sched[blockIdx.x - lb * cv.sched_len]);\n";
   os_ << "  const unsigned role = item >> 30, bidx = item & 0x3fffffffu;\n";
@@ -1022,8 +1043,13 @@ void IcoEmitter::emitKernel(const Group& g, const Group* partner, const Group* c
   }
   os_ << "  } else {\n";
   os_ << "    // wait for the producer blocks this block's elements reach through the neighbour tables\n";
-  os_ << "    const int lo0 = __ldg(&cv.need[4 * bidx]), hi0 = __ldg(&cv.need[4 * bidx + 1]);\n";
-  os_ << "    const int lo1 = __ldg(&cv.need[4 * bidx + 2]), hi1 = __ldg(&cv.need[4 * bidx + 3]);\n";
+  os_ << "    int lo0 = __ldg(&cv.need[4 * bidx]), hi0 = __ldg(&cv.need[4 * bidx + 1]);\n";
+  os_ << "    int lo1 = __ldg(&cv.need[4 * bidx + 2]), hi1 = __ldg(&cv.need[4 * bidx + 3]);\n";
+  if(opt_.IcoChainL1) {
+    os_ << "    // one more producer block on either side: whole cache lines are final (the schedule allows for it)\n";
+    os_ << "    if(hi0 > lo0) { lo0 = lo0 > 0 ? lo0 - 1 : 0; hi0 = hi0 < (int)cv.nb0 ? hi0 + 1 : (int)cv.nb0; }\n";
+    os_ << "    if(hi1 > lo1) { lo1 = lo1 > 0 ? lo1 - 1 : 0; hi1 = hi1 < (int)cv.nb1 ? hi1 + 1 : (int)cv.nb1; }\n";
+  }
   os_ << "    for(int q = lo0 + (int)threadIdx.x; q < hi0; q += " << block_ << ")\n"
       << "      ::dawn_b200::chain::wait(&flags[q], epoch, cv.error);\n";
   os_ << "    for(int q = lo1 + (int)threadIdx.x; q < hi1; q += " << block_ << ")\n"

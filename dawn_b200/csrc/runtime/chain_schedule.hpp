@@ -70,7 +70,9 @@ inline ChainSchedule buildChainSchedule(int n_consumer, int block, int n_roles, 
   for(unsigned c = 0; c < s.nc; ++c) {
     unsigned target[2];
     for(int r = 0; r < 2; ++r) {
-      runmax[r] = std::max(runmax[r], (unsigned)s.need[c * 4 + 2 * r + 1]);
+      // + 1: a consumer may also wait for the producer block after its range (whole cache lines final)
+      if(s.need[c * 4 + 2 * r + 1] > s.need[c * 4 + 2 * r])
+        runmax[r] = std::max(runmax[r], std::min(s.nb[r], (unsigned)s.need[c * 4 + 2 * r + 1] + 1u));
       const unsigned share = tot ? (unsigned)((unsigned long long)lag * s.nb[r] / tot) : 0u;
       target[r] = std::min(s.nb[r], runmax[r] + (runmax[r] ? share : 0u));
     }

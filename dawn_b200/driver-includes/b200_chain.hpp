@@ -26,6 +26,15 @@ __device__ __forceinline__ void wait(const unsigned* flag, unsigned epoch, unsig
   *error = 1u;
 }
 
+// element `idx` of one level (`n` elements from `level`) of a handed-over field: an ordinary load that may stay in
+// L1 - every line the consumer touches holds final values (its wait covers the neighbouring producer blocks) -
+// except within a line's length of either end of the level, where the line is shared with a level that another
+// block of levels produces (later, or earlier in a previous life of the line): those always come from L2
+template <class T>
+__device__ __forceinline__ T load(const T* level, int idx, int n) {
+  return (idx >= 32 && idx < n - 32) ? level[idx] : __ldcg(level + idx);
+}
+
 } // namespace chain
 } // namespace dawn_b200
 #else
@@ -41,6 +50,8 @@ inline void wait(const unsigned* flag, unsigned epoch, unsigned* error) {
   if(reinterpret_cast<const std::atomic<unsigned>*>(flag)->load(std::memory_order_acquire) != epoch)
     *error = 1u;
 }
+template <class T>
+inline T load(const T* level, int idx, int) { return level[idx]; }
 } // namespace chain
 } // namespace dawn_b200
 template <class T>

@@ -84,6 +84,10 @@ typedef struct dawn_b200_options {
                              rot_vec / div_vec is gone, 1.10 x the algorithmic bytes), but the three roles mixed
                              in one launch reach only 61 % DRAM throughput against ~80 % of the two separate
                              launches: 23.2 ms against 20.7 ms.  Bit-exact, tested, off by default */
+  int ico_chain_l1;       /* default 0: chained consumers read the handed-over fields with ld.global.cg; 1: ordinary
+                             (L1-cached) loads behind a wait widened by one producer block on either side, so
+                             that every cache line they touch is final (the ends of a level, shared with other
+                             blocks of levels, still go through L2).  Measured slower: 28.3 against 24.6 ms */
   int ico_chain_lag;      /* producer blocks between a consumer block and the last producer it needs (0 = 2048:
                              below the ~1600 producer blocks of one residency generation - 148 SMs x 16 blocks -
                              consumers are dispatched before their producers finish and spin in their slots:

@@ -167,7 +167,12 @@ def test_icon_laplacian_plan_fuses_edge_stages():
     assert len(heads) == 1 and "chained with 5 stage(s) on edges" in heads[0]
     assert "chain::publish(&flags[bidx], epoch)" in code and "chain::wait(&flags[q], epoch, cv.error)" in code
     assert "__ldcg(&rot_vec_p[" in code and "__ldcg(&div_vec_p[" in code and "__ldg(&rot_vec_p[" not in code
-    assert "__ldcs(&geofac_rot_p[" in code and "__stcs(&nabla2_vec_p[" in code and "__ldg(&vec_p[" in code
+    l1 = _code("ICON_laplacian_stencil", backend="b200-ico", ico_chain=1, ico_chain_l1=1)
+    assert "chain::load(&rot_vec_p[" in l1 and "chain::load(&div_vec_p[" in l1
+    assert "if(hi0 > lo0) { lo0 = lo0 > 0 ? lo0 - 1 : 0;" in l1      # whole cache lines final: L1 may keep them
+    exact = _code("ICON_laplacian_stencil", backend="b200-ico", ico_chain=1, ico_cache_hints=1)
+    assert "__ldcg(&rot_vec_p[" in exact and "__ldcg(&div_vec_p[" in exact and "lo0 - 1" not in exact
+    assert "__ldcs(&geofac_rot_p[" in exact and "__stcs(&nabla2_vec_p[" in exact and "__ldg(&vec_p[" in exact
     assert "__tmp_nab_60_p" not in code and "scratch_field" not in code  # temporaries stay in registers
     assert "setup_ICON_laplacian_stencil(void** handle, const b200_mesh_t* mesh, int k_size" in code
     unfused = _code("ICON_laplacian_stencil", backend="b200-ico", fuse_columns=0, co_schedule=0)

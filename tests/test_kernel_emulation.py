@@ -108,7 +108,8 @@ def test_emitted_kernels_match_the_oracle_on_the_cpu(name):
 
 @pytest.mark.parametrize("opts", [dict(fuse_columns=0, levels_per_thread=1), dict(co_schedule=0),
                                   dict(levels_per_thread=3), dict(ico_chain=1), dict(ico_chain=1, ico_chain_lag=1),
-                                  dict(ico_chain=1, ico_chain_lag=100000, co_schedule=0)])
+                                  dict(ico_chain=1, ico_chain_lag=100000, co_schedule=0),
+                                  dict(ico_chain=1, ico_chain_l1=1), dict(ico_chain=1, ico_cache_hints=1)])
 @pytest.mark.parametrize("name", ["ICON_laplacian_stencil", "ICON_nabla4_stencil", "ICON_laplacian_diamond_stencil",
                                   "fuzzico_03", "fuzzico_11", "fuzzico_16", "fuzzico_17", "fuzzico_18", "fuzzico_19",
                                   "overwriteGathered", "sparseAssignment5", "nestedWithSparse"])

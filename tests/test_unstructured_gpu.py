@@ -75,7 +75,8 @@ def _check(got, want, m, names):
 @pytest.mark.parametrize("opts", [dict(), dict(fuse_columns=0, levels_per_thread=1),
                                   dict(levels_per_thread=8), dict(co_schedule=0), dict(ico_chain=1),
                                   dict(ico_chain=1, co_schedule=0), dict(ico_chain=1, ico_chain_lag=1),
-                                  dict(ico_chain=1, ico_chain_lag=100000)])
+                                  dict(ico_chain=1, ico_chain_lag=100000), dict(ico_chain=1, ico_chain_l1=1),
+                                  dict(ico_chain=1, ico_cache_hints=1)])
 def test_icon_laplacian(nx, ny, k, opts):
     m = TriMesh(nx, ny)
     rng = np.random.default_rng(31)
