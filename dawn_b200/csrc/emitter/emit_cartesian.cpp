@@ -555,26 +555,48 @@ std::set<int> CartesianEmitter::streamedFields(const KernelPlan& kp, const Multi
 }
 
 bool CartesianEmitter::planColumnRing(KernelPlan& kp) const {
-  kp.ringKB = opt_.RingLevels > 0 ? opt_.RingLevels : 8;
   std::set<int> fields;
   int maxFields = 0;
-  for(auto const* ms : kp.ms) {
-    auto depths = ringDepths(*ms);
-    for(auto const& part : analysis::partition(*ms)) {
-      auto sf = streamedFields(kp, *ms, part, depths);
-      fields.insert(sf.begin(), sf.end());
-      maxFields = std::max(maxFields, (int)sf.size());
+  auto collect = [&]() {
+    fields.clear();
+    maxFields = 0;
+    for(auto const* ms : kp.ms) {
+      auto depths = ringDepths(*ms);
+      for(auto const& part : analysis::partition(*ms)) {
+        auto sf = streamedFields(kp, *ms, part, depths);
+        fields.insert(sf.begin(), sf.end());
+        maxFields = std::max(maxFields, (int)sf.size());
+      }
     }
-  }
+  };
+  kp.ringKB = opt_.RingLevels > 0 ? opt_.RingLevels : 8;
+  collect();
   if(fields.empty())
     return false;
+  // Ring shape (round 2, A/B on B200, tridiagonal_solve with 4 streamed fields): 16 levels x 2 slots against 8 x 4,
+  // the same 64 KB per block: 84.3 % against 81.9 % of the HBM peak at 512^2 x 80, 91.9 % against 90.7 % at
+  // 1024^2 x 80 (half as many chunk boundaries - barrier wait, drain, block barrier, TMA issue - per column; 12 x 3:
+  // 84.6 % / 90.0 %).  A drained slot lives in registers (fields x levels doubles per thread), so the slot
+  // is 16 levels deep only while that stays within 64 values.
+  bool deepSlots = false;
+  if(opt_.RingLevels <= 0 && opt_.RingDrain != 0 && opt_.TmaStages <= 0 && maxFields * 16 <= 64) {
+    const int keepKB = kp.ringKB;
+    const std::set<int> keepFields = fields;
+    const int keepMax = maxFields;
+    kp.ringKB = 16;
+    collect(); // ranges shorter than two slots are not streamed: the set may shrink
+    if(fields.empty() || maxFields * 16 > 64)
+      kp.ringKB = keepKB, fields = keepFields, maxFields = keepMax;
+    else
+      deepSlots = true;
+  }
   kp.colring = true;
   kp.ringFields.assign(fields.begin(), fields.end());
   kp.ringMaxFields = maxFields;
   // measured on B200 (tridiagonal 512x512x80): 64x1 threads, 8 levels/slot; 3 slots refilled after the
   // sweep of a slot -> 77 % of the measured HBM peak, slots drained into registers on arrival and
   // refilled at once -> 80 % with 3 slots, 81 % with 4 (3 blocks per SM)
-  kp.stages = opt_.TmaStages > 0 ? opt_.TmaStages : (opt_.RingDrain ? 4 : 3);
+  kp.stages = opt_.TmaStages > 0 ? opt_.TmaStages : deepSlots ? 2 : (opt_.RingDrain ? 4 : 3);
   kp.TI = opt_.BlockSizeI > 0 ? opt_.BlockSizeI : 64;
   kp.TJ = opt_.BlockSizeJ > 0 ? opt_.BlockSizeJ : 1;
   // the producer warp needs the drain order (a slot is free as soon as it has been copied to registers),

@@ -406,14 +406,14 @@ def test_column_ring_issues_its_first_prologue_at_kernel_start():
     early = body.index("TMA prologue of k range [kmin + 1, kmax + 0], ahead of the ranges before it")
     assert early < body.index("{ // k in [kmin + 0, kmin + 0]") < body.index("{ // k in [kmin + 1, kmax + 0]")
     fwd = body[:body.index("(Backward)")]
-    assert fwd.count("for(int c = 0; c < 4 && c < nch; ++c)") == 1
+    assert fwd.count("for(int c = 0; c < 2 && c < nch; ++c)") == 1     # 2 slots of 16 levels (planner default)
     assert "prologue already issued at the top of the sweep" in fwd
     # the backward sweep streams what the forward sweep stored: its prologue stays behind the proxy fence
     bwd = body[body.index("(Backward)"):]
-    assert bwd.index("fence_proxy_async") < bwd.index("for(int c = 0; c < 4 && c < nch; ++c)")
+    assert bwd.index("fence_proxy_async") < bwd.index("for(int c = 0; c < 2 && c < nch; ++c)")
     old = _ring_kernel(_code("tridiagonal_solve", ring_early=0))
     assert "ahead of the ranges before it" not in old
-    assert old.index("{ // k in [kmin + 0, kmin + 0]") < old.index("for(int c = 0; c < 4 && c < nch; ++c)")
+    assert old.index("{ // k in [kmin + 0, kmin + 0]") < old.index("for(int c = 0; c < 2 && c < nch; ++c)")
 
 
 def test_ring_stagger_is_off_by_default():
