@@ -216,8 +216,11 @@ def run_gpu(args):
     # synthetic inputs: fillMath closed form of the reference drivers, generated on the device for
     # this rank's slab of the global domain (global j offset = rank * J)
     stor = {}
+    es = 4 if mod.dtype == "float32" else 8      # ::dawn::float_type of the module (--opt single_precision=1)
+    if es == 4 and world > 1:
+        raise SystemExit("single precision is a 1-GPU bench line: the halo plans of the runtime move doubles")
     for fd in mod.fields:
-        stor[fd["name"]] = dawn_b200.Storage(ni, nj, K + 1, fd["dims"])
+        stor[fd["name"]] = dawn_b200.Storage(ni, nj, K + 1, fd["dims"], dtype=mod.dtype)
     from util import FILL
     keymap = {"in": "u", "out": None}
 
@@ -399,7 +402,7 @@ def run_gpu(args):
     e2e_steps = min(args.steps, 5)
     from dawn_b200 import runtime as rt_
     with rt_.near_device(local) as near:  # pinned staging buffers on the GPU's own NUMA node
-        host = [torch.empty(s.shape[2], s.shape[1], s.shape[0], dtype=torch.float64).pin_memory()
+        host = [torch.empty(s.shape[2], s.shape[1], s.shape[0], dtype=s.dtype).pin_memory()
                 for s in fields]
     for h, s in zip(host, fields):
         h.copy_(s.view())
@@ -429,28 +432,28 @@ def run_gpu(args):
         e2e_cpp = cpp_class_e2e(I, J, K, e2e_steps)
     if rank == 0:
         peak, peak_src = measured_peak()
-        achieved = BYTES_PER_POINT[workload] * pts / (kernel_ms * 1e-3) / 1e9
+        bpp = BYTES_PER_POINT[workload] * es // 8
+        achieved = bpp * pts / (kernel_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % workload)
-        if os.path.exists(tp) and not args.shape:  # the committed ncu capture is of the default shape
+        if os.path.exists(tp) and not args.shape and es == 8:  # the committed ncu capture is of the default shape
             with open(tp) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
         line = {
             "metric": "grid-point updates/s", "value": pts * world * args.steps / (ms_max * 1e-3),
             "unit": "grid-point updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if es == 8 else "f32",
             "data": "synthetic (fillMath closed form of the reference drivers, generated on device)",
             "config": {
-                "workload": "%s %dx%dx%d double per GPU (halo 3, storages %dx%dx%d)%s" % (
-                    name, I, J, K, ni, nj, K + 1,
+                "workload": "%s %dx%dx%d %s per GPU (halo 3, storages %dx%dx%d)%s" % (
+                    name, I, J, K, "double" if es == 8 else "float", ni, nj, K + 1,
                     "" if world == 1 else ", global %dx%dx%d in %d j-slabs, %s halo exchange of "
                     "`in` (2 rows each way) every step, overlapped with the interior rows" % (
                         I, J * world, K, world,
                         "peer-memory (NVLink stores into the neighbour's landing buffer, device-side "
                         "flags)" if args.halo == "p2p" else "NCCL")),
-                "l2": "inputs larger than L2 (%.1f GB per step vs 126 MB), no flush" % (
-                    BYTES_PER_POINT[workload] * pts / 1e9),
+                "l2": "inputs larger than L2 (%.1f GB per step vs 126 MB), no flush" % (bpp * pts / 1e9),
                 "timing": "%d back-to-back steps = %.1f ms timed (%s); at N=1 roofline.achieved uses this "
                           "same region (a step is one kernel launch) - see clocks" % (
                               args.steps, ms_max,
@@ -465,8 +468,7 @@ def run_gpu(args):
                 "committed ncu capture profiles/traffic_%s.json (dram__bytes_read+write per launch), not "
                 "measured in this run" % workload,
                 "kernel": "%s (generated), %d launch(es)/step, %.4f ms/launch, %d algorithmic B/point"
-                          % (name, kernels_per_run, kernel_ms / max(1, kernels_per_run),
-                             BYTES_PER_POINT[workload]),
+                          % (name, kernels_per_run, kernel_ms / max(1, kernels_per_run), bpp),
                 "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
             },
             "e2e": {"value": pts * world * e2e_steps / e2e_s, "unit": "grid-point updates/s",
@@ -530,6 +532,15 @@ def parity_check(workload, mod, stor, fill_inputs, step, shape, rank, world, dep
     I, J, K = shape
     fill_inputs()
     names = [fd["name"] for fd in mod.fields]
+    single = mod.dtype == "float32"
+
+    def interp(fields, nk):
+        """single precision: the pinned interpreter on float32 storages (the C restatements are double)"""
+        from oracle import naive_interp
+        from util import iir_path
+        some = next(iter(fields.values()))
+        dims = (max(a.shape[2] for a in fields.values()), max(a.shape[1] for a in fields.values()), nk)
+        return naive_interp.run_cartesian(iir_path(mod.name), dims, fields, halos=(HALO,) * 4 + (0, 0))
     if workload == "hori_diff":
         planes = sorted({0, 1, 19, 20, 21, K // 2, K - 2, K - 1} & set(range(K)))
         idx = torch.as_tensor(planes, device="cuda")
@@ -545,8 +556,12 @@ def parity_check(workload, mod, stor, fill_inputs, step, shape, rank, world, dep
         step()
         torch.cuda.synchronize()
         got = take(stor["out"])
-        want = capi.hori_diff_type2(before["out"].copy(), before["in"], vec["crlato"].reshape(-1),
-                                    vec["crlatu"].reshape(-1), before["hdmask"], halo=HALO, nk=len(planes))
+        if single:
+            want = interp({"out": before["out"].copy(), "in": before["in"], "crlato": vec["crlato"],
+                           "crlatu": vec["crlatu"], "hdmask": before["hdmask"]}, len(planes))["out"]
+        else:
+            want = capi.hori_diff_type2(before["out"].copy(), before["in"], vec["crlato"].reshape(-1),
+                                        vec["crlatu"].reshape(-1), before["hdmask"], halo=HALO, nk=len(planes))
         checks = [(got, want), (take(stor["in"]), before["in"])]
         what = "out on k planes %s (whole planes incl. halo ring)%s" % (
             planes, "; halo rows of `in` poisoned with NaN before the exchange" if world > 1 else "")
@@ -563,7 +578,11 @@ def parity_check(workload, mod, stor, fill_inputs, step, shape, rank, world, dep
         for q in range(len(bands)):
             sl = slice(q * nb, (q + 1) * nb)
             sub = {n: np.ascontiguousarray(before[n][:, sl, :]) for n in names}
-            wd, wc = capi.tridiagonal_solve(sub["d"], sub["a"], sub["b"], sub["c"], halo=HALO, nk=K)
+            if single:
+                r_ = interp(sub, K)
+                wd, wc = r_["d"], r_["c"]
+            else:
+                wd, wc = capi.tridiagonal_solve(sub["d"], sub["a"], sub["b"], sub["c"], halo=HALO, nk=K)
             # only the band's own interior rows were computed from complete data on both sides
             for n, w in (("d", wd), ("c", wc)):
                 g = take(stor[n])[:, sl, :]
@@ -571,7 +590,7 @@ def parity_check(workload, mod, stor, fill_inputs, step, shape, rank, world, dep
         what = "d and c on 8-row bands of whole columns at interior rows %s" % bands
     ndiff, maxdiff, nvals = 0, 0.0, 0
     for g, w in checks:
-        bad = g.view(np.int64) != w.view(np.int64)
+        bad = g.view(np.int32 if single else np.int64) != w.view(np.int32 if single else np.int64)
         bad &= ~(np.isnan(g) & np.isnan(w))
         ndiff += int(bad.sum())
         nvals += g.size
@@ -579,7 +598,8 @@ def parity_check(workload, mod, stor, fill_inputs, step, shape, rank, world, dep
             d = np.abs(g[bad] - w[bad])
             maxdiff = max(maxdiff, float(np.nanmax(d)) if np.isfinite(d).any() else float("inf"))
     return {"checked": what, "values_compared": nvals, "differing_values": ndiff, "max_abs_diff": maxdiff,
-            "oracle": "oracle/naive_stencils.c (C restatement of the naive backend, bit-equal to the pinned "
+            "oracle": "oracle/naive_interp.py on float32 storages (single precision)" if single else
+                      "oracle/naive_stencils.c (C restatement of the naive backend, bit-equal to the pinned "
                       "interpreter)"}
 
 
