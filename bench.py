@@ -351,6 +351,10 @@ def run_gpu(args):
     sampler.mark_begin()
     l0 = st.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist is not None:
+        # the host barrier leaves the ranks' host threads tens of microseconds apart; a device-side all-reduce
+        # in front of the first event lines the GPUs' streams up, so the timed region starts on all of them at once
+        dist.all_reduce(torch.zeros(1, device="cuda"))
     e0.record()
     for _ in range(args.steps):
         step()
@@ -712,6 +716,8 @@ def run_icon(args):
     sampler.mark_begin()
     l0 = st.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist is not None:
+        dist.all_reduce(torch.zeros(1, device="cuda"))   # device-side line-up of the ranks (see run_gpu)
     e0.record()
     for _ in range(args.steps):
         step()
