@@ -318,7 +318,7 @@ def run_gpu(args):
                 n += (2 if rank > 0 else 0) + (2 if rank + 1 < world else 0)
         # the strips are whole tiles of the kernel (module info "tile"): a 2-row strip would still occupy - and
         # load the inputs of - a full 12-row tile, work the interior launch then repeats
-        tile_j = (mod.info.get("tile") or [0, 0])[1]
+        tile_j = 0 if os.environ.get("B200_BENCH_THIN_STRIPS") == "1" else (mod.info.get("tile") or [0, 0])[1]
         lo = max(dep_lo, tile_j) if rank > 0 else 0
         hi = J - (max(dep_hi, tile_j) if rank + 1 < world else 0)
         if hi - lo < tile_j:
