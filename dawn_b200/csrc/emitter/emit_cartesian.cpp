@@ -2811,9 +2811,14 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
       for(int f : kp.fieldsWritten)
         writtenApi.insert(f);
     size_t nf = inst_.apiFieldIDs.size();
-    os_ << "    bool up[" << nf << "];\n";
+    os_ << "    bool up[" << nf << "], dev_newer[" << nf << "];\n";
     for(size_t a = 0; a < nf; ++a)
-      os_ << "    up[" << a << "] = " << fname(inst_.apiFieldIDs[a]) << ".host_is_newer();\n";
+      os_ << "    up[" << a << "] = " << fname(inst_.apiFieldIDs[a]) << ".host_is_newer(); dev_newer[" << a
+          << "] = " << fname(inst_.apiFieldIDs[a]) << ".device_is_newer();\n";
+    os_ << "    // a field another stream produced on the device: the host waits for that stream first\n";
+    for(size_t a = 0; a < nf; ++a)
+      os_ << "    if(dev_newer[" << a << "] && " << fname(inst_.apiFieldIDs[a]) << ".producer_stream() != compute) "
+          << "::dawn_b200::check(b200rt_stream_synchronize(" << fname(inst_.apiFieldIDs[a]) << ".producer_stream()));\n";
     os_ << "    // fields without a k dimension travel whole, ahead of the first chunk\n";
     for(size_t a = 0; a < nf; ++a)
       if(!maskOf(inst_.apiFieldIDs[a]).k)
@@ -2856,11 +2861,19 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
     os_ << "    ::dawn_b200::check(b200rt_stream_synchronize(m_pipe_dn));\n";
     os_ << "    ::dawn_b200::check(b200rt_stream_synchronize(compute));\n";
     os_ << "    ::dawn_b200::check(b200rt_stream_synchronize(m_pipe_up));\n";
-    for(size_t a = 0; a < nf; ++a)
-      if(writtenApi.count(inst_.apiFieldIDs[a]) && !maskOf(inst_.apiFieldIDs[a]).k)
-        os_ << "    " << fname(inst_.apiFieldIDs[a]) << ".mark_device_dirty(compute); // no k dimension: synced below\n";
+    // bookkeeping: what went up is coherent now; results came down level by level (coherent) unless the device
+    // copy was the newer one before and other levels of it never reached the host; inputs that stayed on the
+    // device keep their state
+    for(size_t a = 0; a < nf; ++a) {
+      const std::string n = fname(inst_.apiFieldIDs[a]);
+      if(!writtenApi.count(inst_.apiFieldIDs[a]))
+        os_ << "    if(up[" << a << "]) " << n << ".mark_coherent(compute);\n";
+      else if(!maskOf(inst_.apiFieldIDs[a]).k)
+        os_ << "    " << n << ".mark_device_dirty(compute); // no k dimension: synced by the caller\n";
       else
-        os_ << "    " << fname(inst_.apiFieldIDs[a]) << ".mark_coherent(compute);\n";
+        os_ << "    if(dev_newer[" << a << "] && !up[" << a << "]) " << n << ".mark_device_dirty(compute); else " << n
+            << ".mark_coherent(compute);\n";
+    }
     os_ << "  }\n\n";
   }
   // run(): API fields in order

@@ -173,6 +173,8 @@ public:
   // [k0, k1) of a field with a k dimension are one contiguous range (k is the slowest dimension); fields
   // without one travel whole.  All copies are asynchronous on `stream`; the caller orders and waits.
   bool host_is_newer() const { return buf_ && (buf_->host_dirty || !buf_->dev); }
+  bool device_is_newer() const { return buf_ && buf_->dev && buf_->dev_dirty; }
+  void* producer_stream() const { return buf_ ? buf_->stream : nullptr; }
   b200_field_t device_descriptor_no_upload() const {
     ensure_device();
     return b200_field_t{buf_->dev + info_->lead(), info_->template stride<1>(), info_->template stride<2>()};

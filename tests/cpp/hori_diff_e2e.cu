@@ -85,6 +85,39 @@ int main(int argc, char** argv) {
     for(int j = 0; j < nj; ++j)
       for(int i = 0; i < ni; ++i)
         diff += vg(i, j, k) != d_out[(size_t)i + (size_t)j * ni + (size_t)k * ni * nj];
+  // the result as the INPUT of another run while it is newer on the device (non-pipelined run leaves it there):
+  // the pipelined run must neither upload the stale host copy nor mark it coherent
+  long diff2 = 0;
+  {
+    storage_t a(meta_data, "a"), b(meta_data, "b");
+    verif.fill(-1.0, a, b);
+    hd.set_host_pipeline(0);
+    hd.run(a, u, crlato, crlatu, hdmask);        // a = f(u), whole storages; run() syncs a to the host
+    {                                            // make the device copy of `a` the only good one
+      auto ro = gridtools::make_host_view<gridtools::access_mode::read_only>(a);
+      for(int k = 0; k < nka; ++k)
+        for(int j = 0; j < nj; ++j)
+          for(int i = 0; i < ni; ++i)
+            ro(i, j, k) = 12345.0;               // host mirror scribbled over behind the storage's back
+      a.mark_device_dirty(nullptr);
+    }
+    hd.set_host_pipeline(chunk);
+    { auto vm2 = gridtools::make_host_view(hdmask); vm2(halo::value, halo::value, 0) += 0.0; } // hdmask newer on host
+    hd.run(b, a, crlato, crlatu, hdmask);        // b = f(a) through the pipeline, a already on the device
+    std::vector<double> d_a(d_out), d_b(d_in.size(), -1.0);
+    std::fill(d_lap.begin(), d_lap.end(), 0.0);
+    double* f2[6] = {d_b.data(), d_a.data(), d_cro.data(), d_cru.data(), d_mask.data(), d_lap.data()};
+    oracle_run_threaded(0, threads, ni, nj, K, halo::value, ni, (size_t)ni * nj, f2, 6);
+    auto vb = gridtools::make_host_view<gridtools::access_mode::read_only>(b);
+    auto va = gridtools::make_host_view<gridtools::access_mode::read_only>(a);
+    for(int k = 0; k < nka; ++k)
+      for(int j = 0; j < nj; ++j)
+        for(int i = 0; i < ni; ++i) {
+          diff2 += vb(i, j, k) != d_b[(size_t)i + (size_t)j * ni + (size_t)k * ni * nj];
+          diff2 += va(i, j, k) != d_a[(size_t)i + (size_t)j * ni + (size_t)k * ni * nj];
+        }
+  }
+  diff += diff2;
   const double h2d = 2.0 * sizeof(double) * ((double)meta_data.padded_total_length()) * K / nka +
                      2.0 * sizeof(double) * meta_data_j.padded_total_length();
   const double d2h = sizeof(double) * ((double)meta_data.padded_total_length()) * K / nka;
