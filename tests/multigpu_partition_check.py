@@ -1,8 +1,9 @@
 """Multi-GPU parity of a PARTITIONED unstructured mesh (dawn_b200/partition.py), launched under torchrun:
 ICON nabla2 on an RCM-renumbered TriMesh cut into one part per GPU, `vec` halo copies refreshed from
 their owners over NCCL point-to-point, generated kernels on the local meshes; owned results must equal
-the oracle's on the undivided mesh bit for bit.  Not part of the pytest run yet: written after the
-round's GPU budget was spent (the host logic is covered by tests/test_partition.py with gloo ranks).
+the oracle's on the undivided mesh bit for bit; then ICON nabla4 the same way with two halo rings (no exchange
+between its passes).  Green on 2 and 8 B200s in round 2 (the host logic is covered by tests/test_partition.py
+with gloo ranks); launched under torchrun, so not part of the single-GPU pytest run.
     torchrun --nproc-per-node N tests/multigpu_partition_check.py"""
 import os
 import sys
@@ -52,6 +53,31 @@ def main():
         v = p.mesh.valid(loc)[:no]
         got = tens[n].cpu().numpy()
         ok = ok and bit_equal(got[:, :no][:, v], want[n][:, p.global_ids[loc][:no]][:, v])
+    # nabla4 = nabla2 of nabla2 on the same partition scheme with TWO halo rings: the whole stencil runs on the
+    # local mesh, only `vec` is refreshed, no exchange between its passes (tests/test_partition.py on the CPU)
+    from test_unstructured_oracle import _nabla_inputs, nabla4_oracle
+    f4 = _nabla_inputs(m, k, 43)
+    f4["nabla2_vec"] = np.full((k, m.num_edges), -1.0)
+    f4["nabla4_vec"] = np.full((k, m.num_edges), -1.0)
+    want4 = nabla4_oracle(m, k, f4)
+    p2 = pt.partition(m, world, rings=2)[rank]
+    mod4 = dawn_b200.load_stencil("ICON_nabla4_stencil")
+    st4 = mod4.on_mesh(p2.mesh, k, splitters=p2.splitters())
+    loc4 = {"geofac_rot": 2, "geofac_div": 0}
+    t4 = {}
+    for fd in mod4.fields:
+        a = p2.to_local(loc4.get(fd["name"], EDGE), f4[fd["name"]], axis=1)
+        if fd["sparse"]:
+            a = np.swapaxes(a, -1, -2)
+        t4[fd["name"]] = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    t4["vec"][:, p2.n_owned[EDGE]:] = float("nan")
+    p2.exchange(EDGE, t4["vec"], dist)
+    st4.run(*[t4[fd["name"]] for fd in mod4.fields])
+    torch.cuda.synchronize()
+    no = p2.n_owned[EDGE]
+    v = p2.mesh.valid(EDGE)[:no]
+    for n in ("nabla2_vec", "nabla4_vec"):
+        ok = ok and bit_equal(t4[n].cpu().numpy()[:, :no][:, v], want4[n][:, p2.global_ids[EDGE][:no]][:, v])
     res = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(res, op=dist.ReduceOp.MIN)
     if rank == 0:

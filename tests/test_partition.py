@@ -127,3 +127,29 @@ def test_two_rank_partitioned_nabla2(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
                        capture_output=True, text=True, env=env, timeout=300)
     assert "PARTS_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("nparts", [2, 3])
+def test_nabla4_runs_on_partitions_with_two_halo_rings(nparts):
+    """ICON_nabla4_stencil = nabla2(nabla2(vec)) reaches two neighbourhoods deep: with rings=2 the halo holds
+    everything the owned results depend on, so the whole stencil runs on the local mesh with only the INPUT
+    `vec` refreshed - no exchange between its two passes ('or recompute halo redundantly to
+    need only the input').  One ring is not enough."""
+    from test_unstructured_oracle import _nabla_inputs, nabla4_oracle
+    m, k = ro.reorder(TriMesh(12, 10), "rcm"), 3
+    f = _nabla_inputs(m, k, 43)
+    f["nabla2_vec"] = np.full((k, m.num_edges), -1.0)
+    f["nabla4_vec"] = np.full((k, m.num_edges), -1.0)
+    want = nabla4_oracle(m, k, f)
+    loc = {"geofac_rot": VERTEX, "geofac_div": CELL, "__tmp_rot_0": VERTEX, "__tmp_rot_1": VERTEX,
+           "__tmp_div_0": CELL, "__tmp_div_1": CELL}
+    for rings, expect in ((2, True), (1, False)):
+        same = True
+        for p in pt.partition(m, nparts, rings=rings):
+            g = {n: p.to_local(loc.get(n, EDGE), f.get(n, np.zeros_like(v)), axis=1).copy() for n, v in want.items()}
+            got = naive_interp.run_unstructured(iir_path("ICON_nabla4_stencil"), p.mesh, k, g)
+            no = p.n_owned[EDGE]
+            v = p.mesh.valid(EDGE)[:no]
+            for n in ("nabla2_vec", "nabla4_vec"):
+                same = same and bit_equal(got[n][:, :no][:, v], want[n][:, p.global_ids[EDGE][:no]][:, v])
+        assert same == expect, rings
