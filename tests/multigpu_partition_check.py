@@ -2,8 +2,8 @@
 ICON nabla2 on an RCM-renumbered TriMesh cut into one part per GPU, `vec` halo copies refreshed from
 their owners over NCCL point-to-point, generated kernels on the local meshes; owned results must equal
 the oracle's on the undivided mesh bit for bit; then ICON nabla4 the same way with two halo rings (no exchange
-between its passes).  Green on 2 and 8 B200s in round 2 (the host logic is covered by tests/test_partition.py
-with gloo ranks); launched under torchrun, so not part of the single-GPU pytest run.
+between its passes).  Round 2: nabla2 green on 2 and 8 B200s, nabla4 on 2 (the host logic is covered by
+tests/test_partition.py with gloo ranks); launched under torchrun, so not part of the single-GPU pytest run.
     torchrun --nproc-per-node N tests/multigpu_partition_check.py"""
 import os
 import sys
