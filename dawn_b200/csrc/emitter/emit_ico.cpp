@@ -768,7 +768,11 @@ void IcoEmitter::emitRole(const Group& g, const std::string& blockExpr, const st
   } else {
     os_ << "  const int k0 = kb + " << ro.levelBlock << " * " << lpt_ << ";\n";
   }
-  const std::string loopHead = "#pragma unroll\n  for(int kk = 0; kk < " + std::to_string(lpt_) +
+  // blocks of up to 16 levels are unrolled completely (independent loads of several levels in flight); deeper
+  // ones in steps of 8, or the body would outgrow the instruction cache (unroll_k overrides)
+  const int unroll = opt_.UnrollK > 0 ? opt_.UnrollK : (lpt_ <= 16 ? 0 : 8);
+  const std::string loopHead = std::string("#pragma unroll") + (unroll ? " " + std::to_string(unroll) : std::string()) +
+                               "\n  for(int kk = 0; kk < " + std::to_string(lpt_) +
                                "; ++kk) {\n    const int k = k0 + kk;\n";
   if(!sequential && !opt_.IcoFullBlocks)
     os_ << loopHead << "    if(k > ke)\n      break;\n";
