@@ -35,6 +35,7 @@ b200::codegen::Options convert(const dawn_b200_options* o) {
   r.RingEarly = o->ring_early;
   r.RingStagger = o->ring_stagger;
   r.IcoFullBlocks = o->ico_full_blocks;
+  r.PairStores = o->pair_stores;
   r.IcoCacheHints = o->ico_cache_hints;
   r.IcoChain = o->ico_chain;
   r.IcoChainL1 = o->ico_chain_l1;
@@ -68,6 +69,7 @@ void dawn_b200_default_options(dawn_b200_options* o) {
   o->ring_early = 1;
   o->ring_producer = 0;
   o->ico_chain = 0;
+  o->pair_stores = 1;
   o->ico_chain_l1 = 0;
 }
 

@@ -53,6 +53,7 @@ struct Options {
   int ColumnRing = 1;      // 1: sequential column kernels stream their inputs through a TMA ring
   int RingLevels = 0;      // k levels per ring slot (0 = default 4)
   int PrefetchK = 0;       // register prefetch depth of sequential column loops (0 = default 8)
+  int PairStores = 1;      // TMA tile kernels: 16-byte stores of the two columns of a micro-tile row
   int IcoCacheHints = 0;   // unstructured: evict-first loads of read-once fields, streaming stores of final results
   int IcoChain = 0;        // 1: unstructured: fuse a launch with the next one that gathers its results (L2 hand-over;
                            // measured: less DRAM traffic but slower on B200, see dawn_b200_codegen.h)

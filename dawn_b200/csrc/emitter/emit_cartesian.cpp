@@ -93,6 +93,7 @@ struct KernelPlan {
   int NT() const { return (TI / RI) * TJ; }
   int tileJ() const { return TJ * RJ; }
   std::set<int> fieldsUsed;   // storage-backed fields referenced by this kernel (pointer args)
+  std::set<int> fieldsRead;   // ... of which read somewhere in the kernel (directly or through an inlined temporary)
   std::set<int> fieldsWritten;
   bool usesGlobals = false;
   // --- TMA variant: read-only ijk inputs staged as (tile + extent) boxes in a smem ring over k ---
@@ -421,7 +422,7 @@ void CartesianEmitter::collectUse(KernelPlan& kp) const {
       if(it != inlined_.end())
         walkExpr(it->second.expr, false);
       else
-        kp.fieldsUsed.insert(e->accessID);
+        kp.fieldsUsed.insert(e->accessID), kp.fieldsRead.insert(e->accessID);
     }
     for(auto const& k : e->kids)
       walkExpr(k, false);
@@ -446,6 +447,8 @@ void CartesianEmitter::collectUse(KernelPlan& kp) const {
           kp.fieldsUsed.insert(e.accessID);
           if(w)
             kp.fieldsWritten.insert(e.accessID);
+          else
+            kp.fieldsRead.insert(e.accessID);
         });
     }
 }
@@ -1164,7 +1167,16 @@ public:
               std::function<MaskClass(int)> m)
       : inst(i), kp(k), inlined(inl), maskOf(std::move(m)) {}
 
+  // ---- 128-bit stores (TMA tile kernels, two columns per thread): the value a cell assigns to a field the
+  // kernel never reads is kept in a register and the two cells of a row are stored together when both are valid
+  bool pairStores = false;
+  struct PairStore {
+    int field, row;
+    std::string var[2]; // per column; empty if that column's cell did not assign
+  };
+  std::vector<PairStore> pairStore;
   void reset() {
+    pairStore.clear();
     loads.clear();
     temps.clear();
     valueNo.clear();
@@ -1478,6 +1490,22 @@ public:
                         s->expr->op.substr(0, 1) + " " + rhs + ";");
         out.push_back(pad + "  " + address(lhs.accessID, curCol, curRow, 0) + " = " + tmp + ";");
         out.push_back(pad + "  " + ccAddress(lhs.accessID, 0) + " = " + tmp + "; }");
+      } else if(pairStores && cols == 2 && indent == 0 && s->expr->op == "=" && !kp.fieldsRead.count(lhs.accessID) &&
+                maskOf(lhs.accessID).i && maskOf(lhs.accessID).j && maskOf(lhs.accessID).k) {
+        PairStore* ps = nullptr;
+        for(auto& q : pairStore)
+          if(q.field == lhs.accessID && q.row == curRow)
+            ps = &q;
+        if(!ps) {
+          pairStore.push_back(PairStore{lhs.accessID, curRow, {"", ""}});
+          ps = &pairStore.back();
+        }
+        if(!ps->var[curCol].empty()) { // a second assignment of the same cell: plain store, in program order
+          out.push_back(pad + address(lhs.accessID, curCol, curRow, 0) + " = " + rhs + ";");
+        } else {
+          ps->var[curCol] = "st_" + fieldName(lhs.accessID) + cellSuffix();
+          out.push_back(pad + ps->var[curCol] + " = " + rhs + ";");
+        }
       } else {
         out.push_back(pad + address(lhs.accessID, curCol, curRow, 0) + " " + s->expr->op + " " + rhs +
                       ";");
@@ -2242,6 +2270,9 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         be.reset();
         const int cols = (uniformRegion ? kp.RI : 1);
         be.cols = cols;
+        // 128-bit stores: TMA tile kernels only (their launch guarantees 16-byte aligned rows and field origins)
+        be.pairStores = kp.tma && uniformRegion && cols == 2 && !stage.hasIRange && !stage.hasJRange &&
+                        opt_.PairStores != 0;
         // cells of the micro-tile in row-major order: cellLines[r * cols + c]
         std::vector<std::vector<std::string>> cellLines(rows * cols);
         for(int r = 0; r < rows; ++r)
@@ -2259,6 +2290,10 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
           drainRefill(pad);
         for(auto const& l : be.temps)
           os_ << pad << l << "\n";
+        for(auto const& ps : be.pairStore)
+          for(int c = 0; c < 2; ++c)
+            if(!ps.var[c].empty())
+              os_ << pad << "::dawn::float_type " << ps.var[c] << ";\n";
         for(int rc = 0; rc < rows * cols; ++rc) {
           const int r = rc / cols, c = rc % cols;
           std::vector<std::string>& rowLinesRef = cellLines[rc];
@@ -2280,6 +2315,26 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
           for(auto const& l : rowLinesRef)
             os_ << pad << "  " << l << "\n";
           os_ << pad << "}\n";
+        }
+        // the two cells of a row go out as ONE 16-byte store when both are valid (lx is even, rows and origins
+        // are 16-byte aligned in the TMA variant), else one by one
+        for(auto const& ps : be.pairStore) {
+          const std::string g0 = be.cellGuard(0, ps.row), g1 = be.cellGuard(1, ps.row);
+          const std::string a0 = be.address(ps.field, 0, ps.row, 0), a1 = be.address(ps.field, 1, ps.row, 0);
+          if(!ps.var[0].empty() && !ps.var[1].empty()) {
+            os_ << pad << "if(" << g0 << " && " << g1 << ")\n";
+            os_ << pad << "  *reinterpret_cast<::dawn::float_type2*>(&" << a0 << ") = ::dawn::make_float_type2("
+                << ps.var[0] << ", " << ps.var[1] << ");\n";
+            os_ << pad << "else {\n";
+            os_ << pad << "  if(" << g0 << ") " << a0 << " = " << ps.var[0] << ";\n";
+            os_ << pad << "  if(" << g1 << ") " << a1 << " = " << ps.var[1] << ";\n";
+            os_ << pad << "}\n";
+          } else {
+            for(int c = 0; c < 2; ++c)
+              if(!ps.var[c].empty())
+                os_ << pad << "if(" << be.cellGuard(c, ps.row) << ") " << be.address(ps.field, c, ps.row, 0) << " = "
+                    << ps.var[c] << ";\n";
+          }
         }
         if(!kp.pointwise) {
           pad.resize(pad.size() - 2);
@@ -2676,6 +2731,10 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
             << 16 / twin->ftBytes << " == 0";
         for(auto const& sg : twin->staged)
           os_ << " && (reinterpret_cast<uintptr_t>(" << fname(sg.field) << "_p) % 16 == 0)";
+        if(opt_.PairStores != 0 && twin->RI == 2) // results go out as 16-byte pairs
+          for(int f : twin->fieldsWritten)
+            if(!twin->fieldsRead.count(f) && isStorageField(f) && maskOf(f).i && maskOf(f).j && maskOf(f).k)
+              os_ << " && (reinterpret_cast<uintptr_t>(" << fname(f) << "_p) % 16 == 0)";
         os_ << ";\n";
         for(auto const& sg : twin->staged)
           os_ << "        alignas(64) CUtensorMap tm_" << fname(sg.field) << ";\n";

@@ -69,6 +69,8 @@ typedef struct dawn_b200_options {
                              backward (L2-fed) sweeps interleave; -1: N from $DAWN_B200_STAGGER_NS (probing) */
   int ico_full_blocks;    /* default 0: unstructured kernels run full blocks of levels through an unrolled
                              loop without per-level bound checks (more loads in flight per thread) */
+  int pair_stores;        /* default 1: TMA tile kernels with two columns per thread store the two results of a row as
+                             one 16-byte store when both cells are valid (fields the kernel never reads) */
   int ico_cache_hints;    /* unstructured kernels: fields that every stage of a launch reads at its own element only
                              (each value is needed once) are loaded evict-first (ld.global.cs) and results no later
                              launch reads are stored streaming (st.global.cs), so that the GATHERED fields keep
