@@ -23,6 +23,11 @@ for w in ("hori_diff", "tridiagonal"):
     try: show(w + " f32", json.loads(open("gpurun_out/r2_bench_%s_f32.json" % w).read().strip().splitlines()[-1]))
     except Exception as e: print(w, "f32 FAILED", e, open("gpurun_out/r2_bench_%s_f32.err" % w).read()[-600:])
 PY
+B="python bench.py --no-cpu-baseline --no-sub-workloads --steps 20 --warmup 3"
+$B > gpurun_out/plain_hd.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -k regex:stencil -c 60 --csv \
+    --log-file gpurun_out/r2_hori_diff_launches.csv $B > gpurun_out/ncu_l1.log 2>&1
+$B > gpurun_out/plain_hd.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:hori_diff.*tma -s 5 -c 2 -f \
+    -o gpurun_out/r2_prof_hd $B > gpurun_out/ncu_f1.log 2>&1
 T="python bench.py --workload tridiagonal --no-cpu-baseline --steps 20 --warmup 3"
 $T > gpurun_out/plain_tri.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -k regex:stencil -c 60 --csv \
     --log-file gpurun_out/r2_tridiagonal_launches.csv $T > gpurun_out/ncu_l2.log 2>&1
