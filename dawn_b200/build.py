@@ -111,8 +111,12 @@ VARIANTS = {
     "ICON_laplacian_stencil": [dict(fuse_columns=0, levels_per_thread=1), dict(levels_per_thread=8),
                                dict(co_schedule=0), dict(ico_chain=1), dict(ico_chain=1, co_schedule=0),
                                dict(ico_chain=1, ico_chain_lag=1), dict(ico_chain=1, ico_chain_lag=100000),
-                               dict(ico_chain=1, ico_chain_l1=1), dict(ico_chain=1, ico_cache_hints=1)],
-    "ICON_nabla4_stencil": [dict(fuse_columns=0, levels_per_thread=1), dict(co_schedule=0), dict(ico_chain=1)],
+                               dict(ico_chain=1, ico_chain_l1=1), dict(ico_chain=1, ico_cache_hints=1),
+                               dict(ico_stage=1), dict(ico_stage=2), dict(ico_stage=2, levels_per_thread=5),
+                               dict(ico_hoist=1), dict(ico_hoist=1, ico_stage=2)],
+    "ICON_nabla4_stencil": [dict(fuse_columns=0, levels_per_thread=1), dict(co_schedule=0), dict(ico_chain=1),
+                            dict(ico_stage=1)],
+    "ICON_laplacian_diamond_stencil": [dict(ico_stage=1), dict(ico_hoist=1, ico_stage=2)],
     "overwriteGathered": [dict(ico_chain=1)],
     **{"fuzzico_%02d" % n: [dict(ico_chain=1)] for n in range(16, 20)},
     "kcache_fill": [dict(column_ring=0)], "kcache_flush": [dict(column_ring=0)],

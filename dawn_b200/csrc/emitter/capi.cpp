@@ -42,6 +42,8 @@ b200::codegen::Options convert(const dawn_b200_options* o) {
   r.IcoChainLag = o->ico_chain_lag;
   r.RingProducer = o->ring_producer;
   r.SinglePrecision = o->single_precision;
+  r.IcoStage = o->ico_stage;
+  r.IcoHoist = o->ico_hoist;
   return r;
 }
 } // namespace

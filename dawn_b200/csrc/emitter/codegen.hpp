@@ -62,6 +62,9 @@ struct Options {
   int RingProducer = 0;    // 1: column-ring kernels get a dedicated TMA producer warp instead of thread 0 +
                            // __syncthreads (measured slower in full waves on B200, see dawn_b200_codegen.h)
   int SinglePrecision = 0; // 1: generate for ::dawn::float_type = float (element size 4)
+  int IcoHoist = 0;        // unstructured: read-only loads of a level hoisted to its top (all in flight together)
+  int IcoStage = 0;        // unstructured: own-element rows staged in shared memory by cp.async.bulk (1: one mbarrier
+                           // per level, 2: one per block); see dawn_b200_codegen.h
 };
 
 // TranslationUnit twin (CodeGen/TranslationUnit.h:26-53)

@@ -17,6 +17,7 @@
 #include "codegen.hpp"
 
 #include <algorithm>
+#include <cctype>
 #include <functional>
 #include <set>
 #include <sstream>
@@ -228,7 +229,19 @@ private:
     std::set<int> streamOnce;              // read-only fields every role reads at its own element only: evict-first
     std::set<int> storeStream;             // written fields nobody in the launch reads again: st.global.cs
     std::set<int> plainLoad;               // fields another role wrote, complete line-wise: ordinary (L1-cached) loads
+    std::set<int> stage;                   // ico_stage: fields no role of the launch writes (candidates for staged rows)
   };
+  // what the staged variant of the kernel being emitted needs (emitKernel -> emitHost)
+  struct StageMeta {
+    size_t smemBytes = 0;
+    std::set<int> fields;
+  };
+  StageMeta curStage_;
+  std::map<std::string, StageMeta> stageMeta_; // by kernel name
+  bool emitRoleStaged(const Group& g, const std::string& blockExpr, const std::string& lo, const std::string& hi,
+                      const RoleOpts& ro);
+  void emitRolePlain(const Group& g, const std::string& blockExpr, const std::string& lo, const std::string& hi,
+                     const RoleOpts& ro);
   void emitKernel(const Group& g, const Group* partner, const Group* consumer);
   void emitRole(const Group& g, const std::string& blockExpr, const std::string& lo,
                 const std::string& hi, const RoleOpts& ro);
@@ -403,6 +416,12 @@ public:
   int uid = 0;
   // chained launches (IcoEmitter::RoleOpts): cache policy per field
   std::set<int> cg, streamOnce, storeStream, plainLoad;
+  // ico_stage: own-element reads of these fields come from the block's staged rows.  A row is one (field, sparse
+  // position) pair, `rows` lists them in slot order; a slot holds rowElems elements per level, the first
+  // `alignElems - 1` of which may be lead-in (the copy starts on a 16-byte boundary)
+  const std::set<int>* stage = nullptr;
+  std::vector<std::pair<int, int>>* rows = nullptr;
+  int rowElems = 0, alignElems = 1;
 
   struct Ctx {
     std::string center = "pidx"; // index of the element the reduction runs on
@@ -453,6 +472,16 @@ public:
     return e.hasOffset || (!d.chain.empty() && d.chain.front() != c.centerLoc);
   }
 
+  // global element index of the first element of a staged row at level k: [k][element] or [k][nbh][element]
+  std::string stagedIndex(const std::pair<int, int>& row) {
+    auto const& d = dims(row.first);
+    const std::string n = stride(d.chain.front());
+    if(row.second < 0)
+      return "(size_t)k * " + n + " + blk_lo";
+    return "((size_t)k * " + std::to_string(sparseSize(row.first)) + " + " + std::to_string(row.second) + ") * " + n +
+           " + blk_lo";
+  }
+
   std::string fieldRef(const Expr& e, const Ctx& c) {
     auto const& d = dims(e.accessID);
     std::string p = fname(e.accessID) + "_p";
@@ -485,6 +514,19 @@ public:
     }
     if(registerOnly.count(e.accessID))
       throw std::runtime_error("b200-ico: internal error, register-only temporary read from memory");
+    if(stage && stage->count(e.accessID) && c.center == "pidx" && e.dk == 0 && e.kFrom.empty()) {
+      auto const& d = dims(e.accessID);
+      if(d.maskK && !d.chain.empty() && (d.isSparse() ? !c.sparseIdx.empty() : !atNeighbour(e, c))) {
+        const std::pair<int, int> row{e.accessID, d.isSparse() ? std::stoi(c.sparseIdx) : -1};
+        size_t slot = 0;
+        while(slot < rows->size() && (*rows)[slot] != row)
+          ++slot;
+        if(slot == rows->size())
+          rows->push_back(row);
+        return "stg[(kk * @ROWS@ + " + std::to_string(slot) + ") * " + std::to_string(rowElems) + " + (unsigned)((" +
+               stagedIndex(row) + ") % " + std::to_string(alignElems) + ") + threadIdx.x]";
+      }
+    }
     std::string ref = fieldRef(e, c);
     if(cg.count(e.accessID))
       return "__ldcg(&" + ref + ")"; // written by another role of this launch: L2 is the point of coherence
@@ -726,9 +768,199 @@ void IcoEmitter::planCoScheduling(std::vector<Group>& groups) const {
   }
 }
 
+// ico_hoist: the loads of read-only fields of one level (`__ldg` at the thread's own element or at a neighbour
+// whose index the thread loaded once) move to the top of the level, each into a constant, so that they are all
+// in flight together.  Left where they are used they are not: a double-precision division ends a basic block
+// (slow-path branch) and the compiler does not move loads across it, so ICON's edge kernel has two gathers in
+// flight per thread at a time.  Safe: the fields are not written by the launch, the addresses are in range for
+// every level of the block (accesses with a vertical offset stay where they are) and a missing neighbour (-1)
+// keeps its guard.  Identical loads share one constant.
+static std::string hoistLevelLoads(const std::string& body, const std::string& ft) {
+  std::string out, head;
+  std::map<std::string, std::string> seen;
+  size_t pos = 0;
+  for(;;) {
+    size_t b = body.find("__ldg(&", pos);
+    if(b == std::string::npos)
+      break;
+    size_t lb = body.find('[', b), rb = lb == std::string::npos ? lb : body.find(']', lb);
+    if(rb == std::string::npos || rb + 1 >= body.size() || body[rb + 1] != ')') {
+      out += body.substr(pos, b + 7 - pos);
+      pos = b + 7;
+      continue;
+    }
+    const std::string load = body.substr(b, rb + 2 - b), idx = body.substr(lb + 1, rb - lb - 1);
+    const bool plainIndex = idx.find('[') == std::string::npos && idx.find("nbi") == std::string::npos &&
+                            idx.find("(k + (") == std::string::npos && idx.find("__ld") == std::string::npos &&
+                            idx.find("(int)") == std::string::npos;
+    if(!plainIndex) {
+      out += body.substr(pos, b + 7 - pos);
+      pos = b + 7;
+      continue;
+    }
+    auto it = seen.find(load);
+    if(it == seen.end()) {
+      const std::string var = "hl" + std::to_string(seen.size());
+      std::string guard;
+      size_t nb = idx.find("nb_");
+      if(nb != std::string::npos) {
+        size_t e = nb;
+        while(e < idx.size() && (std::isalnum((unsigned char)idx[e]) || idx[e] == '_'))
+          ++e;
+        guard = idx.substr(nb, e - nb) + " >= 0 ? ";
+      }
+      head += "    const " + ft + " " + var + " = " + guard + load + (guard.empty() ? "" : " : (" + ft + ")0") + ";\n";
+      it = seen.emplace(load, var).first;
+    }
+    out += body.substr(pos, b - pos) + it->second;
+    pos = rb + 2;
+  }
+  out += body.substr(pos);
+  return head + out;
+}
+
 // One role of a launch: the code of a group for the element block `blockExpr` of [lo, hi).
 void IcoEmitter::emitRole(const Group& g, const std::string& blockExpr, const std::string& lo,
                           const std::string& hi, const RoleOpts& ro) {
+  if(!ro.stage.empty()) {
+    // the staged variant is rendered first: only the body knows which rows it reads at its own element
+    const std::string saved = os_.str();
+    os_.str("");
+    const bool staged = emitRoleStaged(g, blockExpr, lo, hi, ro);
+    const std::string text = os_.str();
+    os_.str("");
+    os_ << saved;
+    if(staged) {
+      os_ << text << "  } else {\n";
+      emitRolePlain(g, blockExpr, lo, hi, ro);
+      os_ << "  }\n";
+      return;
+    }
+  }
+  emitRolePlain(g, blockExpr, lo, hi, ro);
+}
+
+// ico_stage: the variant of a role for FULL element blocks.  The rows the body reads at the thread's own element
+// (dense fields of the role's location, sparse weights [k][nbh][element]) are fetched by 1-D bulk copies
+// (cp.async.bulk -> shared memory, completion on an mbarrier) that the first lanes of the block issue for all
+// levels of the block at once; the threads load their neighbour indices meanwhile and then only gather.  A row
+// starts at an arbitrary element index, so a copy starts on the 16-byte boundary at or below it (`alignElems`
+// elements) and the readers add the lead-in; the block must therefore lie alignElems elements inside its level
+// row at the upper end (checked per block, as is the alignment of the field bases: `stage_ok` from the host).
+// Returns false (nothing emitted) if the body has no such row.
+bool IcoEmitter::emitRoleStaged(const Group& g, const std::string& blockExpr, const std::string& lo,
+                                const std::string& hi, const RoleOpts& ro) {
+  const bool sequential = g.ms->loopOrder != LoopOrder::Parallel;
+  if(sequential || ro.noReturn || lpt_ > 16 || opt_.IcoFullBlocks)
+    return false;
+  const int ftBytes = opt_.SinglePrecision ? 4 : 8;
+  const int E = 16 / ftBytes;
+  const int rowElems = block_ + E;
+  if(block_ % E)
+    return false;
+  int lo_k = Interval::End * 2, hi_k = -Interval::End;
+  for(auto const* st : g.stages)
+    for(auto const& dm : st->doMethods) {
+      lo_k = std::min(lo_k, dm.interval.lowerBound());
+      hi_k = std::max(hi_k, dm.interval.upperBound());
+    }
+  std::vector<std::pair<int, int>> rows;
+  IcoBody body{inst_, g, registerOnly_,
+               [this](int id) { return fname(id); },
+               [this](int id) -> const FieldDims& { return dims(id); },
+               [this](int id) { return sparseSize(id); }, {}, 0, ro.cg, ro.streamOnce, ro.storeStream, ro.plainLoad};
+  body.stage = &ro.stage;
+  body.rows = &rows;
+  body.rowElems = rowElems;
+  body.alignElems = E;
+  std::ostringstream bodyText;
+  for(auto const* st : g.stages) {
+    bodyText << "    // stage " << st->id << "\n";
+    for(auto const& dm : st->doMethods) {
+      bool guard = dm.interval.lowerBound() != lo_k || dm.interval.upperBound() != hi_k;
+      std::vector<std::string> lines;
+      for(auto const& s : dm.stmts)
+        body.stmt(s, lines, 0, guard);
+      if(guard)
+        bodyText << "    if(k >= " << analysis::boundExpr(dm.interval.lowerBound()) << " && k <= "
+                 << analysis::boundExpr(dm.interval.upperBound()) << ") {\n";
+      for(auto const& l : lines)
+        bodyText << (guard ? "      " : "    ") << l << "\n";
+      if(guard) {
+        bodyText << "    }\n";
+        body.forwarded.clear();
+      }
+    }
+  }
+  if(rows.empty())
+    return false;
+  const size_t smem = 128 + (size_t)lpt_ * rows.size() * rowElems * ftBytes;
+  if(smem > 200 * 1024)
+    return false;
+  std::string text = bodyText.str();
+  for(size_t p = text.find("@ROWS@"); p != std::string::npos; p = text.find("@ROWS@", p))
+    text.replace(p, 6, std::to_string(rows.size()));
+  if(opt_.IcoHoist)
+    text = hoistLevelLoads(text, "::dawn::float_type");
+  curStage_.smemBytes = std::max(curStage_.smemBytes, smem);
+  for(auto const& r : rows)
+    curStage_.fields.insert(r.first);
+  const bool oneBarrier = opt_.IcoStage == 2;
+  const std::string n = IcoBody::stride(g.loc);
+  os_ << "  const int blk_lo = " << lo << " + (int)(" << blockExpr << ") * " << block_ << ";\n";
+  os_ << "  if(stage_ok && blk_lo + " << block_ << " <= " << hi << " && blk_lo + " << block_ + E << " <= " << n
+      << ") { // full block: " << rows.size() << " row(s) per level arrive as bulk copies\n";
+  os_ << "  const int pidx = blk_lo + threadIdx.x;\n";
+  os_ << "  unsigned long long* const stg_bar = reinterpret_cast<unsigned long long*>(b200_smem);\n";
+  os_ << "  ::dawn::float_type* const stg = reinterpret_cast<::dawn::float_type*>(b200_smem + 128);\n";
+  os_ << "  const int kmin = 0, kmax = k_size - 1;\n";
+  os_ << "  int kb = " << analysis::boundExpr(lo_k) << ", ke = " << analysis::boundExpr(hi_k) << ";\n";
+  os_ << "  kb = kb < 0 ? 0 : kb; ke = ke > kmax ? kmax : ke;\n";
+  os_ << "  const int k0 = kb + " << ro.levelBlock << " * " << lpt_ << ";\n";
+  os_ << "  const int nlev = ke - k0 + 1 < " << lpt_ << " ? ke - k0 + 1 : " << lpt_ << "; // levels of this block\n";
+  if(oneBarrier)
+    os_ << "  if(threadIdx.x == 0 && nlev > 0) {\n    ::dawn_b200::tma::barrier_init(&stg_bar[0], (unsigned)nlev);\n";
+  else
+    os_ << "  if(threadIdx.x < " << lpt_ << ") {\n    ::dawn_b200::tma::barrier_init(&stg_bar[threadIdx.x], 1);\n";
+  os_ << "    ::dawn_b200::tma::fence_barrier_init();\n  }\n  __syncthreads();\n";
+  os_ << "  if((int)threadIdx.x < nlev) { // lane kk requests the rows of level k0 + kk\n";
+  os_ << "    const int kk = threadIdx.x;\n    const int k = k0 + kk;\n";
+  os_ << "    unsigned long long* const bar = &stg_bar[" << (oneBarrier ? "0" : "kk") << "];\n";
+  for(size_t r = 0; r < rows.size(); ++r) {
+    os_ << "    const size_t gi" << r << " = " << body.stagedIndex(rows[r]) << ";\n";
+    os_ << "    const unsigned sh" << r << " = (unsigned)(gi" << r << " % " << E << ");\n";
+  }
+  os_ << "    ::dawn_b200::tma::expect_bytes(bar, " << ftBytes << "u * (" << rows.size() * block_ << "u";
+  for(size_t r = 0; r < rows.size(); ++r)
+    os_ << " + (sh" << r << " ? " << E << "u : 0u)";
+  os_ << "));\n";
+  for(size_t r = 0; r < rows.size(); ++r)
+    os_ << "    ::dawn_b200::tma::bulk_load_1d(stg + (kk * " << rows.size() << " + " << r << ") * " << rowElems << ", "
+        << fname(rows[r].first) << "_p + (gi" << r << " - sh" << r << "), " << ftBytes << "u * (sh" << r << " ? "
+        << block_ + E << "u : " << block_ << "u), bar);\n";
+  os_ << "  }\n";
+  for(auto const& ch : g.chains) {
+    int size = icoChainSize(ch.first, ch.second);
+    std::string tag = chainTag(ch.first, ch.second);
+    if(!g.topChains.count(tag))
+      continue;
+    for(int q = 0; q < size; ++q)
+      os_ << "  const int nb_" << tag << "_" << q << " = __ldg(&tbl_" << tag << "[pidx + "
+          << IcoBody::stride(ch.first.front()) << " * " << q << "]);\n";
+  }
+  if(oneBarrier)
+    os_ << "  if(nlev > 0)\n    ::dawn_b200::tma::wait(&stg_bar[0], 0u);\n";
+  const int unroll = opt_.UnrollK > 0 ? opt_.UnrollK : 0;
+  os_ << "#pragma unroll" << (unroll ? " " + std::to_string(unroll) : std::string()) << "\n  for(int kk = 0; kk < "
+      << lpt_ << "; ++kk) {\n    const int k = k0 + kk;\n    if(k > ke)\n      break;\n";
+  if(!oneBarrier)
+    os_ << "    ::dawn_b200::tma::wait(&stg_bar[kk], 0u);\n";
+  os_ << text << "  }\n";
+  return true;
+}
+
+void IcoEmitter::emitRolePlain(const Group& g, const std::string& blockExpr, const std::string& lo,
+                               const std::string& hi, const RoleOpts& ro) {
   const bool sequential = g.ms->loopOrder != LoopOrder::Parallel;
   const bool backward = g.ms->loopOrder == LoopOrder::Backward;
   // grid: element blocks fastest (x), level blocks in y.  (Level blocks fastest, so that the blocks
@@ -799,8 +1031,9 @@ void IcoEmitter::emitRole(const Group& g, const std::string& blockExpr, const st
       }
     }
   }
+  const std::string levelText = opt_.IcoHoist ? hoistLevelLoads(bodyText.str(), "::dawn::float_type") : bodyText.str();
   if(sequential || !opt_.IcoFullBlocks) {
-    os_ << bodyText.str() << "  }\n";
+    os_ << levelText << "  }\n";
     if(ro.noReturn)
       os_ << "  }\n";
     return;
@@ -808,8 +1041,8 @@ void IcoEmitter::emitRole(const Group& g, const std::string& blockExpr, const st
   // ico_full_blocks: blocks of levels that lie completely inside the range run the unrolled loop
   // without a bound check per level (loads of several levels may be scheduled together); the last,
   // partial block takes a plain loop
-  os_ << "  if(k0 + " << lpt_ - 1 << " <= ke) {\n" << loopHead << bodyText.str() << "  }\n  } else {\n";
-  os_ << "  for(int k = k0; k <= ke; ++k) {\n" << bodyText.str() << "  }\n  }\n";
+  os_ << "  if(k0 + " << lpt_ - 1 << " <= ke) {\n" << loopHead << levelText << "  }\n  } else {\n";
+  os_ << "  for(int k = k0; k <= ke; ++k) {\n" << levelText << "  }\n  }\n";
   if(ro.noReturn)
     os_ << "  }\n";
 }
@@ -920,52 +1153,17 @@ void IcoEmitter::planChains(std::vector<Group>& groups) const {
 
 void IcoEmitter::emitKernel(const Group& g, const Group* partner, const Group* consumer) {
   const bool sequential = g.ms->loopOrder != LoopOrder::Parallel;
-  os_ << "// kernel " << g.name << ": " << g.stages.size() << " fused stage(s) on " << locName(g.loc);
-  if(partner)
-    os_ << " co-scheduled with " << partner->stages.size() << " stage(s) on " << locName(partner->loc);
-  if(consumer)
-    os_ << ", chained with " << consumer->stages.size() << " stage(s) on " << locName(consumer->loc)
-        << " that gather their results (flags + L2 hand-over)";
-  os_ << ", " << block_ << " threads, "
-      << (sequential ? std::string("sequential k sweep") : std::to_string(lpt_) + " level(s)/thread") << "\n";
-  // --max-blocks-sm (CodeGen/Options.inc): resident blocks per SM the register allocator must allow.
-  // Default: full occupancy (2048 threads per SM, i.e. <= 32 registers per thread) - these kernels are
-  // bound by the latency of their gathers, and ICON nabla2 on B200 measured 78 % of the HBM peak at 64
-  // resident warps against 72 % at the 48 warps ptxas' own 40-register allocation allowed.
-  const int minBlocks = opt_.MaxBlocksPerSM > 0 ? opt_.MaxBlocksPerSM : std::max(1, 2048 / block_);
-  os_ << "__global__ void __launch_bounds__(" << block_ << ", " << minBlocks << ")\n" << g.name << "(";
-  if(g.usesGlobals)
-    os_ << "const globals g, ";
-  os_ << "const int k_size, const int elem_lo, const int elem_hi, const int n_cells, const int n_edges, "
-         "const int n_vertices";
-  if(partner)
-    os_ << ", const int elem_lo1, const int elem_hi1, const unsigned nb0, const unsigned nb1";
-  if(consumer)
-    os_ << ", const int elem_lo2, const int elem_hi2, const b200_chain_view cv, const unsigned epoch";
-  std::set<std::string> tags;
   std::vector<const Group*> roles{&g};
   if(partner)
     roles.push_back(partner);
   if(consumer)
     roles.push_back(consumer);
-  for(auto const* r : roles)
-    for(auto const& ch : r->chains)
-      if(tags.insert(chainTag(ch.first, ch.second)).second)
-        os_ << ",\n    const int* __restrict__ tbl_" << chainTag(ch.first, ch.second);
   std::set<int> args, written;
   for(auto const* r : roles) {
     args.insert(r->fieldsRead.begin(), r->fieldsRead.end());
     args.insert(r->fieldsWritten.begin(), r->fieldsWritten.end());
     written.insert(r->fieldsWritten.begin(), r->fieldsWritten.end());
   }
-  for(int f : args) {
-    if(registerOnly_.count(f))
-      continue;
-    bool ro = !written.count(f);
-    os_ << ",\n    " << (ro ? "const " : "") << "::dawn::float_type* __restrict__ " << fname(f) << "_p";
-  }
-  os_ << ") {\n";
-  os_ << "  (void)n_cells; (void)n_edges; (void)n_vertices;\n";
   RoleOpts plain;
   if(opt_.IcoCacheHints && !consumer) {
     std::set<int> gathered;
@@ -982,7 +1180,17 @@ void IcoEmitter::emitKernel(const Group& g, const Group* partner, const Group* c
       if(!laterReads_.count({&g, f}) && !isVertical(f))
         plain.storeStream.insert(f);
   }
+  if(opt_.IcoStage && !consumer && !sequential)
+    for(int f : args)
+      if(!written.count(f) && !isVertical(f) && hasK(f) && !registerOnly_.count(f) && !scratch_.count(f))
+        plain.stage.insert(f);
+  // the roles are rendered first: whether the kernel has a staged variant (dynamic shared memory, one more
+  // argument, fewer resident blocks) is known only afterwards
+  curStage_ = StageMeta{};
+  std::string rolesText;
   if(!consumer) {
+    const std::string saved = os_.str();
+    os_.str("");
     if(!partner) {
       emitRole(g, "blockIdx.x", "elem_lo", "elem_hi", plain);
     } else {
@@ -997,7 +1205,60 @@ void IcoEmitter::emitKernel(const Group& g, const Group* partner, const Group* c
       emitRole(*partner, "blockIdx.x - r0", "elem_lo1", "elem_hi1", plain);
       os_ << "  }\n";
     }
-    os_ << "}\n\n";
+    rolesText = os_.str();
+    os_.str("");
+    os_ << saved;
+  }
+  const bool staged = curStage_.smemBytes > 0;
+  if(staged)
+    stageMeta_[g.name] = curStage_;
+  os_ << "// kernel " << g.name << ": " << g.stages.size() << " fused stage(s) on " << locName(g.loc);
+  if(partner)
+    os_ << " co-scheduled with " << partner->stages.size() << " stage(s) on " << locName(partner->loc);
+  if(consumer)
+    os_ << ", chained with " << consumer->stages.size() << " stage(s) on " << locName(consumer->loc)
+        << " that gather their results (flags + L2 hand-over)";
+  os_ << ", " << block_ << " threads, "
+      << (sequential ? std::string("sequential k sweep") : std::to_string(lpt_) + " level(s)/thread");
+  if(staged)
+    os_ << ", own-element rows staged by cp.async.bulk (" << curStage_.smemBytes << " bytes of shared memory)";
+  os_ << "\n";
+  // --max-blocks-sm (CodeGen/Options.inc): resident blocks per SM the register allocator must allow.
+  // Default: full occupancy (2048 threads per SM, i.e. <= 32 registers per thread) - these kernels are
+  // bound by the latency of their gathers, and ICON nabla2 on B200 measured 78 % of the HBM peak at 64
+  // resident warps against 72 % at the 48 warps ptxas' own 40-register allocation allowed.  A staged kernel
+  // cannot have more resident blocks than its shared memory allows (227 KB per SM, 1 KB reserved per block).
+  int minBlocks = opt_.MaxBlocksPerSM > 0 ? opt_.MaxBlocksPerSM : std::max(1, 2048 / block_);
+  if(staged && opt_.MaxBlocksPerSM <= 0)
+    minBlocks = std::max(1, std::min<int>(minBlocks, (int)(227 * 1024 / (curStage_.smemBytes + 1024))));
+  os_ << "__global__ void __launch_bounds__(" << block_ << ", " << minBlocks << ")\n" << g.name << "(";
+  if(g.usesGlobals)
+    os_ << "const globals g, ";
+  os_ << "const int k_size, const int elem_lo, const int elem_hi, const int n_cells, const int n_edges, "
+         "const int n_vertices";
+  if(partner)
+    os_ << ", const int elem_lo1, const int elem_hi1, const unsigned nb0, const unsigned nb1";
+  if(consumer)
+    os_ << ", const int elem_lo2, const int elem_hi2, const b200_chain_view cv, const unsigned epoch";
+  if(staged)
+    os_ << ", const int stage_ok";
+  std::set<std::string> tags;
+  for(auto const* r : roles)
+    for(auto const& ch : r->chains)
+      if(tags.insert(chainTag(ch.first, ch.second)).second)
+        os_ << ",\n    const int* __restrict__ tbl_" << chainTag(ch.first, ch.second);
+  for(int f : args) {
+    if(registerOnly_.count(f))
+      continue;
+    bool ro = !written.count(f);
+    os_ << ",\n    " << (ro ? "const " : "") << "::dawn::float_type* __restrict__ " << fname(f) << "_p";
+  }
+  os_ << ") {\n";
+  os_ << "  (void)n_cells; (void)n_edges; (void)n_vertices;\n";
+  if(staged)
+    os_ << "  extern __shared__ __align__(128) unsigned char b200_smem[];\n";
+  if(!consumer) {
+    os_ << rolesText << "}\n\n";
     return;
   }
   // ---- chained launch: blockIdx.x = level block * sched_len + position in the host-built schedule ----------
@@ -1087,6 +1348,9 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
   for(size_t gi = 0; gi < groups.size(); ++gi)
     if(groups[gi].chainNext >= 0)
       os_ << "  b200_chain_plan* m_chain_" << gi << " = nullptr; // block schedule + flags of the chained launch\n";
+  for(size_t gi = 0; gi < groups.size(); ++gi)
+    if(stageMeta_.count(groups[gi].name))
+      os_ << "  bool m_stage_smem_" << gi << " = false; // dynamic shared memory limit of the staged kernel raised\n";
   os_ << "  std::vector<b200_splitter_t> m_splitters; // unstructured_domain twin\n";
   os_ << "  b200_metrics_record* m_record = nullptr;  // the json* the reference hands to setup_<N>\n";
   os_ << "  int m_error = 0;\npublic:\n  long m_launches = 0;\n";
@@ -1244,7 +1508,22 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
       os_ << "      dim3 grid((elem_hi - elem_lo + " << block_ - 1 << ") / " << block_ << ", " << levelBlocks
           << ");\n";
     }
-    os_ << "      " << g.name << "<<<grid, " << block_ << ", 0, stream>>>(";
+    auto sm = stageMeta_.find(g.name);
+    if(sm != stageMeta_.end()) {
+      // the staged variant needs 16-byte aligned field bases (cp.async.bulk); full blocks take it then
+      os_ << "      const bool stage_ok = true";
+      for(int f : sm->second.fields)
+        os_ << " && reinterpret_cast<uintptr_t>(" << fname(f) << "_p) % 16 == 0";
+      os_ << ";\n";
+      os_ << "      if(stage_ok && !m_stage_smem_" << gi << ") {\n"
+          << "        cudaError_t ae = cudaFuncSetAttribute(reinterpret_cast<const void*>(&" << g.name
+          << "), cudaFuncAttributeMaxDynamicSharedMemorySize, " << sm->second.smemBytes << ");\n"
+          << "        if(ae != cudaSuccess) return ::dawn_b200::set_error(B200_ERR_CUDA, cudaGetErrorString(ae));\n"
+          << "        m_stage_smem_" << gi << " = true;\n      }\n";
+      os_ << "      " << g.name << "<<<grid, " << block_ << ", stage_ok ? " << sm->second.smemBytes
+          << " : 0, stream>>>(";
+    } else
+      os_ << "      " << g.name << "<<<grid, " << block_ << ", 0, stream>>>(";
     if(g.usesGlobals)
       os_ << "m_globals, ";
     os_ << "k_size, elem_lo, elem_hi, n_cells, n_edges, n_vertices";
@@ -1252,6 +1531,8 @@ void IcoEmitter::emitHost(const std::vector<Group>& groups) {
       os_ << ", elem_lo1, elem_hi1, nb0, nb1";
     if(consumer)
       os_ << ", elem_lo2, elem_hi2, cv, epoch";
+    if(sm != stageMeta_.end())
+      os_ << ", stage_ok ? 1 : 0";
     std::set<std::string> tags;
     std::vector<const Group*> roles{&g};
     if(partner)

@@ -37,6 +37,14 @@ __device__ __forceinline__ void load_3d(void* smem_dst, const CUtensorMap* map, 
   cuda::ptx::cp_async_bulk_tensor(cuda::ptx::space_cluster, cuda::ptx::space_global, smem_dst, map,
                                   coords, reinterpret_cast<uint64_t*>(bar));
 }
+// 1-D bulk copy global -> shared (cp.async.bulk, SASS UBLKCP): `bytes` a multiple of 16, both addresses 16-byte
+// aligned; completes its bytes on `bar`.  The unstructured kernels stage the rows they read at their own
+// elements this way (ico_stage): the bytes in flight live in shared memory instead of registers.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes,
+                                             unsigned long long* bar) {
+  cuda::ptx::cp_async_bulk(cuda::ptx::space_cluster, cuda::ptx::space_global, smem_dst, gmem_src, bytes,
+                           reinterpret_cast<uint64_t*>(bar));
+}
 __device__ __forceinline__ void wait(unsigned long long* bar, unsigned parity) {
   while(!cuda::ptx::mbarrier_try_wait_parity(reinterpret_cast<uint64_t*>(bar), parity)) {
   }

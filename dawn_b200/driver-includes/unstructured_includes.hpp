@@ -14,6 +14,7 @@
 #include "b200_runtime.hpp"
 #include "timer_b200.hpp"
 #include "b200_chain.hpp"
+#include "b200_tma.hpp"
 
 namespace dawn_b200 {
 

@@ -104,6 +104,18 @@ typedef struct dawn_b200_options {
                              driver-includes/defs.hpp:47-81; here the TMA box geometry and the shared-memory
                              pairs depend on the element size, so the emitter has to know - the emitted text
                              defines DAWN_PRECISION itself and static_asserts the size) */
+  int ico_stage;          /* default 0; 1 | 2: unstructured kernels of Parallel multistages fetch the rows they read at
+                             their OWN elements (dense fields and sparse weights of the kernel's location, never
+                             written by the launch) with 1-D bulk copies (cp.async.bulk) into shared memory - one
+                             copy of block_size elements per level and row, issued by the first lanes of the block
+                             at kernel start, 1: one mbarrier per level, 2: one for the block - so that only the
+                             gathers are left to the load/store path and the streams' bytes in flight do not cost
+                             registers.  Taken per block at run time (full blocks, 16-byte aligned field bases);
+                             other blocks run the plain code of the same kernel */
+  int ico_hoist;          /* default 0; 1: unstructured kernels load every read-only value of a level (own element and
+                             top-level neighbours, no vertical offset) at the top of the level, so that the loads
+                             of a level are in flight together - left at their uses they are split by the basic
+                             blocks a double-precision division ends */
 } dawn_b200_options;
 
 /* Fills `opts` with the defaults above. */

@@ -137,6 +137,8 @@ def run(name, code, info, mesh, k, fields, globals_=None, splitters=None):
     lib.emu_guard_violations.restype = ctypes.c_long
     if lib.emu_guard_violations():
         raise RuntimeError("a kernel of %s wrote outside a scratch allocation" % name)
+    lib.emu_bulk_copies_issued.restype = ctypes.c_long
+    run.bulk_copies = lib.emu_bulk_copies_issued()   # > 0: blocks took the staged (cp.async.bulk) variant
     out = {}
     for fd, a in zip(info["fields"], dev):
         out[fd["name"]] = np.swapaxes(a, -1, -2) if fd["sparse"] else a

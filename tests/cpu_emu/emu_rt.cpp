@@ -90,6 +90,11 @@ struct emu_tensor_map_rt {
 };
 static long g_tensor_maps = 0;
 long emu_tensor_maps_encoded(void) { return g_tensor_maps; }
+#ifdef EMU_BLOCK_THREADS
+long emu_bulk_copies_issued(void) { return dawn_b200::tma::emu_bulk_copies.load(); } // ico_stage: staged blocks ran
+#else
+long emu_bulk_copies_issued(void) { return 0; }
+#endif
 int b200rt_tensor_map_3d_es(void* map, const void* base, int size_i, int size_j, int size_k, int stride_j,
                             int stride_k, int box_i, int box_j, int box_k, int elem_bytes) {
   // the alignment rules of the real encoder (rt.cu): what the emitted launchers promise

@@ -123,6 +123,79 @@ def test_emitter_variants_on_the_cpu(name, opts):
     compare(info, m, got, want)
 
 
+# ---- ico_stage: own-element rows (dense fields and sparse weights of the kernel's location) arrive in shared
+# memory by 1-D bulk copies; the stand-in copy insists on the hardware's 16-byte rules, so the lead-in arithmetic
+# for rows that start at odd element indices (odd element counts; four phases in float) is what is tested here.
+@pytest.mark.parametrize("opts", [dict(ico_stage=1), dict(ico_stage=2, co_schedule=0, ico_hoist=1),
+                                  dict(ico_stage=1, single_precision=1),
+                                  dict(ico_stage=2, single_precision=1, levels_per_thread=5)])
+@pytest.mark.parametrize("name", ["ICON_laplacian_stencil", "ICON_laplacian_diamond_stencil", "nestedWithSparse",
+                                  "fuzzico_16"])
+def test_staged_rows_on_the_cpu(name, opts):
+    code, info = emitted(name, **opts)
+    assert "bulk_load_1d" in code and "stage_ok" in code
+    for nx, ny in ((20, 14), (21, 15)):     # 315 vertices / 945 edges (odd), 352 / 1056 (even)
+        m, k = TriMesh(nx, ny), 9
+        f = random_fields(info, m, k, np.random.default_rng(23))
+        w = with_temporaries(name, m, k, f)
+        if opts.get("single_precision"):
+            f = {n: v.astype(np.float32) for n, v in f.items()}
+            w = {n: v.astype(np.float32) for n, v in with_temporaries(name, m, k, f).items()}
+        want = naive_interp.run_unstructured(iir_path(name), m, k, w)
+        got, _ = emu.run(name, code, info, m, k, f)
+        assert emu.run.bulk_copies > 0      # full blocks took the staged variant
+        compare(info, m, got, want)
+
+
+# ---- ico_hoist: the read-only loads of a level move to its top (one constant each, guards kept)
+@pytest.mark.parametrize("name", ["ICON_laplacian_stencil", "ICON_laplacian_diamond_stencil", "verticalIndirecion",
+                                  "reductionInIfConditional", "tridiagonalSolve", "fuzzico_14", "fuzzico_18",
+                                  "generate_versioned_field", "iterationSpaceUnstructured"])
+def test_hoisted_loads_on_the_cpu(name):
+    code, info = emitted(name, ico_hoist=1)
+    assert "const ::dawn::float_type hl0 = " in code
+    m, k = TriMesh(11, 8), 7
+    rng = np.random.default_rng(29)
+    f = random_fields(info, m, k, rng)
+    spl = None
+    if name == "tridiagonalSolve":
+        f["b"] += 4.0
+    if name == "verticalIndirecion":
+        f["kidx"] = np.zeros((k, m.num_cells)) + np.arange(k, dtype=float)[:, None] + 1
+        f["kidx"][: k - 1] = rng.integers(0, k, (k - 1, m.num_cells)).astype(float)
+    if name == "iterationSpaceUnstructured":
+        spl = {(CELL, 2000, 0): 10, (CELL, 3000, 0): 60, (CELL, 4000, 0): 100}
+    if name == "generate_versioned_field":
+        f["d"] = (f["d"] < 0.9).astype(float)
+        f["e"] = (f["e"] < 1.0).astype(float) * 3.0
+    want = naive_interp.run_unstructured(iir_path(name), m, k, with_temporaries(name, m, k, f), splitters=spl)
+    got, _ = emu.run(name, code, info, m, k, f, splitters=spl)
+    compare(info, m, got, want)
+
+
+def test_hoisting_keeps_guards_and_vertical_offsets():
+    code, _ = emitted("ICON_laplacian_stencil", ico_hoist=1)
+    # a gather through a neighbour index that may be -1 keeps its guard; own-element loads need none
+    assert "= nb_ev_0 >= 0 ? __ldg(&rot_vec_p[(size_t)k * n_vertices + nb_ev_0]) : (::dawn::float_type)0;" in code
+    assert re.search(r"const ::dawn::float_type hl\d+ = __ldg\(&dual_edge_length_p\[\(size_t\)k \* n_edges \+ pidx\]\);", code)
+    # loads at another level stay where the interval guards protect them
+    seq, _ = emitted("verticalSum", ico_hoist=1)
+    for line in seq.splitlines():
+        if " hl" in line and "= " in line and "__ldg" in line:
+            assert "(k + (" not in line
+
+
+def test_staging_leaves_written_and_gathered_accesses_alone():
+    # rows are only what a kernel reads at its own element and no role of the launch writes
+    code, _ = emitted("ICON_laplacian_stencil", ico_stage=1)
+    staged = set(re.findall(r"bulk_load_1d\(stg \+ [^,]+, (\w+)_p", code))
+    assert staged == {"geofac_rot", "geofac_div", "tangent_orientation", "primal_edge_length", "dual_edge_length"}
+    assert "ico_stage" not in emitted("ICON_laplacian_stencil")[0] and "b200_smem" not in emitted("ICON_laplacian_stencil")[0]
+    # sequential sweeps and chained launches keep their plain form
+    assert "bulk_load_1d" not in emitted("tridiagonalSolve", ico_stage=1)[0]
+    assert "bulk_load_1d" not in emitted("ICON_laplacian_stencil", ico_stage=1, ico_chain=1)[0].split("_k2_")[0]
+
+
 @pytest.mark.parametrize("method", ["random", "rcm", "morton"])
 def test_renumbered_mesh_through_the_emitted_kernels(method):
     # same kernels, renumbered tables (dawn_b200/reorder.py): maps back to the undivided oracle run

@@ -76,7 +76,9 @@ def _check(got, want, m, names):
                                   dict(levels_per_thread=8), dict(co_schedule=0), dict(ico_chain=1),
                                   dict(ico_chain=1, co_schedule=0), dict(ico_chain=1, ico_chain_lag=1),
                                   dict(ico_chain=1, ico_chain_lag=100000), dict(ico_chain=1, ico_chain_l1=1),
-                                  dict(ico_chain=1, ico_cache_hints=1)])
+                                  dict(ico_chain=1, ico_cache_hints=1), dict(ico_stage=1), dict(ico_stage=2),
+                                  dict(ico_stage=2, levels_per_thread=5), dict(ico_hoist=1),
+                                  dict(ico_hoist=1, ico_stage=2)])
 def test_icon_laplacian(nx, ny, k, opts):
     m = TriMesh(nx, ny)
     rng = np.random.default_rng(31)
@@ -103,7 +105,7 @@ def test_icon_laplacian(nx, ny, k, opts):
 
 @pytest.mark.parametrize("nx,ny,k", [(7, 5, 3), (33, 20, 9), (64, 64, 65)])
 @pytest.mark.parametrize("opts", [dict(), dict(co_schedule=0), dict(fuse_columns=0, levels_per_thread=1),
-                                  dict(ico_chain=1)])
+                                  dict(ico_chain=1), dict(ico_stage=1)])
 def test_icon_nabla4(nx, ny, k, opts):
     # nabla4 = nabla2(nabla2(vec)): not in the reference; the oracle side is anchored on two passes of
     # the reference-pinned nabla2 oracle (tests/test_unstructured_oracle.py)
@@ -554,15 +556,17 @@ def test_icon_nabla2_on_a_renumbered_mesh(method):
         assert bit_equal(r.to_old(loc, got[n], axis=1)[:, v], want[n][:, v]), n
 
 
+@pytest.mark.parametrize("opts", [dict(), dict(ico_stage=1), dict(ico_hoist=1, ico_stage=2)])
 @pytest.mark.parametrize("nx,ny,k", [(9, 7, 3), (33, 20, 9)])
-def test_icon_diamond_laplacian(nx, ny, k):
-    """ICON_laplacian_diamond_stencil.py (diamond nabla2 + Smagorinsky): 13 fused edge stages, one launch."""
+def test_icon_diamond_laplacian(nx, ny, k, opts):
+    """ICON_laplacian_diamond_stencil.py (diamond nabla2 + Smagorinsky): 13 fused edge stages, one launch.
+    ico_stage=1: the seven rows it reads at the edge itself arrive by bulk copies (full blocks only)."""
     from test_unstructured_oracle import diamond_fields
     m = TriMesh(nx, ny)
     f = diamond_fields(m, k, 54)
     want = naive_interp.run_unstructured(iir_path("ICON_laplacian_diamond_stencil"), m, k,
                                          {n: v.copy() for n, v in f.items()})
-    got, st = _run("ICON_laplacian_diamond_stencil", m, k, f)
+    got, st = _run("ICON_laplacian_diamond_stencil", m, k, f, **opts)
     v = m.valid(EDGE)
     for n in ("vn_vert", "dvt_tang", "dvt_norm", "kh_smag_1", "kh_smag_2", "kh_smag", "nabla2"):
         assert bit_equal(got[n][:, v], want[n][:, v]), n
