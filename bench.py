@@ -67,6 +67,11 @@ class ClockSampler:
     def mark_end(self):
         self.t1 = time.time()
 
+    def mark_same_load_until(self):
+        """a timed region shorter than nvidia-smi's start-up + period holds no sample: the caller keeps the same
+        steps running (untimed) a little longer and the samples up to here stand in for it"""
+        self.t_same = time.time()
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -95,8 +100,10 @@ class ClockSampler:
         sel = [r for r in rows if t0 <= r[0] <= t1]
         window = "timed region"
         if not sel:  # region shorter than the sampling period: nearest samples under the same load
-            sel = [r for r in rows if t0 - 0.25 <= r[0] <= t1 + 0.05]
-            window = "timed region +-0.25 s (same load)"
+            t_same = getattr(self, "t_same", None)
+            sel = [r for r in rows if t0 - 0.25 <= r[0] <= (t_same if t_same is not None else t1 + 0.05)]
+            window = ("timed region -0.25 s .. +%.2f s (the same steps kept running, untimed)" % (t_same - t1)
+                      if t_same is not None else "timed region +-0.25 s (same load)")
         sm = sorted(r[1] for r in sel)
         reasons = sorted({x for r in sel for x in r[3]})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
@@ -361,7 +368,6 @@ def run_gpu(args):
     e1.record()
     barrier()
     sampler.mark_end()
-    clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     launches = (st.launches() - l0) + launches_per_step[0] * args.steps
     if args.halo == "p2p":
@@ -371,6 +377,14 @@ def run_gpu(args):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
+    if ms_max < 300.0:
+        # a region of a few milliseconds ends before nvidia-smi has printed a line: keep the same steps running
+        # (untimed, the same count on every rank) for half a second so that the clock samples describe this load
+        for _ in range(int(500.0 / max(ms_max / args.steps, 1e-3)) + 1):
+            step()
+        barrier()
+        sampler.mark_same_load_until()
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- parity self-check: the launch shape that was just timed, against the oracle ----------------
     parity = parity_check(workload, mod, stor, fill_inputs, step, (I, J, K), rank, world,
