@@ -41,25 +41,48 @@ def measured_peak():
 
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region: nvidia-smi runs from before
-    the warm-up (the GPU is under the same load throughout) with 10 ms period; samples are selected by
-    their timestamps against the wall-clock bracket of the timed region."""
+    the warm-up with 10 ms period and its lines are collected by a reader thread as they arrive; samples are
+    selected by their timestamps against the wall-clock bracket of the timed region.  A region of a few
+    milliseconds can end before nvidia-smi has printed anything: the caller then keeps the same steps running
+    (untimed) in small batches until a sample has arrived (`wants_more_load`), and that is said in `window`."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BEFORE, AFTER = 0.25, 0.05      # s around a region too short to hold a sample (the GPU is under the same load)
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, command="nvidia-smi"):
         self.proc = None
         self.index = index
-        self.t0 = self.t1 = None
+        self.command = command
+        self.t0 = self.t1 = self.t_same = None
+        self.rows = []          # (timestamp, sm MHz, max sm MHz, [active reasons]); appended by the reader thread
 
     def start(self):
+        import threading
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                [self.command, "-i", str(self.index), "--query-gpu=" + self.Q,
                  "--format=csv,noheader,nounits", "-lms", "10"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
         except Exception:
             self.proc = None
+            return
+        self.reader = threading.Thread(target=self._pump, daemon=True)
+        self.reader.start()
+
+    def _pump(self):
+        import datetime
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                self.rows.append((ts, float(parts[1]), float(parts[2]),
+                                  [n for n, v in zip(self.NAMES, parts[4:8]) if v.lower().startswith("active")]))
+            except ValueError:
+                continue
 
     def mark_begin(self):
         self.t0 = time.time()
@@ -67,10 +90,33 @@ class ClockSampler:
     def mark_end(self):
         self.t1 = time.time()
 
-    def mark_same_load_until(self):
-        """a timed region shorter than nvidia-smi's start-up + period holds no sample: the caller keeps the same
-        steps running (untimed) a little longer and the samples up to here stand in for it"""
-        self.t_same = time.time()
+    def _select(self):
+        rows = list(self.rows)
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else 1e18
+        sel = [r for r in rows if t0 <= r[0] <= t1]
+        if sel:
+            return sel, "timed region"
+        sel = [r for r in rows if t0 - self.BEFORE <= r[0] <= t1 + self.AFTER]
+        if sel:
+            return sel, "timed region -%.2f s .. +%.2f s (same load)" % (self.BEFORE, self.AFTER)
+        if self.t_same is not None:
+            sel = [r for r in rows if t0 - self.BEFORE <= r[0] <= self.t_same]
+            if sel:
+                return sel, ("timed region -%.2f s .. +%.2f s (the same steps kept running, untimed, until "
+                             "nvidia-smi had printed a sample)" % (self.BEFORE, self.t_same - t1))
+        return [], "no sample"
+
+    def wants_more_load(self, limit_s=1.5):
+        """after mark_end(): True while no sample describes the timed region yet (and nvidia-smi is alive and the
+        extension is younger than `limit_s`); the caller runs another small batch of the same steps and asks again"""
+        if not self.proc or self.proc.poll() is not None or self.t1 is None:
+            return False
+        now = time.time()
+        if now - self.t1 > limit_s:
+            return False
+        self.t_same = now
+        return not self._select()[0]
 
     def stop(self):
         if not self.proc:
@@ -78,32 +124,11 @@ class ClockSampler:
         time.sleep(0.05)
         self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-            out = ""
-        import datetime
-        rows = []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 8:
-                continue
-            try:
-                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                rows.append((ts, float(parts[1]), float(parts[2]),
-                             [n for n, v in zip(names, parts[4:8]) if v.lower().startswith("active")]))
-            except ValueError:
-                continue
-        t0 = self.t0 if self.t0 is not None else 0.0
-        t1 = self.t1 if self.t1 is not None else 1e18
-        sel = [r for r in rows if t0 <= r[0] <= t1]
-        window = "timed region"
-        if not sel:  # region shorter than the sampling period: nearest samples under the same load
-            t_same = getattr(self, "t_same", None)
-            sel = [r for r in rows if t0 - 0.25 <= r[0] <= (t_same if t_same is not None else t1 + 0.05)]
-            window = ("timed region -0.25 s .. +%.2f s (the same steps kept running, untimed)" % (t_same - t1)
-                      if t_same is not None else "timed region +-0.25 s (same load)")
+        self.reader.join(timeout=2)
+        sel, window = self._select()
         sm = sorted(r[1] for r in sel)
         reasons = sorted({x for r in sel for x in r[3]})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
@@ -377,13 +402,18 @@ def run_gpu(args):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    if ms_max < 300.0:
-        # a region of a few milliseconds ends before nvidia-smi has printed a line: keep the same steps running
-        # (untimed, the same count on every rank) for half a second so that the clock samples describe this load
-        for _ in range(int(500.0 / max(ms_max / args.steps, 1e-3)) + 1):
+    # a region of a few milliseconds can end before nvidia-smi has printed a line: the same steps keep running
+    # (untimed, ~20 ms batches, the same count on every rank) until a sample describes this load
+    batch = int(20.0 / max(ms_max / args.steps, 1e-3)) + 1
+    while True:
+        more = torch.tensor([1.0 if rank == 0 and sampler.wants_more_load() else 0.0], device="cuda")
+        if dist is not None:
+            dist.all_reduce(more, op=dist.ReduceOp.MAX)
+        if float(more.item()) == 0.0:
+            break
+        for _ in range(batch):
             step()
-        barrier()
-        sampler.mark_same_load_until()
+        torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- parity self-check: the launch shape that was just timed, against the oracle ----------------

@@ -147,6 +147,48 @@ void forEachAccess(const Stage& stage,
       ws(s, 0, false);
 }
 
+// A stage runs as one thread per element, all its statements back to back: a statement may not gather (read at
+// another element) what the stage writes - the neighbour's thread may or may not have stored yet - nor may a
+// later statement overwrite what an earlier one gathered.  The reference's cuda-ico kernels have the same race
+// (one kernel per stage, CudaIcoCodeGen.cpp:1316-1464) and its naive loops give a result that depends on the
+// element order; Dawn's PassStageSplitter / PassFieldVersioning remove such stages before code generation.
+// IIR that still has one (GenerateUnstructuredStencils.cpp:900-937 `tempField`, built without the splitter)
+// is rejected.
+void checkStageInternalHazards(const Stage& stage, const std::function<LocationType(int)>& fieldLoc,
+                               const std::function<std::string(int)>& nameOf) {
+  for(auto const& dm : stage.doMethods) {
+    std::set<int> written, gathered;
+    for(auto const& s : dm.stmts) {
+      Stage one;
+      one.location = stage.location;
+      one.doMethods.emplace_back();
+      one.doMethods.back().stmts.push_back(s);
+      std::set<int> away, writes;
+      forEachAccess(one, [&](const Expr& e, int nest, bool) {
+        if(nest > 0 && (e.hasOffset || nest > 1 || fieldLoc(e.accessID) != stage.location))
+          away.insert(e.accessID);
+      });
+      analysis::visitStmts({s}, [&](const Expr& e, bool w) {
+        if(w && e.kind == Expr::Field)
+          writes.insert(e.accessID);
+      });
+      for(int f : away)
+        if(written.count(f) || writes.count(f))
+          throw std::runtime_error("b200-ico: stage " + std::to_string(stage.id) + " gathers field '" + nameOf(f) +
+                                   "' from other elements and writes it as well; the accesses of neighbouring "
+                                   "elements cannot be ordered inside one stage (split the stage or version the field: "
+                                   "PassStageSplitter / PassFieldVersioning)");
+      for(int f : writes)
+        if(gathered.count(f))
+          throw std::runtime_error("b200-ico: stage " + std::to_string(stage.id) + " overwrites field '" + nameOf(f) +
+                                   "' that an earlier statement of the same stage gathers from other elements "
+                                   "(split the stage: PassStageSplitter)");
+      written.insert(writes.begin(), writes.end());
+      gathered.insert(away.begin(), away.end());
+    }
+  }
+}
+
 struct Group {
   std::vector<const Stage*> stages;
   const MultiStage* ms;
@@ -324,6 +366,8 @@ std::vector<Group> IcoEmitter::plan(const Stencil& st) {
       if(stage.location == LocationType::None)
         throw std::runtime_error("b200-ico: stage " + std::to_string(stage.id) +
                                  " has no location type");
+      checkStageInternalHazards(stage, [this](int id) { return fieldLoc(id); },
+                                [this](int id) { return inst_.nameOf(id); });
       bool sameSpace = cur.hasSpace == stage.hasIRange &&
                        (!stage.hasIRange ||
                         (cur.space.lowerLevel == stage.iRange.lowerLevel &&

@@ -444,3 +444,23 @@ def test_icon_diamond_laplacian_is_one_kernel():
     heads = re.findall(r"^// kernel .*$", code, flags=re.M)
     assert len(heads) == 1 and "13 fused stage(s) on edges" in heads[0]
     assert code.count("<<<") == 1 and "sqrt(" in code
+
+
+def test_a_stage_that_gathers_what_it_writes_is_rejected():
+    # `tempField` exactly as GenerateUnstructuredStencils.cpp:900-937 builds it (field versioning, no stage
+    # splitter): its second stage writes `dense` and gathers it from the neighbours in the next statement - a race
+    # for one thread per element (the reference's cuda-ico kernel included), order-dependent in the naive loops
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import make_stencils
+    with pytest.raises(codegen.CodeGenError, match="gathers field 'dense' from other elements and writes it"):
+        codegen.compile_iir(make_stencils.ico_temp_field(split=False).dumps(), backend="b200-ico")
+    assert "tempField_stencil" in codegen.compile_iir(make_stencils.ico_temp_field().dumps(), backend="b200-ico")
+    # the mirror image: a later statement overwrites what an earlier one of the same stage gathered
+    b = make_stencils._ico("warInsideAStage")
+    c, e = b.field("c", "k", "Cell"), b.field("e", "k", "Cell")
+    chain = ["Cell", "Edge", "Cell"]
+    b.stencil(b.multistage("Parallel", b.stage(b.do(make_stencils.FULL, b.assign(e, make_stencils.reduce_over(chain, c.nbh)),
+                                                      b.assign(c, make_stencils.lit(1.0))), location="Cell")))
+    with pytest.raises(codegen.CodeGenError, match="overwrites field 'c' that an earlier statement"):
+        codegen.compile_iir(b.dumps(), backend="b200-ico")

@@ -513,6 +513,26 @@ def _fields(name, m, k, rng):
     return f, {"cout_field": CELL}, extra
 
 
+@pytest.mark.parametrize("nx,ny,k", [(10, 10, 3), (13, 7, 11), (40, 24, 9)])
+def test_generated_temp_field(nx, ny, k):
+    """`tempField` of GenerateUnstructuredStencils.cpp:900-937 (a sparse field versioned by PassFieldVersioning,
+    its copy made in a neighbour loop by PassFixVersionedInputFields, an 18-neighbour chain E>C>V>E) after the stage
+    split of Dawn's default pipeline - tools/make_stencils.py ico_temp_field has the derivation; the unsplit text
+    is rejected (tests/test_emitter.py)."""
+    m = TriMesh(nx, ny)
+    rng = np.random.default_rng(57)
+    f = {"dense": rng.uniform(0.5, 1.5, (k, m.num_edges)), "sparse": rng.uniform(0.5, 1.5, (k, m.num_edges, 18))}
+    want = {n: v.copy() for n, v in f.items()}
+    want["sparse_0"] = np.zeros((k, m.num_edges, 18))
+    naive_interp.run_unstructured(iir_path("tempField"), m, k, want)
+    got, st = _run("tempField", m, k, f)
+    v = m.valid(EDGE)
+    assert bit_equal(got["dense"][:, v], want["dense"][:, v])
+    # a neighbour loop assigns where a neighbour exists; the other positions keep what the host passed in
+    assert bit_equal(got["sparse"][:, v], want["sparse"][:, v])
+    assert st.launches() == 3
+
+
 @pytest.mark.parametrize("nx,ny,k", [(10, 10, 3), (13, 7, 11)])
 @pytest.mark.parametrize("name", ["globalVar", "tempFieldAllocation", "sparseTempFieldAllocation",
                                   "reductionInIfConditional", "reductionWithCenter",

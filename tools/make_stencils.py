@@ -550,6 +550,33 @@ def ico_sparse_temp_field_allocation():  # :968-998 (a temporary with a sparse d
     return b
 
 
+def ico_temp_field(split=True):
+    # GenerateUnstructuredStencils.cpp:900-937 `tempField`: dense = sum over E>C>V>E of sparse; then a neighbour
+    # loop sparse = dense(neighbour).  The generator runs PassFieldVersioning (the cycle dense <- sparse <- dense
+    # with a horizontal access makes it rename `sparse` on the right-hand side of the first statement to a new
+    # version, PassFieldVersioning.cpp:268-286, CreateVersionAndRename.cpp:52-60) and PassFixVersionedInputFields
+    # (a Parallel multistage in front copies the original into the version; a sparse field is copied inside a
+    # neighbour loop over its chain, PassFixVersionedInputFields.cpp:36-63,176-186).  It does NOT run
+    # PassStageSplitter, so the second stage as generated still gathers `dense` right after writing it
+    # (split=False: every backend with one thread per element races there, the naive loops depend on the element
+    # order, and no test of the reference runs the generated file; the b200-ico emitter rejects it).  split=True
+    # is the same program after the stage split Dawn's default pipeline applies: the fixture.
+    b = _ico("tempField")
+    chain = ["Edge", "Cell", "Vertex", "Edge"]
+    dense = b.field("dense", "k", "Edge")
+    sparse = b.field("sparse", "k", sparse_chain=chain)
+    sparse0 = b.tmp("sparse_0", "k", sparse_chain=chain)
+    copy = b.stage(b.do(FULL, loop_over(chain, b.assign(sparse0, sparse.at()))), location="Edge")
+    red = b.assign(dense, reduce_over(chain, sparse0.at(), init=0.0))
+    fill = loop_over(chain, b.assign(sparse, dense.nbh))
+    if split:
+        stages = [b.stage(b.do(FULL, red), location="Edge"), b.stage(b.do(FULL, fill), location="Edge")]
+    else:
+        stages = [b.stage(b.do(FULL, red, fill), location="Edge")]
+    b.stencil(b.multistage("Parallel", copy), b.multistage("Parallel", *stages))
+    return b
+
+
 def ico_reduction_in_if_conditional():  # :1000-1036 (a reduction as the condition of an if)
     b = _ico("reductionInIfConditional")
     c = b.field("c_field", "k", "Cell")
@@ -941,6 +968,7 @@ ALL = {
     "globalVar": ico_global_var,
     "tempFieldAllocation": ico_temp_field_allocation,
     "sparseTempFieldAllocation": ico_sparse_temp_field_allocation,
+    "tempField": ico_temp_field,
     "reductionInIfConditional": ico_reduction_in_if_conditional,
     "reductionWithCenter": lambda: ico_reduction_with_center(0),
     "reductionWithCenterSparse": lambda: ico_reduction_with_center(1),
