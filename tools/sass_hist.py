@@ -17,7 +17,7 @@ for line in out.splitlines():
     m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
     if m and kern:
         hist[kern][m.group(1)] += 1
-WATCH = ("UTMALDG", "SYNCS", "LDS", "STS", "LDG", "STG", "DFMA", "DMUL", "DADD", "FFMA", "FMUL", "FADD", "MUFU", "BAR", "SHFL",
+WATCH = ("UTMALDG", "UBLKCP", "SYNCS", "LDS", "STS", "LDG", "STG", "DFMA", "DMUL", "DADD", "FFMA", "FMUL", "FADD", "MUFU", "BAR", "SHFL",
          "MEMBAR", "ATOM", "LDL", "STL", "CCTL", "ERRBAR")
 print("# " + " ".join(sys.argv))
 for k, h in hist.items():
