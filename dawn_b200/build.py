@@ -130,7 +130,8 @@ VARIANTS = {
     "tridiagonal_solve": [dict(ring_early=0), dict(ring_stagger=-1), dict(ring_drain=0), dict(ring_drain=1, tma_stages=2), dict(ring_drain=1, tma_stages=4),
                           dict(ring_drain=1, ring_levels=4, tma_stages=4), dict(fuse_columns=0), dict(column_ring=0), dict(column_ring=0, column_cache=1, prefetch_k=3),
                           dict(ring_levels=2, tma_stages=2), dict(block_size_i=32, block_size_j=2),
-                          dict(ring_producer=1), dict(ring_producer=1, ring_levels=4, tma_stages=3, block_size_i=32)],
+                          dict(ring_producer=1), dict(ring_producer=1, ring_levels=4, tma_stages=3, block_size_i=32),
+                          dict(persistent_ring=1), dict(persistent_ring=1, ring_levels=4, tma_stages=4)],
 }
 
 
@@ -148,8 +149,13 @@ REFERENCE_IIR = {
 REFERENCE_ROOT = "/root/reference"
 
 
+# three letters per option: the first two of the name and the first of its last word.  Options whose letters would
+# repeat those of an older option get their own (ico_hoist / ico_cache_hints, persistent_ring is free)
+_TAG = {"ico_hoist": "iho"}
+
+
 def variant_tag(options):
-    return "_".join("%s%s" % (k[:2] + k.split("_")[-1][:1], v) for k, v in sorted(options.items()))
+    return "_".join("%s%s" % (_TAG.get(k, k[:2] + k.split("_")[-1][:1]), v) for k, v in sorted(options.items()))
 
 
 def build_all(force=False, jobs=None):

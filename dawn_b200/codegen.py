@@ -34,7 +34,7 @@ class _Options(ctypes.Structure):
         "rows_per_thread", "block_size_k", "inline_temporaries", "fuse_columns", "unroll_k",
         "levels_per_thread", "block_size_ico", "use_tma", "tma_stages", "column_cache", "column_ring", "ring_levels", "prefetch_k", "cols_per_thread",
         "shared_temporaries", "co_schedule", "ring_drain", "ring_early", "ring_stagger",
-        "ico_full_blocks", "pair_stores", "ico_cache_hints", "ico_chain", "ico_chain_l1", "ico_chain_lag", "ring_producer", "single_precision", "ico_stage", "ico_hoist")]
+        "ico_full_blocks", "pair_stores", "ico_cache_hints", "ico_chain", "ico_chain_l1", "ico_chain_lag", "ring_producer", "single_precision", "ico_stage", "ico_hoist", "persistent_ring")]
 
 
 _lib = None

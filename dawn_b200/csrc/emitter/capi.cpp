@@ -44,6 +44,7 @@ b200::codegen::Options convert(const dawn_b200_options* o) {
   r.SinglePrecision = o->single_precision;
   r.IcoStage = o->ico_stage;
   r.IcoHoist = o->ico_hoist;
+  r.RingPersistent = o->persistent_ring;
   return r;
 }
 } // namespace

@@ -62,6 +62,7 @@ struct Options {
   int RingProducer = 0;    // 1: column-ring kernels get a dedicated TMA producer warp instead of thread 0 +
                            // __syncthreads (measured slower in full waves on B200, see dawn_b200_codegen.h)
   int SinglePrecision = 0; // 1: generate for ::dawn::float_type = float (element size 4)
+  int RingPersistent = 0;  // 1: column-ring kernels as persistent blocks that prefetch their next column set
   int IcoHoist = 0;        // unstructured: read-only loads of a level hoisted to its top (all in flight together)
   int IcoStage = 0;        // unstructured: own-element rows staged in shared memory by cp.async.bulk (1: one mbarrier
                            // per level, 2: one per block); see dawn_b200_codegen.h

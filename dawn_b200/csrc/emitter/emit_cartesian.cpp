@@ -115,6 +115,9 @@ struct KernelPlan {
   // a dedicated producer warp (threads NT..NT+31, one elected lane) issues the ring's TMA loads: consumers
   // wait on a slot's `full` barrier, drain it into registers and hand it back through its `empty` barrier
   bool producer = false;
+  // persistent blocks (persistent_ring): a block loops over column sets and requests the first ring slots of its
+  // next set while the last streamed range of the current one drains
+  bool persistent = false;
   int ringHeaderBytes() const { return producer ? 256 : 128; }
   int ringKB = 4;
   std::vector<int> ringFields; // every field that may be streamed (tensor-map kernel args)
@@ -606,6 +609,7 @@ bool CartesianEmitter::planColumnRing(KernelPlan& kp) const {
   // full warps of consumers and at most 8 slots (barrier words in the 256-byte header)
   kp.producer = opt_.RingProducer != 0 && opt_.RingDrain != 0 && opt_.RingStagger == 0 && kp.stages <= 8 &&
                 (kp.TI * kp.TJ) % 32 == 0;
+  kp.persistent = opt_.RingPersistent != 0 && !kp.producer && opt_.RingDrain != 0 && opt_.RingStagger == 0;
   if((kp.TI * kp.ftBytes) % 16 != 0 || kp.TI > 256 || kp.TJ > 256 || kp.ringKB > 256)
     return false;
   return true;
@@ -1643,8 +1647,10 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
     os_ << ",\n    const int stagger_cycles, const int stagger_phases, const int stagger_blocks";
   os_ << ") {\n";
   os_ << "  const int tid = threadIdx.x;\n";
-  os_ << "  const int i0 = blockIdx.x * " << kp.TI << ";\n";
-  os_ << "  const int j0 = blockIdx.y * " << kp.tileJ() << " + jofs; // rows [jofs, ny) of the domain\n";
+  if(!kp.persistent) {
+    os_ << "  const int i0 = blockIdx.x * " << kp.TI << ";\n";
+    os_ << "  const int j0 = blockIdx.y * " << kp.tileJ() << " + jofs; // rows [jofs, ny) of the domain\n";
+  }
   os_ << "  const int kmin = 0, kmax = nz - 1;\n";
   os_ << "  (void)kmin; (void)kmax; (void)kchunk;\n";
 
@@ -1692,6 +1698,59 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
     os_ << "  unsigned tma_it = 0; // k iterations consumed so far: stage = it % " << kp.stages
         << ", parity = (it / " << kp.stages << ") & 1\n";
   }
+  // ---- persistent blocks: which streamed range opens a column set, which one closes it -----------------
+  const MultiStage* pfMs = nullptr;   // first streamed range of a set (only if it belongs to the first sweep:
+  KRange pfPart{};                    // what a later sweep streams may have been written by an earlier one)
+  const MultiStage* lastMs = nullptr; // last streamed range of a set
+  int lastPartIdx = -1;
+  std::set<int> pfFields;
+  if(kp.persistent) {
+    for(auto const* m : kp.ms) {
+      auto depths = ringDepths(*m);
+      auto ps = analysis::partition(*m);
+      for(size_t q = 0; q < ps.size(); ++q) {
+        auto f = streamedFields(kp, *m, ps[q], depths);
+        if(f.empty())
+          continue;
+        if(!lastMs && m == kp.ms.front())
+          pfMs = m, pfPart = ps[q], pfFields = f;
+        lastMs = m, lastPartIdx = (int)q;
+      }
+    }
+    os_ << "  const int nbx = (nx + " << kp.TI - 1 << ") / " << kp.TI << ";\n";
+    os_ << "  const int nsets = nbx * ((ny - jofs + " << kp.tileJ() - 1 << ") / " << kp.tileJ() << ");\n";
+    if(pfMs) {
+      os_ << "  // the first streamed range of a set: its ring prologue is requested ahead, while the last streamed\n"
+          << "  // range of the block's previous set drains\n";
+      os_ << "  int pf_kb = " << analysis::boundExpr(pfPart.lo) << ", pf_ke = " << analysis::boundExpr(pfPart.hi) << ";\n";
+      os_ << "  pf_kb = pf_kb < 0 ? 0 : pf_kb; pf_ke = pf_ke > kmax ? kmax : pf_ke;\n";
+      os_ << "  const int pf_nch = pf_ke >= pf_kb ? (pf_ke - pf_kb + " << kp.ringKB << ") / " << kp.ringKB << " : 0;\n";
+    }
+    os_ << "  for(int set = blockIdx.x; set < nsets; set += (int)gridDim.x) { // one column set per iteration\n";
+    os_ << "  const int i0 = (set % nbx) * " << kp.TI << ";\n";
+    os_ << "  const int j0 = (set / nbx) * " << kp.tileJ() << " + jofs; // rows [jofs, ny) of the domain\n";
+    os_ << "  const int set_n = set + (int)gridDim.x; // the set this block runs next\n";
+    os_ << "  const bool has_next = set_n < nsets;\n";
+    os_ << "  const int i0n = (set_n % nbx) * " << kp.TI << ", j0n = (set_n / nbx) * " << kp.tileJ() << " + jofs;\n";
+    os_ << "  (void)has_next; (void)i0n; (void)j0n;\n";
+  }
+  // request of chunk `c` of the NEXT set's first streamed range; `seq` = its position in the ring's sequence
+  auto emitNextSetIssue = [&](const std::string& pad, const std::string& c, const std::string& seq) {
+    const int KB = kp.ringKB, S = kp.stages, NT = kp.NT();
+    const bool bw = pfMs->loopOrder == LoopOrder::Backward;
+    os_ << pad << "{ // next set, chunk " << c << "\n";
+    os_ << pad << "  const unsigned ts = (" << seq << ") % " << S << ";\n";
+    os_ << pad << "  const int k0 = " << (bw ? "pf_ke - (" + c + ") * " + std::to_string(KB) + " - " + std::to_string(KB - 1)
+                                            : "pf_kb + (" + c + ") * " + std::to_string(KB)) << ";\n";
+    os_ << pad << "  ::dawn_b200::tma::expect_bytes(&tma_full[ts], " << pfFields.size() * (size_t)KB * NT * kp.ftBytes << "u);\n";
+    int fi = 0;
+    for(int f : pfFields) {
+      os_ << pad << "  ::dawn_b200::tma::load_3d(tma_ring + ts * " << ringSlotElems << " + " << fi * KB * NT << ", &tm_"
+          << fname(f) << ", i0n, j0n, k0, &tma_full[ts]);\n";
+      ++fi;
+    }
+    os_ << pad << "}\n";
+  };
   auto emitTmaIssue = [&](const std::string& pad, const std::string& kExpr,
                           const std::string& stageExpr) {
     os_ << pad << "{\n";
@@ -1880,12 +1939,15 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
       prod << "      tma_it += (unsigned)nch;\n";
       prod << "      }\n";
     };
-    auto emitRingPrologue = [&](const std::set<int>& fields) {
+    auto emitRingPrologue = [&](const std::set<int>& fields, bool openingRange = false) {
       const int ahead = opt_.RingDrain != 0 ? kp.stages : kp.stages - 1;
       os_ << "      const int nk_loc = ke - kb + 1;\n";
       os_ << "      const int nch = nk_loc > 0 ? (nk_loc + " << kp.ringKB - 1 << ") / " << kp.ringKB
           << " : 0;\n";
-      os_ << "      if(tid == 0) {\n";
+      if(openingRange) // persistent block: later sets had this requested by the set before them
+        os_ << "      if(tid == 0 && set == (int)blockIdx.x) {\n";
+      else
+        os_ << "      if(tid == 0) {\n";
       os_ << "        for(int c = 0; c < " << ahead << " && c < nch; ++c)\n";
       emitRingIssue(fields, "          ", "c");
       os_ << "      }\n";
@@ -1907,7 +1969,7 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         os_ << "    { // TMA prologue of k range [" << analysis::boundExpr(parts[earlyPart].lo) << ", "
             << analysis::boundExpr(parts[earlyPart].hi) << "], ahead of the ranges before it\n";
         emitRangeBounds(parts[earlyPart]);
-        emitRingPrologue(streamedFields(kp, *ms, parts[earlyPart], msDepths));
+        emitRingPrologue(streamedFields(kp, *ms, parts[earlyPart], msDepths), kp.persistent && pfMs == ms);
         os_ << "    }\n";
       }
     }
@@ -2079,8 +2141,9 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
           os_ << "      const int nk_loc = ke - kb + 1; // prologue already issued at the top of the sweep\n";
           os_ << "      const int nch = nk_loc > 0 ? (nk_loc + " << KB - 1 << ") / " << KB << " : 0;\n";
         } else {
-          emitRingPrologue(be.prefetched);
+          emitRingPrologue(be.prefetched, kp.persistent && pfMs == ms && part.lo == pfPart.lo && part.hi == pfPart.hi);
         }
+        const bool closingRange = kp.persistent && pfMs && ms == lastMs && partIdx == lastPartIdx;
         os_ << "      for(int ch = 0; ch < nch; ++ch) {\n";
         if(!drain) {
           os_ << "        if(tid == 0 && ch + " << S - 1 << " < nch)\n";
@@ -2103,8 +2166,18 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
             os_ << "        if((tid & 31) == 0)\n          ::dawn_b200::tma::arrive(&tma_empty[tcur]);\n";
           } else {
             os_ << "        __syncthreads(); // slot drained by every thread: refill it right away\n";
-            os_ << "        if(tid == 0 && ch + " << S << " < nch)\n";
-            issue("          ", "ch + " + std::to_string(S));
+            if(closingRange) {
+              // the last streamed range of the set: a slot it does not need again takes a chunk of the next set
+              os_ << "        if(tid == 0) {\n";
+              os_ << "          if(ch + " << S << " < nch)\n";
+              issue("            ", "ch + " + std::to_string(S));
+              os_ << "          else if(has_next && ch + " << S << " - nch < pf_nch)\n";
+              emitNextSetIssue("            ", "ch + " + std::to_string(S) + " - nch", "tma_it + ch + " + std::to_string(S));
+              os_ << "        }\n";
+            } else {
+              os_ << "        if(tid == 0 && ch + " << S << " < nch)\n";
+              issue("          ", "ch + " + std::to_string(S));
+            }
           }
         }
         os_ << "#pragma unroll\n";
@@ -2377,6 +2450,11 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
         if(!opt_.RingDrain)
           os_ << "        __syncthreads(); // slot consumed by every thread before it is refilled\n";
         os_ << "      }\n"; // chunk loop
+        if(kp.persistent && pfMs && ms == lastMs && partIdx == lastPartIdx) {
+          os_ << "      if(tid == 0 && has_next) // slots this range never touched (it has fewer chunks than the ring has slots)\n";
+          os_ << "        for(int c = 0; c < " << kp.stages << " - nch && c < pf_nch; ++c)\n";
+          emitNextSetIssue("          ", "c", "tma_it + nch + c");
+        }
         os_ << "      tma_it += (unsigned)nch;\n";
       }
       if(kp.tma) {
@@ -2412,6 +2490,8 @@ void CartesianEmitter::emitKernel(const Stencil& st, const KernelPlan& kp) {
     for(auto const& l : be.invariantLoads)
       os_ << "  " << be.finalize(l) << "\n";
     os_ << body;
+    if(kp.persistent)
+      os_ << "  } // next column set\n";
   }
   os_ << "}\n\n";
 }
@@ -2612,6 +2692,22 @@ void CartesianEmitter::emitWrapperClass(const std::vector<std::vector<KernelPlan
         os_ << pad << "  cudaFuncSetAttribute(reinterpret_cast<const void*>(&" << kp.name
             << "), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);\n";
         os_ << pad << "  smem_set |= 1ull << (smem_dev & 63);\n" << pad << "}\n";
+      }
+      if(kp.persistent) {
+        // one block per resident slot of the device (or per column set, if there are fewer)
+        os_ << pad << "static int pers_slots_dev[64] = {};\n";
+        os_ << pad << "int pers_dev = 0;\n";
+        os_ << pad << "cudaGetDevice(&pers_dev);\n";
+        os_ << pad << "int& pers_slots = pers_slots_dev[pers_dev & 63];\n";
+        os_ << pad << "if(!pers_slots) {\n";
+        os_ << pad << "  int sms = 0, occ = 0;\n";
+        os_ << pad << "  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pers_dev);\n";
+        os_ << pad << "  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, " << kp.name << ", " << kp.NT() << ", " << smem
+            << ");\n";
+        os_ << pad << "  pers_slots = (sms > 0 ? sms : 1) * (occ > 0 ? occ : 1);\n";
+        os_ << pad << "}\n";
+        os_ << pad << "const long pers_sets = (long)grid.x * grid.y;\n";
+        os_ << pad << "grid = dim3((unsigned)(pers_sets < pers_slots ? pers_sets : pers_slots), 1, 1);\n";
       }
       const bool stagger = kp.colring && opt_.RingStagger != 0;
       if(stagger) {

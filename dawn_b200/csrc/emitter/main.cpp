@@ -66,7 +66,7 @@ int main(int argc, char** argv) {
             intOpt(a, "ico-full-blocks", opts.IcoFullBlocks) ||
             intOpt(a, "single-precision", opts.SinglePrecision) ||
             intOpt(a, "ring-producer", opts.RingProducer) ||
-            intOpt(a, "pair-stores", opts.PairStores) || intOpt(a, "ico-cache-hints", opts.IcoCacheHints) || intOpt(a, "ico-stage", opts.IcoStage) || intOpt(a, "ico-hoist", opts.IcoHoist) || intOpt(a, "ico-chain", opts.IcoChain) || intOpt(a, "ico-chain-l1", opts.IcoChainL1) || intOpt(a, "ico-chain-lag", opts.IcoChainLag) ||
+            intOpt(a, "pair-stores", opts.PairStores) || intOpt(a, "ico-cache-hints", opts.IcoCacheHints) || intOpt(a, "ico-stage", opts.IcoStage) || intOpt(a, "ico-hoist", opts.IcoHoist) || intOpt(a, "persistent-ring", opts.RingPersistent) || intOpt(a, "ico-chain", opts.IcoChain) || intOpt(a, "ico-chain-l1", opts.IcoChainL1) || intOpt(a, "ico-chain-lag", opts.IcoChainLag) ||
             intOpt(a, "max-blocks-sm", opts.MaxBlocksPerSM) ||
             intOpt(a, "max-halo-points", opts.MaxHaloSize)) {
     } else if(a.compare(0, 16, "--run-with-sync=") == 0)

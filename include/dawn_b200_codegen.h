@@ -122,6 +122,11 @@ typedef struct dawn_b200_options {
                              blocks a double-precision division ends.  Measured on B200: 21.3 ms against 21.2 ms,
                              no gain at 64 resident warps (the 32-register budget spills what the hoisting holds);
                              off */
+  int persistent_ring;    /* default 0; 1: column-ring kernels run as persistent blocks (one per resident slot of the device)
+                             that loop over the column sets; while a block finishes the last streamed range of a set
+                             it already requests the first ring slots of its NEXT set into the slots that range
+                             frees, so the bulk-copy latency at the start of a set (~1/4 of a lone block's life in
+                             the Thomas solver) is hidden behind the previous set's backward sweep */
 } dawn_b200_options;
 
 /* Fills `opts` with the defaults above. */

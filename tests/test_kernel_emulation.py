@@ -341,6 +341,45 @@ def test_planner_variants_of_the_headline_kernels_on_the_cpu(name, opts):
         _cartesian_case(name, code, info, size, 600)
 
 
+# ---- persistent_ring: a block loops over column sets and requests the first ring slots of its next set while the
+# last streamed range of the current one drains.  The emulated device has EMU_SMS resident slots: 1 and 3 make every
+# block run several sets (the hand-over between sets, phases continuing across them), 1000 gives one set per block.
+@pytest.mark.parametrize("slots", ["1", "3", "1000"])
+@pytest.mark.parametrize("name,opts", [("tridiagonal_solve", dict()), ("tridiagonal_solve", dict(ring_levels=8, tma_stages=3)),
+                                       ("tridiagonal_solve", dict(ring_early=0)), ("kcache_fill_backward", dict()),
+                                       ("intervals03", dict(ring_levels=4, tma_stages=4))],
+                         ids=lambda v: v if isinstance(v, str) else ",".join("%s=%s" % kv for kv in v.items()) or "default")
+def test_persistent_column_blocks_on_the_cpu(name, opts, slots, monkeypatch):
+    monkeypatch.setenv("EMU_SMS", slots)
+    code = codegen.compile_iir(open(iir_path(name)).read(), backend="b200", persistent_ring=1, **opts)
+    assert "next column set" in code and "next set, chunk" in code
+    info = json.loads(re.search(r'return "(\{.*\})";', code).group(1).encode().decode("unicode_escape"))
+    for size in ((70, 9, 12), (130, 5, 37)):
+        _cartesian_case(name, code, info, size, 650)
+
+
+@pytest.mark.parametrize("mutation", ["next set column", "next set sequence"])
+def test_the_emulation_notices_a_broken_hand_over_between_sets(mutation, monkeypatch):
+    monkeypatch.setenv("EMU_SMS", "2")
+    name = "tridiagonal_solve"
+    code = codegen.compile_iir(open(iir_path(name)).read(), backend="b200", persistent_ring=1)
+    info = json.loads(re.search(r'return "(\{.*\})";', code).group(1).encode().decode("unicode_escape"))
+    bad = {"next set column": code.replace("&tm_a, i0n, j0n, k0", "&tm_a, i0, j0n, k0"),
+           "next set sequence": code.replace("const int k0 = pf_kb + (ch + 2 - nch) * 16;", "const int k0 = pf_kb + (ch + 1 - nch) * 16;")}[mutation]
+    assert bad != code
+    _cartesian_case(name, code, info, (130, 5, 37), 660)
+    with pytest.raises(AssertionError):
+        _cartesian_case(name, bad, info, (130, 5, 37), 660)
+
+
+def test_persistent_blocks_are_off_by_default_and_leave_other_kernels_alone():
+    plain = codegen.compile_iir(open(iir_path("tridiagonal_solve")).read(), backend="b200")
+    assert "next column set" not in plain and "has_next" not in plain
+    # tile kernels (horizontal dependencies) have no column ring: the option changes nothing there
+    hd = open(iir_path("hori_diff_type2_stencil")).read()
+    assert codegen.compile_iir(hd, backend="b200", persistent_ring=1) == codegen.compile_iir(hd, backend="b200")
+
+
 @pytest.mark.parametrize("mutation", ["prefetch level", "box row", "hdmask slot offset"])
 def test_the_emulation_notices_a_broken_tma_pipeline(mutation):
     # the harness must have teeth: a wrong level in the refill, a shifted box or a wrong slot offset in the
