@@ -126,7 +126,12 @@ typedef struct dawn_b200_options {
                              that loop over the column sets; while a block finishes the last streamed range of a set
                              it already requests the first ring slots of its NEXT set into the slots that range
                              frees, so the bulk-copy latency at the start of a set (~1/4 of a lone block's life in
-                             the Thomas solver) is hidden behind the previous set's backward sweep */
+                             the Thomas solver) is hidden behind the previous set's backward sweep.  Measured on B200
+                             (tridiagonal_solve, 444 persistent blocks, bit-identical): 512^2 x 80 0.198 ms / 77.7 %
+                             against 0.183 ms / 84.2 %, 1024^2 x 80 0.758 ms / 81 % against 0.689 ms / 89 % - the
+                             hardware's own dispatch of independent blocks balances better than a static
+                             round-robin over sets, and the lead of two short backward chunks does not cover the
+                             latency it was meant to hide; off */
 } dawn_b200_options;
 
 /* Fills `opts` with the defaults above. */
